@@ -1,0 +1,261 @@
+"""Generate the golden fixtures in this directory by running the UNMODIFIED
+reference (/root/reference) on CPU.  Run in the build container only:
+
+    python tests/golden/make_golden.py
+
+The reference has no golden vectors of its own, so these files
+are what pins the oracle (oracle/ganecdotes_oracle.py) to the reference, and -
+through the oracle and directly - the CUDA path.  Every random draw the
+reference makes on the path is recorded so it can be replayed.
+"""
+import os
+import sys
+import tempfile
+import types
+
+import numpy as np
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(os.path.dirname(HERE))
+sys.path.insert(0, HERE)
+sys.path.insert(0, ROOT)
+
+import _reference_loader as L  # noqa: E402
+from oracle import ganecdotes_oracle as O  # noqa: E402
+
+ref = L.load_reference()
+torch.set_num_threads(8)
+
+
+def save(name, **arrs):
+    out = {}
+    for k, v in arrs.items():
+        if isinstance(v, torch.Tensor):
+            v = v.detach().cpu().numpy()
+        out[k] = np.asarray(v)
+    np.savez_compressed(os.path.join(HERE, name + ".npz"), **out)
+    sz = os.path.getsize(os.path.join(HERE, name + ".npz"))
+    print(f"wrote {name}.npz  {sz / 1024:.1f} KiB")
+
+
+# ---------------------------------------------------------------------------------------
+# G1: custom ops (models/stylegan2/model.py:32-102)
+# ---------------------------------------------------------------------------------------
+def golden_ops():
+    g = torch.Generator().manual_seed(1)
+    out = {}
+    cases = [
+        # name, shape, taps, gain, up, down, pad
+        ("blur_up", (2, 5, 9, 9), [1, 3, 3, 1], 4.0, 1, 1, (1, 1)),          # Blur after transposed conv
+        ("rgb_up2", (2, 3, 8, 8), [1, 3, 3, 1], 4.0, 2, 1, (2, 1)),          # Upsample of the RGB skip
+        ("down2", (1, 4, 12, 10), [1, 3, 3, 1], 1.0, 1, 2, (1, 1)),          # Downsample
+        ("k3", (1, 2, 7, 6), [1, 2, 1], 1.0, 1, 1, (1, 1)),
+        ("crop", (1, 2, 10, 10), [1, 3, 3, 1], 1.0, 1, 1, (-1, 2)),          # negative pad crops
+        ("up2down2", (1, 3, 6, 7), [1, 3, 3, 1], 1.0, 2, 2, (2, 1)),
+        ("asym", (1, 2, 5, 8), [1, 4, 6, 4, 1], 1.0, (2, 1), (1, 2), (2, 1, 0, 3)),  # generic path
+    ]
+    for name, shape, taps, gain, up, down, pad in cases:
+        x = torch.randn(*shape, generator=g)
+        k = ref.model.make_kernel(taps) * gain
+        if name == "asym":
+            k = k + 0.01 * torch.randn(k.shape, generator=g)   # non-symmetric: flip matters
+        y = ref.model.upfirdn2d(x, k, up=up, down=down, pad=pad)
+        out[f"{name}_x"] = x
+        out[f"{name}_k"] = k
+        out[f"{name}_y"] = y
+        out[f"{name}_args"] = np.array(
+            list(up if isinstance(up, tuple) else (up, up)) +
+            list(down if isinstance(down, tuple) else (down, down)) +
+            list(pad if len(pad) == 4 else (pad[0], pad[1], pad[0], pad[1])), dtype=np.int64)
+    x = torch.randn(2, 6, 5, 5, generator=g)
+    b = torch.randn(6, generator=g)
+    out["flr_x"], out["flr_b"] = x, b
+    out["flr_y"] = ref.model.fused_leaky_relu(x, b)
+    out["flr_y_nobias"] = ref.model.fused_leaky_relu(x, None)
+    x2 = torch.randn(3, 6, generator=g)
+    out["flr2_x"] = x2
+    out["flr2_y"] = ref.model.fused_leaky_relu(x2, b)
+    save("ops", **out)
+
+
+# ---------------------------------------------------------------------------------------
+# G2: Generator forward (models/stylegan2/model.py:565-648)
+# ---------------------------------------------------------------------------------------
+GEN_SIZE, GEN_STYLE, GEN_MLP, GEN_SEED = 16, 64, 2, 7
+
+
+def build_reference_generator():
+    sd = O.init_generator_state(GEN_SIZE, GEN_STYLE, GEN_MLP, GEN_SEED)
+    gen = ref.model.Generator(GEN_SIZE, GEN_STYLE, GEN_MLP)
+    missing, unexpected = gen.load_state_dict(sd, strict=True), None
+    gen.eval()
+    return gen, sd
+
+
+def golden_generator():
+    gen, sd = build_reference_generator()
+    g = torch.Generator().manual_seed(3)
+    z = torch.randn(2, GEN_STYLE, generator=g)
+    zm = torch.randn(64, GEN_STYLE, generator=g)
+    with torch.no_grad():
+        w = gen.style(z)
+        mean_latent = gen.style(zm).mean(0, keepdim=True)
+        img, feats = gen([z], truncation=0.7, truncation_latent=mean_latent,
+                         input_is_latent=False, randomize_noise=False)
+        img2, latent = gen([w], return_latents=True, truncation=0.7,
+                           truncation_latent=mean_latent, input_is_latent=True,
+                           randomize_noise=False)
+        # W+ input with per-sample noise
+        wplus = torch.randn(2, gen.n_latent, GEN_STYLE, generator=g) * 0.5
+        noises = [torch.randn(2, 1, 2 ** ((i + 5) // 2), 2 ** ((i + 5) // 2), generator=g)
+                  for i in range(gen.num_layers)]
+        img3, feats3 = gen([wplus], input_is_latent=True, noise=noises)
+    out = dict(z=z, zm=zm, w=w, mean_latent=mean_latent, img=img, img_latent=img2, latent=latent,
+               wplus=wplus, img3=img3)
+    for i, f in enumerate(feats):
+        out[f"feat{i}"] = f[:, ::16]              # every 16th channel
+        out[f"feat{i}_sum"] = f.double().sum(dim=(2, 3))
+    for i, f in enumerate(feats3):
+        out[f"feat3_{i}"] = f[:, 5::32]
+    for i, n in enumerate(noises):
+        out[f"noise3_{i}"] = n
+    save("generator", **out)
+
+
+# ---------------------------------------------------------------------------------------
+# G3: SwAV pretrain steps + predict_swav_codes, RNG draws recorded
+# ---------------------------------------------------------------------------------------
+class Recorder:
+    def __init__(self):
+        self.log = []
+
+    def wrap(self, name, fn):
+        def inner(*a, **k):
+            out = fn(*a, **k)
+            self.log.append((name, out))
+            return out
+        return inner
+
+
+def golden_swav():
+    gen, sd = build_reference_generator()
+    swav = ref.swav
+    hlen = 512 + 1024 + 1024
+    nclasses, nproto, patch, npatch, nepochs = 64, 48, 100, 2, 2
+    cfg = dict(
+        perturb_args=dict(truncation=0.7, n_layers=3, n_samples=1, layer_no=None,
+                          perturb_std=[1.0, 0.5, 1.0]),
+        swav_args=dict(num_epochs=nepochs, num_samples=1, num_patches=npatch, sampling_method='random',
+                       patch_size=patch, hf_interp='nearest', warmup_epochs=nepochs, start_warmup=0.01,
+                       use_scheduler=False, base_lr=0.01, final_lr=0.0001, trust_coeff=0.01,
+                       freeze_prototype_niters=313, train_args=dict(lr=0.01, momentum=0.9),
+                       projn_nw='linear', temperature=0.02, nprototypes=nproto, nclasses=nclasses,
+                       hlen=hlen, add_local_loss=False, plot_test_images=False, epoch_print_freq=1,
+                       max_masks=4),
+        sinkhorn_args=dict(source_pdf='uniform', niters=10, eps=0.02),
+        train=True, layer_hf_dim=[512, 1024, 1024])
+    model_config = types.SimpleNamespace(num_latents_for_mean=64, truncation=0.7,
+                                         latent_dim=GEN_STYLE, image_size=GEN_SIZE)
+    rec = Recorder()
+    losses = []
+    tb = types.SimpleNamespace(add_scalar=lambda name, val, step: losses.append(float(val)))
+    logger = types.SimpleNamespace(info=lambda *a, **k: None)
+
+    torch.manual_seed(11)
+    np.random.seed(11)
+    # --- record every draw on the path -------------------------------------------------
+    orig = dict(randn=torch.randn, randn_like=torch.randn_like, randperm=torch.randperm,
+                choice=np.random.choice, rand=torch.rand)
+    torch.randn = rec.wrap("randn", orig["randn"])
+    torch.randn_like = rec.wrap("randn_like", orig["randn_like"])
+    torch.randperm = rec.wrap("randperm", orig["randperm"])
+    torch.rand = rec.wrap("rand", orig["rand"])
+    np.random.choice = rec.wrap("choice", orig["choice"])
+    from torchvision import transforms as T
+    orig_gp = T.RandomRotation.get_params
+    T.RandomRotation.get_params = staticmethod(rec.wrap("angle", orig_gp))
+    init = {}
+    orig_sgd = torch.optim.SGD
+
+    def sgd_spy(params, **kw):
+        params = list(params)
+        init["params"] = [p.detach().clone() for p in params]
+        return orig_sgd(params, **kw)
+    torch.optim.SGD = sgd_spy
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            obj = swav.SwAVClustering(gen, model_config, logger=logger, out_dir=td, device='cpu',
+                                      tb=tb, **cfg)
+            mean_latent = obj.mean_latent.clone()
+            n_ctor = len(rec.log)
+            obj.pretrain(None, num_test_samples=0)
+            n_train = len(rec.log)
+            w_proj = obj.projection[0].weight.detach().clone()
+            w_proto = obj.prototype.weight.detach().clone()
+            b_proto = obj.prototype.bias.detach().clone()
+            # inference
+            wlat = gen.style(orig["randn"](1, GEN_STYLE, generator=torch.Generator().manual_seed(5)))
+            preds, labels = obj.predict_swav_codes(wlat.detach())
+            # direct calls of sinkhorn / loss on small random scores
+            gg = torch.Generator().manual_seed(9)
+            sc_s = 0.1 * orig["randn"](40, 24, generator=gg)
+            sc_t = 0.1 * orig["randn"](40, 24, generator=gg)
+            obj.eps = 0.005
+            q_s = obj.sinkhorn_knopp(sc_s.clone(), None)
+            q_t = obj.sinkhorn_knopp(sc_t.clone(), None)
+            loss_direct = obj.calculate_swapped_prediction_loss(sc_s / 0.01, sc_t / 0.01, q_s, q_t)
+    finally:
+        torch.randn, torch.randn_like, torch.randperm = orig["randn"], orig["randn_like"], orig["randperm"]
+        torch.rand = orig["rand"]
+        np.random.choice = orig["choice"]
+        T.RandomRotation.get_params = orig_gp
+        torch.optim.SGD = orig_sgd
+
+    # --- unpack the recorded draws per step (order: SURVEY §8 quirk 3) ---------------------
+    train_log = rec.log[n_ctor:n_train]
+    out = dict(mean_latent=mean_latent, mean_latent_z=rec.log[0][1],
+               init_w_proj=init["params"][0], init_w_proto=init["params"][1],
+               init_b_proto=init["params"][2],
+               final_w_proj=w_proj, final_w_proto=w_proto, final_b_proto=b_proto,
+               losses=np.array(losses), pred_w=wlat, preds=preds[:, ::4], labels=labels,
+               sk_scores_s=sc_s, sk_scores_t=sc_t, sk_q_s=q_s, sk_q_t=q_t, sk_loss=loss_direct,
+               cfg=np.array([hlen, nclasses, nproto, patch, npatch, nepochs, 3], dtype=np.int64),
+               perturb_std=np.array([1.0, 0.5, 1.0]))
+    it = iter(train_log)
+    for e in range(nepochs):
+        name, z = next(it)
+        assert name == "randn" and tuple(z.shape) == (1, GEN_STYLE), (name, z.shape)
+        out[f"s{e}_z"] = z
+        for v in "st":
+            name, layer = next(it)
+            assert name == "choice", name
+            out[f"s{e}_{v}_layer"] = np.int64(layer)
+            pz = []
+            for _ in range(6):
+                name, d = next(it)
+                assert name == "randn_like", name
+                pz.append(d)
+            out[f"s{e}_{v}_pert_z"] = torch.cat(pz, 0)
+        for v in "st":
+            name, ang = next(it)
+            assert name == "angle", name
+            out[f"s{e}_{v}_angle"] = np.float64(ang)
+            name, r = next(it)
+            assert name == "rand", name
+            out[f"s{e}_{v}_flip"] = np.bool_(bool(r < 0.5))
+            out[f"s{e}_{v}_flip_u"] = r
+        for p in range(npatch):
+            name, perm = next(it)
+            assert name == "randperm", name
+            out[f"s{e}_perm{p}"] = perm
+    rest = list(it)
+    assert not rest, [n for n, _ in rest]
+    save("swav", **out)
+    print("losses", losses)
+
+
+if __name__ == "__main__":
+    golden_ops()
+    golden_generator()
+    golden_swav()
