@@ -1,0 +1,537 @@
+"""ctypes binding of the C ABI (include/ganecdotes_b200.h) + thin torch-tensor wrappers.
+
+There is no CPU fallback: if the shared library is missing, or the device is not a
+CUDA sm_100 device, every op raises RuntimeError.
+"""
+import ctypes as C
+import os
+import threading
+
+import torch
+
+from . import build as _build
+
+_LIB = None
+_LOCK = threading.Lock()
+GX_MAX_LEVELS = 16
+
+# number of CUDA kernels launched through this module (claimed in bench.py's gpu_launches)
+launch_count = 0
+
+
+class GxError(RuntimeError):
+    pass
+
+
+class gx_conv_desc(C.Structure):
+    _fields_ = [
+        ("x_hi", C.c_void_p), ("x_lo", C.c_void_p), ("w_hi", C.c_void_p), ("w_lo", C.c_void_p),
+        ("batch", C.c_int), ("h", C.c_int), ("w", C.c_int), ("cin", C.c_int), ("cout", C.c_int),
+        ("upsample", C.c_int), ("passes", C.c_int),
+        ("demod", C.c_void_p), ("noise", C.c_void_p), ("noise_batch_stride", C.c_longlong),
+        ("noise_strength", C.c_void_p), ("bias", C.c_void_p), ("act", C.c_int),
+        ("out", C.c_void_p), ("next_style", C.c_void_p), ("next_hi", C.c_void_p), ("next_lo", C.c_void_p),
+        ("block_n", C.c_int), ("stages", C.c_int),
+    ]
+
+
+class gx_gemm_desc(C.Structure):
+    _fields_ = [
+        ("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("b_hi", C.c_void_p), ("b_lo", C.c_void_p),
+        ("lda", C.c_longlong), ("ldb", C.c_longlong), ("a_mn_major", C.c_int), ("b_mn_major", C.c_int),
+        ("m", C.c_int), ("n", C.c_int), ("k", C.c_int), ("passes", C.c_int),
+        ("c", C.c_void_p), ("ldc", C.c_longlong), ("bias", C.c_void_p), ("split_k", C.c_int),
+        ("accumulate", C.c_int), ("block_n", C.c_int), ("stages", C.c_int),
+    ]
+
+
+class gx_gather_desc(C.Structure):
+    _fields_ = [
+        ("nlevels", C.c_int),
+        ("feat", C.c_void_p * GX_MAX_LEVELS),
+        ("h", C.c_int * GX_MAX_LEVELS), ("w", C.c_int * GX_MAX_LEVELS), ("c", C.c_int * GX_MAX_LEVELS),
+        ("out_h", C.c_int), ("out_w", C.c_int), ("hlen", C.c_int),
+        ("row_img", C.c_void_p), ("row_src", C.c_void_p), ("nrows", C.c_longlong),
+        ("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("a_f32", C.c_void_p), ("ld", C.c_longlong),
+    ]
+
+
+_I, _LL, _F, _P = C.c_int, C.c_longlong, C.c_float, C.c_void_p
+
+_SIGNATURES = {
+    "gx_version": ([], _I),
+    "gx_last_cuda_error": ([], _I),
+    "gx_error_string": ([_I], C.c_char_p),
+    "gx_device_ok": ([], _I),
+    "gx_upfirdn2d": ([_P, _P, _P] + [_I] * 14 + [_P], _I),
+    "gx_fused_bias_act": ([_P, _P, _P, _P, _LL, _I, _I, _I, _I, _F, _F, _P], _I),
+    "gx_pixel_norm": ([_P, _P, _I, _I, _P], _I),
+    "gx_equal_linear": ([_P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P], _I),
+    "gx_truncate": ([_P, _P, _P, _LL, _I, _F, _P], _I),
+    "gx_modconv_prepare": ([_P, _F, _P, _P, _P, _I, _I, _I, _P], _I),
+    "gx_modconv_demod": ([_P, _P, _P, _I, _I, _I, _P], _I),
+    "gx_modulate_split": ([_P, _LL, _P, _P, _P, _I, _LL, _I, _P], _I),
+    "gx_modconv": ([C.POINTER(gx_conv_desc), _P], _I),
+    "gx_blur_noise_bias_act": ([_P, _P, _I, _I, _I, _I, _P, _LL, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
+    "gx_torgb": ([_P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _P], _I),
+    "gx_gemm": ([C.POINTER(gx_gemm_desc), _P], _I),
+    "gx_gemm_check": ([C.POINTER(gx_gemm_desc), _P], _I),
+    "gx_split_planes": ([_P, _LL, _P, _P, _LL, _LL, _I, _P], _I),
+    "gx_gather_rows": ([C.POINTER(gx_gather_desc), _P], _I),
+    "gx_l2norm_split": ([_P, _P, _P, _P, _LL, _I, _P], _I),
+    "gx_l2norm_bwd_split": ([_P, _P, _P, _P, _P, _P, _LL, _I, _P], _I),
+    "gx_normalize_rows": ([_P, _LL, _I, _P], _I),
+    "gx_sinkhorn_max_parts": ([], _I),
+    "gx_sinkhorn_pass": ([_P, _LL, _I, _LL, _F, _I, _P, _P, _P, _LL, _P, C.POINTER(_I), _P], _I),
+    "gx_sinkhorn_reduce": ([_P, _I, _I, _P, _P], _I),
+    "gx_sinkhorn_log_a": ([_P, _P, _I, _P, _P], _I),
+    "gx_sinkhorn_q": ([_P, _LL, _I, _LL, _F, _P, _P, _P], _I),
+    "gx_loss_max_parts": ([], _I),
+    "gx_swav_loss": ([_P, _P, _LL, _I, _LL, _F, _F, _P, _P, _F, _P, _P, C.POINTER(_I), _P, _P, _P, _P, _LL, _P, _P,
+                      _P], _I),
+    "gx_larc_sgd": ([_P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _P, _P], _I),
+    "gx_argmax_rows": ([_P, _LL, _I, _LL, _P, _P], _I),
+    "gx_kmeans_assign": ([_P, _LL, _I, _LL, _P, _I, _P, _P], _I),
+}
+
+EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())
+
+
+def lib_path() -> str:
+    return _build.LIB_PATH
+
+
+def load(require_device: bool = True):
+    """Load (building if stale and nvcc is available) the CUDA library."""
+    global _LIB
+    with _LOCK:
+        if _LIB is None:
+            path = _build.LIB_PATH
+            if not os.path.exists(path):
+                try:
+                    _build.build()
+                except Exception as e:  # pragma: no cover
+                    raise GxError(f"ganecdotes_b200: CUDA library missing and could not be built: {e}")
+            lib = C.CDLL(path)
+            for name, (argt, rest) in _SIGNATURES.items():
+                fn = getattr(lib, name)
+                fn.argtypes = argt
+                fn.restype = rest
+            _LIB = lib
+    if require_device:
+        if not torch.cuda.is_available():
+            raise GxError("ganecdotes_b200 has no CPU fallback: a CUDA sm_100 (B200) device is required")
+        if not getattr(load, "_dev_ok", False):
+            if _LIB.gx_device_ok() != 1:
+                raise GxError("ganecdotes_b200 kernels are built for sm_100a only; current device is not sm_100")
+            load._dev_ok = True
+    return _LIB
+
+
+def _check(rc: int, what: str):
+    if rc != 0:
+        lib = _LIB
+        msg = lib.gx_error_string(rc).decode()
+        extra = ""
+        if rc == -2:
+            extra = f" (cuda error {lib.gx_last_cuda_error()})"
+        raise GxError(f"{what}: {msg}{extra}")
+
+
+def _ptr(t):
+    return None if t is None else t.data_ptr()
+
+
+def _stream():
+    return torch.cuda.current_stream().cuda_stream
+
+
+def _f32(t, name):
+    if t is None:
+        return None
+    if not t.is_cuda:
+        raise GxError(f"{name} must be a CUDA tensor")
+    if t.dtype != torch.float32:
+        raise GxError(f"{name} must be float32")
+    if not t.is_contiguous():
+        raise GxError(f"{name} must be contiguous")
+    return t
+
+
+def _count(n=1):
+    global launch_count
+    launch_count += n
+
+
+# ----------------------------------------------------------------------------------------
+# op wrappers (raw): callers pass contiguous CUDA tensors of the right dtype
+# ----------------------------------------------------------------------------------------
+
+def upfirdn2d_raw(x4, kernel, up_x, up_y, down_x, down_y, px0, px1, py0, py1):
+    """x4: [major, in_h, in_w, minor] -> [major, out_h, out_w, minor]"""
+    lib = load()
+    _f32(x4, "input"), _f32(kernel, "kernel")
+    major, in_h, in_w, minor = x4.shape
+    kh, kw = kernel.shape
+    out_h = (in_h * up_y + py0 + py1 - kh + down_y) // down_y
+    out_w = (in_w * up_x + px0 + px1 - kw + down_x) // down_x
+    if out_h <= 0 or out_w <= 0:
+        raise GxError("upfirdn2d: empty output")
+    out = torch.empty((major, out_h, out_w, minor), dtype=torch.float32, device=x4.device)
+    if out.numel():
+        _check(lib.gx_upfirdn2d(_ptr(x4), _ptr(kernel), _ptr(out), major, in_h, in_w, minor, kh, kw, up_x, up_y,
+                                down_x, down_y, px0, px1, py0, py1, _stream()), "gx_upfirdn2d")
+        _count()
+    return out
+
+
+def fused_bias_act_raw(x, bias, refer, act, grad, alpha, scale):
+    lib = load()
+    _f32(x, "input")
+    out = torch.empty_like(x)
+    if x.numel() == 0:
+        return out
+    if bias is not None:
+        _f32(bias, "bias")
+        step_b = 1
+        for d in x.shape[2:]:
+            step_b *= d
+        size_b = x.shape[1]
+        if bias.numel() != size_b:
+            raise GxError("fused_bias_act: bias must have input.shape[1] elements")
+    else:
+        step_b = size_b = 1
+    if refer is not None:
+        _f32(refer, "refer")
+    _check(lib.gx_fused_bias_act(_ptr(x), _ptr(bias), _ptr(refer), _ptr(out), x.numel(), step_b, size_b, act, grad,
+                                 float(alpha), float(scale), _stream()), "gx_fused_bias_act")
+    _count()
+    return out
+
+
+def pixel_norm(x):
+    lib = load()
+    _f32(x, "x")
+    y = torch.empty_like(x)
+    _check(lib.gx_pixel_norm(_ptr(x), _ptr(y), x.shape[0], x.shape[1], _stream()), "gx_pixel_norm")
+    _count()
+    return y
+
+
+def equal_linear(x, w, b, w_scale, b_scale, act):
+    lib = load()
+    _f32(x, "x"), _f32(w, "w"), _f32(b, "b")
+    n, in_dim = x.shape
+    out_dim = w.shape[0]
+    y = torch.empty((n, out_dim), dtype=torch.float32, device=x.device)
+    # grid.y limit: chunk rows
+    step = 65535 * 8
+    for r0 in range(0, n, step):
+        xs = x[r0:r0 + step]
+        ys = y[r0:r0 + step]
+        _check(lib.gx_equal_linear(_ptr(xs), _ptr(w), _ptr(b), _ptr(ys), xs.shape[0], in_dim, out_dim,
+                                   float(w_scale), float(b_scale), int(act), _stream()), "gx_equal_linear")
+        _count()
+    return y
+
+
+def truncate(w, mean, psi):
+    lib = load()
+    _f32(w, "w"), _f32(mean, "mean")
+    out = torch.empty_like(w)
+    dim = w.shape[-1]
+    _check(lib.gx_truncate(_ptr(w), _ptr(mean), _ptr(out), w.numel() // dim, dim, float(psi), _stream()),
+           "gx_truncate")
+    _count()
+    return out
+
+
+def modconv_prepare(weight, scale, want_lo=True):
+    """weight [cout,cin,k,k] -> (w_hi, w_lo) [cout, k*k*cin] bf16, wsq [cout,cin]"""
+    lib = load()
+    _f32(weight, "weight")
+    cout, cin, k, _ = weight.shape
+    w_hi = torch.empty((cout, k * k * cin), dtype=torch.bfloat16, device=weight.device)
+    w_lo = torch.empty_like(w_hi) if want_lo else None
+    wsq = torch.empty((cout, cin), dtype=torch.float32, device=weight.device)
+    _check(lib.gx_modconv_prepare(_ptr(weight), float(scale), _ptr(w_hi), _ptr(w_lo), _ptr(wsq), cout, cin, k,
+                                  _stream()), "gx_modconv_prepare")
+    _count()
+    return w_hi, w_lo, wsq
+
+
+def modconv_demod(wsq, s):
+    lib = load()
+    _f32(wsq, "wsq"), _f32(s, "s")
+    cout, cin = wsq.shape
+    b = s.shape[0]
+    d = torch.empty((b, cout), dtype=torch.float32, device=s.device)
+    _check(lib.gx_modconv_demod(_ptr(wsq), _ptr(s), _ptr(d), b, cin, cout, _stream()), "gx_modconv_demod")
+    _count()
+    return d
+
+
+def modulate_split(x_nhwc, s, batch, want_lo=True):
+    """x_nhwc: [B or 1, H, W, C] fp32; s [batch, C] -> hi, lo [batch,H,W,C] bf16"""
+    lib = load()
+    _f32(x_nhwc, "x"), _f32(s, "s")
+    xb, h, w, c = x_nhwc.shape
+    stride = 0 if (xb == 1 and batch > 1) else h * w * c
+    hi = torch.empty((batch, h, w, c), dtype=torch.bfloat16, device=x_nhwc.device)
+    lo = torch.empty_like(hi) if want_lo else None
+    _check(lib.gx_modulate_split(_ptr(x_nhwc), stride, _ptr(s), _ptr(hi), _ptr(lo), batch, h * w, c, _stream()),
+           "gx_modulate_split")
+    _count()
+    return hi, lo
+
+
+def modconv(x_hi, x_lo, w_hi, w_lo, cout, upsample, passes, demod=None, noise=None, noise_strength=None, bias=None,
+            act=0, next_style=None, want_next_lo=True, block_n=0, stages=0):
+    """Implicit-GEMM modulated conv.  x_*: [B,H,W,Cin] bf16.  Returns (out fp32 NHWC, next_hi, next_lo)."""
+    lib = load()
+    b, h, w, cin = x_hi.shape
+    ho, wo = (2 * h + 1, 2 * w + 1) if upsample else (h, w)
+    dev = x_hi.device
+    out = torch.empty((b, ho, wo, cout), dtype=torch.float32, device=dev)
+    next_hi = next_lo = None
+    if next_style is not None:
+        next_hi = torch.empty((b, ho, wo, cout), dtype=torch.bfloat16, device=dev)
+        if want_next_lo:
+            next_lo = torch.empty_like(next_hi)
+    d = gx_conv_desc()
+    d.x_hi, d.x_lo, d.w_hi, d.w_lo = _ptr(x_hi), _ptr(x_lo), _ptr(w_hi), _ptr(w_lo)
+    d.batch, d.h, d.w, d.cin, d.cout = b, h, w, cin, cout
+    d.upsample, d.passes = int(bool(upsample)), passes
+    d.demod = _ptr(demod)
+    d.noise = _ptr(noise)
+    if noise is not None:
+        d.noise_batch_stride = 0 if noise.shape[0] == 1 else ho * wo
+        d.noise_strength = _ptr(noise_strength)
+    d.bias = _ptr(bias)
+    d.act = int(act)
+    d.out = _ptr(out)
+    d.next_style, d.next_hi, d.next_lo = _ptr(next_style), _ptr(next_hi), _ptr(next_lo)
+    d.block_n, d.stages = block_n, stages
+    _check(lib.gx_modconv(C.byref(d), _stream()), "gx_modconv")
+    _count()
+    return out, next_hi, next_lo
+
+
+def blur_noise_bias_act(x_nhwc, fir, pad0, pad1, noise, noise_strength, bias, act, next_style, want_next_lo=True):
+    lib = load()
+    _f32(x_nhwc, "x"), _f32(fir, "fir")
+    b, hi, wi, c = x_nhwc.shape
+    kh, kw = fir.shape
+    ho, wo = hi + pad0 + pad1 - kh + 1, wi + pad0 + pad1 - kw + 1
+    dev = x_nhwc.device
+    out = torch.empty((b, ho, wo, c), dtype=torch.float32, device=dev)
+    next_hi = next_lo = None
+    if next_style is not None:
+        next_hi = torch.empty((b, ho, wo, c), dtype=torch.bfloat16, device=dev)
+        if want_next_lo:
+            next_lo = torch.empty_like(next_hi)
+    nbs = 0
+    if noise is not None:
+        nbs = 0 if noise.shape[0] == 1 else ho * wo
+    _check(lib.gx_blur_noise_bias_act(_ptr(x_nhwc), _ptr(fir), kh, kw, pad0, pad1, _ptr(noise), nbs,
+                                      _ptr(noise_strength), _ptr(bias), int(act), _ptr(out), _ptr(next_style),
+                                      _ptr(next_hi), _ptr(next_lo), b, hi, wi, c, _stream()),
+           "gx_blur_noise_bias_act")
+    _count()
+    return out, next_hi, next_lo
+
+
+def torgb(x_nhwc, w3c, w_scale, s, bias3, skip):
+    lib = load()
+    b, h, w, c = x_nhwc.shape
+    out = torch.empty((b, 3, h, w), dtype=torch.float32, device=x_nhwc.device)
+    _check(lib.gx_torgb(_ptr(x_nhwc), _ptr(w3c), float(w_scale), _ptr(s), _ptr(bias3), _ptr(skip), _ptr(out), b,
+                        h * w, c, _stream()), "gx_torgb")
+    _count()
+    return out
+
+
+def split_planes(x, transpose=False, want_lo=True):
+    """fp32 [rows, cols] -> bf16 (hi, lo) planes, optionally transposed."""
+    lib = load()
+    assert x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1
+    rows, cols = x.shape
+    shape = (cols, rows) if transpose else (rows, cols)
+    hi = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
+    lo = torch.empty_like(hi) if want_lo else None
+    _check(lib.gx_split_planes(_ptr(x), x.stride(0), _ptr(hi), _ptr(lo), rows, cols, int(transpose), _stream()),
+           "gx_split_planes")
+    _count()
+    return hi, lo
+
+
+def gemm(a_hi, a_lo, b_hi, b_lo, m, n, k, passes, out=None, bias=None, a_mn=False, b_mn=False, split_k=1,
+         block_n=0, stages=0, check=False, accumulate=False):
+    """C[m,n] = A * B^T.  Planes are 2-D bf16 tensors: A is [m,k] (or [k,m] if a_mn), B is [n,k] (or [k,n])."""
+    lib = load()
+    dev = a_hi.device
+    if out is None:
+        out = (torch.zeros if split_k > 1 else torch.empty)((m, n), dtype=torch.float32, device=dev)
+    d = gx_gemm_desc()
+    d.a_hi, d.a_lo, d.b_hi, d.b_lo = _ptr(a_hi), _ptr(a_lo), _ptr(b_hi), _ptr(b_lo)
+    d.lda, d.ldb = a_hi.stride(0), b_hi.stride(0)
+    d.a_mn_major, d.b_mn_major = int(a_mn), int(b_mn)
+    d.m, d.n, d.k, d.passes = m, n, k, passes
+    d.c, d.ldc = _ptr(out), out.stride(0)
+    d.bias = _ptr(bias)
+    d.split_k, d.block_n, d.stages = split_k, block_n, stages
+    d.accumulate = int(accumulate)
+    fn = lib.gx_gemm_check if check else lib.gx_gemm
+    _check(fn(C.byref(d), _stream()), "gx_gemm")
+    _count()
+    return out
+
+
+def gather_rows(feats_nhwc, out_h, out_w, hlen, row_img, row_src, nrows, ld=None, want_lo=True, want_f32=False):
+    """feats_nhwc: list of fp32 [nimg,h,w,c] tensors -> A planes [nrows, ld] bf16"""
+    lib = load()
+    dev = feats_nhwc[0].device
+    ld = ld or hlen
+    a_hi = torch.empty((nrows, ld), dtype=torch.bfloat16, device=dev)
+    a_lo = torch.empty_like(a_hi) if want_lo else None
+    a_f = torch.empty((nrows, ld), dtype=torch.float32, device=dev) if want_f32 else None
+    d = gx_gather_desc()
+    d.nlevels = len(feats_nhwc)
+    for i, f in enumerate(feats_nhwc):
+        _f32(f, "feature")
+        d.feat[i] = f.data_ptr()
+        d.h[i], d.w[i], d.c[i] = f.shape[1], f.shape[2], f.shape[3]
+    d.out_h, d.out_w, d.hlen = out_h, out_w, hlen
+    d.row_img, d.row_src, d.nrows = _ptr(row_img), _ptr(row_src), nrows
+    d.a_hi, d.a_lo, d.a_f32, d.ld = _ptr(a_hi), _ptr(a_lo), _ptr(a_f), ld
+    _check(lib.gx_gather_rows(C.byref(d), _stream()), "gx_gather_rows")
+    _count()
+    return a_hi, a_lo, a_f
+
+
+def l2norm_split(z, want_lo=True):
+    lib = load()
+    _f32(z, "z")
+    n, c = z.shape
+    hi = torch.empty((n, c), dtype=torch.bfloat16, device=z.device)
+    lo = torch.empty_like(hi) if want_lo else None
+    inv = torch.empty((n,), dtype=torch.float32, device=z.device)
+    _check(lib.gx_l2norm_split(_ptr(z), _ptr(hi), _ptr(lo), _ptr(inv), n, c, _stream()), "gx_l2norm_split")
+    _count()
+    return hi, lo, inv
+
+
+def l2norm_bwd_split(dzn, zn_hi, zn_lo, inv_norm, want_lo=True):
+    lib = load()
+    _f32(dzn, "dzn")
+    n, c = dzn.shape
+    hi = torch.empty((n, c), dtype=torch.bfloat16, device=dzn.device)
+    lo = torch.empty_like(hi) if want_lo else None
+    _check(lib.gx_l2norm_bwd_split(_ptr(dzn), _ptr(zn_hi), _ptr(zn_lo), _ptr(inv_norm), _ptr(hi), _ptr(lo), n, c,
+                                   _stream()), "gx_l2norm_bwd_split")
+    _count()
+    return hi, lo
+
+
+def normalize_rows_(w):
+    lib = load()
+    _f32(w, "w")
+    _check(lib.gx_normalize_rows(_ptr(w), w.shape[0], w.shape[1], _stream()), "gx_normalize_rows")
+    _count()
+    return w
+
+
+class SinkhornWorkspace:
+    def __init__(self, k, device):
+        lib = load()
+        self.k = k
+        self.max_parts = lib.gx_sinkhorn_max_parts()
+        self.partials = torch.empty((self.max_parts, k), dtype=torch.float32, device=device)
+        self.u = torch.empty((k,), dtype=torch.float32, device=device)
+
+
+def sinkhorn_pass(s, inv_eps, first, u_in, r, c, n_total, ws: SinkhornWorkspace):
+    """One streaming pass over S [n,k]; afterwards ws.u holds the LOCAL column sums."""
+    lib = load()
+    n, k = s.shape
+    nparts = C.c_int(0)
+    _check(lib.gx_sinkhorn_pass(_ptr(s), n, k, s.stride(0), float(inv_eps), int(first), _ptr(u_in), _ptr(r), _ptr(c),
+                                int(n_total), _ptr(ws.partials), C.byref(nparts), _stream()), "gx_sinkhorn_pass")
+    _check(lib.gx_sinkhorn_reduce(_ptr(ws.partials), nparts.value, k, _ptr(ws.u), _stream()), "gx_sinkhorn_reduce")
+    _count(2)
+    return ws.u
+
+
+def sinkhorn_log_a(u, r):
+    lib = load()
+    k = u.numel()
+    la = torch.empty((k,), dtype=torch.float32, device=u.device)
+    _check(lib.gx_sinkhorn_log_a(_ptr(u), _ptr(r), k, _ptr(la), _stream()), "gx_sinkhorn_log_a")
+    _count()
+    return la
+
+
+def sinkhorn_q(s, inv_eps, log_a):
+    lib = load()
+    n, k = s.shape
+    q = torch.empty((n, k), dtype=torch.float32, device=s.device)
+    _check(lib.gx_sinkhorn_q(_ptr(s), n, k, s.stride(0), float(inv_eps), _ptr(log_a), _ptr(q), _stream()),
+           "gx_sinkhorn_q")
+    _count()
+    return q
+
+
+def swav_loss(s_s, s_t, inv_eps, inv_temp, la_s, la_t, grad_scale, want_lo=False, want_f32=False, want_db=True):
+    """Returns (loss_sum tensor [1] (not divided by N), dS_s planes, dS_t planes, db [k], f32 grads)."""
+    lib = load()
+    n, k = s_s.shape
+    dev = s_s.device
+    maxp = lib.gx_loss_max_parts()
+    loss_parts = torch.zeros((maxp,), dtype=torch.float32, device=dev)
+    db_parts = torch.empty((maxp, k), dtype=torch.float32, device=dev) if want_db else None
+    ds_s_hi = torch.empty((n, k), dtype=torch.bfloat16, device=dev)
+    ds_t_hi = torch.empty((n, k), dtype=torch.bfloat16, device=dev)
+    ds_s_lo = torch.empty_like(ds_s_hi) if want_lo else None
+    ds_t_lo = torch.empty_like(ds_t_hi) if want_lo else None
+    fs = torch.empty((n, k), dtype=torch.float32, device=dev) if want_f32 else None
+    ft = torch.empty((n, k), dtype=torch.float32, device=dev) if want_f32 else None
+    nparts = C.c_int(0)
+    _check(lib.gx_swav_loss(_ptr(s_s), _ptr(s_t), n, k, s_s.stride(0), float(inv_eps), float(inv_temp), _ptr(la_s),
+                            _ptr(la_t), float(grad_scale), _ptr(loss_parts), _ptr(db_parts), C.byref(nparts),
+                            _ptr(ds_s_hi), _ptr(ds_s_lo), _ptr(ds_t_hi), _ptr(ds_t_lo), k, _ptr(fs), _ptr(ft),
+                            _stream()), "gx_swav_loss")
+    _count()
+    db = None
+    if want_db:
+        db = torch.empty((k,), dtype=torch.float32, device=dev)
+        _check(lib.gx_sinkhorn_reduce(_ptr(db_parts), nparts.value, k, _ptr(db), _stream()), "gx_sinkhorn_reduce")
+        _count()
+    return loss_parts, (ds_s_hi, ds_s_lo), (ds_t_hi, ds_t_lo), db, (fs, ft)
+
+
+def larc_sgd_(p, g, buf, lr, momentum, trust, weight_decay, eps, first_step, norms):
+    lib = load()
+    _f32(p, "p"), _f32(g, "g"), _f32(buf, "buf")
+    _check(lib.gx_larc_sgd(_ptr(p), _ptr(g), _ptr(buf), p.numel(), float(lr), float(momentum), float(trust),
+                           float(weight_decay), float(eps), int(first_step), _ptr(norms), _stream()), "gx_larc_sgd")
+    _count(2)
+
+
+def argmax_rows(x):
+    lib = load()
+    n, c = x.shape
+    labels = torch.empty((n,), dtype=torch.int64, device=x.device)
+    _check(lib.gx_argmax_rows(_ptr(x), n, c, x.stride(0), _ptr(labels), _stream()), "gx_argmax_rows")
+    _count()
+    return labels
+
+
+def kmeans_assign(x, centers):
+    lib = load()
+    _f32(centers, "centers")
+    n, c = x.shape
+    labels = torch.empty((n,), dtype=torch.int32, device=x.device)
+    _check(lib.gx_kmeans_assign(_ptr(x), n, c, x.stride(0), _ptr(centers), centers.shape[0], _ptr(labels), _stream()),
+           "gx_kmeans_assign")
+    _count()
+    return labels

@@ -1,0 +1,83 @@
+// Shared helpers for the ganecdotes_b200 CUDA library (sm_100a only).
+#pragma once
+#include <cuda_runtime.h>
+#include <cuda_bf16.h>
+#include <stdint.h>
+
+#include "../../include/ganecdotes_b200.h"
+
+#define GX_SM_COUNT_FALLBACK 148
+
+#define GX_CHECK_ARG(cond)            \
+  do {                                \
+    if (!(cond)) return GX_ERR_ARG;   \
+  } while (0)
+
+#define GX_CHECK_CUDA(expr)                          \
+  do {                                               \
+    cudaError_t _e = (expr);                         \
+    if (_e != cudaSuccess) {                         \
+      gx_set_last_cuda_error((int)_e);               \
+      return GX_ERR_CUDA;                            \
+    }                                                \
+  } while (0)
+
+#define GX_LAUNCH_CHECK() GX_CHECK_CUDA(cudaGetLastError())
+
+void gx_set_last_cuda_error(int e);
+int gx_sm_count();
+
+static inline int gx_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+#ifdef __CUDACC__
+
+// ---------------------------------------------------------------------------
+// split-bf16: x = hi + lo with hi = bf16(x), lo = bf16(x - hi).  Three bf16 MMAs
+// (hi*hi + hi*lo + lo*hi) then reproduce an fp32 product to ~2^-16 relative.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ void gx_split_bf16(float x, __nv_bfloat16& hi, __nv_bfloat16& lo) {
+  hi = __float2bfloat16_rn(x);
+  lo = __float2bfloat16_rn(x - __bfloat162float(hi));
+}
+
+__device__ __forceinline__ uint32_t gx_pack_bf16x2(__nv_bfloat16 a, __nv_bfloat16 b) {
+  return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
+}
+
+// split 4 floats into packed hi (2 words) and lo (2 words)
+__device__ __forceinline__ void gx_split4(const float4 v, uint2& hi, uint2& lo) {
+  __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
+  gx_split_bf16(v.x, h0, l0);
+  gx_split_bf16(v.y, h1, l1);
+  gx_split_bf16(v.z, h2, l2);
+  gx_split_bf16(v.w, h3, l3);
+  hi = make_uint2(gx_pack_bf16x2(h0, h1), gx_pack_bf16x2(h2, h3));
+  lo = make_uint2(gx_pack_bf16x2(l0, l1), gx_pack_bf16x2(l2, l3));
+}
+
+__device__ __forceinline__ float gx_warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+__device__ __forceinline__ float gx_warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+
+// streaming 128-bit accesses that do not pollute L1
+__device__ __forceinline__ float4 gx_ldg_stream(const float4* p) {
+  float4 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v4.f32 {%0,%1,%2,%3}, [%4];"
+               : "=f"(r.x), "=f"(r.y), "=f"(r.z), "=f"(r.w)
+               : "l"(p));
+  return r;
+}
+__device__ __forceinline__ void gx_stg_stream(float4* p, const float4 v) {
+  asm volatile("st.global.L1::no_allocate.v4.f32 [%0], {%1,%2,%3,%4};" ::"l"(p), "f"(v.x), "f"(v.y),
+               "f"(v.z), "f"(v.w)
+               : "memory");
+}
+
+#endif  // __CUDACC__

@@ -1,0 +1,306 @@
+// FIR resampling (upfirdn2d), fused bias+activation, and the hot-path fusion of both:
+// blur + noise + bias + leaky-relu*sqrt2 (+ next conv's modulate/split) on NHWC maps.
+#include "gx_common.cuh"
+
+namespace {
+
+// --------------------------------------------------------------------------
+// Generic upfirdn2d, layout [major, h, w, minor] (ref: upfirdn2d_kernel.cu:52-215).
+// out[oy,ox] = sum_{ky,kx} k[kh-1-ky][kw-1-kx] * u[oy*dy+ky][ox*dx+kx], where u is the
+// zero-inserted, padded/cropped input.  Only taps that land on real samples are visited.
+// --------------------------------------------------------------------------
+struct UpfirParams {
+  int major, in_h, in_w, minor, kh, kw, up_x, up_y, down_x, down_y, pad_x0, pad_y0, out_h, out_w;
+};
+
+__device__ __forceinline__ int floor_div(int a, int b) {
+  int q = a / b;
+  return (q * b > a) ? q - 1 : q;
+}
+
+__global__ void upfirdn2d_kernel(const float* __restrict__ in, const float* __restrict__ kern,
+                                 float* __restrict__ out, const UpfirParams p, long long total) {
+  extern __shared__ float sk[];  // flipped taps
+  for (int i = threadIdx.x; i < p.kh * p.kw; i += blockDim.x) {
+    const int ky = i / p.kw, kx = i - ky * p.kw;
+    sk[i] = kern[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)];
+  }
+  __syncthreads();
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx;
+    const int mi = (int)(r % p.minor); r /= p.minor;
+    const int ox = (int)(r % p.out_w); r /= p.out_w;
+    const int oy = (int)(r % p.out_h); r /= p.out_h;
+    const int mj = (int)r;
+    // u index of tap ky is oy*dy+ky; it maps to input row (oy*dy+ky-pad_y0)/up_y when divisible
+    const int base_y = oy * p.down_y - p.pad_y0;
+    const int base_x = ox * p.down_x - p.pad_x0;
+    int ky0 = ((-base_y) % p.up_y + p.up_y) % p.up_y;  // smallest ky >= 0 with (base_y+ky) % up_y == 0
+    int kx0 = ((-base_x) % p.up_x + p.up_x) % p.up_x;
+    float acc = 0.f;
+    const float* src = in + (long long)mj * p.in_h * p.in_w * p.minor + mi;
+    for (int ky = ky0; ky < p.kh; ky += p.up_y) {
+      const int iy = floor_div(base_y + ky, p.up_y);
+      if (iy < 0 || iy >= p.in_h) continue;
+      for (int kx = kx0; kx < p.kw; kx += p.up_x) {
+        const int ix = floor_div(base_x + kx, p.up_x);
+        if (ix < 0 || ix >= p.in_w) continue;
+        acc = fmaf(__ldg(src + ((long long)iy * p.in_w + ix) * p.minor), sk[ky * p.kw + kx], acc);
+      }
+    }
+    out[idx] = acc;
+  }
+}
+
+// --------------------------------------------------------------------------
+// fused_bias_act (ref: fused_bias_act_kernel.cu:18-85)
+// --------------------------------------------------------------------------
+__device__ __forceinline__ float bias_act_one(float x, float b, float ref, int mode, float alpha, float scale) {
+  x += b;
+  float y;
+  switch (mode) {
+    default:
+    case 10: case 11: y = x; break;
+    case 12: y = 0.f; break;
+    case 30: y = (x > 0.f) ? x : x * alpha; break;
+    case 31: y = (ref > 0.f) ? x : x * alpha; break;
+    case 32: y = 0.f; break;
+  }
+  return y * scale;
+}
+
+__global__ void fused_bias_act_kernel(const float* __restrict__ x, const float* __restrict__ b,
+                                      const float* __restrict__ ref, float* __restrict__ out, long long n, int step_b,
+                                      int size_b, int mode, float alpha, float scale, int vec) {
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  if (vec) {
+    const long long n4 = n >> 2;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += stride) {
+      const float4 v = gx_ldg_stream(reinterpret_cast<const float4*>(x) + i);
+      float4 rv = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (ref) rv = gx_ldg_stream(reinterpret_cast<const float4*>(ref) + i);
+      float bb = 0.f;
+      if (b) bb = __ldg(b + ((i * 4) / step_b) % size_b);  // step_b % 4 == 0: one bias per vector
+      float4 o;
+      o.x = bias_act_one(v.x, bb, rv.x, mode, alpha, scale);
+      o.y = bias_act_one(v.y, bb, rv.y, mode, alpha, scale);
+      o.z = bias_act_one(v.z, bb, rv.z, mode, alpha, scale);
+      o.w = bias_act_one(v.w, bb, rv.w, mode, alpha, scale);
+      gx_stg_stream(reinterpret_cast<float4*>(out) + i, o);
+    }
+  } else {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) {
+      const float bb = b ? __ldg(b + (i / step_b) % size_b) : 0.f;
+      const float rv = ref ? ref[i] : 0.f;
+      out[i] = bias_act_one(x[i], bb, rv, mode, alpha, scale);
+    }
+  }
+}
+
+// --------------------------------------------------------------------------
+// Hot path: blur (4x4 FIR, up=down=1) of the (2H+1)^2 transposed-conv output, fused with
+// noise + bias + lrelu*sqrt2 and the next layer's modulate+split.  NHWC, 4 channels per
+// thread (128-bit accesses), a sliding 4-row window of input vectors held in registers so
+// each input vector is fetched once per output column.
+// --------------------------------------------------------------------------
+constexpr int BLUR_STRIP = 16;
+
+template <int KH, int KW>
+__global__ void __launch_bounds__(256)
+blur_fused_kernel(const float* __restrict__ in, const float* __restrict__ fir, int pad0, const float* __restrict__ noise,
+                  long long noise_bstride, const float* __restrict__ noise_strength, const float* __restrict__ bias,
+                  int act, float* __restrict__ out, const float* __restrict__ next_style,
+                  __nv_bfloat16* __restrict__ next_hi, __nv_bfloat16* __restrict__ next_lo, int batch, int hi, int wi,
+                  int ho, int wo, int c) {
+  __shared__ float sk[KH * KW];
+  if (threadIdx.x < KH * KW) {
+    const int ky = threadIdx.x / KW, kx = threadIdx.x % KW;
+    sk[threadIdx.x] = fir[(KH - 1 - ky) * KW + (KW - 1 - kx)];
+  }
+  __syncthreads();
+  const int cq = c >> 2;                       // channel quads
+  const int cq_blk = cq < 256 ? cq : 256;      // quads handled per block row
+  const int xs_per_blk = 256 / cq_blk;
+  const int qi = threadIdx.x % cq_blk;
+  const int xi = threadIdx.x / cq_blk;
+  const int cq_groups = (cq + cq_blk - 1) / cq_blk;
+  const int cq0 = (blockIdx.z % cq_groups) * cq_blk;
+  const int b = blockIdx.z / cq_groups;
+  const int ox = blockIdx.x * xs_per_blk + xi;
+  const int q = cq0 + qi;
+  if (ox >= wo || q >= cq || b >= batch) return;
+  const int oy0 = blockIdx.y * BLUR_STRIP;
+  const int oy1 = min(ho, oy0 + BLUR_STRIP);
+  float kreg[KH * KW];
+#pragma unroll
+  for (int i = 0; i < KH * KW; ++i) kreg[i] = sk[i];
+  const float4* src = reinterpret_cast<const float4*>(in) + (long long)b * hi * wi * cq + q;
+  float4 win[KH][KW];
+  auto load_row = [&](int iy, float4 (&dst)[KW]) {
+#pragma unroll
+    for (int kx = 0; kx < KW; ++kx) {
+      const int ix = ox + kx - pad0;
+      if (iy >= 0 && iy < hi && ix >= 0 && ix < wi)
+        dst[kx] = __ldg(src + ((long long)iy * wi + ix) * cq);
+      else
+        dst[kx] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+  };
+#pragma unroll
+  for (int ky = 0; ky < KH - 1; ++ky) load_row(oy0 + ky - pad0, win[ky + 1]);
+  const float nstr = noise ? __ldg(noise_strength) : 0.f;
+  float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) bs = __ldg(reinterpret_cast<const float4*>(bias) + q);
+  float4 st = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (next_style) st = __ldg(reinterpret_cast<const float4*>(next_style) + (long long)b * cq + q);
+  for (int oy = oy0; oy < oy1; ++oy) {
+#pragma unroll
+    for (int ky = 0; ky < KH - 1; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < KW; ++kx) win[ky][kx] = win[ky + 1][kx];
+    load_row(oy + KH - 1 - pad0, win[KH - 1]);
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < KH; ++ky)
+#pragma unroll
+      for (int kx = 0; kx < KW; ++kx) {
+        const float kv = kreg[ky * KW + kx];
+        acc.x = fmaf(win[ky][kx].x, kv, acc.x);
+        acc.y = fmaf(win[ky][kx].y, kv, acc.y);
+        acc.z = fmaf(win[ky][kx].z, kv, acc.z);
+        acc.w = fmaf(win[ky][kx].w, kv, acc.w);
+      }
+    if (noise) {
+      const float nz = nstr * __ldg(noise + (long long)b * noise_bstride + (long long)oy * wo + ox);
+      acc.x += nz; acc.y += nz; acc.z += nz; acc.w += nz;
+    }
+    acc.x += bs.x; acc.y += bs.y; acc.z += bs.z; acc.w += bs.w;
+    if (act) {
+      const float s2 = 1.41421356237309515f;
+      acc.x = (acc.x > 0.f ? acc.x : acc.x * 0.2f) * s2;
+      acc.y = (acc.y > 0.f ? acc.y : acc.y * 0.2f) * s2;
+      acc.z = (acc.z > 0.f ? acc.z : acc.z * 0.2f) * s2;
+      acc.w = (acc.w > 0.f ? acc.w : acc.w * 0.2f) * s2;
+    }
+    const long long o = (((long long)b * ho + oy) * wo + ox) * cq + q;
+    reinterpret_cast<float4*>(out)[o] = acc;
+    if (next_hi) {
+      uint2 h, l;
+      gx_split4(make_float4(acc.x * st.x, acc.y * st.y, acc.z * st.z, acc.w * st.w), h, l);
+      reinterpret_cast<uint2*>(next_hi)[o] = h;
+      if (next_lo) reinterpret_cast<uint2*>(next_lo)[o] = l;
+    }
+  }
+}
+
+// ToRGB: warp per pixel, 3 dot products over C with the per-sample modulated 1x1 weights.
+__global__ void torgb_kernel(const float* __restrict__ x, const float* __restrict__ w, float w_scale,
+                             const float* __restrict__ s, const float* __restrict__ bias,
+                             const float* __restrict__ skip, float* __restrict__ out, int batch, int hw, int c) {
+  const int lane = threadIdx.x & 31;
+  const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pix >= (long long)batch * hw) return;
+  const int b = (int)(pix / hw);
+  const int p = (int)(pix - (long long)b * hw);
+  const float4* xr = reinterpret_cast<const float4*>(x + pix * c);
+  const float4* sr = reinterpret_cast<const float4*>(s + (long long)b * c);
+  float a0 = 0.f, a1 = 0.f, a2 = 0.f;
+  for (int i = lane; i < (c >> 2); i += 32) {
+    const float4 xv = __ldg(xr + i);
+    const float4 sv = __ldg(sr + i);
+    const float4 w0 = __ldg(reinterpret_cast<const float4*>(w) + i);
+    const float4 w1 = __ldg(reinterpret_cast<const float4*>(w + c) + i);
+    const float4 w2 = __ldg(reinterpret_cast<const float4*>(w + 2 * c) + i);
+    const float m0 = xv.x * sv.x, m1 = xv.y * sv.y, m2 = xv.z * sv.z, m3 = xv.w * sv.w;
+    a0 += m0 * (w0.x * w_scale) + m1 * (w0.y * w_scale) + m2 * (w0.z * w_scale) + m3 * (w0.w * w_scale);
+    a1 += m0 * (w1.x * w_scale) + m1 * (w1.y * w_scale) + m2 * (w1.z * w_scale) + m3 * (w1.w * w_scale);
+    a2 += m0 * (w2.x * w_scale) + m1 * (w2.y * w_scale) + m2 * (w2.z * w_scale) + m3 * (w2.w * w_scale);
+  }
+  a0 = gx_warp_sum(a0); a1 = gx_warp_sum(a1); a2 = gx_warp_sum(a2);
+  if (lane < 3) {
+    float v = lane == 0 ? a0 : (lane == 1 ? a1 : a2);
+    v += bias ? bias[lane] : 0.f;
+    const long long o = ((long long)b * 3 + lane) * hw + p;
+    if (skip) v += skip[o];
+    out[o] = v;
+  }
+}
+
+}  // namespace
+
+extern "C" int gx_upfirdn2d(const float* input, const float* kernel, float* out, int major, int in_h, int in_w,
+                            int minor, int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0,
+                            int pad_x1, int pad_y0, int pad_y1, void* stream) {
+  GX_CHECK_ARG(input && kernel && out);
+  GX_CHECK_ARG(major > 0 && in_h > 0 && in_w > 0 && minor > 0 && kh > 0 && kw > 0);
+  GX_CHECK_ARG(up_x > 0 && up_y > 0 && down_x > 0 && down_y > 0);
+  UpfirParams p;
+  p.major = major; p.in_h = in_h; p.in_w = in_w; p.minor = minor; p.kh = kh; p.kw = kw;
+  p.up_x = up_x; p.up_y = up_y; p.down_x = down_x; p.down_y = down_y; p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
+  p.out_h = (in_h * up_y + pad_y0 + pad_y1 - kh + down_y) / down_y;
+  p.out_w = (in_w * up_x + pad_x0 + pad_x1 - kw + down_x) / down_x;
+  GX_CHECK_ARG(p.out_h > 0 && p.out_w > 0);
+  GX_CHECK_ARG(kh * kw * 4 <= 48 * 1024);
+  const long long total = (long long)major * p.out_h * p.out_w * minor;
+  int grid = (int)((total + 255) / 256);
+  const int cap = gx_sm_count() * 16;
+  if (grid > cap) grid = cap;
+  upfirdn2d_kernel<<<grid, 256, kh * kw * sizeof(float), (cudaStream_t)stream>>>(input, kernel, out, p, total);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_fused_bias_act(const float* input, const float* bias, const float* refer, float* out, long long n,
+                                 int step_b, int size_b, int act, int grad, float alpha, float scale, void* stream) {
+  GX_CHECK_ARG(input && out && n >= 0);
+  if (n == 0) return GX_OK;
+  const int mode = act * 10 + grad;
+  GX_CHECK_ARG(mode == 10 || mode == 11 || mode == 12 || mode == 30 || mode == 31 || mode == 32);
+  GX_CHECK_ARG(mode != 31 || refer != nullptr);
+  if (bias) GX_CHECK_ARG(step_b > 0 && size_b > 0);
+  else { step_b = 1; size_b = 1; }
+  const bool aligned = ((reinterpret_cast<uintptr_t>(input) | reinterpret_cast<uintptr_t>(out) |
+                         reinterpret_cast<uintptr_t>(refer)) & 15) == 0;
+  const int vec = (aligned && (n % 4 == 0) && (step_b % 4 == 0)) ? 1 : 0;
+  const long long work = vec ? n / 4 : n;
+  int grid = (int)((work + 255) / 256);
+  const int cap = gx_sm_count() * 16;
+  if (grid > cap) grid = cap;
+  fused_bias_act_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(input, bias, refer, out, n, step_b, size_b, mode, alpha,
+                                                                scale, vec);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_blur_noise_bias_act(const float* in, const float* fir, int kh, int kw, int pad0, int pad1,
+                                      const float* noise, long long noise_batch_stride, const float* noise_strength,
+                                      const float* bias, int act, float* out, const float* next_style, void* next_hi,
+                                      void* next_lo, int batch, int hi, int wi, int c, void* stream) {
+  GX_CHECK_ARG(in && fir && out && batch > 0 && hi > 0 && wi > 0);
+  GX_CHECK_ARG(c % 4 == 0);
+  GX_CHECK_ARG(kh == 4 && kw == 4);  // StyleGAN2 blur_kernel=[1,3,3,1]; other sizes go through gx_upfirdn2d
+  GX_CHECK_ARG(noise == nullptr || noise_strength != nullptr);
+  GX_CHECK_ARG(next_style == nullptr || next_hi != nullptr);
+  const int ho = hi + pad0 + pad1 - kh + 1, wo = wi + pad0 + pad1 - kw + 1;
+  GX_CHECK_ARG(ho > 0 && wo > 0);
+  const int cq = c / 4;
+  const int cq_blk = cq < 256 ? cq : 256;
+  const int xs = 256 / cq_blk;
+  dim3 grid(gx_cdiv(wo, xs), gx_cdiv(ho, BLUR_STRIP), batch * gx_cdiv(cq, cq_blk));
+  GX_CHECK_ARG(256 % cq_blk == 0);
+  blur_fused_kernel<4, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(
+      in, fir, pad0, noise, noise_batch_stride, noise_strength, bias, act, out, next_style,
+      reinterpret_cast<__nv_bfloat16*>(next_hi), reinterpret_cast<__nv_bfloat16*>(next_lo), batch, hi, wi, ho, wo, c);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_torgb(const float* x, const float* w, float w_scale, const float* s, const float* bias,
+                        const float* skip, float* out, int batch, int hw, int c, void* stream) {
+  GX_CHECK_ARG(x && w && s && out && batch > 0 && hw > 0 && c % 4 == 0);
+  const long long npix = (long long)batch * hw;
+  torgb_kernel<<<gx_cdiv(npix, 8), 256, 0, (cudaStream_t)stream>>>(x, w, w_scale, s, bias, skip, out, batch, hw, c);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}

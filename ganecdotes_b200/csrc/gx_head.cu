@@ -1,0 +1,734 @@
+// Memory-bound stages of the SwAV head: per-pixel feature gather, L2 normalisation,
+// Sinkhorn-Knopp passes, fused swapped-prediction loss fwd+bwd, LARC+SGD, arg-max label
+// maps and k-means assignment.  All kernels use 128-bit coalesced accesses and
+// warp-shuffle + shared-memory reductions; none of them is reshaped into a GEMM.
+#include "gx_common.cuh"
+
+namespace {
+
+constexpr float LOG2E = 1.4426950408889634f;
+
+// ---------------------------------------------------------------------------
+// gather: rotate/flip + random-pixel sampling + nearest upsample + concat + [:hlen]
+// one 128-thread block per output row (= one sampled pixel), 16 B per thread per access
+// ---------------------------------------------------------------------------
+__global__ void __launch_bounds__(128)
+gather_rows_kernel(const gx_gather_desc d) {
+  const long long r = blockIdx.x;
+  if (r >= d.nrows) return;
+  int img, src;
+  if (d.row_src) {
+    img = d.row_img ? d.row_img[r] : 0;
+    src = d.row_src[r];
+  } else {
+    const long long per = (long long)d.out_h * d.out_w;
+    img = (int)(r / per);
+    src = (int)(r - (long long)img * per);
+  }
+  const int sy = src >= 0 ? src / d.out_w : 0;
+  const int sx = src >= 0 ? src - sy * d.out_w : 0;
+  uint2* ah = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.a_hi) + r * d.ld);
+  uint2* al = d.a_lo ? reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.a_lo) + r * d.ld) : nullptr;
+  float4* af = d.a_f32 ? reinterpret_cast<float4*>(d.a_f32 + r * d.ld) : nullptr;
+  int off = 0;
+  for (int l = 0; l < d.nlevels && off < d.hlen; ++l) {
+    const int cl = d.c[l];
+    const int keep = min(cl, d.hlen - off);
+    // F.interpolate(mode='nearest'): src = floor(dst * in / out)
+    const int ly = (int)(((long long)sy * d.h[l]) / d.out_h);
+    const int lx = (int)(((long long)sx * d.w[l]) / d.out_w);
+    const float4* f = reinterpret_cast<const float4*>(
+        d.feat[l] + (((long long)img * d.h[l] + ly) * d.w[l] + lx) * cl);
+    for (int q = threadIdx.x; q < (keep >> 2); q += blockDim.x) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (src >= 0) v = __ldg(f + q);
+      uint2 h, lo;
+      gx_split4(v, h, lo);
+      const int o = (off >> 2) + q;
+      ah[o] = h;
+      if (al) al[o] = lo;
+      if (af) af[o] = v;
+    }
+    off += keep;
+  }
+  // zero the padding columns [hlen, ld)
+  for (int q = (d.hlen >> 2) + threadIdx.x; q < (int)(d.ld >> 2); q += blockDim.x) {
+    ah[q] = make_uint2(0u, 0u);
+    if (al) al[q] = make_uint2(0u, 0u);
+    if (af) af[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+}
+
+// ---------------------------------------------------------------------------
+// L2 normalisation of projected rows (warp per row)
+// ---------------------------------------------------------------------------
+__global__ void l2norm_split_kernel(const float* __restrict__ z, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, float* __restrict__ inv_norm, long long n, int c) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float4* zr = reinterpret_cast<const float4*>(z + row * c);
+  const int cq = c >> 2;
+  float ss = 0.f;
+  for (int i = lane; i < cq; i += 32) {
+    const float4 v = __ldg(zr + i);
+    ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
+  }
+  ss = gx_warp_sum(ss);
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  if (lane == 0 && inv_norm) inv_norm[row] = inv;
+  uint2* oh = reinterpret_cast<uint2*>(hi + row * c);
+  uint2* ol = lo ? reinterpret_cast<uint2*>(lo + row * c) : nullptr;
+  for (int i = lane; i < cq; i += 32) {
+    const float4 v = __ldg(zr + i);
+    uint2 h, l;
+    gx_split4(make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv), h, l);
+    oh[i] = h;
+    if (ol) ol[i] = l;
+  }
+}
+
+__device__ __forceinline__ float4 planes_to_float4(uint2 h, const uint2* lo_ptr) {
+  float4 v;
+  v.x = __uint_as_float(h.x << 16);
+  v.y = __uint_as_float(h.x & 0xffff0000u);
+  v.z = __uint_as_float(h.y << 16);
+  v.w = __uint_as_float(h.y & 0xffff0000u);
+  if (lo_ptr) {
+    const uint2 l = *lo_ptr;
+    v.x += __uint_as_float(l.x << 16);
+    v.y += __uint_as_float(l.x & 0xffff0000u);
+    v.z += __uint_as_float(l.y << 16);
+    v.w += __uint_as_float(l.y & 0xffff0000u);
+  }
+  return v;
+}
+
+__global__ void l2norm_bwd_split_kernel(const float* __restrict__ dzn, const __nv_bfloat16* __restrict__ zh,
+                                        const __nv_bfloat16* __restrict__ zl, const float* __restrict__ inv_norm,
+                                        __nv_bfloat16* __restrict__ dh, __nv_bfloat16* __restrict__ dl, long long n,
+                                        int c) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const int cq = c >> 2;
+  const float4* gr = reinterpret_cast<const float4*>(dzn + row * c);
+  const uint2* hr = reinterpret_cast<const uint2*>(zh + row * c);
+  const uint2* lr = zl ? reinterpret_cast<const uint2*>(zl + row * c) : nullptr;
+  float dot = 0.f;
+  for (int i = lane; i < cq; i += 32) {
+    const float4 g = __ldg(gr + i);
+    const float4 zv = planes_to_float4(hr[i], lr ? lr + i : nullptr);
+    dot += g.x * zv.x + g.y * zv.y + g.z * zv.z + g.w * zv.w;
+  }
+  dot = gx_warp_sum(dot);
+  const float inv = inv_norm[row];
+  uint2* oh = reinterpret_cast<uint2*>(dh + row * c);
+  uint2* ol = dl ? reinterpret_cast<uint2*>(dl + row * c) : nullptr;
+  for (int i = lane; i < cq; i += 32) {
+    const float4 g = __ldg(gr + i);
+    const float4 zv = planes_to_float4(hr[i], lr ? lr + i : nullptr);
+    uint2 h, l;
+    gx_split4(make_float4((g.x - zv.x * dot) * inv, (g.y - zv.y * dot) * inv, (g.z - zv.z * dot) * inv,
+                          (g.w - zv.w * dot) * inv),
+              h, l);
+    oh[i] = h;
+    if (ol) ol[i] = l;
+  }
+}
+
+__global__ void normalize_rows_kernel(float* __restrict__ w, long long rows, int cols) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= rows) return;
+  float* wr = w + row * cols;
+  float ss = 0.f;
+  for (int i = lane; i < cols; i += 32) ss = fmaf(wr[i], wr[i], ss);
+  ss = gx_warp_sum(ss);
+  const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
+  for (int i = lane; i < cols; i += 32) wr[i] *= inv;
+}
+
+// ---------------------------------------------------------------------------
+// fp32 -> split planes (optionally transposed through a padded smem tile)
+// ---------------------------------------------------------------------------
+__global__ void split_planes_kernel(const float* __restrict__ x, long long ld, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo, long long rows, long long cols) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    __nv_bfloat16 h, l;
+    gx_split_bf16(x[r * ld + c], h, l);
+    hi[i] = h;
+    if (lo) lo[i] = l;
+  }
+}
+
+__global__ void split_planes_t_kernel(const float* __restrict__ x, long long ld, __nv_bfloat16* __restrict__ hi,
+                                      __nv_bfloat16* __restrict__ lo, long long rows, long long cols) {
+  __shared__ float tile[32][33];
+  const long long r0 = (long long)blockIdx.y * 32, c0 = (long long)blockIdx.x * 32;
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long r = r0 + j, c = c0 + threadIdx.x;
+    tile[j][threadIdx.x] = (r < rows && c < cols) ? x[r * ld + c] : 0.f;
+  }
+  __syncthreads();
+  for (int j = threadIdx.y; j < 32; j += blockDim.y) {
+    const long long c = c0 + j, r = r0 + threadIdx.x;  // output [cols, rows]
+    if (c < cols && r < rows) {
+      __nv_bfloat16 h, l;
+      gx_split_bf16(tile[threadIdx.x][j], h, l);
+      hi[c * rows + r] = h;
+      if (lo) lo[c * rows + r] = l;
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Sinkhorn-Knopp pass (scaling-vector form).  512 threads own the K columns
+// (4 consecutive columns per thread per 2048-column sweep, J sweeps), stream rows of S
+// once, keep the column accumulators u'_k in registers.
+// ---------------------------------------------------------------------------
+constexpr int SK_THREADS = 512;
+constexpr int SK_ROWS = 2;
+
+template <int J>
+__global__ void __launch_bounds__(SK_THREADS, 1)
+sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long lds, float scale_log2, int first,
+                     const float* __restrict__ u_in, const float* __restrict__ r, const float* __restrict__ cvec,
+                     float c_uniform, float* __restrict__ partials) {
+  __shared__ float red[2][SK_ROWS][SK_THREADS / 32];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  float a[J][4], acc[J][4];
+  bool colok[J];
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int col = j * (SK_THREADS * 4) + tid * 4;
+    colok[j] = col < k;
+#pragma unroll
+    for (int e = 0; e < 4; ++e) {
+      acc[j][e] = 0.f;
+      a[j][e] = 1.f;
+      if (!first && colok[j]) {
+        const float rk = r ? r[col + e] : 1.f / (float)k;
+        a[j][e] = rk / u_in[col + e];
+      }
+    }
+  }
+  int buf = 0;
+  for (long long row0 = (long long)blockIdx.x * SK_ROWS; row0 < n; row0 += (long long)gridDim.x * SK_ROWS) {
+    float4 v[SK_ROWS][J];
+#pragma unroll
+    for (int rr = 0; rr < SK_ROWS; ++rr) {
+      const long long row = row0 + rr;
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        v[rr][j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
+        if (row < n && colok[j])
+          v[rr][j] = gx_ldg_stream(reinterpret_cast<const float4*>(s + row * lds + j * (SK_THREADS * 4) + tid * 4));
+      }
+    }
+    float t[SK_ROWS];
+#pragma unroll
+    for (int rr = 0; rr < SK_ROWS; ++rr) {
+      t[rr] = 0.f;
+#pragma unroll
+      for (int j = 0; j < J; ++j) {
+        v[rr][j].x = exp2f(v[rr][j].x * scale_log2);
+        v[rr][j].y = exp2f(v[rr][j].y * scale_log2);
+        v[rr][j].z = exp2f(v[rr][j].z * scale_log2);
+        v[rr][j].w = exp2f(v[rr][j].w * scale_log2);
+        t[rr] += a[j][0] * v[rr][j].x + a[j][1] * v[rr][j].y + a[j][2] * v[rr][j].z + a[j][3] * v[rr][j].w;
+      }
+    }
+    float bn[SK_ROWS];
+    if (first) {
+#pragma unroll
+      for (int rr = 0; rr < SK_ROWS; ++rr) bn[rr] = 1.f;
+    } else {
+#pragma unroll
+      for (int rr = 0; rr < SK_ROWS; ++rr) {
+        const float w = gx_warp_sum(t[rr]);
+        if (lane == 0) red[buf][rr][warp] = w;
+      }
+      __syncthreads();
+#pragma unroll
+      for (int rr = 0; rr < SK_ROWS; ++rr) {
+        float tot = 0.f;
+#pragma unroll
+        for (int w = 0; w < SK_THREADS / 32; ++w) tot += red[buf][rr][w];
+        const long long row = row0 + rr;
+        const float cn = (row < n) ? (cvec ? cvec[row] : c_uniform) : 0.f;
+        bn[rr] = (row < n) ? cn / tot : 0.f;
+      }
+      buf ^= 1;
+    }
+#pragma unroll
+    for (int rr = 0; rr < SK_ROWS; ++rr) {
+      if (row0 + rr < n) {
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          acc[j][0] = fmaf(v[rr][j].x, bn[rr], acc[j][0]);
+          acc[j][1] = fmaf(v[rr][j].y, bn[rr], acc[j][1]);
+          acc[j][2] = fmaf(v[rr][j].z, bn[rr], acc[j][2]);
+          acc[j][3] = fmaf(v[rr][j].w, bn[rr], acc[j][3]);
+        }
+      }
+    }
+  }
+  float* prow = partials + (long long)blockIdx.x * k;
+#pragma unroll
+  for (int j = 0; j < J; ++j)
+    if (colok[j])
+      *reinterpret_cast<float4*>(prow + j * (SK_THREADS * 4) + tid * 4) =
+          make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+}
+
+__global__ void colsum_parts_kernel(const float* __restrict__ parts, int nparts, int k, float* __restrict__ u) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= k) return;
+  float acc = 0.f;
+  for (int p = 0; p < nparts; ++p) acc += parts[(long long)p * k + col];
+  u[col] = acc;
+}
+
+__global__ void log_a_kernel(const float* __restrict__ u, const float* __restrict__ r, int k,
+                             float* __restrict__ log_a) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col >= k) return;
+  const float rk = r ? r[col] : 1.f / (float)k;
+  log_a[col] = logf(rk / u[col]);
+}
+
+// block-wide reductions of NV values at once (512 threads)
+template <int NV, bool IS_MAX>
+__device__ __forceinline__ void block_reduce(float (&v)[NV], float (*red)[SK_THREADS / 32]) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float w = IS_MAX ? gx_warp_max(v[i]) : gx_warp_sum(v[i]);
+    if (lane == 0) red[i][warp] = w;
+  }
+  __syncthreads();
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float tot = red[i][0];
+#pragma unroll
+    for (int w = 1; w < SK_THREADS / 32; ++w) tot = IS_MAX ? fmaxf(tot, red[i][w]) : tot + red[i][w];
+    v[i] = tot;
+  }
+  __syncthreads();
+}
+
+// Q = softmax_k(S/eps + log_a)  (materialised only for API parity / tests)
+template <int J>
+__global__ void __launch_bounds__(SK_THREADS, 1)
+sinkhorn_q_kernel(const float* __restrict__ s, long long n, int k, long long lds, float inv_eps,
+                  const float* __restrict__ log_a, float* __restrict__ q) {
+  __shared__ float red[1][SK_THREADS / 32];
+  const int tid = threadIdx.x;
+  for (long long row = blockIdx.x; row < n; row += gridDim.x) {
+    float x[J][4];
+    float mx[1] = {-INFINITY};
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int col = j * (SK_THREADS * 4) + tid * 4;
+#pragma unroll
+      for (int e = 0; e < 4; ++e) x[j][e] = -INFINITY;
+      if (col < k) {
+        const float4 v = *reinterpret_cast<const float4*>(s + row * lds + col);
+        const float4 la = __ldg(reinterpret_cast<const float4*>(log_a + col));
+        x[j][0] = fmaf(v.x, inv_eps, la.x); x[j][1] = fmaf(v.y, inv_eps, la.y);
+        x[j][2] = fmaf(v.z, inv_eps, la.z); x[j][3] = fmaf(v.w, inv_eps, la.w);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) mx[0] = fmaxf(mx[0], x[j][e]);
+      }
+    }
+    block_reduce<1, true>(mx, red);
+    float sm[1] = {0.f};
+#pragma unroll
+    for (int j = 0; j < J; ++j)
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        x[j][e] = exp2f((x[j][e] - mx[0]) * LOG2E);
+        sm[0] += x[j][e];
+      }
+    block_reduce<1, false>(sm, red);
+    const float inv = 1.f / sm[0];
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int col = j * (SK_THREADS * 4) + tid * 4;
+      if (col < k)
+        *reinterpret_cast<float4*>(q + row * (long long)k + col) =
+            make_float4(x[j][0] * inv, x[j][1] * inv, x[j][2] * inv, x[j][3] * inv);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// Swapped-prediction loss, forward + d/dS fused; one row pair per block iteration.
+// ---------------------------------------------------------------------------
+template <int J>
+__global__ void __launch_bounds__(SK_THREADS, 1)
+swav_loss_kernel(const float* __restrict__ ss, const float* __restrict__ st, long long n, int k, long long lds,
+                 float inv_eps, float inv_temp, const float* __restrict__ la_s, const float* __restrict__ la_t,
+                 float grad_scale, float* __restrict__ loss_parts, float* __restrict__ db_parts,
+                 __nv_bfloat16* __restrict__ ds_s_hi, __nv_bfloat16* __restrict__ ds_s_lo,
+                 __nv_bfloat16* __restrict__ ds_t_hi, __nv_bfloat16* __restrict__ ds_t_lo, long long ldd,
+                 float* __restrict__ ds_s_f32, float* __restrict__ ds_t_f32) {
+  __shared__ float red[6][SK_THREADS / 32];
+  const int tid = threadIdx.x;
+  float loss_acc = 0.f;
+  float db[J][4];
+#pragma unroll
+  for (int j = 0; j < J; ++j)
+#pragma unroll
+    for (int e = 0; e < 4; ++e) db[j][e] = 0.f;
+  const float gs = grad_scale * 0.5f * inv_temp;
+  for (long long row = blockIdx.x; row < n; row += gridDim.x) {
+    float vs[J][4], vt[J][4];     // raw scores, later softmax(p) numerators
+    float e1s[J][4], e1t[J][4];   // exp(S/eps + log a - max): q numerators
+    float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // max x1_s, max s_s, max x1_t, max s_t
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int col = j * (SK_THREADS * 4) + tid * 4;
+      if (col < k) {
+        const float4 a = gx_ldg_stream(reinterpret_cast<const float4*>(ss + row * lds + col));
+        const float4 b = gx_ldg_stream(reinterpret_cast<const float4*>(st + row * lds + col));
+        const float4 las = __ldg(reinterpret_cast<const float4*>(la_s + col));
+        const float4 lat = __ldg(reinterpret_cast<const float4*>(la_t + col));
+        vs[j][0] = a.x; vs[j][1] = a.y; vs[j][2] = a.z; vs[j][3] = a.w;
+        vt[j][0] = b.x; vt[j][1] = b.y; vt[j][2] = b.z; vt[j][3] = b.w;
+        e1s[j][0] = fmaf(a.x, inv_eps, las.x); e1s[j][1] = fmaf(a.y, inv_eps, las.y);
+        e1s[j][2] = fmaf(a.z, inv_eps, las.z); e1s[j][3] = fmaf(a.w, inv_eps, las.w);
+        e1t[j][0] = fmaf(b.x, inv_eps, lat.x); e1t[j][1] = fmaf(b.y, inv_eps, lat.y);
+        e1t[j][2] = fmaf(b.z, inv_eps, lat.z); e1t[j][3] = fmaf(b.w, inv_eps, lat.w);
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          mx[0] = fmaxf(mx[0], e1s[j][e]); mx[1] = fmaxf(mx[1], vs[j][e]);
+          mx[2] = fmaxf(mx[2], e1t[j][e]); mx[3] = fmaxf(mx[3], vt[j][e]);
+        }
+      } else {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          vs[j][e] = vt[j][e] = -INFINITY;
+          e1s[j][e] = e1t[j][e] = -INFINITY;
+        }
+      }
+    }
+    block_reduce<4, true>(mx, red);
+    // sums: Z1_s, Z2_s, D_st = sum e1s*s_t, Z1_t, Z2_t, D_ts = sum e1t*s_s
+    float sm[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    const float m2s = mx[1] * inv_temp, m2t = mx[3] * inv_temp;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int col = j * (SK_THREADS * 4) + tid * 4;
+      if (col < k) {
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {
+          const float rs = vs[j][e], rt = vt[j][e];
+          e1s[j][e] = exp2f((e1s[j][e] - mx[0]) * LOG2E);
+          e1t[j][e] = exp2f((e1t[j][e] - mx[2]) * LOG2E);
+          sm[0] += e1s[j][e];
+          sm[3] += e1t[j][e];
+          sm[2] = fmaf(e1s[j][e], rt, sm[2]);
+          sm[5] = fmaf(e1t[j][e], rs, sm[5]);
+          vs[j][e] = exp2f((rs * inv_temp - m2s) * LOG2E);
+          vt[j][e] = exp2f((rt * inv_temp - m2t) * LOG2E);
+          sm[1] += vs[j][e];
+          sm[4] += vt[j][e];
+        }
+      }
+    }
+    block_reduce<6, false>(sm, red);
+    const float iz1s = 1.f / sm[0], iz2s = 1.f / sm[1], iz1t = 1.f / sm[3], iz2t = 1.f / sm[4];
+    if (tid == 0) {
+      const float lse_s = m2s + logf(sm[1]), lse_t = m2t + logf(sm[4]);
+      const float qs_pt = sm[2] * iz1s * inv_temp - lse_t;  // sum_k q_s * log_softmax(p_t)
+      const float qt_ps = sm[5] * iz1t * inv_temp - lse_s;
+      loss_acc += -0.5f * (qs_pt + qt_ps);
+    }
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int col = j * (SK_THREADS * 4) + tid * 4;
+      if (col < k) {
+        float4 gs_s, gs_t;  // dL/dS_s uses q_t ; dL/dS_t uses q_s
+        gs_s.x = gs * (vs[j][0] * iz2s - e1t[j][0] * iz1t); gs_s.y = gs * (vs[j][1] * iz2s - e1t[j][1] * iz1t);
+        gs_s.z = gs * (vs[j][2] * iz2s - e1t[j][2] * iz1t); gs_s.w = gs * (vs[j][3] * iz2s - e1t[j][3] * iz1t);
+        gs_t.x = gs * (vt[j][0] * iz2t - e1s[j][0] * iz1s); gs_t.y = gs * (vt[j][1] * iz2t - e1s[j][1] * iz1s);
+        gs_t.z = gs * (vt[j][2] * iz2t - e1s[j][2] * iz1s); gs_t.w = gs * (vt[j][3] * iz2t - e1s[j][3] * iz1s);
+        db[j][0] += gs_s.x + gs_t.x; db[j][1] += gs_s.y + gs_t.y;
+        db[j][2] += gs_s.z + gs_t.z; db[j][3] += gs_s.w + gs_t.w;
+        uint2 h, l;
+        gx_split4(gs_s, h, l);
+        *reinterpret_cast<uint2*>(ds_s_hi + row * ldd + col) = h;
+        if (ds_s_lo) *reinterpret_cast<uint2*>(ds_s_lo + row * ldd + col) = l;
+        gx_split4(gs_t, h, l);
+        *reinterpret_cast<uint2*>(ds_t_hi + row * ldd + col) = h;
+        if (ds_t_lo) *reinterpret_cast<uint2*>(ds_t_lo + row * ldd + col) = l;
+        if (ds_s_f32) *reinterpret_cast<float4*>(ds_s_f32 + row * (long long)k + col) = gs_s;
+        if (ds_t_f32) *reinterpret_cast<float4*>(ds_t_f32 + row * (long long)k + col) = gs_t;
+      }
+    }
+  }
+  if (tid == 0) loss_parts[blockIdx.x] = loss_acc;
+  if (db_parts) {
+    float* prow = db_parts + (long long)blockIdx.x * k;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int col = j * (SK_THREADS * 4) + tid * 4;
+      if (col < k) *reinterpret_cast<float4*>(prow + col) = make_float4(db[j][0], db[j][1], db[j][2], db[j][3]);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
+// LARC + SGD(momentum)
+// ---------------------------------------------------------------------------
+__global__ void sq_norms_kernel(const float* __restrict__ p, const float* __restrict__ g, long long n,
+                                float* __restrict__ norms) {
+  float sp = 0.f, sg = 0.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    sp = fmaf(p[i], p[i], sp);
+    sg = fmaf(g[i], g[i], sg);
+  }
+  sp = gx_warp_sum(sp);
+  sg = gx_warp_sum(sg);
+  __shared__ float rp[8], rg[8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) { rp[warp] = sp; rg[warp] = sg; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    float a = 0.f, b = 0.f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += rp[w]; b += rg[w]; }
+    atomicAdd(norms, a);
+    atomicAdd(norms + 1, b);
+  }
+}
+
+__global__ void larc_sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
+                                long long n, float lr, float momentum, float trust, float wd, float eps, int first,
+                                const float* __restrict__ norms) {
+  const float pn = sqrtf(norms[0]), gn = sqrtf(norms[1]);
+  const bool adapt = (pn != 0.f) && (gn != 0.f);
+  const float alr = adapt ? trust * pn / (gn + pn * wd + eps) : 1.f;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    float gi = g[i];
+    if (adapt) gi = (gi + wd * p[i]) * alr;
+    const float b = first ? gi : momentum * buf[i] + gi;
+    buf[i] = b;
+    p[i] -= lr * b;
+  }
+}
+
+// ---------------------------------------------------------------------------
+// label maps
+// ---------------------------------------------------------------------------
+__global__ void argmax_rows_kernel(const float* __restrict__ x, long long n, int c, long long ldx,
+                                   long long* __restrict__ labels) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float* xr = x + row * ldx;
+  float best = -INFINITY;
+  int bi = 0x7fffffff;
+  for (int i = lane; i < c; i += 32) {
+    const float v = xr[i];
+    if (v > best || (v == best && i < bi)) { best = v; bi = i; }
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (lane == 0) labels[row] = (long long)bi;
+}
+
+__global__ void kmeans_assign_kernel(const float* __restrict__ x, long long n, int c, long long ldx,
+                                     const float* __restrict__ centers, int k, int* __restrict__ labels) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  const float* xr = x + row * ldx;
+  float best = INFINITY;
+  int bi = 0;
+  for (int kk = 0; kk < k; ++kk) {
+    const float* cr = centers + (long long)kk * c;
+    float d = 0.f;
+    for (int i = lane; i < c; i += 32) {
+      const float t = xr[i] - __ldg(cr + i);
+      d = fmaf(t, t, d);
+    }
+    d = gx_warp_sum(d);
+    if (d < best) { best = d; bi = kk; }
+  }
+  if (lane == 0) labels[row] = bi;
+}
+
+inline int sk_grid(long long n, int rows_per_iter) {
+  long long g = (n + rows_per_iter - 1) / rows_per_iter;
+  const int cap = gx_sm_count();
+  return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
+}
+
+}  // namespace
+
+extern "C" int gx_gather_rows(const gx_gather_desc* d, void* stream) {
+  GX_CHECK_ARG(d && d->a_hi && d->nlevels > 0 && d->nlevels <= GX_MAX_LEVELS && d->nrows > 0);
+  GX_CHECK_ARG(d->hlen % 4 == 0 && d->ld % 4 == 0 && d->ld >= d->hlen);
+  GX_CHECK_ARG(d->nrows < (1ll << 31));
+  for (int l = 0; l < d->nlevels; ++l) GX_CHECK_ARG(d->feat[l] && d->c[l] % 4 == 0 && d->h[l] > 0 && d->w[l] > 0);
+  gather_rows_kernel<<<(unsigned)d->nrows, 128, 0, (cudaStream_t)stream>>>(*d);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_l2norm_split(const float* z, void* zn_hi, void* zn_lo, float* inv_norm, long long n, int c,
+                               void* stream) {
+  GX_CHECK_ARG(z && zn_hi && n > 0 && c % 4 == 0);
+  l2norm_split_kernel<<<gx_cdiv(n, 8), 256, 0, (cudaStream_t)stream>>>(
+      z, reinterpret_cast<__nv_bfloat16*>(zn_hi), reinterpret_cast<__nv_bfloat16*>(zn_lo), inv_norm, n, c);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_l2norm_bwd_split(const float* dzn, const void* zn_hi, const void* zn_lo, const float* inv_norm,
+                                   void* dz_hi, void* dz_lo, long long n, int c, void* stream) {
+  GX_CHECK_ARG(dzn && zn_hi && inv_norm && dz_hi && n > 0 && c % 4 == 0);
+  l2norm_bwd_split_kernel<<<gx_cdiv(n, 8), 256, 0, (cudaStream_t)stream>>>(
+      dzn, reinterpret_cast<const __nv_bfloat16*>(zn_hi), reinterpret_cast<const __nv_bfloat16*>(zn_lo), inv_norm,
+      reinterpret_cast<__nv_bfloat16*>(dz_hi), reinterpret_cast<__nv_bfloat16*>(dz_lo), n, c);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_normalize_rows(float* w, long long rows, int cols, void* stream) {
+  GX_CHECK_ARG(w && rows > 0 && cols > 0);
+  normalize_rows_kernel<<<gx_cdiv(rows, 8), 256, 0, (cudaStream_t)stream>>>(w, rows, cols);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_split_planes(const float* x, long long ld, void* hi, void* lo, long long rows, long long cols,
+                               int transpose, void* stream) {
+  GX_CHECK_ARG(x && hi && rows > 0 && cols > 0 && ld >= cols);
+  if (!transpose) {
+    int grid = gx_cdiv(rows * cols, 256);
+    const int cap = gx_sm_count() * 16;
+    if (grid > cap) grid = cap;
+    split_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ld, reinterpret_cast<__nv_bfloat16*>(hi),
+                                                               reinterpret_cast<__nv_bfloat16*>(lo), rows, cols);
+  } else {
+    dim3 grid(gx_cdiv(cols, 32), gx_cdiv(rows, 32));
+    GX_CHECK_ARG(grid.y <= 65535);
+    split_planes_t_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
+        x, ld, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), rows, cols);
+  }
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_sinkhorn_max_parts(void) { return gx_sm_count(); }
+extern "C" int gx_loss_max_parts(void) { return gx_sm_count(); }
+
+#define GX_DISPATCH_J(J_, CALL)          \
+  switch (J_) {                          \
+    case 1: { constexpr int J = 1; CALL; } break; \
+    case 2: { constexpr int J = 2; CALL; } break; \
+    case 3: { constexpr int J = 3; CALL; } break; \
+    case 4: { constexpr int J = 4; CALL; } break; \
+    default: return GX_ERR_ARG;          \
+  }
+
+extern "C" int gx_sinkhorn_pass(const float* s, long long n, int k, long long lds, float inv_eps, int first,
+                                const float* u_in, const float* r, const float* c, long long n_total,
+                                float* partials, int* nparts_out, void* stream) {
+  GX_CHECK_ARG(s && partials && n > 0 && k > 0 && k % 4 == 0 && lds % 4 == 0 && lds >= k);
+  GX_CHECK_ARG(first || u_in);
+  GX_CHECK_ARG((reinterpret_cast<uintptr_t>(s) & 15) == 0);
+  const int jn = gx_cdiv(k, SK_THREADS * 4);
+  const int grid = sk_grid(n, SK_ROWS);
+  if (nparts_out) *nparts_out = grid;
+  const float cu = 1.f / (float)(n_total > 0 ? n_total : n);
+  GX_DISPATCH_J(jn, (sinkhorn_pass_kernel<J><<<grid, SK_THREADS, 0, (cudaStream_t)stream>>>(
+                        s, n, k, lds, inv_eps * LOG2E, first, u_in, r, c, cu, partials)));
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_sinkhorn_reduce(const float* partials, int nparts, int k, float* u, void* stream) {
+  GX_CHECK_ARG(partials && u && nparts > 0 && k > 0);
+  colsum_parts_kernel<<<gx_cdiv(k, 256), 256, 0, (cudaStream_t)stream>>>(partials, nparts, k, u);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_sinkhorn_log_a(const float* u, const float* r, int k, float* log_a, void* stream) {
+  GX_CHECK_ARG(u && log_a && k > 0);
+  log_a_kernel<<<gx_cdiv(k, 256), 256, 0, (cudaStream_t)stream>>>(u, r, k, log_a);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_sinkhorn_q(const float* s, long long n, int k, long long lds, float inv_eps, const float* log_a,
+                             float* q, void* stream) {
+  GX_CHECK_ARG(s && log_a && q && n > 0 && k > 0 && k % 4 == 0 && lds % 4 == 0);
+  const int jn = gx_cdiv(k, SK_THREADS * 4);
+  const int grid = sk_grid(n, 1);
+  GX_DISPATCH_J(jn, (sinkhorn_q_kernel<J><<<grid, SK_THREADS, 0, (cudaStream_t)stream>>>(s, n, k, lds, inv_eps,
+                                                                                      log_a, q)));
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_swav_loss(const float* s_s, const float* s_t, long long n, int k, long long lds, float inv_eps,
+                            float inv_temp, const float* log_a_s, const float* log_a_t, float grad_scale,
+                            float* loss_parts, float* db_parts, int* nparts_out, void* ds_s_hi, void* ds_s_lo,
+                            void* ds_t_hi, void* ds_t_lo, long long ldd, float* ds_s_f32, float* ds_t_f32,
+                            void* stream) {
+  GX_CHECK_ARG(s_s && s_t && log_a_s && log_a_t && loss_parts && ds_s_hi && ds_t_hi);
+  GX_CHECK_ARG(n > 0 && k > 0 && k % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ldd >= k);
+  const int jn = gx_cdiv(k, SK_THREADS * 4);
+  const int grid = sk_grid(n, 1);
+  if (nparts_out) *nparts_out = grid;
+  GX_DISPATCH_J(jn, (swav_loss_kernel<J><<<grid, SK_THREADS, 0, (cudaStream_t)stream>>>(
+                        s_s, s_t, n, k, lds, inv_eps, inv_temp, log_a_s, log_a_t, grad_scale, loss_parts, db_parts,
+                        reinterpret_cast<__nv_bfloat16*>(ds_s_hi), reinterpret_cast<__nv_bfloat16*>(ds_s_lo),
+                        reinterpret_cast<__nv_bfloat16*>(ds_t_hi), reinterpret_cast<__nv_bfloat16*>(ds_t_lo), ldd,
+                        ds_s_f32, ds_t_f32)));
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_larc_sgd(float* p, const float* g, float* buf, long long n, float lr, float momentum, float trust,
+                           float weight_decay, float eps, int first_step, float* norms, void* stream) {
+  GX_CHECK_ARG(p && g && buf && norms && n > 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  GX_CHECK_CUDA(cudaMemsetAsync(norms, 0, 2 * sizeof(float), st));
+  int grid = gx_cdiv(n, 256 * 8);
+  const int cap = gx_sm_count() * 4;
+  if (grid > cap) grid = cap;
+  if (grid < 1) grid = 1;
+  sq_norms_kernel<<<grid, 256, 0, st>>>(p, g, n, norms);
+  GX_LAUNCH_CHECK();
+  larc_sgd_kernel<<<grid, 256, 0, st>>>(p, g, buf, n, lr, momentum, trust, weight_decay, eps, first_step, norms);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_argmax_rows(const float* x, long long n, int c, long long ldx, long long* labels, void* stream) {
+  GX_CHECK_ARG(x && labels && n > 0 && c > 0);
+  argmax_rows_kernel<<<gx_cdiv(n, 8), 256, 0, (cudaStream_t)stream>>>(x, n, c, ldx, labels);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_kmeans_assign(const float* x, long long n, int c, long long ldx, const float* centers, int k,
+                                int* labels, void* stream) {
+  GX_CHECK_ARG(x && centers && labels && n > 0 && c > 0 && k > 0);
+  kmeans_assign_kernel<<<gx_cdiv(n, 8), 256, 0, (cudaStream_t)stream>>>(x, n, c, ldx, centers, k, labels);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}

@@ -1,0 +1,663 @@
+// tcgen05 / TMEM / TMA contraction engine for sm_100a.
+//
+// One persistent, warp-specialised kernel serves every dense contraction on the path:
+//   * gx_gemm    : C[M,N] = A * B^T (+bias), A/B as bf16 planes (K- or MN-major), split-K
+//                  -> projection / prototype scores / their gradient GEMMs
+//   * gx_modconv : modulated 3x3 conv (plain, or transposed stride 2 as 4 sub-pixel
+//                  phases) as implicit GEMM: the A tile of a tap is ONE 4-D TMA box of
+//                  the NHWC activation shifted by the tap offset; TMA's out-of-bounds
+//                  zero fill is the conv padding.
+// Roles (256 threads, 1 CTA / SM): warp 0 = TMA producer, warp 1 = MMA issuer,
+// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> global).
+// Pipelines: smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring
+// (tmem_full/tmem_empty) so the epilogue of tile i overlaps the MMAs of tile i+1.
+// Precision: passes == 3 issues A_lo*B_hi + A_hi*B_lo + A_hi*B_hi into the same fp32
+// accumulator (split-bf16, ~2^-16 relative per product); passes == 1 is plain bf16.
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
+#include "gx_common.cuh"
+#include "gx_ptx.cuh"
+
+using namespace gxptx;
+
+namespace {
+
+constexpr int BM = 128;
+constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle atom
+constexpr int A_PLANE_BYTES = BM * BK * 2;
+constexpr int MAX_STAGES = 8;
+constexpr int NTHREADS = 256;
+constexpr int TMEM_COLS = 512;
+constexpr int SMEM_LIMIT = 227 * 1024;
+
+struct UmmaParams {
+  int mode;  // 0 = gemm, 1 = conv
+  int passes, block_n, stages;
+  int a_mn, b_mn;
+  // ---- gemm
+  int M, N, K;
+  int tiles_m, tiles_n, split_k, kiters_total;
+  float* c;
+  long long ldc;
+  const float* bias;
+  int atomic;
+  // ---- conv
+  int B, H, W, Cin, Cout, upsample;
+  int th, tw, nb;
+  int Ho, Wo;
+  int nphases;
+  int phase_tile_start[5];
+  int phase_ty[4], phase_tx[4], phase_eh[4], phase_ew[4], phase_a[4], phase_b[4];
+  int ntaps[4];
+  signed char tap_dy[4][9], tap_dx[4][9], tap_w[4][9];
+  const float* demod;
+  const float* noise;
+  long long noise_bstride;
+  const float* noise_strength;
+  int act;
+  float* out;
+  const float* next_style;
+  __nv_bfloat16* next_hi;
+  __nv_bfloat16* next_lo;
+};
+
+struct TileInfo {
+  // gemm
+  int m0, n0, kbeg, kend;
+  // conv
+  int phase, b0, y0, x0;
+};
+
+__device__ __forceinline__ TileInfo decode_tile(const UmmaParams& p, int w) {
+  TileInfo t;
+  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int split = w / tiles_mn;
+  const int tmn = w - split * tiles_mn;
+  const int tile_n = tmn % p.tiles_n;
+  const int tile_m = tmn / p.tiles_n;
+  t.n0 = tile_n * p.block_n;
+  t.m0 = tile_m * BM;
+  t.phase = 0; t.b0 = 0; t.y0 = 0; t.x0 = 0;
+  if (p.mode == 0) {
+    const int per = (p.kiters_total + p.split_k - 1) / p.split_k;
+    t.kbeg = split * per;
+    t.kend = min(p.kiters_total, t.kbeg + per);
+  } else {
+    int ph = 0;
+    while (ph + 1 < p.nphases && tile_m >= p.phase_tile_start[ph + 1]) ++ph;
+    int r = tile_m - p.phase_tile_start[ph];
+    const int tx = r % p.phase_tx[ph];
+    r /= p.phase_tx[ph];
+    const int ty = r % p.phase_ty[ph];
+    const int g = r / p.phase_ty[ph];
+    t.phase = ph;
+    t.b0 = g * p.nb;
+    t.y0 = ty * p.th;
+    t.x0 = tx * p.tw;
+    t.kbeg = 0;
+    t.kend = p.ntaps[ph] * (p.Cin / BK);
+  }
+  return t;
+}
+
+__device__ __forceinline__ float lrelu_sqrt2(float v) {
+  return (v > 0.f ? v : v * 0.2f) * 1.41421356237309515f;
+}
+
+__global__ void __launch_bounds__(NTHREADS, 1)
+gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
+               const __grid_constant__ CUtensorMap tm_a_lo, const __grid_constant__ CUtensorMap tm_b_hi,
+               const __grid_constant__ CUtensorMap tm_b_lo, int total_work) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  // carve (stage buffers must be 1024-aligned for the 128B swizzle)
+  uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
+  const int b_plane_bytes = p.block_n * BK * 2;
+  const int nplanes = (p.passes == 3) ? 2 : 1;
+  const int stage_bytes = nplanes * (A_PLANE_BYTES + b_plane_bytes);
+  uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
+  uint64_t* full_bar = bars;
+  uint64_t* empty_bar = bars + MAX_STAGES;
+  uint64_t* tfull_bar = bars + 2 * MAX_STAGES;
+  uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 2;
+  uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+
+  const int warp = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+
+  if (warp == 0 && lane == 0) {
+    prefetch_tmap(&tm_a_hi);
+    prefetch_tmap(&tm_b_hi);
+    if (p.passes == 3) {
+      prefetch_tmap(&tm_a_lo);
+      prefetch_tmap(&tm_b_lo);
+    }
+  }
+  if (warp == 1 && lane == 0) {
+    for (int i = 0; i < p.stages; ++i) {
+      mbar_init(&full_bar[i], 1);
+      mbar_init(&empty_bar[i], 1);
+    }
+    for (int i = 0; i < 2; ++i) {
+      mbar_init(&tfull_bar[i], 1);
+      mbar_init(&tempty_bar[i], 4);
+    }
+    fence_mbar_init();
+  }
+  if (warp == 2) {
+    tmem_alloc(tmem_slot, TMEM_COLS);
+    tmem_relinquish();
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  if (warp == 0) {
+    // ============================== TMA producer ==============================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const int cblocks = (p.mode == 1) ? p.Cin / BK : 1;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
+        const TileInfo t = decode_tile(p, w);
+        for (int kit = t.kbeg; kit < t.kend; ++kit) {
+          mbar_wait(&empty_bar[stage], phase ^ 1);
+          uint8_t* sa = smem + stage * stage_bytes;
+          uint8_t* sb = sa + nplanes * A_PLANE_BYTES;
+          mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
+          for (int pl = 0; pl < nplanes; ++pl) {
+            const CUtensorMap* ma = pl ? &tm_a_lo : &tm_a_hi;
+            const CUtensorMap* mb = pl ? &tm_b_lo : &tm_b_hi;
+            uint8_t* da = sa + pl * A_PLANE_BYTES;
+            uint8_t* db = sb + pl * b_plane_bytes;
+            if (p.mode == 0) {
+              const int k0 = kit * BK;
+              if (!p.a_mn) {
+                tma_load_2d(da, ma, &full_bar[stage], k0, t.m0);
+              } else {
+                tma_load_2d(da, ma, &full_bar[stage], t.m0, k0);
+                tma_load_2d(da + 8192, ma, &full_bar[stage], t.m0 + 64, k0);
+              }
+              if (!p.b_mn) {
+                tma_load_2d(db, mb, &full_bar[stage], k0, t.n0);
+              } else {
+                for (int i = 0; i < p.block_n / 64; ++i)
+                  tma_load_2d(db + i * 8192, mb, &full_bar[stage], t.n0 + i * 64, k0);
+              }
+            } else {
+              const int tap = kit / cblocks;
+              const int c0 = (kit - tap * cblocks) * BK;
+              const int dy = p.tap_dy[t.phase][tap], dx = p.tap_dx[t.phase][tap];
+              const int wk = p.tap_w[t.phase][tap];
+              tma_load_4d(da, ma, &full_bar[stage], c0, t.x0 + dx, t.y0 + dy, t.b0);
+              tma_load_2d(db, mb, &full_bar[stage], wk * p.Cin + c0, t.n0);
+            }
+          }
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ============================== MMA issuer ================================
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      const uint32_t idesc = make_idesc_bf16(BM, p.block_n, p.a_mn, p.b_mn);
+      const uint32_t a_lbo = p.a_mn ? 8192u : 0u, b_lbo = p.b_mn ? 8192u : 0u;
+      const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
+      int it = 0;
+      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+        const TileInfo t = decode_tile(p, w);
+        const int acc = it & 1;
+        const uint32_t acc_phase = (it >> 1) & 1;
+        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
+        uint32_t accumulate = 0;
+        for (int kit = t.kbeg; kit < t.kend; ++kit) {
+          mbar_wait(&full_bar[stage], phase);
+          tc_fence_after();
+          const uint32_t sa = smem_u32(smem + stage * stage_bytes);
+          const uint32_t sb = sa + nplanes * A_PLANE_BYTES;
+          for (int ps = 0; ps < p.passes; ++ps) {
+            // passes==3: (A_lo,B_hi) (A_hi,B_lo) (A_hi,B_hi); passes==1: (A_hi,B_hi)
+            const int apl = (p.passes == 3 && ps == 0) ? 1 : 0;
+            const int bpl = (p.passes == 3 && ps == 1) ? 1 : 0;
+            const uint32_t abase = sa + apl * A_PLANE_BYTES;
+            const uint32_t bbase = sb + bpl * b_plane_bytes;
+#pragma unroll
+            for (int k4 = 0; k4 < BK / 16; ++k4) {
+              const uint64_t adesc = make_smem_desc(abase + k4 * a_kstep, a_lbo, 1024u);
+              const uint64_t bdesc = make_smem_desc(bbase + k4 * b_kstep, b_lbo, 1024u);
+              umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+              accumulate = 1;
+            }
+          }
+          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          if (++stage == p.stages) { stage = 0; phase ^= 1; }
+        }
+        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+      }
+    }
+  } else if (warp >= 4) {
+    // ============================== epilogue ==================================
+    const int q = warp & 3;             // TMEM lane quarter owned by this warp
+    const int row = q * 32 + lane;      // tile row == TMEM lane
+    int it = 0;
+    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
+      const TileInfo t = decode_tile(p, w);
+      const int acc = it & 1;
+      const uint32_t acc_phase = (it >> 1) & 1;
+      mbar_wait(&tfull_bar[acc], acc_phase);
+      tc_fence_after();
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
+      const int nchunks = p.block_n / 32;
+
+      if (p.mode == 0) {
+        const long long m = (long long)t.m0 + row;
+        const bool mvalid = m < p.M;
+        float* crow = p.c + m * p.ldc;
+        const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
+        const bool add_bias = p.bias != nullptr && (!p.atomic || t.kbeg == 0);
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const int n_base = t.n0 + ch * 32;
+          if (n_base >= p.N) break;  // warp-uniform
+          uint32_t r[32];
+          tmem_ld_32x32(taddr0 + ch * 32, r);
+          tmem_ld_wait();
+          if (!mvalid) continue;
+          if (add_bias) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n_base + i < p.N) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(p.bias + n_base + i));
+          }
+          if (p.atomic) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n_base + i < p.N) atomicAdd(crow + n_base + i, __uint_as_float(r[i]));
+          } else if (vec_ok && n_base + 32 <= p.N) {
+            float4* dst = reinterpret_cast<float4*>(crow + n_base);
+#pragma unroll
+            for (int i = 0; i < 8; ++i)
+              dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
+                                   __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
+          } else {
+#pragma unroll
+            for (int i = 0; i < 32; ++i)
+              if (n_base + i < p.N) crow[n_base + i] = __uint_as_float(r[i]);
+          }
+        }
+      } else {
+        const int ph = t.phase;
+        const int per_img = p.th * p.tw;
+        const int bi = row / per_img;
+        const int rem = row - bi * per_img;
+        const int iy = rem / p.tw, ix = rem - iy * p.tw;
+        const int b = t.b0 + bi, i = t.y0 + iy, j = t.x0 + ix;
+        const bool valid = (b < p.B) && (i < p.phase_eh[ph]) && (j < p.phase_ew[ph]);
+        const int oy = p.upsample ? 2 * i + p.phase_a[ph] : i;
+        const int ox = p.upsample ? 2 * j + p.phase_b[ph] : j;
+        const long long pix = valid ? ((long long)b * p.Ho + oy) * p.Wo + ox : 0;
+        float nz = 0.f;
+        if (valid && p.noise != nullptr)
+          nz = __ldg(p.noise_strength) * __ldg(p.noise + (long long)b * p.noise_bstride + (long long)oy * p.Wo + ox);
+        for (int ch = 0; ch < nchunks; ++ch) {
+          const int co = t.n0 + ch * 32;
+          if (co >= p.Cout) break;
+          uint32_t r[32];
+          tmem_ld_32x32(taddr0 + ch * 32, r);
+          tmem_ld_wait();
+          if (!valid) continue;
+          float v[32];
+#pragma unroll
+          for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+          if (p.demod != nullptr) {
+            const float4* dm = reinterpret_cast<const float4*>(p.demod + (long long)b * p.Cout + co);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 d4 = __ldg(dm + e);
+              v[4 * e] *= d4.x; v[4 * e + 1] *= d4.y; v[4 * e + 2] *= d4.z; v[4 * e + 3] *= d4.w;
+            }
+          }
+          if (p.noise != nullptr) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] += nz;
+          }
+          if (p.bias != nullptr) {
+            const float4* bs = reinterpret_cast<const float4*>(p.bias + co);
+#pragma unroll
+            for (int e = 0; e < 8; ++e) {
+              const float4 b4 = __ldg(bs + e);
+              v[4 * e] += b4.x; v[4 * e + 1] += b4.y; v[4 * e + 2] += b4.z; v[4 * e + 3] += b4.w;
+            }
+          }
+          if (p.act) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = lrelu_sqrt2(v[e]);
+          }
+          float4* dst = reinterpret_cast<float4*>(p.out + pix * p.Cout + co);
+#pragma unroll
+          for (int e = 0; e < 8; ++e) dst[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+          if (p.next_style != nullptr) {
+            const float4* st = reinterpret_cast<const float4*>(p.next_style + (long long)b * p.Cout + co);
+            uint4* dh = reinterpret_cast<uint4*>(p.next_hi + pix * p.Cout + co);
+            uint4* dl = (p.next_lo != nullptr) ? reinterpret_cast<uint4*>(p.next_lo + pix * p.Cout + co) : nullptr;
+#pragma unroll
+            for (int e = 0; e < 4; ++e) {
+              const float4 s0 = __ldg(st + 2 * e), s1 = __ldg(st + 2 * e + 1);
+              uint2 h0, l0, h1, l1;
+              gx_split4(make_float4(v[8 * e] * s0.x, v[8 * e + 1] * s0.y, v[8 * e + 2] * s0.z, v[8 * e + 3] * s0.w),
+                        h0, l0);
+              gx_split4(make_float4(v[8 * e + 4] * s1.x, v[8 * e + 5] * s1.y, v[8 * e + 6] * s1.z,
+                                    v[8 * e + 7] * s1.w),
+                        h1, l1);
+              dh[e] = make_uint4(h0.x, h0.y, h1.x, h1.y);
+              if (dl != nullptr) dl[e] = make_uint4(l0.x, l0.y, l1.x, l1.y);
+            }
+          }
+        }
+      }
+      // release the accumulator stage
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+    }
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  if (warp == 2) {
+    tc_fence_after();
+    tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// ------------------------------------------------------------------ host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+EncodeTiledFn get_encode() {
+  static EncodeTiledFn fn = nullptr;
+  if (fn) return fn;
+  void* ptr = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+      qres != cudaDriverEntryPointSuccess)
+    return nullptr;
+  fn = reinterpret_cast<EncodeTiledFn>(ptr);
+  return fn;
+}
+
+// bf16 tensor, dims listed innermost first; strides in elements for dims 1..rank-1
+int make_tmap(CUtensorMap* m, const void* base, int rank, const unsigned long long* dims,
+              const unsigned long long* strides_elems, const unsigned* box) {
+  EncodeTiledFn enc = get_encode();
+  if (!enc) return GX_ERR_CUDA;
+  cuuint64_t gdim[5], gstr[4];
+  cuuint32_t bx[5], es[5];
+  for (int i = 0; i < rank; ++i) {
+    gdim[i] = dims[i];
+    bx[i] = box[i];
+    es[i] = 1;
+  }
+  for (int i = 0; i + 1 < rank; ++i) gstr[i] = strides_elems[i] * 2ull;
+  if (reinterpret_cast<uintptr_t>(base) & 15) return GX_ERR_ARG;
+  for (int i = 0; i + 1 < rank; ++i)
+    if (gstr[i] & 15) return GX_ERR_ARG;
+  CUresult r = enc(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, (cuuint32_t)rank, const_cast<void*>(base), gdim, gstr, bx, es,
+                   CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                   CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) {
+    gx_set_last_cuda_error(1000 + (int)r);
+    return GX_ERR_CUDA;
+  }
+  return GX_OK;
+}
+
+int pick_stages(int passes, int block_n, int want) {
+  const int nplanes = passes == 3 ? 2 : 1;
+  const int stage_bytes = nplanes * (A_PLANE_BYTES + block_n * BK * 2);
+  const int avail = SMEM_LIMIT - 1024 /*align slack*/ - 256 /*barriers*/;
+  int s = avail / stage_bytes;
+  if (s > MAX_STAGES) s = MAX_STAGES;
+  if (want > 0 && want < s) s = want;
+  return s;
+}
+
+int launch(const UmmaParams& p, const CUtensorMap* maps, int total_work, cudaStream_t st) {
+  const int nplanes = p.passes == 3 ? 2 : 1;
+  const int stage_bytes = nplanes * (A_PLANE_BYTES + p.block_n * BK * 2);
+  const int smem_bytes = p.stages * stage_bytes + 256 + 1024;
+  static bool attr_set = false;
+  if (!attr_set) {
+    GX_CHECK_CUDA(cudaFuncSetAttribute(gx_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    attr_set = true;
+  }
+  int grid = gx_sm_count();
+  if (grid > total_work) grid = total_work;
+  if (grid < 1) return GX_OK;
+  gx_umma_kernel<<<grid, NTHREADS, smem_bytes, st>>>(p, maps[0], maps[1], maps[2], maps[3], total_work);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+}  // namespace
+
+extern "C" int gx_gemm(const gx_gemm_desc* d, void* stream) {
+  GX_CHECK_ARG(d != nullptr && d->a_hi && d->b_hi && d->c);
+  GX_CHECK_ARG(d->m > 0 && d->n > 0 && d->k > 0);
+  GX_CHECK_ARG(d->passes == 1 || d->passes == 3);
+  GX_CHECK_ARG(d->passes == 1 || (d->a_lo && d->b_lo));
+  UmmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = 0;
+  p.passes = d->passes;
+  p.a_mn = d->a_mn_major ? 1 : 0;
+  p.b_mn = d->b_mn_major ? 1 : 0;
+  p.M = d->m; p.N = d->n; p.K = d->k;
+  int bn = d->block_n;
+  if (bn == 0) bn = (d->n > 128) ? 256 : 128;
+  GX_CHECK_ARG(bn == 64 || bn == 128 || bn == 256);
+  p.block_n = bn;
+  p.stages = pick_stages(p.passes, bn, d->stages);
+  GX_CHECK_ARG(p.stages >= 2);
+  p.tiles_m = gx_cdiv(d->m, BM);
+  p.tiles_n = gx_cdiv(d->n, bn);
+  p.kiters_total = gx_cdiv(d->k, BK);
+  int sk = d->split_k < 1 ? 1 : d->split_k;
+  if (sk > p.kiters_total) sk = p.kiters_total;
+  // every split must own at least one k-iteration
+  while (sk > 1 && (long long)(sk - 1) * gx_cdiv(p.kiters_total, sk) >= p.kiters_total) --sk;
+  p.split_k = sk;
+  p.atomic = (sk > 1 || d->accumulate) ? 1 : 0;
+  p.c = d->c; p.ldc = d->ldc; p.bias = d->bias;
+
+  CUtensorMap maps[4];
+  memset(maps, 0, sizeof(maps));
+  const void* aptr[2] = {d->a_hi, d->a_lo};
+  const void* bptr[2] = {d->b_hi, d->b_lo};
+  const int nplanes = p.passes == 3 ? 2 : 1;
+  for (int pl = 0; pl < nplanes; ++pl) {
+    int rc;
+    if (!p.a_mn) {
+      unsigned long long dims[2] = {(unsigned long long)d->k, (unsigned long long)d->m};
+      unsigned long long str[1] = {(unsigned long long)d->lda};
+      unsigned box[2] = {BK, BM};
+      rc = make_tmap(&maps[pl], aptr[pl], 2, dims, str, box);
+    } else {
+      unsigned long long dims[2] = {(unsigned long long)d->m, (unsigned long long)d->k};
+      unsigned long long str[1] = {(unsigned long long)d->lda};
+      unsigned box[2] = {64, BK};
+      rc = make_tmap(&maps[pl], aptr[pl], 2, dims, str, box);
+    }
+    if (rc != GX_OK) return rc;
+    if (!p.b_mn) {
+      unsigned long long dims[2] = {(unsigned long long)d->k, (unsigned long long)d->n};
+      unsigned long long str[1] = {(unsigned long long)d->ldb};
+      unsigned box[2] = {BK, (unsigned)bn};
+      rc = make_tmap(&maps[2 + pl], bptr[pl], 2, dims, str, box);
+    } else {
+      unsigned long long dims[2] = {(unsigned long long)d->n, (unsigned long long)d->k};
+      unsigned long long str[1] = {(unsigned long long)d->ldb};
+      unsigned box[2] = {64, BK};
+      rc = make_tmap(&maps[2 + pl], bptr[pl], 2, dims, str, box);
+    }
+    if (rc != GX_OK) return rc;
+  }
+  if (nplanes == 1) {
+    maps[1] = maps[0];
+    maps[3] = maps[2];
+  }
+  const int total = p.tiles_m * p.tiles_n * p.split_k;
+  return launch(p, maps, total, (cudaStream_t)stream);
+}
+
+extern "C" int gx_modconv(const gx_conv_desc* d, void* stream) {
+  GX_CHECK_ARG(d != nullptr && d->x_hi && d->w_hi && d->out);
+  GX_CHECK_ARG(d->passes == 1 || d->passes == 3);
+  GX_CHECK_ARG(d->passes == 1 || (d->x_lo && d->w_lo));
+  GX_CHECK_ARG(d->batch > 0 && d->h > 0 && d->w > 0);
+  GX_CHECK_ARG(d->cin % BK == 0 && d->cout % 32 == 0);
+  GX_CHECK_ARG(d->next_style == nullptr || d->next_hi != nullptr);
+  UmmaParams p;
+  memset(&p, 0, sizeof(p));
+  p.mode = 1;
+  p.passes = d->passes;
+  p.B = d->batch; p.H = d->h; p.W = d->w; p.Cin = d->cin; p.Cout = d->cout;
+  p.upsample = d->upsample ? 1 : 0;
+  int bn = d->block_n;
+  if (bn == 0) bn = (d->cout >= 256) ? 256 : 128;
+  if (bn > d->cout) bn = (d->cout >= 128) ? 128 : 64;
+  GX_CHECK_ARG(bn == 64 || bn == 128 || bn == 256);
+  GX_CHECK_ARG(d->cout % 32 == 0);
+  p.block_n = bn;
+  p.stages = pick_stages(p.passes, bn, d->stages);
+  GX_CHECK_ARG(p.stages >= 2);
+  // pixel tile: 128 rows = nb images x th x tw
+  const int ext_w = p.upsample ? d->w + 1 : d->w;
+  const int ext_h = p.upsample ? d->h + 1 : d->h;
+  int tw = 16, th = 8, nb = 1;
+  if (ext_w <= 4 && ext_h <= 4) { tw = 4; th = 4; nb = 8; }
+  else if (ext_w <= 8 && ext_h <= 8) { tw = 8; th = 8; nb = 2; }
+  else if (ext_w <= 8) { tw = 8; th = 16; nb = 1; }
+  p.tw = tw; p.th = th; p.nb = nb;
+  p.Ho = p.upsample ? 2 * d->h + 1 : d->h;
+  p.Wo = p.upsample ? 2 * d->w + 1 : d->w;
+  const int groups = gx_cdiv(d->batch, nb);
+  if (!p.upsample) {
+    p.nphases = 1;
+    p.phase_eh[0] = d->h; p.phase_ew[0] = d->w;
+    p.phase_ty[0] = gx_cdiv(d->h, th); p.phase_tx[0] = gx_cdiv(d->w, tw);
+    p.ntaps[0] = 9;
+    for (int ky = 0; ky < 3; ++ky)
+      for (int kx = 0; kx < 3; ++kx) {
+        const int tpi = ky * 3 + kx;
+        p.tap_dy[0][tpi] = (signed char)(ky - 1);
+        p.tap_dx[0][tpi] = (signed char)(kx - 1);
+        p.tap_w[0][tpi] = (signed char)tpi;
+      }
+    p.phase_tile_start[0] = 0;
+    p.phase_tile_start[1] = groups * p.phase_ty[0] * p.phase_tx[0];
+  } else {
+    // out[2i+a, 2j+b] = sum over taps (ky,kx) with ky%2==a, kx%2==b of x[i-ky/2, j-kx/2] * w[ky,kx]
+    p.nphases = 4;
+    int start = 0;
+    for (int ph = 0; ph < 4; ++ph) {
+      const int a = ph >> 1, b = ph & 1;
+      p.phase_a[ph] = a; p.phase_b[ph] = b;
+      p.phase_eh[ph] = a ? d->h : d->h + 1;
+      p.phase_ew[ph] = b ? d->w : d->w + 1;
+      p.phase_ty[ph] = gx_cdiv(p.phase_eh[ph], th);
+      p.phase_tx[ph] = gx_cdiv(p.phase_ew[ph], tw);
+      int nt = 0;
+      for (int ky = a; ky < 3; ky += 2)
+        for (int kx = b; kx < 3; kx += 2) {
+          p.tap_dy[ph][nt] = (signed char)(-(ky / 2));
+          p.tap_dx[ph][nt] = (signed char)(-(kx / 2));
+          p.tap_w[ph][nt] = (signed char)(ky * 3 + kx);
+          ++nt;
+        }
+      p.ntaps[ph] = nt;
+      p.phase_tile_start[ph] = start;
+      start += groups * p.phase_ty[ph] * p.phase_tx[ph];
+    }
+    p.phase_tile_start[4] = start;
+  }
+  p.tiles_m = p.phase_tile_start[p.nphases];
+  p.tiles_n = gx_cdiv(d->cout, bn);
+  p.split_k = 1;
+  p.demod = d->demod; p.noise = d->noise; p.noise_bstride = d->noise_batch_stride;
+  p.noise_strength = d->noise_strength; p.bias = d->bias; p.act = d->act;
+  GX_CHECK_ARG(d->noise == nullptr || d->noise_strength != nullptr);
+  p.out = d->out; p.next_style = d->next_style;
+  p.next_hi = reinterpret_cast<__nv_bfloat16*>(d->next_hi);
+  p.next_lo = reinterpret_cast<__nv_bfloat16*>(d->next_lo);
+
+  CUtensorMap maps[4];
+  memset(maps, 0, sizeof(maps));
+  const void* xptr[2] = {d->x_hi, d->x_lo};
+  const void* wptr[2] = {d->w_hi, d->w_lo};
+  const int nplanes = p.passes == 3 ? 2 : 1;
+  for (int pl = 0; pl < nplanes; ++pl) {
+    unsigned long long dims[4] = {(unsigned long long)d->cin, (unsigned long long)d->w, (unsigned long long)d->h,
+                                  (unsigned long long)d->batch};
+    unsigned long long str[3] = {(unsigned long long)d->cin, (unsigned long long)d->cin * d->w,
+                                 (unsigned long long)d->cin * d->w * d->h};
+    unsigned box[4] = {BK, (unsigned)tw, (unsigned)th, (unsigned)nb};
+    // a box may not exceed the tensor extent in TMA encoding only through its
+    // dimension limit of 256; partial boxes are zero-filled
+    int rc = make_tmap(&maps[pl], xptr[pl], 4, dims, str, box);
+    if (rc != GX_OK) return rc;
+    unsigned long long wd[2] = {(unsigned long long)9 * d->cin, (unsigned long long)d->cout};
+    unsigned long long ws[1] = {(unsigned long long)9 * d->cin};
+    unsigned wb[2] = {BK, (unsigned)bn};
+    rc = make_tmap(&maps[2 + pl], wptr[pl], 2, wd, ws, wb);
+    if (rc != GX_OK) return rc;
+  }
+  if (nplanes == 1) {
+    maps[1] = maps[0];
+    maps[3] = maps[2];
+  }
+  const int total = p.tiles_m * p.tiles_n;
+  return launch(p, maps, total, (cudaStream_t)stream);
+}
+
+// --------------------------------------------------------------------------
+// fp32 SIMT cross-check GEMM on the same planes (tests only)
+// --------------------------------------------------------------------------
+namespace {
+__device__ __forceinline__ float plane_val(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long idx) {
+  float v = __bfloat162float(hi[idx]);
+  if (lo) v += __bfloat162float(lo[idx]);
+  return v;
+}
+__global__ void gemm_check_kernel(const __nv_bfloat16* ah, const __nv_bfloat16* al, const __nv_bfloat16* bh,
+                                  const __nv_bfloat16* bl, long long lda, long long ldb, int a_mn, int b_mn, int M,
+                                  int N, int K, float* c, long long ldc, const float* bias) {
+  const int n = blockIdx.x * blockDim.x + threadIdx.x;
+  const int m = blockIdx.y;
+  if (n >= N || m >= M) return;
+  float acc = 0.f;
+  for (int k = 0; k < K; ++k) {
+    const long long ia = a_mn ? (long long)k * lda + m : (long long)m * lda + k;
+    const long long ib = b_mn ? (long long)k * ldb + n : (long long)n * ldb + k;
+    acc = fmaf(plane_val(ah, al, ia), plane_val(bh, bl, ib), acc);
+  }
+  if (bias) acc += bias[n];
+  c[(long long)m * ldc + n] = acc;
+}
+}  // namespace
+
+extern "C" int gx_gemm_check(const gx_gemm_desc* d, void* stream) {
+  GX_CHECK_ARG(d != nullptr && d->a_hi && d->b_hi && d->c);
+  dim3 grid(gx_cdiv(d->n, 128), d->m);
+  gemm_check_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
+      (const __nv_bfloat16*)d->a_hi, d->passes == 3 ? (const __nv_bfloat16*)d->a_lo : nullptr,
+      (const __nv_bfloat16*)d->b_hi, d->passes == 3 ? (const __nv_bfloat16*)d->b_lo : nullptr, d->lda, d->ldb,
+      d->a_mn_major, d->b_mn_major, d->m, d->n, d->k, d->c, d->ldc, d->bias);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}

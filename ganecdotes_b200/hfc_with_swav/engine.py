@@ -1,0 +1,326 @@
+"""Fused SwAV engine: the batched / sharded hot path behind `SwAVClustering`.
+
+One optimiser step (ref hfc_with_swav/swav_clustering.py:320-460) for a batch of B
+latents on this rank (joint-batch = SwAV "distributed Sinkhorn" semantics; B = 1 on one
+rank is exactly the reference):
+
+  w = style(z)                                   mapping MLP kernels
+  per view:  W+ with two perturbed rows, double truncation        (ref :593-640, aug:42-53,75-79)
+             synthesis (tcgen05 implicit-GEMM convs, fused FIR)   -> 13 NHWC feature maps
+  per patch: gather(rotate+flip+sample+upsample+concat)           -> A [B*N, hlen]  (bf16 planes)
+             Z = A Wp^T ; Zn = Z/|Z| ; S = Zn Wk^T + b            (tcgen05 GEMMs)
+             Sinkhorn: niters streaming passes over S, only the K-vector of column
+                       marginals is exchanged (all-reduce over ranks)
+             fused swapped-prediction loss fwd + dS
+             dZn = dS Wk ; gWk += dS^T Zn ; dZ = normalise'(dZn) ; gWp += dZ^T A
+  all-reduce gradients ; LARC + SGD(momentum)
+
+Everything on the device is a hand-written kernel from `ganecdotes_b200._lib`; the only
+host arithmetic is the data-independent index bookkeeping (rotation/flip index map,
+random permutations), a few KB per latent.
+"""
+import math
+from dataclasses import dataclass, field
+from typing import List, Optional
+
+import torch
+
+from .. import _lib as L
+
+
+# ----------------------------------------------------------------------------------------
+# host-side index bookkeeping
+# ----------------------------------------------------------------------------------------
+
+def rotate_flip_index_map(h: int, w: int, angle: float, flip: bool) -> torch.Tensor:
+    """int64 [h*w] on the CPU: for every pixel of `flip(rotate(x, angle))` the flat index of
+    the source pixel it copies, or -1 where the rotation fills with zeros.
+
+    The map is produced by pushing an index image through torchvision's own rotate / hflip
+    (the ops `fixed_transforms` applies to the feature tensor, ref swav_clustering.py:98-102,
+    358-359), so the nearest-neighbour rounding is torchvision's, bit for bit."""
+    import torchvision.transforms.functional as TF
+    from torchvision.transforms import InterpolationMode
+    idx = (torch.arange(h * w, dtype=torch.float32) + 1).view(1, 1, h, w)
+    y = TF.rotate(idx, float(angle), InterpolationMode.NEAREST, False, None, [0.0])
+    if flip:
+        y = TF.hflip(y)
+    return y.round().long().flatten() - 1
+
+
+@dataclass
+class ViewDraws:
+    """Random draws of one view for every latent of the local batch."""
+    layer_no: List[int]                 # np.random.choice(n_layers) per latent   (ref :610-612)
+    pert_z: torch.Tensor                # [B, 2*n_layers, D] randn_like draws     (ref aug:47)
+    angle: List[float]                  # RandomRotation angle per latent        (ref :358-359)
+    flip: List[bool]                    # RandomHorizontalFlip decision per latent
+
+
+@dataclass
+class StepDraws:
+    z: torch.Tensor                     # [B, D] latents (ref :323)
+    view_s: ViewDraws
+    view_t: ViewDraws
+    perms: List[List[torch.Tensor]]     # perms[p][b]: randperm(H*W) (ref :388), shared by both views
+
+
+def build_row_indices(h, w, view: ViewDraws, perms, patch_size, device):
+    """[P, B*N] int32 (row_src), [B*N] int32 (row_img) for one view."""
+    b = len(view.angle)
+    maps = [rotate_flip_index_map(h, w, view.angle[i], view.flip[i]) for i in range(b)]
+    n = patch_size if patch_size is not None else h * w
+    rows = []
+    for p in range(len(perms)):
+        rows.append(torch.cat([maps[i][perms[p][i][:n]] for i in range(b)]))
+    row_src = torch.stack(rows).to(torch.int32)
+    row_img = torch.arange(b, dtype=torch.int32).repeat_interleave(n)
+    return row_src.to(device, non_blocking=True), row_img.to(device, non_blocking=True)
+
+
+# ----------------------------------------------------------------------------------------
+# W+ construction for a perturbed view
+# ----------------------------------------------------------------------------------------
+
+@torch.no_grad()
+def view_wplus(gen, w, mean_latent, truncation, view: ViewDraws, perturb_std):
+    """W+ [B, n_latent, D] fed to the synthesis network for one view, including the
+    reference's double truncation.  Only the two perturbed rows need
+    the mapping network: the other ten `style(randn)` passes of the reference are
+    multiplied by sigma = 0 (ref aug:42-53) and are skipped."""
+    b, d = w.shape
+    mean = mean_latent.reshape(-1).float().contiguous()
+    wt = L.truncate(w.float().contiguous(), mean, truncation) if truncation < 1 else w
+    wplus = wt.unsqueeze(1).repeat(1, gen.n_latent, 1).contiguous()
+    rows = []
+    for i in range(b):
+        l = view.layer_no[i]
+        rows += [view.pert_z[i, 2 * l], view.pert_z[i, 2 * l + 1]]
+    noise_w = gen.style(torch.stack(rows).to(w.device).float().contiguous())       # [2B, D]
+    for i in range(b):
+        l = view.layer_no[i]
+        sg = float(perturb_std[l])
+        for j, r in enumerate((2 * l, 2 * l + 1)):
+            wplus[i, r] = (1 - sg) * wplus[i, r] + sg * noise_w[2 * i + j]
+    if truncation < 1:
+        wplus = L.truncate(wplus, mean, truncation)                                   # second truncation
+    return wplus
+
+
+def regroup_order(nfeat: int) -> List[int]:
+    """Feature order after the reference's 13 -> 7 regrouping (ref aug:80-90): it only
+    concatenates neighbours, so the channel order of the final per-pixel vector is the
+    plain layer order."""
+    return list(range(nfeat))
+
+
+# ----------------------------------------------------------------------------------------
+# head state
+# ----------------------------------------------------------------------------------------
+
+def pick_split_k(tiles: int, kiters: int, sms: int = 148, min_iters: int = 8, max_split: int = 64) -> int:
+    best, best_eff = 1, 0.0
+    for s in range(1, max(1, min(max_split, kiters // min_iters)) + 1):
+        work = tiles * s
+        eff = work / (sms * math.ceil(work / sms))
+        if eff > best_eff + 1e-9:
+            best, best_eff = s, eff
+    return best
+
+
+class SwavHead:
+    """Projection (Linear hlen->C, no bias) + prototype (Linear C->K with bias) layers,
+    their bf16 operand planes, gradients and LARC/SGD state.  Operates IN PLACE on the
+    parameters of the nn.Modules the caller saves (ref :504-505)."""
+
+    def __init__(self, w_proj, w_proto, b_proto, lr, momentum, trust, passes_fwd=3, passes_bwd=1):
+        self.w_proj, self.w_proto, self.b_proto = w_proj, w_proto, b_proto
+        self.lr, self.momentum, self.trust = lr, momentum, trust
+        self.passes_fwd, self.passes_bwd = passes_fwd, passes_bwd
+        dev = w_proj.device
+        self.g_proj = torch.zeros_like(w_proj)
+        self.g_proto = torch.zeros_like(w_proto)
+        self.g_bias = torch.zeros_like(b_proto)
+        self.m_proj = torch.zeros_like(w_proj)
+        self.m_proto = torch.zeros_like(w_proto)
+        self.m_bias = torch.zeros_like(b_proto)
+        self.norms = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.steps = 0
+        self.planes_ready = False
+
+    @property
+    def c(self):
+        return self.w_proj.shape[0]
+
+    @property
+    def d(self):
+        return self.w_proj.shape[1]
+
+    @property
+    def k(self):
+        return self.w_proto.shape[0]
+
+    def refresh_planes(self, need_bwd=True):
+        want_lo = self.passes_fwd == 3
+        self.wp_hi, self.wp_lo = L.split_planes(self.w_proj, want_lo=want_lo)
+        self.wk_hi, self.wk_lo = L.split_planes(self.w_proto, want_lo=want_lo)
+        if need_bwd:
+            self.wkT_hi, self.wkT_lo = L.split_planes(self.w_proto, transpose=True, want_lo=self.passes_bwd == 3)
+        self.planes_ready = True
+
+    def zero_grad(self):
+        self.g_proj.zero_()
+        self.g_proto.zero_()
+        self.g_bias.zero_()
+
+    def optimizer_step(self):
+        first = 1 if self.steps == 0 else 0
+        for p, g, m in ((self.w_proj, self.g_proj, self.m_proj), (self.w_proto, self.g_proto, self.m_proto),
+                        (self.b_proto, self.g_bias, self.m_bias)):
+            L.larc_sgd_(p, g, m, self.lr, self.momentum, self.trust, 0.0, 1e-8, first, self.norms)
+        self.steps += 1
+        self.planes_ready = False
+
+
+# ----------------------------------------------------------------------------------------
+# stages
+# ----------------------------------------------------------------------------------------
+
+def scores_forward(head: SwavHead, feats, out_h, out_w, hlen, row_img, row_src, nrows):
+    """gather -> projection -> normalise -> prototype scores.  Returns a dict of the
+    tensors the backward needs."""
+    lo = head.passes_fwd == 3
+    a_hi, a_lo, _ = L.gather_rows(feats, out_h, out_w, hlen, row_img, row_src, nrows, want_lo=lo)
+    z = L.gemm(a_hi, a_lo, head.wp_hi, head.wp_lo, nrows, head.c, hlen, head.passes_fwd)
+    zn_hi, zn_lo, inv = L.l2norm_split(z, want_lo=lo or head.passes_bwd == 3)
+    s = L.gemm(zn_hi, zn_lo if lo else None, head.wk_hi, head.wk_lo, nrows, head.k, head.c, head.passes_fwd,
+               bias=head.b_proto)
+    return dict(a_hi=a_hi, a_lo=a_lo, zn_hi=zn_hi, zn_lo=zn_lo, inv=inv, s=s, n=nrows)
+
+
+def sinkhorn_log_a(s, niters, eps, ws: L.SinkhornWorkspace, n_total, group=None, r=None, c=None):
+    """Sinkhorn-Knopp in scaling-vector form (ref :509-544): niters streaming passes over
+    S; only u[K] crosses ranks.  Returns log a[K]; Q = softmax_k(S/eps + log a)."""
+    inv_eps = 1.0 / eps
+    u = None
+    for it in range(niters):
+        u = L.sinkhorn_pass(s, inv_eps, it == 0, u, r, c, n_total, ws)
+        if group is not None:
+            torch.distributed.all_reduce(u, group=group.pg)
+    return L.sinkhorn_log_a(u, r)
+
+
+def scores_backward(head: SwavHead, fw, ds_hi, ds_lo):
+    """Accumulates gWk += dS^T Zn and gWp += dZ^T A for one view-patch."""
+    n, k, c, d = fw["n"], head.k, head.c, head.d
+    pb = head.passes_bwd
+    dzn = L.gemm(ds_hi, ds_lo if pb == 3 else None, head.wkT_hi, head.wkT_lo if pb == 3 else None, n, c, k, pb)
+    kit = (n + 63) // 64
+    sms = L.load().gx_sinkhorn_max_parts()
+    sk1 = pick_split_k(math.ceil(k / 128) * math.ceil(c / 256), kit, sms)
+    L.gemm(ds_hi, ds_lo if pb == 3 else None, fw["zn_hi"], fw["zn_lo"] if pb == 3 else None, k, c, n, pb,
+           out=head.g_proto, a_mn=True, b_mn=True, split_k=sk1, accumulate=True)
+    dz_hi, dz_lo = L.l2norm_bwd_split(dzn, fw["zn_hi"], fw["zn_lo"], fw["inv"], want_lo=pb == 3)
+    sk2 = pick_split_k(math.ceil(c / 128) * math.ceil(d / 256), kit, sms)
+    L.gemm(dz_hi, dz_lo, fw["a_hi"], fw["a_lo"] if pb == 3 else None, c, d, n, pb, out=head.g_proj, a_mn=True,
+           b_mn=True, split_k=sk2, accumulate=True)
+
+
+@dataclass
+class DistGroup:
+    pg: object
+    rank: int
+    world: int
+
+
+@dataclass
+class StepConfig:
+    hlen: int
+    patch_size: Optional[int]
+    num_patches: int
+    niters: int
+    eps: float
+    temperature: float
+    truncation: float
+    perturb_std: List[float]
+    need_image: bool = False
+
+
+@torch.no_grad()
+def swav_train_step(gen, head: SwavHead, mean_latent, draws: StepDraws, cfg: StepConfig,
+                    group: Optional[DistGroup] = None, ws: Optional[L.SinkhornWorkspace] = None):
+    """One optimiser step on this rank's latents.  Returns the (global) loss as a 0-dim
+    device tensor; no host synchronisation."""
+    dev = head.w_proj.device
+    b = draws.z.shape[0]
+    world = group.world if group is not None else 1
+    # prototype re-normalisation every step (ref :328-331), then operand planes
+    L.normalize_rows_(head.w_proto)
+    head.refresh_planes()
+    head.zero_grad()
+    ws = ws or L.SinkhornWorkspace(head.k, dev)
+
+    w = gen.style(draws.z.to(dev).float().contiguous())
+    feats, rows = {}, {}
+    out_h = out_w = gen.size
+    for name, view in (("s", draws.view_s), ("t", draws.view_t)):
+        wplus = view_wplus(gen, w, mean_latent, cfg.truncation, view, cfg.perturb_std)
+        _, f = gen.synthesize(wplus, None, need_image=cfg.need_image)
+        feats[name] = f
+        rows[name] = build_row_indices(out_h, out_w, view, draws.perms, cfg.patch_size, dev)
+
+    n_local = b * (cfg.patch_size if cfg.patch_size is not None else out_h * out_w)
+    n_total = n_local * world
+    grad_scale = 1.0 / (n_total * cfg.num_patches)
+    loss_acc = torch.zeros((), dtype=torch.float32, device=dev)
+    for p in range(cfg.num_patches):
+        fw = {}
+        for name in ("s", "t"):
+            row_src, row_img = rows[name]
+            fw[name] = scores_forward(head, feats[name], out_h, out_w, cfg.hlen, row_img, row_src[p], n_local)
+        la_s = sinkhorn_log_a(fw["s"]["s"], cfg.niters, cfg.eps, ws, n_total, group)
+        la_t = sinkhorn_log_a(fw["t"]["s"], cfg.niters, cfg.eps, ws, n_total, group)
+        lo = head.passes_bwd == 3
+        loss_parts, ds_s, ds_t, db, _ = L.swav_loss(fw["s"]["s"], fw["t"]["s"], 1.0 / cfg.eps, 1.0 / cfg.temperature,
+                                                    la_s, la_t, grad_scale, want_lo=lo)
+        loss_acc += loss_parts.sum()
+        head.g_bias += db
+        fw["s"].pop("s"), fw["t"].pop("s")
+        scores_backward(head, fw["s"], ds_s[0], ds_s[1])
+        scores_backward(head, fw["t"], ds_t[0], ds_t[1])
+    loss = loss_acc / (n_total * cfg.num_patches)
+    if group is not None:
+        for g in (head.g_proj, head.g_proto, head.g_bias):
+            torch.distributed.all_reduce(g, group=group.pg)
+        torch.distributed.all_reduce(loss, group=group.pg)
+    head.optimizer_step()
+    return loss
+
+
+@torch.no_grad()
+def predict_codes(gen, w_proj, w, mean_latent, truncation, hlen, passes=3, images_per_chunk=4):
+    """predict_swav_codes (ref :659-693): generator forward with the fixed noise buffers,
+    per-pixel vectors, projection only, arg-max over the code channels.
+    Returns (codes [B,C,H,W] fp32 in channels_last memory, labels int64 [B,H,W])."""
+    dev = w_proj.device
+    mean = mean_latent.reshape(-1).float().contiguous()
+    w = w.to(dev).float().contiguous()
+    wt = L.truncate(w, mean, truncation) if truncation < 1 else w
+    latent = wt.unsqueeze(1).repeat(1, gen.n_latent, 1) if wt.dim() == 2 else wt
+    _, feats = gen.synthesize(latent, None, need_image=False)
+    b = latent.shape[0]
+    h = wd = gen.size
+    c = w_proj.shape[0]
+    wp_hi, wp_lo = L.split_planes(w_proj.contiguous(), want_lo=passes == 3)
+    z = torch.empty((b * h * wd, c), dtype=torch.float32, device=dev)
+    labels = torch.empty((b * h * wd,), dtype=torch.int64, device=dev)
+    for i0 in range(0, b, images_per_chunk):
+        i1 = min(b, i0 + images_per_chunk)
+        sub = [f[i0:i1] for f in feats]
+        n = (i1 - i0) * h * wd
+        a_hi, a_lo, _ = L.gather_rows(sub, h, wd, hlen, None, None, n, want_lo=passes == 3)
+        zc = z[i0 * h * wd: i1 * h * wd]
+        L.gemm(a_hi, a_lo, wp_hi, wp_lo, n, c, hlen, passes, out=zc)
+        labels[i0 * h * wd: i1 * h * wd] = L.argmax_rows(zc)
+    preds = z.view(b, h, wd, c).permute(0, 3, 1, 2)
+    return preds, labels.view(b, h, wd)

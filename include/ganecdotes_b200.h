@@ -1,0 +1,259 @@
+/* ganecdotes_b200 - C ABI of the B200 (sm_100a) per-pixel hidden-feature clustering path.
+ *
+ * This is the drop-in boundary: every entry point replaces one op (or one fused
+ * stage) of the reference's path.  Plain pointers and sizes only; all pointers are
+ * DEVICE pointers unless stated; outputs are caller-allocated; calls are
+ * asynchronous on `stream` (a cudaStream_t passed as void*); no hidden allocation
+ * or synchronisation (the tcgen05 entry points encode TMA descriptors on the host,
+ * which is synchronous CPU work only).  Return value: GX_OK or a negative error;
+ * nothing throws across the ABI.  Re-entrant, no global state besides the
+ * last-error slot.
+ *
+ * Citations `ref:` are relative to the reference repository root.
+ */
+#ifndef GANECDOTES_B200_H
+#define GANECDOTES_B200_H
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define GX_OK 0
+#define GX_ERR_ARG (-1)         /* invalid argument / unsupported shape          */
+#define GX_ERR_CUDA (-2)        /* CUDA runtime/driver error: gx_last_cuda_error */
+#define GX_ERR_UNSUPPORTED (-3) /* device is not sm_100                           */
+
+int gx_version(void);
+int gx_last_cuda_error(void);             /* cudaError_t of the last GX_ERR_CUDA  */
+const char* gx_error_string(int gx_code); /* static string                        */
+int gx_device_ok(void);                   /* 1 if the current device is sm_100    */
+
+/* ------------------------------------------------------------------------------------
+ * L0 native ops of the reference
+ * ---------------------------------------------------------------------------------- */
+
+/* upfirdn2d forward.  ref: lib/gan/optim/upfirdn2d.cpp:18-39 (pybind `upfirdn2d`),
+ * lib/gan/optim/upfirdn2d_kernel.cu:217-379.  input [major,in_h,in_w,minor] fp32,
+ * kernel [kh,kw] fp32 (NOT flipped by the caller; the op correlates with the
+ * flipped kernel like the reference), out [major,out_h,out_w,minor] with
+ * out = (in*up + pad0 + pad1 - k + down) / down.  Negative pads crop. */
+int gx_upfirdn2d(const float* input, const float* kernel, float* out, int major, int in_h, int in_w, int minor,
+                 int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1, int pad_y0,
+                 int pad_y1, void* stream);
+
+/* fused_bias_act.  ref: lib/gan/optim/fused_bias_act.cpp:18-36,
+ * fused_bias_act_kernel.cu:18-85.  x += b[(i/step_b)%size_b]; act*10+grad in
+ * {10,11,12,30,31,32}; out = y*scale.  bias/refer may be NULL ("empty tensor"). */
+int gx_fused_bias_act(const float* input, const float* bias, const float* refer, float* out, long long n,
+                      int step_b, int size_b, int act, int grad, float alpha, float scale, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * StyleGAN2 synthesis (ref: models/stylegan2/model.py)
+ * ---------------------------------------------------------------------------------- */
+
+/* PixelNorm, ref: model.py:105-110.  x,y [n,dim]. */
+int gx_pixel_norm(const float* x, float* y, int n, int dim, void* stream);
+
+/* EqualLinear, ref: model.py:223-252.  y[n,o] = act(sum_i x[n,i]*w[o,i]*w_scale + b[o]*b_scale);
+ * act: 0 none, 1 fused leaky relu (0.2, *sqrt2).  b may be NULL. */
+int gx_equal_linear(const float* x, const float* w, const float* b, float* y, int n, int in_dim, int out_dim,
+                    float w_scale, float b_scale, int act, void* stream);
+
+/* out[i,:] = mean + psi*(w[i,:]-mean): the truncation trick, ref: model.py:594-602. */
+int gx_truncate(const float* w, const float* mean, float* out, long long rows, int dim, float psi, void* stream);
+
+/* One-time weight preparation of a modulated conv (ref: model.py:316-320,330):
+ * w [cout,cin,k,k] fp32 -> split-bf16 planes w_hi/w_lo [cout, k*k*cin] holding
+ * scale*w with k index = (ky*k+kx)*cin + ci, and wsq [cout,cin] = sum_taps (scale*w)^2. */
+int gx_modconv_prepare(const float* w, float scale, void* w_hi, void* w_lo, float* wsq, int cout, int cin, int k,
+                       void* stream);
+
+/* demod[b,co] = rsqrt(sum_ci wsq[co,ci]*s[b,ci]^2 + 1e-8), ref: model.py:332-334. */
+int gx_modconv_demod(const float* wsq, const float* s, float* demod, int batch, int cin, int cout, void* stream);
+
+/* x_mod = x * s[b,c] split into bf16 hi/lo planes (NHWC).  x has `x_batch_stride`
+ * elements between samples (0 = broadcast, e.g. the constant input, ref: model.py:385-395). */
+int gx_modulate_split(const float* x, long long x_batch_stride, const float* s, void* hi, void* lo, int batch,
+                      long long hw, int c, void* stream);
+
+typedef struct gx_conv_desc {
+  /* operands (bf16 planes; *_lo may be NULL when passes == 1) */
+  const void* x_hi; /* [B,H,W,Cin] NHWC, already modulated by the style     */
+  const void* x_lo;
+  const void* w_hi; /* [Cout, taps*Cin] from gx_modconv_prepare              */
+  const void* w_lo;
+  int batch, h, w, cin, cout;
+  int upsample; /* 0: 3x3 pad 1 -> [B,H,W,Cout]; 1: transposed stride 2 -> [B,2H+1,2W+1,Cout] */
+  int passes;   /* 1: bf16, 3: split-bf16 (fp32-equivalent)                  */
+  /* epilogue: v = acc*demod[b,co] + strength*noise[b,y,x] + bias[co]; act; */
+  const float* demod;          /* [B,Cout] or NULL                            */
+  const float* noise;          /* [*,Ho,Wo] or NULL                           */
+  long long noise_batch_stride; /* 0: shared across the batch                 */
+  const float* noise_strength; /* device scalar (ref: NoiseInjection.weight) */
+  const float* bias;           /* [Cout] or NULL                              */
+  int act;                     /* 0 none, 1 lrelu(0.2)*sqrt2                  */
+  float* out;                  /* fp32 NHWC [B,Ho,Wo,Cout]                    */
+  const float* next_style;     /* [B,Cout] or NULL: also emit next conv input */
+  void* next_hi;               /* bf16 NHWC [B,Ho,Wo,Cout]                    */
+  void* next_lo;
+  int block_n; /* 0 = auto (128 or 256) */
+  int stages;  /* 0 = auto               */
+} gx_conv_desc;
+
+/* Modulated 3x3 conv as implicit GEMM on tcgen05 (TMA im2col boxes, TMEM accumulators),
+ * ref: ModulatedConv2d.forward model.py:327-368 in the algebraic form
+ * y = demod * conv(scale*W, s*x).  Requires cin % 64 == 0, cout % 16 == 0. */
+int gx_modconv(const gx_conv_desc* d, void* stream);
+
+/* Blur (upfirdn2d up=1, down=1, pad=(p0,p1)) of the transposed-conv output fused with
+ * noise + bias + leaky-relu*sqrt2 and with the next conv's modulate+split, NHWC.
+ * ref: Blur model.py:166-182 + NoiseInjection :371-382 + FusedLeakyReLU :15-43.
+ * in [B,Hi,Wi,C]; fir [kh,kw] device fp32 (unflipped); out [B,Ho,Wo,C], Ho = Hi+p0+p1-kh+1. */
+int gx_blur_noise_bias_act(const float* in, const float* fir, int kh, int kw, int pad0, int pad1,
+                           const float* noise, long long noise_batch_stride, const float* noise_strength,
+                           const float* bias, int act, float* out, const float* next_style, void* next_hi,
+                           void* next_lo, int batch, int hi, int wi, int c, void* stream);
+
+/* ToRGB: 1x1 modulated conv without demodulation + bias (+ skip), ref: model.py:435-454.
+ * x fp32 NHWC [B,H,W,C]; w [3,C]; s [B,C]; bias [3]; skip (already upsampled) [B,3,H,W] or NULL;
+ * out [B,3,H,W] NCHW fp32. */
+int gx_torgb(const float* x, const float* w, float w_scale, const float* s, const float* bias, const float* skip,
+             float* out, int batch, int hw, int c, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Dense contractions (tcgen05)
+ * ---------------------------------------------------------------------------------- */
+typedef struct gx_gemm_desc {
+  const void* a_hi; /* bf16 plane(s) of A */
+  const void* a_lo;
+  const void* b_hi; /* bf16 plane(s) of B */
+  const void* b_lo;
+  long long lda, ldb; /* leading dimensions in elements                         */
+  int a_mn_major;     /* 0: A stored [M,K] (K contiguous); 1: stored [K,M]      */
+  int b_mn_major;     /* 0: B stored [N,K] (K contiguous); 1: stored [K,N]      */
+  int m, n, k;
+  int passes;        /* 1 or 3                                                   */
+  float* c;          /* fp32 [M,N] row-major                                     */
+  long long ldc;
+  const float* bias; /* [N] or NULL, added once                                  */
+  int split_k;       /* >= 1; > 1 accumulates atomically into c (caller zeroes c) */
+  int accumulate;    /* != 0: c += A*B^T (atomic adds) even when split_k == 1       */
+  int block_n;       /* 0 = auto                                                 */
+  int stages;        /* 0 = auto                                                 */
+} gx_gemm_desc;
+
+/* C = A * B^T (+ bias): projection / prototype / gradient GEMMs
+ * (ref: hfc_with_swav/swav_clustering.py:171,175 and their autograd backward). */
+int gx_gemm(const gx_gemm_desc* d, void* stream);
+
+/* Plain fp32 SIMT GEMM on the same operands (A = hi+lo, B = hi+lo): the on-device
+ * cross-check used by the tests, not used on the product path. */
+int gx_gemm_check(const gx_gemm_desc* d, void* stream);
+
+/* fp32 [rows,cols] (row stride ld) -> bf16 hi (+lo) planes, optionally transposed
+ * ([cols,rows]).  lo may be NULL. */
+int gx_split_planes(const float* x, long long ld, void* hi, void* lo, long long rows, long long cols,
+                    int transpose, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Per-pixel feature vectors (ref: hfc_with_swav/swav_clustering.py:108-182)
+ * ---------------------------------------------------------------------------------- */
+#define GX_MAX_LEVELS 16
+typedef struct gx_gather_desc {
+  int nlevels;
+  const float* feat[GX_MAX_LEVELS]; /* fp32 NHWC [nimg,h_l,w_l,c_l]             */
+  int h[GX_MAX_LEVELS], w[GX_MAX_LEVELS], c[GX_MAX_LEVELS];
+  int out_h, out_w; /* resolution every map is (nearest) upsampled to           */
+  int hlen;         /* channels kept after concatenation ([:, :hlen])           */
+  /* rows: row r reads image row_img[r], source pixel row_src[r] (flat index in
+   * out_h*out_w AFTER undoing rotate/flip; -1 = rotation fill -> zeros).
+   * If row_src == NULL the rows are all pixels of all images in order. */
+  const int* row_img;
+  const int* row_src;
+  long long nrows;
+  void* a_hi; /* bf16 [nrows, ld]                                              */
+  void* a_lo; /* may be NULL                                                   */
+  float* a_f32; /* optional fp32 copy [nrows, ld] (tests), may be NULL          */
+  long long ld;
+} gx_gather_desc;
+
+/* nearest-upsample + concat + [:hlen] + rotate/flip + random-pixel sampling in one
+ * gather, emitting the projection GEMM's A operand (ref: :108-130,:158-167,:358-359). */
+int gx_gather_rows(const gx_gather_desc* d, void* stream);
+
+/* z [n,c] -> zn = z / max(||z||,1e-12) as split planes, inv_norm[n] kept for backward
+ * (ref: F.normalize at swav_clustering.py:174). */
+int gx_l2norm_split(const float* z, void* zn_hi, void* zn_lo, float* inv_norm, long long n, int c, void* stream);
+
+/* backward of the normalisation: dz = (dzn - zn*(zn.dzn)) * inv_norm, emitted as split planes. */
+int gx_l2norm_bwd_split(const float* dzn, const void* zn_hi, const void* zn_lo, const float* inv_norm, void* dz_hi,
+                        void* dz_lo, long long n, int c, void* stream);
+
+/* prototype row normalisation in place + split planes (+ transposed planes for dZ),
+ * ref: swav_clustering.py:328-331. w [k,c]. */
+int gx_normalize_rows(float* w, long long rows, int cols, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Sinkhorn-Knopp (ref: hfc_with_swav/swav_clustering.py:509-544)
+ *
+ * Scaling-vector form: Q = diag(b) * exp(S/eps) * diag(a) (S is [N,K]).  One pass
+ * over S per iteration: for every row n: t = sum_k a_k e_nk ; b_n = c_n / t ;
+ * u'_k += e_nk * b_n.  Between passes a_k = r_k / u_k.  The final per-pixel
+ * normalisation removes b, so the result is q[n,:] = softmax_k(S[n,k]/eps + log a_k).
+ * ---------------------------------------------------------------------------------- */
+
+/* One pass.  first != 0: u'_k = sum_n e_nk (a and b are 1).  Otherwise a_k = r_k/u_in[k]
+ * (r == NULL: 1/K) and c == NULL: c_n = 1/n_total.  Writes per-CTA partials
+ * [nparts,K]; returns the number of partials through *nparts_out (host int).
+ * partials must hold at least gx_sinkhorn_max_parts()*K floats. */
+int gx_sinkhorn_max_parts(void);
+int gx_sinkhorn_pass(const float* s, long long n, int k, long long lds, float inv_eps, int first, const float* u_in,
+                     const float* r, const float* c, long long n_total, float* partials, int* nparts_out,
+                     void* stream);
+/* u[k] = sum_p partials[p,k] (deterministic order). */
+int gx_sinkhorn_reduce(const float* partials, int nparts, int k, float* u, void* stream);
+/* log_a[k] = log(r_k / u[k]). */
+int gx_sinkhorn_log_a(const float* u, const float* r, int k, float* log_a, void* stream);
+/* Materialise Q [N,K] = softmax_k(S/eps + log_a) (API parity with sinkhorn_knopp's return). */
+int gx_sinkhorn_q(const float* s, long long n, int k, long long lds, float inv_eps, const float* log_a, float* q,
+                  void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Swapped-prediction loss, forward + d/dscores fused
+ * (ref: hfc_with_swav/swav_clustering.py:547-570, p = S/temperature, q from Sinkhorn)
+ * loss_sum += sum_n -0.5*(sum_k q_s*logsoftmax(p_t) + sum_k q_t*logsoftmax(p_s))   (not yet / N)
+ * dS_t = grad_scale * (softmax(p_t) - q_s) / (2*T), dS_s likewise; written as bf16 planes.
+ * grad_scale = 1 / (N_total * num_patches).  loss_parts: [gx_loss_max_parts()] per-CTA sums;
+ * db_parts (optional): [gx_loss_max_parts(), K] per-CTA column sums of dS_s + dS_t (the
+ * prototype-bias gradient), reduced with gx_sinkhorn_reduce.
+ * ---------------------------------------------------------------------------------- */
+int gx_loss_max_parts(void);
+int gx_swav_loss(const float* s_s, const float* s_t, long long n, int k, long long lds, float inv_eps,
+                 float inv_temp, const float* log_a_s, const float* log_a_t, float grad_scale, float* loss_parts,
+                 float* db_parts, int* nparts_out, void* ds_s_hi, void* ds_s_lo, void* ds_t_hi, void* ds_t_lo,
+                 long long ldd, float* ds_s_f32, float* ds_t_f32, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Optimiser: apex LARC(clip=False) around SGD(momentum)
+ * (ref: swav_clustering.py:286-292,458-460).  norms: scratch [2] floats (zeroed by the call).
+ * first_step != 0: momentum buffer := g.
+ * ---------------------------------------------------------------------------------- */
+int gx_larc_sgd(float* p, const float* g, float* buf, long long n, float lr, float momentum, float trust,
+                float weight_decay, float eps, int first_step, float* norms, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Inference
+ * ---------------------------------------------------------------------------------- */
+/* labels[n] = first argmax_c x[n,c]  (ref: out_preds.max(1)[1], swav_clustering.py:691). int64 out. */
+int gx_argmax_rows(const float* x, long long n, int c, long long ldx, long long* labels, void* stream);
+
+/* k-means assignment: labels[n] = first argmin_k ||x_n - c_k||^2
+ * (ref: baseline/hfc_kmeans/hfc_kmeans_clustering.py:184).  x [n,c] fp32 (row stride ldx),
+ * centers [k,c]; int32 out; optional one-hot map written by the caller. */
+int gx_kmeans_assign(const float* x, long long n, int c, long long ldx, const float* centers, int k, int* labels,
+                     void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* GANECDOTES_B200_H */

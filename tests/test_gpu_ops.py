@@ -1,0 +1,407 @@
+"""GPU parity tests of the individual kernels, called through the C ABI (ctypes) and
+checked against the golden vectors of the reference and the CPU oracle."""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ganecdotes_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    d = np.load(os.path.join(GOLD, name + ".npz"))
+    return {k: torch.from_numpy(np.asarray(d[k])) for k in d.files}
+
+
+@pytest.fixture(scope="module")
+def L():
+    from ganecdotes_b200 import _lib
+    _lib.load()
+    return _lib
+
+
+def planes(x):
+    hi = x.to(torch.bfloat16)
+    lo = (x - hi.float()).to(torch.bfloat16)
+    return hi.contiguous(), lo.contiguous()
+
+
+# ------------------------------------------------------------------------------- L0 ops
+@pytest.mark.parametrize("name", ["blur_up", "rgb_up2", "down2", "k3", "crop", "up2down2", "asym"])
+def test_upfirdn2d_golden(L, name):
+    from ganecdotes_b200.stylegan2.op import upfirdn2d
+    g = load("ops")
+    a = [int(v) for v in g[f"{name}_args"]]
+    y = upfirdn2d(g[f"{name}_x"].cuda(), g[f"{name}_k"].cuda(), up=(a[0], a[1]), down=(a[2], a[3]), pad=tuple(a[4:8]))
+    assert y.shape == g[f"{name}_y"].shape
+    # fp32, same taps, different summation order / FMA contraction than the reference conv2d
+    torch.testing.assert_close(y.cpu(), g[f"{name}_y"], rtol=1e-5, atol=1e-6)
+
+
+def test_upfirdn2d_native_layout_minor(L):
+    """the pybind-level layout [major,h,w,minor] with minor > 1 (ref upfirdn2d.cpp:18-39)"""
+    from ganecdotes_b200.stylegan2.op import upfirdn2d_native_layout
+    torch.manual_seed(0)
+    x = torch.randn(3, 9, 7, 5)
+    k = O.make_fir_kernel([1, 3, 3, 1]) * 4
+    ref = O.upfirdn2d(x.permute(0, 3, 1, 2).contiguous(), k, up=2, down=1, pad=(2, 1)).permute(0, 2, 3, 1)
+    y = upfirdn2d_native_layout(x.cuda(), k.cuda(), 2, 2, 1, 1, 2, 1, 2, 1)
+    torch.testing.assert_close(y.cpu(), ref.contiguous(), rtol=1e-5, atol=1e-6)
+
+
+def test_upfirdn2d_errors(L):
+    from ganecdotes_b200.stylegan2.op import upfirdn2d_native_layout
+    k = O.make_fir_kernel([1, 3, 3, 1])
+    with pytest.raises(RuntimeError):
+        upfirdn2d_native_layout(torch.randn(1, 4, 4, 1), k, 1, 1, 1, 1, 0, 0, 0, 0)       # CPU tensor
+    with pytest.raises(RuntimeError):
+        upfirdn2d_native_layout(torch.randn(1, 4, 4, 2).cuda()[..., :1], k.cuda(), 1, 1, 1, 1, 0, 0, 0, 0)
+
+
+def test_fused_leaky_relu_golden(L):
+    from ganecdotes_b200.stylegan2.op import fused_leaky_relu, fused_bias_act, FusedLeakyReLU
+    g = load("ops")
+    y = fused_leaky_relu(g["flr_x"].cuda(), g["flr_b"].cuda())
+    torch.testing.assert_close(y.cpu(), g["flr_y"], rtol=1e-6, atol=1e-7)
+    y = fused_leaky_relu(g["flr_x"].cuda(), None)
+    torch.testing.assert_close(y.cpu(), g["flr_y_nobias"], rtol=1e-6, atol=1e-7)
+    y = fused_leaky_relu(g["flr2_x"].cuda(), g["flr_b"].cuda())
+    torch.testing.assert_close(y.cpu(), g["flr2_y"], rtol=1e-6, atol=1e-7)
+    m = FusedLeakyReLU(6).cuda()
+    assert "bias" in dict(m.named_parameters())
+    with torch.no_grad():
+        m.bias.copy_(g["flr_b"])
+    torch.testing.assert_close(m(g["flr_x"].cuda()).cpu(), g["flr_y"], rtol=1e-6, atol=1e-7)
+    # all modes of the native op, vectorised and scalar paths
+    torch.manual_seed(1)
+    for shape in [(2, 6, 8, 8), (3, 5, 3)]:
+        x = torch.randn(*shape)
+        b = torch.randn(shape[1])
+        r = torch.randn(*shape)
+        for act, grad in [(1, 0), (1, 1), (1, 2), (3, 0), (3, 1), (3, 2)]:
+            ref = O.fused_bias_act(x, b, r, act, grad, 0.2, 1.5)
+            out = fused_bias_act(x.cuda(), b.cuda(), r.cuda(), act, grad, 0.2, 1.5)
+            torch.testing.assert_close(out.cpu(), ref, rtol=1e-6, atol=1e-7)
+    assert fused_bias_act(torch.empty(0, 4).cuda(), torch.empty(0).cuda(), torch.empty(0).cuda(), 3, 0, 0.2,
+                          1.0).numel() == 0
+
+
+# ------------------------------------------------------------------------------- GEMM engine
+@pytest.mark.parametrize("m,n,k,passes,a_mn,b_mn,split,bias", [
+    (128, 128, 64, 1, 0, 0, 1, 0),
+    (300, 72, 200, 1, 0, 0, 1, 1),          # ragged everywhere
+    (1000, 520, 5376, 3, 0, 0, 1, 0),       # projection-shaped
+    (777, 5000, 512, 3, 0, 0, 1, 1),        # prototype-shaped, N not a tile multiple
+    (256, 512, 5000, 1, 0, 0, 1, 0),        # dZn-shaped, K not a multiple of 64
+    (5000, 512, 3000, 1, 1, 1, 7, 0),       # gWk-shaped, both MN-major, split-K
+    (520, 5376, 4096, 3, 1, 1, 4, 0),       # gWp-shaped
+    (1, 8, 8, 3, 0, 0, 1, 1),               # minimum sizes
+])
+def test_gemm_vs_fp64(L, m, n, k, passes, a_mn, b_mn, split, bias):
+    torch.manual_seed(m + n + k)
+    a = torch.randn(m, k, device="cuda")
+    b = torch.randn(n, k, device="cuda")
+    ah, al = planes(a.t().contiguous() if a_mn else a)
+    bh, bl = planes(b.t().contiguous() if b_mn else b)
+    bv = torch.randn(n, device="cuda") if bias else None
+    if a_mn and (m * 2) % 16:
+        pytest.skip("TMA needs 16-byte row pitch")
+    out = L.gemm(ah, al if passes == 3 else None, bh, bl if passes == 3 else None, m, n, k, passes, bias=bv,
+                 a_mn=bool(a_mn), b_mn=bool(b_mn), split_k=split)
+    ar = ah.double() + (al.double() if passes == 3 else 0)
+    br = bh.double() + (bl.double() if passes == 3 else 0)
+    if a_mn:
+        ar = ar.t()
+    if b_mn:
+        br = br.t()
+    ref = ar @ br.t() + (bv.double() if bias else 0)
+    # the tensor core accumulates in fp32 with truncation: error grows ~ K * 2^-24 * |acc|
+    tol = 4e-7 * k * passes ** 0.5 * max(1.0, ref.abs().max().item()) / 30 + 1e-5
+    err = (out.double() - ref).abs().max().item()
+    assert err < tol, (err, tol)
+    if passes == 3:   # and the split planes reproduce the fp32 product
+        ref32 = a.double() @ b.double().t() + (bv.double() if bias else 0)
+        rel = (out.double() - ref32).abs().max().item() / ref32.abs().max().item()
+        assert rel < 1e-4, rel
+    # on-device cross-check kernel agrees too
+    chk = L.gemm(ah, al if passes == 3 else None, bh, bl if passes == 3 else None, m, n, k, passes, bias=bv,
+                 a_mn=bool(a_mn), b_mn=bool(b_mn), check=True)
+    assert (chk.double() - ref).abs().max().item() < tol
+
+
+def test_gemm_accumulate(L):
+    torch.manual_seed(3)
+    a = torch.randn(200, 96, device="cuda")
+    b = torch.randn(64, 96, device="cuda")
+    ah, al = planes(a)
+    bh, bl = planes(b)
+    out = torch.ones(200, 64, device="cuda")
+    L.gemm(ah, al, bh, bl, 200, 64, 96, 3, out=out, accumulate=True)
+    L.gemm(ah, al, bh, bl, 200, 64, 96, 3, out=out, accumulate=True)
+    ref = 1 + 2 * (a.double() @ b.double().t())
+    assert (out.double() - ref).abs().max().item() < 1e-3
+
+
+# ------------------------------------------------------------------------------- synthesis pieces
+def test_equal_linear_pixelnorm_truncate(L):
+    torch.manual_seed(0)
+    x = torch.randn(37, 64)
+    w = torch.randn(48, 64) / 0.01
+    b = torch.randn(48)
+    for act in (False, True):
+        ref = O.equal_linear(x, w, b, 0.01, act)
+        y = L.equal_linear(x.cuda(), w.cuda(), b.cuda(), (1 / 8) * 0.01, 0.01, int(act))
+        torch.testing.assert_close(y.cpu(), ref, rtol=1e-5, atol=1e-5)
+    ref = x * torch.rsqrt(torch.mean(x ** 2, dim=1, keepdim=True) + 1e-8)
+    torch.testing.assert_close(L.pixel_norm(x.cuda()).cpu(), ref, rtol=1e-6, atol=1e-6)
+    m = torch.randn(64)
+    wl = torch.randn(5, 6, 64)
+    torch.testing.assert_close(L.truncate(wl.cuda(), m.cuda(), 0.7).cpu(), m + 0.7 * (wl - m), rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("b,cin,cout,h,up,passes", [
+    (2, 64, 64, 4, False, 3),
+    (3, 128, 64, 8, False, 3),
+    (1, 64, 128, 16, False, 3),
+    (2, 64, 32, 20, False, 1),
+    (2, 64, 64, 4, True, 3),
+    (3, 128, 64, 8, True, 3),
+    (1, 64, 64, 16, True, 3),
+    (1, 512, 512, 32, False, 3),
+])
+def test_modconv_vs_oracle(L, b, cin, cout, h, up, passes):
+    """Modulated conv (+ blur for the up path) vs the per-sample reference formulation."""
+    torch.manual_seed(b * 1000 + cin + h)
+    x = torch.randn(b, cin, h, h)
+    style = torch.randn(b, 24)
+    weight = torch.randn(1, cout, cin, 3, 3)
+    mod_w = torch.randn(cin, 24)
+    mod_b = 1 + 0.1 * torch.randn(cin)
+    blur_k = O.make_fir_kernel([1, 3, 3, 1]) * 4
+    ref = O.modulated_conv2d(x, style, weight, mod_w, mod_b, True, up, blur_k)
+
+    s = L.equal_linear(style.cuda(), mod_w.cuda(), mod_b.cuda(), 1 / 24 ** 0.5, 1.0, 0)
+    scale = 1 / (cin * 9) ** 0.5
+    w_hi, w_lo, wsq = L.modconv_prepare(weight[0].contiguous().cuda(), scale)
+    demod = L.modconv_demod(wsq, s)
+    x_hi, x_lo = L.modulate_split(x.permute(0, 2, 3, 1).contiguous().cuda(), s, b)
+    out, _, _ = L.modconv(x_hi, x_lo if passes == 3 else None, w_hi, w_lo if passes == 3 else None, cout, up, passes,
+                          demod=demod)
+    if up:
+        out, _, _ = L.blur_noise_bias_act(out, blur_k.cuda(), 1, 1, None, None, None, 0, None)
+    got = out.permute(0, 3, 1, 2).cpu()
+    assert got.shape == ref.shape
+    tol = 2e-4 if passes == 3 else 4e-2
+    torch.testing.assert_close(got, ref, rtol=tol, atol=tol)
+
+
+def test_modconv_fused_epilogue(L):
+    """noise + bias + lrelu*sqrt2 + next-layer modulate/split in the conv epilogue and in
+    the blur kernel."""
+    torch.manual_seed(5)
+    b, cin, cout, h = 2, 64, 64, 8
+    x = torch.randn(b, cin, h, h)
+    s = 1 + 0.2 * torch.randn(b, cin)
+    weight = torch.randn(cout, cin, 3, 3)
+    bias = torch.randn(cout)
+    strength = torch.tensor([0.37])
+    nxt = 1 + 0.3 * torch.randn(b, cout)
+    scale = 1 / (cin * 9) ** 0.5
+    w_hi, w_lo, wsq = L.modconv_prepare(weight.cuda(), scale)
+    demod = L.modconv_demod(wsq, s.cuda())
+    x_hi, x_lo = L.modulate_split(x.permute(0, 2, 3, 1).contiguous().cuda(), s.cuda(), b)
+    for up in (False, True):
+        ho = 2 * h if up else h
+        for per_sample in (False, True):
+            noise = torch.randn(b if per_sample else 1, 1, ho, ho)
+            wmod = scale * weight[None] * s[:, None, :, None, None]
+            d = torch.rsqrt(wmod.pow(2).sum([2, 3, 4]) + 1e-8)
+            wmod = wmod * d[:, :, None, None, None]
+            outs = []
+            for i in range(b):
+                if up:
+                    o = torch.nn.functional.conv_transpose2d(x[i:i + 1], wmod[i].transpose(0, 1), stride=2)
+                    o = O.upfirdn2d(o, O.make_fir_kernel([1, 3, 3, 1]) * 4, pad=(1, 1))
+                else:
+                    o = torch.nn.functional.conv2d(x[i:i + 1], wmod[i], padding=1)
+                outs.append(o)
+            ref = torch.cat(outs) + strength * noise
+            ref = O.fused_leaky_relu(ref, bias)
+            ref_next = ref * nxt[:, :, None, None]
+            if up:
+                tmp, _, _ = L.modconv(x_hi, x_lo, w_hi, w_lo, cout, True, 3, demod=demod)
+                out, nh, nl = L.blur_noise_bias_act(tmp, (O.make_fir_kernel([1, 3, 3, 1]) * 4).cuda(), 1, 1,
+                                                    noise.cuda(), strength.cuda(), bias.cuda(), 1, nxt.cuda())
+            else:
+                out, nh, nl = L.modconv(x_hi, x_lo, w_hi, w_lo, cout, False, 3, demod=demod, noise=noise.cuda(),
+                                        noise_strength=strength.cuda(), bias=bias.cuda(), act=1,
+                                        next_style=nxt.cuda())
+            torch.testing.assert_close(out.permute(0, 3, 1, 2).cpu(), ref, rtol=2e-4, atol=2e-4)
+            nxt_got = (nh.float() + nl.float()).permute(0, 3, 1, 2).cpu()
+            torch.testing.assert_close(nxt_got, ref_next, rtol=3e-4, atol=3e-4)
+
+
+def test_torgb(L):
+    torch.manual_seed(2)
+    b, c, h = 2, 64, 8
+    x = torch.randn(b, c, h, h)
+    w = torch.randn(3, c)
+    s = torch.randn(b, c)
+    bias = torch.randn(3)
+    skip = torch.randn(b, 3, h, h)
+    scale = 1 / c ** 0.5
+    ref = torch.einsum("bchw,oc,bc->bohw", x, w * scale, s) + bias.view(1, 3, 1, 1) + skip
+    got = L.torgb(x.permute(0, 2, 3, 1).contiguous().cuda(), w.cuda(), scale, s.cuda(), bias.cuda(), skip.cuda())
+    torch.testing.assert_close(got.cpu(), ref, rtol=1e-4, atol=1e-4)
+
+
+# ------------------------------------------------------------------------------- head pieces
+def test_gather_rows_vs_oracle(L):
+    torch.manual_seed(7)
+    b = 2
+    feats = [torch.randn(b, 8, 4, 4), torch.randn(b, 12, 8, 8), torch.randn(b, 8, 8, 8), torch.randn(b, 4, 16, 16)]
+    hlen = 28   # cuts into the last map like [:, :hlen]
+    hf = O.pixel_feature_vectors(feats, hlen)
+    nhwc = [f.permute(0, 2, 3, 1).contiguous().cuda() for f in feats]
+    rows_ref, row_src, row_img = [], [], []
+    for i, (ang, flip) in enumerate([(7.5, True), (-3.0, False)]):
+        t = O.rotate_flip(hf[i:i + 1], ang, flip)
+        perm = torch.randperm(256)
+        rows_ref.append(O.sample_rows(t, perm, 100))
+        from ganecdotes_b200.hfc_with_swav.engine import rotate_flip_index_map
+        mp = rotate_flip_index_map(16, 16, ang, flip)
+        assert torch.equal(mp, O.rotate_flip_index_map(16, 16, ang, flip))
+        row_src.append(mp[perm[:100]])
+        row_img.append(torch.full((100,), i))
+    rows_ref = torch.cat(rows_ref)
+    row_src = torch.cat(row_src).to(torch.int32).cuda()
+    row_img = torch.cat(row_img).to(torch.int32).cuda()
+    a_hi, a_lo, a_f = L.gather_rows(nhwc, 16, 16, hlen, row_img, row_src, 200, ld=32, want_f32=True)
+    assert torch.equal(a_f[:, :hlen].cpu(), rows_ref)                 # exact: it is a gather
+    assert torch.count_nonzero(a_f[:, hlen:]) == 0
+    rec = (a_hi.float() + a_lo.float())[:, :hlen].cpu()
+    torch.testing.assert_close(rec, rows_ref, rtol=2e-5, atol=1e-6)
+    # all pixels in order (prediction path)
+    a_hi, a_lo, a_f = L.gather_rows(nhwc, 16, 16, hlen, None, None, b * 256, want_f32=True)
+    assert torch.equal(a_f.cpu(), hf.permute(0, 2, 3, 1).reshape(-1, hlen))
+
+
+def test_l2norm_fwd_bwd(L):
+    torch.manual_seed(0)
+    z = torch.randn(50, 64, requires_grad=True)
+    zn = torch.nn.functional.normalize(z, p=2, dim=1)
+    g = torch.randn(50, 64)
+    zn.backward(g)
+    hi, lo, inv = L.l2norm_split(z.detach().cuda())
+    torch.testing.assert_close((hi.float() + lo.float()).cpu(), zn.detach(), rtol=2e-5, atol=1e-6)
+    dh, dl = L.l2norm_bwd_split(g.cuda(), hi, lo, inv)
+    torch.testing.assert_close((dh.float() + dl.float()).cpu(), z.grad, rtol=1e-4, atol=1e-5)
+    w = torch.randn(30, 16)
+    torch.testing.assert_close(L.normalize_rows_(w.clone().cuda()).cpu(), torch.nn.functional.normalize(w, dim=1),
+                               rtol=1e-6, atol=1e-6)
+
+
+@pytest.mark.parametrize("n,k", [(40, 24), (333, 48), (1000, 5000), (64, 4000)])
+def test_sinkhorn_vs_oracle(L, n, k):
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    torch.manual_seed(n + k)
+    s = 0.05 * torch.randn(n, k)
+    ref = O.sinkhorn_knopp(s.double(), 10, 0.005).float()
+    ws = L.SinkhornWorkspace(k, "cuda")
+    la = E.sinkhorn_log_a(s.cuda(), 10, 0.005, ws, n)
+    q = L.sinkhorn_q(s.cuda(), 1 / 0.005, la)
+    torch.testing.assert_close(q.cpu(), ref, rtol=2e-3, atol=1e-9)
+    assert abs(q.sum(1).max().item() - 1) < 1e-4
+
+
+def test_sinkhorn_golden_and_image_pdf(L):
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    g = load("swav")
+    s = g["sk_scores_s"].cuda()
+    ws = L.SinkhornWorkspace(s.shape[1], "cuda")
+    la = E.sinkhorn_log_a(s, 10, 0.005, ws, s.shape[0])
+    q = L.sinkhorn_q(s, 1 / 0.005, la)
+    torch.testing.assert_close(q.cpu(), g["sk_q_s"], rtol=2e-3, atol=1e-9)
+    # non-uniform marginals (source_pdf == 'image')
+    torch.manual_seed(1)
+    n, k = 96, 32
+    sc = 0.08 * torch.randn(n, k)
+    img = torch.rand(1, 12, 12)
+    r, c = O.image_marginals(img, k, n)
+    ref = O.sinkhorn_knopp(sc.double(), 10, 0.005, r.double(), c.double()).float()
+    ws = L.SinkhornWorkspace(k, "cuda")
+    la = E.sinkhorn_log_a(sc.cuda(), 10, 0.005, ws, n, None, r.cuda(), c.cuda())
+    q = L.sinkhorn_q(sc.cuda(), 1 / 0.005, la)
+    torch.testing.assert_close(q.cpu(), ref, rtol=2e-3, atol=1e-9)
+
+
+@pytest.mark.parametrize("n,k", [(40, 24), (257, 5000)])
+def test_swav_loss_fwd_bwd_vs_oracle(L, n, k):
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    torch.manual_seed(n)
+    s_s = (0.05 * torch.randn(n, k)).requires_grad_(True)
+    s_t = (0.05 * torch.randn(n, k)).requires_grad_(True)
+    q_s = O.sinkhorn_knopp(s_s.detach(), 10, 0.005)
+    q_t = O.sinkhorn_knopp(s_t.detach(), 10, 0.005)
+    loss = O.swapped_prediction_loss(s_s / 0.01, s_t / 0.01, q_s, q_t)
+    loss.backward()
+    ws = L.SinkhornWorkspace(k, "cuda")
+    la_s = E.sinkhorn_log_a(s_s.detach().cuda(), 10, 0.005, ws, n)
+    la_t = E.sinkhorn_log_a(s_t.detach().cuda(), 10, 0.005, ws, n)
+    parts, ds_s, ds_t, db, f32 = L.swav_loss(s_s.detach().cuda(), s_t.detach().cuda(), 200.0, 100.0, la_s, la_t,
+                                              1.0 / n, want_lo=True, want_f32=True)
+    got = parts.sum().item() / n
+    assert abs(got - loss.item()) < 2e-4 * abs(loss.item()) + 1e-5, (got, loss.item())
+    gmax = s_s.grad.abs().max().item()
+    assert (f32[0].cpu() - s_s.grad).abs().max().item() < 3e-3 * gmax
+    assert (f32[1].cpu() - s_t.grad).abs().max().item() < 3e-3 * gmax
+    rec = ds_s[0].float() + ds_s[1].float()
+    assert (rec - f32[0]).abs().max().item() < 1e-4 * gmax
+    assert (ds_t[0].float() - f32[1]).abs().max().item() < 1e-2 * gmax          # bf16 plane alone
+    torch.testing.assert_close(db.cpu(), (s_s.grad + s_t.grad).sum(0), rtol=1e-2, atol=3e-3 * gmax)
+
+
+def test_larc_sgd_vs_oracle(L):
+    torch.manual_seed(0)
+    p = torch.randn(1000, 33)
+    bufs = [None]
+    ps = [p]
+    pd = p.clone().cuda()
+    buf = torch.zeros_like(pd)
+    norms = torch.zeros(2, device="cuda")
+    for step in range(3):
+        g = torch.randn(1000, 33) * 0.01
+        ps, bufs = O.larc_sgd_step(ps, [g], bufs, 0.01, 0.9, 0.01)
+        L.larc_sgd_(pd, g.cuda(), buf, 0.01, 0.9, 0.01, 0.0, 1e-8, step == 0, norms)
+        torch.testing.assert_close(pd.cpu(), ps[0], rtol=1e-5, atol=1e-6)
+
+
+def test_argmax_and_kmeans(L):
+    torch.manual_seed(0)
+    x = torch.randn(1000, 512)
+    x[5, 7] = x[5, 300] = 9.0            # tie -> first index
+    lab = L.argmax_rows(x.cuda())
+    assert lab.dtype == torch.int64
+    assert torch.equal(lab.cpu(), x.max(1)[1])
+    assert lab[5].item() == 7
+    xv = torch.randn(700, 96)
+    c = torch.randn(16, 96)
+    got = L.kmeans_assign(xv.cuda(), c.cuda())
+    assert got.dtype == torch.int32
+    assert torch.equal(got.cpu(), O.kmeans_assign(xv, c))
+    # exact ties -> first centre
+    c2 = torch.stack([c[0], c[1], c[1]])
+    assert set(L.kmeans_assign(c2.cuda(), c2.cuda()).cpu().tolist()) <= {0, 1}
+
+
+def test_split_planes(L):
+    torch.manual_seed(0)
+    x = torch.randn(70, 45, device="cuda")
+    hi, lo = L.split_planes(x)
+    assert (hi.float() + lo.float() - x).abs().max().item() < 2e-5 * x.abs().max().item()
+    hi_t, lo_t = L.split_planes(x, transpose=True)
+    assert torch.equal(hi_t, hi.t().contiguous()) and torch.equal(lo_t, lo.t().contiguous())

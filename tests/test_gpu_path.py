@@ -1,0 +1,259 @@
+"""GPU parity tests of the assembled path: Generator drop-in, SwAV pretrain steps and
+predict_swav_codes against the golden outputs of the unmodified reference, and the
+batched (joint Sinkhorn) step against the CPU oracle."""
+import os
+import types
+
+import numpy as np
+import pytest
+import torch
+
+from oracle import ganecdotes_oracle as O
+
+pytestmark = pytest.mark.gpu
+GOLD = os.path.join(os.path.dirname(__file__), "golden")
+
+
+def load(name):
+    d = np.load(os.path.join(GOLD, name + ".npz"))
+    return {k: torch.from_numpy(np.asarray(d[k])) for k in d.files}
+
+
+@pytest.fixture(scope="module")
+def gen():
+    from ganecdotes_b200.stylegan2.model import Generator
+    sd = O.init_generator_state(16, 64, 2, 7)
+    g = Generator(16, 64, 2)
+    missing, unexpected = g.load_state_dict(sd, strict=True)
+    return g.cuda()
+
+
+def test_generator_state_dict_layout(gen):
+    """same parameter / buffer names as the reference Generator (rosinality layout)"""
+    sd = O.init_generator_state(16, 64, 2, 7)
+    assert set(gen.state_dict().keys()) == set(sd.keys())
+
+
+def test_generator_forward_matches_reference(gen):
+    g = load("generator")
+    w = gen.style(g["z"].cuda())
+    torch.testing.assert_close(w.cpu(), g["w"], rtol=1e-4, atol=1e-4)
+    img, feats = gen([g["z"].cuda()], truncation=0.7, truncation_latent=g["mean_latent"].cuda(),
+                     input_is_latent=False, randomize_noise=False)
+    assert [tuple(f.shape) for f in feats] == [(2, 512, 4, 4), (2, 512, 8, 8), (2, 512, 8, 8), (2, 512, 16, 16),
+                                               (2, 512, 16, 16)]
+    for i, f in enumerate(feats):
+        ref = g[f"feat{i}"]
+        got = f[:, ::16].cpu()
+        scale = ref.abs().max().item()
+        assert (got - ref).abs().max().item() < 5e-4 * scale, (i, (got - ref).abs().max().item(), scale)
+        torch.testing.assert_close(f.double().sum(dim=(2, 3)).cpu(), g[f"feat{i}_sum"], rtol=1e-3, atol=5e-2)
+    torch.testing.assert_close(img.cpu(), g["img"], rtol=1e-3, atol=2e-3 * g["img"].abs().max().item())
+    img2, latent = gen([g["w"].cuda()], return_latents=True, truncation=0.7,
+                       truncation_latent=g["mean_latent"].cuda(), input_is_latent=True, randomize_noise=False)
+    torch.testing.assert_close(latent.cpu(), g["latent"], rtol=1e-5, atol=1e-5)
+    # W+ input with explicit per-sample noise
+    noises = [g[f"noise3_{i}"].cuda() for i in range(5)]
+    img3, feats3 = gen([g["wplus"].cuda()], input_is_latent=True, noise=noises)
+    for i, f in enumerate(feats3):
+        ref = g[f"feat3_{i}"]
+        assert (f[:, 5::32].cpu() - ref).abs().max().item() < 5e-4 * ref.abs().max().item()
+    torch.testing.assert_close(img3.cpu(), g["img3"], rtol=1e-3, atol=2e-3 * g["img3"].abs().max().item())
+
+
+def golden_cfg(g):
+    hlen, nclasses, nproto, patch, npatch, nepochs, nl = [int(v) for v in g["cfg"]]
+    cfg = dict(
+        perturb_args=dict(truncation=0.7, n_layers=nl, n_samples=1, layer_no=None,
+                          perturb_std=[float(v) for v in g["perturb_std"]]),
+        swav_args=dict(num_epochs=nepochs, num_samples=1, num_patches=npatch, sampling_method='random',
+                       patch_size=patch, hf_interp='nearest', warmup_epochs=nepochs, start_warmup=0.01,
+                       use_scheduler=False, base_lr=0.01, final_lr=0.0001, trust_coeff=0.01,
+                       freeze_prototype_niters=313, train_args=dict(lr=0.01, momentum=0.9),
+                       projn_nw='linear', temperature=0.02, nprototypes=nproto, nclasses=nclasses,
+                       hlen=hlen, add_local_loss=False, plot_test_images=False, epoch_print_freq=1,
+                       max_masks=4),
+        sinkhorn_args=dict(source_pdf='uniform', niters=10, eps=0.02),
+        train=True, layer_hf_dim=[512, 1024, 1024])
+    mc = types.SimpleNamespace(num_latents_for_mean=64, truncation=0.7, latent_dim=64, image_size=16)
+    return cfg, mc
+
+
+def test_pretrain_matches_reference_golden(gen, tmp_path):
+    """Seeded end-to-end run of SwAVClustering.pretrain vs the seeded CPU run of the
+    unmodified reference: same random stream, losses and weights within tolerance."""
+    from ganecdotes_b200.hfc_with_swav import SwAVClustering
+    g = load("swav")
+    cfg, mc = golden_cfg(g)
+    losses = []
+    tb = types.SimpleNamespace(add_scalar=lambda name, val, step: losses.append(float(val)))
+    torch.manual_seed(11)
+    np.random.seed(11)
+    obj = SwAVClustering(gen, mc, out_dir=str(tmp_path), device='cuda', tb=tb, **cfg)
+    torch.testing.assert_close(obj.mean_latent.cpu(), g["mean_latent"], rtol=1e-4, atol=1e-5)
+    recorded = []
+    orig = obj.draw_step
+    obj.draw_step = lambda b: recorded.append(orig(b)) or recorded[-1]
+    init = {}
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    orig_head = E.SwavHead
+
+    def spy(*a, **k):
+        init["p"] = [a[0].clone(), a[1].clone(), a[2].clone()]
+        return orig_head(*a, **k)
+    E.SwavHead = spy
+    try:
+        obj.pretrain(None, num_test_samples=0)
+    finally:
+        E.SwavHead = orig_head
+    # identical random stream
+    for e, d in enumerate(recorded):
+        assert torch.equal(d.z, g[f"s{e}_z"])
+        assert d.view_s.layer_no[0] == int(g[f"s{e}_s_layer"]) and d.view_t.layer_no[0] == int(g[f"s{e}_t_layer"])
+        assert torch.equal(d.view_s.pert_z[0], g[f"s{e}_s_pert_z"])
+        assert torch.equal(d.view_t.pert_z[0], g[f"s{e}_t_pert_z"])
+        assert d.view_s.angle[0] == float(g[f"s{e}_s_angle"]) and d.view_t.flip[0] == bool(g[f"s{e}_t_flip"])
+        assert torch.equal(d.perms[1][0], g[f"s{e}_perm1"])
+    torch.testing.assert_close(init["p"][0].cpu(), g["init_w_proj"], rtol=0, atol=0)
+    torch.testing.assert_close(init["p"][1].cpu(), g["init_w_proto"], rtol=0, atol=0)
+    # losses: fp32 reference vs split-bf16 tensor-core path
+    ref_losses = g["losses"].tolist()
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) < 2e-3 * abs(b), (losses, ref_losses)
+    # weights: compare the UPDATES (two LARC steps move each tensor by ~2e-4 relative)
+    fin = [obj.projection[0].weight.data.cpu(), obj.prototype.weight.data.cpu(), obj.prototype.bias.data.cpu()]
+    ref_fin = [g["final_w_proj"], g["final_w_proto"], g["final_b_proto"]]
+    ref_init = [g["init_w_proj"], torch.nn.functional.normalize(g["init_w_proto"], dim=1), g["init_b_proto"]]
+    for f, rf, ri in zip(fin, ref_fin, ref_init):
+        upd = (rf - ri).norm().item()
+        assert (f - rf).norm().item() < 3e-2 * upd, ((f - rf).norm().item(), upd)
+    # artefacts: pickled modules like the reference
+    assert os.path.exists(os.path.join(str(tmp_path), "projection.pt"))
+    proj = torch.load(os.path.join(str(tmp_path), "projection.pt"), weights_only=False)
+    assert isinstance(proj, torch.nn.Sequential) and proj[0].weight.shape == (64, 2560)
+
+    # inference with the trained head: label map identical except near-ties
+    with torch.no_grad():
+        obj.projection[0].weight.data.copy_(g["final_w_proj"])
+    preds, labels = obj.predict_swav_codes(g["pred_w"].cuda())
+    assert tuple(preds.shape) == (1, 64, 16, 16) and labels.dtype == torch.int64 and tuple(labels.shape) == (1, 16, 16)
+    ref_p = g["preds"]
+    assert (preds[:, ::4].cpu() - ref_p).abs().max().item() < 5e-4 * ref_p.abs().max().item()
+    mism = labels.cpu() != g["labels"]
+    if mism.any():   # only allowed where the reference's own top-2 margin is inside our error band
+        full_ref, _ = O.predict_codes(O.init_generator_state(16, 64, 2, 7), g["pred_w"], g["mean_latent"], 0.7,
+                                      g["final_w_proj"], 2560)
+        top2 = full_ref.topk(2, dim=1).values
+        margin = (top2[:, 0] - top2[:, 1])[mism]
+        assert margin.max().item() < 1e-3 * full_ref.abs().max().item()
+    assert mism.float().mean().item() < 0.02
+
+
+def make_draws(b, d, n_layers, hw, npatch, seed):
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    g = torch.Generator().manual_seed(seed)
+    rs = np.random.RandomState(seed)
+
+    def view():
+        return E.ViewDraws(layer_no=[int(rs.randint(n_layers)) for _ in range(b)],
+                           pert_z=torch.randn(b, 2 * n_layers, d, generator=g),
+                           angle=[float(rs.uniform(-10, 10)) for _ in range(b)],
+                           flip=[bool(rs.rand() < 0.5) for _ in range(b)])
+    return E.StepDraws(z=torch.randn(b, d, generator=g), view_s=view(), view_t=view(),
+                       perms=[[torch.randperm(hw, generator=g) for _ in range(b)] for _ in range(npatch)])
+
+
+def oracle_step(sd, mean_latent, draws, wp, wk, bk, hlen, patch, npatch, pstd, niters, eps, temp, bufs=None):
+    b = draws.z.shape[0]
+    w = O.style_mlp(sd, draws.z)
+    rows = {"s": [[] for _ in range(npatch)], "t": [[] for _ in range(npatch)]}
+    for name, view in (("s", draws.view_s), ("t", draws.view_t)):
+        for i in range(b):
+            hf, _ = O.view_features(sd, w[i:i + 1], mean_latent, 0.7, view.layer_no[i], view.pert_z[i], 3, pstd, hlen)
+            hf = O.rotate_flip(hf, view.angle[i], view.flip[i])
+            for p in range(npatch):
+                rows[name][p].append(O.sample_rows(hf, draws.perms[p][i], patch))
+    rs = [torch.cat(r) for r in rows["s"]]
+    rt = [torch.cat(r) for r in rows["t"]]
+    return O.swav_step(rs, rt, wp, wk, bk, niters, eps, temp, bufs)
+
+
+def test_batched_joint_step_matches_oracle(gen):
+    """B = 3 latents per step: joint-batch Sinkhorn over the row-concatenation."""
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    from ganecdotes_b200 import _lib as L
+    sd = O.init_generator_state(16, 64, 2, 7)
+    torch.manual_seed(0)
+    hlen, c, k, patch, npatch = 2560, 64, 48, 120, 2
+    wp = torch.randn(c, hlen) / hlen ** 0.5
+    wk = torch.randn(k, c)
+    bk = 0.05 * torch.randn(k)
+    mean_latent = O.style_mlp(sd, torch.randn(64, 64)).mean(0, keepdim=True)
+    pstd = [1.0, 0.5, 1.0]
+    head = E.SwavHead(wp.clone().cuda(), wk.clone().cuda(), bk.clone().cuda(), 0.01, 0.9, 0.01, 3, 1)
+    cfg = E.StepConfig(hlen=hlen, patch_size=patch, num_patches=npatch, niters=10, eps=0.02, temperature=0.02,
+                       truncation=0.7, perturb_std=pstd)
+    bufs = None
+    rwp, rwk, rbk = wp, wk, bk
+    for step in range(2):
+        draws = make_draws(3, 64, 3, 256, npatch, 100 + step)
+        ref = oracle_step(sd, mean_latent, draws, rwp, rwk, rbk, hlen, patch, npatch, pstd, 10, 0.02, 0.02, bufs)
+        loss = E.swav_train_step(gen, head, mean_latent.cuda(), draws, cfg)
+        assert abs(loss.item() - ref["loss"].item()) < 2e-3 * abs(ref["loss"].item()), (loss.item(), ref["loss"])
+        # gradients (bf16 backward GEMMs): relative Frobenius error
+        for got, exp in zip((head.g_proj, head.g_proto, head.g_bias), ref["grads"]):
+            rel = (got.cpu() - exp).norm().item() / exp.norm().item()
+            assert rel < 2e-2, rel
+        rwp, rwk, rbk = ref["params"]
+        bufs = ref["bufs"]
+        for got, exp in zip((head.w_proj, head.w_proto, head.b_proto), ref["params"]):
+            torch.testing.assert_close(got.cpu(), exp, rtol=1e-4, atol=2e-6)
+
+
+def test_full_precision_backward_option(gen):
+    """passes_bwd = 3 tightens the gradients to the fp32 reference."""
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    sd = O.init_generator_state(16, 64, 2, 7)
+    torch.manual_seed(1)
+    hlen, c, k, patch, npatch = 2560, 64, 48, 200, 1
+    wp = torch.randn(c, hlen) / hlen ** 0.5
+    wk = torch.randn(k, c)
+    bk = 0.05 * torch.randn(k)
+    mean_latent = O.style_mlp(sd, torch.randn(64, 64)).mean(0, keepdim=True)
+    pstd = [1.0, 1.0, 1.0]
+    head = E.SwavHead(wp.clone().cuda(), wk.clone().cuda(), bk.clone().cuda(), 0.01, 0.9, 0.01, 3, 3)
+    cfg = E.StepConfig(hlen=hlen, patch_size=patch, num_patches=npatch, niters=10, eps=0.02, temperature=0.02,
+                       truncation=0.7, perturb_std=pstd)
+    draws = make_draws(1, 64, 3, 256, npatch, 7)
+    ref = oracle_step(sd, mean_latent, draws, wp, wk, bk, hlen, patch, npatch, pstd, 10, 0.02, 0.02)
+    E.swav_train_step(gen, head, mean_latent.cuda(), draws, cfg)
+    for got, exp in zip((head.g_proj, head.g_proto, head.g_bias), ref["grads"]):
+        rel = (got.cpu() - exp).norm().item() / exp.norm().item()
+        assert rel < 3e-3, rel
+
+
+def test_api_parity_methods(gen, tmp_path):
+    """sinkhorn_knopp / create_pixel_feature_vectors / get_swav_codes_from_hidden_features
+    keep the reference's call signatures and results."""
+    from ganecdotes_b200.hfc_with_swav import SwAVClustering
+    g = load("swav")
+    cfg, mc = golden_cfg(g)
+    obj = SwAVClustering(gen, mc, out_dir=str(tmp_path), device='cuda', tb=None, **cfg)
+    obj.eps = 0.005
+    q = obj.sinkhorn_knopp(g["sk_scores_s"].cuda(), None)
+    torch.testing.assert_close(q.cpu(), g["sk_q_s"], rtol=2e-3, atol=1e-9)
+    sd = O.init_generator_state(16, 64, 2, 7)
+    gg = load("generator")
+    _, feats, _ = O.generator_forward(sd, gg["z"][:1], 0.7, gg["mean_latent"], False)
+    hf_ref = O.pixel_feature_vectors(O.regroup_features(feats), 2560)
+    hf = obj.create_pixel_feature_vectors([f.cuda() for f in O.regroup_features(feats)])
+    assert torch.equal(hf.cpu(), hf_ref)
+    obj.projection = torch.nn.Sequential(torch.nn.Linear(2560, 64, bias=False)).cuda()
+    obj.prototype = torch.nn.Linear(64, 48).cuda()
+    perm = torch.randperm(256)
+    sc = obj.get_swav_codes_from_hidden_features(hf, picks=perm, train=True)
+    ref = O.swav_scores(O.sample_rows(hf_ref, perm, 100), obj.projection[0].weight.data.cpu(),
+                        obj.prototype.weight.data.cpu(), obj.prototype.bias.data.cpu())
+    torch.testing.assert_close(sc.cpu(), ref, rtol=1e-3, atol=2e-4)
+    codes = obj.get_swav_codes_from_hidden_features(hf, (1, 64, 16, 16), train=False)
+    assert tuple(codes.shape) == (1, 64, 16, 16)
