@@ -121,6 +121,8 @@ def test_gemm_vs_fp64(L, m, n, k, passes, a_mn, b_mn, split, bias):
     ref = ar @ br.t() + (bv.double() if bias else 0)
     # the tensor core accumulates in fp32 with truncation: error grows ~ K * 2^-24 * |acc|
     tol = 4e-7 * k * passes ** 0.5 * max(1.0, ref.abs().max().item()) / 30 + 1e-5
+    if passes == 3:   # the a_lo*b_lo term (2^-16 relative per product) is dropped by design
+        tol += 2e-5 * k ** 0.5
     err = (out.double() - ref).abs().max().item()
     assert err < tol, (err, tol)
     if passes == 3:   # and the split planes reproduce the fp32 product
