@@ -163,6 +163,31 @@ def _count(n=1):
     launch_count += n
 
 
+# Optional per-kernel CUDA-event timing (used by bench.py for the live roofline numbers).
+# event_log: None (off) or a list of (name, start_event, end_event, work) tuples.
+event_log = None
+
+
+class timed:
+    """with timed("name", work): launch...  - records CUDA events on the launching stream."""
+
+    def __init__(self, name, work=0.0):
+        self.name, self.work = name, work
+
+    def __enter__(self):
+        if event_log is not None:
+            self.e0 = torch.cuda.Event(enable_timing=True)
+            self.e1 = torch.cuda.Event(enable_timing=True)
+            self.e0.record()
+        return self
+
+    def __exit__(self, *a):
+        if event_log is not None:
+            self.e1.record()
+            event_log.append((self.name, self.e0, self.e1, self.work))
+        return False
+
+
 # ----------------------------------------------------------------------------------------
 # op wrappers (raw): callers pass contiguous CUDA tensors of the right dtype
 # ----------------------------------------------------------------------------------------
@@ -286,7 +311,7 @@ def modulate_split(x_nhwc, s, batch, want_lo=True):
 
 
 def modconv(x_hi, x_lo, w_hi, w_lo, cout, upsample, passes, demod=None, noise=None, noise_strength=None, bias=None,
-            act=0, next_style=None, want_next_lo=True, block_n=0, stages=0):
+            act=0, next_style=None, want_next_lo=True, block_n=0, stages=0, tag="modconv"):
     """Implicit-GEMM modulated conv.  x_*: [B,H,W,Cin] bf16.  Returns (out fp32 NHWC, next_hi, next_lo)."""
     lib = load()
     b, h, w, cin = x_hi.shape
@@ -312,7 +337,8 @@ def modconv(x_hi, x_lo, w_hi, w_lo, cout, upsample, passes, demod=None, noise=No
     d.out = _ptr(out)
     d.next_style, d.next_hi, d.next_lo = _ptr(next_style), _ptr(next_hi), _ptr(next_lo)
     d.block_n, d.stages = block_n, stages
-    _check(lib.gx_modconv(C.byref(d), _stream()), "gx_modconv")
+    with timed(tag + ("_up" if upsample else ""), 2.0 * b * h * w * 9 * cin * cout):
+        _check(lib.gx_modconv(C.byref(d), _stream()), "gx_modconv")
     _count()
     return out, next_hi, next_lo
 
@@ -333,10 +359,13 @@ def blur_noise_bias_act(x_nhwc, fir, pad0, pad1, noise, noise_strength, bias, ac
     nbs = 0
     if noise is not None:
         nbs = 0 if noise.shape[0] == 1 else ho * wo
-    _check(lib.gx_blur_noise_bias_act(_ptr(x_nhwc), _ptr(fir), kh, kw, pad0, pad1, _ptr(noise), nbs,
-                                      _ptr(noise_strength), _ptr(bias), int(act), _ptr(out), _ptr(next_style),
-                                      _ptr(next_hi), _ptr(next_lo), b, hi, wi, c, _stream()),
-           "gx_blur_noise_bias_act")
+    nbytes = 4.0 * b * c * (hi * wi + ho * wo) + (2.0 * b * c * ho * wo * (2 if next_lo is not None else 1)
+                                                   if next_hi is not None else 0.0)
+    with timed("blur_noise_bias_act", nbytes):
+        _check(lib.gx_blur_noise_bias_act(_ptr(x_nhwc), _ptr(fir), kh, kw, pad0, pad1, _ptr(noise), nbs,
+                                          _ptr(noise_strength), _ptr(bias), int(act), _ptr(out), _ptr(next_style),
+                                          _ptr(next_hi), _ptr(next_lo), b, hi, wi, c, _stream()),
+               "gx_blur_noise_bias_act")
     _count()
     return out, next_hi, next_lo
 
@@ -366,7 +395,7 @@ def split_planes(x, transpose=False, want_lo=True):
 
 
 def gemm(a_hi, a_lo, b_hi, b_lo, m, n, k, passes, out=None, bias=None, a_mn=False, b_mn=False, split_k=1,
-         block_n=0, stages=0, check=False, accumulate=False):
+         block_n=0, stages=0, check=False, accumulate=False, tag="gemm"):
     """C[m,n] = A * B^T.  Planes are 2-D bf16 tensors: A is [m,k] (or [k,m] if a_mn), B is [n,k] (or [k,n])."""
     lib = load()
     dev = a_hi.device
@@ -382,7 +411,8 @@ def gemm(a_hi, a_lo, b_hi, b_lo, m, n, k, passes, out=None, bias=None, a_mn=Fals
     d.split_k, d.block_n, d.stages = split_k, block_n, stages
     d.accumulate = int(accumulate)
     fn = lib.gx_gemm_check if check else lib.gx_gemm
-    _check(fn(C.byref(d), _stream()), "gx_gemm")
+    with timed(tag, 2.0 * m * n * k):
+        _check(fn(C.byref(d), _stream()), "gx_gemm")
     _count()
     return out
 
@@ -404,7 +434,8 @@ def gather_rows(feats_nhwc, out_h, out_w, hlen, row_img, row_src, nrows, ld=None
     d.out_h, d.out_w, d.hlen = out_h, out_w, hlen
     d.row_img, d.row_src, d.nrows = _ptr(row_img), _ptr(row_src), nrows
     d.a_hi, d.a_lo, d.a_f32, d.ld = _ptr(a_hi), _ptr(a_lo), _ptr(a_f), ld
-    _check(lib.gx_gather_rows(C.byref(d), _stream()), "gx_gather_rows")
+    with timed("gather_rows", float(nrows) * hlen * (4 + (4 if want_lo else 2))):
+        _check(lib.gx_gather_rows(C.byref(d), _stream()), "gx_gather_rows")
     _count()
     return a_hi, a_lo, a_f
 
@@ -416,7 +447,8 @@ def l2norm_split(z, want_lo=True):
     hi = torch.empty((n, c), dtype=torch.bfloat16, device=z.device)
     lo = torch.empty_like(hi) if want_lo else None
     inv = torch.empty((n,), dtype=torch.float32, device=z.device)
-    _check(lib.gx_l2norm_split(_ptr(z), _ptr(hi), _ptr(lo), _ptr(inv), n, c, _stream()), "gx_l2norm_split")
+    with timed("l2norm_split", float(n) * c * (4 + (4 if want_lo else 2))):
+        _check(lib.gx_l2norm_split(_ptr(z), _ptr(hi), _ptr(lo), _ptr(inv), n, c, _stream()), "gx_l2norm_split")
     _count()
     return hi, lo, inv
 
@@ -427,8 +459,9 @@ def l2norm_bwd_split(dzn, zn_hi, zn_lo, inv_norm, want_lo=True):
     n, c = dzn.shape
     hi = torch.empty((n, c), dtype=torch.bfloat16, device=dzn.device)
     lo = torch.empty_like(hi) if want_lo else None
-    _check(lib.gx_l2norm_bwd_split(_ptr(dzn), _ptr(zn_hi), _ptr(zn_lo), _ptr(inv_norm), _ptr(hi), _ptr(lo), n, c,
-                                   _stream()), "gx_l2norm_bwd_split")
+    with timed("l2norm_bwd_split", float(n) * c * (4 + (4 if zn_lo is not None else 2) + (4 if want_lo else 2))):
+        _check(lib.gx_l2norm_bwd_split(_ptr(dzn), _ptr(zn_hi), _ptr(zn_lo), _ptr(inv_norm), _ptr(hi), _ptr(lo), n,
+                                       c, _stream()), "gx_l2norm_bwd_split")
     _count()
     return hi, lo
 
@@ -455,8 +488,10 @@ def sinkhorn_pass(s, inv_eps, first, u_in, r, c, n_total, ws: SinkhornWorkspace)
     lib = load()
     n, k = s.shape
     nparts = C.c_int(0)
-    _check(lib.gx_sinkhorn_pass(_ptr(s), n, k, s.stride(0), float(inv_eps), int(first), _ptr(u_in), _ptr(r), _ptr(c),
-                                int(n_total), _ptr(ws.partials), C.byref(nparts), _stream()), "gx_sinkhorn_pass")
+    with timed("sinkhorn_pass", 4.0 * n * k):
+        _check(lib.gx_sinkhorn_pass(_ptr(s), n, k, s.stride(0), float(inv_eps), int(first), _ptr(u_in), _ptr(r),
+                                    _ptr(c), int(n_total), _ptr(ws.partials), C.byref(nparts), _stream()),
+               "gx_sinkhorn_pass")
     _check(lib.gx_sinkhorn_reduce(_ptr(ws.partials), nparts.value, k, _ptr(ws.u), _stream()), "gx_sinkhorn_reduce")
     _count(2)
     return ws.u
@@ -496,10 +531,11 @@ def swav_loss(s_s, s_t, inv_eps, inv_temp, la_s, la_t, grad_scale, want_lo=False
     fs = torch.empty((n, k), dtype=torch.float32, device=dev) if want_f32 else None
     ft = torch.empty((n, k), dtype=torch.float32, device=dev) if want_f32 else None
     nparts = C.c_int(0)
-    _check(lib.gx_swav_loss(_ptr(s_s), _ptr(s_t), n, k, s_s.stride(0), float(inv_eps), float(inv_temp), _ptr(la_s),
-                            _ptr(la_t), float(grad_scale), _ptr(loss_parts), _ptr(db_parts), C.byref(nparts),
-                            _ptr(ds_s_hi), _ptr(ds_s_lo), _ptr(ds_t_hi), _ptr(ds_t_lo), k, _ptr(fs), _ptr(ft),
-                            _stream()), "gx_swav_loss")
+    with timed("swav_loss_fwd_bwd", 2.0 * n * k * (4 + (4 if want_lo else 2))):
+        _check(lib.gx_swav_loss(_ptr(s_s), _ptr(s_t), n, k, s_s.stride(0), float(inv_eps), float(inv_temp),
+                                _ptr(la_s), _ptr(la_t), float(grad_scale), _ptr(loss_parts), _ptr(db_parts),
+                                C.byref(nparts), _ptr(ds_s_hi), _ptr(ds_s_lo), _ptr(ds_t_hi), _ptr(ds_t_lo), k,
+                                _ptr(fs), _ptr(ft), _stream()), "gx_swav_loss")
     _count()
     db = None
     if want_db:

@@ -191,10 +191,10 @@ def scores_forward(head: SwavHead, feats, out_h, out_w, hlen, row_img, row_src, 
     tensors the backward needs."""
     lo = head.passes_fwd == 3
     a_hi, a_lo, _ = L.gather_rows(feats, out_h, out_w, hlen, row_img, row_src, nrows, want_lo=lo)
-    z = L.gemm(a_hi, a_lo, head.wp_hi, head.wp_lo, nrows, head.c, hlen, head.passes_fwd)
+    z = L.gemm(a_hi, a_lo, head.wp_hi, head.wp_lo, nrows, head.c, hlen, head.passes_fwd, tag="gemm_projection_fwd")
     zn_hi, zn_lo, inv = L.l2norm_split(z, want_lo=lo or head.passes_bwd == 3)
     s = L.gemm(zn_hi, zn_lo if lo else None, head.wk_hi, head.wk_lo, nrows, head.k, head.c, head.passes_fwd,
-               bias=head.b_proto)
+               bias=head.b_proto, tag="gemm_prototype_fwd")
     return dict(a_hi=a_hi, a_lo=a_lo, zn_hi=zn_hi, zn_lo=zn_lo, inv=inv, s=s, n=nrows)
 
 
@@ -214,16 +214,17 @@ def scores_backward(head: SwavHead, fw, ds_hi, ds_lo):
     """Accumulates gWk += dS^T Zn and gWp += dZ^T A for one view-patch."""
     n, k, c, d = fw["n"], head.k, head.c, head.d
     pb = head.passes_bwd
-    dzn = L.gemm(ds_hi, ds_lo if pb == 3 else None, head.wkT_hi, head.wkT_lo if pb == 3 else None, n, c, k, pb)
+    dzn = L.gemm(ds_hi, ds_lo if pb == 3 else None, head.wkT_hi, head.wkT_lo if pb == 3 else None, n, c, k, pb,
+                 tag="gemm_dzn_bwd")
     kit = (n + 63) // 64
     sms = L.load().gx_sinkhorn_max_parts()
     sk1 = pick_split_k(math.ceil(k / 128) * math.ceil(c / 256), kit, sms)
     L.gemm(ds_hi, ds_lo if pb == 3 else None, fw["zn_hi"], fw["zn_lo"] if pb == 3 else None, k, c, n, pb,
-           out=head.g_proto, a_mn=True, b_mn=True, split_k=sk1, accumulate=True)
+           out=head.g_proto, a_mn=True, b_mn=True, split_k=sk1, accumulate=True, tag="gemm_gproto_bwd")
     dz_hi, dz_lo = L.l2norm_bwd_split(dzn, fw["zn_hi"], fw["zn_lo"], fw["inv"], want_lo=pb == 3)
     sk2 = pick_split_k(math.ceil(c / 128) * math.ceil(d / 256), kit, sms)
     L.gemm(dz_hi, dz_lo, fw["a_hi"], fw["a_lo"] if pb == 3 else None, c, d, n, pb, out=head.g_proj, a_mn=True,
-           b_mn=True, split_k=sk2, accumulate=True)
+           b_mn=True, split_k=sk2, accumulate=True, tag="gemm_gproj_bwd")
 
 
 @dataclass
@@ -246,13 +247,59 @@ class StepConfig:
     need_image: bool = False
 
 
+@dataclass
+class StepInputs:
+    """Device-resident inputs of one optimiser step (what `prepare_step_inputs` uploads)."""
+    z: torch.Tensor                    # [B, D]
+    views: dict                        # name -> (layer_no list, pert rows [2B, D] on device)
+    rows: dict                         # name -> (row_src [P, B*N] int32, row_img [B*N] int32)
+    h2d_bytes: int = 0
+
+
+def prepare_step_inputs(gen, draws: StepDraws, cfg: StepConfig, device) -> StepInputs:
+    """Host bookkeeping + host->device copies of one step: latents, the two perturbation
+    draws per latent-view that are actually used, and the sampled-pixel source indices."""
+    out_h = out_w = gen.size
+    views, rows, nbytes = {}, {}, 0
+    z = draws.z.to(device, non_blocking=True)
+    nbytes += draws.z.numel() * 4
+    for name, view in (("s", draws.view_s), ("t", draws.view_t)):
+        pr = []
+        for i, l in enumerate(view.layer_no):
+            pr += [view.pert_z[i, 2 * l], view.pert_z[i, 2 * l + 1]]
+        pr = torch.stack(pr)
+        views[name] = (list(view.layer_no), pr.to(device, non_blocking=True))
+        rs, ri = build_row_indices(out_h, out_w, view, draws.perms, cfg.patch_size, device)
+        rows[name] = (rs, ri)
+        nbytes += pr.numel() * 4 + rs.numel() * 4 + ri.numel() * 4
+    return StepInputs(z=z, views=views, rows=rows, h2d_bytes=nbytes)
+
+
 @torch.no_grad()
-def swav_train_step(gen, head: SwavHead, mean_latent, draws: StepDraws, cfg: StepConfig,
-                    group: Optional[DistGroup] = None, ws: Optional[L.SinkhornWorkspace] = None):
-    """One optimiser step on this rank's latents.  Returns the (global) loss as a 0-dim
-    device tensor; no host synchronisation."""
+def view_wplus_device(gen, w, mean_latent, truncation, layer_no, pert_rows, perturb_std):
+    """`view_wplus` on device-resident draws (pert_rows [2B, D])."""
+    b, d = w.shape
+    mean = mean_latent.reshape(-1).float().contiguous()
+    wt = L.truncate(w.float().contiguous(), mean, truncation) if truncation < 1 else w
+    wplus = wt.unsqueeze(1).repeat(1, gen.n_latent, 1).contiguous()
+    noise_w = gen.style(pert_rows.float().contiguous())
+    for i in range(b):
+        l = layer_no[i]
+        sg = float(perturb_std[l])
+        for j, r in enumerate((2 * l, 2 * l + 1)):
+            wplus[i, r] = (1 - sg) * wplus[i, r] + sg * noise_w[2 * i + j]
+    if truncation < 1:
+        wplus = L.truncate(wplus, mean, truncation)
+    return wplus
+
+
+@torch.no_grad()
+def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cfg: StepConfig,
+                           group: Optional[DistGroup] = None, ws: Optional[L.SinkhornWorkspace] = None):
+    """One optimiser step on this rank's latents from device-resident inputs.  Returns the
+    (global) loss as a 0-dim device tensor; no host synchronisation."""
     dev = head.w_proj.device
-    b = draws.z.shape[0]
+    b = inp.z.shape[0]
     world = group.world if group is not None else 1
     # prototype re-normalisation every step (ref :328-331), then operand planes
     L.normalize_rows_(head.w_proto)
@@ -260,14 +307,14 @@ def swav_train_step(gen, head: SwavHead, mean_latent, draws: StepDraws, cfg: Ste
     head.zero_grad()
     ws = ws or L.SinkhornWorkspace(head.k, dev)
 
-    w = gen.style(draws.z.to(dev).float().contiguous())
-    feats, rows = {}, {}
+    w = gen.style(inp.z.float().contiguous())
+    feats = {}
     out_h = out_w = gen.size
-    for name, view in (("s", draws.view_s), ("t", draws.view_t)):
-        wplus = view_wplus(gen, w, mean_latent, cfg.truncation, view, cfg.perturb_std)
+    for name in ("s", "t"):
+        layer_no, pert_rows = inp.views[name]
+        wplus = view_wplus_device(gen, w, mean_latent, cfg.truncation, layer_no, pert_rows, cfg.perturb_std)
         _, f = gen.synthesize(wplus, None, need_image=cfg.need_image)
         feats[name] = f
-        rows[name] = build_row_indices(out_h, out_w, view, draws.perms, cfg.patch_size, dev)
 
     n_local = b * (cfg.patch_size if cfg.patch_size is not None else out_h * out_w)
     n_total = n_local * world
@@ -276,7 +323,7 @@ def swav_train_step(gen, head: SwavHead, mean_latent, draws: StepDraws, cfg: Ste
     for p in range(cfg.num_patches):
         fw = {}
         for name in ("s", "t"):
-            row_src, row_img = rows[name]
+            row_src, row_img = inp.rows[name]
             fw[name] = scores_forward(head, feats[name], out_h, out_w, cfg.hlen, row_img, row_src[p], n_local)
         la_s = sinkhorn_log_a(fw["s"]["s"], cfg.niters, cfg.eps, ws, n_total, group)
         la_t = sinkhorn_log_a(fw["t"]["s"], cfg.niters, cfg.eps, ws, n_total, group)
@@ -295,6 +342,14 @@ def swav_train_step(gen, head: SwavHead, mean_latent, draws: StepDraws, cfg: Ste
         torch.distributed.all_reduce(loss, group=group.pg)
     head.optimizer_step()
     return loss
+
+
+@torch.no_grad()
+def swav_train_step(gen, head: SwavHead, mean_latent, draws: StepDraws, cfg: StepConfig,
+                    group: Optional[DistGroup] = None, ws: Optional[L.SinkhornWorkspace] = None):
+    """Public step: host draws in, loss tensor out (host bookkeeping + uploads + device step)."""
+    inp = prepare_step_inputs(gen, draws, cfg, head.w_proj.device)
+    return swav_train_step_device(gen, head, mean_latent, inp, cfg, group, ws)
 
 
 @torch.no_grad()
@@ -320,7 +375,7 @@ def predict_codes(gen, w_proj, w, mean_latent, truncation, hlen, passes=3, image
         n = (i1 - i0) * h * wd
         a_hi, a_lo, _ = L.gather_rows(sub, h, wd, hlen, None, None, n, want_lo=passes == 3)
         zc = z[i0 * h * wd: i1 * h * wd]
-        L.gemm(a_hi, a_lo, wp_hi, wp_lo, n, c, hlen, passes, out=zc)
+        L.gemm(a_hi, a_lo, wp_hi, wp_lo, n, c, hlen, passes, out=zc, tag="gemm_projection_fwd")
         labels[i0 * h * wd: i1 * h * wd] = L.argmax_rows(zc)
     preds = z.view(b, h, wd, c).permute(0, 3, 1, 2)
     return preds, labels.view(b, h, wd)
