@@ -3,6 +3,7 @@
 // maps and k-means assignment.  All kernels use 128-bit coalesced accesses and
 // warp-shuffle + shared-memory reductions; none of them is reshaped into a GEMM.
 #include "gx_common.cuh"
+#include "gx_ptx.cuh"
 
 namespace {
 
@@ -193,96 +194,154 @@ __global__ void split_planes_t_kernel(const float* __restrict__ x, long long ld,
 constexpr int SK_THREADS = 512;
 constexpr int SK_ROWS = 2;
 
-template <int J>
+// ---------------------------------------------------------------------------
+// Streaming kernels over the rows of S.  Rows are brought into a shared-memory ring by the
+// TMA engine (cp.async.bulk, one contiguous K*4-byte copy per row) several iterations
+// ahead of the compute.  The CTA is split into NG independent groups of GT threads (named
+// barriers), each group owning all K columns (4 consecutive columns per thread per
+// GT*4-column sweep, J sweeps) and consuming every NG-th ring stage, so the exp / shuffle /
+// barrier phases of one group overlap those of the other.
+// ---------------------------------------------------------------------------
+__device__ __forceinline__ float ex2_fast(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+__device__ __forceinline__ void group_bar(int id, int nthreads) {
+  asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+template <int J, int R, int GT>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long lds, float scale_log2, int first,
                      const float* __restrict__ u_in, const float* __restrict__ r, const float* __restrict__ cvec,
-                     float c_uniform, float* __restrict__ partials) {
-  __shared__ float red[2][SK_ROWS][SK_THREADS / 32];
-  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-  float a[J][4], acc[J][4];
-  bool colok[J];
+                     float c_uniform, float* __restrict__ partials, int stages) {
+  constexpr int NG = SK_THREADS / GT;   // groups per CTA
+  constexpr int NW = GT / 32;           // warps per group
+  extern __shared__ __align__(128) uint8_t sk_smem[];
+  __shared__ __align__(16) float red[NG][2][R][NW];
+  __shared__ uint64_t full_bar[8];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int grp = tid / GT, gt = tid % GT, gwarp = gt >> 5;
+  const uint32_t row_bytes = (uint32_t)k * 4u;
+  const uint32_t stage_bytes = row_bytes * R;
+  if (tid == 0) {
+    for (int i = 0; i < stages; ++i) gxptx::mbar_init(&full_bar[i], 1);
+    gxptx::fence_mbar_init();
+  }
+  __syncthreads();
+  // iteration `it` of this CTA covers rows [(blockIdx.x + it*gridDim.x) * R, +R)
+  const long long groups_total = (n + R - 1) / R;
+  const int n_iters = (int)((groups_total - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  auto issue = [&](int it) {
+    const int st = it % stages;
+    const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * R;
+    const int valid = (int)min((long long)R, n - row0);
+    gxptx::mbar_arrive_expect_tx(&full_bar[st], row_bytes * valid);
+    for (int rr = 0; rr < valid; ++rr)
+      gxptx::bulk_load_1d(sk_smem + (size_t)st * stage_bytes + (size_t)rr * row_bytes, s + (row0 + rr) * lds,
+                          row_bytes, &full_bar[st]);
+  };
+  if (tid == 0)
+    for (int it = 0; it < stages && it < n_iters; ++it) issue(it);
+
+  // per-thread columns; out-of-range columns read a clamped (valid) address and are
+  // neutralised by log2(a) = -inf  ->  exp2(-inf) = 0
+  float la2[J][4], acc[J][4];
+  int coff[J];
 #pragma unroll
   for (int j = 0; j < J; ++j) {
-    const int col = j * (SK_THREADS * 4) + tid * 4;
-    colok[j] = col < k;
+    const int col = j * (GT * 4) + gt * 4;
+    coff[j] = min(col, k - 4);
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       acc[j][e] = 0.f;
-      a[j][e] = 1.f;
-      if (!first && colok[j]) {
-        const float rk = r ? r[col + e] : 1.f / (float)k;
-        a[j][e] = rk / u_in[col + e];
+      if (col < k) {
+        la2[j][e] = 0.f;
+        if (!first) {
+          const float rk = r ? r[col + e] : 1.f / (float)k;
+          la2[j][e] = log2f(rk / u_in[col + e]);
+        }
+      } else {
+        la2[j][e] = -INFINITY;
       }
     }
   }
   int buf = 0;
-  for (long long row0 = (long long)blockIdx.x * SK_ROWS; row0 < n; row0 += (long long)gridDim.x * SK_ROWS) {
-    float4 v[SK_ROWS][J];
+  for (int it = grp; it < n_iters; it += NG) {
+    const int st = it % stages;
+    const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * R;
+    gxptx::mbar_wait(&full_bar[st], (uint32_t)((it / stages) & 1));
+    const float* srow = reinterpret_cast<const float*>(sk_smem + (size_t)st * stage_bytes);
+    float4 p[R][J];
+    float t[R];
 #pragma unroll
-    for (int rr = 0; rr < SK_ROWS; ++rr) {
-      const long long row = row0 + rr;
-#pragma unroll
-      for (int j = 0; j < J; ++j) {
-        v[rr][j] = make_float4(-INFINITY, -INFINITY, -INFINITY, -INFINITY);
-        if (row < n && colok[j])
-          v[rr][j] = gx_ldg_stream(reinterpret_cast<const float4*>(s + row * lds + j * (SK_THREADS * 4) + tid * 4));
-      }
-    }
-    float t[SK_ROWS];
-#pragma unroll
-    for (int rr = 0; rr < SK_ROWS; ++rr) {
+    for (int rr = 0; rr < R; ++rr) {
       t[rr] = 0.f;
+      if (row0 + rr < n) {   // warp-uniform
 #pragma unroll
-      for (int j = 0; j < J; ++j) {
-        v[rr][j].x = exp2f(v[rr][j].x * scale_log2);
-        v[rr][j].y = exp2f(v[rr][j].y * scale_log2);
-        v[rr][j].z = exp2f(v[rr][j].z * scale_log2);
-        v[rr][j].w = exp2f(v[rr][j].w * scale_log2);
-        t[rr] += a[j][0] * v[rr][j].x + a[j][1] * v[rr][j].y + a[j][2] * v[rr][j].z + a[j][3] * v[rr][j].w;
+        for (int j = 0; j < J; ++j) {
+          const float4 v = *reinterpret_cast<const float4*>(srow + (size_t)rr * k + coff[j]);
+          p[rr][j].x = ex2_fast(fmaf(v.x, scale_log2, la2[j][0]));
+          p[rr][j].y = ex2_fast(fmaf(v.y, scale_log2, la2[j][1]));
+          p[rr][j].z = ex2_fast(fmaf(v.z, scale_log2, la2[j][2]));
+          p[rr][j].w = ex2_fast(fmaf(v.w, scale_log2, la2[j][3]));
+          t[rr] += (p[rr][j].x + p[rr][j].y) + (p[rr][j].z + p[rr][j].w);
+        }
+      } else {
+#pragma unroll
+        for (int j = 0; j < J; ++j) p[rr][j] = make_float4(0.f, 0.f, 0.f, 0.f);
       }
     }
-    float bn[SK_ROWS];
-    if (first) {
+    if (!first) {
 #pragma unroll
-      for (int rr = 0; rr < SK_ROWS; ++rr) bn[rr] = 1.f;
-    } else {
-#pragma unroll
-      for (int rr = 0; rr < SK_ROWS; ++rr) {
+      for (int rr = 0; rr < R; ++rr) {
         const float w = gx_warp_sum(t[rr]);
-        if (lane == 0) red[buf][rr][warp] = w;
+        if (lane == 0) red[grp][buf][rr][gwarp] = w;
       }
-      __syncthreads();
+    }
+    group_bar(1 + grp, GT);   // the group has consumed the stage (and published its partial sums)
+    if (gt == 0 && it + stages < n_iters) issue(it + stages);
+    float bn[R];
 #pragma unroll
-      for (int rr = 0; rr < SK_ROWS; ++rr) {
+    for (int rr = 0; rr < R; ++rr) {
+      bn[rr] = 1.f;
+      if (!first) {
         float tot = 0.f;
 #pragma unroll
-        for (int w = 0; w < SK_THREADS / 32; ++w) tot += red[buf][rr][w];
+        for (int w = 0; w < NW; w += 4) {
+          const float4 q = *reinterpret_cast<const float4*>(&red[grp][buf][rr][w]);
+          tot += (q.x + q.y) + (q.z + q.w);
+        }
         const long long row = row0 + rr;
-        const float cn = (row < n) ? (cvec ? cvec[row] : c_uniform) : 0.f;
-        bn[rr] = (row < n) ? cn / tot : 0.f;
+        const float cn = cvec ? ((row < n) ? cvec[row] : 0.f) : c_uniform;
+        bn[rr] = __fdividef(cn, tot);
       }
-      buf ^= 1;
     }
+    buf ^= 1;
 #pragma unroll
-    for (int rr = 0; rr < SK_ROWS; ++rr) {
+    for (int rr = 0; rr < R; ++rr) {
       if (row0 + rr < n) {
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-          acc[j][0] = fmaf(v[rr][j].x, bn[rr], acc[j][0]);
-          acc[j][1] = fmaf(v[rr][j].y, bn[rr], acc[j][1]);
-          acc[j][2] = fmaf(v[rr][j].z, bn[rr], acc[j][2]);
-          acc[j][3] = fmaf(v[rr][j].w, bn[rr], acc[j][3]);
+          acc[j][0] = fmaf(p[rr][j].x, bn[rr], acc[j][0]);
+          acc[j][1] = fmaf(p[rr][j].y, bn[rr], acc[j][1]);
+          acc[j][2] = fmaf(p[rr][j].z, bn[rr], acc[j][2]);
+          acc[j][3] = fmaf(p[rr][j].w, bn[rr], acc[j][3]);
         }
       }
     }
   }
-  float* prow = partials + (long long)blockIdx.x * k;
+  // acc holds sum_n a_k e_nk b_n; the marginal of the unscaled matrix is acc / a_k
+  float* prow = partials + ((long long)blockIdx.x * NG + grp) * k;
 #pragma unroll
-  for (int j = 0; j < J; ++j)
-    if (colok[j])
-      *reinterpret_cast<float4*>(prow + j * (SK_THREADS * 4) + tid * 4) =
-          make_float4(acc[j][0], acc[j][1], acc[j][2], acc[j][3]);
+  for (int j = 0; j < J; ++j) {
+    const int col = j * (GT * 4) + gt * 4;
+    if (col < k)
+      *reinterpret_cast<float4*>(prow + col) =
+          make_float4(acc[j][0] * ex2_fast(-la2[j][0]), acc[j][1] * ex2_fast(-la2[j][1]),
+                      acc[j][2] * ex2_fast(-la2[j][2]), acc[j][3] * ex2_fast(-la2[j][3]));
+  }
 }
 
 __global__ void colsum_parts_kernel(const float* __restrict__ parts, int nparts, int k, float* __restrict__ u) {
@@ -367,117 +426,197 @@ sinkhorn_q_kernel(const float* __restrict__ s, long long n, int k, long long lds
 }
 
 // ---------------------------------------------------------------------------
-// Swapped-prediction loss, forward + d/dS fused; one row pair per block iteration.
+// Swapped-prediction loss, forward + d/dS fused.  Same TMA row ring / group structure as
+// the Sinkhorn pass: one (S_s row, S_t row) pair per ring stage, one pair per group
+// iteration.  All exponentials are ex2 of a single FFMA (log2-domain constants folded).
 // ---------------------------------------------------------------------------
-template <int J>
+template <int NV, bool IS_MAX, int NW>
+__device__ __forceinline__ void group_reduce(float (&v)[NV], float* red /* [NV][NW] */, int gwarp, int lane,
+                                             int bar_id, int nthreads) {
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    const float w = IS_MAX ? gx_warp_max(v[i]) : gx_warp_sum(v[i]);
+    if (lane == 0) red[i * NW + gwarp] = w;
+  }
+  group_bar(bar_id, nthreads);
+#pragma unroll
+  for (int i = 0; i < NV; ++i) {
+    float tot = IS_MAX ? -INFINITY : 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; w += 4) {
+      const float4 q = *reinterpret_cast<const float4*>(red + i * NW + w);
+      tot = IS_MAX ? fmaxf(tot, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w))) : tot + ((q.x + q.y) + (q.z + q.w));
+    }
+    v[i] = tot;
+  }
+}
+
+__device__ __forceinline__ uint32_t pack_bf16x2_rn(float a, float b) {
+  uint32_t r;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(r) : "f"(b), "f"(a));
+  return r;
+}
+
+template <int J, int GT>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 swav_loss_kernel(const float* __restrict__ ss, const float* __restrict__ st, long long n, int k, long long lds,
                  float inv_eps, float inv_temp, const float* __restrict__ la_s, const float* __restrict__ la_t,
                  float grad_scale, float* __restrict__ loss_parts, float* __restrict__ db_parts,
                  __nv_bfloat16* __restrict__ ds_s_hi, __nv_bfloat16* __restrict__ ds_s_lo,
                  __nv_bfloat16* __restrict__ ds_t_hi, __nv_bfloat16* __restrict__ ds_t_lo, long long ldd,
-                 float* __restrict__ ds_s_f32, float* __restrict__ ds_t_f32) {
-  __shared__ float red[6][SK_THREADS / 32];
-  const int tid = threadIdx.x;
-  float loss_acc = 0.f;
+                 float* __restrict__ ds_s_f32, float* __restrict__ ds_t_f32, int stages) {
+  constexpr int NG = SK_THREADS / GT;
+  constexpr int NW = GT / 32;
+  extern __shared__ __align__(128) uint8_t sk_smem[];
+  __shared__ __align__(16) float red_max[NG][4 * NW];
+  __shared__ __align__(16) float red_sum[NG][6 * NW];
+  __shared__ uint64_t full_bar[8];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int grp = tid / GT, gt = tid % GT, gwarp = gt >> 5;
+  const uint32_t row_bytes = (uint32_t)k * 4u;
+  const uint32_t stage_bytes = row_bytes * 2u;   // one row of S_s and one of S_t
+  if (tid == 0) {
+    for (int i = 0; i < stages; ++i) gxptx::mbar_init(&full_bar[i], 1);
+    gxptx::fence_mbar_init();
+  }
+  __syncthreads();
+  const int n_iters = (int)((n - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  auto issue = [&](int it) {
+    const int sg = it % stages;
+    const long long row = (long long)blockIdx.x + (long long)it * gridDim.x;
+    gxptx::mbar_arrive_expect_tx(&full_bar[sg], stage_bytes);
+    gxptx::bulk_load_1d(sk_smem + (size_t)sg * stage_bytes, ss + row * lds, row_bytes, &full_bar[sg]);
+    gxptx::bulk_load_1d(sk_smem + (size_t)sg * stage_bytes + row_bytes, st + row * lds, row_bytes, &full_bar[sg]);
+  };
+  if (tid == 0)
+    for (int it = 0; it < stages && it < n_iters; ++it) issue(it);
+
+  // log2-domain constants.  log2(a) of both views lives in shared memory behind the ring
+  // (K floats each).  Out-of-range columns read a clamped address and are removed by a -inf
+  // additive mask.
+  const float ce = inv_eps * LOG2E, ct = inv_temp * LOG2E;
+  float* sla_s = reinterpret_cast<float*>(sk_smem + (size_t)stages * stage_bytes);
+  float* sla_t = sla_s + k;
+  for (int i = tid; i < k; i += SK_THREADS) {
+    sla_s[i] = la_s[i] * LOG2E;
+    sla_t[i] = la_t[i] * LOG2E;
+  }
+  __syncthreads();
   float db[J][4];
+  int coff[J];
+  bool colok[J];
 #pragma unroll
-  for (int j = 0; j < J; ++j)
+  for (int j = 0; j < J; ++j) {
+    const int col = j * (GT * 4) + gt * 4;
+    colok[j] = col < k;
+    coff[j] = min(col, k - 4);
 #pragma unroll
     for (int e = 0; e < 4; ++e) db[j][e] = 0.f;
+  }
+  float loss_acc = 0.f;
   const float gs = grad_scale * 0.5f * inv_temp;
-  for (long long row = blockIdx.x; row < n; row += gridDim.x) {
+  for (int it = grp; it < n_iters; it += NG) {
+    const long long row = (long long)blockIdx.x + (long long)it * gridDim.x;
+    const int sg = it % stages;
+    gxptx::mbar_wait(&full_bar[sg], (uint32_t)((it / stages) & 1));
+    const float* srow_s = reinterpret_cast<const float*>(sk_smem + (size_t)sg * stage_bytes);
+    const float* srow_t = srow_s + k;
     float vs[J][4], vt[J][4];     // raw scores, later softmax(p) numerators
-    float e1s[J][4], e1t[J][4];   // exp(S/eps + log a - max): q numerators
+    float e1s[J][4], e1t[J][4];   // log2-domain S/eps + log a, later q numerators
     float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // max x1_s, max s_s, max x1_t, max s_t
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-      const int col = j * (SK_THREADS * 4) + tid * 4;
-      if (col < k) {
-        const float4 a = gx_ldg_stream(reinterpret_cast<const float4*>(ss + row * lds + col));
-        const float4 b = gx_ldg_stream(reinterpret_cast<const float4*>(st + row * lds + col));
-        const float4 las = __ldg(reinterpret_cast<const float4*>(la_s + col));
-        const float4 lat = __ldg(reinterpret_cast<const float4*>(la_t + col));
-        vs[j][0] = a.x; vs[j][1] = a.y; vs[j][2] = a.z; vs[j][3] = a.w;
-        vt[j][0] = b.x; vt[j][1] = b.y; vt[j][2] = b.z; vt[j][3] = b.w;
-        e1s[j][0] = fmaf(a.x, inv_eps, las.x); e1s[j][1] = fmaf(a.y, inv_eps, las.y);
-        e1s[j][2] = fmaf(a.z, inv_eps, las.z); e1s[j][3] = fmaf(a.w, inv_eps, las.w);
-        e1t[j][0] = fmaf(b.x, inv_eps, lat.x); e1t[j][1] = fmaf(b.y, inv_eps, lat.y);
-        e1t[j][2] = fmaf(b.z, inv_eps, lat.z); e1t[j][3] = fmaf(b.w, inv_eps, lat.w);
+      const float4 a = *reinterpret_cast<const float4*>(srow_s + coff[j]);
+      const float4 b = *reinterpret_cast<const float4*>(srow_t + coff[j]);
+      const float4 ls = *reinterpret_cast<const float4*>(sla_s + coff[j]);
+      const float4 lt = *reinterpret_cast<const float4*>(sla_t + coff[j]);
+      const float msk = colok[j] ? 0.f : -INFINITY;
+      vs[j][0] = a.x; vs[j][1] = a.y; vs[j][2] = a.z; vs[j][3] = a.w;
+      vt[j][0] = b.x; vt[j][1] = b.y; vt[j][2] = b.z; vt[j][3] = b.w;
+      const float l2s[4] = {ls.x + msk, ls.y + msk, ls.z + msk, ls.w + msk};
+      const float l2t[4] = {lt.x + msk, lt.y + msk, lt.z + msk, lt.w + msk};
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          mx[0] = fmaxf(mx[0], e1s[j][e]); mx[1] = fmaxf(mx[1], vs[j][e]);
-          mx[2] = fmaxf(mx[2], e1t[j][e]); mx[3] = fmaxf(mx[3], vt[j][e]);
-        }
-      } else {
-#pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          vs[j][e] = vt[j][e] = -INFINITY;
-          e1s[j][e] = e1t[j][e] = -INFINITY;
+      for (int e = 0; e < 4; ++e) {
+        e1s[j][e] = fmaf(vs[j][e], ce, l2s[e]);
+        e1t[j][e] = fmaf(vt[j][e], ce, l2t[e]);
+        mx[0] = fmaxf(mx[0], e1s[j][e]);
+        mx[2] = fmaxf(mx[2], e1t[j][e]);
+        if (colok[j]) {
+          mx[1] = fmaxf(mx[1], vs[j][e]);
+          mx[3] = fmaxf(mx[3], vt[j][e]);
         }
       }
     }
-    block_reduce<4, true>(mx, red);
+    group_reduce<4, true, NW>(mx, red_max[grp], gwarp, lane, 1 + grp, GT);   // stage consumed after this barrier
+    if (gt == 0 && it + stages < n_iters) issue(it + stages);
     // sums: Z1_s, Z2_s, D_st = sum e1s*s_t, Z1_t, Z2_t, D_ts = sum e1t*s_s
     float sm[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
-    const float m2s = mx[1] * inv_temp, m2t = mx[3] * inv_temp;
+    const float m2s = mx[1] * ct, m2t = mx[3] * ct;   // log2 domain
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-      const int col = j * (SK_THREADS * 4) + tid * 4;
-      if (col < k) {
+      const float msk = colok[j] ? 0.f : -INFINITY;
 #pragma unroll
-        for (int e = 0; e < 4; ++e) {
-          const float rs = vs[j][e], rt = vt[j][e];
-          e1s[j][e] = exp2f((e1s[j][e] - mx[0]) * LOG2E);
-          e1t[j][e] = exp2f((e1t[j][e] - mx[2]) * LOG2E);
-          sm[0] += e1s[j][e];
-          sm[3] += e1t[j][e];
-          sm[2] = fmaf(e1s[j][e], rt, sm[2]);
-          sm[5] = fmaf(e1t[j][e], rs, sm[5]);
-          vs[j][e] = exp2f((rs * inv_temp - m2s) * LOG2E);
-          vt[j][e] = exp2f((rt * inv_temp - m2t) * LOG2E);
-          sm[1] += vs[j][e];
-          sm[4] += vt[j][e];
-        }
+      for (int e = 0; e < 4; ++e) {
+        const float rs = vs[j][e], rt = vt[j][e];
+        e1s[j][e] = ex2_fast(e1s[j][e] - mx[0]);
+        e1t[j][e] = ex2_fast(e1t[j][e] - mx[2]);
+        sm[0] += e1s[j][e];
+        sm[3] += e1t[j][e];
+        sm[2] = fmaf(e1s[j][e], rt, sm[2]);
+        sm[5] = fmaf(e1t[j][e], rs, sm[5]);
+        vs[j][e] = ex2_fast(fmaf(rs, ct, msk - m2s));
+        vt[j][e] = ex2_fast(fmaf(rt, ct, msk - m2t));
+        sm[1] += vs[j][e];
+        sm[4] += vt[j][e];
       }
     }
-    block_reduce<6, false>(sm, red);
-    const float iz1s = 1.f / sm[0], iz2s = 1.f / sm[1], iz1t = 1.f / sm[3], iz2t = 1.f / sm[4];
-    if (tid == 0) {
-      const float lse_s = m2s + logf(sm[1]), lse_t = m2t + logf(sm[4]);
+    group_reduce<6, false, NW>(sm, red_sum[grp], gwarp, lane, 1 + grp, GT);
+    const float iz1s = __fdividef(1.f, sm[0]), iz2s = __fdividef(1.f, sm[1]);
+    const float iz1t = __fdividef(1.f, sm[3]), iz2t = __fdividef(1.f, sm[4]);
+    if (gt == 0) {
+      const float ln2 = 0.69314718055994531f;
+      const float lse_s = (m2s + log2f(sm[1])) * ln2, lse_t = (m2t + log2f(sm[4])) * ln2;
       const float qs_pt = sm[2] * iz1s * inv_temp - lse_t;  // sum_k q_s * log_softmax(p_t)
       const float qt_ps = sm[5] * iz1t * inv_temp - lse_s;
       loss_acc += -0.5f * (qs_pt + qt_ps);
     }
+    const float a2s = gs * iz2s, a1t = gs * iz1t, a2t = gs * iz2t, a1s = gs * iz1s;
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-      const int col = j * (SK_THREADS * 4) + tid * 4;
-      if (col < k) {
-        float4 gs_s, gs_t;  // dL/dS_s uses q_t ; dL/dS_t uses q_s
-        gs_s.x = gs * (vs[j][0] * iz2s - e1t[j][0] * iz1t); gs_s.y = gs * (vs[j][1] * iz2s - e1t[j][1] * iz1t);
-        gs_s.z = gs * (vs[j][2] * iz2s - e1t[j][2] * iz1t); gs_s.w = gs * (vs[j][3] * iz2s - e1t[j][3] * iz1t);
-        gs_t.x = gs * (vt[j][0] * iz2t - e1s[j][0] * iz1s); gs_t.y = gs * (vt[j][1] * iz2t - e1s[j][1] * iz1s);
-        gs_t.z = gs * (vt[j][2] * iz2t - e1s[j][2] * iz1s); gs_t.w = gs * (vt[j][3] * iz2t - e1s[j][3] * iz1s);
-        db[j][0] += gs_s.x + gs_t.x; db[j][1] += gs_s.y + gs_t.y;
-        db[j][2] += gs_s.z + gs_t.z; db[j][3] += gs_s.w + gs_t.w;
-        uint2 h, l;
-        gx_split4(gs_s, h, l);
-        *reinterpret_cast<uint2*>(ds_s_hi + row * ldd + col) = h;
-        if (ds_s_lo) *reinterpret_cast<uint2*>(ds_s_lo + row * ldd + col) = l;
-        gx_split4(gs_t, h, l);
-        *reinterpret_cast<uint2*>(ds_t_hi + row * ldd + col) = h;
-        if (ds_t_lo) *reinterpret_cast<uint2*>(ds_t_lo + row * ldd + col) = l;
-        if (ds_s_f32) *reinterpret_cast<float4*>(ds_s_f32 + row * (long long)k + col) = gs_s;
-        if (ds_t_f32) *reinterpret_cast<float4*>(ds_t_f32 + row * (long long)k + col) = gs_t;
+      if (colok[j]) {
+        const int col = j * (GT * 4) + gt * 4;
+        float4 g_s, g_t;  // dL/dS_s uses q_t ; dL/dS_t uses q_s
+        g_s.x = vs[j][0] * a2s - e1t[j][0] * a1t; g_s.y = vs[j][1] * a2s - e1t[j][1] * a1t;
+        g_s.z = vs[j][2] * a2s - e1t[j][2] * a1t; g_s.w = vs[j][3] * a2s - e1t[j][3] * a1t;
+        g_t.x = vt[j][0] * a2t - e1s[j][0] * a1s; g_t.y = vt[j][1] * a2t - e1s[j][1] * a1s;
+        g_t.z = vt[j][2] * a2t - e1s[j][2] * a1s; g_t.w = vt[j][3] * a2t - e1s[j][3] * a1s;
+        db[j][0] += g_s.x + g_t.x; db[j][1] += g_s.y + g_t.y;
+        db[j][2] += g_s.z + g_t.z; db[j][3] += g_s.w + g_t.w;
+        if (ds_s_lo || ds_t_lo) {
+          uint2 h, l;
+          gx_split4(g_s, h, l);
+          *reinterpret_cast<uint2*>(ds_s_hi + row * ldd + col) = h;
+          if (ds_s_lo) *reinterpret_cast<uint2*>(ds_s_lo + row * ldd + col) = l;
+          gx_split4(g_t, h, l);
+          *reinterpret_cast<uint2*>(ds_t_hi + row * ldd + col) = h;
+          if (ds_t_lo) *reinterpret_cast<uint2*>(ds_t_lo + row * ldd + col) = l;
+        } else {
+          *reinterpret_cast<uint2*>(ds_s_hi + row * ldd + col) =
+              make_uint2(pack_bf16x2_rn(g_s.x, g_s.y), pack_bf16x2_rn(g_s.z, g_s.w));
+          *reinterpret_cast<uint2*>(ds_t_hi + row * ldd + col) =
+              make_uint2(pack_bf16x2_rn(g_t.x, g_t.y), pack_bf16x2_rn(g_t.z, g_t.w));
+        }
+        if (ds_s_f32) *reinterpret_cast<float4*>(ds_s_f32 + row * (long long)k + col) = g_s;
+        if (ds_t_f32) *reinterpret_cast<float4*>(ds_t_f32 + row * (long long)k + col) = g_t;
       }
     }
   }
-  if (tid == 0) loss_parts[blockIdx.x] = loss_acc;
+  if (gt == 0) loss_parts[blockIdx.x * NG + grp] = loss_acc;
   if (db_parts) {
-    float* prow = db_parts + (long long)blockIdx.x * k;
+    float* prow = db_parts + ((long long)blockIdx.x * NG + grp) * k;
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-      const int col = j * (SK_THREADS * 4) + tid * 4;
+      const int col = j * (GT * 4) + gt * 4;
       if (col < k) *reinterpret_cast<float4*>(prow + col) = make_float4(db[j][0], db[j][1], db[j][2], db[j][3]);
     }
   }
@@ -630,30 +769,72 @@ extern "C" int gx_split_planes(const float* x, long long ld, void* hi, void* lo,
   return GX_OK;
 }
 
-extern "C" int gx_sinkhorn_max_parts(void) { return gx_sm_count(); }
-extern "C" int gx_loss_max_parts(void) { return gx_sm_count(); }
+extern "C" int gx_sinkhorn_max_parts(void) { return 2 * gx_sm_count(); }
+extern "C" int gx_loss_max_parts(void) { return 2 * gx_sm_count(); }
 
-#define GX_DISPATCH_J(J_, CALL)          \
-  switch (J_) {                          \
-    case 1: { constexpr int J = 1; CALL; } break; \
-    case 2: { constexpr int J = 2; CALL; } break; \
-    case 3: { constexpr int J = 3; CALL; } break; \
-    case 4: { constexpr int J = 4; CALL; } break; \
-    default: return GX_ERR_ARG;          \
+#define GX_DISPATCH_J(J_, ...)                           \
+  switch (J_) {                                          \
+    case 1: { constexpr int J = 1; __VA_ARGS__; } break; \
+    case 2: { constexpr int J = 2; __VA_ARGS__; } break; \
+    case 3: { constexpr int J = 3; __VA_ARGS__; } break; \
+    case 4: { constexpr int J = 4; __VA_ARGS__; } break; \
+    default: return GX_ERR_ARG;                          \
   }
+
+template <int J, int R, int GT>
+static int launch_sinkhorn_pass(const float* s, long long n, int k, long long lds, float scale_log2, int first,
+                                const float* u_in, const float* r, const float* c, float cu, float* partials,
+                                int grid, cudaStream_t st) {
+  const int stage_bytes = k * 4 * R;
+  // Each of the NG groups must own a fixed subset of the ring (stage index parity == iteration
+  // parity): with a stage shared between groups, a group running ahead would observe the
+  // mbarrier of a fill it does not own one phase early (parity aliasing).
+  constexpr int NG = SK_THREADS / GT;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  stages -= stages % NG;
+  GX_CHECK_ARG(stages >= 2 * NG || (NG == 1 && stages >= 2));
+  static bool attr = false;
+  if (!attr) {
+    GX_CHECK_CUDA(cudaFuncSetAttribute(sinkhorn_pass_kernel<J, R, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       200 * 1024));
+    attr = true;
+  }
+  sinkhorn_pass_kernel<J, R, GT><<<grid, SK_THREADS, stages * stage_bytes, st>>>(s, n, k, lds, scale_log2, first, u_in,
+                                                                               r, c, cu, partials, stages);
+  return GX_OK;
+}
 
 extern "C" int gx_sinkhorn_pass(const float* s, long long n, int k, long long lds, float inv_eps, int first,
                                 const float* u_in, const float* r, const float* c, long long n_total,
                                 float* partials, int* nparts_out, void* stream) {
-  GX_CHECK_ARG(s && partials && n > 0 && k > 0 && k % 4 == 0 && lds % 4 == 0 && lds >= k);
+  GX_CHECK_ARG(s && partials && n > 0 && k >= 4 && k % 4 == 0 && lds % 4 == 0 && lds >= k);
   GX_CHECK_ARG(first || u_in);
   GX_CHECK_ARG((reinterpret_cast<uintptr_t>(s) & 15) == 0);
-  const int jn = gx_cdiv(k, SK_THREADS * 4);
+  GX_CHECK_ARG(k <= 8192);
   const int grid = sk_grid(n, SK_ROWS);
-  if (nparts_out) *nparts_out = grid;
   const float cu = 1.f / (float)(n_total > 0 ? n_total : n);
-  GX_DISPATCH_J(jn, (sinkhorn_pass_kernel<J><<<grid, SK_THREADS, 0, (cudaStream_t)stream>>>(
-                        s, n, k, lds, inv_eps * LOG2E, first, u_in, r, c, cu, partials)));
+  const float sl = inv_eps * LOG2E;
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  const int j256 = gx_cdiv(k, 1024);
+#define GX_SK(J_, GT_) rc = launch_sinkhorn_pass<J_, SK_ROWS, GT_>(s, n, k, lds, sl, first, u_in, r, c, cu, partials, grid, st)
+  if (j256 <= 5) {
+    if (nparts_out) *nparts_out = grid * 2;
+    switch (j256) {
+      case 1: GX_SK(1, 256); break;
+      case 2: GX_SK(2, 256); break;
+      case 3: GX_SK(3, 256); break;
+      case 4: GX_SK(4, 256); break;
+      default: GX_SK(5, 256); break;
+    }
+  } else {
+    if (nparts_out) *nparts_out = grid;
+    if (k <= 6144) GX_SK(3, 512);
+    else GX_SK(4, 512);
+  }
+#undef GX_SK
+  if (rc != GX_OK) return rc;
   GX_LAUNCH_CHECK();
   return GX_OK;
 }
@@ -683,21 +864,61 @@ extern "C" int gx_sinkhorn_q(const float* s, long long n, int k, long long lds, 
   return GX_OK;
 }
 
+template <int J, int GT>
+static int launch_swav_loss(const float* s_s, const float* s_t, long long n, int k, long long lds, float inv_eps,
+                            float inv_temp, const float* la_s, const float* la_t, float grad_scale, float* loss_parts,
+                            float* db_parts, void* ds_s_hi, void* ds_s_lo, void* ds_t_hi, void* ds_t_lo,
+                            long long ldd, float* fs, float* ft, int grid, cudaStream_t st) {
+  const int stage_bytes = k * 4 * 2;
+  constexpr int NG = SK_THREADS / GT;
+  int stages = (200 * 1024 - stage_bytes) / stage_bytes;   // one stage worth of smem holds log2(a) of both views
+  if (stages > 8) stages = 8;
+  stages -= stages % NG;                                   // fixed stage ownership per group (see sinkhorn pass)
+  GX_CHECK_ARG(stages >= 2 * NG || (NG == 1 && stages >= 2));
+  static bool attr = false;
+  if (!attr) {
+    GX_CHECK_CUDA(cudaFuncSetAttribute(swav_loss_kernel<J, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       200 * 1024));
+    attr = true;
+  }
+  swav_loss_kernel<J, GT><<<grid, SK_THREADS, (stages + 1) * stage_bytes, st>>>(
+      s_s, s_t, n, k, lds, inv_eps, inv_temp, la_s, la_t, grad_scale, loss_parts, db_parts,
+      reinterpret_cast<__nv_bfloat16*>(ds_s_hi), reinterpret_cast<__nv_bfloat16*>(ds_s_lo),
+      reinterpret_cast<__nv_bfloat16*>(ds_t_hi), reinterpret_cast<__nv_bfloat16*>(ds_t_lo), ldd, fs, ft, stages);
+  return GX_OK;
+}
+
 extern "C" int gx_swav_loss(const float* s_s, const float* s_t, long long n, int k, long long lds, float inv_eps,
                             float inv_temp, const float* log_a_s, const float* log_a_t, float grad_scale,
                             float* loss_parts, float* db_parts, int* nparts_out, void* ds_s_hi, void* ds_s_lo,
                             void* ds_t_hi, void* ds_t_lo, long long ldd, float* ds_s_f32, float* ds_t_f32,
                             void* stream) {
   GX_CHECK_ARG(s_s && s_t && log_a_s && log_a_t && loss_parts && ds_s_hi && ds_t_hi);
-  GX_CHECK_ARG(n > 0 && k > 0 && k % 4 == 0 && lds % 4 == 0 && ldd % 4 == 0 && ldd >= k);
-  const int jn = gx_cdiv(k, SK_THREADS * 4);
+  GX_CHECK_ARG(n > 0 && k >= 4 && k % 4 == 0 && k <= 8192 && lds % 4 == 0 && ldd % 4 == 0 && ldd >= k);
+  GX_CHECK_ARG((reinterpret_cast<uintptr_t>(s_s) & 15) == 0 && (reinterpret_cast<uintptr_t>(s_t) & 15) == 0);
   const int grid = sk_grid(n, 1);
-  if (nparts_out) *nparts_out = grid;
-  GX_DISPATCH_J(jn, (swav_loss_kernel<J><<<grid, SK_THREADS, 0, (cudaStream_t)stream>>>(
-                        s_s, s_t, n, k, lds, inv_eps, inv_temp, log_a_s, log_a_t, grad_scale, loss_parts, db_parts,
-                        reinterpret_cast<__nv_bfloat16*>(ds_s_hi), reinterpret_cast<__nv_bfloat16*>(ds_s_lo),
-                        reinterpret_cast<__nv_bfloat16*>(ds_t_hi), reinterpret_cast<__nv_bfloat16*>(ds_t_lo), ldd,
-                        ds_s_f32, ds_t_f32)));
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc;
+  const int j256 = gx_cdiv(k, 1024);
+#define GX_LS(J_, GT_)                                                                                            \
+  rc = launch_swav_loss<J_, GT_>(s_s, s_t, n, k, lds, inv_eps, inv_temp, log_a_s, log_a_t, grad_scale, loss_parts, \
+                                 db_parts, ds_s_hi, ds_s_lo, ds_t_hi, ds_t_lo, ldd, ds_s_f32, ds_t_f32, grid, st)
+  if (j256 <= 5) {
+    if (nparts_out) *nparts_out = grid * 2;
+    switch (j256) {
+      case 1: GX_LS(1, 256); break;
+      case 2: GX_LS(2, 256); break;
+      case 3: GX_LS(3, 256); break;
+      case 4: GX_LS(4, 256); break;
+      default: GX_LS(5, 256); break;
+    }
+  } else {
+    if (nparts_out) *nparts_out = grid;
+    if (k <= 6144) GX_LS(3, 512);
+    else GX_LS(4, 512);
+  }
+#undef GX_LS
+  if (rc != GX_OK) return rc;
   GX_LAUNCH_CHECK();
   return GX_OK;
 }
