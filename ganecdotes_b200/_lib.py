@@ -41,7 +41,7 @@ class gx_gemm_desc(C.Structure):
         ("lda", C.c_longlong), ("ldb", C.c_longlong), ("a_mn_major", C.c_int), ("b_mn_major", C.c_int),
         ("m", C.c_int), ("n", C.c_int), ("k", C.c_int), ("passes", C.c_int),
         ("c", C.c_void_p), ("ldc", C.c_longlong), ("bias", C.c_void_p), ("split_k", C.c_int),
-        ("accumulate", C.c_int), ("block_n", C.c_int), ("stages", C.c_int),
+        ("accumulate", C.c_int), ("force_m128", C.c_int), ("block_n", C.c_int), ("stages", C.c_int),
     ]
 
 
@@ -395,7 +395,7 @@ def split_planes(x, transpose=False, want_lo=True):
 
 
 def gemm(a_hi, a_lo, b_hi, b_lo, m, n, k, passes, out=None, bias=None, a_mn=False, b_mn=False, split_k=1,
-         block_n=0, stages=0, check=False, accumulate=False, tag="gemm"):
+         block_n=0, stages=0, check=False, accumulate=False, tag="gemm", force_m128=False):
     """C[m,n] = A * B^T.  Planes are 2-D bf16 tensors: A is [m,k] (or [k,m] if a_mn), B is [n,k] (or [k,n])."""
     lib = load()
     dev = a_hi.device
@@ -410,6 +410,7 @@ def gemm(a_hi, a_lo, b_hi, b_lo, m, n, k, passes, out=None, bias=None, a_mn=Fals
     d.bias = _ptr(bias)
     d.split_k, d.block_n, d.stages = split_k, block_n, stages
     d.accumulate = int(accumulate)
+    d.force_m128 = int(force_m128)
     fn = lib.gx_gemm_check if check else lib.gx_gemm
     with timed(tag, 2.0 * m * n * k):
         _check(fn(C.byref(d), _stream()), "gx_gemm")

@@ -31,10 +31,13 @@ constexpr int MAX_STAGES = 8;
 constexpr int NTHREADS = 256;
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_LIMIT = 227 * 1024;
+constexpr int STAGING_BYTES = 4 * 32 * 33 * 4;  // per-warp 32x33 fp32 transpose tiles of the epilogue
 
 struct UmmaParams {
   int mode;  // 0 = gemm, 1 = conv
   int passes, block_n, stages;
+  int mtiles;      // 128-row sub-tiles per CTA tile (2 = 256-row tiles, halves B traffic per FLOP)
+  int acc_stages;  // TMEM accumulator ring depth (2 when mtiles*block_n <= 256)
   int a_mn, b_mn;
   // ---- gemm
   int M, N, K;
@@ -78,7 +81,7 @@ __device__ __forceinline__ TileInfo decode_tile(const UmmaParams& p, int w) {
   const int tile_n = tmn % p.tiles_n;
   const int tile_m = tmn / p.tiles_n;
   t.n0 = tile_n * p.block_n;
-  t.m0 = tile_m * BM;
+  t.m0 = tile_m * BM * p.mtiles;
   t.phase = 0; t.b0 = 0; t.y0 = 0; t.x0 = 0;
   if (p.mode == 0) {
     const int per = (p.kiters_total + p.split_k - 1) / p.split_k;
@@ -115,13 +118,15 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
   const int b_plane_bytes = p.block_n * BK * 2;
   const int nplanes = (p.passes == 3) ? 2 : 1;
-  const int stage_bytes = nplanes * (A_PLANE_BYTES + b_plane_bytes);
+  const int a_plane_bytes = A_PLANE_BYTES * p.mtiles;
+  const int stage_bytes = nplanes * (a_plane_bytes + b_plane_bytes);
   uint64_t* bars = reinterpret_cast<uint64_t*>(smem + p.stages * stage_bytes);
   uint64_t* full_bar = bars;
   uint64_t* empty_bar = bars + MAX_STAGES;
   uint64_t* tfull_bar = bars + 2 * MAX_STAGES;
   uint64_t* tempty_bar = bars + 2 * MAX_STAGES + 2;
   uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(bars + 2 * MAX_STAGES + 4);
+  float* staging = reinterpret_cast<float*>(bars + 2 * MAX_STAGES + 6);
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
@@ -165,20 +170,21 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
         for (int kit = t.kbeg; kit < t.kend; ++kit) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
-          uint8_t* sb = sa + nplanes * A_PLANE_BYTES;
+          uint8_t* sb = sa + nplanes * a_plane_bytes;
           mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
           for (int pl = 0; pl < nplanes; ++pl) {
             const CUtensorMap* ma = pl ? &tm_a_lo : &tm_a_hi;
             const CUtensorMap* mb = pl ? &tm_b_lo : &tm_b_hi;
-            uint8_t* da = sa + pl * A_PLANE_BYTES;
+            uint8_t* da = sa + pl * a_plane_bytes;
             uint8_t* db = sb + pl * b_plane_bytes;
             if (p.mode == 0) {
               const int k0 = kit * BK;
               if (!p.a_mn) {
-                tma_load_2d(da, ma, &full_bar[stage], k0, t.m0);
+                for (int i = 0; i < p.mtiles; ++i)
+                  tma_load_2d(da + i * A_PLANE_BYTES, ma, &full_bar[stage], k0, t.m0 + i * BM);
               } else {
-                tma_load_2d(da, ma, &full_bar[stage], t.m0, k0);
-                tma_load_2d(da + 8192, ma, &full_bar[stage], t.m0 + 64, k0);
+                for (int i = 0; i < 2 * p.mtiles; ++i)
+                  tma_load_2d(da + i * 8192, ma, &full_bar[stage], t.m0 + i * 64, k0);
               }
               if (!p.b_mn) {
                 tma_load_2d(db, mb, &full_bar[stage], k0, t.n0);
@@ -210,28 +216,30 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
       int it = 0;
       for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
         const TileInfo t = decode_tile(p, w);
-        const int acc = it & 1;
-        const uint32_t acc_phase = (it >> 1) & 1;
+        const int acc = it % p.acc_stages;
+        const uint32_t acc_phase = (it / p.acc_stages) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
         tc_fence_after();
-        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.block_n);
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * p.mtiles * p.block_n);
         uint32_t accumulate = 0;
         for (int kit = t.kbeg; kit < t.kend; ++kit) {
           mbar_wait(&full_bar[stage], phase);
           tc_fence_after();
           const uint32_t sa = smem_u32(smem + stage * stage_bytes);
-          const uint32_t sb = sa + nplanes * A_PLANE_BYTES;
+          const uint32_t sb = sa + nplanes * a_plane_bytes;
           for (int ps = 0; ps < p.passes; ++ps) {
             // passes==3: (A_lo,B_hi) (A_hi,B_lo) (A_hi,B_hi); passes==1: (A_hi,B_hi)
             const int apl = (p.passes == 3 && ps == 0) ? 1 : 0;
             const int bpl = (p.passes == 3 && ps == 1) ? 1 : 0;
-            const uint32_t abase = sa + apl * A_PLANE_BYTES;
+            const uint32_t abase = sa + apl * a_plane_bytes;
             const uint32_t bbase = sb + bpl * b_plane_bytes;
 #pragma unroll
             for (int k4 = 0; k4 < BK / 16; ++k4) {
-              const uint64_t adesc = make_smem_desc(abase + k4 * a_kstep, a_lbo, 1024u);
               const uint64_t bdesc = make_smem_desc(bbase + k4 * b_kstep, b_lbo, 1024u);
-              umma_bf16(d_tmem, adesc, bdesc, idesc, accumulate);
+              for (int sub = 0; sub < p.mtiles; ++sub) {
+                const uint64_t adesc = make_smem_desc(abase + sub * A_PLANE_BYTES + k4 * a_kstep, a_lbo, 1024u);
+                umma_bf16(d_tmem + (uint32_t)(sub * p.block_n), adesc, bdesc, idesc, accumulate);
+              }
               accumulate = 1;
             }
           }
@@ -248,45 +256,46 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
     int it = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
       const TileInfo t = decode_tile(p, w);
-      const int acc = it & 1;
-      const uint32_t acc_phase = (it >> 1) & 1;
+      const int acc = it % p.acc_stages;
+      const uint32_t acc_phase = (it / p.acc_stages) & 1;
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
-      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.block_n);
+      const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.mtiles * p.block_n);
       const int nchunks = p.block_n / 32;
 
       if (p.mode == 0) {
-        const long long m = (long long)t.m0 + row;
-        const bool mvalid = m < p.M;
-        float* crow = p.c + m * p.ldc;
-        const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
+        // TMEM -> registers (thread = row) -> per-warp 32x33 smem tile -> registers (lane =
+        // column) so that every global store / atomic of a warp covers one contiguous 128 B row
+        // segment.
+        float* stg = staging + q * (32 * 33);
         const bool add_bias = p.bias != nullptr && (!p.atomic || t.kbeg == 0);
-        for (int ch = 0; ch < nchunks; ++ch) {
-          const int n_base = t.n0 + ch * 32;
-          if (n_base >= p.N) break;  // warp-uniform
-          uint32_t r[32];
-          tmem_ld_32x32(taddr0 + ch * 32, r);
-          tmem_ld_wait();
-          if (!mvalid) continue;
-          if (add_bias) {
+        for (int sub = 0; sub < p.mtiles; ++sub) {
+          const long long mrow0 = (long long)t.m0 + sub * BM + q * 32;   // first row of this warp
+          if (mrow0 >= p.M) break;                                        // warp-uniform
+          for (int ch = 0; ch < nchunks; ++ch) {
+            const int n_base = t.n0 + ch * 32;
+            if (n_base >= p.N) break;  // warp-uniform
+            uint32_t r[32];
+            tmem_ld_32x32(taddr0 + sub * p.block_n + ch * 32, r);
+            tmem_ld_wait();
 #pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (n_base + i < p.N) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(p.bias + n_base + i));
-          }
-          if (p.atomic) {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (n_base + i < p.N) atomicAdd(crow + n_base + i, __uint_as_float(r[i]));
-          } else if (vec_ok && n_base + 32 <= p.N) {
-            float4* dst = reinterpret_cast<float4*>(crow + n_base);
-#pragma unroll
-            for (int i = 0; i < 8; ++i)
-              dst[i] = make_float4(__uint_as_float(r[4 * i]), __uint_as_float(r[4 * i + 1]),
-                                   __uint_as_float(r[4 * i + 2]), __uint_as_float(r[4 * i + 3]));
-          } else {
-#pragma unroll
-            for (int i = 0; i < 32; ++i)
-              if (n_base + i < p.N) crow[n_base + i] = __uint_as_float(r[i]);
+            for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(r[i]);
+            __syncwarp();
+            const int n = n_base + lane;
+            const bool nvalid = n < p.N;
+            const float bv = (add_bias && nvalid) ? __ldg(p.bias + n) : 0.f;
+            float* cptr = p.c + mrow0 * p.ldc + n;
+            const int rows_valid = (int)min((long long)32, (long long)p.M - mrow0);
+            if (p.atomic) {
+#pragma unroll 8
+              for (int rr = 0; rr < 32; ++rr)
+                if (rr < rows_valid && nvalid) atomicAdd(cptr + (long long)rr * p.ldc, stg[rr * 33 + lane] + bv);
+            } else {
+#pragma unroll 8
+              for (int rr = 0; rr < 32; ++rr)
+                if (rr < rows_valid && nvalid) cptr[(long long)rr * p.ldc] = stg[rr * 33 + lane] + bv;
+            }
+            __syncwarp();
           }
         }
       } else {
@@ -417,10 +426,10 @@ int make_tmap(CUtensorMap* m, const void* base, int rank, const unsigned long lo
   return GX_OK;
 }
 
-int pick_stages(int passes, int block_n, int want) {
+int pick_stages(int passes, int block_n, int mtiles, int want) {
   const int nplanes = passes == 3 ? 2 : 1;
-  const int stage_bytes = nplanes * (A_PLANE_BYTES + block_n * BK * 2);
-  const int avail = SMEM_LIMIT - 1024 /*align slack*/ - 256 /*barriers*/;
+  const int stage_bytes = nplanes * (A_PLANE_BYTES * mtiles + block_n * BK * 2);
+  const int avail = SMEM_LIMIT - 1024 /*align slack*/ - 256 /*barriers*/ - STAGING_BYTES;
   int s = avail / stage_bytes;
   if (s > MAX_STAGES) s = MAX_STAGES;
   if (want > 0 && want < s) s = want;
@@ -429,8 +438,8 @@ int pick_stages(int passes, int block_n, int want) {
 
 int launch(const UmmaParams& p, const CUtensorMap* maps, int total_work, cudaStream_t st) {
   const int nplanes = p.passes == 3 ? 2 : 1;
-  const int stage_bytes = nplanes * (A_PLANE_BYTES + p.block_n * BK * 2);
-  const int smem_bytes = p.stages * stage_bytes + 256 + 1024;
+  const int stage_bytes = nplanes * (A_PLANE_BYTES * p.mtiles + p.block_n * BK * 2);
+  const int smem_bytes = p.stages * stage_bytes + 256 + STAGING_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {
     GX_CHECK_CUDA(cudaFuncSetAttribute(gx_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
@@ -462,9 +471,13 @@ extern "C" int gx_gemm(const gx_gemm_desc* d, void* stream) {
   if (bn == 0) bn = (d->n > 128) ? 256 : 128;
   GX_CHECK_ARG(bn == 64 || bn == 128 || bn == 256);
   p.block_n = bn;
-  p.stages = pick_stages(p.passes, bn, d->stages);
+  // 256-row tiles for single-pass GEMMs: one B tile in smem feeds two M=128 MMAs, which keeps the
+  // smem fill rate (L2 -> SM) at the level of the 3-pass mode instead of 1.5x above it
+  p.mtiles = (p.passes == 1 && bn == 256 && d->m > BM && !d->force_m128) ? 2 : 1;
+  p.acc_stages = (p.mtiles * bn <= 256) ? 2 : 1;
+  p.stages = pick_stages(p.passes, bn, p.mtiles, d->stages);
   GX_CHECK_ARG(p.stages >= 2);
-  p.tiles_m = gx_cdiv(d->m, BM);
+  p.tiles_m = gx_cdiv(d->m, BM * p.mtiles);
   p.tiles_n = gx_cdiv(d->n, bn);
   p.kiters_total = gx_cdiv(d->k, BK);
   int sk = d->split_k < 1 ? 1 : d->split_k;
@@ -534,7 +547,9 @@ extern "C" int gx_modconv(const gx_conv_desc* d, void* stream) {
   GX_CHECK_ARG(bn == 64 || bn == 128 || bn == 256);
   GX_CHECK_ARG(d->cout % 32 == 0);
   p.block_n = bn;
-  p.stages = pick_stages(p.passes, bn, d->stages);
+  p.mtiles = 1;
+  p.acc_stages = 2;
+  p.stages = pick_stages(p.passes, bn, 1, d->stages);
   GX_CHECK_ARG(p.stages >= 2);
   // pixel tile: 128 rows = nb images x th x tw
   const int ext_w = p.upsample ? d->w + 1 : d->w;

@@ -218,11 +218,12 @@ def scores_backward(head: SwavHead, fw, ds_hi, ds_lo):
                  tag="gemm_dzn_bwd")
     kit = (n + 63) // 64
     sms = L.load().gx_sinkhorn_max_parts()
-    sk1 = pick_split_k(math.ceil(k / 128) * math.ceil(c / 256), kit, sms)
+    bm = 256 if pb == 1 else 128     # the engine uses 256-row CTA tiles for single-pass GEMMs
+    sk1 = pick_split_k(math.ceil(k / bm) * math.ceil(c / 256), kit, sms)
     L.gemm(ds_hi, ds_lo if pb == 3 else None, fw["zn_hi"], fw["zn_lo"] if pb == 3 else None, k, c, n, pb,
            out=head.g_proto, a_mn=True, b_mn=True, split_k=sk1, accumulate=True, tag="gemm_gproto_bwd")
     dz_hi, dz_lo = L.l2norm_bwd_split(dzn, fw["zn_hi"], fw["zn_lo"], fw["inv"], want_lo=pb == 3)
-    sk2 = pick_split_k(math.ceil(c / 128) * math.ceil(d / 256), kit, sms)
+    sk2 = pick_split_k(math.ceil(c / bm) * math.ceil(d / 256), kit, sms)
     L.gemm(dz_hi, dz_lo, fw["a_hi"], fw["a_lo"] if pb == 3 else None, c, d, n, pb, out=head.g_proj, a_mn=True,
            b_mn=True, split_k=sk2, accumulate=True, tag="gemm_gproj_bwd")
 

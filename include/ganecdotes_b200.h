@@ -138,6 +138,7 @@ typedef struct gx_gemm_desc {
   const float* bias; /* [N] or NULL, added once                                  */
   int split_k;       /* >= 1; > 1 accumulates atomically into c (caller zeroes c) */
   int accumulate;    /* != 0: c += A*B^T (atomic adds) even when split_k == 1       */
+  int force_m128;    /* != 0: never use 256-row CTA tiles (tuning / tests)          */
   int block_n;       /* 0 = auto                                                 */
   int stages;        /* 0 = auto                                                 */
 } gx_gemm_desc;

@@ -100,6 +100,8 @@ def test_fused_leaky_relu_golden(L):
     (5000, 512, 3000, 1, 1, 1, 7, 0),       # gWk-shaped, both MN-major, split-K
     (520, 5376, 4096, 3, 1, 1, 4, 0),       # gWp-shaped
     (1, 8, 8, 3, 0, 0, 1, 1),               # minimum sizes
+    (4000, 512, 1024, 1, 0, 0, 1, 1),       # 256-row CTA tiles, K-major, ragged M
+    (300, 512, 2048, 1, 1, 0, 3, 0),        # 256-row tiles, MN-major A only
 ])
 def test_gemm_vs_fp64(L, m, n, k, passes, a_mn, b_mn, split, bias):
     torch.manual_seed(m + n + k)
