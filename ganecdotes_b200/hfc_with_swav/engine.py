@@ -198,16 +198,24 @@ def scores_forward(head: SwavHead, feats, out_h, out_w, hlen, row_img, row_src, 
     return dict(a_hi=a_hi, a_lo=a_lo, zn_hi=zn_hi, zn_lo=zn_lo, inv=inv, s=s, n=nrows)
 
 
-def sinkhorn_log_a(s, niters, eps, ws: L.SinkhornWorkspace, n_total, group=None, r=None, c=None):
+def sinkhorn_log_a(s, niters, eps, ws, n_total, group=None, r=None, c=None, pass_fn=None, log_a_fn=None):
     """Sinkhorn-Knopp in scaling-vector form (ref :509-544): niters streaming passes over
-    S; only u[K] crosses ranks.  Returns log a[K]; Q = softmax_k(S/eps + log a)."""
+    the LOCAL rows of S; only u[K] crosses ranks (all-reduce SUM, as in SwAV's distributed
+    Sinkhorn), and c_n = 1/n_total uses the GLOBAL row count.  Returns log a[K];
+    Q = softmax_k(S/eps + log a).
+
+    `pass_fn(s, inv_eps, first, u_in, r, c, n_total, ws) -> local column sums u[K]` and
+    `log_a_fn(u, r)` default to the CUDA kernels; the CPU tests of the multi-rank logic
+    inject torch stand-ins."""
+    pass_fn = pass_fn or L.sinkhorn_pass
+    log_a_fn = log_a_fn or L.sinkhorn_log_a
     inv_eps = 1.0 / eps
     u = None
     for it in range(niters):
-        u = L.sinkhorn_pass(s, inv_eps, it == 0, u, r, c, n_total, ws)
+        u = pass_fn(s, inv_eps, it == 0, u, r, c, n_total, ws)
         if group is not None:
             torch.distributed.all_reduce(u, group=group.pg)
-    return L.sinkhorn_log_a(u, r)
+    return log_a_fn(u, r)
 
 
 def scores_backward(head: SwavHead, fw, ds_hi, ds_lo):
