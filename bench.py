@@ -41,33 +41,55 @@ def peaks():
     return dict(hbm=6650.0, tf=1590.0, tf_sustained=1400.0, src="fallback")
 
 
-class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+class ClockSampler:
+    """`nvidia-smi -lms 100` running beside the timed region: SM clocks and throttle reasons."""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
-        super().__init__(daemon=True)
-        self.index, self.rows, self.stop_flag = index, [], False
+        self.index, self.proc, self.t0, self.t1 = index, None, None, None
 
-    def run(self):
-        while not self.stop_flag:
-            try:
-                out = subprocess.run(["nvidia-smi", "-i", str(self.index), f"--query-gpu={self.Q}",
-                                      "--format=csv,noheader,nounits"], capture_output=True, text=True, timeout=5)
-                if out.returncode == 0 and out.stdout.strip():
-                    self.rows.append([c.strip() for c in out.stdout.strip().split(",")])
-            except Exception:
-                pass
-            time.sleep(0.2)
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu=timestamp,{self.Q}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+        except Exception:
+            self.proc = None
+
+    def mark_begin(self):
+        self.t0 = time.time()
+
+    def mark_end(self):
+        self.t1 = time.time()
 
     def summary(self):
-        sm = [float(r[0]) for r in self.rows if r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if r[1].replace(".", "").isdigit()]
+        rows = []
+        if self.proc is not None:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                out, _ = self.proc.communicate(timeout=5)
+            except Exception:
+                out = ""
+            import datetime
+            for line in out.strip().splitlines():
+                c = [x.strip() for x in line.split(",")]
+                if len(c) < 7:
+                    continue
+                try:
+                    ts = datetime.datetime.strptime(c[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+                except Exception:
+                    continue
+                if self.t0 is not None and (ts < self.t0 - 0.05 or ts > self.t1 + 0.05):
+                    continue
+                rows.append(c[1:])
+        sm = [float(r[0]) for r in rows if r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if r[1].replace(".", "").isdigit()]
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        reasons = sorted({names[i] for r in self.rows for i in range(4) if len(r) > 2 + i and r[2 + i] == "Active"})
+        reasons = sorted({names[i] for r in rows for i in range(4) if len(r) > 2 + i and r[2 + i] == "Active"})
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": reasons, "samples": len(self.rows)}
+                "reasons": reasons, "samples": len(rows)}
 
 
 # ----------------------------------------------------------------------------------------
@@ -219,6 +241,9 @@ def run_ours(args):
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
+        time.sleep(0.3)
+    sync()
+    sampler.mark_begin()
     L.launch_count = 0
     L.event_log = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -228,7 +253,8 @@ def run_ours(args):
         loss = E.swav_train_step_device(gen, head, mean_latent, inputs[args.warmup + i], scfg, group, ws)
     e1.record()
     sync()
-    sampler.stop_flag = True
+    sampler.mark_end()
+    clocks = sampler.summary() if rank == 0 else None
     ms = e0.elapsed_time(e1)
     launches = L.launch_count
     log = L.event_log
@@ -267,15 +293,17 @@ def run_ours(args):
                             "split-bf16 GEMM issues 3x its algorithmic FLOPs on the tensor pipe"}
 
     # ---------------------------------------------------------------- end-to-end region
-    e2e_steps = max(1, min(args.steps, 3))
+    # public API from pinned host buffers: host bookkeeping + H2D of step i+1 are issued while
+    # the GPU runs step i; the loss of every step is read back to the host.
+    e2e_steps = max(1, min(args.steps, 5))
     sync()
     t0 = time.perf_counter()
-    h2d = 0
+    inp = E.prepare_step_inputs(gen, draws[args.warmup], scfg, dev)
+    h2d = inp.h2d_bytes
     for i in range(e2e_steps):
-        d = draws[args.warmup + i]
-        inp = E.prepare_step_inputs(gen, d, scfg, dev)
-        h2d = inp.h2d_bytes
         l = E.swav_train_step_device(gen, head, mean_latent, inp, scfg, group, ws)
+        if i + 1 < e2e_steps:
+            inp = E.prepare_step_inputs(gen, draws[args.warmup + (i + 1) % args.steps], scfg, dev)
         _ = float(l)                                                   # device -> host read of the loss
     sync()
     dt = time.perf_counter() - t0
@@ -305,7 +333,7 @@ def run_ours(args):
             "roofline": roofline, "roofline_stages": stage_rows[:14], "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": "vectors/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps},
-            "gpu_launches": launches, "clocks": sampler.summary(), "final_loss": final_loss,
+            "gpu_launches": launches, "clocks": clocks, "final_loss": final_loss,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -315,7 +343,7 @@ def run_ours(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--latents-per-gpu", type=int, default=8)

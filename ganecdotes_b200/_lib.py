@@ -53,6 +53,7 @@ class gx_gather_desc(C.Structure):
         ("out_h", C.c_int), ("out_w", C.c_int), ("hlen", C.c_int),
         ("row_img", C.c_void_p), ("row_src", C.c_void_p), ("nrows", C.c_longlong),
         ("a_hi", C.c_void_p), ("a_lo", C.c_void_p), ("a_f32", C.c_void_p), ("ld", C.c_longlong),
+        ("row_norm", C.c_void_p),
     ]
 
 
@@ -63,6 +64,7 @@ _SIGNATURES = {
     "gx_last_cuda_error": ([], _I),
     "gx_error_string": ([_I], C.c_char_p),
     "gx_device_ok": ([], _I),
+    "gx_set_sm_budget": ([_I, _I], _I),
     "gx_upfirdn2d": ([_P, _P, _P] + [_I] * 14 + [_P], _I),
     "gx_fused_bias_act": ([_P, _P, _P, _P, _LL, _I, _I, _I, _I, _F, _F, _P], _I),
     "gx_pixel_norm": ([_P, _P, _I, _I, _P], _I),
@@ -91,7 +93,8 @@ _SIGNATURES = {
                       _P], _I),
     "gx_larc_sgd": ([_P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _P, _P], _I),
     "gx_argmax_rows": ([_P, _LL, _I, _LL, _P, _P], _I),
-    "gx_kmeans_assign": ([_P, _LL, _I, _LL, _P, _I, _P, _P], _I),
+    "gx_kmeans_assign": ([_P, _I, _P, _I, _LL, _P, _I, _P, _P], _I),
+    "gx_onehot_nearest": ([_P, _I, _I, _I, _I, _I, _I, _P, _P], _I),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())
@@ -136,6 +139,11 @@ def _check(rc: int, what: str):
         if rc == -2:
             extra = f" (cuda error {lib.gx_last_cuda_error()})"
         raise GxError(f"{what}: {msg}{extra}")
+
+
+def set_sm_budget(umma_ctas=0, stream_ctas=0):
+    """CTA budgets of the persistent kernel families (0 = all SMs)."""
+    _check(load().gx_set_sm_budget(int(umma_ctas), int(stream_ctas)), "gx_set_sm_budget")
 
 
 def _ptr(t):
@@ -418,14 +426,16 @@ def gemm(a_hi, a_lo, b_hi, b_lo, m, n, k, passes, out=None, bias=None, a_mn=Fals
     return out
 
 
-def gather_rows(feats_nhwc, out_h, out_w, hlen, row_img, row_src, nrows, ld=None, want_lo=True, want_f32=False):
+def gather_rows(feats_nhwc, out_h, out_w, hlen, row_img, row_src, nrows, ld=None, want_lo=True, want_f32=False,
+                want_planes=True, want_norm=False):
     """feats_nhwc: list of fp32 [nimg,h,w,c] tensors -> A planes [nrows, ld] bf16"""
     lib = load()
     dev = feats_nhwc[0].device
     ld = ld or hlen
-    a_hi = torch.empty((nrows, ld), dtype=torch.bfloat16, device=dev)
-    a_lo = torch.empty_like(a_hi) if want_lo else None
+    a_hi = torch.empty((nrows, ld), dtype=torch.bfloat16, device=dev) if want_planes else None
+    a_lo = torch.empty_like(a_hi) if (want_lo and want_planes) else None
     a_f = torch.empty((nrows, ld), dtype=torch.float32, device=dev) if want_f32 else None
+    nrm = torch.empty((nrows,), dtype=torch.float32, device=dev) if want_norm else None
     d = gx_gather_desc()
     d.nlevels = len(feats_nhwc)
     for i, f in enumerate(feats_nhwc):
@@ -435,9 +445,12 @@ def gather_rows(feats_nhwc, out_h, out_w, hlen, row_img, row_src, nrows, ld=None
     d.out_h, d.out_w, d.hlen = out_h, out_w, hlen
     d.row_img, d.row_src, d.nrows = _ptr(row_img), _ptr(row_src), nrows
     d.a_hi, d.a_lo, d.a_f32, d.ld = _ptr(a_hi), _ptr(a_lo), _ptr(a_f), ld
+    d.row_norm = _ptr(nrm)
     with timed("gather_rows", float(nrows) * hlen * (4 + (4 if want_lo else 2))):
         _check(lib.gx_gather_rows(C.byref(d), _stream()), "gx_gather_rows")
     _count()
+    if want_norm:
+        return a_hi, a_lo, a_f, nrm
     return a_hi, a_lo, a_f
 
 
@@ -563,12 +576,26 @@ def argmax_rows(x):
     return labels
 
 
-def kmeans_assign(x, centers):
+def kmeans_assign(x, centers, x2=None):
+    """x [n,c1] (+ x2 [n,c2]) fp32 contiguous, centers [k,c1+c2] -> int32 labels [n]"""
     lib = load()
-    _f32(centers, "centers")
-    n, c = x.shape
+    _f32(centers, "centers"), _f32(x, "x"), _f32(x2, "x2")
+    n, c1 = x.shape
+    c2 = 0 if x2 is None else x2.shape[1]
+    if centers.shape[1] != c1 + c2:
+        raise GxError("kmeans_assign: centers must have c1+c2 columns")
     labels = torch.empty((n,), dtype=torch.int32, device=x.device)
-    _check(lib.gx_kmeans_assign(_ptr(x), n, c, x.stride(0), _ptr(centers), centers.shape[0], _ptr(labels), _stream()),
-           "gx_kmeans_assign")
+    _check(lib.gx_kmeans_assign(_ptr(x), c1, _ptr(x2), c2, n, _ptr(centers), centers.shape[0], _ptr(labels),
+                                _stream()), "gx_kmeans_assign")
     _count()
     return labels
+
+
+def onehot_nearest(labels_bhw, k, out_h, out_w):
+    lib = load()
+    b, h, w = labels_bhw.shape
+    out = torch.empty((b, k, out_h, out_w), dtype=torch.float32, device=labels_bhw.device)
+    _check(lib.gx_onehot_nearest(_ptr(labels_bhw), b, h, w, k, out_h, out_w, _ptr(out), _stream()),
+           "gx_onehot_nearest")
+    _count()
+    return out

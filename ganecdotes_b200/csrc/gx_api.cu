@@ -16,6 +16,19 @@ int gx_sm_count() {
   return n;
 }
 
+// SM budgets of the two kernel families (0 = all SMs).  They let a caller run tensor-bound
+// contractions and HBM-bound streaming kernels side by side on disjoint SM sets.
+static int g_umma_ctas = 0, g_stream_ctas = 0;
+int gx_umma_cta_budget() { return g_umma_ctas > 0 ? g_umma_ctas : gx_sm_count(); }
+int gx_stream_cta_budget() { return g_stream_ctas > 0 ? g_stream_ctas : gx_sm_count(); }
+
+extern "C" int gx_set_sm_budget(int umma_ctas, int stream_ctas) {
+  if (umma_ctas < 0 || stream_ctas < 0) return GX_ERR_ARG;
+  g_umma_ctas = umma_ctas;
+  g_stream_ctas = stream_ctas;
+  return GX_OK;
+}
+
 extern "C" int gx_version(void) { return 100; }
 
 extern "C" int gx_last_cuda_error(void) { return g_last_cuda_error; }

@@ -26,6 +26,8 @@
 
 void gx_set_last_cuda_error(int e);
 int gx_sm_count();
+int gx_umma_cta_budget();
+int gx_stream_cta_budget();
 
 static inline int gx_cdiv(long long a, long long b) { return (int)((a + b - 1) / b); }
 

@@ -28,9 +28,10 @@ gather_rows_kernel(const gx_gather_desc d) {
   }
   const int sy = src >= 0 ? src / d.out_w : 0;
   const int sx = src >= 0 ? src - sy * d.out_w : 0;
-  uint2* ah = reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.a_hi) + r * d.ld);
+  uint2* ah = d.a_hi ? reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.a_hi) + r * d.ld) : nullptr;
   uint2* al = d.a_lo ? reinterpret_cast<uint2*>(reinterpret_cast<__nv_bfloat16*>(d.a_lo) + r * d.ld) : nullptr;
   float4* af = d.a_f32 ? reinterpret_cast<float4*>(d.a_f32 + r * d.ld) : nullptr;
+  float ss = 0.f;
   int off = 0;
   for (int l = 0; l < d.nlevels && off < d.hlen; ++l) {
     const int cl = d.c[l];
@@ -43,20 +44,30 @@ gather_rows_kernel(const gx_gather_desc d) {
     for (int q = threadIdx.x; q < (keep >> 2); q += blockDim.x) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (src >= 0) v = __ldg(f + q);
-      uint2 h, lo;
-      gx_split4(v, h, lo);
       const int o = (off >> 2) + q;
-      ah[o] = h;
-      if (al) al[o] = lo;
+      if (ah) {
+        uint2 h, lo;
+        gx_split4(v, h, lo);
+        ah[o] = h;
+        if (al) al[o] = lo;
+      }
       if (af) af[o] = v;
+      ss += v.x * v.x + v.y * v.y + v.z * v.z + v.w * v.w;
     }
     off += keep;
   }
   // zero the padding columns [hlen, ld)
   for (int q = (d.hlen >> 2) + threadIdx.x; q < (int)(d.ld >> 2); q += blockDim.x) {
-    ah[q] = make_uint2(0u, 0u);
+    if (ah) ah[q] = make_uint2(0u, 0u);
     if (al) al[q] = make_uint2(0u, 0u);
     if (af) af[q] = make_float4(0.f, 0.f, 0.f, 0.f);
+  }
+  if (d.row_norm) {   // ||row||_2 (ref: torch.norm(hfeat, p=2, dim=1), swav_clustering.py:361-362)
+    __shared__ float red[4];
+    ss = gx_warp_sum(ss);
+    if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = ss;
+    __syncthreads();
+    if (threadIdx.x == 0) d.row_norm[r] = sqrtf(red[0] + red[1] + red[2] + red[3]);
   }
 }
 
@@ -685,19 +696,28 @@ __global__ void argmax_rows_kernel(const float* __restrict__ x, long long n, int
   if (lane == 0) labels[row] = (long long)bi;
 }
 
-__global__ void kmeans_assign_kernel(const float* __restrict__ x, long long n, int c, long long ldx,
-                                     const float* __restrict__ centers, int k, int* __restrict__ labels) {
+// x = concat(x1 [n,c1], x2 [n,c2]) along channels (x2 may be null): the two maps of one
+// resolution are never concatenated in memory
+__global__ void kmeans_assign_kernel(const float* __restrict__ x1, int c1, const float* __restrict__ x2, int c2,
+                                     long long n, const float* __restrict__ centers, int k,
+                                     int* __restrict__ labels) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
-  const float* xr = x + row * ldx;
+  const float* xr1 = x1 + row * c1;
+  const float* xr2 = x2 ? x2 + row * c2 : nullptr;
+  const int c = c1 + c2;
   float best = INFINITY;
   int bi = 0;
   for (int kk = 0; kk < k; ++kk) {
     const float* cr = centers + (long long)kk * c;
     float d = 0.f;
-    for (int i = lane; i < c; i += 32) {
-      const float t = xr[i] - __ldg(cr + i);
+    for (int i = lane; i < c1; i += 32) {
+      const float t = xr1[i] - __ldg(cr + i);
+      d = fmaf(t, t, d);
+    }
+    for (int i = lane; i < c2; i += 32) {
+      const float t = xr2[i] - __ldg(cr + c1 + i);
       d = fmaf(t, t, d);
     }
     d = gx_warp_sum(d);
@@ -706,16 +726,34 @@ __global__ void kmeans_assign_kernel(const float* __restrict__ x, long long n, i
   if (lane == 0) labels[row] = bi;
 }
 
+// one-hot cluster maps resized with nearest neighbour (ref hfc_kmeans_clustering.py:190-206)
+__global__ void onehot_nearest_kernel(const int* __restrict__ labels, int b, int h, int w, int k, int oh, int ow,
+                                      float* __restrict__ out) {
+  const long long total = (long long)b * k * oh * ow;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    long long r = i;
+    const int ox = (int)(r % ow); r /= ow;
+    const int oy = (int)(r % oh); r /= oh;
+    const int kk = (int)(r % k);
+    const int bb = (int)(r / k);
+    const int sy = (int)(((long long)oy * h) / oh), sx = (int)(((long long)ox * w) / ow);
+    out[i] = labels[((long long)bb * h + sy) * w + sx] == kk ? 1.f : 0.f;
+  }
+}
+
 inline int sk_grid(long long n, int rows_per_iter) {
   long long g = (n + rows_per_iter - 1) / rows_per_iter;
-  const int cap = gx_sm_count();
+  const int cap = gx_stream_cta_budget();
   return (int)(g < cap ? (g < 1 ? 1 : g) : cap);
 }
 
 }  // namespace
 
 extern "C" int gx_gather_rows(const gx_gather_desc* d, void* stream) {
-  GX_CHECK_ARG(d && d->a_hi && d->nlevels > 0 && d->nlevels <= GX_MAX_LEVELS && d->nrows > 0);
+  GX_CHECK_ARG(d && (d->a_hi || d->a_f32 || d->row_norm) && d->nlevels > 0 && d->nlevels <= GX_MAX_LEVELS &&
+               d->nrows > 0);
+  GX_CHECK_ARG(d->a_lo == nullptr || d->a_hi != nullptr);
   GX_CHECK_ARG(d->hlen % 4 == 0 && d->ld % 4 == 0 && d->ld >= d->hlen);
   GX_CHECK_ARG(d->nrows < (1ll << 31));
   for (int l = 0; l < d->nlevels; ++l) GX_CHECK_ARG(d->feat[l] && d->c[l] % 4 == 0 && d->h[l] > 0 && d->w[l] > 0);
@@ -946,10 +984,23 @@ extern "C" int gx_argmax_rows(const float* x, long long n, int c, long long ldx,
   return GX_OK;
 }
 
-extern "C" int gx_kmeans_assign(const float* x, long long n, int c, long long ldx, const float* centers, int k,
-                                int* labels, void* stream) {
-  GX_CHECK_ARG(x && centers && labels && n > 0 && c > 0 && k > 0);
-  kmeans_assign_kernel<<<gx_cdiv(n, 8), 256, 0, (cudaStream_t)stream>>>(x, n, c, ldx, centers, k, labels);
+extern "C" int gx_kmeans_assign(const float* x1, int c1, const float* x2, int c2, long long n, const float* centers,
+                                int k, int* labels, void* stream) {
+  GX_CHECK_ARG(x1 && centers && labels && n > 0 && c1 > 0 && k > 0 && c2 >= 0);
+  GX_CHECK_ARG((x2 != nullptr) == (c2 > 0));
+  kmeans_assign_kernel<<<gx_cdiv(n, 8), 256, 0, (cudaStream_t)stream>>>(x1, c1, x2, c2, n, centers, k, labels);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_onehot_nearest(const int* labels, int b, int h, int w, int k, int out_h, int out_w, float* out,
+                                 void* stream) {
+  GX_CHECK_ARG(labels && out && b > 0 && h > 0 && w > 0 && k > 0 && out_h > 0 && out_w > 0);
+  const long long total = (long long)b * k * out_h * out_w;
+  int grid = gx_cdiv(total, 256);
+  const int cap = gx_sm_count() * 16;
+  if (grid > cap) grid = cap;
+  onehot_nearest_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(labels, b, h, w, k, out_h, out_w, out);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }

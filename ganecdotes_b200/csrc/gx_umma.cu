@@ -445,7 +445,7 @@ int launch(const UmmaParams& p, const CUtensorMap* maps, int total_work, cudaStr
     GX_CHECK_CUDA(cudaFuncSetAttribute(gx_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set = true;
   }
-  int grid = gx_sm_count();
+  int grid = gx_umma_cta_budget();
   if (grid > total_work) grid = total_work;
   if (grid < 1) return GX_OK;
   gx_umma_kernel<<<grid, NTHREADS, smem_bytes, st>>>(p, maps[0], maps[1], maps[2], maps[3], total_work);

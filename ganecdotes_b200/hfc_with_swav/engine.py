@@ -189,6 +189,8 @@ class SwavHead:
 def scores_forward(head: SwavHead, feats, out_h, out_w, hlen, row_img, row_src, nrows):
     """gather -> projection -> normalise -> prototype scores.  Returns a dict of the
     tensors the backward needs."""
+    if hlen % 8:
+        raise ValueError("hlen must be a multiple of 8 (16-byte TMA row pitch of the bf16 operand planes)")
     lo = head.passes_fwd == 3
     a_hi, a_lo, _ = L.gather_rows(feats, out_h, out_w, hlen, row_img, row_src, nrows, want_lo=lo)
     z = L.gemm(a_hi, a_lo, head.wp_hi, head.wp_lo, nrows, head.c, hlen, head.passes_fwd, tag="gemm_projection_fwd")
@@ -243,6 +245,22 @@ class DistGroup:
     world: int
 
 
+def image_marginals(feats, out_h, out_w, hlen, index_map, k, n):
+    """source_pdf == 'image' (ref :361-362, :523-532): per-pixel L2 norm of the transformed
+    feature tensor -> histograms with K and N bins -> Sinkhorn marginals r[K], c[N].
+    index_map: int32 [H*W] device tensor (rotate/flip source pixels).  Single image only."""
+    _, _, _, nrm = L.gather_rows(feats, out_h, out_w, hlen, torch.zeros_like(index_map), index_map,
+                                 index_map.numel(), want_lo=False, want_planes=False, want_norm=True)
+    img = nrm.view(1, out_h, out_w)
+    histb = torch.histc(img, n) + 1e-9
+    histb[0] = histb[1]
+    histb = histb / histb.sum()
+    histk = torch.histc(img, k) + 1e-9
+    histk[0] = histk[1]
+    histk = histk / histk.sum()
+    return histk.contiguous(), histb.contiguous()
+
+
 @dataclass
 class StepConfig:
     hlen: int
@@ -254,6 +272,7 @@ class StepConfig:
     truncation: float
     perturb_std: List[float]
     need_image: bool = False
+    source_pdf: str = 'uniform'
 
 
 @dataclass
@@ -263,6 +282,7 @@ class StepInputs:
     views: dict                        # name -> (layer_no list, pert rows [2B, D] on device)
     rows: dict                         # name -> (row_src [P, B*N] int32, row_img [B*N] int32)
     h2d_bytes: int = 0
+    index_maps: Optional[dict] = None  # name -> int32 [H*W] (source_pdf == 'image', single latent)
 
 
 def prepare_step_inputs(gen, draws: StepDraws, cfg: StepConfig, device) -> StepInputs:
@@ -281,7 +301,16 @@ def prepare_step_inputs(gen, draws: StepDraws, cfg: StepConfig, device) -> StepI
         rs, ri = build_row_indices(out_h, out_w, view, draws.perms, cfg.patch_size, device)
         rows[name] = (rs, ri)
         nbytes += pr.numel() * 4 + rs.numel() * 4 + ri.numel() * 4
-    return StepInputs(z=z, views=views, rows=rows, h2d_bytes=nbytes)
+    index_maps = None
+    if cfg.source_pdf == 'image':
+        if draws.z.shape[0] != 1:
+            raise NotImplementedError("source_pdf='image' is defined for one latent per step (as in the reference)")
+        index_maps = {}
+        for name, view in (("s", draws.view_s), ("t", draws.view_t)):
+            m = rotate_flip_index_map(out_h, out_w, view.angle[0], view.flip[0]).to(torch.int32)
+            index_maps[name] = m.to(device, non_blocking=True)
+            nbytes += m.numel() * 4
+    return StepInputs(z=z, views=views, rows=rows, h2d_bytes=nbytes, index_maps=index_maps)
 
 
 @torch.no_grad()
@@ -334,8 +363,12 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
         for name in ("s", "t"):
             row_src, row_img = inp.rows[name]
             fw[name] = scores_forward(head, feats[name], out_h, out_w, cfg.hlen, row_img, row_src[p], n_local)
-        la_s = sinkhorn_log_a(fw["s"]["s"], cfg.niters, cfg.eps, ws, n_total, group)
-        la_t = sinkhorn_log_a(fw["t"]["s"], cfg.niters, cfg.eps, ws, n_total, group)
+        rc_s = rc_t = (None, None)
+        if cfg.source_pdf == 'image':
+            rc_s = image_marginals(feats["s"], out_h, out_w, cfg.hlen, inp.index_maps["s"], head.k, n_local)
+            rc_t = image_marginals(feats["t"], out_h, out_w, cfg.hlen, inp.index_maps["t"], head.k, n_local)
+        la_s = sinkhorn_log_a(fw["s"]["s"], cfg.niters, cfg.eps, ws, n_total, group, rc_s[0], rc_s[1])
+        la_t = sinkhorn_log_a(fw["t"]["s"], cfg.niters, cfg.eps, ws, n_total, group, rc_t[0], rc_t[1])
         lo = head.passes_bwd == 3
         loss_parts, ds_s, ds_t, db, _ = L.swav_loss(fw["s"]["s"], fw["t"]["s"], 1.0 / cfg.eps, 1.0 / cfg.temperature,
                                                     la_s, la_t, grad_scale, want_lo=lo)
@@ -366,6 +399,8 @@ def predict_codes(gen, w_proj, w, mean_latent, truncation, hlen, passes=3, image
     """predict_swav_codes (ref :659-693): generator forward with the fixed noise buffers,
     per-pixel vectors, projection only, arg-max over the code channels.
     Returns (codes [B,C,H,W] fp32 in channels_last memory, labels int64 [B,H,W])."""
+    if hlen % 8:
+        raise ValueError("hlen must be a multiple of 8 (16-byte TMA row pitch of the bf16 operand planes)")
     dev = w_proj.device
     mean = mean_latent.reshape(-1).float().contiguous()
     w = w.to(dev).float().contiguous()

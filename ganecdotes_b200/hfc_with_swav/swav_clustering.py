@@ -103,7 +103,8 @@ class SwAVClustering(object):
         return E.StepConfig(hlen=self.swav_args['hlen'], patch_size=self.swav_args['patch_size'],
                             num_patches=self.swav_args['num_patches'], niters=self.niters, eps=self.eps,
                             temperature=self.swav_args['temperature'], truncation=self.truncation,
-                            perturb_std=list(self.perturb_args['perturb_std']))
+                            perturb_std=list(self.perturb_args['perturb_std']),
+                            source_pdf=self.sinkhorn_args.get('source_pdf', 'uniform'))
 
     def _draw_view(self, b, layer_no):
         n_layers = self.perturb_args['n_layers']

@@ -27,6 +27,9 @@ int gx_version(void);
 int gx_last_cuda_error(void);             /* cudaError_t of the last GX_ERR_CUDA  */
 const char* gx_error_string(int gx_code); /* static string                        */
 int gx_device_ok(void);                   /* 1 if the current device is sm_100    */
+/* CTA (= SM) budgets of the persistent kernels: tcgen05 contractions and the streaming
+ * Sinkhorn/loss kernels; 0 = all SMs.  Disjoint budgets let both families run concurrently. */
+int gx_set_sm_budget(int umma_ctas, int stream_ctas);
 
 /* ------------------------------------------------------------------------------------
  * L0 native ops of the reference
@@ -172,10 +175,11 @@ typedef struct gx_gather_desc {
   const int* row_img;
   const int* row_src;
   long long nrows;
-  void* a_hi; /* bf16 [nrows, ld]                                              */
+  void* a_hi; /* bf16 [nrows, ld]; may be NULL when only a_f32 / row_norm are wanted */
   void* a_lo; /* may be NULL                                                   */
   float* a_f32; /* optional fp32 copy [nrows, ld] (tests), may be NULL          */
   long long ld;
+  float* row_norm; /* optional [nrows]: L2 norm of every gathered row (ref :361-362)     */
 } gx_gather_desc;
 
 /* nearest-upsample + concat + [:hlen] + rotate/flip + random-pixel sampling in one
@@ -248,11 +252,16 @@ int gx_larc_sgd(float* p, const float* g, float* buf, long long n, float lr, flo
 /* labels[n] = first argmax_c x[n,c]  (ref: out_preds.max(1)[1], swav_clustering.py:691). int64 out. */
 int gx_argmax_rows(const float* x, long long n, int c, long long ldx, long long* labels, void* stream);
 
-/* k-means assignment: labels[n] = first argmin_k ||x_n - c_k||^2
- * (ref: baseline/hfc_kmeans/hfc_kmeans_clustering.py:184).  x [n,c] fp32 (row stride ldx),
- * centers [k,c]; int32 out; optional one-hot map written by the caller. */
-int gx_kmeans_assign(const float* x, long long n, int c, long long ldx, const float* centers, int k, int* labels,
-                     void* stream);
+/* k-means assignment: labels[n] = first argmin_k ||x_n - c_k||^2 with x_n = concat(x1[n,:c1], x2[n,:c2])
+ * (the two same-resolution maps the reference concatenates, image_augmentor.py:80-90; x2 may be NULL)
+ * (ref: clusterer.predict, baseline/hfc_kmeans/hfc_kmeans_clustering.py:184).  centers [k,c1+c2]; int32 out. */
+int gx_kmeans_assign(const float* x1, int c1, const float* x2, int c2, long long n, const float* centers, int k,
+                     int* labels, void* stream);
+
+/* one-hot cluster maps [b,k,out_h,out_w] from labels [b,h,w], nearest-neighbour resize
+ * (ref: hfc_kmeans_clustering.py:190-206). */
+int gx_onehot_nearest(const int* labels, int b, int h, int w, int k, int out_h, int out_w, float* out,
+                      void* stream);
 
 #ifdef __cplusplus
 }

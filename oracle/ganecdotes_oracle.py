@@ -442,11 +442,12 @@ def larc_sgd_step(params: List[torch.Tensor], grads: List[torch.Tensor],
 
 def swav_step(rows_s: List[torch.Tensor], rows_t: List[torch.Tensor], w_proj, w_proto, b_proto,
               niters: int, eps: float, temperature: float, bufs=None, lr=0.01, momentum=0.9,
-              trust=0.01):
+              trust=0.01, marginals=None):
     """One optimiser step of the pretrain loop (swav_clustering.py:377-460) given
     the sampled per-pixel rows of every patch: rows_s[p], rows_t[p] are [N_p, D]
     (for a batch of latents: the row-concatenation over latents = SwAV's joint /
     distributed Sinkhorn).  Prototype rows are re-normalised first.
+    marginals: ((r_s, c_s), (r_t, c_t)) for source_pdf == 'image' (:523-532), else uniform.
     Returns dict(loss, grads, new params, bufs, per-patch scores/Q)."""
     w_proto = normalize_prototypes(w_proto.detach())
     wp = w_proj.detach().clone().requires_grad_(True)
@@ -457,9 +458,10 @@ def swav_step(rows_s: List[torch.Tensor], rows_t: List[torch.Tensor], w_proj, w_
     for rs, rt in zip(rows_s, rows_t):
         s_s = swav_scores(rs, wp, wk, bk)
         s_t = swav_scores(rt, wp, wk, bk)
+        (r_s, c_s), (r_t, c_t) = marginals if marginals is not None else ((None, None), (None, None))
         with torch.no_grad():
-            q_s = sinkhorn_knopp(s_s, niters, eps)
-            q_t = sinkhorn_knopp(s_t, niters, eps)
+            q_s = sinkhorn_knopp(s_s, niters, eps, r_s, c_s)
+            q_t = sinkhorn_knopp(s_t, niters, eps, r_t, c_t)
         loss = loss + swapped_prediction_loss(s_s / temperature, s_t / temperature, q_s, q_t)
         dbg.append((s_s.detach(), s_t.detach(), q_s, q_t))
     loss = loss / len(rows_s)

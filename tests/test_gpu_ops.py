@@ -397,9 +397,30 @@ def test_argmax_and_kmeans(L):
     got = L.kmeans_assign(xv.cuda(), c.cuda())
     assert got.dtype == torch.int32
     assert torch.equal(got.cpu(), O.kmeans_assign(xv, c))
+    got2 = L.kmeans_assign(xv[:, :64].contiguous().cuda(), c.cuda(), xv[:, 64:].contiguous().cuda())
+    assert torch.equal(got2, got)
     # exact ties -> first centre
     c2 = torch.stack([c[0], c[1], c[1]])
     assert set(L.kmeans_assign(c2.cuda(), c2.cuda()).cpu().tolist()) <= {0, 1}
+
+
+def test_kmeans_layer_maps_vs_oracle(L):
+    """config 5: per-layer assignment + one-hot NEAREST maps on generator features"""
+    from ganecdotes_b200.hfc_kmeans.hfc_kmeans_clustering import FlatKMeansAssign
+    torch.manual_seed(4)
+    b = 2
+    shapes = [(32, 4)] + [(32, 8), (32, 8), (16, 16), (16, 16)]
+    feats = [torch.randn(b, c, r, r) for c, r in shapes]
+    ks = [4, 8]
+    centers = [torch.randn(ks[0], 64), torch.randn(ks[1], 32)]
+    pairs = [torch.cat([feats[2 * n + 1], feats[2 * n + 2]], 1) for n in range(2)]
+    ref_maps, ref_labels = O.kmeans_layer_maps(pairs, centers, 32)
+    ref_maps = (ref_maps + 1) / 2          # the oracle helper returns the {-1,+1} encoding
+    km = FlatKMeansAssign(centers, out_size=32)
+    maps, labels = km.predict([f.cuda().contiguous(memory_format=torch.channels_last) for f in feats])
+    for a, r in zip(labels, ref_labels):
+        assert torch.equal(a.cpu(), r)
+    assert torch.equal(maps.cpu(), ref_maps)
 
 
 def test_split_planes(L):

@@ -257,3 +257,59 @@ def test_api_parity_methods(gen, tmp_path):
     torch.testing.assert_close(sc.cpu(), ref, rtol=1e-3, atol=2e-4)
     codes = obj.get_swav_codes_from_hidden_features(hf, (1, 64, 16, 16), train=False)
     assert tuple(codes.shape) == (1, 64, 16, 16)
+
+
+def test_image_source_pdf_step_matches_oracle(gen):
+    """source_pdf == 'image' (cat config): Sinkhorn marginals from histograms of the per-pixel
+    feature norm of the transformed tensor (ref :361-362, :523-532)."""
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    sd = O.init_generator_state(16, 64, 2, 7)
+    torch.manual_seed(2)
+    hlen, c, k, patch, npatch = 2560, 64, 48, 128, 1
+    wp = torch.randn(c, hlen) / hlen ** 0.5
+    wk = torch.randn(k, c)
+    bk = 0.05 * torch.randn(k)
+    mean_latent = O.style_mlp(sd, torch.randn(64, 64)).mean(0, keepdim=True)
+    pstd = [1.0, 1.0, 1.0]
+    draws = make_draws(1, 64, 3, 256, npatch, 21)
+    w = O.style_mlp(sd, draws.z)
+    rows, marg = {}, []
+    for name, view in (("s", draws.view_s), ("t", draws.view_t)):
+        hf, _ = O.view_features(sd, w, mean_latent, 0.7, view.layer_no[0], view.pert_z[0], 3, pstd, hlen)
+        hf = O.rotate_flip(hf, view.angle[0], view.flip[0])
+        rows[name] = [O.sample_rows(hf, draws.perms[0][0], patch)]
+        marg.append(O.image_marginals(torch.norm(hf, p=2, dim=1), k, patch))
+    ref = O.swav_step(rows["s"], rows["t"], wp, wk, bk, 10, 0.02, 0.02, marginals=(marg[0], marg[1]))
+    head = E.SwavHead(wp.clone().cuda(), wk.clone().cuda(), bk.clone().cuda(), 0.01, 0.9, 0.01, 3, 3)
+    cfg = E.StepConfig(hlen=hlen, patch_size=patch, num_patches=npatch, niters=10, eps=0.02, temperature=0.02,
+                       truncation=0.7, perturb_std=pstd, source_pdf='image')
+    loss = E.swav_train_step(gen, head, mean_latent.cuda(), draws, cfg)
+    assert abs(loss.item() - ref["loss"].item()) < 3e-3 * abs(ref["loss"].item()), (loss.item(), ref["loss"])
+    for got, exp in zip((head.g_proj, head.g_proto, head.g_bias), ref["grads"]):
+        assert (got.cpu() - exp).norm().item() / exp.norm().item() < 2e-2
+
+
+@pytest.mark.parametrize("size", [32])
+def test_larger_generator_sliced_hlen(size):
+    """car-512-like case at reduced size: more feature channels than hlen, the slice [:hlen]
+    cuts through the concatenation; label map vs the oracle."""
+    from ganecdotes_b200.stylegan2.model import Generator
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    sd = O.init_generator_state(size, 64, 2, 9)
+    g = Generator(size, 64, 2)
+    g.load_state_dict(sd, strict=True)
+    g = g.cuda()
+    torch.manual_seed(0)
+    total = 512 * (1 + 2 * 3)
+    hlen = total - 304                      # not on a map boundary (TMA needs hlen % 8 == 0)
+    wp = torch.randn(48, hlen) / hlen ** 0.5
+    mean_latent = O.style_mlp(sd, torch.randn(32, 64)).mean(0, keepdim=True)
+    w = O.style_mlp(sd, torch.randn(2, 64))
+    ref_p, ref_l = O.predict_codes(sd, w, mean_latent, 0.7, wp, hlen)
+    preds, labels = E.predict_codes(g, wp.cuda(), w.cuda(), mean_latent.cuda(), 0.7, hlen)
+    assert (preds.cpu() - ref_p).abs().max().item() < 5e-4 * ref_p.abs().max().item()
+    mism = labels.cpu() != ref_l
+    if mism.any():
+        top2 = ref_p.topk(2, dim=1).values
+        assert (top2[:, 0] - top2[:, 1])[mism].max().item() < 1e-3 * ref_p.abs().max().item()
+    assert mism.float().mean().item() < 0.02
