@@ -2,6 +2,8 @@
 // Sinkhorn-Knopp passes, fused swapped-prediction loss fwd+bwd, LARC+SGD, arg-max label
 // maps and k-means assignment.  All kernels use 128-bit coalesced accesses and
 // warp-shuffle + shared-memory reductions; none of them is reshaped into a GEMM.
+#include <stdlib.h>
+
 #include "gx_common.cuh"
 #include "gx_ptx.cuh"
 
@@ -453,10 +455,15 @@ __device__ __forceinline__ void group_reduce(float (&v)[NV], float* red /* [NV][
 #pragma unroll
   for (int i = 0; i < NV; ++i) {
     float tot = IS_MAX ? -INFINITY : 0.f;
+    if constexpr (NW % 4 == 0) {
 #pragma unroll
-    for (int w = 0; w < NW; w += 4) {
-      const float4 q = *reinterpret_cast<const float4*>(red + i * NW + w);
-      tot = IS_MAX ? fmaxf(tot, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w))) : tot + ((q.x + q.y) + (q.z + q.w));
+      for (int w = 0; w < NW; w += 4) {
+        const float4 q = *reinterpret_cast<const float4*>(red + i * NW + w);
+        tot = IS_MAX ? fmaxf(tot, fmaxf(fmaxf(q.x, q.y), fmaxf(q.z, q.w))) : tot + ((q.x + q.y) + (q.z + q.w));
+      }
+    } else {
+#pragma unroll
+      for (int w = 0; w < NW; ++w) tot = IS_MAX ? fmaxf(tot, red[i * NW + w]) : tot + red[i * NW + w];
     }
     v[i] = tot;
   }
@@ -468,15 +475,15 @@ __device__ __forceinline__ uint32_t pack_bf16x2_rn(float a, float b) {
   return r;
 }
 
-template <int J, int GT>
-__global__ void __launch_bounds__(SK_THREADS, 1)
+template <int J, int GT, int NT>
+__global__ void __launch_bounds__(NT, 1)
 swav_loss_kernel(const float* __restrict__ ss, const float* __restrict__ st, long long n, int k, long long lds,
                  float inv_eps, float inv_temp, const float* __restrict__ la_s, const float* __restrict__ la_t,
                  float grad_scale, float* __restrict__ loss_parts, float* __restrict__ db_parts,
                  __nv_bfloat16* __restrict__ ds_s_hi, __nv_bfloat16* __restrict__ ds_s_lo,
                  __nv_bfloat16* __restrict__ ds_t_hi, __nv_bfloat16* __restrict__ ds_t_lo, long long ldd,
                  float* __restrict__ ds_s_f32, float* __restrict__ ds_t_f32, int stages) {
-  constexpr int NG = SK_THREADS / GT;
+  constexpr int NG = NT / GT;
   constexpr int NW = GT / 32;
   extern __shared__ __align__(128) uint8_t sk_smem[];
   __shared__ __align__(16) float red_max[NG][4 * NW];
@@ -508,22 +515,19 @@ swav_loss_kernel(const float* __restrict__ ss, const float* __restrict__ st, lon
   const float ce = inv_eps * LOG2E, ct = inv_temp * LOG2E;
   float* sla_s = reinterpret_cast<float*>(sk_smem + (size_t)stages * stage_bytes);
   float* sla_t = sla_s + k;
-  for (int i = tid; i < k; i += SK_THREADS) {
+  for (int i = tid; i < k; i += NT) {
     sla_s[i] = la_s[i] * LOG2E;
     sla_t[i] = la_t[i] * LOG2E;
   }
   __syncthreads();
+  // Out-of-range column slots (col >= k) read a clamped, valid address; their contributions to
+  // the sums are removed with a -inf additive mask and they store nothing.
   float db[J][4];
-  int coff[J];
-  bool colok[J];
 #pragma unroll
-  for (int j = 0; j < J; ++j) {
-    const int col = j * (GT * 4) + gt * 4;
-    colok[j] = col < k;
-    coff[j] = min(col, k - 4);
+  for (int j = 0; j < J; ++j)
 #pragma unroll
     for (int e = 0; e < 4; ++e) db[j][e] = 0.f;
-  }
+  const int col0 = gt * 4;
   float loss_acc = 0.f;
   const float gs = grad_scale * 0.5f * inv_temp;
   for (int it = grp; it < n_iters; it += NG) {
@@ -534,51 +538,54 @@ swav_loss_kernel(const float* __restrict__ ss, const float* __restrict__ st, lon
     const float* srow_t = srow_s + k;
     float vs[J][4], vt[J][4];     // raw scores, later softmax(p) numerators
     float e1s[J][4], e1t[J][4];   // log2-domain S/eps + log a, later q numerators
+    // pass 1: maxima.  Clamped slots re-read valid columns, which leaves the maxima unchanged.
     float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // max x1_s, max s_s, max x1_t, max s_t
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-      const float4 a = *reinterpret_cast<const float4*>(srow_s + coff[j]);
-      const float4 b = *reinterpret_cast<const float4*>(srow_t + coff[j]);
-      const float4 ls = *reinterpret_cast<const float4*>(sla_s + coff[j]);
-      const float4 lt = *reinterpret_cast<const float4*>(sla_t + coff[j]);
-      const float msk = colok[j] ? 0.f : -INFINITY;
+      const int cofs = min(col0 + j * (GT * 4), k - 4);
+      const float4 a = *reinterpret_cast<const float4*>(srow_s + cofs);
+      const float4 b = *reinterpret_cast<const float4*>(srow_t + cofs);
+      const float4 ls = *reinterpret_cast<const float4*>(sla_s + cofs);
+      const float4 lt = *reinterpret_cast<const float4*>(sla_t + cofs);
       vs[j][0] = a.x; vs[j][1] = a.y; vs[j][2] = a.z; vs[j][3] = a.w;
       vt[j][0] = b.x; vt[j][1] = b.y; vt[j][2] = b.z; vt[j][3] = b.w;
-      const float l2s[4] = {ls.x + msk, ls.y + msk, ls.z + msk, ls.w + msk};
-      const float l2t[4] = {lt.x + msk, lt.y + msk, lt.z + msk, lt.w + msk};
+      e1s[j][0] = fmaf(a.x, ce, ls.x); e1s[j][1] = fmaf(a.y, ce, ls.y);
+      e1s[j][2] = fmaf(a.z, ce, ls.z); e1s[j][3] = fmaf(a.w, ce, ls.w);
+      e1t[j][0] = fmaf(b.x, ce, lt.x); e1t[j][1] = fmaf(b.y, ce, lt.y);
+      e1t[j][2] = fmaf(b.z, ce, lt.z); e1t[j][3] = fmaf(b.w, ce, lt.w);
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
-        e1s[j][e] = fmaf(vs[j][e], ce, l2s[e]);
-        e1t[j][e] = fmaf(vt[j][e], ce, l2t[e]);
         mx[0] = fmaxf(mx[0], e1s[j][e]);
+        mx[1] = fmaxf(mx[1], vs[j][e]);
         mx[2] = fmaxf(mx[2], e1t[j][e]);
-        if (colok[j]) {
-          mx[1] = fmaxf(mx[1], vs[j][e]);
-          mx[3] = fmaxf(mx[3], vt[j][e]);
-        }
+        mx[3] = fmaxf(mx[3], vt[j][e]);
       }
     }
     group_reduce<4, true, NW>(mx, red_max[grp], gwarp, lane, 1 + grp, GT);   // stage consumed after this barrier
     if (gt == 0 && it + stages < n_iters) issue(it + stages);
-    // sums: Z1_s, Z2_s, D_st = sum e1s*s_t, Z1_t, Z2_t, D_ts = sum e1t*s_s
+    // pass 2: sums  Z1_s, Z2_s, D_st = sum e1s*s_t, Z1_t, Z2_t, D_ts = sum e1t*s_s
     float sm[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
     const float m2s = mx[1] * ct, m2t = mx[3] * ct;   // log2 domain
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-      const float msk = colok[j] ? 0.f : -INFINITY;
+      const float mskj = (col0 + j * (GT * 4) < k) ? 0.f : -INFINITY;
+      const float c1s = mskj - mx[0], c1t = mskj - mx[2];
+      const float c2s = mskj - m2s, c2t = mskj - m2t;
 #pragma unroll
       for (int e = 0; e < 4; ++e) {
         const float rs = vs[j][e], rt = vt[j][e];
-        e1s[j][e] = ex2_fast(e1s[j][e] - mx[0]);
-        e1t[j][e] = ex2_fast(e1t[j][e] - mx[2]);
-        sm[0] += e1s[j][e];
-        sm[3] += e1t[j][e];
-        sm[2] = fmaf(e1s[j][e], rt, sm[2]);
-        sm[5] = fmaf(e1t[j][e], rs, sm[5]);
-        vs[j][e] = ex2_fast(fmaf(rs, ct, msk - m2s));
-        vt[j][e] = ex2_fast(fmaf(rt, ct, msk - m2t));
-        sm[1] += vs[j][e];
-        sm[4] += vt[j][e];
+        const float q1s = ex2_fast(e1s[j][e] + c1s);
+        const float q1t = ex2_fast(e1t[j][e] + c1t);
+        const float p2s = ex2_fast(fmaf(rs, ct, c2s));
+        const float p2t = ex2_fast(fmaf(rt, ct, c2t));
+        sm[0] += q1s;
+        sm[3] += q1t;
+        sm[2] = fmaf(q1s, rt, sm[2]);
+        sm[5] = fmaf(q1t, rs, sm[5]);
+        sm[1] += p2s;
+        sm[4] += p2t;
+        e1s[j][e] = q1s; e1t[j][e] = q1t;
+        vs[j][e] = p2s; vt[j][e] = p2t;
       }
     }
     group_reduce<6, false, NW>(sm, red_sum[grp], gwarp, lane, 1 + grp, GT);
@@ -591,30 +598,34 @@ swav_loss_kernel(const float* __restrict__ ss, const float* __restrict__ st, lon
       const float qt_ps = sm[5] * iz1t * inv_temp - lse_s;
       loss_acc += -0.5f * (qs_pt + qt_ps);
     }
-    const float a2s = gs * iz2s, a1t = gs * iz1t, a2t = gs * iz2t, a1s = gs * iz1s;
+    // pass 3: gradients.  dL/dS_s uses q_t ; dL/dS_t uses q_s
+    const float a2s = gs * iz2s, a1t = -gs * iz1t, a2t = gs * iz2t, a1s = -gs * iz1s;
+    __nv_bfloat16* ps_hi = ds_s_hi + row * ldd;
+    __nv_bfloat16* pt_hi = ds_t_hi + row * ldd;
+    const bool want_lo = (ds_s_lo != nullptr) || (ds_t_lo != nullptr);
 #pragma unroll
     for (int j = 0; j < J; ++j) {
-      if (colok[j]) {
-        const int col = j * (GT * 4) + gt * 4;
-        float4 g_s, g_t;  // dL/dS_s uses q_t ; dL/dS_t uses q_s
-        g_s.x = vs[j][0] * a2s - e1t[j][0] * a1t; g_s.y = vs[j][1] * a2s - e1t[j][1] * a1t;
-        g_s.z = vs[j][2] * a2s - e1t[j][2] * a1t; g_s.w = vs[j][3] * a2s - e1t[j][3] * a1t;
-        g_t.x = vt[j][0] * a2t - e1s[j][0] * a1s; g_t.y = vt[j][1] * a2t - e1s[j][1] * a1s;
-        g_t.z = vt[j][2] * a2t - e1s[j][2] * a1s; g_t.w = vt[j][3] * a2t - e1s[j][3] * a1s;
+      const int col = col0 + j * (GT * 4);
+      if (col < k) {
+        float4 g_s, g_t;
+        g_s.x = fmaf(vs[j][0], a2s, e1t[j][0] * a1t); g_s.y = fmaf(vs[j][1], a2s, e1t[j][1] * a1t);
+        g_s.z = fmaf(vs[j][2], a2s, e1t[j][2] * a1t); g_s.w = fmaf(vs[j][3], a2s, e1t[j][3] * a1t);
+        g_t.x = fmaf(vt[j][0], a2t, e1s[j][0] * a1s); g_t.y = fmaf(vt[j][1], a2t, e1s[j][1] * a1s);
+        g_t.z = fmaf(vt[j][2], a2t, e1s[j][2] * a1s); g_t.w = fmaf(vt[j][3], a2t, e1s[j][3] * a1s);
         db[j][0] += g_s.x + g_t.x; db[j][1] += g_s.y + g_t.y;
         db[j][2] += g_s.z + g_t.z; db[j][3] += g_s.w + g_t.w;
-        if (ds_s_lo || ds_t_lo) {
+        if (want_lo) {
           uint2 h, l;
           gx_split4(g_s, h, l);
-          *reinterpret_cast<uint2*>(ds_s_hi + row * ldd + col) = h;
+          *reinterpret_cast<uint2*>(ps_hi + col) = h;
           if (ds_s_lo) *reinterpret_cast<uint2*>(ds_s_lo + row * ldd + col) = l;
           gx_split4(g_t, h, l);
-          *reinterpret_cast<uint2*>(ds_t_hi + row * ldd + col) = h;
+          *reinterpret_cast<uint2*>(pt_hi + col) = h;
           if (ds_t_lo) *reinterpret_cast<uint2*>(ds_t_lo + row * ldd + col) = l;
         } else {
-          *reinterpret_cast<uint2*>(ds_s_hi + row * ldd + col) =
+          *reinterpret_cast<uint2*>(ps_hi + col) =
               make_uint2(pack_bf16x2_rn(g_s.x, g_s.y), pack_bf16x2_rn(g_s.z, g_s.w));
-          *reinterpret_cast<uint2*>(ds_t_hi + row * ldd + col) =
+          *reinterpret_cast<uint2*>(pt_hi + col) =
               make_uint2(pack_bf16x2_rn(g_t.x, g_t.y), pack_bf16x2_rn(g_t.z, g_t.w));
         }
         if (ds_s_f32) *reinterpret_cast<float4*>(ds_s_f32 + row * (long long)k + col) = g_s;
@@ -902,24 +913,24 @@ extern "C" int gx_sinkhorn_q(const float* s, long long n, int k, long long lds, 
   return GX_OK;
 }
 
-template <int J, int GT>
+template <int J, int GT, int NT>
 static int launch_swav_loss(const float* s_s, const float* s_t, long long n, int k, long long lds, float inv_eps,
                             float inv_temp, const float* la_s, const float* la_t, float grad_scale, float* loss_parts,
                             float* db_parts, void* ds_s_hi, void* ds_s_lo, void* ds_t_hi, void* ds_t_lo,
                             long long ldd, float* fs, float* ft, int grid, cudaStream_t st) {
   const int stage_bytes = k * 4 * 2;
-  constexpr int NG = SK_THREADS / GT;
+  constexpr int NG = NT / GT;
   int stages = (200 * 1024 - stage_bytes) / stage_bytes;   // one stage worth of smem holds log2(a) of both views
   if (stages > 8) stages = 8;
   stages -= stages % NG;                                   // fixed stage ownership per group (see sinkhorn pass)
   GX_CHECK_ARG(stages >= 2 * NG || (NG == 1 && stages >= 2));
   static bool attr = false;
   if (!attr) {
-    GX_CHECK_CUDA(cudaFuncSetAttribute(swav_loss_kernel<J, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    GX_CHECK_CUDA(cudaFuncSetAttribute(swav_loss_kernel<J, GT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        200 * 1024));
     attr = true;
   }
-  swav_loss_kernel<J, GT><<<grid, SK_THREADS, (stages + 1) * stage_bytes, st>>>(
+  swav_loss_kernel<J, GT, NT><<<grid, NT, (stages + 1) * stage_bytes, st>>>(
       s_s, s_t, n, k, lds, inv_eps, inv_temp, la_s, la_t, grad_scale, loss_parts, db_parts,
       reinterpret_cast<__nv_bfloat16*>(ds_s_hi), reinterpret_cast<__nv_bfloat16*>(ds_s_lo),
       reinterpret_cast<__nv_bfloat16*>(ds_t_hi), reinterpret_cast<__nv_bfloat16*>(ds_t_lo), ldd, fs, ft, stages);
@@ -937,23 +948,47 @@ extern "C" int gx_swav_loss(const float* s_s, const float* s_t, long long n, int
   const int grid = sk_grid(n, 1);
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
-  const int j256 = gx_cdiv(k, 1024);
-#define GX_LS(J_, GT_)                                                                                            \
-  rc = launch_swav_loss<J_, GT_>(s_s, s_t, n, k, lds, inv_eps, inv_temp, log_a_s, log_a_t, grad_scale, loss_parts, \
-                                 db_parts, ds_s_hi, ds_s_lo, ds_t_hi, ds_t_lo, ldd, ds_s_f32, ds_t_f32, grid, st)
-  if (j256 <= 5) {
+  // Two independent groups of NWG warps with J <= 8 sweeps of 4 columns per thread, so that the
+  // four exponential arrays + bias-gradient accumulators of a row pair stay in registers
+  // (K = 5000: 5 warps per group, 8 sweeps).
+  const int nwg = gx_cdiv(k, 1024);
+#define GX_LS(J_, GT_, NT_)                                                                                     \
+  rc = launch_swav_loss<J_, GT_, NT_>(s_s, s_t, n, k, lds, inv_eps, inv_temp, log_a_s, log_a_t, grad_scale,     \
+                                      loss_parts, db_parts, ds_s_hi, ds_s_lo, ds_t_hi, ds_t_lo, ldd, ds_s_f32, \
+                                      ds_t_f32, grid, st)
+  if (nwg == 1) {
     if (nparts_out) *nparts_out = grid * 2;
-    switch (j256) {
-      case 1: GX_LS(1, 256); break;
-      case 2: GX_LS(2, 256); break;
-      case 3: GX_LS(3, 256); break;
-      case 4: GX_LS(4, 256); break;
-      default: GX_LS(5, 256); break;
+    switch (gx_cdiv(k, 128)) {
+      case 1: GX_LS(1, 32, 64); break;
+      case 2: GX_LS(2, 32, 64); break;
+      case 3: GX_LS(3, 32, 64); break;
+      case 4: GX_LS(4, 32, 64); break;
+      case 5: GX_LS(5, 32, 64); break;
+      case 6: GX_LS(6, 32, 64); break;
+      case 7: GX_LS(7, 32, 64); break;
+      default: GX_LS(8, 32, 64); break;
+    }
+  } else if (k > 5120) {
+    // two groups of 256 threads (register-limited: spills, still correct)
+    if (nparts_out) *nparts_out = grid * 2;
+    switch (nwg) {
+      case 6: GX_LS(6, 256, 512); break;
+      case 7: GX_LS(7, 256, 512); break;
+      default: GX_LS(8, 256, 512); break;
     }
   } else {
-    if (nparts_out) *nparts_out = grid;
-    if (k <= 6144) GX_LS(3, 512);
-    else GX_LS(4, 512);
+    // two independent groups of 128 threads
+    if (nparts_out) *nparts_out = grid * 2;
+    switch (gx_cdiv(k, 512)) {
+      case 3: GX_LS(3, 128, 256); break;
+      case 4: GX_LS(4, 128, 256); break;
+      case 5: GX_LS(5, 128, 256); break;
+      case 6: GX_LS(6, 128, 256); break;
+      case 7: GX_LS(7, 128, 256); break;
+      case 8: GX_LS(8, 128, 256); break;
+      case 9: GX_LS(9, 128, 256); break;
+      default: GX_LS(10, 128, 256); break;
+    }
   }
 #undef GX_LS
   if (rc != GX_OK) return rc;
