@@ -27,11 +27,11 @@ class gx_conv_desc(C.Structure):
     _fields_ = [
         ("x_hi", C.c_void_p), ("x_lo", C.c_void_p), ("w_hi", C.c_void_p), ("w_lo", C.c_void_p),
         ("batch", C.c_int), ("h", C.c_int), ("w", C.c_int), ("cin", C.c_int), ("cout", C.c_int),
-        ("upsample", C.c_int), ("passes", C.c_int),
+        ("cin_ld", C.c_int), ("upsample", C.c_int), ("passes", C.c_int),
         ("demod", C.c_void_p), ("noise", C.c_void_p), ("noise_batch_stride", C.c_longlong),
         ("noise_strength", C.c_void_p), ("bias", C.c_void_p), ("act", C.c_int),
         ("out", C.c_void_p), ("next_style", C.c_void_p), ("next_hi", C.c_void_p), ("next_lo", C.c_void_p),
-        ("block_n", C.c_int), ("stages", C.c_int),
+        ("next_ld", C.c_int), ("block_n", C.c_int), ("stages", C.c_int),
     ]
 
 
@@ -70,11 +70,11 @@ _SIGNATURES = {
     "gx_pixel_norm": ([_P, _P, _I, _I, _P], _I),
     "gx_equal_linear": ([_P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P], _I),
     "gx_truncate": ([_P, _P, _P, _LL, _I, _F, _P], _I),
-    "gx_modconv_prepare": ([_P, _F, _P, _P, _P, _I, _I, _I, _P], _I),
+    "gx_modconv_prepare": ([_P, _F, _P, _P, _P, _I, _I, _I, _I, _P], _I),
     "gx_modconv_demod": ([_P, _P, _P, _I, _I, _I, _P], _I),
-    "gx_modulate_split": ([_P, _LL, _P, _P, _P, _I, _LL, _I, _P], _I),
+    "gx_modulate_split": ([_P, _LL, _P, _P, _P, _I, _LL, _I, _I, _P], _I),
     "gx_modconv": ([C.POINTER(gx_conv_desc), _P], _I),
-    "gx_blur_noise_bias_act": ([_P, _P, _I, _I, _I, _I, _P, _LL, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _P], _I),
+    "gx_blur_noise_bias_act": ([_P, _P, _I, _I, _I, _I, _P, _LL, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
     "gx_torgb": ([_P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _P], _I),
     "gx_gemm": ([C.POINTER(gx_gemm_desc), _P], _I),
     "gx_gemm_check": ([C.POINTER(gx_gemm_desc), _P], _I),
@@ -279,16 +279,29 @@ def truncate(w, mean, psi):
     return out
 
 
+def pad64(c):
+    """channels per pixel of the bf16 operand planes: multiple of the 64-element K block"""
+    return (c + 63) // 64 * 64
+
+
+def _planes(shape, dev, padded, want_lo=True):
+    alloc = torch.zeros if padded else torch.empty
+    hi = alloc(shape, dtype=torch.bfloat16, device=dev)
+    lo = alloc(shape, dtype=torch.bfloat16, device=dev) if want_lo else None
+    return hi, lo
+
+
 def modconv_prepare(weight, scale, want_lo=True):
-    """weight [cout,cin,k,k] -> (w_hi, w_lo) [cout, k*k*cin] bf16, wsq [cout,cin]"""
+    """weight [cout,cin,k,k] -> (w_hi, w_lo) [cout, k*k*pad64(cin)] bf16, wsq [cout,cin]"""
     lib = load()
     _f32(weight, "weight")
     cout, cin, k, _ = weight.shape
-    w_hi = torch.empty((cout, k * k * cin), dtype=torch.bfloat16, device=weight.device)
+    cin_ld = pad64(cin)
+    w_hi = torch.empty((cout, k * k * cin_ld), dtype=torch.bfloat16, device=weight.device)
     w_lo = torch.empty_like(w_hi) if want_lo else None
     wsq = torch.empty((cout, cin), dtype=torch.float32, device=weight.device)
-    _check(lib.gx_modconv_prepare(_ptr(weight), float(scale), _ptr(w_hi), _ptr(w_lo), _ptr(wsq), cout, cin, k,
-                                  _stream()), "gx_modconv_prepare")
+    _check(lib.gx_modconv_prepare(_ptr(weight), float(scale), _ptr(w_hi), _ptr(w_lo), _ptr(wsq), cout, cin, cin_ld,
+                                  k, _stream()), "gx_modconv_prepare")
     _count()
     return w_hi, w_lo, wsq
 
@@ -305,35 +318,36 @@ def modconv_demod(wsq, s):
 
 
 def modulate_split(x_nhwc, s, batch, want_lo=True):
-    """x_nhwc: [B or 1, H, W, C] fp32; s [batch, C] -> hi, lo [batch,H,W,C] bf16"""
+    """x_nhwc: [B or 1, H, W, C] fp32; s [batch, C] -> hi, lo [batch,H,W,pad64(C)] bf16"""
     lib = load()
     _f32(x_nhwc, "x"), _f32(s, "s")
     xb, h, w, c = x_nhwc.shape
     stride = 0 if (xb == 1 and batch > 1) else h * w * c
-    hi = torch.empty((batch, h, w, c), dtype=torch.bfloat16, device=x_nhwc.device)
-    lo = torch.empty_like(hi) if want_lo else None
-    _check(lib.gx_modulate_split(_ptr(x_nhwc), stride, _ptr(s), _ptr(hi), _ptr(lo), batch, h * w, c, _stream()),
-           "gx_modulate_split")
+    c_ld = pad64(c)
+    hi, lo = _planes((batch, h, w, c_ld), x_nhwc.device, c_ld != c, want_lo)
+    _check(lib.gx_modulate_split(_ptr(x_nhwc), stride, _ptr(s), _ptr(hi), _ptr(lo), batch, h * w, c, c_ld,
+                                 _stream()), "gx_modulate_split")
     _count()
     return hi, lo
 
 
 def modconv(x_hi, x_lo, w_hi, w_lo, cout, upsample, passes, demod=None, noise=None, noise_strength=None, bias=None,
-            act=0, next_style=None, want_next_lo=True, block_n=0, stages=0, tag="modconv"):
-    """Implicit-GEMM modulated conv.  x_*: [B,H,W,Cin] bf16.  Returns (out fp32 NHWC, next_hi, next_lo)."""
+            act=0, next_style=None, want_next_lo=True, block_n=0, stages=0, tag="modconv", cin_true=None):
+    """Implicit-GEMM modulated conv.  x_*: [B,H,W,pad64(Cin)] bf16 planes.
+    Returns (out fp32 NHWC [B,Ho,Wo,cout], next_hi, next_lo [B,Ho,Wo,pad64(cout)])."""
     lib = load()
-    b, h, w, cin = x_hi.shape
+    b, h, w, cin_ld = x_hi.shape
+    cin = cin_ld
     ho, wo = (2 * h + 1, 2 * w + 1) if upsample else (h, w)
     dev = x_hi.device
     out = torch.empty((b, ho, wo, cout), dtype=torch.float32, device=dev)
     next_hi = next_lo = None
+    next_ld = pad64(cout)
     if next_style is not None:
-        next_hi = torch.empty((b, ho, wo, cout), dtype=torch.bfloat16, device=dev)
-        if want_next_lo:
-            next_lo = torch.empty_like(next_hi)
+        next_hi, next_lo = _planes((b, ho, wo, next_ld), dev, next_ld != cout, want_next_lo)
     d = gx_conv_desc()
     d.x_hi, d.x_lo, d.w_hi, d.w_lo = _ptr(x_hi), _ptr(x_lo), _ptr(w_hi), _ptr(w_lo)
-    d.batch, d.h, d.w, d.cin, d.cout = b, h, w, cin, cout
+    d.batch, d.h, d.w, d.cin, d.cout, d.cin_ld = b, h, w, cin, cout, cin_ld
     d.upsample, d.passes = int(bool(upsample)), passes
     d.demod = _ptr(demod)
     d.noise = _ptr(noise)
@@ -344,8 +358,9 @@ def modconv(x_hi, x_lo, w_hi, w_lo, cout, upsample, passes, demod=None, noise=No
     d.act = int(act)
     d.out = _ptr(out)
     d.next_style, d.next_hi, d.next_lo = _ptr(next_style), _ptr(next_hi), _ptr(next_lo)
+    d.next_ld = next_ld
     d.block_n, d.stages = block_n, stages
-    with timed(tag + ("_up" if upsample else ""), 2.0 * b * h * w * 9 * cin * cout):
+    with timed(tag + ("_up" if upsample else ""), 2.0 * b * h * w * 9 * (cin_true or cin) * cout):
         _check(lib.gx_modconv(C.byref(d), _stream()), "gx_modconv")
     _count()
     return out, next_hi, next_lo
@@ -360,10 +375,9 @@ def blur_noise_bias_act(x_nhwc, fir, pad0, pad1, noise, noise_strength, bias, ac
     dev = x_nhwc.device
     out = torch.empty((b, ho, wo, c), dtype=torch.float32, device=dev)
     next_hi = next_lo = None
+    next_ld = pad64(c)
     if next_style is not None:
-        next_hi = torch.empty((b, ho, wo, c), dtype=torch.bfloat16, device=dev)
-        if want_next_lo:
-            next_lo = torch.empty_like(next_hi)
+        next_hi, next_lo = _planes((b, ho, wo, next_ld), dev, next_ld != c, want_next_lo)
     nbs = 0
     if noise is not None:
         nbs = 0 if noise.shape[0] == 1 else ho * wo
@@ -372,7 +386,7 @@ def blur_noise_bias_act(x_nhwc, fir, pad0, pad1, noise, noise_strength, bias, ac
     with timed("blur_noise_bias_act", nbytes):
         _check(lib.gx_blur_noise_bias_act(_ptr(x_nhwc), _ptr(fir), kh, kw, pad0, pad1, _ptr(noise), nbs,
                                           _ptr(noise_strength), _ptr(bias), int(act), _ptr(out), _ptr(next_style),
-                                          _ptr(next_hi), _ptr(next_lo), b, hi, wi, c, _stream()),
+                                          _ptr(next_hi), _ptr(next_lo), next_ld, b, hi, wi, c, _stream()),
                "gx_blur_noise_bias_act")
     _count()
     return out, next_hi, next_lo

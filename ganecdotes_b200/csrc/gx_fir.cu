@@ -111,8 +111,8 @@ __global__ void __launch_bounds__(256)
 blur_fused_kernel(const float* __restrict__ in, const float* __restrict__ fir, int pad0, const float* __restrict__ noise,
                   long long noise_bstride, const float* __restrict__ noise_strength, const float* __restrict__ bias,
                   int act, float* __restrict__ out, const float* __restrict__ next_style,
-                  __nv_bfloat16* __restrict__ next_hi, __nv_bfloat16* __restrict__ next_lo, int batch, int hi, int wi,
-                  int ho, int wo, int c) {
+                  __nv_bfloat16* __restrict__ next_hi, __nv_bfloat16* __restrict__ next_lo, int next_ld, int batch,
+                  int hi, int wi, int ho, int wo, int c) {
   __shared__ float sk[KH * KW];
   if (threadIdx.x < KH * KW) {
     const int ky = threadIdx.x / KW, kx = threadIdx.x % KW;
@@ -188,8 +188,9 @@ blur_fused_kernel(const float* __restrict__ in, const float* __restrict__ fir, i
     if (next_hi) {
       uint2 h, l;
       gx_split4(make_float4(acc.x * st.x, acc.y * st.y, acc.z * st.z, acc.w * st.w), h, l);
-      reinterpret_cast<uint2*>(next_hi)[o] = h;
-      if (next_lo) reinterpret_cast<uint2*>(next_lo)[o] = l;
+      const long long on = (((long long)b * ho + oy) * wo + ox) * (next_ld >> 2) + q;
+      reinterpret_cast<uint2*>(next_hi)[on] = h;
+      if (next_lo) reinterpret_cast<uint2*>(next_lo)[on] = l;
     }
   }
 }
@@ -276,7 +277,9 @@ extern "C" int gx_fused_bias_act(const float* input, const float* bias, const fl
 extern "C" int gx_blur_noise_bias_act(const float* in, const float* fir, int kh, int kw, int pad0, int pad1,
                                       const float* noise, long long noise_batch_stride, const float* noise_strength,
                                       const float* bias, int act, float* out, const float* next_style, void* next_hi,
-                                      void* next_lo, int batch, int hi, int wi, int c, void* stream) {
+                                      void* next_lo, int next_ld, int batch, int hi, int wi, int c, void* stream) {
+  if (next_ld <= 0) next_ld = c;
+  GX_CHECK_ARG(next_ld >= c && next_ld % 4 == 0);
   GX_CHECK_ARG(in && fir && out && batch > 0 && hi > 0 && wi > 0);
   GX_CHECK_ARG(c % 4 == 0);
   GX_CHECK_ARG(kh == 4 && kw == 4);  // StyleGAN2 blur_kernel=[1,3,3,1]; other sizes go through gx_upfirdn2d
@@ -291,7 +294,8 @@ extern "C" int gx_blur_noise_bias_act(const float* in, const float* fir, int kh,
   GX_CHECK_ARG(256 % cq_blk == 0);
   blur_fused_kernel<4, 4><<<grid, 256, 0, (cudaStream_t)stream>>>(
       in, fir, pad0, noise, noise_batch_stride, noise_strength, bias, act, out, next_style,
-      reinterpret_cast<__nv_bfloat16*>(next_hi), reinterpret_cast<__nv_bfloat16*>(next_lo), batch, hi, wi, ho, wo, c);
+      reinterpret_cast<__nv_bfloat16*>(next_hi), reinterpret_cast<__nv_bfloat16*>(next_lo), next_ld, batch, hi, wi, ho,
+      wo, c);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }

@@ -47,22 +47,22 @@ __global__ void truncate_kernel(const float* __restrict__ w, const float* __rest
 
 __global__ void modconv_prepare_kernel(const float* __restrict__ w, float scale, __nv_bfloat16* __restrict__ w_hi,
                                        __nv_bfloat16* __restrict__ w_lo, float* __restrict__ wsq, int cout, int cin,
-                                       int kk) {
+                                       int cin_ld, int kk) {
   const long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x;
-  if (idx >= (long long)cout * cin) return;
-  const int ci = (int)(idx % cin);
-  const int co = (int)(idx / cin);
+  if (idx >= (long long)cout * cin_ld) return;
+  const int ci = (int)(idx % cin_ld);
+  const int co = (int)(idx / cin_ld);
   float ss = 0.f;
   for (int t = 0; t < kk; ++t) {
-    const float v = w[((long long)co * cin + ci) * kk + t] * scale;
+    const float v = ci < cin ? w[((long long)co * cin + ci) * kk + t] * scale : 0.f;
     ss = fmaf(v, v, ss);
     __nv_bfloat16 h, l;
     gx_split_bf16(v, h, l);
-    const long long o = ((long long)co * kk + t) * cin + ci;
+    const long long o = ((long long)co * kk + t) * cin_ld + ci;
     w_hi[o] = h;
     if (w_lo) w_lo[o] = l;
   }
-  if (wsq) wsq[idx] = ss;
+  if (wsq && ci < cin) wsq[(long long)co * cin + ci] = ss;
 }
 
 __global__ void modconv_demod_kernel(const float* __restrict__ wsq, const float* __restrict__ s,
@@ -82,7 +82,7 @@ __global__ void modconv_demod_kernel(const float* __restrict__ wsq, const float*
 
 __global__ void modulate_split_kernel(const float* __restrict__ x, long long xbs, const float* __restrict__ s,
                                       __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int batch,
-                                      long long hw, int c) {
+                                      long long hw, int c, int c_ld) {
   const int cq = c >> 2;
   const long long total = (long long)batch * hw * cq;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
@@ -95,8 +95,9 @@ __global__ void modulate_split_kernel(const float* __restrict__ x, long long xbs
     const float4 sv = __ldg(reinterpret_cast<const float4*>(s + (long long)b * c) + q);
     uint2 h, l;
     gx_split4(make_float4(v.x * sv.x, v.y * sv.y, v.z * sv.z, v.w * sv.w), h, l);
-    reinterpret_cast<uint2*>(hi)[i] = h;
-    if (lo) reinterpret_cast<uint2*>(lo)[i] = l;
+    const long long o = pix * (c_ld >> 2) + q;
+    reinterpret_cast<uint2*>(hi)[o] = h;
+    if (lo) reinterpret_cast<uint2*>(lo)[o] = l;
   }
 }
 
@@ -129,11 +130,14 @@ extern "C" int gx_truncate(const float* w, const float* mean, float* out, long l
 }
 
 extern "C" int gx_modconv_prepare(const float* w, float scale, void* w_hi, void* w_lo, float* wsq, int cout, int cin,
-                                  int k, void* stream) {
+                                  int cin_ld, int k, void* stream) {
   GX_CHECK_ARG(w && w_hi && cout > 0 && cin > 0 && k > 0);
-  const long long total = (long long)cout * cin;
+  if (cin_ld <= 0) cin_ld = cin;
+  GX_CHECK_ARG(cin_ld >= cin);
+  const long long total = (long long)cout * cin_ld;
   modconv_prepare_kernel<<<gx_cdiv(total, 256), 256, 0, (cudaStream_t)stream>>>(
-      w, scale, reinterpret_cast<__nv_bfloat16*>(w_hi), reinterpret_cast<__nv_bfloat16*>(w_lo), wsq, cout, cin, k * k);
+      w, scale, reinterpret_cast<__nv_bfloat16*>(w_hi), reinterpret_cast<__nv_bfloat16*>(w_lo), wsq, cout, cin, cin_ld,
+      k * k);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }
@@ -148,15 +152,17 @@ extern "C" int gx_modconv_demod(const float* wsq, const float* s, float* demod, 
 }
 
 extern "C" int gx_modulate_split(const float* x, long long x_batch_stride, const float* s, void* hi, void* lo,
-                                 int batch, long long hw, int c, void* stream) {
+                                 int batch, long long hw, int c, int c_ld, void* stream) {
   GX_CHECK_ARG(x && s && hi && batch > 0 && hw > 0 && c % 4 == 0);
+  if (c_ld <= 0) c_ld = c;
+  GX_CHECK_ARG(c_ld >= c && c_ld % 4 == 0);
   const long long total = (long long)batch * hw * (c / 4);
   int grid = gx_cdiv(total, 256);
   const int cap = gx_sm_count() * 16;
   if (grid > cap) grid = cap;
   modulate_split_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, x_batch_stride, s,
                                                                reinterpret_cast<__nv_bfloat16*>(hi),
-                                                               reinterpret_cast<__nv_bfloat16*>(lo), batch, hw, c);
+                                                               reinterpret_cast<__nv_bfloat16*>(lo), batch, hw, c, c_ld);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }

@@ -64,6 +64,7 @@ struct UmmaParams {
   const float* next_style;
   __nv_bfloat16* next_hi;
   __nv_bfloat16* next_lo;
+  int next_ld;
 };
 
 struct TileInfo {
@@ -322,12 +323,15 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
           float v[32];
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
+          const int nq = min(8, (p.Cout - co) >> 2);   // valid float4 groups of this chunk (warp-uniform)
           if (p.demod != nullptr) {
             const float4* dm = reinterpret_cast<const float4*>(p.demod + (long long)b * p.Cout + co);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const float4 d4 = __ldg(dm + e);
-              v[4 * e] *= d4.x; v[4 * e + 1] *= d4.y; v[4 * e + 2] *= d4.z; v[4 * e + 3] *= d4.w;
+              if (e < nq) {
+                const float4 d4 = __ldg(dm + e);
+                v[4 * e] *= d4.x; v[4 * e + 1] *= d4.y; v[4 * e + 2] *= d4.z; v[4 * e + 3] *= d4.w;
+              }
             }
           }
           if (p.noise != nullptr) {
@@ -338,8 +342,10 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
             const float4* bs = reinterpret_cast<const float4*>(p.bias + co);
 #pragma unroll
             for (int e = 0; e < 8; ++e) {
-              const float4 b4 = __ldg(bs + e);
-              v[4 * e] += b4.x; v[4 * e + 1] += b4.y; v[4 * e + 2] += b4.z; v[4 * e + 3] += b4.w;
+              if (e < nq) {
+                const float4 b4 = __ldg(bs + e);
+                v[4 * e] += b4.x; v[4 * e + 1] += b4.y; v[4 * e + 2] += b4.z; v[4 * e + 3] += b4.w;
+              }
             }
           }
           if (p.act) {
@@ -348,22 +354,22 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
           }
           float4* dst = reinterpret_cast<float4*>(p.out + pix * p.Cout + co);
 #pragma unroll
-          for (int e = 0; e < 8; ++e) dst[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+          for (int e = 0; e < 8; ++e)
+            if (e < nq) dst[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
           if (p.next_style != nullptr) {
             const float4* st = reinterpret_cast<const float4*>(p.next_style + (long long)b * p.Cout + co);
-            uint4* dh = reinterpret_cast<uint4*>(p.next_hi + pix * p.Cout + co);
-            uint4* dl = (p.next_lo != nullptr) ? reinterpret_cast<uint4*>(p.next_lo + pix * p.Cout + co) : nullptr;
+            uint2* dh = reinterpret_cast<uint2*>(p.next_hi + pix * p.next_ld + co);
+            uint2* dl = (p.next_lo != nullptr) ? reinterpret_cast<uint2*>(p.next_lo + pix * p.next_ld + co) : nullptr;
 #pragma unroll
-            for (int e = 0; e < 4; ++e) {
-              const float4 s0 = __ldg(st + 2 * e), s1 = __ldg(st + 2 * e + 1);
-              uint2 h0, l0, h1, l1;
-              gx_split4(make_float4(v[8 * e] * s0.x, v[8 * e + 1] * s0.y, v[8 * e + 2] * s0.z, v[8 * e + 3] * s0.w),
-                        h0, l0);
-              gx_split4(make_float4(v[8 * e + 4] * s1.x, v[8 * e + 5] * s1.y, v[8 * e + 6] * s1.z,
-                                    v[8 * e + 7] * s1.w),
-                        h1, l1);
-              dh[e] = make_uint4(h0.x, h0.y, h1.x, h1.y);
-              if (dl != nullptr) dl[e] = make_uint4(l0.x, l0.y, l1.x, l1.y);
+            for (int e = 0; e < 8; ++e) {
+              if (e < nq) {
+                const float4 s0 = __ldg(st + e);
+                uint2 h0, l0;
+                gx_split4(make_float4(v[4 * e] * s0.x, v[4 * e + 1] * s0.y, v[4 * e + 2] * s0.z, v[4 * e + 3] * s0.w),
+                          h0, l0);
+                dh[e] = h0;
+                if (dl != nullptr) dl[e] = l0;
+              }
             }
           }
         }
@@ -533,19 +539,19 @@ extern "C" int gx_modconv(const gx_conv_desc* d, void* stream) {
   GX_CHECK_ARG(d->passes == 1 || d->passes == 3);
   GX_CHECK_ARG(d->passes == 1 || (d->x_lo && d->w_lo));
   GX_CHECK_ARG(d->batch > 0 && d->h > 0 && d->w > 0);
-  GX_CHECK_ARG(d->cin % BK == 0 && d->cout % 32 == 0);
+  const int cin_ld = d->cin_ld > 0 ? d->cin_ld : d->cin;
+  GX_CHECK_ARG(cin_ld % BK == 0 && cin_ld >= d->cin && d->cout % 4 == 0);
   GX_CHECK_ARG(d->next_style == nullptr || d->next_hi != nullptr);
   UmmaParams p;
   memset(&p, 0, sizeof(p));
   p.mode = 1;
   p.passes = d->passes;
-  p.B = d->batch; p.H = d->h; p.W = d->w; p.Cin = d->cin; p.Cout = d->cout;
+  p.B = d->batch; p.H = d->h; p.W = d->w; p.Cin = cin_ld; p.Cout = d->cout;  // the K loop runs over padded channels
   p.upsample = d->upsample ? 1 : 0;
   int bn = d->block_n;
   if (bn == 0) bn = (d->cout >= 256) ? 256 : 128;
   if (bn > d->cout) bn = (d->cout >= 128) ? 128 : 64;
   GX_CHECK_ARG(bn == 64 || bn == 128 || bn == 256);
-  GX_CHECK_ARG(d->cout % 32 == 0);
   p.block_n = bn;
   p.mtiles = 1;
   p.acc_stages = 2;
@@ -610,6 +616,8 @@ extern "C" int gx_modconv(const gx_conv_desc* d, void* stream) {
   p.out = d->out; p.next_style = d->next_style;
   p.next_hi = reinterpret_cast<__nv_bfloat16*>(d->next_hi);
   p.next_lo = reinterpret_cast<__nv_bfloat16*>(d->next_lo);
+  p.next_ld = d->next_ld > 0 ? d->next_ld : d->cout;
+  GX_CHECK_ARG(p.next_ld >= d->cout && p.next_ld % 4 == 0);
 
   CUtensorMap maps[4];
   memset(maps, 0, sizeof(maps));
@@ -617,17 +625,17 @@ extern "C" int gx_modconv(const gx_conv_desc* d, void* stream) {
   const void* wptr[2] = {d->w_hi, d->w_lo};
   const int nplanes = p.passes == 3 ? 2 : 1;
   for (int pl = 0; pl < nplanes; ++pl) {
-    unsigned long long dims[4] = {(unsigned long long)d->cin, (unsigned long long)d->w, (unsigned long long)d->h,
+    unsigned long long dims[4] = {(unsigned long long)cin_ld, (unsigned long long)d->w, (unsigned long long)d->h,
                                   (unsigned long long)d->batch};
-    unsigned long long str[3] = {(unsigned long long)d->cin, (unsigned long long)d->cin * d->w,
-                                 (unsigned long long)d->cin * d->w * d->h};
+    unsigned long long str[3] = {(unsigned long long)cin_ld, (unsigned long long)cin_ld * d->w,
+                                 (unsigned long long)cin_ld * d->w * d->h};
     unsigned box[4] = {BK, (unsigned)tw, (unsigned)th, (unsigned)nb};
     // a box may not exceed the tensor extent in TMA encoding only through its
     // dimension limit of 256; partial boxes are zero-filled
     int rc = make_tmap(&maps[pl], xptr[pl], 4, dims, str, box);
     if (rc != GX_OK) return rc;
-    unsigned long long wd[2] = {(unsigned long long)9 * d->cin, (unsigned long long)d->cout};
-    unsigned long long ws[1] = {(unsigned long long)9 * d->cin};
+    unsigned long long wd[2] = {(unsigned long long)9 * cin_ld, (unsigned long long)d->cout};
+    unsigned long long ws[1] = {(unsigned long long)9 * cin_ld};
     unsigned wb[2] = {BK, (unsigned)bn};
     rc = make_tmap(&maps[2 + pl], wptr[pl], 2, wd, ws, wb);
     if (rc != GX_OK) return rc;

@@ -339,13 +339,14 @@ class Generator(nn.Module):
             strength = layer.noise.weight.detach()
             bias = layer.activate.bias.detach()
             if conv.upsample:
-                tmp, _, _ = L.modconv(x_hi, x_lo, w_hi, w_lo, conv.out_channel, True, passes, demod=demods[n])
+                tmp, _, _ = L.modconv(x_hi, x_lo, w_hi, w_lo, conv.out_channel, True, passes, demod=demods[n],
+                                      cin_true=conv.in_channel)
                 f, x_hi, x_lo = L.blur_noise_bias_act(tmp, conv.blur.kernel, conv.blur.pad[0], conv.blur.pad[1], nz,
                                                       strength, bias, 1, nxt, want_lo)
             else:
                 f, x_hi, x_lo = L.modconv(x_hi, x_lo, w_hi, w_lo, conv.out_channel, False, passes, demod=demods[n],
                                           noise=nz, noise_strength=strength, bias=bias, act=1, next_style=nxt,
-                                          want_next_lo=want_lo)
+                                          want_next_lo=want_lo, cin_true=conv.in_channel)
             feats.append(f)
             if need_image and n % 2 == 0:
                 rgb = self.to_rgb1 if n == 0 else self.to_rgbs[n // 2 - 1]

@@ -66,18 +66,20 @@ int gx_equal_linear(const float* x, const float* w, const float* b, float* y, in
 int gx_truncate(const float* w, const float* mean, float* out, long long rows, int dim, float psi, void* stream);
 
 /* One-time weight preparation of a modulated conv (ref: model.py:316-320,330):
- * w [cout,cin,k,k] fp32 -> split-bf16 planes w_hi/w_lo [cout, k*k*cin] holding
- * scale*w with k index = (ky*k+kx)*cin + ci, and wsq [cout,cin] = sum_taps (scale*w)^2. */
-int gx_modconv_prepare(const float* w, float scale, void* w_hi, void* w_lo, float* wsq, int cout, int cin, int k,
-                       void* stream);
+ * w [cout,cin,k,k] fp32 -> split-bf16 planes w_hi/w_lo [cout, k*k*cin_ld] holding
+ * scale*w with k index = (ky*k+kx)*cin_ld + ci (zero for ci >= cin; cin_ld = cin rounded up to 64),
+ * and wsq [cout,cin] = sum_taps (scale*w)^2. */
+int gx_modconv_prepare(const float* w, float scale, void* w_hi, void* w_lo, float* wsq, int cout, int cin,
+                       int cin_ld, int k, void* stream);
 
 /* demod[b,co] = rsqrt(sum_ci wsq[co,ci]*s[b,ci]^2 + 1e-8), ref: model.py:332-334. */
 int gx_modconv_demod(const float* wsq, const float* s, float* demod, int batch, int cin, int cout, void* stream);
 
 /* x_mod = x * s[b,c] split into bf16 hi/lo planes (NHWC).  x has `x_batch_stride`
- * elements between samples (0 = broadcast, e.g. the constant input, ref: model.py:385-395). */
+ * elements between samples (0 = broadcast, e.g. the constant input, ref: model.py:385-395).
+ * Planes have c_ld >= c channels per pixel (the caller zero-fills channels [c, c_ld)). */
 int gx_modulate_split(const float* x, long long x_batch_stride, const float* s, void* hi, void* lo, int batch,
-                      long long hw, int c, void* stream);
+                      long long hw, int c, int c_ld, void* stream);
 
 typedef struct gx_conv_desc {
   /* operands (bf16 planes; *_lo may be NULL when passes == 1) */
@@ -86,6 +88,7 @@ typedef struct gx_conv_desc {
   const void* w_hi; /* [Cout, taps*Cin] from gx_modconv_prepare              */
   const void* w_lo;
   int batch, h, w, cin, cout;
+  int cin_ld;   /* channels per pixel of the x planes / per tap of the w planes (multiple of 64)   */
   int upsample; /* 0: 3x3 pad 1 -> [B,H,W,Cout]; 1: transposed stride 2 -> [B,2H+1,2W+1,Cout] */
   int passes;   /* 1: bf16, 3: split-bf16 (fp32-equivalent)                  */
   /* epilogue: v = acc*demod[b,co] + strength*noise[b,y,x] + bias[co]; act; */
@@ -97,15 +100,16 @@ typedef struct gx_conv_desc {
   int act;                     /* 0 none, 1 lrelu(0.2)*sqrt2                  */
   float* out;                  /* fp32 NHWC [B,Ho,Wo,Cout]                    */
   const float* next_style;     /* [B,Cout] or NULL: also emit next conv input */
-  void* next_hi;               /* bf16 NHWC [B,Ho,Wo,Cout]                    */
+  void* next_hi;               /* bf16 NHWC [B,Ho,Wo,next_ld]                 */
   void* next_lo;
+  int next_ld;                 /* channels per pixel of the next planes (>= cout; caller zero-fills the rest) */
   int block_n; /* 0 = auto (128 or 256) */
   int stages;  /* 0 = auto               */
 } gx_conv_desc;
 
 /* Modulated 3x3 conv as implicit GEMM on tcgen05 (TMA im2col boxes, TMEM accumulators),
  * ref: ModulatedConv2d.forward model.py:327-368 in the algebraic form
- * y = demod * conv(scale*W, s*x).  Requires cin % 64 == 0, cout % 16 == 0. */
+ * y = demod * conv(scale*W, s*x).  Requires cin_ld % 64 == 0 (channels zero-padded), cout % 4 == 0. */
 int gx_modconv(const gx_conv_desc* d, void* stream);
 
 /* Blur (upfirdn2d up=1, down=1, pad=(p0,p1)) of the transposed-conv output fused with
@@ -115,7 +119,7 @@ int gx_modconv(const gx_conv_desc* d, void* stream);
 int gx_blur_noise_bias_act(const float* in, const float* fir, int kh, int kw, int pad0, int pad1,
                            const float* noise, long long noise_batch_stride, const float* noise_strength,
                            const float* bias, int act, float* out, const float* next_style, void* next_hi,
-                           void* next_lo, int batch, int hi, int wi, int c, void* stream);
+                           void* next_lo, int next_ld, int batch, int hi, int wi, int c, void* stream);
 
 /* ToRGB: 1x1 modulated conv without demodulation + bias (+ skip), ref: model.py:435-454.
  * x fp32 NHWC [B,H,W,C]; w [3,C]; s [B,C]; bias [3]; skip (already upsampled) [B,3,H,W] or NULL;

@@ -112,6 +112,32 @@ def init_generator_state(size: int, style_dim: int, n_mlp: int, seed: int,
     return sd
 
 
+def baggan_channels() -> Dict[int, int]:
+    """BagGAN StyleGANGenerator channel map as read at construction time
+    (models/baggan/models.py:383-390 rebinding, used at :121-122)."""
+    return {4: 512, 8: 512, 16: 256, 32: 128, 64: 64, 128: 32, 256: 16, 512: 8}
+
+
+def to_baggan_key(key: str) -> str:
+    """rosinality Generator key -> the name the same tensor has in BagGAN's StyleGANGenerator
+    (models/baggan/models.py:86-210, blocks.py:155-660)."""
+    import re
+    k = key
+    k = re.sub(r"^style\.(\d+)\.", r"style.mapper.\1.", k)
+    k = re.sub(r"^input\.input$", "const_input_block.const_block", k)
+    k = re.sub(r"^conv1\.", "conv_init.", k)
+    k = re.sub(r"^to_rgb1\.", "x_to_img_init.", k)
+    k = re.sub(r"^convs\.(\d+)\.", r"conv_blks.\1.", k)
+    k = re.sub(r"^to_rgbs\.(\d+)\.", r"x_to_img_blks.\1.", k)
+    k = re.sub(r"^noises\.noise_(\d+)$", r"noise_blks.noise_\1", k)
+    if k.startswith(("conv_init.", "conv_blks.")):
+        k = k.replace(".conv.modulation.", ".style_block.mod.").replace(".conv.", ".style_block.")
+        k = k.replace(".noise.", ".noise_block.").replace(".activate.", ".activation.")
+    else:
+        k = k.replace(".conv.modulation.", ".conv.mod.")
+    return k
+
+
 def generator_dims(sd: Dict[str, torch.Tensor]) -> Tuple[int, int, int]:
     """(size, style_dim, n_mlp) recovered from a state dict."""
     n_mlp = len([k for k in sd if k.startswith("style.") and k.endswith(".weight")])

@@ -255,7 +255,48 @@ def golden_swav():
     print("losses", losses)
 
 
+# ---------------------------------------------------------------------------------------
+# G4: BagGAN generator (models/baggan/models.py:86-379), pidray channel map
+# ---------------------------------------------------------------------------------------
+def golden_baggan():
+    """The real `lib/gan/optim` python modules are imported with `cpp_extension.load` neutralised
+    (no CUDA JIT in this container): on CPU tensors they take their own native branches
+    (upfirdn2d.py:156-157, fused_act.py:234-248), which is the path the reference's CPU run uses."""
+    import torch.utils.cpp_extension as ce
+    ce.load = lambda *a, **k: types.SimpleNamespace()
+    import models.baggan.models as bm
+    sys.path.insert(0, ROOT)
+    from oracle import ganecdotes_oracle as O2
+    size = 256
+    ch = O2.baggan_channels()
+    sd = O2.init_generator_state(size, 512, 8, 13, channels=ch)
+    gen = bm.StyleGANGenerator((512, 512), size)
+    ref_sd = {O2.to_baggan_key(k): v for k, v in sd.items()}
+    missing, unexpected = gen.load_state_dict(ref_sd, strict=False)
+    assert not unexpected, unexpected
+    assert all(k.startswith("head_m.") for k in missing), missing
+    gen.eval()
+    g = torch.Generator().manual_seed(4)
+    w = torch.randn(2, 512, generator=g) * 0.7
+    zm = torch.randn(32, 512, generator=g)
+    with torch.no_grad():
+        mean_latent = gen.style(zm).mean(0, keepdim=True)
+        wz = gen.style(torch.randn(2, 512, generator=g))
+        img, feats = gen([wz], truncation=0.9, truncation_latent=mean_latent, input_is_latent=True,
+                         randomize_noise=False)
+    out = dict(w=wz, zm=zm, mean_latent=mean_latent, img=img, size=np.int64(size),
+               chans=np.array([f.shape[1] for f in feats], dtype=np.int64))
+    for i, f in enumerate(feats):
+        cs = 16 if f.shape[1] >= 128 else 4
+        sp = 1 if f.shape[-1] <= 16 else (2 if f.shape[-1] <= 32 else f.shape[-1] // 16)
+        out[f"feat{i}"] = f[:, 1::cs, ::sp, ::sp]
+        out[f"feat{i}_sum"] = f.double().sum(dim=(2, 3))
+    out["img"] = img[:, :, ::4, ::4]
+    save("baggan", **out)
+
+
 if __name__ == "__main__":
     golden_ops()
     golden_generator()
     golden_swav()
+    golden_baggan()

@@ -176,6 +176,10 @@ def test_equal_linear_pixelnorm_truncate(L):
     (3, 128, 64, 8, True, 3),
     (1, 64, 64, 16, True, 3),
     (1, 512, 512, 32, False, 3),
+    (2, 32, 16, 16, False, 3),      # BagGAN widths: channels zero-padded to the 64-wide K block
+    (2, 64, 32, 8, True, 3),
+    (1, 16, 16, 32, True, 3),
+    (3, 32, 32, 4, False, 1),
 ])
 def test_modconv_vs_oracle(L, b, cin, cout, h, up, passes):
     """Modulated conv (+ blur for the up path) vs the per-sample reference formulation."""

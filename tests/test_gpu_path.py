@@ -313,3 +313,42 @@ def test_larger_generator_sliced_hlen(size):
         top2 = ref_p.topk(2, dim=1).values
         assert (top2[:, 0] - top2[:, 1])[mism].max().item() < 1e-3 * ref_p.abs().max().item()
     assert mism.float().mean().item() < 0.02
+
+
+def test_baggan_generator_and_label_map():
+    """pidray-256 config: BagGAN StyleGANGenerator state dict -> drop-in Generator
+    (key mapping + narrow channel map), features vs the reference golden, label map vs the oracle."""
+    from ganecdotes_b200.baggan import generator_from_baggan, baggan_channels
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    g = load("baggan")
+    size = int(g["size"])
+    sd = O.init_generator_state(size, 512, 8, 13, channels=O.baggan_channels())
+    baggan_sd = {O.to_baggan_key(k): v for k, v in sd.items()}
+    baggan_sd["head_m.0.weight"] = torch.zeros(1, 1, 3, 3)          # present in real checkpoints, unused
+    gen = generator_from_baggan(baggan_sd, img_resolution=size)
+    assert {r: c for r, c in baggan_channels().items() if r <= 256} == {r: c for r, c in O.baggan_channels().items()
+                                                                        if r <= 256}
+    img, feats = gen([g["w"].cuda()], truncation=0.9, truncation_latent=g["mean_latent"].cuda(),
+                     input_is_latent=True, randomize_noise=False)
+    assert [f.shape[1] for f in feats] == g["chans"].tolist()
+    for i, f in enumerate(feats):
+        cs = 16 if f.shape[1] >= 128 else 4
+        sp = 1 if f.shape[-1] <= 16 else (2 if f.shape[-1] <= 32 else f.shape[-1] // 16)
+        ref = g[f"feat{i}"]
+        err = (f[:, 1::cs, ::sp, ::sp].cpu() - ref).abs().max().item()
+        assert err < 1e-3 * ref.abs().max().item(), (i, err, ref.abs().max().item())
+    ref_img = g["img"]
+    assert (img[:, :, ::4, ::4].cpu() - ref_img).abs().max().item() < 2e-3 * ref_img.abs().max().item()
+    # one-shot inference head: projection 2528 -> 512, arg-max label map (evaluate.py path)
+    torch.manual_seed(0)
+    hlen = 2528
+    wp = torch.randn(512, hlen) / hlen ** 0.5
+    w1 = g["w"][:1]
+    ref_p, ref_l = O.predict_codes(sd, w1, g["mean_latent"], 0.9, wp, hlen)
+    preds, labels = E.predict_codes(gen, wp.cuda(), w1.cuda(), g["mean_latent"].cuda(), 0.9, hlen)
+    assert labels.shape == (1, size, size) and labels.dtype == torch.int64
+    mism = labels.cpu() != ref_l
+    if mism.any():
+        top2 = ref_p.topk(2, dim=1).values
+        assert (top2[:, 0] - top2[:, 1])[mism].max().item() < 2e-3 * ref_p.abs().max().item()
+    assert mism.float().mean().item() < 0.02, mism.float().mean().item()
