@@ -80,8 +80,9 @@ _SIGNATURES = {
     "gx_gemm_check": ([C.POINTER(gx_gemm_desc), _P], _I),
     "gx_split_planes": ([_P, _LL, _P, _P, _LL, _LL, _I, _P], _I),
     "gx_gather_rows": ([C.POINTER(gx_gather_desc), _P], _I),
-    "gx_l2norm_split": ([_P, _P, _P, _P, _LL, _I, _P], _I),
-    "gx_l2norm_bwd_split": ([_P, _P, _P, _P, _P, _P, _LL, _I, _P], _I),
+    "gx_l2norm_split": ([_P, _P, _P, _P, _P, _LL, _I, _P], _I),
+    "gx_l2norm_bwd_split": ([_P, _P, _P, _P, _P, _P, _P, _LL, _I, _P], _I),
+    "gx_segment_sum_rows": ([_P, _P, _P, _P, _P, _LL, _I, _P], _I),
     "gx_normalize_rows": ([_P, _LL, _I, _P], _I),
     "gx_sinkhorn_max_parts": ([], _I),
     "gx_sinkhorn_pass": ([_P, _LL, _I, _LL, _F, _I, _P, _P, _P, _LL, _P, C.POINTER(_I), _P], _I),
@@ -468,28 +469,48 @@ def gather_rows(feats_nhwc, out_h, out_w, hlen, row_img, row_src, nrows, ld=None
     return a_hi, a_lo, a_f
 
 
-def l2norm_split(z, want_lo=True):
+def l2norm_split(z, want_lo=True, row_idx=None):
+    """zn = normalise(z[row_idx]) (row_idx int32 [n], -1 = zero row) or normalise(z)"""
     lib = load()
     _f32(z, "z")
-    n, c = z.shape
+    c = z.shape[1]
+    n = z.shape[0] if row_idx is None else row_idx.numel()
     hi = torch.empty((n, c), dtype=torch.bfloat16, device=z.device)
     lo = torch.empty_like(hi) if want_lo else None
     inv = torch.empty((n,), dtype=torch.float32, device=z.device)
     with timed("l2norm_split", float(n) * c * (4 + (4 if want_lo else 2))):
-        _check(lib.gx_l2norm_split(_ptr(z), _ptr(hi), _ptr(lo), _ptr(inv), n, c, _stream()), "gx_l2norm_split")
+        _check(lib.gx_l2norm_split(_ptr(z), _ptr(row_idx), _ptr(hi), _ptr(lo), _ptr(inv), n, c, _stream()),
+               "gx_l2norm_split")
     _count()
     return hi, lo, inv
 
 
-def l2norm_bwd_split(dzn, zn_hi, zn_lo, inv_norm, want_lo=True):
+def l2norm_bwd_split(dzn, zn_hi, zn_lo, inv_norm, want_lo=True, want_planes=True, out_f32=None):
+    """dz planes and / or fp32 rows written into `out_f32` [n,c]"""
     lib = load()
     _f32(dzn, "dzn")
     n, c = dzn.shape
-    hi = torch.empty((n, c), dtype=torch.bfloat16, device=dzn.device)
-    lo = torch.empty_like(hi) if want_lo else None
+    hi = torch.empty((n, c), dtype=torch.bfloat16, device=dzn.device) if want_planes else None
+    lo = torch.empty_like(hi) if (want_lo and want_planes) else None
+    if out_f32 is not None:
+        _f32(out_f32, "out_f32")
     with timed("l2norm_bwd_split", float(n) * c * (4 + (4 if zn_lo is not None else 2) + (4 if want_lo else 2))):
-        _check(lib.gx_l2norm_bwd_split(_ptr(dzn), _ptr(zn_hi), _ptr(zn_lo), _ptr(inv_norm), _ptr(hi), _ptr(lo), n,
-                                       c, _stream()), "gx_l2norm_bwd_split")
+        _check(lib.gx_l2norm_bwd_split(_ptr(dzn), _ptr(zn_hi), _ptr(zn_lo), _ptr(inv_norm), _ptr(hi), _ptr(lo),
+                                       _ptr(out_f32), n, c, _stream()), "gx_l2norm_bwd_split")
+    _count()
+    return hi, lo
+
+
+def segment_sum_rows(rows, order, seg_off, nseg, want_lo=False):
+    """bf16 planes [nseg, c] of the per-segment sums of `rows[order[...]]`"""
+    lib = load()
+    _f32(rows, "rows")
+    c = rows.shape[1]
+    hi = torch.empty((nseg, c), dtype=torch.bfloat16, device=rows.device)
+    lo = torch.empty_like(hi) if want_lo else None
+    with timed("segment_sum_rows", float(rows.shape[0]) * c * 4 + float(nseg) * c * (4 if want_lo else 2)):
+        _check(lib.gx_segment_sum_rows(_ptr(rows), _ptr(order), _ptr(seg_off), _ptr(hi), _ptr(lo), nseg, c,
+                                       _stream()), "gx_segment_sum_rows")
     _count()
     return hi, lo
 

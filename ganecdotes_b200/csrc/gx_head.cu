@@ -76,13 +76,27 @@ gather_rows_kernel(const gx_gather_desc d) {
 // ---------------------------------------------------------------------------
 // L2 normalisation of projected rows (warp per row)
 // ---------------------------------------------------------------------------
-__global__ void l2norm_split_kernel(const float* __restrict__ z, __nv_bfloat16* __restrict__ hi,
-                                    __nv_bfloat16* __restrict__ lo, float* __restrict__ inv_norm, long long n, int c) {
+__global__ void l2norm_split_kernel(const float* __restrict__ z, const int* __restrict__ row_idx,
+                                    __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
+                                    float* __restrict__ inv_norm, long long n, int c) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
-  const float4* zr = reinterpret_cast<const float4*>(z + row * c);
   const int cq = c >> 2;
+  uint2* oh = reinterpret_cast<uint2*>(hi + row * c);
+  uint2* ol = lo ? reinterpret_cast<uint2*>(lo + row * c) : nullptr;
+  // optional gather: output row `row` normalises input row row_idx[row]; -1 = an all-zero row
+  // (rotation fill), whose normalisation is 0 (F.normalize clamps the norm at 1e-12)
+  const long long src = row_idx ? (long long)row_idx[row] : row;
+  if (src < 0) {
+    if (lane == 0 && inv_norm) inv_norm[row] = 1e12f;
+    for (int i = lane; i < cq; i += 32) {
+      oh[i] = make_uint2(0u, 0u);
+      if (ol) ol[i] = make_uint2(0u, 0u);
+    }
+    return;
+  }
+  const float4* zr = reinterpret_cast<const float4*>(z + src * c);
   float ss = 0.f;
   for (int i = lane; i < cq; i += 32) {
     const float4 v = __ldg(zr + i);
@@ -91,8 +105,6 @@ __global__ void l2norm_split_kernel(const float* __restrict__ z, __nv_bfloat16* 
   ss = gx_warp_sum(ss);
   const float inv = 1.f / fmaxf(sqrtf(ss), 1e-12f);
   if (lane == 0 && inv_norm) inv_norm[row] = inv;
-  uint2* oh = reinterpret_cast<uint2*>(hi + row * c);
-  uint2* ol = lo ? reinterpret_cast<uint2*>(lo + row * c) : nullptr;
   for (int i = lane; i < cq; i += 32) {
     const float4 v = __ldg(zr + i);
     uint2 h, l;
@@ -120,8 +132,8 @@ __device__ __forceinline__ float4 planes_to_float4(uint2 h, const uint2* lo_ptr)
 
 __global__ void l2norm_bwd_split_kernel(const float* __restrict__ dzn, const __nv_bfloat16* __restrict__ zh,
                                         const __nv_bfloat16* __restrict__ zl, const float* __restrict__ inv_norm,
-                                        __nv_bfloat16* __restrict__ dh, __nv_bfloat16* __restrict__ dl, long long n,
-                                        int c) {
+                                        __nv_bfloat16* __restrict__ dh, __nv_bfloat16* __restrict__ dl,
+                                        float* __restrict__ dz_f32, long long n, int c) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
@@ -137,15 +149,45 @@ __global__ void l2norm_bwd_split_kernel(const float* __restrict__ dzn, const __n
   }
   dot = gx_warp_sum(dot);
   const float inv = inv_norm[row];
-  uint2* oh = reinterpret_cast<uint2*>(dh + row * c);
+  uint2* oh = dh ? reinterpret_cast<uint2*>(dh + row * c) : nullptr;
   uint2* ol = dl ? reinterpret_cast<uint2*>(dl + row * c) : nullptr;
+  float4* of = dz_f32 ? reinterpret_cast<float4*>(dz_f32 + row * c) : nullptr;
   for (int i = lane; i < cq; i += 32) {
     const float4 g = __ldg(gr + i);
     const float4 zv = planes_to_float4(hr[i], lr ? lr + i : nullptr);
+    const float4 d = make_float4((g.x - zv.x * dot) * inv, (g.y - zv.y * dot) * inv, (g.z - zv.z * dot) * inv,
+                                 (g.w - zv.w * dot) * inv);
+    if (oh) {
+      uint2 h, l;
+      gx_split4(d, h, l);
+      oh[i] = h;
+      if (ol) ol[i] = l;
+    }
+    if (of) of[i] = d;
+  }
+}
+
+// out[seg,:] = sum over r in [seg_off[seg], seg_off[seg+1]) of rows[order[r], :]  (deterministic
+// gather-reduce; used to fold the per-patch dZ rows of pixels sampled several times into one
+// row per pixel), written as bf16 planes.  Warp per segment.
+__global__ void segment_sum_rows_kernel(const float* __restrict__ rows, const int* __restrict__ order,
+                                        const int* __restrict__ seg_off, __nv_bfloat16* __restrict__ hi,
+                                        __nv_bfloat16* __restrict__ lo, long long nseg, int c) {
+  const int lane = threadIdx.x & 31;
+  const long long seg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (seg >= nseg) return;
+  const int r0 = seg_off[seg], r1 = seg_off[seg + 1];
+  const int cq = c >> 2;
+  uint2* oh = reinterpret_cast<uint2*>(hi + seg * c);
+  uint2* ol = lo ? reinterpret_cast<uint2*>(lo + seg * c) : nullptr;
+  for (int i = lane; i < cq; i += 32) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int r = r0; r < r1; ++r) {
+      const float4 v = __ldg(reinterpret_cast<const float4*>(rows + (long long)order[r] * c) + i);
+      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+    }
     uint2 h, l;
-    gx_split4(make_float4((g.x - zv.x * dot) * inv, (g.y - zv.y * dot) * inv, (g.z - zv.z * dot) * inv,
-                          (g.w - zv.w * dot) * inv),
-              h, l);
+    gx_split4(acc, h, l);
     oh[i] = h;
     if (ol) ol[i] = l;
   }
@@ -773,21 +815,31 @@ extern "C" int gx_gather_rows(const gx_gather_desc* d, void* stream) {
   return GX_OK;
 }
 
-extern "C" int gx_l2norm_split(const float* z, void* zn_hi, void* zn_lo, float* inv_norm, long long n, int c,
-                               void* stream) {
+extern "C" int gx_l2norm_split(const float* z, const int* row_idx, void* zn_hi, void* zn_lo, float* inv_norm,
+                               long long n, int c, void* stream) {
   GX_CHECK_ARG(z && zn_hi && n > 0 && c % 4 == 0);
   l2norm_split_kernel<<<gx_cdiv(n, 8), 256, 0, (cudaStream_t)stream>>>(
-      z, reinterpret_cast<__nv_bfloat16*>(zn_hi), reinterpret_cast<__nv_bfloat16*>(zn_lo), inv_norm, n, c);
+      z, row_idx, reinterpret_cast<__nv_bfloat16*>(zn_hi), reinterpret_cast<__nv_bfloat16*>(zn_lo), inv_norm, n, c);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }
 
 extern "C" int gx_l2norm_bwd_split(const float* dzn, const void* zn_hi, const void* zn_lo, const float* inv_norm,
-                                   void* dz_hi, void* dz_lo, long long n, int c, void* stream) {
-  GX_CHECK_ARG(dzn && zn_hi && inv_norm && dz_hi && n > 0 && c % 4 == 0);
+                                   void* dz_hi, void* dz_lo, float* dz_f32, long long n, int c, void* stream) {
+  GX_CHECK_ARG(dzn && zn_hi && inv_norm && (dz_hi || dz_f32) && n > 0 && c % 4 == 0);
+  GX_CHECK_ARG(dz_lo == nullptr || dz_hi != nullptr);
   l2norm_bwd_split_kernel<<<gx_cdiv(n, 8), 256, 0, (cudaStream_t)stream>>>(
       dzn, reinterpret_cast<const __nv_bfloat16*>(zn_hi), reinterpret_cast<const __nv_bfloat16*>(zn_lo), inv_norm,
-      reinterpret_cast<__nv_bfloat16*>(dz_hi), reinterpret_cast<__nv_bfloat16*>(dz_lo), n, c);
+      reinterpret_cast<__nv_bfloat16*>(dz_hi), reinterpret_cast<__nv_bfloat16*>(dz_lo), dz_f32, n, c);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_segment_sum_rows(const float* rows, const int* order, const int* seg_off, void* hi, void* lo,
+                                   long long nseg, int c, void* stream) {
+  GX_CHECK_ARG(rows && order && seg_off && hi && nseg > 0 && c % 4 == 0);
+  segment_sum_rows_kernel<<<gx_cdiv(nseg, 8), 256, 0, (cudaStream_t)stream>>>(
+      rows, order, seg_off, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), nseg, c);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }

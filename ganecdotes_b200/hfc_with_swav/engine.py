@@ -220,8 +220,21 @@ def sinkhorn_log_a(s, niters, eps, ws, n_total, group=None, r=None, c=None, pass
     return log_a_fn(u, r)
 
 
-def scores_backward(head: SwavHead, fw, ds_hi, ds_lo):
-    """Accumulates gWk += dS^T Zn and gWp += dZ^T A for one view-patch."""
+def scores_forward_dedup(head: SwavHead, z_all, row_idx):
+    """Per-patch part of the forward when every pixel has been projected once: gather +
+    normalise the patch's rows of Z, prototype scores."""
+    lo = head.passes_fwd == 3
+    n = row_idx.numel()
+    zn_hi, zn_lo, inv = L.l2norm_split(z_all, want_lo=lo or head.passes_bwd == 3, row_idx=row_idx)
+    s = L.gemm(zn_hi, zn_lo if lo else None, head.wk_hi, head.wk_lo, n, head.k, head.c, head.passes_fwd,
+               bias=head.b_proto, tag="gemm_prototype_fwd")
+    return dict(zn_hi=zn_hi, zn_lo=zn_lo, inv=inv, s=s, n=n)
+
+
+def scores_backward(head: SwavHead, fw, ds_hi, ds_lo, dz_rows_out=None):
+    """Accumulates gWk += dS^T Zn and gWp += dZ^T A for one view-patch.  With `dz_rows_out`
+    (fp32 [n,c] slice) the projection-weight gradient is deferred: dZ rows are stored and later
+    folded per pixel (`project_backward_dedup`)."""
     n, k, c, d = fw["n"], head.k, head.c, head.d
     pb = head.passes_bwd
     dzn = L.gemm(ds_hi, ds_lo if pb == 3 else None, head.wkT_hi, head.wkT_lo if pb == 3 else None, n, c, k, pb,
@@ -232,10 +245,24 @@ def scores_backward(head: SwavHead, fw, ds_hi, ds_lo):
     sk1 = pick_split_k(math.ceil(k / bm) * math.ceil(c / 256), kit, sms)
     L.gemm(ds_hi, ds_lo if pb == 3 else None, fw["zn_hi"], fw["zn_lo"] if pb == 3 else None, k, c, n, pb,
            out=head.g_proto, a_mn=True, b_mn=True, split_k=sk1, accumulate=True, tag="gemm_gproto_bwd")
+    if dz_rows_out is not None:
+        L.l2norm_bwd_split(dzn, fw["zn_hi"], fw["zn_lo"], fw["inv"], want_planes=False, out_f32=dz_rows_out)
+        return
     dz_hi, dz_lo = L.l2norm_bwd_split(dzn, fw["zn_hi"], fw["zn_lo"], fw["inv"], want_lo=pb == 3)
     sk2 = pick_split_k(math.ceil(c / bm) * math.ceil(d / 256), kit, sms)
     L.gemm(dz_hi, dz_lo, fw["a_hi"], fw["a_lo"] if pb == 3 else None, c, d, n, pb, out=head.g_proj, a_mn=True,
            b_mn=True, split_k=sk2, accumulate=True, tag="gemm_gproj_bwd")
+
+
+def project_backward_dedup(head: SwavHead, dz_rows, order, seg_off, a_hi, a_lo, npix):
+    """gWp += dZ_pix^T A_pix with dZ_pix[pixel] = sum of the dZ rows of all samples of that pixel."""
+    pb = head.passes_bwd
+    dz_hi, dz_lo = L.segment_sum_rows(dz_rows, order, seg_off, npix, want_lo=pb == 3)
+    c, d = head.c, head.d
+    bm = 256 if pb == 1 else 128
+    sk = pick_split_k(math.ceil(c / bm) * math.ceil(d / 256), (npix + 63) // 64, L.load().gx_sinkhorn_max_parts())
+    L.gemm(dz_hi, dz_lo, a_hi, a_lo if pb == 3 else None, c, d, npix, pb, out=head.g_proj, a_mn=True, b_mn=True,
+           split_k=sk, accumulate=True, tag="gemm_gproj_bwd")
 
 
 @dataclass
@@ -273,6 +300,7 @@ class StepConfig:
     perturb_std: List[float]
     need_image: bool = False
     source_pdf: str = 'uniform'
+    dedup: Optional[bool] = None   # project every pixel once (None: automatic, when P*N > H*W)
 
 
 @dataclass
@@ -283,6 +311,17 @@ class StepInputs:
     rows: dict                         # name -> (row_src [P, B*N] int32, row_img [B*N] int32)
     h2d_bytes: int = 0
     index_maps: Optional[dict] = None  # name -> int32 [H*W] (source_pdf == 'image', single latent)
+    dedup: Optional[dict] = None       # name -> (row_idx [P, B*N] int32, order int32, seg_off int32 [B*H*W+1])
+
+
+def use_dedup(cfg: StepConfig, out_h, out_w) -> bool:
+    """The projection depends on the pixel, not on the patch: when the patches of a step sample
+    more rows than the image has pixels (ffhq: 5 x 20000 > 65536) it is cheaper to project every
+    pixel once and let the patches gather rows of Z."""
+    if cfg.dedup is not None:
+        return bool(cfg.dedup)
+    n = cfg.patch_size if cfg.patch_size is not None else out_h * out_w
+    return cfg.num_patches * n > out_h * out_w
 
 
 def prepare_step_inputs(gen, draws: StepDraws, cfg: StepConfig, device) -> StepInputs:
@@ -301,6 +340,20 @@ def prepare_step_inputs(gen, draws: StepDraws, cfg: StepConfig, device) -> StepI
         rs, ri = build_row_indices(out_h, out_w, view, draws.perms, cfg.patch_size, device)
         rows[name] = (rs, ri)
         nbytes += pr.numel() * 4 + rs.numel() * 4 + ri.numel() * 4
+    dedup = None
+    if use_dedup(cfg, out_h, out_w):
+        dedup = {}
+        hw = out_h * out_w
+        for name in ("s", "t"):
+            rs, ri = rows[name]
+            ridx = torch.where(rs >= 0, ri.unsqueeze(0) * hw + rs, torch.full_like(rs, -1))      # [P, B*N]
+            keys = ridx.flatten().long()
+            order = torch.argsort(keys)
+            n_invalid = int((keys < 0).sum())
+            counts = torch.bincount(keys[keys >= 0], minlength=draws.z.shape[0] * hw)
+            seg_off = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=device)
+            seg_off[1:] = torch.cumsum(counts, 0).to(torch.int32)
+            dedup[name] = (ridx.contiguous(), order[n_invalid:].to(torch.int32).contiguous(), seg_off)
     index_maps = None
     if cfg.source_pdf == 'image':
         if draws.z.shape[0] != 1:
@@ -310,7 +363,7 @@ def prepare_step_inputs(gen, draws: StepDraws, cfg: StepConfig, device) -> StepI
             m = rotate_flip_index_map(out_h, out_w, view.angle[0], view.flip[0]).to(torch.int32)
             index_maps[name] = m.to(device, non_blocking=True)
             nbytes += m.numel() * 4
-    return StepInputs(z=z, views=views, rows=rows, h2d_bytes=nbytes, index_maps=index_maps)
+    return StepInputs(z=z, views=views, rows=rows, h2d_bytes=nbytes, index_maps=index_maps, dedup=dedup)
 
 
 @torch.no_grad()
@@ -348,11 +401,23 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
     w = gen.style(inp.z.float().contiguous())
     feats = {}
     out_h = out_w = gen.size
+    dedup = inp.dedup is not None
+    allpix = {}
+    if cfg.hlen % 8:
+        raise ValueError("hlen must be a multiple of 8 (16-byte TMA row pitch of the bf16 operand planes)")
+    n_patch_rows = b * (cfg.patch_size if cfg.patch_size is not None else out_h * out_w)
     for name in ("s", "t"):
         layer_no, pert_rows = inp.views[name]
         wplus = view_wplus_device(gen, w, mean_latent, cfg.truncation, layer_no, pert_rows, cfg.perturb_std)
         _, f = gen.synthesize(wplus, None, need_image=cfg.need_image)
         feats[name] = f
+        if dedup:
+            npix = b * out_h * out_w
+            a_hi, a_lo, _ = L.gather_rows(f, out_h, out_w, cfg.hlen, None, None, npix, want_lo=head.passes_fwd == 3)
+            z_all = L.gemm(a_hi, a_lo, head.wp_hi, head.wp_lo, npix, head.c, cfg.hlen, head.passes_fwd,
+                           tag="gemm_projection_fwd")
+            dz_rows = torch.empty((cfg.num_patches * n_patch_rows, head.c), dtype=torch.float32, device=dev)
+            allpix[name] = dict(a_hi=a_hi, a_lo=a_lo, z=z_all, dz_rows=dz_rows, npix=npix)
 
     n_local = b * (cfg.patch_size if cfg.patch_size is not None else out_h * out_w)
     n_total = n_local * world
@@ -361,8 +426,11 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
     for p in range(cfg.num_patches):
         fw = {}
         for name in ("s", "t"):
-            row_src, row_img = inp.rows[name]
-            fw[name] = scores_forward(head, feats[name], out_h, out_w, cfg.hlen, row_img, row_src[p], n_local)
+            if dedup:
+                fw[name] = scores_forward_dedup(head, allpix[name]["z"], inp.dedup[name][0][p])
+            else:
+                row_src, row_img = inp.rows[name]
+                fw[name] = scores_forward(head, feats[name], out_h, out_w, cfg.hlen, row_img, row_src[p], n_local)
         rc_s = rc_t = (None, None)
         if cfg.source_pdf == 'image':
             rc_s = image_marginals(feats["s"], out_h, out_w, cfg.hlen, inp.index_maps["s"], head.k, n_local)
@@ -375,8 +443,14 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
         loss_acc += loss_parts.sum()
         head.g_bias += db
         fw["s"].pop("s"), fw["t"].pop("s")
-        scores_backward(head, fw["s"], ds_s[0], ds_s[1])
-        scores_backward(head, fw["t"], ds_t[0], ds_t[1])
+        for name, ds in (("s", ds_s), ("t", ds_t)):
+            out = allpix[name]["dz_rows"][p * n_local:(p + 1) * n_local] if dedup else None
+            scores_backward(head, fw[name], ds[0], ds[1], out)
+    if dedup:
+        for name in ("s", "t"):
+            ap = allpix[name]
+            project_backward_dedup(head, ap["dz_rows"], inp.dedup[name][1], inp.dedup[name][2], ap["a_hi"],
+                                   ap["a_lo"], ap["npix"])
     loss = loss_acc / (n_total * cfg.num_patches)
     if group is not None:
         for g in (head.g_proj, head.g_proto, head.g_bias):

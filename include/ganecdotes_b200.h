@@ -190,13 +190,22 @@ typedef struct gx_gather_desc {
  * gather, emitting the projection GEMM's A operand (ref: :108-130,:158-167,:358-359). */
 int gx_gather_rows(const gx_gather_desc* d, void* stream);
 
-/* z [n,c] -> zn = z / max(||z||,1e-12) as split planes, inv_norm[n] kept for backward
- * (ref: F.normalize at swav_clustering.py:174). */
-int gx_l2norm_split(const float* z, void* zn_hi, void* zn_lo, float* inv_norm, long long n, int c, void* stream);
+/* zn[r,:] = z[src,:] / max(||z[src,:]||,1e-12) as split planes, src = row_idx ? row_idx[r] : r
+ * (row_idx[r] = -1: an all-zero input row -> zero output); inv_norm[n] kept for backward
+ * (ref: F.normalize at swav_clustering.py:174).  z [*,c]; outputs have n rows. */
+int gx_l2norm_split(const float* z, const int* row_idx, void* zn_hi, void* zn_lo, float* inv_norm, long long n,
+                    int c, void* stream);
 
-/* backward of the normalisation: dz = (dzn - zn*(zn.dzn)) * inv_norm, emitted as split planes. */
+/* backward of the normalisation: dz = (dzn - zn*(zn.dzn)) * inv_norm, emitted as split planes
+ * and / or fp32 rows (either output may be NULL). */
 int gx_l2norm_bwd_split(const float* dzn, const void* zn_hi, const void* zn_lo, const float* inv_norm, void* dz_hi,
-                        void* dz_lo, long long n, int c, void* stream);
+                        void* dz_lo, float* dz_f32, long long n, int c, void* stream);
+
+/* out[seg,:] = sum_{r in [seg_off[seg], seg_off[seg+1])} rows[order[r],:] as bf16 planes: folds the
+ * dZ rows of pixels that were sampled by several patches into one row per pixel (deterministic,
+ * no atomics), so the projection-weight gradient GEMM runs over pixels, not samples. */
+int gx_segment_sum_rows(const float* rows, const int* order, const int* seg_off, void* hi, void* lo,
+                        long long nseg, int c, void* stream);
 
 /* prototype row normalisation in place + split planes (+ transposed planes for dZ),
  * ref: swav_clustering.py:328-331. w [k,c]. */

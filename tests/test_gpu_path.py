@@ -178,8 +178,11 @@ def oracle_step(sd, mean_latent, draws, wp, wk, bk, hlen, patch, npatch, pstd, n
     return O.swav_step(rs, rt, wp, wk, bk, niters, eps, temp, bufs)
 
 
-def test_batched_joint_step_matches_oracle(gen):
-    """B = 3 latents per step: joint-batch Sinkhorn over the row-concatenation."""
+@pytest.mark.parametrize("dedup", [False, True])
+def test_batched_joint_step_matches_oracle(gen, dedup):
+    """B = 3 latents per step: joint-batch Sinkhorn over the row-concatenation.
+    dedup=True: every pixel is projected once and the patches gather rows of Z (the path the
+    full-size ffhq step takes, where 5 x 20000 samples > 65536 pixels)."""
     from ganecdotes_b200.hfc_with_swav import engine as E
     from ganecdotes_b200 import _lib as L
     sd = O.init_generator_state(16, 64, 2, 7)
@@ -192,7 +195,7 @@ def test_batched_joint_step_matches_oracle(gen):
     pstd = [1.0, 0.5, 1.0]
     head = E.SwavHead(wp.clone().cuda(), wk.clone().cuda(), bk.clone().cuda(), 0.01, 0.9, 0.01, 3, 1)
     cfg = E.StepConfig(hlen=hlen, patch_size=patch, num_patches=npatch, niters=10, eps=0.02, temperature=0.02,
-                       truncation=0.7, perturb_std=pstd)
+                       truncation=0.7, perturb_std=pstd, dedup=dedup)
     bufs = None
     rwp, rwk, rbk = wp, wk, bk
     for step in range(2):
