@@ -7,12 +7,14 @@
 //                  phases) as implicit GEMM: the A tile of a tap is ONE 4-D TMA box of
 //                  the NHWC activation shifted by the tap offset; TMA's out-of-bounds
 //                  zero fill is the conv padding.
-// Roles (256 threads, 1 CTA / SM): warp 0 = TMA producer, warp 1 = MMA issuer,
-// warp 2 = TMEM allocator, warps 4-7 = epilogue (TMEM -> registers -> global).
+// Roles (384 threads, 1 CTA / SM): warp 0 = TMA producer, warp 1 = MMA issuer,
+// warp 2 = TMEM allocator, warps 4-11 = epilogue (TMEM -> registers -> smem transpose -> global).
 // Pipelines: smem ring (full/empty mbarriers) and a 2-deep TMEM accumulator ring
 // (tmem_full/tmem_empty) so the epilogue of tile i overlaps the MMAs of tile i+1.
 // Precision: passes == 3 issues A_lo*B_hi + A_hi*B_lo + A_hi*B_hi into the same fp32
 // accumulator (split-bf16, ~2^-16 relative per product); passes == 1 is plain bf16.
+#include <stdlib.h>
+
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -28,14 +30,16 @@ constexpr int BM = 128;
 constexpr int BK = 64;            // 64 bf16 = 128 B = one swizzle atom
 constexpr int A_PLANE_BYTES = BM * BK * 2;
 constexpr int MAX_STAGES = 8;
-constexpr int NTHREADS = 256;
+constexpr int NTHREADS = 384;      // warps 0-3: producer / MMA / TMEM alloc / spare, warps 4-11: epilogue
+constexpr int EPI_WARPS = 8;       // two warps per TMEM lane quarter, each taking every other 32-column chunk
 constexpr int TMEM_COLS = 512;
 constexpr int SMEM_LIMIT = 227 * 1024;
-constexpr int STAGING_BYTES = 4 * 32 * 33 * 4;  // per-warp 32x33 fp32 transpose tiles of the epilogue
+constexpr int STAGING_BYTES = EPI_WARPS * 32 * 33 * 4;  // per-warp 32x33 fp32 transpose tiles of the epilogue
 
 struct UmmaParams {
   int mode;  // 0 = gemm, 1 = conv
   int passes, block_n, stages;
+  int debug;       // bit 0: skip epilogue global stores (profiling aid, GX_UMMA_DEBUG)
   int mtiles;      // 128-row sub-tiles per CTA tile (2 = 256-row tiles, halves B traffic per FLOP)
   int acc_stages;  // TMEM accumulator ring depth (2 when mtiles*block_n <= 256)
   int a_mn, b_mn;
@@ -147,7 +151,7 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], 4);
+      mbar_init(&tempty_bar[i], EPI_WARPS);
     }
     fence_mbar_init();
   }
@@ -253,6 +257,7 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
   } else if (warp >= 4) {
     // ============================== epilogue ==================================
     const int q = warp & 3;             // TMEM lane quarter owned by this warp
+    const int ehalf = (warp - 4) >> 2;  // which half of the chunks this warp handles
     const int row = q * 32 + lane;      // tile row == TMEM lane
     int it = 0;
     for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
@@ -265,36 +270,63 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
       const int nchunks = p.block_n / 32;
 
       if (p.mode == 0) {
-        // TMEM -> registers (thread = row) -> per-warp 32x33 smem tile -> registers (lane =
-        // column) so that every global store / atomic of a warp covers one contiguous 128 B row
-        // segment.
-        float* stg = staging + q * (32 * 33);
+        // TMEM -> registers (thread = row) -> per-warp 32x33 smem tile -> registers (8 lanes per
+        // row, 4 columns per lane) so that every 128-bit global store of a warp covers four
+        // contiguous 128 B row segments.
+        const uint32_t stg = smem_u32(staging) + (uint32_t)((warp - 4) * (32 * 33 * 4));
         const bool add_bias = p.bias != nullptr && (!p.atomic || t.kbeg == 0);
+        const bool vec_ok = !p.atomic && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
+        const int lr = lane >> 3, lc = (lane & 7) * 4;   // vector path: row-in-group, first column
         for (int sub = 0; sub < p.mtiles; ++sub) {
           const long long mrow0 = (long long)t.m0 + sub * BM + q * 32;   // first row of this warp
           if (mrow0 >= p.M) break;                                        // warp-uniform
-          for (int ch = 0; ch < nchunks; ++ch) {
+          const int rows_valid = (int)min((long long)32, (long long)p.M - mrow0);
+          for (int ch = ehalf; ch < nchunks; ch += 2) {
             const int n_base = t.n0 + ch * 32;
             if (n_base >= p.N) break;  // warp-uniform
             uint32_t r[32];
             tmem_ld_32x32(taddr0 + sub * p.block_n + ch * 32, r);
             tmem_ld_wait();
+            if (p.debug & 2) continue;
+            {
+              const uint32_t wa = stg + (uint32_t)(lane * 33 * 4);
 #pragma unroll
-            for (int i = 0; i < 32; ++i) stg[lane * 33 + i] = __uint_as_float(r[i]);
+              for (int i = 0; i < 32; ++i)
+                asm volatile("st.shared.b32 [%0], %1;" ::"r"(wa + i * 4), "r"(r[i]) : "memory");
+            }
             __syncwarp();
-            const int n = n_base + lane;
-            const bool nvalid = n < p.N;
-            const float bv = (add_bias && nvalid) ? __ldg(p.bias + n) : 0.f;
-            float* cptr = p.c + mrow0 * p.ldc + n;
-            const int rows_valid = (int)min((long long)32, (long long)p.M - mrow0);
-            if (p.atomic) {
-#pragma unroll 8
-              for (int rr = 0; rr < 32; ++rr)
-                if (rr < rows_valid && nvalid) atomicAdd(cptr + (long long)rr * p.ldc, stg[rr * 33 + lane] + bv);
+            if (vec_ok && n_base + 32 <= p.N) {
+              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+              if (add_bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + lc));
+              float* cptr = p.c + (mrow0 + lr) * p.ldc + n_base + lc;
+              const uint32_t ra = stg + (uint32_t)((lr * 33 + lc) * 4);
+              const long long rstep = 4 * p.ldc;
+#pragma unroll
+              for (int g = 0; g < 8; ++g) {      // rows 4g + lr
+                float4 v;
+                asm volatile("ld.shared.f32 %0, [%4];\n\tld.shared.f32 %1, [%4+4];\n\t"
+                             "ld.shared.f32 %2, [%4+8];\n\tld.shared.f32 %3, [%4+12];"
+                             : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
+                             : "r"(ra + (uint32_t)(g * 4 * 33 * 4)));
+                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
+                if (4 * g + lr < rows_valid && !(p.debug & 1)) *reinterpret_cast<float4*>(cptr) = v;
+                cptr += rstep;
+              }
             } else {
-#pragma unroll 8
-              for (int rr = 0; rr < 32; ++rr)
-                if (rr < rows_valid && nvalid) cptr[(long long)rr * p.ldc] = stg[rr * 33 + lane] + bv;
+              const int n = n_base + lane;
+              const bool nvalid = n < p.N;
+              const float bv = (add_bias && nvalid) ? __ldg(p.bias + n) : 0.f;
+              float* cptr = p.c + mrow0 * p.ldc + n;
+              const uint32_t ra = stg + (uint32_t)(lane * 4);
+              for (int rr = 0; rr < rows_valid; ++rr) {
+                float v;
+                asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ra + (uint32_t)(rr * 33 * 4)));
+                if (nvalid) {
+                  if (p.atomic) atomicAdd(cptr, v + bv);
+                  else cptr[0] = v + bv;
+                }
+                cptr += p.ldc;
+              }
             }
             __syncwarp();
           }
@@ -313,7 +345,7 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
         float nz = 0.f;
         if (valid && p.noise != nullptr)
           nz = __ldg(p.noise_strength) * __ldg(p.noise + (long long)b * p.noise_bstride + (long long)oy * p.Wo + ox);
-        for (int ch = 0; ch < nchunks; ++ch) {
+        for (int ch = ehalf; ch < nchunks; ch += 2) {
           const int co = t.n0 + ch * 32;
           if (co >= p.Cout) break;
           uint32_t r[32];
@@ -442,7 +474,16 @@ int pick_stages(int passes, int block_n, int mtiles, int want) {
   return s;
 }
 
-int launch(const UmmaParams& p, const CUtensorMap* maps, int total_work, cudaStream_t st) {
+int launch(const UmmaParams& p_in, const CUtensorMap* maps, int total_work, cudaStream_t st) {
+  UmmaParams p = p_in;
+  {
+    static int dbg = -1;
+    if (dbg < 0) {
+      const char* e = getenv("GX_UMMA_DEBUG");
+      dbg = e ? atoi(e) : 0;
+    }
+    p.debug = dbg;
+  }
   const int nplanes = p.passes == 3 ? 2 : 1;
   const int stage_bytes = nplanes * (A_PLANE_BYTES * p.mtiles + p.block_n * BK * 2);
   const int smem_bytes = p.stages * stage_bytes + 256 + STAGING_BYTES + 1024;
