@@ -399,12 +399,23 @@ sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long 
   }
 }
 
-__global__ void colsum_parts_kernel(const float* __restrict__ parts, int nparts, int k, float* __restrict__ u) {
-  const int col = blockIdx.x * blockDim.x + threadIdx.x;
-  if (col >= k) return;
+// u[col] = sum_p parts[p, col]; 32 columns x 8 part-slices per block, fixed summation order
+__global__ void __launch_bounds__(256)
+colsum_parts_kernel(const float* __restrict__ parts, int nparts, int k, float* __restrict__ u) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
   float acc = 0.f;
-  for (int p = 0; p < nparts; ++p) acc += parts[(long long)p * k + col];
-  u[col] = acc;
+  if (col < k)
+    for (int p = ty; p < nparts; p += 8) acc += parts[(long long)p * k + col];
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && col < k) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    u[col] = t;
+  }
 }
 
 __global__ void log_a_kernel(const float* __restrict__ u, const float* __restrict__ r, int k,
@@ -942,7 +953,7 @@ extern "C" int gx_sinkhorn_pass(const float* s, long long n, int k, long long ld
 
 extern "C" int gx_sinkhorn_reduce(const float* partials, int nparts, int k, float* u, void* stream) {
   GX_CHECK_ARG(partials && u && nparts > 0 && k > 0);
-  colsum_parts_kernel<<<gx_cdiv(k, 256), 256, 0, (cudaStream_t)stream>>>(partials, nparts, k, u);
+  colsum_parts_kernel<<<gx_cdiv(k, 32), 256, 0, (cudaStream_t)stream>>>(partials, nparts, k, u);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }

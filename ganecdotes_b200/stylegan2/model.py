@@ -298,6 +298,12 @@ class Generator(nn.Module):
         return image, [f.permute(0, 3, 1, 2) for f in feats]
 
     # ------------------------------------------------------------------ fused pipeline
+    # per-resolution timing tags (bench / profiling): off by default
+    tag_layers = False
+
+    def _conv_tag(self, x_hi):
+        return f"modconv@{x_hi.shape[1]}" if self.tag_layers else "modconv"
+
     def _styled_layers(self):
         return [self.conv1] + list(self.convs)
 
@@ -340,13 +346,13 @@ class Generator(nn.Module):
             bias = layer.activate.bias.detach()
             if conv.upsample:
                 tmp, _, _ = L.modconv(x_hi, x_lo, w_hi, w_lo, conv.out_channel, True, passes, demod=demods[n],
-                                      cin_true=conv.in_channel)
+                                      cin_true=conv.in_channel, tag=self._conv_tag(x_hi))
                 f, x_hi, x_lo = L.blur_noise_bias_act(tmp, conv.blur.kernel, conv.blur.pad[0], conv.blur.pad[1], nz,
                                                       strength, bias, 1, nxt, want_lo)
             else:
                 f, x_hi, x_lo = L.modconv(x_hi, x_lo, w_hi, w_lo, conv.out_channel, False, passes, demod=demods[n],
                                           noise=nz, noise_strength=strength, bias=bias, act=1, next_style=nxt,
-                                          want_next_lo=want_lo, cin_true=conv.in_channel)
+                                          want_next_lo=want_lo, cin_true=conv.in_channel, tag=self._conv_tag(x_hi))
             feats.append(f)
             if need_image and n % 2 == 0:
                 rgb = self.to_rgb1 if n == 0 else self.to_rgbs[n // 2 - 1]
