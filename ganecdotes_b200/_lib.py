@@ -41,7 +41,8 @@ class gx_gemm_desc(C.Structure):
         ("lda", C.c_longlong), ("ldb", C.c_longlong), ("a_mn_major", C.c_int), ("b_mn_major", C.c_int),
         ("m", C.c_int), ("n", C.c_int), ("k", C.c_int), ("passes", C.c_int),
         ("c", C.c_void_p), ("ldc", C.c_longlong), ("bias", C.c_void_p), ("split_k", C.c_int),
-        ("accumulate", C.c_int), ("force_m128", C.c_int), ("block_n", C.c_int), ("stages", C.c_int),
+        ("accumulate", C.c_int), ("force_m128", C.c_int), ("colexp_sum", C.c_void_p), ("colexp_scale", C.c_float),
+        ("block_n", C.c_int), ("stages", C.c_int),
     ]
 
 
@@ -418,7 +419,7 @@ def split_planes(x, transpose=False, want_lo=True):
 
 
 def gemm(a_hi, a_lo, b_hi, b_lo, m, n, k, passes, out=None, bias=None, a_mn=False, b_mn=False, split_k=1,
-         block_n=0, stages=0, check=False, accumulate=False, tag="gemm", force_m128=False):
+         block_n=0, stages=0, check=False, accumulate=False, tag="gemm", force_m128=False, colexp=None):
     """C[m,n] = A * B^T.  Planes are 2-D bf16 tensors: A is [m,k] (or [k,m] if a_mn), B is [n,k] (or [k,n])."""
     lib = load()
     dev = a_hi.device
@@ -434,6 +435,8 @@ def gemm(a_hi, a_lo, b_hi, b_lo, m, n, k, passes, out=None, bias=None, a_mn=Fals
     d.split_k, d.block_n, d.stages = split_k, block_n, stages
     d.accumulate = int(accumulate)
     d.force_m128 = int(force_m128)
+    if colexp is not None:      # (zeroed fp32 [n] tensor, scale in the log2 domain)
+        d.colexp_sum, d.colexp_scale = _ptr(colexp[0]), float(colexp[1])
     fn = lib.gx_gemm_check if check else lib.gx_gemm
     with timed(tag, 2.0 * m * n * k):
         _check(fn(C.byref(d), _stream()), "gx_gemm")

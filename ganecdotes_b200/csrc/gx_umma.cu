@@ -50,6 +50,8 @@ struct UmmaParams {
   long long ldc;
   const float* bias;
   int atomic;
+  float* colexp_sum;   // optional [N]: += sum_m exp2(colexp_scale * C[m,n])  (first Sinkhorn pass fused)
+  float colexp_scale;
   // ---- conv
   int B, H, W, Cin, Cout, upsample;
   int th, tw, nb;
@@ -301,6 +303,7 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
               float* cptr = p.c + (mrow0 + lr) * p.ldc + n_base + lc;
               const uint32_t ra = stg + (uint32_t)((lr * 33 + lc) * 4);
               const long long rstep = 4 * p.ldc;
+              float4 es = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll
               for (int g = 0; g < 8; ++g) {      // rows 4g + lr
                 float4 v;
@@ -309,8 +312,24 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
                              : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
                              : "r"(ra + (uint32_t)(g * 4 * 33 * 4)));
                 v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                if (4 * g + lr < rows_valid && !(p.debug & 1)) *reinterpret_cast<float4*>(cptr) = v;
+                if (4 * g + lr < rows_valid) {
+                  if (!(p.debug & 1)) *reinterpret_cast<float4*>(cptr) = v;
+                  if (p.colexp_sum != nullptr) {
+                    es.x += exp2f(v.x * p.colexp_scale); es.y += exp2f(v.y * p.colexp_scale);
+                    es.z += exp2f(v.z * p.colexp_scale); es.w += exp2f(v.w * p.colexp_scale);
+                  }
+                }
                 cptr += rstep;
+              }
+              if (p.colexp_sum != nullptr) {     // fold the 4 row groups, then one atomic per column
+                es.x += __shfl_xor_sync(0xffffffffu, es.x, 8);  es.y += __shfl_xor_sync(0xffffffffu, es.y, 8);
+                es.z += __shfl_xor_sync(0xffffffffu, es.z, 8);  es.w += __shfl_xor_sync(0xffffffffu, es.w, 8);
+                es.x += __shfl_xor_sync(0xffffffffu, es.x, 16); es.y += __shfl_xor_sync(0xffffffffu, es.y, 16);
+                es.z += __shfl_xor_sync(0xffffffffu, es.z, 16); es.w += __shfl_xor_sync(0xffffffffu, es.w, 16);
+                if (lr == 0) {
+                  float* up = p.colexp_sum + n_base + lc;
+                  atomicAdd(up, es.x); atomicAdd(up + 1, es.y); atomicAdd(up + 2, es.z); atomicAdd(up + 3, es.w);
+                }
               }
             } else {
               const int n = n_base + lane;
@@ -318,15 +337,18 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
               const float bv = (add_bias && nvalid) ? __ldg(p.bias + n) : 0.f;
               float* cptr = p.c + mrow0 * p.ldc + n;
               const uint32_t ra = stg + (uint32_t)(lane * 4);
+              float es = 0.f;
               for (int rr = 0; rr < rows_valid; ++rr) {
                 float v;
                 asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ra + (uint32_t)(rr * 33 * 4)));
                 if (nvalid) {
                   if (p.atomic) atomicAdd(cptr, v + bv);
                   else cptr[0] = v + bv;
+                  if (p.colexp_sum != nullptr) es += exp2f((v + bv) * p.colexp_scale);
                 }
                 cptr += p.ldc;
               }
+              if (p.colexp_sum != nullptr && nvalid && !p.atomic) atomicAdd(p.colexp_sum + n, es);
             }
             __syncwarp();
           }
@@ -534,6 +556,9 @@ extern "C" int gx_gemm(const gx_gemm_desc* d, void* stream) {
   p.split_k = sk;
   p.atomic = (sk > 1 || d->accumulate) ? 1 : 0;
   p.c = d->c; p.ldc = d->ldc; p.bias = d->bias;
+  p.colexp_sum = d->colexp_sum;
+  p.colexp_scale = d->colexp_scale;
+  GX_CHECK_ARG(d->colexp_sum == nullptr || !p.atomic);
 
   CUtensorMap maps[4];
   memset(maps, 0, sizeof(maps));

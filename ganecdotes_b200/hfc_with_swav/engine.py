@@ -186,7 +186,23 @@ class SwavHead:
 # stages
 # ----------------------------------------------------------------------------------------
 
-def scores_forward(head: SwavHead, feats, out_h, out_w, hlen, row_img, row_src, nrows):
+LOG2E = 1.4426950408889634
+
+
+def _proto_scores(head: SwavHead, zn_hi, zn_lo, n, eps):
+    """S = Zn Wk^T + b on the tensor cores; with `eps` the epilogue also accumulates the first
+    Sinkhorn marginal u_k = sum_n exp(S_nk / eps), saving one pass over S."""
+    u0 = None
+    colexp = None
+    if eps is not None:
+        u0 = torch.zeros(head.k, dtype=torch.float32, device=zn_hi.device)
+        colexp = (u0, LOG2E / eps)
+    s = L.gemm(zn_hi, zn_lo if head.passes_fwd == 3 else None, head.wk_hi, head.wk_lo, n, head.k, head.c,
+               head.passes_fwd, bias=head.b_proto, tag="gemm_prototype_fwd", colexp=colexp)
+    return s, u0
+
+
+def scores_forward(head: SwavHead, feats, out_h, out_w, hlen, row_img, row_src, nrows, eps=None):
     """gather -> projection -> normalise -> prototype scores.  Returns a dict of the
     tensors the backward needs."""
     if hlen % 8:
@@ -195,12 +211,12 @@ def scores_forward(head: SwavHead, feats, out_h, out_w, hlen, row_img, row_src, 
     a_hi, a_lo, _ = L.gather_rows(feats, out_h, out_w, hlen, row_img, row_src, nrows, want_lo=lo)
     z = L.gemm(a_hi, a_lo, head.wp_hi, head.wp_lo, nrows, head.c, hlen, head.passes_fwd, tag="gemm_projection_fwd")
     zn_hi, zn_lo, inv = L.l2norm_split(z, want_lo=lo or head.passes_bwd == 3)
-    s = L.gemm(zn_hi, zn_lo if lo else None, head.wk_hi, head.wk_lo, nrows, head.k, head.c, head.passes_fwd,
-               bias=head.b_proto, tag="gemm_prototype_fwd")
-    return dict(a_hi=a_hi, a_lo=a_lo, zn_hi=zn_hi, zn_lo=zn_lo, inv=inv, s=s, n=nrows)
+    s, u0 = _proto_scores(head, zn_hi, zn_lo, nrows, eps)
+    return dict(a_hi=a_hi, a_lo=a_lo, zn_hi=zn_hi, zn_lo=zn_lo, inv=inv, s=s, n=nrows, u0=u0)
 
 
-def sinkhorn_log_a(s, niters, eps, ws, n_total, group=None, r=None, c=None, pass_fn=None, log_a_fn=None):
+def sinkhorn_log_a(s, niters, eps, ws, n_total, group=None, r=None, c=None, pass_fn=None, log_a_fn=None,
+                   u_first=None):
     """Sinkhorn-Knopp in scaling-vector form (ref :509-544): niters streaming passes over
     the LOCAL rows of S; only u[K] crosses ranks (all-reduce SUM, as in SwAV's distributed
     Sinkhorn), and c_n = 1/n_total uses the GLOBAL row count.  Returns log a[K];
@@ -208,27 +224,29 @@ def sinkhorn_log_a(s, niters, eps, ws, n_total, group=None, r=None, c=None, pass
 
     `pass_fn(s, inv_eps, first, u_in, r, c, n_total, ws) -> local column sums u[K]` and
     `log_a_fn(u, r)` default to the CUDA kernels; the CPU tests of the multi-rank logic
-    inject torch stand-ins."""
+    inject torch stand-ins.  `u_first`: the result of the first pass if already available."""
     pass_fn = pass_fn or L.sinkhorn_pass
     log_a_fn = log_a_fn or L.sinkhorn_log_a
     inv_eps = 1.0 / eps
     u = None
     for it in range(niters):
-        u = pass_fn(s, inv_eps, it == 0, u, r, c, n_total, ws)
+        if it == 0 and u_first is not None:
+            u = u_first          # local u_k = sum_n exp(S_nk/eps), produced by the score GEMM's epilogue
+        else:
+            u = pass_fn(s, inv_eps, it == 0, u, r, c, n_total, ws)
         if group is not None:
             torch.distributed.all_reduce(u, group=group.pg)
     return log_a_fn(u, r)
 
 
-def scores_forward_dedup(head: SwavHead, z_all, row_idx):
+def scores_forward_dedup(head: SwavHead, z_all, row_idx, eps=None):
     """Per-patch part of the forward when every pixel has been projected once: gather +
     normalise the patch's rows of Z, prototype scores."""
     lo = head.passes_fwd == 3
     n = row_idx.numel()
     zn_hi, zn_lo, inv = L.l2norm_split(z_all, want_lo=lo or head.passes_bwd == 3, row_idx=row_idx)
-    s = L.gemm(zn_hi, zn_lo if lo else None, head.wk_hi, head.wk_lo, n, head.k, head.c, head.passes_fwd,
-               bias=head.b_proto, tag="gemm_prototype_fwd")
-    return dict(zn_hi=zn_hi, zn_lo=zn_lo, inv=inv, s=s, n=n)
+    s, u0 = _proto_scores(head, zn_hi, zn_lo, n, eps)
+    return dict(zn_hi=zn_hi, zn_lo=zn_lo, inv=inv, s=s, n=n, u0=u0)
 
 
 def scores_backward(head: SwavHead, fw, ds_hi, ds_lo, dz_rows_out=None):
@@ -427,16 +445,19 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
         fw = {}
         for name in ("s", "t"):
             if dedup:
-                fw[name] = scores_forward_dedup(head, allpix[name]["z"], inp.dedup[name][0][p])
+                fw[name] = scores_forward_dedup(head, allpix[name]["z"], inp.dedup[name][0][p], cfg.eps)
             else:
                 row_src, row_img = inp.rows[name]
-                fw[name] = scores_forward(head, feats[name], out_h, out_w, cfg.hlen, row_img, row_src[p], n_local)
+                fw[name] = scores_forward(head, feats[name], out_h, out_w, cfg.hlen, row_img, row_src[p], n_local,
+                                          cfg.eps)
         rc_s = rc_t = (None, None)
         if cfg.source_pdf == 'image':
             rc_s = image_marginals(feats["s"], out_h, out_w, cfg.hlen, inp.index_maps["s"], head.k, n_local)
             rc_t = image_marginals(feats["t"], out_h, out_w, cfg.hlen, inp.index_maps["t"], head.k, n_local)
-        la_s = sinkhorn_log_a(fw["s"]["s"], cfg.niters, cfg.eps, ws, n_total, group, rc_s[0], rc_s[1])
-        la_t = sinkhorn_log_a(fw["t"]["s"], cfg.niters, cfg.eps, ws, n_total, group, rc_t[0], rc_t[1])
+        la_s = sinkhorn_log_a(fw["s"]["s"], cfg.niters, cfg.eps, ws, n_total, group, rc_s[0], rc_s[1],
+                              u_first=fw["s"]["u0"])
+        la_t = sinkhorn_log_a(fw["t"]["s"], cfg.niters, cfg.eps, ws, n_total, group, rc_t[0], rc_t[1],
+                              u_first=fw["t"]["u0"])
         lo = head.passes_bwd == 3
         loss_parts, ds_s, ds_t, db, _ = L.swav_loss(fw["s"]["s"], fw["t"]["s"], 1.0 / cfg.eps, 1.0 / cfg.temperature,
                                                     la_s, la_t, grad_scale, want_lo=lo)

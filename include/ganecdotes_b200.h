@@ -146,6 +146,9 @@ typedef struct gx_gemm_desc {
   int split_k;       /* >= 1; > 1 accumulates atomically into c (caller zeroes c) */
   int accumulate;    /* != 0: c += A*B^T (atomic adds) even when split_k == 1       */
   int force_m128;    /* != 0: never use 256-row CTA tiles (tuning / tests)          */
+  float* colexp_sum; /* optional [N], caller-zeroed: += sum_m exp2(colexp_scale*C[m,n]) - the first
+                        Sinkhorn pass (u_k = sum_n exp(S_nk/eps)) fused into the score GEMM's epilogue */
+  float colexp_scale;
   int block_n;       /* 0 = auto                                                 */
   int stages;        /* 0 = auto                                                 */
 } gx_gemm_desc;

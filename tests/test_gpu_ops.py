@@ -137,6 +137,25 @@ def test_gemm_vs_fp64(L, m, n, k, passes, a_mn, b_mn, split, bias):
     assert (chk.double() - ref).abs().max().item() < tol
 
 
+def test_gemm_fused_first_sinkhorn_marginal(L):
+    """the score GEMM's epilogue can accumulate u_k = sum_n exp(S_nk/eps) (first Sinkhorn pass)"""
+    torch.manual_seed(5)
+    for m, n, k in [(1000, 5000, 512), (333, 72, 64)]:
+        a = torch.nn.functional.normalize(torch.randn(m, k, device="cuda"), dim=1)
+        b = torch.nn.functional.normalize(torch.randn(n, k, device="cuda"), dim=1)
+        bias = 0.02 * torch.randn(n, device="cuda")
+        ah, al = planes(a)
+        bh, bl = planes(b)
+        u = torch.zeros(n, device="cuda")
+        s = L.gemm(ah, al, bh, bl, m, n, k, 3, bias=bias, colexp=(u, 1.4426950408889634 / 0.005))
+        ref = torch.exp(s.double() / 0.005).sum(0)
+        torch.testing.assert_close(u.double(), ref, rtol=2e-4, atol=0)
+        ws = L.SinkhornWorkspace(n, "cuda") if n % 4 == 0 else None
+        if ws is not None:
+            u2 = L.sinkhorn_pass(s, 200.0, True, None, None, None, m, ws)
+            torch.testing.assert_close(u, u2, rtol=2e-4, atol=0)
+
+
 def test_gemm_accumulate(L):
     torch.manual_seed(3)
     a = torch.randn(200, 96, device="cuda")
