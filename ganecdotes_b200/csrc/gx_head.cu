@@ -262,6 +262,32 @@ __device__ __forceinline__ float ex2_fast(float x) {
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
 }
+// packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2): halves the FMA-pipe instruction count
+// of the streaming kernels, which are bound by instruction issue rather than by arithmetic
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
+  float2 d;
+  asm("fma.rn.f32x2 %0, %1, %2, %3;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
+        "l"(reinterpret_cast<unsigned long long&>(c)));
+  return d;
+}
+__device__ __forceinline__ float2 add2(float2 a, float2 b) {
+  float2 d;
+  asm("add.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
+  float2 d;
+  asm("mul.rn.f32x2 %0, %1, %2;"
+      : "=l"(reinterpret_cast<unsigned long long&>(d))
+      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
+  return d;
+}
+__device__ __forceinline__ float2 ex2_2(float2 a) { return make_float2(ex2_fast(a.x), ex2_fast(a.y)); }
+
 __device__ __forceinline__ void group_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
@@ -575,12 +601,11 @@ swav_loss_kernel(const float* __restrict__ ss, const float* __restrict__ st, lon
   __syncthreads();
   // Out-of-range column slots (col >= k) read a clamped, valid address; their contributions to
   // the sums are removed with a -inf additive mask and they store nothing.
-  float db[J][4];
+  float2 db[J][2];
 #pragma unroll
-  for (int j = 0; j < J; ++j)
-#pragma unroll
-    for (int e = 0; e < 4; ++e) db[j][e] = 0.f;
+  for (int j = 0; j < J; ++j) db[j][0] = db[j][1] = make_float2(0.f, 0.f);
   const int col0 = gt * 4;
+  const float2 ce2 = make_float2(ce, ce), ct2 = make_float2(ct, ct);
   float loss_acc = 0.f;
   const float gs = grad_scale * 0.5f * inv_temp;
   for (int it = grp; it < n_iters; it += NG) {
@@ -589,8 +614,8 @@ swav_loss_kernel(const float* __restrict__ ss, const float* __restrict__ st, lon
     gxptx::mbar_wait(&full_bar[sg], (uint32_t)((it / stages) & 1));
     const float* srow_s = reinterpret_cast<const float*>(sk_smem + (size_t)sg * stage_bytes);
     const float* srow_t = srow_s + k;
-    float vs[J][4], vt[J][4];     // raw scores, later softmax(p) numerators
-    float e1s[J][4], e1t[J][4];   // log2-domain S/eps + log a, later q numerators
+    float2 vs[J][2], vt[J][2];     // raw scores, later softmax(p) numerators
+    float2 e1s[J][2], e1t[J][2];   // log2-domain S/eps + log a, later q numerators
     // pass 1: maxima.  Clamped slots re-read valid columns, which leaves the maxima unchanged.
     float mx[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};  // max x1_s, max s_s, max x1_t, max s_t
 #pragma unroll
@@ -600,47 +625,52 @@ swav_loss_kernel(const float* __restrict__ ss, const float* __restrict__ st, lon
       const float4 b = *reinterpret_cast<const float4*>(srow_t + cofs);
       const float4 ls = *reinterpret_cast<const float4*>(sla_s + cofs);
       const float4 lt = *reinterpret_cast<const float4*>(sla_t + cofs);
-      vs[j][0] = a.x; vs[j][1] = a.y; vs[j][2] = a.z; vs[j][3] = a.w;
-      vt[j][0] = b.x; vt[j][1] = b.y; vt[j][2] = b.z; vt[j][3] = b.w;
-      e1s[j][0] = fmaf(a.x, ce, ls.x); e1s[j][1] = fmaf(a.y, ce, ls.y);
-      e1s[j][2] = fmaf(a.z, ce, ls.z); e1s[j][3] = fmaf(a.w, ce, ls.w);
-      e1t[j][0] = fmaf(b.x, ce, lt.x); e1t[j][1] = fmaf(b.y, ce, lt.y);
-      e1t[j][2] = fmaf(b.z, ce, lt.z); e1t[j][3] = fmaf(b.w, ce, lt.w);
+      vs[j][0] = make_float2(a.x, a.y); vs[j][1] = make_float2(a.z, a.w);
+      vt[j][0] = make_float2(b.x, b.y); vt[j][1] = make_float2(b.z, b.w);
+      e1s[j][0] = fma2(vs[j][0], ce2, make_float2(ls.x, ls.y));
+      e1s[j][1] = fma2(vs[j][1], ce2, make_float2(ls.z, ls.w));
+      e1t[j][0] = fma2(vt[j][0], ce2, make_float2(lt.x, lt.y));
+      e1t[j][1] = fma2(vt[j][1], ce2, make_float2(lt.z, lt.w));
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        mx[0] = fmaxf(mx[0], e1s[j][e]);
-        mx[1] = fmaxf(mx[1], vs[j][e]);
-        mx[2] = fmaxf(mx[2], e1t[j][e]);
-        mx[3] = fmaxf(mx[3], vt[j][e]);
+      for (int h = 0; h < 2; ++h) {
+        mx[0] = fmaxf(mx[0], fmaxf(e1s[j][h].x, e1s[j][h].y));
+        mx[1] = fmaxf(mx[1], fmaxf(vs[j][h].x, vs[j][h].y));
+        mx[2] = fmaxf(mx[2], fmaxf(e1t[j][h].x, e1t[j][h].y));
+        mx[3] = fmaxf(mx[3], fmaxf(vt[j][h].x, vt[j][h].y));
       }
     }
     group_reduce<4, true, NW>(mx, red_max[grp], gwarp, lane, 1 + grp, GT);   // stage consumed after this barrier
     if (gt == 0 && it + stages < n_iters) issue(it + stages);
-    // pass 2: sums  Z1_s, Z2_s, D_st = sum e1s*s_t, Z1_t, Z2_t, D_ts = sum e1t*s_s
-    float sm[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f};
+    // pass 2: sums  Z1_s, Z2_s, D_st = sum e1s*s_t, Z1_t, Z2_t, D_ts = sum e1t*s_s   (packed partials)
+    float2 s2[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s2[i] = make_float2(0.f, 0.f);
     const float m2s = mx[1] * ct, m2t = mx[3] * ct;   // log2 domain
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       const float mskj = (col0 + j * (GT * 4) < k) ? 0.f : -INFINITY;
-      const float c1s = mskj - mx[0], c1t = mskj - mx[2];
-      const float c2s = mskj - m2s, c2t = mskj - m2t;
+      const float2 c1s = make_float2(mskj - mx[0], mskj - mx[0]), c1t = make_float2(mskj - mx[2], mskj - mx[2]);
+      const float2 c2s = make_float2(mskj - m2s, mskj - m2s), c2t = make_float2(mskj - m2t, mskj - m2t);
 #pragma unroll
-      for (int e = 0; e < 4; ++e) {
-        const float rs = vs[j][e], rt = vt[j][e];
-        const float q1s = ex2_fast(e1s[j][e] + c1s);
-        const float q1t = ex2_fast(e1t[j][e] + c1t);
-        const float p2s = ex2_fast(fmaf(rs, ct, c2s));
-        const float p2t = ex2_fast(fmaf(rt, ct, c2t));
-        sm[0] += q1s;
-        sm[3] += q1t;
-        sm[2] = fmaf(q1s, rt, sm[2]);
-        sm[5] = fmaf(q1t, rs, sm[5]);
-        sm[1] += p2s;
-        sm[4] += p2t;
-        e1s[j][e] = q1s; e1t[j][e] = q1t;
-        vs[j][e] = p2s; vt[j][e] = p2t;
+      for (int h = 0; h < 2; ++h) {
+        const float2 rs = vs[j][h], rt = vt[j][h];
+        const float2 q1s = ex2_2(add2(e1s[j][h], c1s));
+        const float2 q1t = ex2_2(add2(e1t[j][h], c1t));
+        const float2 p2s = ex2_2(fma2(rs, ct2, c2s));
+        const float2 p2t = ex2_2(fma2(rt, ct2, c2t));
+        s2[0] = add2(s2[0], q1s);
+        s2[3] = add2(s2[3], q1t);
+        s2[2] = fma2(q1s, rt, s2[2]);
+        s2[5] = fma2(q1t, rs, s2[5]);
+        s2[1] = add2(s2[1], p2s);
+        s2[4] = add2(s2[4], p2t);
+        e1s[j][h] = q1s; e1t[j][h] = q1t;
+        vs[j][h] = p2s; vt[j][h] = p2t;
       }
     }
+    float sm[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sm[i] = s2[i].x + s2[i].y;
     group_reduce<6, false, NW>(sm, red_sum[grp], gwarp, lane, 1 + grp, GT);
     const float iz1s = __fdividef(1.f, sm[0]), iz2s = __fdividef(1.f, sm[1]);
     const float iz1t = __fdividef(1.f, sm[3]), iz2t = __fdividef(1.f, sm[4]);
@@ -652,7 +682,8 @@ swav_loss_kernel(const float* __restrict__ ss, const float* __restrict__ st, lon
       loss_acc += -0.5f * (qs_pt + qt_ps);
     }
     // pass 3: gradients.  dL/dS_s uses q_t ; dL/dS_t uses q_s
-    const float a2s = gs * iz2s, a1t = -gs * iz1t, a2t = gs * iz2t, a1s = -gs * iz1s;
+    const float2 a2s = make_float2(gs * iz2s, gs * iz2s), a1t = make_float2(-gs * iz1t, -gs * iz1t);
+    const float2 a2t = make_float2(gs * iz2t, gs * iz2t), a1s = make_float2(-gs * iz1s, -gs * iz1s);
     __nv_bfloat16* ps_hi = ds_s_hi + row * ldd;
     __nv_bfloat16* pt_hi = ds_t_hi + row * ldd;
     const bool want_lo = (ds_s_lo != nullptr) || (ds_t_lo != nullptr);
@@ -660,13 +691,12 @@ swav_loss_kernel(const float* __restrict__ ss, const float* __restrict__ st, lon
     for (int j = 0; j < J; ++j) {
       const int col = col0 + j * (GT * 4);
       if (col < k) {
-        float4 g_s, g_t;
-        g_s.x = fmaf(vs[j][0], a2s, e1t[j][0] * a1t); g_s.y = fmaf(vs[j][1], a2s, e1t[j][1] * a1t);
-        g_s.z = fmaf(vs[j][2], a2s, e1t[j][2] * a1t); g_s.w = fmaf(vs[j][3], a2s, e1t[j][3] * a1t);
-        g_t.x = fmaf(vt[j][0], a2t, e1s[j][0] * a1s); g_t.y = fmaf(vt[j][1], a2t, e1s[j][1] * a1s);
-        g_t.z = fmaf(vt[j][2], a2t, e1s[j][2] * a1s); g_t.w = fmaf(vt[j][3], a2t, e1s[j][3] * a1s);
-        db[j][0] += g_s.x + g_t.x; db[j][1] += g_s.y + g_t.y;
-        db[j][2] += g_s.z + g_t.z; db[j][3] += g_s.w + g_t.w;
+        const float2 gs0 = fma2(vs[j][0], a2s, mul2(e1t[j][0], a1t)), gs1 = fma2(vs[j][1], a2s, mul2(e1t[j][1], a1t));
+        const float2 gt0 = fma2(vt[j][0], a2t, mul2(e1s[j][0], a1s)), gt1 = fma2(vt[j][1], a2t, mul2(e1s[j][1], a1s));
+        db[j][0] = add2(db[j][0], add2(gs0, gt0));
+        db[j][1] = add2(db[j][1], add2(gs1, gt1));
+        const float4 g_s = make_float4(gs0.x, gs0.y, gs1.x, gs1.y);
+        const float4 g_t = make_float4(gt0.x, gt0.y, gt1.x, gt1.y);
         if (want_lo) {
           uint2 h, l;
           gx_split4(g_s, h, l);
@@ -692,7 +722,8 @@ swav_loss_kernel(const float* __restrict__ ss, const float* __restrict__ st, lon
 #pragma unroll
     for (int j = 0; j < J; ++j) {
       const int col = j * (GT * 4) + gt * 4;
-      if (col < k) *reinterpret_cast<float4*>(prow + col) = make_float4(db[j][0], db[j][1], db[j][2], db[j][3]);
+      if (col < k)
+        *reinterpret_cast<float4*>(prow + col) = make_float4(db[j][0].x, db[j][0].y, db[j][1].x, db[j][1].y);
     }
   }
 }
