@@ -205,7 +205,7 @@ def run_ours(args):
     proj = torch.nn.Linear(cfg["hlen"], cfg["nclasses"], bias=False).to(dev)
     proto = torch.nn.Linear(cfg["nclasses"], cfg["nprototypes"]).to(dev)
     head = E.SwavHead(proj.weight.data, proto.weight.data, proto.bias.data, cfg["lr"], cfg["momentum"], cfg["trust"],
-                      args.passes_fwd, args.passes_bwd)
+                      args.passes_fwd, args.passes_bwd, proto_f16=args.proto_f16)
     scfg = E.StepConfig(hlen=cfg["hlen"], patch_size=cfg["patch"], num_patches=cfg["npatch"], niters=cfg["niters"],
                         eps=cfg["eps"], temperature=cfg["temperature"], truncation=cfg["truncation"],
                         perturb_std=cfg["perturb_std"])
@@ -324,8 +324,8 @@ def run_ours(args):
             "metric": "per-pixel feature vectors/sec (ffhq-256 SwAV step)", "value": value, "unit": "vectors/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": f"bf16x{args.passes_fwd}-split fwd / bf16x{args.passes_bwd} bwd operands, fp32 accumulate + "
-                     f"fp32 everywhere else",
+            "dtype": f"bf16x{args.passes_fwd}-split fwd" + (" (score GEMM fp16x1)" if args.proto_f16 else "") +
+                     f" / bf16x{args.passes_bwd} bwd operands, fp32 accumulate + fp32 everywhere else",
             "data": "synthetic",
             "config": {"workload": workload_name(b), "latents_per_gpu": b, "global_latents": b * world,
                        "vectors_per_step": vec_per_step, "l2": "inputs_larger_than_l2 (3.2 GB score matrices)",
@@ -349,6 +349,8 @@ def main():
     ap.add_argument("--latents-per-gpu", type=int, default=8)
     ap.add_argument("--passes-fwd", type=int, default=3, choices=[1, 3])
     ap.add_argument("--passes-bwd", type=int, default=1, choices=[1, 3])
+    ap.add_argument("--proto-f16", action="store_true",
+                    help="pixel x prototype score GEMM on single fp16 planes (|dS| ~ 1e-5) instead of the bf16x3 split")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

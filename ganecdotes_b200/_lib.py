@@ -42,7 +42,7 @@ class gx_gemm_desc(C.Structure):
         ("m", C.c_int), ("n", C.c_int), ("k", C.c_int), ("passes", C.c_int),
         ("c", C.c_void_p), ("ldc", C.c_longlong), ("bias", C.c_void_p), ("split_k", C.c_int),
         ("accumulate", C.c_int), ("force_m128", C.c_int), ("colexp_sum", C.c_void_p), ("colexp_scale", C.c_float),
-        ("block_n", C.c_int), ("stages", C.c_int),
+        ("block_n", C.c_int), ("stages", C.c_int), ("cluster_pair", C.c_int), ("ab_f16", C.c_int),
     ]
 
 
@@ -79,11 +79,14 @@ _SIGNATURES = {
     "gx_torgb": ([_P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _P], _I),
     "gx_gemm": ([C.POINTER(gx_gemm_desc), _P], _I),
     "gx_gemm_check": ([C.POINTER(gx_gemm_desc), _P], _I),
-    "gx_split_planes": ([_P, _LL, _P, _P, _LL, _LL, _I, _P], _I),
+    "gx_split_planes": ([_P, _LL, _P, _P, _LL, _LL, _I, _LL, _P], _I),
     "gx_gather_rows": ([C.POINTER(gx_gather_desc), _P], _I),
-    "gx_l2norm_split": ([_P, _P, _P, _P, _P, _LL, _I, _P], _I),
+    "gx_l2norm_split": ([_P, _P, _P, _P, _P, _P, _LL, _I, _P], _I),
+    "gx_round_f16": ([_P, _LL, _P, _LL, _LL, _P], _I),
     "gx_l2norm_bwd_split": ([_P, _P, _P, _P, _P, _P, _P, _LL, _I, _P], _I),
-    "gx_segment_sum_rows": ([_P, _P, _P, _P, _P, _LL, _I, _P], _I),
+    "gx_segment_sum_rows": ([_P, _P, _P, _P, _P, _P, _LL, _I, _P], _I),
+    "gx_upsample_sum": ([_I, _P, _P, _P, _I, _I, _I, _I, _P, _P], _I),
+    "gx_pool_sum": ([_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P], _I),
     "gx_normalize_rows": ([_P, _LL, _I, _P], _I),
     "gx_sinkhorn_max_parts": ([], _I),
     "gx_sinkhorn_pass": ([_P, _LL, _I, _LL, _F, _I, _P, _P, _P, _LL, _P, C.POINTER(_I), _P], _I),
@@ -404,25 +407,46 @@ def torgb(x_nhwc, w3c, w_scale, s, bias3, skip):
     return out
 
 
-def split_planes(x, transpose=False, want_lo=True):
-    """fp32 [rows, cols] -> bf16 (hi, lo) planes, optionally transposed."""
+def split_planes(x, transpose=False, want_lo=True, out=None):
+    """fp32 [rows, cols] -> bf16 (hi, lo) planes, optionally transposed.  `out=(hi, lo)`: write into
+    (column-slice) views of wider planes instead of allocating."""
     lib = load()
     assert x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1
     rows, cols = x.shape
-    shape = (cols, rows) if transpose else (rows, cols)
-    hi = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
-    lo = torch.empty_like(hi) if want_lo else None
-    _check(lib.gx_split_planes(_ptr(x), x.stride(0), _ptr(hi), _ptr(lo), rows, cols, int(transpose), _stream()),
-           "gx_split_planes")
+    if out is not None:
+        assert not transpose
+        hi, lo = out
+        assert hi.shape == (rows, cols) and hi.stride(1) == 1 and (lo is None or lo.stride() == hi.stride())
+    else:
+        shape = (cols, rows) if transpose else (rows, cols)
+        hi = torch.empty(shape, dtype=torch.bfloat16, device=x.device)
+        lo = torch.empty_like(hi) if want_lo else None
+    with timed("split_planes", float(rows) * cols * (4 + (4 if lo is not None else 2))):
+        _check(lib.gx_split_planes(_ptr(x), x.stride(0), _ptr(hi), _ptr(lo), rows, cols, int(transpose),
+                                   0 if transpose else hi.stride(0), _stream()), "gx_split_planes")
     _count()
     return hi, lo
 
 
+def round_f16(x):
+    """fp32 [rows, cols] -> one fp16 plane"""
+    lib = load()
+    assert x.dim() == 2 and x.dtype == torch.float32 and x.stride(1) == 1
+    out = torch.empty(x.shape, dtype=torch.float16, device=x.device)
+    _check(lib.gx_round_f16(_ptr(x), x.stride(0), _ptr(out), x.shape[0], x.shape[1], _stream()), "gx_round_f16")
+    _count()
+    return out
+
+
 def gemm(a_hi, a_lo, b_hi, b_lo, m, n, k, passes, out=None, bias=None, a_mn=False, b_mn=False, split_k=1,
-         block_n=0, stages=0, check=False, accumulate=False, tag="gemm", force_m128=False, colexp=None):
-    """C[m,n] = A * B^T.  Planes are 2-D bf16 tensors: A is [m,k] (or [k,m] if a_mn), B is [n,k] (or [k,n])."""
+         block_n=0, stages=0, check=False, accumulate=False, tag="gemm", force_m128=False, colexp=None, pair=False):
+    """C[m,n] = A * B^T.  Planes are 2-D bf16 tensors: A is [m,k] (or [k,m] if a_mn), B is [n,k] (or [k,n]).
+    fp16 planes (both operands, passes == 1) are recognised by dtype."""
     lib = load()
     dev = a_hi.device
+    f16 = a_hi.dtype == torch.float16
+    if f16 and (b_hi.dtype != torch.float16 or passes != 1):
+        raise ValueError("fp16 operands: both planes fp16 and passes == 1")
     if out is None:
         out = (torch.zeros if split_k > 1 else torch.empty)((m, n), dtype=torch.float32, device=dev)
     d = gx_gemm_desc()
@@ -435,6 +459,8 @@ def gemm(a_hi, a_lo, b_hi, b_lo, m, n, k, passes, out=None, bias=None, a_mn=Fals
     d.split_k, d.block_n, d.stages = split_k, block_n, stages
     d.accumulate = int(accumulate)
     d.force_m128 = int(force_m128)
+    d.ab_f16 = int(f16)
+    d.cluster_pair = int(pair)
     if colexp is not None:      # (zeroed fp32 [n] tensor, scale in the log2 domain)
         d.colexp_sum, d.colexp_scale = _ptr(colexp[0]), float(colexp[1])
     fn = lib.gx_gemm_check if check else lib.gx_gemm
@@ -472,8 +498,9 @@ def gather_rows(feats_nhwc, out_h, out_w, hlen, row_img, row_src, nrows, ld=None
     return a_hi, a_lo, a_f
 
 
-def l2norm_split(z, want_lo=True, row_idx=None):
-    """zn = normalise(z[row_idx]) (row_idx int32 [n], -1 = zero row) or normalise(z)"""
+def l2norm_split(z, want_lo=True, row_idx=None, want_f16=False):
+    """zn = normalise(z[row_idx]) (row_idx int32 [n], -1 = zero row) or normalise(z).
+    Returns (hi, lo, inv_norm) or, with want_f16, (hi, lo, inv_norm, fp16 plane)."""
     lib = load()
     _f32(z, "z")
     c = z.shape[1]
@@ -481,10 +508,13 @@ def l2norm_split(z, want_lo=True, row_idx=None):
     hi = torch.empty((n, c), dtype=torch.bfloat16, device=z.device)
     lo = torch.empty_like(hi) if want_lo else None
     inv = torch.empty((n,), dtype=torch.float32, device=z.device)
-    with timed("l2norm_split", float(n) * c * (4 + (4 if want_lo else 2))):
-        _check(lib.gx_l2norm_split(_ptr(z), _ptr(row_idx), _ptr(hi), _ptr(lo), _ptr(inv), n, c, _stream()),
-               "gx_l2norm_split")
+    f16 = torch.empty((n, c), dtype=torch.float16, device=z.device) if want_f16 else None
+    with timed("l2norm_split", float(n) * c * (4 + (4 if want_lo else 2) + (2 if want_f16 else 0))):
+        _check(lib.gx_l2norm_split(_ptr(z), _ptr(row_idx), _ptr(hi), _ptr(lo), _ptr(f16), _ptr(inv), n, c,
+                                   _stream()), "gx_l2norm_split")
     _count()
+    if want_f16:
+        return hi, lo, inv, f16
     return hi, lo, inv
 
 
@@ -504,18 +534,55 @@ def l2norm_bwd_split(dzn, zn_hi, zn_lo, inv_norm, want_lo=True, want_planes=True
     return hi, lo
 
 
-def segment_sum_rows(rows, order, seg_off, nseg, want_lo=False):
-    """bf16 planes [nseg, c] of the per-segment sums of `rows[order[...]]`"""
+def segment_sum_rows(rows, order, seg_off, nseg, want_lo=False, want_planes=True, want_f32=False):
+    """per-segment sums of `rows[order[...]]` as bf16 planes [nseg, c] and / or fp32"""
     lib = load()
     _f32(rows, "rows")
     c = rows.shape[1]
-    hi = torch.empty((nseg, c), dtype=torch.bfloat16, device=rows.device)
-    lo = torch.empty_like(hi) if want_lo else None
-    with timed("segment_sum_rows", float(rows.shape[0]) * c * 4 + float(nseg) * c * (4 if want_lo else 2)):
-        _check(lib.gx_segment_sum_rows(_ptr(rows), _ptr(order), _ptr(seg_off), _ptr(hi), _ptr(lo), nseg, c,
+    hi = torch.empty((nseg, c), dtype=torch.bfloat16, device=rows.device) if want_planes else None
+    lo = torch.empty_like(hi) if (want_lo and want_planes) else None
+    f = torch.empty((nseg, c), dtype=torch.float32, device=rows.device) if want_f32 else None
+    with timed("segment_sum_rows", float(rows.shape[0]) * c * 4 + float(nseg) * c * (4 if want_lo or want_f32 else 2)):
+        _check(lib.gx_segment_sum_rows(_ptr(rows), _ptr(order), _ptr(seg_off), _ptr(hi), _ptr(lo), _ptr(f), nseg, c,
                                        _stream()), "gx_segment_sum_rows")
     _count()
-    return hi, lo
+    return hi, lo, f
+
+
+def upsample_sum(parts, batch, out_h, out_w, out=None):
+    """parts: list of fp32 [batch, h_l, w_l, c] tensors -> fp32 [batch*out_h*out_w, c]"""
+    lib = load()
+    n = len(parts)
+    c = parts[0].shape[3]
+    ptrs = (C.c_void_p * n)(*[p.data_ptr() for p in parts])
+    hs = (C.c_int * n)(*[p.shape[1] for p in parts])
+    ws = (C.c_int * n)(*[p.shape[2] for p in parts])
+    for p in parts:
+        _f32(p, "part")
+    if out is None:
+        out = torch.empty((batch * out_h * out_w, c), dtype=torch.float32, device=parts[0].device)
+    assert out.is_contiguous() and out.numel() == batch * out_h * out_w * c
+    nbytes = 4.0 * c * (sum(p.shape[0] * p.shape[1] * p.shape[2] for p in parts) + batch * out_h * out_w)
+    with timed("upsample_sum", nbytes):
+        _check(lib.gx_upsample_sum(n, ptrs, hs, ws, batch, out_h, out_w, c, _ptr(out), _stream()), "gx_upsample_sum")
+    _count()
+    return out
+
+
+def pool_sum(x_nhwc, out_h, out_w, want_f32=True, want_planes=True, want_lo=False):
+    """block sums of fp32 [b,H,W,c] onto [b,out_h,out_w,c]: (fp32, hi, lo)"""
+    lib = load()
+    _f32(x_nhwc, "x")
+    b, h, w, c = x_nhwc.shape
+    dev = x_nhwc.device
+    f = torch.empty((b, out_h, out_w, c), dtype=torch.float32, device=dev) if want_f32 else None
+    hi = torch.empty((b * out_h * out_w, c), dtype=torch.bfloat16, device=dev) if want_planes else None
+    lo = torch.empty_like(hi) if (want_lo and want_planes) else None
+    with timed("pool_sum", 4.0 * b * c * (h * w + out_h * out_w)):
+        _check(lib.gx_pool_sum(_ptr(x_nhwc), b, h, w, out_h, out_w, c, _ptr(f), _ptr(hi), _ptr(lo), _stream()),
+               "gx_pool_sum")
+    _count()
+    return f, hi, lo
 
 
 def normalize_rows_(w):

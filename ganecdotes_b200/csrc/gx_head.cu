@@ -76,15 +76,21 @@ gather_rows_kernel(const gx_gather_desc d) {
 // ---------------------------------------------------------------------------
 // L2 normalisation of projected rows (warp per row)
 // ---------------------------------------------------------------------------
+__device__ __forceinline__ uint2 f16x4(const float4 v) {
+  const __half2 a = __floats2half2_rn(v.x, v.y), b = __floats2half2_rn(v.z, v.w);
+  return make_uint2(*reinterpret_cast<const uint32_t*>(&a), *reinterpret_cast<const uint32_t*>(&b));
+}
+
 __global__ void l2norm_split_kernel(const float* __restrict__ z, const int* __restrict__ row_idx,
                                     __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo,
-                                    float* __restrict__ inv_norm, long long n, int c) {
+                                    __half* __restrict__ f16, float* __restrict__ inv_norm, long long n, int c) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
   const int cq = c >> 2;
   uint2* oh = reinterpret_cast<uint2*>(hi + row * c);
   uint2* ol = lo ? reinterpret_cast<uint2*>(lo + row * c) : nullptr;
+  uint2* of = f16 ? reinterpret_cast<uint2*>(f16 + row * c) : nullptr;
   // optional gather: output row `row` normalises input row row_idx[row]; -1 = an all-zero row
   // (rotation fill), whose normalisation is 0 (F.normalize clamps the norm at 1e-12)
   const long long src = row_idx ? (long long)row_idx[row] : row;
@@ -93,6 +99,7 @@ __global__ void l2norm_split_kernel(const float* __restrict__ z, const int* __re
     for (int i = lane; i < cq; i += 32) {
       oh[i] = make_uint2(0u, 0u);
       if (ol) ol[i] = make_uint2(0u, 0u);
+      if (of) of[i] = make_uint2(0u, 0u);
     }
     return;
   }
@@ -108,9 +115,21 @@ __global__ void l2norm_split_kernel(const float* __restrict__ z, const int* __re
   for (int i = lane; i < cq; i += 32) {
     const float4 v = __ldg(zr + i);
     uint2 h, l;
-    gx_split4(make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv), h, l);
+    const float4 zn = make_float4(v.x * inv, v.y * inv, v.z * inv, v.w * inv);
+    gx_split4(zn, h, l);
     oh[i] = h;
     if (ol) ol[i] = l;
+    if (of) of[i] = f16x4(zn);
+  }
+}
+
+__global__ void round_f16_kernel(const float* __restrict__ x, long long ld, __half* __restrict__ out, long long rows,
+                                 long long cols) {
+  const long long total = rows * cols;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cols, c = i - r * cols;
+    out[i] = __float2half_rn(x[r * ld + c]);
   }
 }
 
@@ -172,24 +191,105 @@ __global__ void l2norm_bwd_split_kernel(const float* __restrict__ dzn, const __n
 // row per pixel), written as bf16 planes.  Warp per segment.
 __global__ void segment_sum_rows_kernel(const float* __restrict__ rows, const int* __restrict__ order,
                                         const int* __restrict__ seg_off, __nv_bfloat16* __restrict__ hi,
-                                        __nv_bfloat16* __restrict__ lo, long long nseg, int c) {
+                                        __nv_bfloat16* __restrict__ lo, float* __restrict__ out_f32, long long nseg,
+                                        int c) {
   const int lane = threadIdx.x & 31;
   const long long seg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (seg >= nseg) return;
   const int r0 = seg_off[seg], r1 = seg_off[seg + 1];
   const int cq = c >> 2;
-  uint2* oh = reinterpret_cast<uint2*>(hi + seg * c);
+  uint2* oh = hi ? reinterpret_cast<uint2*>(hi + seg * c) : nullptr;
   uint2* ol = lo ? reinterpret_cast<uint2*>(lo + seg * c) : nullptr;
+  float4* of = out_f32 ? reinterpret_cast<float4*>(out_f32 + seg * c) : nullptr;
   for (int i = lane; i < cq; i += 32) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r = r0; r < r1; ++r) {
       const float4 v = __ldg(reinterpret_cast<const float4*>(rows + (long long)order[r] * c) + i);
       acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
     }
-    uint2 h, l;
-    gx_split4(acc, h, l);
-    oh[i] = h;
-    if (ol) ol[i] = l;
+    if (oh) {
+      uint2 h, l;
+      gx_split4(acc, h, l);
+      oh[i] = h;
+      if (ol) ol[i] = l;
+    }
+    if (of) of[i] = acc;
+  }
+}
+
+// Z[b,y,x,:] = sum_l P_l[b, y*h_l/H, x*w_l/W, :]  - the projection of the nearest-upsampled,
+// channel-concatenated feature vector is the sum of the per-level projections evaluated at
+// each level's native resolution (linearity), so the 11x redundant upsampled GEMM is never run.
+struct UpsumDesc {
+  int nlevels;
+  const float* p[GX_MAX_LEVELS];
+  int h[GX_MAX_LEVELS], w[GX_MAX_LEVELS];
+  int out_h, out_w, c;
+  long long npix;   // B*out_h*out_w
+};
+__global__ void upsample_sum_kernel(const UpsumDesc d, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (pix >= d.npix) return;
+  const int per = d.out_h * d.out_w;
+  const int b = (int)(pix / per);
+  const int r = (int)(pix - (long long)b * per);
+  const int y = r / d.out_w, x = r - y * d.out_w;
+  const int cq = d.c >> 2;
+  for (int c0 = 0; c0 < cq; c0 += 128) {        // 512 channels per sweep, 4 float4 per lane
+    float4 acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int l = 0; l < d.nlevels; ++l) {
+      const int ly = (y * d.h[l]) / d.out_h, lx = (x * d.w[l]) / d.out_w;
+      const float4* src =
+          reinterpret_cast<const float4*>(d.p[l] + (((long long)b * d.h[l] + ly) * d.w[l] + lx) * d.c) + c0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = lane + 32 * j;
+        if (c0 + i < cq) {
+          const float4 v = __ldg(src + i);
+          acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w;
+        }
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = lane + 32 * j;
+      if (c0 + i < cq) gx_stg_stream(reinterpret_cast<float4*>(out + pix * d.c) + c0 + i, acc[j]);
+    }
+  }
+}
+
+// out[b,y,x,:] = sum of the f x f block of in (f = H/h): the adjoint of nearest upsampling; also
+// emitted as bf16 planes (operand of the per-level weight-gradient GEMM).  Warp per output pixel.
+__global__ void pool_sum_kernel(const float* __restrict__ in, int H, int W, int h, int w, int c, long long nout,
+                                float* __restrict__ out, __nv_bfloat16* __restrict__ hi,
+                                __nv_bfloat16* __restrict__ lo) {
+  const int lane = threadIdx.x & 31;
+  const long long o = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (o >= nout) return;
+  const long long per = (long long)h * w;
+  const int b = (int)(o / per);
+  const int r = (int)(o - (long long)b * per);
+  const int oy = r / w, ox = r - oy * w;
+  const int fy = H / h, fx = W / w;
+  const int cq = c >> 2;
+  for (int i = lane; i < cq; i += 32) {
+    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int dy = 0; dy < fy; ++dy)
+      for (int dx = 0; dx < fx; ++dx) {
+        const float4 v = __ldg(reinterpret_cast<const float4*>(
+                                   in + (((long long)b * H + oy * fy + dy) * W + ox * fx + dx) * c) + i);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    if (out) reinterpret_cast<float4*>(out + o * c)[i] = acc;
+    if (hi) {
+      uint2 hh, ll;
+      gx_split4(acc, hh, ll);
+      reinterpret_cast<uint2*>(hi + o * c)[i] = hh;
+      if (lo) reinterpret_cast<uint2*>(lo + o * c)[i] = ll;
+    }
   }
 }
 
@@ -209,15 +309,31 @@ __global__ void normalize_rows_kernel(float* __restrict__ w, long long rows, int
 // fp32 -> split planes (optionally transposed through a padded smem tile)
 // ---------------------------------------------------------------------------
 __global__ void split_planes_kernel(const float* __restrict__ x, long long ld, __nv_bfloat16* __restrict__ hi,
-                                    __nv_bfloat16* __restrict__ lo, long long rows, long long cols) {
+                                    __nv_bfloat16* __restrict__ lo, long long rows, long long cols, long long ldo) {
   const long long total = rows * cols;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const long long r = i / cols, c = i - r * cols;
     __nv_bfloat16 h, l;
     gx_split_bf16(x[r * ld + c], h, l);
-    hi[i] = h;
-    if (lo) lo[i] = l;
+    hi[r * ldo + c] = h;
+    if (lo) lo[r * ldo + c] = l;
+  }
+}
+
+// 4 columns per thread (all pitches and base addresses multiples of 4 elements)
+__global__ void split_planes_v4_kernel(const float* __restrict__ x, long long ld, __nv_bfloat16* __restrict__ hi,
+                                       __nv_bfloat16* __restrict__ lo, long long rows, int cq, long long ldo) {
+  const long long total = rows * cq;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const long long r = i / cq;
+    const int q = (int)(i - r * cq);
+    const float4 v = gx_ldg_stream(reinterpret_cast<const float4*>(x + r * ld) + q);
+    uint2 h, l;
+    gx_split4(v, h, l);
+    reinterpret_cast<uint2*>(hi + r * ldo)[q] = h;
+    if (lo) reinterpret_cast<uint2*>(lo + r * ldo)[q] = l;
   }
 }
 
@@ -261,30 +377,6 @@ __device__ __forceinline__ float ex2_fast(float x) {
   float y;
   asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
   return y;
-}
-// packed fp32x2 arithmetic (Blackwell FFMA2 / FADD2 / FMUL2): halves the FMA-pipe instruction count
-// of the streaming kernels, which are bound by instruction issue rather than by arithmetic
-__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c) {
-  float2 d;
-  asm("fma.rn.f32x2 %0, %1, %2, %3;"
-      : "=l"(reinterpret_cast<unsigned long long&>(d))
-      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)),
-        "l"(reinterpret_cast<unsigned long long&>(c)));
-  return d;
-}
-__device__ __forceinline__ float2 add2(float2 a, float2 b) {
-  float2 d;
-  asm("add.rn.f32x2 %0, %1, %2;"
-      : "=l"(reinterpret_cast<unsigned long long&>(d))
-      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
-  return d;
-}
-__device__ __forceinline__ float2 mul2(float2 a, float2 b) {
-  float2 d;
-  asm("mul.rn.f32x2 %0, %1, %2;"
-      : "=l"(reinterpret_cast<unsigned long long&>(d))
-      : "l"(reinterpret_cast<unsigned long long&>(a)), "l"(reinterpret_cast<unsigned long long&>(b)));
-  return d;
 }
 __device__ __forceinline__ float2 ex2_2(float2 a) { return make_float2(ex2_fast(a.x), ex2_fast(a.y)); }
 
@@ -857,11 +949,12 @@ extern "C" int gx_gather_rows(const gx_gather_desc* d, void* stream) {
   return GX_OK;
 }
 
-extern "C" int gx_l2norm_split(const float* z, const int* row_idx, void* zn_hi, void* zn_lo, float* inv_norm,
-                               long long n, int c, void* stream) {
+extern "C" int gx_l2norm_split(const float* z, const int* row_idx, void* zn_hi, void* zn_lo, void* zn_f16,
+                               float* inv_norm, long long n, int c, void* stream) {
   GX_CHECK_ARG(z && zn_hi && n > 0 && c % 4 == 0);
   l2norm_split_kernel<<<gx_cdiv(n, 8), 256, 0, (cudaStream_t)stream>>>(
-      z, row_idx, reinterpret_cast<__nv_bfloat16*>(zn_hi), reinterpret_cast<__nv_bfloat16*>(zn_lo), inv_norm, n, c);
+      z, row_idx, reinterpret_cast<__nv_bfloat16*>(zn_hi), reinterpret_cast<__nv_bfloat16*>(zn_lo),
+      reinterpret_cast<__half*>(zn_f16), inv_norm, n, c);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }
@@ -878,10 +971,41 @@ extern "C" int gx_l2norm_bwd_split(const float* dzn, const void* zn_hi, const vo
 }
 
 extern "C" int gx_segment_sum_rows(const float* rows, const int* order, const int* seg_off, void* hi, void* lo,
-                                   long long nseg, int c, void* stream) {
-  GX_CHECK_ARG(rows && order && seg_off && hi && nseg > 0 && c % 4 == 0);
+                                   float* out_f32, long long nseg, int c, void* stream) {
+  GX_CHECK_ARG(rows && order && seg_off && (hi || out_f32) && nseg > 0 && c % 4 == 0);
+  GX_CHECK_ARG(lo == nullptr || hi != nullptr);
   segment_sum_rows_kernel<<<gx_cdiv(nseg, 8), 256, 0, (cudaStream_t)stream>>>(
-      rows, order, seg_off, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), nseg, c);
+      rows, order, seg_off, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), out_f32, nseg,
+      c);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_upsample_sum(int nlevels, const float* const* p, const int* h, const int* w, int batch, int out_h,
+                               int out_w, int c, float* out, void* stream) {
+  GX_CHECK_ARG(nlevels > 0 && nlevels <= GX_MAX_LEVELS && p && h && w && out && batch > 0 && c % 4 == 0);
+  UpsumDesc d;
+  d.nlevels = nlevels;
+  for (int l = 0; l < nlevels; ++l) {
+    GX_CHECK_ARG(p[l] && h[l] > 0 && w[l] > 0);
+    d.p[l] = p[l]; d.h[l] = h[l]; d.w[l] = w[l];
+  }
+  d.out_h = out_h; d.out_w = out_w; d.c = c;
+  d.npix = (long long)batch * out_h * out_w;
+  upsample_sum_kernel<<<gx_cdiv(d.npix, 8), 256, 0, (cudaStream_t)stream>>>(d, out);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_pool_sum(const float* in, int batch, int in_h, int in_w, int out_h, int out_w, int c, float* out,
+                           void* hi, void* lo, void* stream) {
+  GX_CHECK_ARG(in && (out || hi) && batch > 0 && c % 4 == 0 && out_h > 0 && out_w > 0);
+  GX_CHECK_ARG(in_h % out_h == 0 && in_w % out_w == 0);
+  GX_CHECK_ARG(lo == nullptr || hi != nullptr);
+  const long long nout = (long long)batch * out_h * out_w;
+  pool_sum_kernel<<<gx_cdiv(nout, 8), 256, 0, (cudaStream_t)stream>>>(
+      in, in_h, in_w, out_h, out_w, c, nout, out, reinterpret_cast<__nv_bfloat16*>(hi),
+      reinterpret_cast<__nv_bfloat16*>(lo));
   GX_LAUNCH_CHECK();
   return GX_OK;
 }
@@ -894,20 +1018,42 @@ extern "C" int gx_normalize_rows(float* w, long long rows, int cols, void* strea
 }
 
 extern "C" int gx_split_planes(const float* x, long long ld, void* hi, void* lo, long long rows, long long cols,
-                               int transpose, void* stream) {
+                               int transpose, long long ld_out, void* stream) {
   GX_CHECK_ARG(x && hi && rows > 0 && cols > 0 && ld >= cols);
+  if (ld_out <= 0) ld_out = transpose ? rows : cols;
   if (!transpose) {
-    int grid = gx_cdiv(rows * cols, 256);
+    GX_CHECK_ARG(ld_out >= cols);
+    const bool v4 = cols % 4 == 0 && ld % 4 == 0 && ld_out % 4 == 0 && ((uintptr_t)x & 15) == 0 &&
+                    ((uintptr_t)hi & 7) == 0 && ((uintptr_t)lo & 7) == 0;
+    const long long work = v4 ? rows * (cols / 4) : rows * cols;
+    int grid = gx_cdiv(work, 256);
     const int cap = gx_sm_count() * 16;
     if (grid > cap) grid = cap;
-    split_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ld, reinterpret_cast<__nv_bfloat16*>(hi),
-                                                               reinterpret_cast<__nv_bfloat16*>(lo), rows, cols);
+    if (v4)
+      split_planes_v4_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(
+          x, ld, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), rows, (int)(cols / 4),
+          ld_out);
+    else
+      split_planes_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ld, reinterpret_cast<__nv_bfloat16*>(hi),
+                                                                 reinterpret_cast<__nv_bfloat16*>(lo), rows, cols,
+                                                                 ld_out);
   } else {
+    GX_CHECK_ARG(ld_out == rows);
     dim3 grid(gx_cdiv(cols, 32), gx_cdiv(rows, 32));
     GX_CHECK_ARG(grid.y <= 65535);
     split_planes_t_kernel<<<grid, dim3(32, 8), 0, (cudaStream_t)stream>>>(
         x, ld, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), rows, cols);
   }
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_round_f16(const float* x, long long ld, void* out, long long rows, long long cols, void* stream) {
+  GX_CHECK_ARG(x && out && rows > 0 && cols > 0 && ld >= cols);
+  int grid = gx_cdiv(rows * cols, 256);
+  const int cap = gx_sm_count() * 16;
+  if (grid > cap) grid = cap;
+  round_f16_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ld, reinterpret_cast<__half*>(out), rows, cols);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }

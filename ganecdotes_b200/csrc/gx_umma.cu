@@ -43,6 +43,9 @@ struct UmmaParams {
   int mtiles;      // 128-row sub-tiles per CTA tile (2 = 256-row tiles, halves B traffic per FLOP)
   int acc_stages;  // TMEM accumulator ring depth (2 when mtiles*block_n <= 256)
   int a_mn, b_mn;
+  int f16;         // operand planes are fp16 (single-pass only) instead of bf16
+  int pair;        // gemm: 2-CTA clusters on adjacent m-tiles of one n-tile; each CTA loads half of the
+                   // B tile and multicasts it to both (halves the L2 -> SM operand traffic of B)
   // ---- gemm
   int M, N, K;
   int tiles_m, tiles_n, split_k, kiters_total;
@@ -80,13 +83,14 @@ struct TileInfo {
   int phase, b0, y0, x0;
 };
 
-__device__ __forceinline__ TileInfo decode_tile(const UmmaParams& p, int w) {
+__device__ __forceinline__ TileInfo decode_tile(const UmmaParams& p, int w, int rank = 0) {
   TileInfo t;
-  const int tiles_mn = p.tiles_m * p.tiles_n;
+  const int tiles_m_units = p.pair ? (p.tiles_m + 1) >> 1 : p.tiles_m;
+  const int tiles_mn = tiles_m_units * p.tiles_n;
   const int split = w / tiles_mn;
   const int tmn = w - split * tiles_mn;
   const int tile_n = tmn % p.tiles_n;
-  const int tile_m = tmn / p.tiles_n;
+  const int tile_m = p.pair ? 2 * (tmn / p.tiles_n) + rank : tmn / p.tiles_n;
   t.n0 = tile_n * p.block_n;
   t.m0 = tile_m * BM * p.mtiles;
   t.phase = 0; t.b0 = 0; t.y0 = 0; t.x0 = 0;
@@ -112,8 +116,93 @@ __device__ __forceinline__ TileInfo decode_tile(const UmmaParams& p, int w) {
   return t;
 }
 
+__device__ __forceinline__ float ex2_approx(float x) {
+  float y;
+  asm("ex2.approx.ftz.f32 %0, %1;" : "=f"(y) : "f"(x));
+  return y;
+}
+
 __device__ __forceinline__ float lrelu_sqrt2(float v) {
   return (v > 0.f ? v : v * 0.2f) * 1.41421356237309515f;
+}
+
+// Epilogue of one 32x32 accumulator chunk of a warp (thread = row on entry).  Staging tile of 32 rows x
+// 8 16-byte pieces, piece j of row r at physical piece j ^ (r & 7): conflict-free both for the row owner's
+// 128-bit writes and for the reads, after which 8 lanes hold one row (4 columns per lane) so that every
+// 128-bit global store of the warp covers four contiguous 128 B row segments.
+template <bool COLEXP, bool ATOMIC>
+__device__ __forceinline__ void epi_chunk_vec(const uint32_t (&r)[32], uint32_t stg, int lane, float* cptr,
+                                              long long rstep, const float* bias4, int rows_valid, float colexp_scale,
+                                              float* colsum4, bool do_store) {
+  {
+    const uint32_t wa = stg + (uint32_t)(lane * 128);
+    const uint32_t sw = (uint32_t)(lane & 7);
+#pragma unroll
+    for (int j = 0; j < 8; ++j)
+      asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(wa + ((j ^ sw) << 4)), "r"(r[4 * j]),
+                   "r"(r[4 * j + 1]), "r"(r[4 * j + 2]), "r"(r[4 * j + 3])
+                   : "memory");
+  }
+  __syncwarp();
+  const int lr = lane >> 3;
+  float2 v[8][2];
+  {
+    // row 4g + lr: (row & 7) = (4g + lr) & 7 alternates between lr and lr + 4
+    const uint32_t ra = stg + (uint32_t)(lr * 128);
+    const uint32_t p0 = (uint32_t)(((lane & 7) ^ lr) << 4), p1 = (uint32_t)(((lane & 7) ^ (lr + 4)) << 4);
+#pragma unroll
+    for (int g = 0; g < 8; ++g)
+      asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];"
+                   : "=f"(v[g][0].x), "=f"(v[g][0].y), "=f"(v[g][1].x), "=f"(v[g][1].y)
+                   : "r"(ra + (uint32_t)(g * 512) + ((g & 1) ? p1 : p0))
+                   : "memory");
+  }
+  __syncwarp();   // the tile may be overwritten from here on; the rest works from registers
+  if (bias4 != nullptr) {
+    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias4));
+    const float2 b0 = make_float2(bv.x, bv.y), b1 = make_float2(bv.z, bv.w);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      v[g][0] = add2(v[g][0], b0);
+      v[g][1] = add2(v[g][1], b1);
+    }
+  }
+  const bool full = rows_valid == 32;   // warp-uniform
+  if (do_store) {
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (full || 4 * g + lr < rows_valid) {
+        if (ATOMIC)
+          asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(cptr), "f"(v[g][0].x), "f"(v[g][0].y),
+                       "f"(v[g][1].x), "f"(v[g][1].y)
+                       : "memory");
+        else
+          *reinterpret_cast<float4*>(cptr) = make_float4(v[g][0].x, v[g][0].y, v[g][1].x, v[g][1].y);
+      }
+      cptr += rstep;
+    }
+  }
+  if (COLEXP) {
+    const float2 sc = make_float2(colexp_scale, colexp_scale);
+    float2 e0 = make_float2(0.f, 0.f), e1 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int g = 0; g < 8; ++g) {
+      if (full || 4 * g + lr < rows_valid) {
+        const float2 t0 = mul2(v[g][0], sc), t1 = mul2(v[g][1], sc);
+        e0 = add2(e0, make_float2(ex2_approx(t0.x), ex2_approx(t0.y)));
+        e1 = add2(e1, make_float2(ex2_approx(t1.x), ex2_approx(t1.y)));
+      }
+    }
+    // fold the 4 row groups, then one vector reduction per column quad
+    e0.x += __shfl_xor_sync(0xffffffffu, e0.x, 8);  e0.y += __shfl_xor_sync(0xffffffffu, e0.y, 8);
+    e1.x += __shfl_xor_sync(0xffffffffu, e1.x, 8);  e1.y += __shfl_xor_sync(0xffffffffu, e1.y, 8);
+    e0.x += __shfl_xor_sync(0xffffffffu, e0.x, 16); e0.y += __shfl_xor_sync(0xffffffffu, e0.y, 16);
+    e1.x += __shfl_xor_sync(0xffffffffu, e1.x, 16); e1.y += __shfl_xor_sync(0xffffffffu, e1.y, 16);
+    if (lr == 0 && colsum4 != nullptr)
+      asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(colsum4), "f"(e0.x), "f"(e0.y), "f"(e1.x),
+                   "f"(e1.y)
+                   : "memory");
+  }
 }
 
 __global__ void __launch_bounds__(NTHREADS, 1)
@@ -137,6 +226,9 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
+  const int crank = p.pair ? (int)cluster_ctarank() : 0;
+  const int w_first = p.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int w_step = p.pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a_hi);
@@ -149,7 +241,7 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], 1);
+      mbar_init(&empty_bar[i], p.pair ? 2 : 1);   // pair: both CTAs' MMAs must have retired
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
@@ -163,6 +255,7 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
   }
   tc_fence_before();
   __syncthreads();
+  if (p.pair) cluster_sync_all();   // the peer's barriers are initialised before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -172,8 +265,8 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
       int stage = 0;
       uint32_t phase = 0;
       const int cblocks = (p.mode == 1) ? p.Cin / BK : 1;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x) {
-        const TileInfo t = decode_tile(p, w);
+      for (int w = w_first; w < total_work; w += w_step) {
+        const TileInfo t = decode_tile(p, w, crank);
         for (int kit = t.kbeg; kit < t.kend; ++kit) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
@@ -193,7 +286,11 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
                 for (int i = 0; i < 2 * p.mtiles; ++i)
                   tma_load_2d(da + i * 8192, ma, &full_bar[stage], t.m0 + i * 64, k0);
               }
-              if (!p.b_mn) {
+              if (p.pair) {
+                const int half_rows = p.block_n >> 1;
+                tma_load_2d_mc(db + crank * half_rows * (BK * 2), mb, &full_bar[stage], k0,
+                               t.n0 + crank * half_rows, (uint16_t)3);
+              } else if (!p.b_mn) {
                 tma_load_2d(db, mb, &full_bar[stage], k0, t.n0);
               } else {
                 for (int i = 0; i < p.block_n / 64; ++i)
@@ -217,12 +314,12 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t idesc = make_idesc_bf16(BM, p.block_n, p.a_mn, p.b_mn);
+      const uint32_t idesc = make_idesc_bf16(BM, p.block_n, p.a_mn, p.b_mn, p.f16);
       const uint32_t a_lbo = p.a_mn ? 8192u : 0u, b_lbo = p.b_mn ? 8192u : 0u;
       const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
       int it = 0;
-      for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
-        const TileInfo t = decode_tile(p, w);
+      for (int w = w_first; w < total_work; w += w_step, ++it) {
+        const TileInfo t = decode_tile(p, w, crank);
         const int acc = it % p.acc_stages;
         const uint32_t acc_phase = (it / p.acc_stages) & 1;
         mbar_wait(&tempty_bar[acc], acc_phase ^ 1);
@@ -250,7 +347,9 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
               accumulate = 1;
             }
           }
-          umma_commit(&empty_bar[stage]);  // frees the smem slot when these MMAs retire
+          // frees the smem slot when these MMAs retire (pair: in both CTAs, whose producers write into it)
+          if (p.pair) umma_commit_mc(&empty_bar[stage], (uint16_t)3);
+          else umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
         umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
@@ -262,8 +361,8 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
     const int ehalf = (warp - 4) >> 2;  // which half of the chunks this warp handles
     const int row = q * 32 + lane;      // tile row == TMEM lane
     int it = 0;
-    for (int w = blockIdx.x; w < total_work; w += gridDim.x, ++it) {
-      const TileInfo t = decode_tile(p, w);
+    for (int w = w_first; w < total_work; w += w_step, ++it) {
+      const TileInfo t = decode_tile(p, w, crank);
       const int acc = it % p.acc_stages;
       const uint32_t acc_phase = (it / p.acc_stages) & 1;
       mbar_wait(&tfull_bar[acc], acc_phase);
@@ -277,7 +376,7 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
         // contiguous 128 B row segments.
         const uint32_t stg = smem_u32(staging) + (uint32_t)((warp - 4) * (32 * 33 * 4));
         const bool add_bias = p.bias != nullptr && (!p.atomic || t.kbeg == 0);
-        const bool vec_ok = !p.atomic && ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
+        const bool vec_ok = ((p.ldc & 3) == 0) && ((reinterpret_cast<uintptr_t>(p.c) & 15) == 0);
         const int lr = lane >> 3, lc = (lane & 7) * 4;   // vector path: row-in-group, first column
         for (int sub = 0; sub < p.mtiles; ++sub) {
           const long long mrow0 = (long long)t.m0 + sub * BM + q * 32;   // first row of this warp
@@ -290,48 +389,26 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
             tmem_ld_32x32(taddr0 + sub * p.block_n + ch * 32, r);
             tmem_ld_wait();
             if (p.debug & 2) continue;
-            {
-              const uint32_t wa = stg + (uint32_t)(lane * 33 * 4);
-#pragma unroll
-              for (int i = 0; i < 32; ++i)
-                asm volatile("st.shared.b32 [%0], %1;" ::"r"(wa + i * 4), "r"(r[i]) : "memory");
-            }
-            __syncwarp();
             if (vec_ok && n_base + 32 <= p.N) {
-              float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
-              if (add_bias) bv = __ldg(reinterpret_cast<const float4*>(p.bias + n_base + lc));
               float* cptr = p.c + (mrow0 + lr) * p.ldc + n_base + lc;
-              const uint32_t ra = stg + (uint32_t)((lr * 33 + lc) * 4);
-              const long long rstep = 4 * p.ldc;
-              float4 es = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll
-              for (int g = 0; g < 8; ++g) {      // rows 4g + lr
-                float4 v;
-                asm volatile("ld.shared.f32 %0, [%4];\n\tld.shared.f32 %1, [%4+4];\n\t"
-                             "ld.shared.f32 %2, [%4+8];\n\tld.shared.f32 %3, [%4+12];"
-                             : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w)
-                             : "r"(ra + (uint32_t)(g * 4 * 33 * 4)));
-                v.x += bv.x; v.y += bv.y; v.z += bv.z; v.w += bv.w;
-                if (4 * g + lr < rows_valid) {
-                  if (!(p.debug & 1)) *reinterpret_cast<float4*>(cptr) = v;
-                  if (p.colexp_sum != nullptr) {
-                    es.x += exp2f(v.x * p.colexp_scale); es.y += exp2f(v.y * p.colexp_scale);
-                    es.z += exp2f(v.z * p.colexp_scale); es.w += exp2f(v.w * p.colexp_scale);
-                  }
-                }
-                cptr += rstep;
-              }
-              if (p.colexp_sum != nullptr) {     // fold the 4 row groups, then one atomic per column
-                es.x += __shfl_xor_sync(0xffffffffu, es.x, 8);  es.y += __shfl_xor_sync(0xffffffffu, es.y, 8);
-                es.z += __shfl_xor_sync(0xffffffffu, es.z, 8);  es.w += __shfl_xor_sync(0xffffffffu, es.w, 8);
-                es.x += __shfl_xor_sync(0xffffffffu, es.x, 16); es.y += __shfl_xor_sync(0xffffffffu, es.y, 16);
-                es.z += __shfl_xor_sync(0xffffffffu, es.z, 16); es.w += __shfl_xor_sync(0xffffffffu, es.w, 16);
-                if (lr == 0) {
-                  float* up = p.colexp_sum + n_base + lc;
-                  atomicAdd(up, es.x); atomicAdd(up + 1, es.y); atomicAdd(up + 2, es.z); atomicAdd(up + 3, es.w);
-                }
-              }
+              const float* bptr = add_bias ? p.bias + n_base + lc : nullptr;
+              float* uptr = (p.colexp_sum != nullptr && !(p.debug & 4)) ? p.colexp_sum + n_base + lc : nullptr;
+              if (p.colexp_sum != nullptr)
+                epi_chunk_vec<true, false>(r, stg, lane, cptr, 4 * p.ldc, bptr, rows_valid, p.colexp_scale, uptr,
+                                           !(p.debug & 1));
+              else if (p.atomic)
+                epi_chunk_vec<false, true>(r, stg, lane, cptr, 4 * p.ldc, bptr, rows_valid, 0.f, nullptr, true);
+              else
+                epi_chunk_vec<false, false>(r, stg, lane, cptr, 4 * p.ldc, bptr, rows_valid, 0.f, nullptr,
+                                            !(p.debug & 1));
             } else {
+              {
+                const uint32_t wa = stg + (uint32_t)(lane * 33 * 4);
+#pragma unroll
+                for (int i = 0; i < 32; ++i)
+                  asm volatile("st.shared.b32 [%0], %1;" ::"r"(wa + i * 4), "r"(r[i]) : "memory");
+              }
+              __syncwarp();
               const int n = n_base + lane;
               const bool nvalid = n < p.N;
               const float bv = (add_bias && nvalid) ? __ldg(p.bias + n) : 0.f;
@@ -344,7 +421,7 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
                 if (nvalid) {
                   if (p.atomic) atomicAdd(cptr, v + bv);
                   else cptr[0] = v + bv;
-                  if (p.colexp_sum != nullptr) es += exp2f((v + bv) * p.colexp_scale);
+                  if (p.colexp_sum != nullptr) es += ex2_approx((v + bv) * p.colexp_scale);
                 }
                 cptr += p.ldc;
               }
@@ -437,6 +514,7 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
 
   tc_fence_before();
   __syncthreads();
+  if (p.pair) cluster_sync_all();   // no CTA leaves while its peer can still signal its barriers
   if (warp == 2) {
     tc_fence_after();
     tmem_dealloc(tmem_base, TMEM_COLS);
@@ -515,6 +593,28 @@ int launch(const UmmaParams& p_in, const CUtensorMap* maps, int total_work, cuda
     attr_set = true;
   }
   int grid = gx_umma_cta_budget();
+  if (p.pair) {
+    // total_work counts PAIRS of tiles; one 2-CTA cluster per unit of work in flight
+    grid &= ~1;
+    if (grid > 2 * total_work) grid = 2 * total_work;
+    if (grid < 2) return GX_OK;
+    cudaLaunchConfig_t cfg;
+    memset(&cfg, 0, sizeof(cfg));
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(NTHREADS);
+    cfg.dynamicSmemBytes = smem_bytes;
+    cfg.stream = st;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeClusterDimension;
+    at[0].val.clusterDim.x = 2;
+    at[0].val.clusterDim.y = 1;
+    at[0].val.clusterDim.z = 1;
+    cfg.attrs = at;
+    cfg.numAttrs = 1;
+    GX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gx_umma_kernel, p, maps[0], maps[1], maps[2], maps[3], total_work));
+    GX_LAUNCH_CHECK();
+    return GX_OK;
+  }
   if (grid > total_work) grid = total_work;
   if (grid < 1) return GX_OK;
   gx_umma_kernel<<<grid, NTHREADS, smem_bytes, st>>>(p, maps[0], maps[1], maps[2], maps[3], total_work);
@@ -533,6 +633,8 @@ extern "C" int gx_gemm(const gx_gemm_desc* d, void* stream) {
   memset(&p, 0, sizeof(p));
   p.mode = 0;
   p.passes = d->passes;
+  p.f16 = d->ab_f16 ? 1 : 0;
+  GX_CHECK_ARG(!p.f16 || d->passes == 1);
   p.a_mn = d->a_mn_major ? 1 : 0;
   p.b_mn = d->b_mn_major ? 1 : 0;
   p.M = d->m; p.N = d->n; p.K = d->k;
@@ -542,7 +644,8 @@ extern "C" int gx_gemm(const gx_gemm_desc* d, void* stream) {
   p.block_n = bn;
   // 256-row tiles for single-pass GEMMs: one B tile in smem feeds two M=128 MMAs, which keeps the
   // smem fill rate (L2 -> SM) at the level of the 3-pass mode instead of 1.5x above it
-  p.mtiles = (p.passes == 1 && bn == 256 && d->m > BM && !d->force_m128) ? 2 : 1;
+  p.pair = (d->cluster_pair && !p.b_mn && d->m > BM) ? 1 : 0;
+  p.mtiles = (p.passes == 1 && bn == 256 && d->m > BM && !d->force_m128 && !p.pair) ? 2 : 1;
   p.acc_stages = (p.mtiles * bn <= 256) ? 2 : 1;
   p.stages = pick_stages(p.passes, bn, p.mtiles, d->stages);
   GX_CHECK_ARG(p.stages >= 2);
@@ -582,7 +685,7 @@ extern "C" int gx_gemm(const gx_gemm_desc* d, void* stream) {
     if (!p.b_mn) {
       unsigned long long dims[2] = {(unsigned long long)d->k, (unsigned long long)d->n};
       unsigned long long str[1] = {(unsigned long long)d->ldb};
-      unsigned box[2] = {BK, (unsigned)bn};
+      unsigned box[2] = {BK, (unsigned)(p.pair ? bn / 2 : bn)};
       rc = make_tmap(&maps[2 + pl], bptr[pl], 2, dims, str, box);
     } else {
       unsigned long long dims[2] = {(unsigned long long)d->n, (unsigned long long)d->k};
@@ -596,7 +699,7 @@ extern "C" int gx_gemm(const gx_gemm_desc* d, void* stream) {
     maps[1] = maps[0];
     maps[3] = maps[2];
   }
-  const int total = p.tiles_m * p.tiles_n * p.split_k;
+  const int total = (p.pair ? (p.tiles_m + 1) / 2 : p.tiles_m) * p.tiles_n * p.split_k;
   return launch(p, maps, total, (cudaStream_t)stream);
 }
 
@@ -718,14 +821,16 @@ extern "C" int gx_modconv(const gx_conv_desc* d, void* stream) {
 // fp32 SIMT cross-check GEMM on the same planes (tests only)
 // --------------------------------------------------------------------------
 namespace {
-__device__ __forceinline__ float plane_val(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long idx) {
+__device__ __forceinline__ float plane_val(const __nv_bfloat16* hi, const __nv_bfloat16* lo, long long idx,
+                                           int f16 = 0) {
+  if (f16) return __half2float(reinterpret_cast<const __half*>(hi)[idx]);
   float v = __bfloat162float(hi[idx]);
   if (lo) v += __bfloat162float(lo[idx]);
   return v;
 }
 __global__ void gemm_check_kernel(const __nv_bfloat16* ah, const __nv_bfloat16* al, const __nv_bfloat16* bh,
                                   const __nv_bfloat16* bl, long long lda, long long ldb, int a_mn, int b_mn, int M,
-                                  int N, int K, float* c, long long ldc, const float* bias) {
+                                  int N, int K, float* c, long long ldc, const float* bias, int f16) {
   const int n = blockIdx.x * blockDim.x + threadIdx.x;
   const int m = blockIdx.y;
   if (n >= N || m >= M) return;
@@ -733,7 +838,7 @@ __global__ void gemm_check_kernel(const __nv_bfloat16* ah, const __nv_bfloat16* 
   for (int k = 0; k < K; ++k) {
     const long long ia = a_mn ? (long long)k * lda + m : (long long)m * lda + k;
     const long long ib = b_mn ? (long long)k * ldb + n : (long long)n * ldb + k;
-    acc = fmaf(plane_val(ah, al, ia), plane_val(bh, bl, ib), acc);
+    acc = fmaf(plane_val(ah, al, ia, f16), plane_val(bh, bl, ib, f16), acc);
   }
   if (bias) acc += bias[n];
   c[(long long)m * ldc + n] = acc;
@@ -746,7 +851,7 @@ extern "C" int gx_gemm_check(const gx_gemm_desc* d, void* stream) {
   gemm_check_kernel<<<grid, 128, 0, (cudaStream_t)stream>>>(
       (const __nv_bfloat16*)d->a_hi, d->passes == 3 ? (const __nv_bfloat16*)d->a_lo : nullptr,
       (const __nv_bfloat16*)d->b_hi, d->passes == 3 ? (const __nv_bfloat16*)d->b_lo : nullptr, d->lda, d->ldb,
-      d->a_mn_major, d->b_mn_major, d->m, d->n, d->k, d->c, d->ldc, d->bias);
+      d->a_mn_major, d->b_mn_major, d->m, d->n, d->k, d->c, d->ldc, d->bias, d->ab_f16);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }

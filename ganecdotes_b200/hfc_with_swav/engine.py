@@ -133,10 +133,13 @@ class SwavHead:
     their bf16 operand planes, gradients and LARC/SGD state.  Operates IN PLACE on the
     parameters of the nn.Modules the caller saves (ref :504-505)."""
 
-    def __init__(self, w_proj, w_proto, b_proto, lr, momentum, trust, passes_fwd=3, passes_bwd=1):
+    def __init__(self, w_proj, w_proto, b_proto, lr, momentum, trust, passes_fwd=3, passes_bwd=1, proto_f16=False):
         self.w_proj, self.w_proto, self.b_proto = w_proj, w_proto, b_proto
         self.lr, self.momentum, self.trust = lr, momentum, trust
         self.passes_fwd, self.passes_bwd = passes_fwd, passes_bwd
+        # score GEMM on single fp16 planes: both operands are unit-norm rows, so fp16 (11-bit significand,
+        # no range problem) gives |dS| ~ 1e-5; the default is the fp32-grade 3-plane bf16 split (|dS| ~ 1e-6)
+        self.proto_f16 = bool(proto_f16)
         dev = w_proj.device
         self.g_proj = torch.zeros_like(w_proj)
         self.g_proto = torch.zeros_like(w_proto)
@@ -163,7 +166,10 @@ class SwavHead:
     def refresh_planes(self, need_bwd=True):
         want_lo = self.passes_fwd == 3
         self.wp_hi, self.wp_lo = L.split_planes(self.w_proj, want_lo=want_lo)
-        self.wk_hi, self.wk_lo = L.split_planes(self.w_proto, want_lo=want_lo)
+        if self.proto_f16:
+            self.wk_f16 = L.round_f16(self.w_proto)
+        else:
+            self.wk_hi, self.wk_lo = L.split_planes(self.w_proto, want_lo=want_lo)
         if need_bwd:
             self.wkT_hi, self.wkT_lo = L.split_planes(self.w_proto, transpose=True, want_lo=self.passes_bwd == 3)
         self.planes_ready = True
@@ -197,9 +203,24 @@ def _proto_scores(head: SwavHead, zn_hi, zn_lo, n, eps):
     if eps is not None:
         u0 = torch.zeros(head.k, dtype=torch.float32, device=zn_hi.device)
         colexp = (u0, LOG2E / eps)
-    s = L.gemm(zn_hi, zn_lo if head.passes_fwd == 3 else None, head.wk_hi, head.wk_lo, n, head.k, head.c,
-               head.passes_fwd, bias=head.b_proto, tag="gemm_prototype_fwd", colexp=colexp)
+    if head.proto_f16:     # zn_hi is the fp16 plane here (see scores_forward*)
+        # 128-row tiles: two accumulator stages in TMEM, so the (store-heavy) epilogue overlaps the next tile
+        s = L.gemm(zn_hi, None, head.wk_f16, None, n, head.k, head.c, 1, bias=head.b_proto,
+                   tag="gemm_prototype_fwd", colexp=colexp, force_m128=True)
+    else:
+        s = L.gemm(zn_hi, zn_lo if head.passes_fwd == 3 else None, head.wk_hi, head.wk_lo, n, head.k, head.c,
+                   head.passes_fwd, bias=head.b_proto, tag="gemm_prototype_fwd", colexp=colexp)
     return s, u0
+
+
+def _normalise(head: SwavHead, z, row_idx=None):
+    """(zn_hi, zn_lo, inv_norm, operand of the score GEMM)"""
+    lo = head.passes_fwd == 3 and not head.proto_f16
+    if head.proto_f16:
+        zn_hi, zn_lo, inv, zf = L.l2norm_split(z, want_lo=True, row_idx=row_idx, want_f16=True)
+        return zn_hi, zn_lo, inv, zf
+    zn_hi, zn_lo, inv = L.l2norm_split(z, want_lo=lo or head.passes_bwd == 3, row_idx=row_idx)
+    return zn_hi, zn_lo, inv, zn_hi
 
 
 def scores_forward(head: SwavHead, feats, out_h, out_w, hlen, row_img, row_src, nrows, eps=None):
@@ -210,8 +231,8 @@ def scores_forward(head: SwavHead, feats, out_h, out_w, hlen, row_img, row_src, 
     lo = head.passes_fwd == 3
     a_hi, a_lo, _ = L.gather_rows(feats, out_h, out_w, hlen, row_img, row_src, nrows, want_lo=lo)
     z = L.gemm(a_hi, a_lo, head.wp_hi, head.wp_lo, nrows, head.c, hlen, head.passes_fwd, tag="gemm_projection_fwd")
-    zn_hi, zn_lo, inv = L.l2norm_split(z, want_lo=lo or head.passes_bwd == 3)
-    s, u0 = _proto_scores(head, zn_hi, zn_lo, nrows, eps)
+    zn_hi, zn_lo, inv, za = _normalise(head, z)
+    s, u0 = _proto_scores(head, za, zn_lo, nrows, eps)
     return dict(a_hi=a_hi, a_lo=a_lo, zn_hi=zn_hi, zn_lo=zn_lo, inv=inv, s=s, n=nrows, u0=u0)
 
 
@@ -244,8 +265,8 @@ def scores_forward_dedup(head: SwavHead, z_all, row_idx, eps=None):
     normalise the patch's rows of Z, prototype scores."""
     lo = head.passes_fwd == 3
     n = row_idx.numel()
-    zn_hi, zn_lo, inv = L.l2norm_split(z_all, want_lo=lo or head.passes_bwd == 3, row_idx=row_idx)
-    s, u0 = _proto_scores(head, zn_hi, zn_lo, n, eps)
+    zn_hi, zn_lo, inv, za = _normalise(head, z_all, row_idx)
+    s, u0 = _proto_scores(head, za, zn_lo, n, eps)
     return dict(zn_hi=zn_hi, zn_lo=zn_lo, inv=inv, s=s, n=n, u0=u0)
 
 
@@ -272,15 +293,79 @@ def scores_backward(head: SwavHead, fw, ds_hi, ds_lo, dz_rows_out=None):
            b_mn=True, split_k=sk2, accumulate=True, tag="gemm_gproj_bwd")
 
 
-def project_backward_dedup(head: SwavHead, dz_rows, order, seg_off, a_hi, a_lo, npix):
-    """gWp += dZ_pix^T A_pix with dZ_pix[pixel] = sum of the dZ rows of all samples of that pixel."""
+def resolution_groups(feats, hlen):
+    """Consecutive feature maps of equal resolution, cut at `hlen` channels of the concatenated
+    per-pixel vector (ref :108-130): [dict(maps, h, w, off, keep)]."""
+    groups, off = [], 0
+    for f in feats:
+        if off >= hlen:
+            break
+        h, w, c = f.shape[1], f.shape[2], f.shape[3]
+        keep = min(c, hlen - off)
+        if groups and groups[-1]["h"] == h and groups[-1]["w"] == w:
+            groups[-1]["maps"].append(f)
+            groups[-1]["keep"] += keep
+        else:
+            groups.append(dict(maps=[f], h=h, w=w, off=off, keep=keep))
+        off += keep
+    return groups
+
+
+def project_all_pixels(wp_hi, wp_lo, feats, batch, out_h, out_w, hlen, passes, want_hi_only_planes=False, out=None):
+    """Z[pixel] = Wp . (nearest-upsampled, concatenated feature vector of the pixel) for EVERY
+    pixel of `batch` images.  Upsampling and projection are both linear, so
+    Z = sum_r upsample(F_r Wp[:, cols_r]^T): each resolution is projected at its native size
+    (11x fewer flops than projecting the upsampled vectors for the ffhq pyramid) and the
+    partial maps are summed per pixel.  Returns (Z fp32 [batch*H*W, C], levels) where each
+    level keeps the bf16 planes of F_r for the weight-gradient GEMM."""
+    c = wp_hi.shape[0]
+    levels, parts = [], []
+    for g in resolution_groups(feats, hlen):
+        n = batch * g["h"] * g["w"]
+        a_hi = torch.empty((n, g["keep"]), dtype=torch.bfloat16, device=wp_hi.device)
+        a_lo = torch.empty_like(a_hi) if passes == 3 else None
+        col = 0
+        for f in g["maps"]:                       # K-concatenate the maps of this resolution
+            cw = min(f.shape[3], g["keep"] - col)
+            L.split_planes(f.view(n, f.shape[3])[:, :cw],
+                           out=(a_hi[:, col:col + cw], a_lo[:, col:col + cw] if a_lo is not None else None))
+            col += cw
+        sl = slice(g["off"], g["off"] + g["keep"])
+        p = L.gemm(a_hi, a_lo, wp_hi[:, sl], wp_lo[:, sl] if wp_lo is not None else None, n, c, g["keep"], passes,
+                   tag="gemm_projection_fwd")
+        parts.append(p.view(batch, g["h"], g["w"], c))
+        levels.append(dict(a_hi=a_hi, a_lo=None if want_hi_only_planes else a_lo, h=g["h"], w=g["w"], off=g["off"],
+                           keep=g["keep"]))
+    if len(parts) == 1 and parts[0].shape[1] == out_h and parts[0].shape[2] == out_w and out is None:
+        return parts[0].view(-1, c), levels
+    z = L.upsample_sum(parts, batch, out_h, out_w, out=out)
+    return z, levels
+
+
+def project_backward_dedup(head: SwavHead, dz_rows, order, seg_off, levels, batch, out_h, out_w):
+    """gWp[:, cols_r] += pool_r(dZ_pix)^T F_r per resolution, with dZ_pix[pixel] = sum of the dZ rows
+    of all samples of that pixel and pool_r = block sums (the adjoint of nearest upsampling)."""
     pb = head.passes_bwd
-    dz_hi, dz_lo = L.segment_sum_rows(dz_rows, order, seg_off, npix, want_lo=pb == 3)
-    c, d = head.c, head.d
+    c = head.c
+    npix = batch * out_h * out_w
+    need_f32 = any(lv["h"] != out_h or lv["w"] != out_w for lv in levels)
+    need_planes = any(lv["h"] == out_h and lv["w"] == out_w for lv in levels)
+    hi, lo, f32 = L.segment_sum_rows(dz_rows, order, seg_off, npix, want_lo=pb == 3, want_planes=need_planes,
+                                     want_f32=need_f32)
+    cur = dict(h=out_h, w=out_w, f32=f32.view(batch, out_h, out_w, c) if f32 is not None else None, hi=hi, lo=lo)
     bm = 256 if pb == 1 else 128
-    sk = pick_split_k(math.ceil(c / bm) * math.ceil(d / 256), (npix + 63) // 64, L.load().gx_sinkhorn_max_parts())
-    L.gemm(dz_hi, dz_lo, a_hi, a_lo if pb == 3 else None, c, d, npix, pb, out=head.g_proj, a_mn=True, b_mn=True,
-           split_k=sk, accumulate=True, tag="gemm_gproj_bwd")
+    sms = L.load().gx_sinkhorn_max_parts()
+    order_lv = sorted(levels, key=lambda lv: -lv["h"] * lv["w"])
+    for i, lv in enumerate(order_lv):
+        if lv["h"] != cur["h"] or lv["w"] != cur["w"]:
+            more = any(o["h"] * o["w"] < lv["h"] * lv["w"] for o in order_lv[i + 1:])
+            f, hi, lo = L.pool_sum(cur["f32"], lv["h"], lv["w"], want_f32=more, want_planes=True, want_lo=pb == 3)
+            cur = dict(h=lv["h"], w=lv["w"], f32=f, hi=hi, lo=lo)
+        n = batch * lv["h"] * lv["w"]
+        sk = pick_split_k(math.ceil(c / bm) * math.ceil(lv["keep"] / 256), (n + 63) // 64, sms)
+        L.gemm(cur["hi"], cur["lo"], lv["a_hi"], lv["a_lo"] if pb == 3 else None, c, lv["keep"], n, pb,
+               out=head.g_proj[:, lv["off"]:lv["off"] + lv["keep"]], a_mn=True, b_mn=True, split_k=sk, accumulate=True,
+               tag="gemm_gproj_bwd")
 
 
 @dataclass
@@ -333,13 +418,14 @@ class StepInputs:
 
 
 def use_dedup(cfg: StepConfig, out_h, out_w) -> bool:
-    """The projection depends on the pixel, not on the patch: when the patches of a step sample
-    more rows than the image has pixels (ffhq: 5 x 20000 > 65536) it is cheaper to project every
-    pixel once and let the patches gather rows of Z."""
+    """The projection depends on the pixel, not on the patch, and the all-pixel projection runs
+    at each level's native resolution (`project_all_pixels`, ~11x cheaper per pixel than projecting
+    gathered rows for the ffhq pyramid): project every pixel once and let the patches gather rows
+    of Z unless the patches touch only a small fraction of the image."""
     if cfg.dedup is not None:
         return bool(cfg.dedup)
     n = cfg.patch_size if cfg.patch_size is not None else out_h * out_w
-    return cfg.num_patches * n > out_h * out_w
+    return 4 * cfg.num_patches * n > out_h * out_w
 
 
 def prepare_step_inputs(gen, draws: StepDraws, cfg: StepConfig, device) -> StepInputs:
@@ -430,12 +516,10 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
         _, f = gen.synthesize(wplus, None, need_image=cfg.need_image)
         feats[name] = f
         if dedup:
-            npix = b * out_h * out_w
-            a_hi, a_lo, _ = L.gather_rows(f, out_h, out_w, cfg.hlen, None, None, npix, want_lo=head.passes_fwd == 3)
-            z_all = L.gemm(a_hi, a_lo, head.wp_hi, head.wp_lo, npix, head.c, cfg.hlen, head.passes_fwd,
-                           tag="gemm_projection_fwd")
+            z_all, levels = project_all_pixels(head.wp_hi, head.wp_lo, f, b, out_h, out_w, cfg.hlen, head.passes_fwd,
+                                               want_hi_only_planes=head.passes_bwd != 3)
             dz_rows = torch.empty((cfg.num_patches * n_patch_rows, head.c), dtype=torch.float32, device=dev)
-            allpix[name] = dict(a_hi=a_hi, a_lo=a_lo, z=z_all, dz_rows=dz_rows, npix=npix)
+            allpix[name] = dict(levels=levels, z=z_all, dz_rows=dz_rows)
 
     n_local = b * (cfg.patch_size if cfg.patch_size is not None else out_h * out_w)
     n_total = n_local * world
@@ -470,8 +554,8 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
     if dedup:
         for name in ("s", "t"):
             ap = allpix[name]
-            project_backward_dedup(head, ap["dz_rows"], inp.dedup[name][1], inp.dedup[name][2], ap["a_hi"],
-                                   ap["a_lo"], ap["npix"])
+            project_backward_dedup(head, ap["dz_rows"], inp.dedup[name][1], inp.dedup[name][2], ap["levels"], b,
+                                   out_h, out_w)
     loss = loss_acc / (n_total * cfg.num_patches)
     if group is not None:
         for g in (head.g_proj, head.g_proto, head.g_bias):
@@ -511,10 +595,8 @@ def predict_codes(gen, w_proj, w, mean_latent, truncation, hlen, passes=3, image
     for i0 in range(0, b, images_per_chunk):
         i1 = min(b, i0 + images_per_chunk)
         sub = [f[i0:i1] for f in feats]
-        n = (i1 - i0) * h * wd
-        a_hi, a_lo, _ = L.gather_rows(sub, h, wd, hlen, None, None, n, want_lo=passes == 3)
         zc = z[i0 * h * wd: i1 * h * wd]
-        L.gemm(a_hi, a_lo, wp_hi, wp_lo, n, c, hlen, passes, out=zc, tag="gemm_projection_fwd")
+        project_all_pixels(wp_hi, wp_lo, sub, i1 - i0, h, wd, hlen, passes, out=zc)
         labels[i0 * h * wd: i1 * h * wd] = L.argmax_rows(zc)
     preds = z.view(b, h, wd, c).permute(0, 3, 1, 2)
     return preds, labels.view(b, h, wd)

@@ -78,6 +78,7 @@ class SwAVClustering(object):
         self.match_reference_rng = True
         self.passes_fwd = int(swav_args.get('passes_fwd', 3))
         self.passes_bwd = int(swav_args.get('passes_bwd', 1))
+        self.proto_f16 = bool(swav_args.get('proto_f16', False))
 
     # ------------------------------------------------------------------ helpers
     def _mean_latent(self, n):
@@ -243,7 +244,7 @@ class SwAVClustering(object):
         ta = self.swav_args['train_args']
         self._head = E.SwavHead(self.projection[0].weight.data, self.prototype.weight.data,
                                 self.prototype.bias.data, ta['lr'], ta.get('momentum', 0.0),
-                                self.swav_args['trust_coeff'], self.passes_fwd, self.passes_bwd)
+                                self.swav_args['trust_coeff'], self.passes_fwd, self.passes_bwd, self.proto_f16)
         self._sk_ws = L.SinkhornWorkspace(self.nprototypes, self.device)
         group = self._dist_group()
         world = group.world if group is not None else 1

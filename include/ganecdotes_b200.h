@@ -151,6 +151,10 @@ typedef struct gx_gemm_desc {
   float colexp_scale;
   int block_n;       /* 0 = auto                                                 */
   int stages;        /* 0 = auto                                                 */
+  int cluster_pair;  /* != 0 (K-major B only): 2-CTA clusters work on two adjacent 128-row tiles of one
+                        n-tile and share the B tile by TMA multicast (half the B traffic from L2) */
+  int ab_f16;        /* != 0: a_hi / b_hi are IEEE fp16 planes (passes must be 1): 11-bit significands
+                        for operands bounded by 1 (normalised rows), error ~8x below bf16  */
 } gx_gemm_desc;
 
 /* C = A * B^T (+ bias): projection / prototype / gradient GEMMs
@@ -161,10 +165,14 @@ int gx_gemm(const gx_gemm_desc* d, void* stream);
  * cross-check used by the tests, not used on the product path. */
 int gx_gemm_check(const gx_gemm_desc* d, void* stream);
 
-/* fp32 [rows,cols] (row stride ld) -> bf16 hi (+lo) planes, optionally transposed
- * ([cols,rows]).  lo may be NULL. */
+/* fp32 [rows,cols] (row stride ld) -> bf16 hi (+lo) planes with row pitch ld_out (0: dense),
+ * optionally transposed ([cols,rows], dense).  lo may be NULL.  With a pitch the planes of several
+ * maps are written side by side (the K-concatenated operand of one resolution). */
 int gx_split_planes(const float* x, long long ld, void* hi, void* lo, long long rows, long long cols,
-                    int transpose, void* stream);
+                    int transpose, long long ld_out, void* stream);
+
+/* fp32 [rows,cols] (row stride ld) -> one IEEE fp16 plane (dense), round to nearest even. */
+int gx_round_f16(const float* x, long long ld, void* out, long long rows, long long cols, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * Per-pixel feature vectors (ref: hfc_with_swav/swav_clustering.py:108-182)
@@ -195,9 +203,10 @@ int gx_gather_rows(const gx_gather_desc* d, void* stream);
 
 /* zn[r,:] = z[src,:] / max(||z[src,:]||,1e-12) as split planes, src = row_idx ? row_idx[r] : r
  * (row_idx[r] = -1: an all-zero input row -> zero output); inv_norm[n] kept for backward
- * (ref: F.normalize at swav_clustering.py:174).  z [*,c]; outputs have n rows. */
-int gx_l2norm_split(const float* z, const int* row_idx, void* zn_hi, void* zn_lo, float* inv_norm, long long n,
-                    int c, void* stream);
+ * (ref: F.normalize at swav_clustering.py:174).  z [*,c]; outputs have n rows.  zn_f16 (optional):
+ * the same rows rounded to one IEEE fp16 plane (operand of the single-pass fp16 score GEMM). */
+int gx_l2norm_split(const float* z, const int* row_idx, void* zn_hi, void* zn_lo, void* zn_f16, float* inv_norm,
+                    long long n, int c, void* stream);
 
 /* backward of the normalisation: dz = (dzn - zn*(zn.dzn)) * inv_norm, emitted as split planes
  * and / or fp32 rows (either output may be NULL). */
@@ -208,7 +217,18 @@ int gx_l2norm_bwd_split(const float* dzn, const void* zn_hi, const void* zn_lo, 
  * dZ rows of pixels that were sampled by several patches into one row per pixel (deterministic,
  * no atomics), so the projection-weight gradient GEMM runs over pixels, not samples. */
 int gx_segment_sum_rows(const float* rows, const int* order, const int* seg_off, void* hi, void* lo,
-                        long long nseg, int c, void* stream);
+                        float* out_f32, long long nseg, int c, void* stream);
+
+/* Z[b,y,x,:] = sum_l P_l[b, y*h_l/out_h, x*w_l/out_w, :] (fp32 NHWC, c channels).  By linearity the
+ * projection of the nearest-upsampled + concatenated per-pixel vector (ref swav_clustering.py:108-130,
+ * :171) is the sum of per-level projections computed at each level's native resolution. */
+int gx_upsample_sum(int nlevels, const float* const* p, const int* h, const int* w, int batch, int out_h,
+                    int out_w, int c, float* out, void* stream);
+
+/* out[b,y,x,:] = sum of the (in_h/out_h x in_w/out_w) block of `in` - the adjoint of nearest upsampling,
+ * used to fold dZ onto a level's native resolution; fp32 out and/or bf16 planes (any may be NULL). */
+int gx_pool_sum(const float* in, int batch, int in_h, int in_w, int out_h, int out_w, int c, float* out, void* hi,
+                void* lo, void* stream);
 
 /* prototype row normalisation in place + split planes (+ transposed planes for dZ),
  * ref: swav_clustering.py:328-331. w [k,c]. */

@@ -156,6 +156,36 @@ def test_gemm_fused_first_sinkhorn_marginal(L):
             torch.testing.assert_close(u, u2, rtol=2e-4, atol=0)
 
 
+@pytest.mark.parametrize("m,n,k,passes,f16", [
+    (1000, 5000, 512, 3, False),     # odd number of 128-row tiles (8): last pair full
+    (1100, 600, 512, 1, True),       # 9 m-tiles: the second CTA of the last pair has no rows
+    (130, 136, 64, 1, False),        # ragged n tail inside the second B half
+    (4096, 264, 200, 3, False),
+])
+def test_gemm_cluster_pair_multicast(L, m, n, k, passes, f16):
+    """2-CTA clusters sharing the B tile by TMA multicast give the same numbers as the 1-CTA kernel"""
+    torch.manual_seed(m + n)
+    a = torch.nn.functional.normalize(torch.randn(m, k, device="cuda"), dim=1)
+    b = torch.nn.functional.normalize(torch.randn(n, k, device="cuda"), dim=1)
+    bias = 0.02 * torch.randn(n, device="cuda")
+    if f16:
+        ah, al, bh, bl = a.half(), None, b.half(), None
+    else:
+        ah, al = planes(a)
+        bh, bl = planes(b)
+        if passes == 1:
+            al = bl = None
+    u1 = torch.zeros(n, device="cuda")
+    u2 = torch.zeros(n, device="cuda")
+    ref = L.gemm(ah, al, bh, bl, m, n, k, passes, bias=bias, force_m128=True, colexp=(u1, 20.0))
+    got = L.gemm(ah, al, bh, bl, m, n, k, passes, bias=bias, pair=True, colexp=(u2, 20.0))
+    assert torch.equal(ref, got)
+    torch.testing.assert_close(u1, u2, rtol=1e-5, atol=0)
+    for _ in range(3):     # repeated launches (barrier phases, cluster exit)
+        got = L.gemm(ah, al, bh, bl, m, n, k, passes, bias=bias, pair=True)
+    assert torch.equal(ref, got)
+
+
 def test_gemm_accumulate(L):
     torch.manual_seed(3)
     a = torch.randn(200, 96, device="cuda")
@@ -315,6 +345,64 @@ def test_gather_rows_vs_oracle(L):
     # all pixels in order (prediction path)
     a_hi, a_lo, a_f = L.gather_rows(nhwc, 16, 16, hlen, None, None, b * 256, want_f32=True)
     assert torch.equal(a_f.cpu(), hf.permute(0, 2, 3, 1).reshape(-1, hlen))
+
+
+def test_gemm_fp16_planes_and_l2norm_fp16_output(L):
+    torch.manual_seed(9)
+    n, k, c = 700, 300, 512
+    z = torch.randn(n, c).cuda()
+    w = torch.nn.functional.normalize(torch.randn(k, c), dim=1).cuda()
+    hi, lo, inv, zf = L.l2norm_split(z, want_lo=True, want_f16=True)
+    zn = torch.nn.functional.normalize(z, dim=1)
+    assert zf.dtype == torch.float16
+    torch.testing.assert_close(zf.float(), zn, rtol=5e-4, atol=1e-7)     # one fp16 rounding (2^-11)
+    wf = L.round_f16(w)
+    assert torch.equal(wf, w.half())
+    bias = torch.randn(k).cuda()
+    s = L.gemm(zf, None, wf, None, n, k, c, 1, bias=bias)
+    chk = L.gemm(zf, None, wf, None, n, k, c, 1, bias=bias, check=True)
+    torch.testing.assert_close(s, chk, rtol=0, atol=2e-6)                  # tensor-core vs SIMT on the same planes
+    ref = (zn.double() @ w.double().t() + bias.double()).float()
+    err = (s - ref).abs()
+    assert err.max().item() < 1e-4 and err.pow(2).mean().sqrt().item() < 2e-5, (err.max().item(),)
+
+
+def test_upsample_sum_and_pool_sum(L):
+    torch.manual_seed(3)
+    b, c = 2, 24
+    parts = [torch.randn(b, 4, 4, c), torch.randn(b, 8, 8, c), torch.randn(b, 16, 16, c)]
+    ref = sum(torch.nn.functional.interpolate(p.permute(0, 3, 1, 2), size=(16, 16), mode="nearest") for p in parts)
+    got = L.upsample_sum([p.cuda() for p in parts], b, 16, 16)
+    torch.testing.assert_close(got.view(b, 16, 16, c).cpu(), ref.permute(0, 2, 3, 1), rtol=1e-6, atol=1e-6)
+    x = torch.randn(b, 16, 16, c)
+    f, hi, lo = L.pool_sum(x.cuda(), 4, 4, want_lo=True)
+    pref = torch.nn.functional.avg_pool2d(x.permute(0, 3, 1, 2), 4).permute(0, 2, 3, 1) * 16
+    torch.testing.assert_close(f.cpu(), pref, rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close((hi.float() + lo.float()).view(b, 4, 4, c).cpu(), pref, rtol=2e-5, atol=1e-5)
+    # adjointness: <upsample(p), x> == <p, pool(x)>
+    p = parts[0]
+    up = torch.nn.functional.interpolate(p.permute(0, 3, 1, 2), size=(16, 16), mode="nearest").permute(0, 2, 3, 1)
+    torch.testing.assert_close((up * x).sum(), (p * f.cpu()).sum(), rtol=1e-4, atol=1e-3)
+
+
+@pytest.mark.parametrize("hlen,passes", [(32, 3), (24, 3), (32, 1)])
+def test_per_level_projection_equals_projection_of_upsampled_vectors(L, hlen, passes):
+    """Z = Wp . concat_l(upsample(F_l)) computed per resolution (engine.project_all_pixels) against the
+    oracle's upsample -> concat -> 1x1 conv (ref swav_clustering.py:108-130, :171)."""
+    from ganecdotes_b200.hfc_with_swav.engine import project_all_pixels
+    torch.manual_seed(5)
+    b, c = 3, 64
+    feats = [torch.randn(b, 8, 4, 4), torch.randn(b, 8, 8, 8), torch.randn(b, 8, 8, 8), torch.randn(b, 8, 16, 16)]
+    wp = torch.randn(c, hlen) / hlen ** 0.5
+    hf = O.pixel_feature_vectors(feats, hlen)                              # [b, hlen, 16, 16]
+    ref = torch.einsum("bdhw,cd->bhwc", hf.double(), wp.double()).reshape(-1, c).float()
+    nhwc = [f.permute(0, 2, 3, 1).contiguous().cuda() for f in feats]
+    wp_hi, wp_lo = L.split_planes(wp.cuda(), want_lo=passes == 3)
+    z, levels = project_all_pixels(wp_hi, wp_lo, nhwc, b, 16, 16, hlen, passes)
+    tol = 5e-5 if passes == 3 else 2e-2
+    torch.testing.assert_close(z.cpu(), ref, rtol=tol, atol=tol)
+    assert [lv["h"] for lv in levels] == [4, 8, 16][:len(levels)]
+    assert sum(lv["keep"] for lv in levels) == hlen
 
 
 def test_l2norm_fwd_bwd(L):

@@ -213,6 +213,32 @@ def test_batched_joint_step_matches_oracle(gen, dedup):
             torch.testing.assert_close(got.cpu(), exp, rtol=1e-4, atol=2e-6)
 
 
+def test_fp16_score_gemm_option(gen):
+    """proto_f16: the pixel x prototype scores from single fp16 planes (unit-norm operands, |dS| ~ 1e-5)
+    stay inside the tolerances of the default bf16x3 path on a joint-batch step."""
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    sd = O.init_generator_state(16, 64, 2, 7)
+    torch.manual_seed(0)
+    hlen, c, k, patch, npatch = 2560, 64, 48, 120, 2
+    wp = torch.randn(c, hlen) / hlen ** 0.5
+    wk = torch.randn(k, c)
+    bk = 0.05 * torch.randn(k)
+    mean_latent = O.style_mlp(sd, torch.randn(64, 64)).mean(0, keepdim=True)
+    pstd = [1.0, 0.5, 1.0]
+    head = E.SwavHead(wp.clone().cuda(), wk.clone().cuda(), bk.clone().cuda(), 0.01, 0.9, 0.01, 3, 1, proto_f16=True)
+    cfg = E.StepConfig(hlen=hlen, patch_size=patch, num_patches=npatch, niters=10, eps=0.02, temperature=0.02,
+                       truncation=0.7, perturb_std=pstd)
+    draws = make_draws(3, 64, 3, 256, npatch, 100)
+    ref = oracle_step(sd, mean_latent, draws, wp, wk, bk, hlen, patch, npatch, pstd, 10, 0.02, 0.02)
+    loss = E.swav_train_step(gen, head, mean_latent.cuda(), draws, cfg)
+    assert abs(loss.item() - ref["loss"].item()) < 2e-3 * abs(ref["loss"].item()), (loss.item(), ref["loss"])
+    for got, exp in zip((head.g_proj, head.g_proto, head.g_bias), ref["grads"]):
+        rel = (got.cpu() - exp).norm().item() / exp.norm().item()
+        assert rel < 2e-2, rel
+    for got, exp in zip((head.w_proj, head.w_proto, head.b_proto), ref["params"]):
+        torch.testing.assert_close(got.cpu(), exp, rtol=1e-4, atol=2e-6)
+
+
 def test_full_precision_backward_option(gen):
     """passes_bwd = 3 tightens the gradients to the fp32 reference."""
     from ganecdotes_b200.hfc_with_swav import engine as E
