@@ -205,7 +205,7 @@ def run_ours(args):
     proj = torch.nn.Linear(cfg["hlen"], cfg["nclasses"], bias=False).to(dev)
     proto = torch.nn.Linear(cfg["nclasses"], cfg["nprototypes"]).to(dev)
     head = E.SwavHead(proj.weight.data, proto.weight.data, proto.bias.data, cfg["lr"], cfg["momentum"], cfg["trust"],
-                      args.passes_fwd, args.passes_bwd, proto_f16=args.proto_f16)
+                      args.passes_fwd, args.passes_bwd, proto_f16=not args.proto_bf16x3)
     scfg = E.StepConfig(hlen=cfg["hlen"], patch_size=cfg["patch"], num_patches=cfg["npatch"], niters=cfg["niters"],
                         eps=cfg["eps"], temperature=cfg["temperature"], truncation=cfg["truncation"],
                         perturb_std=cfg["perturb_std"])
@@ -276,6 +276,10 @@ def run_ours(args):
         s[2] += 1
     pk = peaks()
     tensor_bound = {"gemm", "modconv"}
+    # tensor-core passes issued per algorithmic FLOP (split-bf16 = 3 MMAs per product)
+    issued = {"gemm_prototype_fwd": 3 if args.proto_bf16x3 else 1, "gemm_projection_fwd": args.passes_fwd,
+              "modconv": args.passes_fwd, "modconv_up": args.passes_fwd, "gemm_dzn_bwd": args.passes_bwd,
+              "gemm_gproto_bwd": args.passes_bwd, "gemm_gproj_bwd": args.passes_bwd}
     stage_rows = []
     for name, (tms, work, cnt) in sorted(stages.items(), key=lambda kv: -kv[1][0]):
         is_tensor = name.split("_")[0] in tensor_bound
@@ -284,11 +288,23 @@ def run_ours(args):
         stage_rows.append({"kernel": name, "bound": "tensor" if is_tensor else "hbm", "launches": cnt,
                            "ms_per_step": tms / args.steps, "share": tms / ms, "achieved": achieved, "peak": peak,
                            "unit": "TFLOP/s" if is_tensor else "GB/s", "frac": achieved / peak})
+        if is_tensor:
+            stage_rows[-1]["mma_passes"] = issued.get(name, 1)
+            stage_rows[-1]["frac_issued"] = issued.get(name, 1) * achieved / peak
     top = stage_rows[0] if stage_rows else None
     roofline = None
     if top:
+        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
+        traffic = None
+        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")
+        if os.path.exists(tpath):
+            with open(tpath) as f:
+                traffic = json.load(f).get(top["kernel"], {}).get("dram_bytes_per_launch")
+        tms, work, cnt = stages[top["kernel"]]
         roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
-                    "unit": top["unit"], "frac": top["frac"], "traffic": None, "peak_source": pk["src"],
+                    "unit": top["unit"], "frac": top["frac"], "traffic": traffic,
+                    "algorithmic_per_launch": work / cnt, "launches": cnt, "ms_per_launch": tms / cnt,
+                    "peak_source": pk["src"],
                     "note": "algorithmic FLOPs/bytes per launch / mean CUDA-event launch time; a 3-pass "
                             "split-bf16 GEMM issues 3x its algorithmic FLOPs on the tensor pipe"}
 
@@ -324,7 +340,7 @@ def run_ours(args):
             "metric": "per-pixel feature vectors/sec (ffhq-256 SwAV step)", "value": value, "unit": "vectors/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": f"bf16x{args.passes_fwd}-split fwd" + (" (score GEMM fp16x1)" if args.proto_f16 else "") +
+            "dtype": f"bf16x{args.passes_fwd}-split fwd" + ("" if args.proto_bf16x3 else " (score GEMM fp16x1 on unit-norm operands)") +
                      f" / bf16x{args.passes_bwd} bwd operands, fp32 accumulate + fp32 everywhere else",
             "data": "synthetic",
             "config": {"workload": workload_name(b), "latents_per_gpu": b, "global_latents": b * world,
@@ -349,8 +365,9 @@ def main():
     ap.add_argument("--latents-per-gpu", type=int, default=8)
     ap.add_argument("--passes-fwd", type=int, default=3, choices=[1, 3])
     ap.add_argument("--passes-bwd", type=int, default=1, choices=[1, 3])
-    ap.add_argument("--proto-f16", action="store_true",
-                    help="pixel x prototype score GEMM on single fp16 planes (|dS| ~ 1e-5) instead of the bf16x3 split")
+    ap.add_argument("--proto-bf16x3", action="store_true",
+                    help="pixel x prototype score GEMM on the 3-plane bf16 split (|dS| ~ 1e-6) instead of single "
+                         "fp16 planes (|dS| ~ 1e-5 rms, the default)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

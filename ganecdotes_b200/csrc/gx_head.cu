@@ -1163,7 +1163,7 @@ static int launch_swav_loss(const float* s_s, const float* s_t, long long n, int
   int stages = (200 * 1024 - stage_bytes) / stage_bytes;   // one stage worth of smem holds log2(a) of both views
   if (stages > 8) stages = 8;
   stages -= stages % NG;                                   // fixed stage ownership per group (see sinkhorn pass)
-  GX_CHECK_ARG(stages >= 2 * NG || (NG == 1 && stages >= 2));
+  GX_CHECK_ARG(stages >= NG);   // a stage is refilled once its group holds the row in registers
   static bool attr = false;
   if (!attr) {
     GX_CHECK_CUDA(cudaFuncSetAttribute(swav_loss_kernel<J, GT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,

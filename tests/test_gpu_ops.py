@@ -454,7 +454,7 @@ def test_sinkhorn_golden_and_image_pdf(L):
     torch.testing.assert_close(q.cpu(), ref, rtol=2e-3, atol=1e-9)
 
 
-@pytest.mark.parametrize("n,k", [(40, 24), (257, 5000)])
+@pytest.mark.parametrize("n,k", [(40, 24), (257, 5000), (300, 1500), (1000, 3000), (90, 8192)])
 def test_swav_loss_fwd_bwd_vs_oracle(L, n, k):
     from ganecdotes_b200.hfc_with_swav import engine as E
     torch.manual_seed(n)

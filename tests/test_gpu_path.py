@@ -178,11 +178,13 @@ def oracle_step(sd, mean_latent, draws, wp, wk, bk, hlen, patch, npatch, pstd, n
     return O.swav_step(rs, rt, wp, wk, bk, niters, eps, temp, bufs)
 
 
-@pytest.mark.parametrize("dedup", [False, True])
-def test_batched_joint_step_matches_oracle(gen, dedup):
+@pytest.mark.parametrize("dedup,proto_f16", [(False, True), (True, True), (True, False)])
+def test_batched_joint_step_matches_oracle(gen, dedup, proto_f16):
     """B = 3 latents per step: joint-batch Sinkhorn over the row-concatenation.
     dedup=True: every pixel is projected once and the patches gather rows of Z (the path the
-    full-size ffhq step takes, where 5 x 20000 samples > 65536 pixels)."""
+    full-size ffhq step takes, where 5 x 20000 samples > 65536 pixels).
+    proto_f16: pixel x prototype scores from single fp16 planes of the unit-norm operands (default,
+    |dS| ~ 1e-5) or from the 3-plane bf16 split; both meet the same tolerances."""
     from ganecdotes_b200.hfc_with_swav import engine as E
     from ganecdotes_b200 import _lib as L
     sd = O.init_generator_state(16, 64, 2, 7)
@@ -193,7 +195,8 @@ def test_batched_joint_step_matches_oracle(gen, dedup):
     bk = 0.05 * torch.randn(k)
     mean_latent = O.style_mlp(sd, torch.randn(64, 64)).mean(0, keepdim=True)
     pstd = [1.0, 0.5, 1.0]
-    head = E.SwavHead(wp.clone().cuda(), wk.clone().cuda(), bk.clone().cuda(), 0.01, 0.9, 0.01, 3, 1)
+    head = E.SwavHead(wp.clone().cuda(), wk.clone().cuda(), bk.clone().cuda(), 0.01, 0.9, 0.01, 3, 1,
+                      proto_f16=proto_f16)
     cfg = E.StepConfig(hlen=hlen, patch_size=patch, num_patches=npatch, niters=10, eps=0.02, temperature=0.02,
                        truncation=0.7, perturb_std=pstd, dedup=dedup)
     bufs = None
@@ -211,32 +214,6 @@ def test_batched_joint_step_matches_oracle(gen, dedup):
         bufs = ref["bufs"]
         for got, exp in zip((head.w_proj, head.w_proto, head.b_proto), ref["params"]):
             torch.testing.assert_close(got.cpu(), exp, rtol=1e-4, atol=2e-6)
-
-
-def test_fp16_score_gemm_option(gen):
-    """proto_f16: the pixel x prototype scores from single fp16 planes (unit-norm operands, |dS| ~ 1e-5)
-    stay inside the tolerances of the default bf16x3 path on a joint-batch step."""
-    from ganecdotes_b200.hfc_with_swav import engine as E
-    sd = O.init_generator_state(16, 64, 2, 7)
-    torch.manual_seed(0)
-    hlen, c, k, patch, npatch = 2560, 64, 48, 120, 2
-    wp = torch.randn(c, hlen) / hlen ** 0.5
-    wk = torch.randn(k, c)
-    bk = 0.05 * torch.randn(k)
-    mean_latent = O.style_mlp(sd, torch.randn(64, 64)).mean(0, keepdim=True)
-    pstd = [1.0, 0.5, 1.0]
-    head = E.SwavHead(wp.clone().cuda(), wk.clone().cuda(), bk.clone().cuda(), 0.01, 0.9, 0.01, 3, 1, proto_f16=True)
-    cfg = E.StepConfig(hlen=hlen, patch_size=patch, num_patches=npatch, niters=10, eps=0.02, temperature=0.02,
-                       truncation=0.7, perturb_std=pstd)
-    draws = make_draws(3, 64, 3, 256, npatch, 100)
-    ref = oracle_step(sd, mean_latent, draws, wp, wk, bk, hlen, patch, npatch, pstd, 10, 0.02, 0.02)
-    loss = E.swav_train_step(gen, head, mean_latent.cuda(), draws, cfg)
-    assert abs(loss.item() - ref["loss"].item()) < 2e-3 * abs(ref["loss"].item()), (loss.item(), ref["loss"])
-    for got, exp in zip((head.g_proj, head.g_proto, head.g_bias), ref["grads"]):
-        rel = (got.cpu() - exp).norm().item() / exp.norm().item()
-        assert rel < 2e-2, rel
-    for got, exp in zip((head.w_proj, head.w_proto, head.b_proto), ref["params"]):
-        torch.testing.assert_close(got.cpu(), exp, rtol=1e-4, atol=2e-6)
 
 
 def test_full_precision_backward_option(gen):
