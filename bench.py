@@ -311,16 +311,31 @@ def run_ours(args):
     # ---------------------------------------------------------------- end-to-end region
     # public API from pinned host buffers: host bookkeeping + H2D of step i+1 are issued while
     # the GPU runs step i; the loss of every step is read back to the host.
-    e2e_steps = max(1, min(args.steps, 5))
+    # Same schedule as SwAVClustering.pretrain: inputs of step i+1 go through pinned memory on a side
+    # stream while step i computes; the loss of step i is read back once step i+1 has been launched.
+    e2e_steps = max(1, args.steps)
+    side = torch.cuda.Stream(device=dev)
     sync()
     t0 = time.perf_counter()
-    inp = E.prepare_step_inputs(gen, draws[args.warmup], scfg, dev)
+    inp = E.prepare_step_inputs(gen, draws[args.warmup], scfg, dev, stream=side)
     h2d = inp.h2d_bytes
+    pending = None
+    host_ms = {"prepare": (time.perf_counter() - t0) * 1e3, "launch": 0.0, "wait": 0.0}
     for i in range(e2e_steps):
+        ta = time.perf_counter()
         l = E.swav_train_step_device(gen, head, mean_latent, inp, scfg, group, ws)
+        tb = time.perf_counter()
         if i + 1 < e2e_steps:
-            inp = E.prepare_step_inputs(gen, draws[args.warmup + (i + 1) % args.steps], scfg, dev)
-        _ = float(l)                                                   # device -> host read of the loss
+            inp = E.prepare_step_inputs(gen, draws[args.warmup + (i + 1) % args.steps], scfg, dev, stream=side)
+        tc = time.perf_counter()
+        if pending is not None:
+            _ = float(pending)                                         # device -> host read of the loss
+        pending = l
+        td = time.perf_counter()
+        host_ms["launch"] += (tb - ta) * 1e3
+        host_ms["prepare"] += (tc - tb) * 1e3
+        host_ms["wait"] += (td - tc) * 1e3
+    _ = float(pending)
     sync()
     dt = time.perf_counter() - t0
     if world > 1:
@@ -348,7 +363,8 @@ def run_ours(args):
                        "generator": "StyleGAN2-256 random init seed 42", "sinkhorn": "joint-batch (distributed)"},
             "roofline": roofline, "roofline_stages": stage_rows[:14], "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": "vectors/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
-                    "steps": e2e_steps},
+                    "steps": e2e_steps, "ms_per_step": dt * 1e3 / e2e_steps,
+                    "host_ms_per_step": {k: v / e2e_steps for k, v in host_ms.items()}},
             "gpu_launches": launches, "clocks": clocks, "final_loss": final_loss,
         }
         print(json.dumps(line), flush=True)

@@ -65,17 +65,41 @@ class StepDraws:
     perms: List[List[torch.Tensor]]     # perms[p][b]: randperm(H*W) (ref :388), shared by both views
 
 
-def build_row_indices(h, w, view: ViewDraws, perms, patch_size, device):
-    """[P, B*N] int32 (row_src), [B*N] int32 (row_img) for one view."""
+_MAP_POOL = None
+
+
+def _map_pool():
+    global _MAP_POOL
+    if _MAP_POOL is None:
+        from concurrent.futures import ThreadPoolExecutor
+        _MAP_POOL = ThreadPoolExecutor(max_workers=4, thread_name_prefix="gx-index-map")
+    return _MAP_POOL
+
+
+def build_row_indices(h, w, view: ViewDraws, perms, patch_size, device, count_fill=False):
+    """[P, B*N] int32 (row_src), [B*N] int32 (row_img) for one view; with count_fill also the number
+    of samples that fall on rotation fill (row_src == -1), counted on the host."""
     b = len(view.angle)
-    maps = [rotate_flip_index_map(h, w, view.angle[i], view.flip[i]) for i in range(b)]
+    if b >= 4:      # the torchvision ops release the GIL: a few host threads hide most of the map cost
+        maps = list(_map_pool().map(lambda i: rotate_flip_index_map(h, w, view.angle[i], view.flip[i]), range(b)))
+    else:
+        maps = [rotate_flip_index_map(h, w, view.angle[i], view.flip[i]) for i in range(b)]
     n = patch_size if patch_size is not None else h * w
     rows = []
     for p in range(len(perms)):
         rows.append(torch.cat([maps[i][perms[p][i][:n]] for i in range(b)]))
     row_src = torch.stack(rows).to(torch.int32)
     row_img = torch.arange(b, dtype=torch.int32).repeat_interleave(n)
-    return row_src.to(device, non_blocking=True), row_img.to(device, non_blocking=True)
+    if count_fill:
+        return _upload(row_src, device), _upload(row_img, device), int((row_src < 0).sum())
+    return _upload(row_src, device), _upload(row_img, device)
+
+
+def _upload(t, device):
+    """host -> device through pinned memory (truly asynchronous on the current stream)"""
+    if torch.device(device).type != "cuda":
+        return t.to(device)
+    return t.contiguous().pin_memory().to(device, non_blocking=True)
 
 
 # ----------------------------------------------------------------------------------------
@@ -416,6 +440,7 @@ class StepInputs:
     h2d_bytes: int = 0
     index_maps: Optional[dict] = None  # name -> int32 [H*W] (source_pdf == 'image', single latent)
     dedup: Optional[dict] = None       # name -> (row_idx [P, B*N] int32, order int32, seg_off int32 [B*H*W+1])
+    ready: Optional[object] = None     # CUDA event recorded on the upload stream (None: same stream)
 
 
 def use_dedup(cfg: StepConfig, out_h, out_w) -> bool:
@@ -429,20 +454,32 @@ def use_dedup(cfg: StepConfig, out_h, out_w) -> bool:
     return 4 * cfg.num_patches * n > out_h * out_w
 
 
-def prepare_step_inputs(gen, draws: StepDraws, cfg: StepConfig, device) -> StepInputs:
+def prepare_step_inputs(gen, draws: StepDraws, cfg: StepConfig, device, stream=None) -> StepInputs:
     """Host bookkeeping + host->device copies of one step: latents, the two perturbation
-    draws per latent-view that are actually used, and the sampled-pixel source indices."""
+    draws per latent-view that are actually used, and the sampled-pixel source indices.
+    With `stream` (a side CUDA stream) the uploads and the index bookkeeping kernels are issued
+    there, so the inputs of step i+1 are staged while the compute stream runs step i; the step
+    waits on `ready`."""
+    if stream is not None:
+        main = torch.cuda.current_stream()
+        with torch.cuda.stream(stream):
+            inp = prepare_step_inputs(gen, draws, cfg, device)
+            inp.ready = torch.cuda.Event()
+            inp.ready.record(stream)
+        for t in _tensors_of(inp):      # allocated on the side stream, consumed on the compute stream
+            t.record_stream(main)
+        return inp
     out_h = out_w = gen.size
-    views, rows, nbytes = {}, {}, 0
-    z = draws.z.to(device, non_blocking=True)
+    views, rows, nbytes, n_fill = {}, {}, 0, {}
+    z = _upload(draws.z, device)
     nbytes += draws.z.numel() * 4
     for name, view in (("s", draws.view_s), ("t", draws.view_t)):
         pr = []
         for i, l in enumerate(view.layer_no):
             pr += [view.pert_z[i, 2 * l], view.pert_z[i, 2 * l + 1]]
         pr = torch.stack(pr)
-        views[name] = (list(view.layer_no), pr.to(device, non_blocking=True))
-        rs, ri = build_row_indices(out_h, out_w, view, draws.perms, cfg.patch_size, device)
+        views[name] = (list(view.layer_no), _upload(pr, device))
+        rs, ri, n_fill[name] = build_row_indices(out_h, out_w, view, draws.perms, cfg.patch_size, device, True)
         rows[name] = (rs, ri)
         nbytes += pr.numel() * 4 + rs.numel() * 4 + ri.numel() * 4
     dedup = None
@@ -454,10 +491,15 @@ def prepare_step_inputs(gen, draws: StepDraws, cfg: StepConfig, device) -> StepI
             ridx = torch.where(rs >= 0, ri.unsqueeze(0) * hw + rs, torch.full_like(rs, -1))      # [P, B*N]
             keys = ridx.flatten().long()
             order = torch.argsort(keys)
-            n_invalid = int((keys < 0).sum())
-            counts = torch.bincount(keys[keys >= 0], minlength=draws.z.shape[0] * hw)
-            seg_off = torch.zeros(counts.numel() + 1, dtype=torch.int32, device=device)
-            seg_off[1:] = torch.cumsum(counts, 0).to(torch.int32)
+            n_invalid = n_fill[name]          # counted on the host: no device synchronisation here
+            # samples per pixel without host synchronisation (boolean indexing / bincount would sync):
+            # rotation-fill samples go to an extra bin that is dropped
+            npix = draws.z.shape[0] * hw
+            counts = torch.zeros(npix + 1, dtype=torch.int32, device=device)
+            counts.index_add_(0, torch.where(keys >= 0, keys, torch.full_like(keys, npix)),
+                              torch.ones(keys.numel(), dtype=torch.int32, device=device))
+            seg_off = torch.zeros(npix + 1, dtype=torch.int32, device=device)
+            seg_off[1:] = torch.cumsum(counts[:npix], 0).to(torch.int32)
             dedup[name] = (ridx.contiguous(), order[n_invalid:].to(torch.int32).contiguous(), seg_off)
     index_maps = None
     if cfg.source_pdf == 'image':
@@ -466,9 +508,24 @@ def prepare_step_inputs(gen, draws: StepDraws, cfg: StepConfig, device) -> StepI
         index_maps = {}
         for name, view in (("s", draws.view_s), ("t", draws.view_t)):
             m = rotate_flip_index_map(out_h, out_w, view.angle[0], view.flip[0]).to(torch.int32)
-            index_maps[name] = m.to(device, non_blocking=True)
+            index_maps[name] = _upload(m, device)
             nbytes += m.numel() * 4
     return StepInputs(z=z, views=views, rows=rows, h2d_bytes=nbytes, index_maps=index_maps, dedup=dedup)
+
+
+def _tensors_of(inp: StepInputs):
+    out = [inp.z]
+    for _, pr in inp.views.values():
+        out.append(pr)
+    for rs, ri in inp.rows.values():
+        out += [rs, ri]
+    for d in (inp.index_maps, ):
+        if d:
+            out += list(d.values())
+    if inp.dedup:
+        for tup in inp.dedup.values():
+            out += list(tup)
+    return [t for t in out if t.is_cuda]
 
 
 @torch.no_grad()
@@ -497,6 +554,8 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
     dev = head.w_proj.device
     b = inp.z.shape[0]
     world = group.world if group is not None else 1
+    if inp.ready is not None:
+        torch.cuda.current_stream().wait_event(inp.ready)
     # prototype re-normalisation every step (ref :328-331), then operand planes
     L.normalize_rows_(head.w_proto)
     head.refresh_planes()

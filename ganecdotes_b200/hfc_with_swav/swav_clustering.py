@@ -252,12 +252,25 @@ class SwAVClustering(object):
         cfg = self._step_config()
         t0 = time.time()
         loss = None
+        # The host draws of a step do not depend on device results: the inputs of step i+1 are drawn and
+        # uploaded on a side stream while the compute stream runs step i.
+        side = torch.cuda.Stream(device=self.device)
+
+        def stage_next():
+            draws = self.draw_step(b_global)
+            if group is not None:
+                draws = self.shard_draws(draws, group.rank, world)
+            return E.prepare_step_inputs(self.model, draws, cfg, self.device, stream=side)
+
+        total = num_epochs * num_samples
+        nxt = stage_next() if total > 0 else None
+        done = 0
         for e in range(num_epochs):
             for i in range(num_samples):
-                draws = self.draw_step(b_global)
-                if group is not None:
-                    draws = self.shard_draws(draws, group.rank, world)
-                loss = E.swav_train_step(self.model, self._head, self.mean_latent, draws, cfg, group, self._sk_ws)
+                inp, done = nxt, done + 1
+                loss = E.swav_train_step_device(self.model, self._head, self.mean_latent, inp, cfg, group,
+                                                self._sk_ws)
+                nxt = stage_next() if done < total else None
                 if self.writer is not None:
                     self.writer.add_scalar('swav/loss', loss, e)
             if self.logger is not None and e % self.swav_args['epoch_print_freq'] == 0:
