@@ -44,8 +44,9 @@ struct UmmaParams {
   int acc_stages;  // TMEM accumulator ring depth (2 when mtiles*block_n <= 256)
   int a_mn, b_mn;
   int f16;         // operand planes are fp16 (single-pass only) instead of bf16
-  int pair;        // gemm: 2-CTA clusters on adjacent m-tiles of one n-tile; each CTA loads half of the
-                   // B tile and multicasts it to both (halves the L2 -> SM operand traffic of B)
+  int pair;        // gemm: CTA pairs (clusters of 2, tcgen05 cta_group::2) on adjacent 128-row tiles of one
+                   // n-tile: one M=256 MMA spans both SMs, each CTA loads its A rows and HALF of the B tile
+                   // (a third less operand ingest per SM and FLOP than two independent 128-row tiles)
   // ---- gemm
   int M, N, K;
   int tiles_m, tiles_n, split_k, kiters_total;
@@ -134,6 +135,9 @@ template <bool COLEXP, bool ATOMIC>
 __device__ __forceinline__ void epi_chunk_vec(const uint32_t (&r)[32], uint32_t stg, int lane, float* cptr,
                                               long long rstep, const float* bias4, int rows_valid, float colexp_scale,
                                               float* colsum4, bool do_store) {
+  // issued first: its latency hides behind the smem transpose
+  float4 bv = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias4 != nullptr) bv = __ldg(reinterpret_cast<const float4*>(bias4));
   {
     const uint32_t wa = stg + (uint32_t)(lane * 128);
     const uint32_t sw = (uint32_t)(lane & 7);
@@ -159,7 +163,6 @@ __device__ __forceinline__ void epi_chunk_vec(const uint32_t (&r)[32], uint32_t 
   }
   __syncwarp();   // the tile may be overwritten from here on; the rest works from registers
   if (bias4 != nullptr) {
-    const float4 bv = __ldg(reinterpret_cast<const float4*>(bias4));
     const float2 b0 = make_float2(bv.x, bv.y), b1 = make_float2(bv.z, bv.w);
 #pragma unroll
     for (int g = 0; g < 8; ++g) {
@@ -205,6 +208,8 @@ __device__ __forceinline__ void epi_chunk_vec(const uint32_t (&r)[32], uint32_t 
   }
 }
 
+// PAIR = true: the cta_group::2 instantiation, only ever launched as clusters of two CTAs
+template <bool PAIR>
 __global__ void __launch_bounds__(NTHREADS, 1)
 gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
                const __grid_constant__ CUtensorMap tm_a_lo, const __grid_constant__ CUtensorMap tm_b_hi,
@@ -212,7 +217,7 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve (stage buffers must be 1024-aligned for the 128B swizzle)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_plane_bytes = p.block_n * BK * 2;
+  const int b_plane_bytes = (PAIR ? p.block_n / 2 : p.block_n) * BK * 2;
   const int nplanes = (p.passes == 3) ? 2 : 1;
   const int a_plane_bytes = A_PLANE_BYTES * p.mtiles;
   const int stage_bytes = nplanes * (a_plane_bytes + b_plane_bytes);
@@ -226,9 +231,9 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
 
   const int warp = threadIdx.x >> 5;
   const int lane = threadIdx.x & 31;
-  const int crank = p.pair ? (int)cluster_ctarank() : 0;
-  const int w_first = p.pair ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
-  const int w_step = p.pair ? (int)(gridDim.x >> 1) : (int)gridDim.x;
+  const int crank = PAIR ? (int)cluster_ctarank() : 0;
+  const int w_first = PAIR ? (int)(blockIdx.x >> 1) : (int)blockIdx.x;
+  const int w_step = PAIR ? (int)(gridDim.x >> 1) : (int)gridDim.x;
 
   if (warp == 0 && lane == 0) {
     prefetch_tmap(&tm_a_hi);
@@ -241,21 +246,27 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
   if (warp == 1 && lane == 0) {
     for (int i = 0; i < p.stages; ++i) {
       mbar_init(&full_bar[i], 1);
-      mbar_init(&empty_bar[i], p.pair ? 2 : 1);   // pair: both CTAs' MMAs must have retired
+      mbar_init(&empty_bar[i], 1);
     }
     for (int i = 0; i < 2; ++i) {
       mbar_init(&tfull_bar[i], 1);
-      mbar_init(&tempty_bar[i], EPI_WARPS);
+      // pair: the leader's MMA thread waits for the epilogue warps of both CTAs
+      mbar_init(&tempty_bar[i], PAIR ? 2 * EPI_WARPS : EPI_WARPS);
     }
     fence_mbar_init();
   }
   if (warp == 2) {
-    tmem_alloc(tmem_slot, TMEM_COLS);
-    tmem_relinquish();
+    if constexpr (PAIR) {
+      tmem_alloc_pair(tmem_slot, TMEM_COLS);
+      tmem_relinquish_pair();
+    } else {
+      tmem_alloc(tmem_slot, TMEM_COLS);
+      tmem_relinquish();
+    }
   }
   tc_fence_before();
   __syncthreads();
-  if (p.pair) cluster_sync_all();   // the peer's barriers are initialised before anything targets them
+  if constexpr (PAIR) cluster_sync_all();   // the peer's barriers are initialised before anything targets them
   tc_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
@@ -271,6 +282,20 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* sa = smem + stage * stage_bytes;
           uint8_t* sb = sa + nplanes * a_plane_bytes;
+          if constexpr (PAIR) {
+            // both CTAs' loads are counted on the LEADER's barrier (its MMA thread consumes both halves)
+            if (crank == 0) mbar_arrive_expect_tx(&full_bar[stage], 2u * (uint32_t)stage_bytes);
+            const uint32_t lead_bar = cluster_addr_of(&full_bar[stage], 0);
+            const int k0 = kit * BK;
+            const int half_rows = p.block_n >> 1;
+            for (int pl = 0; pl < nplanes; ++pl) {
+              tma_load_2d_pair(sa + pl * a_plane_bytes, pl ? &tm_a_lo : &tm_a_hi, lead_bar, k0, t.m0);
+              tma_load_2d_pair(sb + pl * b_plane_bytes, pl ? &tm_b_lo : &tm_b_hi, lead_bar, k0,
+                               t.n0 + crank * half_rows);
+            }
+            if (++stage == p.stages) { stage = 0; phase ^= 1; }
+            continue;
+          }
           mbar_arrive_expect_tx(&full_bar[stage], (uint32_t)stage_bytes);
           for (int pl = 0; pl < nplanes; ++pl) {
             const CUtensorMap* ma = pl ? &tm_a_lo : &tm_a_hi;
@@ -286,11 +311,7 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
                 for (int i = 0; i < 2 * p.mtiles; ++i)
                   tma_load_2d(da + i * 8192, ma, &full_bar[stage], t.m0 + i * 64, k0);
               }
-              if (p.pair) {
-                const int half_rows = p.block_n >> 1;
-                tma_load_2d_mc(db + crank * half_rows * (BK * 2), mb, &full_bar[stage], k0,
-                               t.n0 + crank * half_rows, (uint16_t)3);
-              } else if (!p.b_mn) {
+              if (!p.b_mn) {
                 tma_load_2d(db, mb, &full_bar[stage], k0, t.n0);
               } else {
                 for (int i = 0; i < p.block_n / 64; ++i)
@@ -311,10 +332,10 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
     }
   } else if (warp == 1) {
     // ============================== MMA issuer ================================
-    if (lane == 0) {
+    if (lane == 0 && crank == 0) {     // pair: the leader CTA issues for both SMs
       int stage = 0;
       uint32_t phase = 0;
-      const uint32_t idesc = make_idesc_bf16(BM, p.block_n, p.a_mn, p.b_mn, p.f16);
+      const uint32_t idesc = make_idesc_bf16(PAIR ? 2 * BM : BM, p.block_n, p.a_mn, p.b_mn, p.f16);
       const uint32_t a_lbo = p.a_mn ? 8192u : 0u, b_lbo = p.b_mn ? 8192u : 0u;
       const uint32_t a_kstep = p.a_mn ? 2048u : 32u, b_kstep = p.b_mn ? 2048u : 32u;
       int it = 0;
@@ -340,19 +361,25 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
 #pragma unroll
             for (int k4 = 0; k4 < BK / 16; ++k4) {
               const uint64_t bdesc = make_smem_desc(bbase + k4 * b_kstep, b_lbo, 1024u);
-              for (int sub = 0; sub < p.mtiles; ++sub) {
-                const uint64_t adesc = make_smem_desc(abase + sub * A_PLANE_BYTES + k4 * a_kstep, a_lbo, 1024u);
-                umma_bf16(d_tmem + (uint32_t)(sub * p.block_n), adesc, bdesc, idesc, accumulate);
+              if constexpr (PAIR) {
+                umma_bf16_pair(d_tmem, make_smem_desc(abase + k4 * a_kstep, a_lbo, 1024u), bdesc, idesc, accumulate);
+              } else {
+                for (int sub = 0; sub < p.mtiles; ++sub) {
+                  const uint64_t adesc = make_smem_desc(abase + sub * A_PLANE_BYTES + k4 * a_kstep, a_lbo, 1024u);
+                  umma_bf16(d_tmem + (uint32_t)(sub * p.block_n), adesc, bdesc, idesc, accumulate);
+                }
               }
               accumulate = 1;
             }
           }
-          // frees the smem slot when these MMAs retire (pair: in both CTAs, whose producers write into it)
-          if (p.pair) umma_commit_mc(&empty_bar[stage], (uint16_t)3);
+          // frees the smem slot when these MMAs retire (pair: in both CTAs)
+          if constexpr (PAIR) umma_commit_pair(&empty_bar[stage], (uint16_t)3);
           else umma_commit(&empty_bar[stage]);
           if (++stage == p.stages) { stage = 0; phase ^= 1; }
         }
-        umma_commit(&tfull_bar[acc]);  // accumulator complete -> epilogue
+        // accumulator complete -> epilogue (pair: of both CTAs)
+        if constexpr (PAIR) umma_commit_pair(&tfull_bar[acc], (uint16_t)3);
+        else umma_commit(&tfull_bar[acc]);
       }
     }
   } else if (warp >= 4) {
@@ -382,13 +409,10 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
           const long long mrow0 = (long long)t.m0 + sub * BM + q * 32;   // first row of this warp
           if (mrow0 >= p.M) break;                                        // warp-uniform
           const int rows_valid = (int)min((long long)32, (long long)p.M - mrow0);
-          for (int ch = ehalf; ch < nchunks; ch += 2) {
+          const uint32_t tsub = taddr0 + (uint32_t)(sub * p.block_n);
+          auto process = [&](const uint32_t (&r)[32], int ch) {
             const int n_base = t.n0 + ch * 32;
-            if (n_base >= p.N) break;  // warp-uniform
-            uint32_t r[32];
-            tmem_ld_32x32(taddr0 + sub * p.block_n + ch * 32, r);
-            tmem_ld_wait();
-            if (p.debug & 2) continue;
+            if (p.debug & 2) return;
             if (vec_ok && n_base + 32 <= p.N) {
               float* cptr = p.c + (mrow0 + lr) * p.ldc + n_base + lc;
               const float* bptr = add_bias ? p.bias + n_base + lc : nullptr;
@@ -428,6 +452,24 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
               if (p.colexp_sum != nullptr && nvalid && !p.atomic) atomicAdd(p.colexp_sum + n, es);
             }
             __syncwarp();
+          };
+          // two register sets: the TMEM load of the next chunk is in flight while this one is staged / stored
+          uint32_t ra[32], rb[32];
+          int ch = ehalf;
+          bool have = ch < nchunks && t.n0 + ch * 32 < p.N;   // warp-uniform
+          if (have) tmem_ld_32x32(tsub + ch * 32, ra);
+          while (have) {
+            tmem_ld_wait();
+            const int ch2 = ch + 2;
+            const bool have2 = ch2 < nchunks && t.n0 + ch2 * 32 < p.N;
+            if (have2) tmem_ld_32x32(tsub + ch2 * 32, rb);
+            process(ra, ch);
+            if (!have2) break;
+            tmem_ld_wait();
+            ch = ch2 + 2;
+            have = ch < nchunks && t.n0 + ch * 32 < p.N;
+            if (have) tmem_ld_32x32(tsub + ch * 32, ra);
+            process(rb, ch2);
           }
         }
       } else {
@@ -508,16 +550,20 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
       // release the accumulator stage
       tc_fence_before();
       __syncwarp();
-      if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+      if (lane == 0) {
+        if (crank == 0) mbar_arrive(&tempty_bar[acc]);
+        else mbar_arrive_cluster(cluster_addr_of(&tempty_bar[acc], 0));
+      }
     }
   }
 
   tc_fence_before();
   __syncthreads();
-  if (p.pair) cluster_sync_all();   // no CTA leaves while its peer can still signal its barriers
+  if constexpr (PAIR) cluster_sync_all();   // no CTA leaves while its peer can still signal its barriers
   if (warp == 2) {
     tc_fence_after();
-    tmem_dealloc(tmem_base, TMEM_COLS);
+    if constexpr (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
+    else tmem_dealloc(tmem_base, TMEM_COLS);
   }
 }
 
@@ -585,11 +631,12 @@ int launch(const UmmaParams& p_in, const CUtensorMap* maps, int total_work, cuda
     p.debug = dbg;
   }
   const int nplanes = p.passes == 3 ? 2 : 1;
-  const int stage_bytes = nplanes * (A_PLANE_BYTES * p.mtiles + p.block_n * BK * 2);
+  const int stage_bytes = nplanes * (A_PLANE_BYTES * p.mtiles + (p.pair ? p.block_n / 2 : p.block_n) * BK * 2);
   const int smem_bytes = p.stages * stage_bytes + 256 + STAGING_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {
-    GX_CHECK_CUDA(cudaFuncSetAttribute(gx_umma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    GX_CHECK_CUDA(cudaFuncSetAttribute(gx_umma_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
+    GX_CHECK_CUDA(cudaFuncSetAttribute(gx_umma_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SMEM_LIMIT));
     attr_set = true;
   }
   int grid = gx_umma_cta_budget();
@@ -611,13 +658,13 @@ int launch(const UmmaParams& p_in, const CUtensorMap* maps, int total_work, cuda
     at[0].val.clusterDim.z = 1;
     cfg.attrs = at;
     cfg.numAttrs = 1;
-    GX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gx_umma_kernel, p, maps[0], maps[1], maps[2], maps[3], total_work));
+    GX_CHECK_CUDA(cudaLaunchKernelEx(&cfg, gx_umma_kernel<true>, p, maps[0], maps[1], maps[2], maps[3], total_work));
     GX_LAUNCH_CHECK();
     return GX_OK;
   }
   if (grid > total_work) grid = total_work;
   if (grid < 1) return GX_OK;
-  gx_umma_kernel<<<grid, NTHREADS, smem_bytes, st>>>(p, maps[0], maps[1], maps[2], maps[3], total_work);
+  gx_umma_kernel<false><<<grid, NTHREADS, smem_bytes, st>>>(p, maps[0], maps[1], maps[2], maps[3], total_work);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }
@@ -644,10 +691,10 @@ extern "C" int gx_gemm(const gx_gemm_desc* d, void* stream) {
   p.block_n = bn;
   // 256-row tiles for single-pass GEMMs: one B tile in smem feeds two M=128 MMAs, which keeps the
   // smem fill rate (L2 -> SM) at the level of the 3-pass mode instead of 1.5x above it
-  p.pair = (d->cluster_pair && !p.b_mn && d->m > BM) ? 1 : 0;
+  p.pair = (d->cluster_pair && !p.a_mn && !p.b_mn && d->m > BM && bn >= 64) ? 1 : 0;
   p.mtiles = (p.passes == 1 && bn == 256 && d->m > BM && !d->force_m128 && !p.pair) ? 2 : 1;
   p.acc_stages = (p.mtiles * bn <= 256) ? 2 : 1;
-  p.stages = pick_stages(p.passes, bn, p.mtiles, d->stages);
+  p.stages = pick_stages(p.passes, p.pair ? bn / 2 : bn, p.mtiles, d->stages);
   GX_CHECK_ARG(p.stages >= 2);
   p.tiles_m = gx_cdiv(d->m, BM * p.mtiles);
   p.tiles_n = gx_cdiv(d->n, bn);

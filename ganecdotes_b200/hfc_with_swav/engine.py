@@ -229,12 +229,13 @@ def _proto_scores(head: SwavHead, zn_hi, zn_lo, n, eps):
         u0 = torch.zeros(head.k, dtype=torch.float32, device=zn_hi.device)
         colexp = (u0, LOG2E / eps)
     if head.proto_f16:     # zn_hi is the fp16 plane here (see scores_forward*)
-        # 128-row tiles: two accumulator stages in TMEM, so the (store-heavy) epilogue overlaps the next tile
+        # CTA pairs (cta_group::2): M=256 MMAs over two SMs, each loading half of the Wk tile, with two
+        # accumulator stages per SM so the (store-heavy) epilogue overlaps the next tile's MMAs
         s = L.gemm(zn_hi, None, head.wk_f16, None, n, head.k, head.c, 1, bias=head.b_proto,
-                   tag="gemm_prototype_fwd", colexp=colexp, force_m128=True)
+                   tag="gemm_prototype_fwd", colexp=colexp, pair=True)
     else:
         s = L.gemm(zn_hi, zn_lo if head.passes_fwd == 3 else None, head.wk_hi, head.wk_lo, n, head.k, head.c,
-                   head.passes_fwd, bias=head.b_proto, tag="gemm_prototype_fwd", colexp=colexp)
+                   head.passes_fwd, bias=head.b_proto, tag="gemm_prototype_fwd", colexp=colexp, pair=True)
     return s, u0
 
 

@@ -162,8 +162,9 @@ def test_gemm_fused_first_sinkhorn_marginal(L):
     (130, 136, 64, 1, False),        # ragged n tail inside the second B half
     (4096, 264, 200, 3, False),
 ])
-def test_gemm_cluster_pair_multicast(L, m, n, k, passes, f16):
-    """2-CTA clusters sharing the B tile by TMA multicast give the same numbers as the 1-CTA kernel"""
+def test_gemm_cta_pair(L, m, n, k, passes, f16):
+    """CTA pairs (tcgen05 cta_group::2: one M=256 MMA over two SMs, half of the B tile per SM) give the
+    same numbers as the 1-CTA kernel"""
     torch.manual_seed(m + n)
     a = torch.nn.functional.normalize(torch.randn(m, k, device="cuda"), dim=1)
     b = torch.nn.functional.normalize(torch.randn(n, k, device="cuda"), dim=1)
