@@ -289,9 +289,21 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
             const int k0 = kit * BK;
             const int half_rows = p.block_n >> 1;
             for (int pl = 0; pl < nplanes; ++pl) {
-              tma_load_2d_pair(sa + pl * a_plane_bytes, pl ? &tm_a_lo : &tm_a_hi, lead_bar, k0, t.m0);
-              tma_load_2d_pair(sb + pl * b_plane_bytes, pl ? &tm_b_lo : &tm_b_hi, lead_bar, k0,
-                               t.n0 + crank * half_rows);
+              const CUtensorMap* ma = pl ? &tm_a_lo : &tm_a_hi;
+              const CUtensorMap* mb = pl ? &tm_b_lo : &tm_b_hi;
+              uint8_t* da = sa + pl * a_plane_bytes;
+              uint8_t* db = sb + pl * b_plane_bytes;
+              if (!p.a_mn) {
+                tma_load_2d_pair(da, ma, lead_bar, k0, t.m0);
+              } else {
+                for (int i = 0; i < 2; ++i) tma_load_2d_pair(da + i * 8192, ma, lead_bar, t.m0 + i * 64, k0);
+              }
+              if (!p.b_mn) {
+                tma_load_2d_pair(db, mb, lead_bar, k0, t.n0 + crank * half_rows);
+              } else {
+                for (int i = 0; i < half_rows / 64; ++i)
+                  tma_load_2d_pair(db + i * 8192, mb, lead_bar, t.n0 + crank * half_rows + i * 64, k0);
+              }
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
             continue;
@@ -691,7 +703,8 @@ extern "C" int gx_gemm(const gx_gemm_desc* d, void* stream) {
   p.block_n = bn;
   // 256-row tiles for single-pass GEMMs: one B tile in smem feeds two M=128 MMAs, which keeps the
   // smem fill rate (L2 -> SM) at the level of the 3-pass mode instead of 1.5x above it
-  p.pair = (d->cluster_pair && !p.a_mn && !p.b_mn && d->m > BM && bn >= 64) ? 1 : 0;
+  // (MN-major B is loaded in 64-wide boxes: each CTA's half must hold at least one)
+  p.pair = (d->cluster_pair && d->m > BM && bn >= (p.b_mn ? 128 : 64)) ? 1 : 0;
   p.mtiles = (p.passes == 1 && bn == 256 && d->m > BM && !d->force_m128 && !p.pair) ? 2 : 1;
   p.acc_stages = (p.mtiles * bn <= 256) ? 2 : 1;
   p.stages = pick_stages(p.passes, p.pair ? bn / 2 : bn, p.mtiles, d->stages);

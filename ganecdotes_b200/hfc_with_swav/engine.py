@@ -303,13 +303,14 @@ def scores_backward(head: SwavHead, fw, ds_hi, ds_lo, dz_rows_out=None):
     n, k, c, d = fw["n"], head.k, head.c, head.d
     pb = head.passes_bwd
     dzn = L.gemm(ds_hi, ds_lo if pb == 3 else None, head.wkT_hi, head.wkT_lo if pb == 3 else None, n, c, k, pb,
-                 tag="gemm_dzn_bwd")
+                 tag="gemm_dzn_bwd", pair=True)
     kit = (n + 63) // 64
     sms = L.load().gx_sinkhorn_max_parts()
     bm = 256 if pb == 1 else 128     # the engine uses 256-row CTA tiles for single-pass GEMMs
-    sk1 = pick_split_k(math.ceil(k / bm) * math.ceil(c / 256), kit, sms)
+    # CTA pairs: one unit of work = 256 x 256 outputs on two SMs
+    sk1 = pick_split_k(math.ceil(k / 256) * math.ceil(c / 256), kit, sms // 2)
     L.gemm(ds_hi, ds_lo if pb == 3 else None, fw["zn_hi"], fw["zn_lo"] if pb == 3 else None, k, c, n, pb,
-           out=head.g_proto, a_mn=True, b_mn=True, split_k=sk1, accumulate=True, tag="gemm_gproto_bwd")
+           out=head.g_proto, a_mn=True, b_mn=True, split_k=sk1, accumulate=True, tag="gemm_gproto_bwd", pair=True)
     if dz_rows_out is not None:
         L.l2norm_bwd_split(dzn, fw["zn_hi"], fw["zn_lo"], fw["inv"], want_planes=False, out_f32=dz_rows_out)
         return
@@ -358,7 +359,7 @@ def project_all_pixels(wp_hi, wp_lo, feats, batch, out_h, out_w, hlen, passes, w
             col += cw
         sl = slice(g["off"], g["off"] + g["keep"])
         p = L.gemm(a_hi, a_lo, wp_hi[:, sl], wp_lo[:, sl] if wp_lo is not None else None, n, c, g["keep"], passes,
-                   tag="gemm_projection_fwd")
+                   tag="gemm_projection_fwd", pair=True)
         parts.append(p.view(batch, g["h"], g["w"], c))
         levels.append(dict(a_hi=a_hi, a_lo=None if want_hi_only_planes else a_lo, h=g["h"], w=g["w"], off=g["off"],
                            keep=g["keep"]))

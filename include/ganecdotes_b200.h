@@ -151,7 +151,7 @@ typedef struct gx_gemm_desc {
   float colexp_scale;
   int block_n;       /* 0 = auto                                                 */
   int stages;        /* 0 = auto                                                 */
-  int cluster_pair;  /* != 0 (K-major A and B): CTA pairs (tcgen05 cta_group::2) - one M=256 MMA spans two SMs,
+  int cluster_pair;  /* != 0: CTA pairs (tcgen05 cta_group::2) - one M=256 MMA spans two SMs,
                         each CTA loads its 128 A rows and half of the B tile: a third less operand traffic
                         per SM than two independent 128-row tiles */
   int ab_f16;        /* != 0: a_hi / b_hi are IEEE fp16 planes (passes must be 1): 11-bit significands

@@ -187,6 +187,25 @@ def test_gemm_cta_pair(L, m, n, k, passes, f16):
     assert torch.equal(ref, got)
 
 
+def test_gemm_cta_pair_mn_major_split_k(L):
+    """weight-gradient shape: C[m,n] += A^T B with both operands stored [K, *] (MN-major), split-K, CTA pairs"""
+    torch.manual_seed(11)
+    m, n, k = 704, 512, 3000   # MN-major rows need a 16-byte pitch
+    a = torch.randn(k, m, device="cuda") * 0.1
+    b = torch.randn(k, n, device="cuda") * 0.1
+    ah, bh = a.bfloat16(), b.bfloat16()
+    ref = torch.zeros(m, n, device="cuda")
+    got = torch.zeros(m, n, device="cuda")
+    L.gemm(ah, None, bh, None, m, n, k, 1, out=ref, a_mn=True, b_mn=True, split_k=3, accumulate=True)
+    L.gemm(ah, None, bh, None, m, n, k, 1, out=got, a_mn=True, b_mn=True, split_k=3, accumulate=True, pair=True)
+    exact = ah.double().t() @ bh.double()
+    tol = 4e-7 * k * exact.abs().max().item() + 1e-4
+    assert (ref.double() - exact).abs().max().item() < tol
+    assert (got.double() - exact).abs().max().item() < tol
+    L.gemm(ah, None, bh, None, m, n, k, 1, out=got, a_mn=True, b_mn=True, split_k=5, accumulate=True, pair=True)
+    assert (got.double() - 2 * exact).abs().max().item() < 2 * tol
+
+
 def test_gemm_accumulate(L):
     torch.manual_seed(3)
     a = torch.randn(200, 96, device="cuda")
