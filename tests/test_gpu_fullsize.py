@@ -1,0 +1,190 @@
+"""GPU tests at BASELINE.json's FULL sizes.  The CPU oracle does not
+finish these in seconds, so the checks are size-independent properties of the path:
+
+* Sinkhorn-Knopp output: rows of Q sum to 1, prototype marginals are uniform (N/K per column);
+* swapped-prediction gradient: every row of dS sums to zero (softmax minus a distribution), hence
+  the bias gradient sums to zero; the loss is finite and the same for the fp16 and bf16x3 score GEMMs;
+* linearity of the per-resolution projection: Z of the all-pixel path equals the projection of the
+  gathered upsampled+concatenated vectors on sampled pixels (two different kernel routes);
+* label maps: labels == arg-max of the returned codes, first index on ties; k-means assignment equals
+  an fp64 distance arg-min wherever the top-2 margin is not a rounding tie.
+"""
+import math
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+
+def _draws(E, b, d, n_layers, hw, npatch, seed):
+    g = torch.Generator().manual_seed(seed)
+    rs = np.random.RandomState(seed)
+
+    def view():
+        return E.ViewDraws(layer_no=[int(rs.randint(n_layers)) for _ in range(b)],
+                           pert_z=torch.randn(b, 2 * n_layers, d, generator=g),
+                           angle=[float(rs.uniform(-10, 10)) for _ in range(b)],
+                           flip=[bool(rs.rand() < 0.5) for _ in range(b)])
+    return E.StepDraws(z=torch.randn(b, d, generator=g), view_s=view(), view_t=view(),
+                       perms=[[torch.randperm(hw, generator=g) for _ in range(b)] for _ in range(npatch)])
+
+
+def _generator(size, seed=42, channels=None):
+    from ganecdotes_b200.stylegan2.model import Generator
+    torch.manual_seed(seed)
+    g = Generator(size, 512, 8) if channels is None else Generator(size, 512, 8, channels=channels)
+    return g.cuda()
+
+
+def _head(E, hlen, c, k, seed=1, **kw):
+    torch.manual_seed(seed)
+    proj = torch.nn.Linear(hlen, c, bias=False)
+    proto = torch.nn.Linear(c, k)
+    return E.SwavHead(proj.weight.data.cuda(), proto.weight.data.cuda(), proto.bias.data.cuda(), 0.01, 0.9, 0.01, 3, 1,
+                      **kw)
+
+
+@pytest.fixture(scope="module")
+def ffhq():
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    gen = _generator(256)
+    with torch.no_grad():
+        mean_latent = gen.style(torch.randn(1024, 512, generator=torch.Generator().manual_seed(3)).cuda()).mean(0, keepdim=True)
+    return E, gen, mean_latent
+
+
+def test_ffhq256_full_step_properties(ffhq):
+    """config 2 shape per GPU, 2 latents: D=5376, C=512, K=5000, 5 patches x 20000 px, eps 0.05-scale"""
+    E, gen, mean_latent = ffhq
+    cfg = E.StepConfig(hlen=5376, patch_size=20000, num_patches=5, niters=10, eps=0.05, temperature=0.1,
+                       truncation=0.7, perturb_std=[1.0] * 6)
+    draws = _draws(E, 2, 512, 6, 65536, 5, 7)
+    losses = {}
+    for f16 in (True, False):
+        head = _head(E, 5376, 512, 5000, proto_f16=f16)
+        w0 = head.w_proj.clone()
+        loss = E.swav_train_step(gen, head, mean_latent, draws, cfg)
+        losses[f16] = loss.item()
+        assert math.isfinite(losses[f16]) and 0 < losses[f16] < 10 * math.log(5000)
+        # rows of dS sum to zero -> so does the bias gradient (relative to its magnitude)
+        gb = head.g_bias
+        assert abs(gb.sum().item()) < 1e-3 * gb.abs().sum().item() + 1e-12
+        for g in (head.g_proj, head.g_proto):
+            assert torch.isfinite(g).all() and g.abs().max().item() > 0
+        assert not torch.equal(head.w_proj, w0)           # the LARC/SGD step moved the weights
+    assert abs(losses[True] - losses[False]) < 2e-4 * abs(losses[False]), losses
+
+
+def test_ffhq256_sinkhorn_marginals_full_size(ffhq):
+    """Q = softmax_k(S/eps + log a) of a 40000 x 5000 score matrix: unit rows, uniform prototype marginals"""
+    E, gen, mean_latent = ffhq
+    from ganecdotes_b200 import _lib as L
+    torch.manual_seed(0)
+    n, k, c = 40000, 5000, 512
+    z = torch.nn.functional.normalize(torch.randn(n, c, device="cuda"), dim=1)
+    wk = torch.nn.functional.normalize(torch.randn(k, c, device="cuda"), dim=1)
+    zf, wf = L.round_f16(z), L.round_f16(wk)
+    u0 = torch.zeros(k, device="cuda")
+    eps = 0.05
+    s = L.gemm(zf, None, wf, None, n, k, c, 1, colexp=(u0, E.LOG2E / eps), pair=True)
+    ws = L.SinkhornWorkspace(k, "cuda")
+    la = E.sinkhorn_log_a(s, 10, eps, ws, n, u_first=u0)
+    la_ref = E.sinkhorn_log_a(s, 10, eps, ws, n)                      # first pass by the streaming kernel
+    torch.testing.assert_close(la, la_ref, rtol=0, atol=2e-4)
+    q = L.sinkhorn_q(s, 1.0 / eps, la)
+    torch.testing.assert_close(q.sum(1), torch.ones(n, device="cuda"), rtol=1e-4, atol=0)
+    col = q.sum(0)
+    # 10 iterations from random scores: marginals within a few percent of N/K, mean exactly N/K
+    assert abs(col.mean().item() - n / k) < 1e-3 * n / k
+    assert (col - n / k).abs().max().item() < 0.05 * n / k
+    assert (q >= 0).all()
+
+
+def test_ffhq256_projection_routes_agree(ffhq):
+    """per-resolution projection + upsample-sum == projection of gathered upsampled vectors (full D)"""
+    E, gen, mean_latent = ffhq
+    from ganecdotes_b200 import _lib as L
+    torch.manual_seed(5)
+    lat = torch.randn(2, gen.n_latent, 512, device="cuda")
+    _, feats = gen.synthesize(lat, None, need_image=False)
+    wp = (torch.randn(512, 5376) / 5376 ** 0.5).cuda()
+    wp_hi, wp_lo = L.split_planes(wp, want_lo=True)
+    z_all, levels = E.project_all_pixels(wp_hi, wp_lo, feats, 2, 256, 256, 5376, 3)
+    assert [lv["h"] for lv in levels] == [4, 8, 16, 32, 64, 128, 256]
+    idx = torch.randint(0, 2 * 65536, (4096,), device="cuda", dtype=torch.int32)
+    a_hi, a_lo, _ = L.gather_rows(feats, 256, 256, 5376, (idx // 65536).to(torch.int32), (idx % 65536).to(torch.int32),
+                                  4096, want_lo=True)
+    z_rows = L.gemm(a_hi, a_lo, wp_hi, wp_lo, 4096, 512, 5376, 3)
+    ref = z_rows
+    got = z_all[idx.long()]
+    scale = ref.abs().max().item()
+    assert (got - ref).abs().max().item() < 2e-4 * scale, ((got - ref).abs().max().item(), scale)
+
+
+def test_car512_steps_and_label_map():
+    """config 3: 512^2 generator, the 512^2-native maps fall outside hlen=5376, K=4000,
+    eps=0.01; N=20000 as configured and the full-image Sinkhorn problem N=262144."""
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    gen = _generator(512)
+    with torch.no_grad():
+        mean_latent = gen.style(torch.randn(512, 512, generator=torch.Generator().manual_seed(3)).cuda()).mean(0, keepdim=True)
+    n_layers = 7
+    for patch, npatch in ((20000, 5), (None, 1)):
+        cfg = E.StepConfig(hlen=5376, patch_size=patch, num_patches=npatch, niters=10, eps=0.01, temperature=0.1,
+                           truncation=0.7, perturb_std=[1.0] * n_layers)
+        head = _head(E, 5376, 512, 4000)
+        draws = _draws(E, 1, 512, n_layers, 512 * 512, npatch, 11)
+        loss = E.swav_train_step(gen, head, mean_latent, draws, cfg)
+        assert math.isfinite(loss.item()) and 0 < loss.item() < 10 * math.log(4000), loss.item()
+        gb = head.g_bias
+        assert abs(gb.sum().item()) < 1e-3 * gb.abs().sum().item() + 1e-12
+        assert torch.isfinite(head.g_proj).all() and torch.isfinite(head.g_proto).all()
+    # label map at 512^2
+    w = torch.randn(1, 512, generator=torch.Generator().manual_seed(5))
+    with torch.no_grad():
+        wl = gen.style(w.cuda())
+    preds, labels = E.predict_codes(gen, head.w_proj, wl, mean_latent, 0.7, 5376)
+    assert tuple(preds.shape) == (1, 512, 512, 512) and tuple(labels.shape) == (1, 512, 512)
+    assert labels.dtype == torch.int64
+    assert torch.equal(labels, preds.argmax(dim=1))
+
+
+def test_pidray256_label_map_batch():
+    """config 4: BagGAN channel map (sum C = 2528), projection 2528 -> 512, arg-max label maps, batch of 4"""
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    from ganecdotes_b200.baggan import baggan_channels
+    gen = _generator(256, seed=13, channels=baggan_channels())
+    with torch.no_grad():
+        mean_latent = gen.style(torch.randn(512, 512, generator=torch.Generator().manual_seed(3)).cuda()).mean(0, keepdim=True)
+        wl = gen.style(torch.randn(4, 512, generator=torch.Generator().manual_seed(9)).cuda())
+    torch.manual_seed(2)
+    wp = (torch.randn(512, 2528) / 2528 ** 0.5).cuda()
+    preds, labels = E.predict_codes(gen, wp, wl, mean_latent, 0.9, 2528)
+    assert tuple(labels.shape) == (4, 256, 256) and labels.dtype == torch.int64
+    assert torch.equal(labels, preds.argmax(dim=1))
+    # deterministic: the same call gives the same bits
+    preds2, labels2 = E.predict_codes(gen, wp, wl, mean_latent, 0.9, 2528)
+    assert torch.equal(labels, labels2) and torch.equal(preds, preds2)
+    # images of the batch are independent: image 2 alone gives the same map
+    _, l2 = E.predict_codes(gen, wp, wl[2:3], mean_latent, 0.9, 2528)
+    assert torch.equal(l2[0], labels[2])
+
+
+@pytest.mark.parametrize("c,h,k", [(1024, 64, 32), (512, 128, 64), (1024, 8, 4)])
+def test_kmeans_assign_full_shapes(c, h, k):
+    """config 5: per-pixel nearest centre on [b, C, h, w] features"""
+    from ganecdotes_b200 import _lib as L
+    torch.manual_seed(c + h)
+    b = 2
+    x = torch.randn(b * h * h, c, device="cuda")
+    cen = torch.randn(k, c, device="cuda")
+    lab = L.kmeans_assign(x, cen)
+    d = torch.cdist(x.double(), cen.double())
+    ref = d.argmin(1)
+    mism = lab.long() != ref
+    if mism.any():      # only where fp32 cannot separate the two nearest centres
+        top2 = d.topk(2, dim=1, largest=False).values
+        assert ((top2[:, 1] - top2[:, 0])[mism] < 1e-4 * top2[:, 0][mism]).all()
+    assert mism.float().mean().item() < 1e-3
