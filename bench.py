@@ -361,7 +361,7 @@ def run_ours(args):
             "config": {"workload": workload_name(b), "latents_per_gpu": b, "global_latents": b * world,
                        "vectors_per_step": vec_per_step, "l2": "inputs_larger_than_l2 (3.2 GB score matrices)",
                        "generator": "StyleGAN2-256 random init seed 42", "sinkhorn": "joint-batch (distributed)"},
-            "roofline": roofline, "roofline_stages": stage_rows[:14], "cpu_baseline": cpu_base,
+            "roofline": roofline, "roofline_stages": stage_rows, "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": "vectors/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps, "ms_per_step": dt * 1e3 / e2e_steps,
                     "host_ms_per_step": {k: v / e2e_steps for k, v in host_ms.items()}},

@@ -420,50 +420,56 @@ sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long 
 
   // per-thread columns; out-of-range columns read a clamped (valid) address and are
   // neutralised by log2(a) = -inf  ->  exp2(-inf) = 0
-  float la2[J][4], acc[J][4];
+  // (packed fp32x2 arithmetic: the pass is close enough to the issue limit that its HBM rate follows the
+  // SM clock under the power cap; FFMA2/FADD2 cut the FMA-pipe instructions per score from 3 to 1.5)
+  float2 la2[J][2], acc[J][2];
   int coff[J];
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const int col = j * (GT * 4) + gt * 4;
     coff[j] = min(col, k - 4);
+    float l4[4];
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
-      acc[j][e] = 0.f;
       if (col < k) {
-        la2[j][e] = 0.f;
+        l4[e] = 0.f;
         if (!first) {
           const float rk = r ? r[col + e] : 1.f / (float)k;
-          la2[j][e] = log2f(rk / u_in[col + e]);
+          l4[e] = log2f(rk / u_in[col + e]);
         }
       } else {
-        la2[j][e] = -INFINITY;
+        l4[e] = -INFINITY;
       }
     }
+    la2[j][0] = make_float2(l4[0], l4[1]);
+    la2[j][1] = make_float2(l4[2], l4[3]);
+    acc[j][0] = acc[j][1] = make_float2(0.f, 0.f);
   }
+  const float2 sc2 = make_float2(scale_log2, scale_log2);
   int buf = 0;
   for (int it = grp; it < n_iters; it += NG) {
     const int st = it % stages;
     const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * R;
     gxptx::mbar_wait(&full_bar[st], (uint32_t)((it / stages) & 1));
     const float* srow = reinterpret_cast<const float*>(sk_smem + (size_t)st * stage_bytes);
-    float4 p[R][J];
+    float2 p[R][J][2];
     float t[R];
 #pragma unroll
     for (int rr = 0; rr < R; ++rr) {
       t[rr] = 0.f;
       if (row0 + rr < n) {   // warp-uniform
+        float2 t2 = make_float2(0.f, 0.f);
 #pragma unroll
         for (int j = 0; j < J; ++j) {
           const float4 v = *reinterpret_cast<const float4*>(srow + (size_t)rr * k + coff[j]);
-          p[rr][j].x = ex2_fast(fmaf(v.x, scale_log2, la2[j][0]));
-          p[rr][j].y = ex2_fast(fmaf(v.y, scale_log2, la2[j][1]));
-          p[rr][j].z = ex2_fast(fmaf(v.z, scale_log2, la2[j][2]));
-          p[rr][j].w = ex2_fast(fmaf(v.w, scale_log2, la2[j][3]));
-          t[rr] += (p[rr][j].x + p[rr][j].y) + (p[rr][j].z + p[rr][j].w);
+          p[rr][j][0] = ex2_2(fma2(make_float2(v.x, v.y), sc2, la2[j][0]));
+          p[rr][j][1] = ex2_2(fma2(make_float2(v.z, v.w), sc2, la2[j][1]));
+          t2 = add2(t2, add2(p[rr][j][0], p[rr][j][1]));
         }
+        t[rr] = t2.x + t2.y;
       } else {
 #pragma unroll
-        for (int j = 0; j < J; ++j) p[rr][j] = make_float4(0.f, 0.f, 0.f, 0.f);
+        for (int j = 0; j < J; ++j) p[rr][j][0] = p[rr][j][1] = make_float2(0.f, 0.f);
       }
     }
     if (!first) {
@@ -495,12 +501,11 @@ sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long 
 #pragma unroll
     for (int rr = 0; rr < R; ++rr) {
       if (row0 + rr < n) {
+        const float2 b2 = make_float2(bn[rr], bn[rr]);
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-          acc[j][0] = fmaf(p[rr][j].x, bn[rr], acc[j][0]);
-          acc[j][1] = fmaf(p[rr][j].y, bn[rr], acc[j][1]);
-          acc[j][2] = fmaf(p[rr][j].z, bn[rr], acc[j][2]);
-          acc[j][3] = fmaf(p[rr][j].w, bn[rr], acc[j][3]);
+          acc[j][0] = fma2(p[rr][j][0], b2, acc[j][0]);
+          acc[j][1] = fma2(p[rr][j][1], b2, acc[j][1]);
         }
       }
     }
@@ -512,8 +517,8 @@ sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long 
     const int col = j * (GT * 4) + gt * 4;
     if (col < k)
       *reinterpret_cast<float4*>(prow + col) =
-          make_float4(acc[j][0] * ex2_fast(-la2[j][0]), acc[j][1] * ex2_fast(-la2[j][1]),
-                      acc[j][2] * ex2_fast(-la2[j][2]), acc[j][3] * ex2_fast(-la2[j][3]));
+          make_float4(acc[j][0].x * ex2_fast(-la2[j][0].x), acc[j][0].y * ex2_fast(-la2[j][0].y),
+                      acc[j][1].x * ex2_fast(-la2[j][1].x), acc[j][1].y * ex2_fast(-la2[j][1].y));
   }
 }
 
