@@ -837,6 +837,13 @@ extern "C" int gx_modconv(const gx_conv_desc* d, void* stream) {
     p.phase_tile_start[4] = start;
   }
   p.tiles_m = p.phase_tile_start[p.nphases];
+  // few pixel tiles (4x4 ... 16x16 layers): narrower channel tiles put more SMs on the layer, which is
+  // bound by the serial K loop of a handful of CTAs otherwise
+  if (d->block_n == 0) {
+    while (bn > 64 && p.tiles_m * gx_cdiv(d->cout, bn) * 2 <= gx_sm_count()) bn >>= 1;
+    p.block_n = bn;
+    p.stages = pick_stages(p.passes, bn, 1, d->stages);
+  }
   p.tiles_n = gx_cdiv(d->cout, bn);
   p.split_k = 1;
   p.demod = d->demod; p.noise = d->noise; p.noise_bstride = d->noise_batch_stride;
