@@ -533,9 +533,12 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
               }
             }
           }
-          if (p.act) {
+          if (p.act == 1) {
 #pragma unroll
             for (int e = 0; e < 32; ++e) v[e] = lrelu_sqrt2(v[e]);
+          } else if (p.act == 2) {
+#pragma unroll
+            for (int e = 0; e < 32; ++e) v[e] = v[e] > 0.f ? v[e] : v[e] * 0.2f;
           }
           float4* dst = reinterpret_cast<float4*>(p.out + pix * p.Cout + co);
 #pragma unroll
@@ -777,6 +780,8 @@ extern "C" int gx_modconv(const gx_conv_desc* d, void* stream) {
   p.passes = d->passes;
   p.B = d->batch; p.H = d->h; p.W = d->w; p.Cin = cin_ld; p.Cout = d->cout;  // the K loop runs over padded channels
   p.upsample = d->upsample ? 1 : 0;
+  const int dil = d->dilation > 0 ? d->dilation : 1;
+  GX_CHECK_ARG(dil <= 64 && (dil == 1 || !p.upsample));
   int bn = d->block_n;
   if (bn == 0) bn = (d->cout >= 256) ? 256 : 128;
   if (bn > d->cout) bn = (d->cout >= 128) ? 128 : 64;
@@ -805,8 +810,8 @@ extern "C" int gx_modconv(const gx_conv_desc* d, void* stream) {
     for (int ky = 0; ky < 3; ++ky)
       for (int kx = 0; kx < 3; ++kx) {
         const int tpi = ky * 3 + kx;
-        p.tap_dy[0][tpi] = (signed char)(ky - 1);
-        p.tap_dx[0][tpi] = (signed char)(kx - 1);
+        p.tap_dy[0][tpi] = (signed char)((ky - 1) * dil);
+        p.tap_dx[0][tpi] = (signed char)((kx - 1) * dil);
         p.tap_w[0][tpi] = (signed char)tpi;
       }
     p.phase_tile_start[0] = 0;

@@ -1,0 +1,104 @@
+"""Drop-in for the reference's `OneShotSegmentor` (hfc_with_swav/swav_clustering.py:697-758): the small
+dilated 3x3 conv stack that turns the 512-channel SwAV code map into class scores, and the arg-max label
+map `evaluate.py` takes from it (src/one_shot_pipeline.py:664-665).
+
+Same constructor, same `nn.Sequential` of `Conv2d` / `LeakyReLU(0.2)` (so `state_dict` keys and pickled
+checkpoints are interchangeable), including the reference's quirk that `zip` stops at the shorter list
+(size 'XXS' is ONE `Conv2d(in_ch, 12, 3)` whatever `n_class` is).
+
+The inference forward runs every layer as an implicit GEMM on the tcgen05 conv kernel (`gx_modconv` with
+unmodulated planes, bias + LeakyReLU in the epilogue, next layer's operand planes emitted by the same
+epilogue), on the NHWC code map `predict_swav_codes` produces - nothing goes back to the host, where the
+reference runs this head (`.to('cpu')`, src/one_shot_pipeline.py:610,662).
+
+Not here yet (second half): the one-shot fine-tune loop needs the weight gradients
+of these convs; calling the module with autograd enabled on parameters that require grad raises.
+"""
+import torch
+import torch.nn as nn
+
+from .. import _lib as L
+
+_DILATIONS = {'XXS': [1], 'XS': [1, 2, 1], 'S': [1, 2, 1, 2, 1], 'M': [1, 2, 4, 1, 2, 4, 1],
+              'L': [1, 2, 4, 8, 1, 2, 4, 8, 1]}
+_CHANNELS = {'XXS': [12], 'XS': [16, 8], 'S': [128, 64, 64, 32], 'M': [128, 64, 64, 64, 64, 32],
+             'L': [128, 64, 64, 64, 64, 64, 64, 32]}
+
+
+class OneShotSegmentor(nn.Module):
+
+    def __init__(self, in_ch, n_class, size='S'):
+        super().__init__()
+        if size == 'Lin':
+            raise NotImplementedError("size='Lin' (a per-pixel Linear) is not used by any shipped config")
+        if size not in _DILATIONS:
+            raise AssertionError(f"size must be one of {sorted(_DILATIONS)} or 'Lin'")
+        widths = [in_ch] + _CHANNELS[size] + [n_class]
+        mods = []
+        for d, c_in, c_out in zip(_DILATIONS[size], widths[:-1], widths[1:]):   # stops at len(dilations)
+            mods += [nn.Conv2d(c_in, c_out, kernel_size=3, padding=d, dilation=d), nn.LeakyReLU(0.2, inplace=True)]
+        self.layers = nn.Sequential(*mods[:-1])                                   # no activation after the last conv
+        self.channels = n_class
+        self.size = size
+        self.passes = 3
+        self._planes = {}       # conv index -> (weight version, bias version, operand planes)
+
+    # ------------------------------------------------------------------------------------
+    def _convs(self):
+        return [(i, m) for i, m in enumerate(self.layers) if isinstance(m, nn.Conv2d)]
+
+    def _prepared(self, i, conv):
+        """bf16 operand planes of one conv, output channels zero-padded to a multiple of 4"""
+        key = (conv.weight._version, conv.bias._version, conv.weight.data_ptr())
+        hit = self._planes.get(i)
+        if hit is not None and hit[0] == key:
+            return hit[1]
+        w = conv.weight.detach().float()
+        b = conv.bias.detach().float()
+        cout = w.shape[0]
+        pad = (-cout) % 4
+        if pad:
+            w = torch.cat([w, w.new_zeros((pad,) + tuple(w.shape[1:]))])
+            b = torch.cat([b, b.new_zeros(pad)])
+        w_hi, w_lo, _ = L.modconv_prepare(w.contiguous(), 1.0, want_lo=self.passes == 3)
+        prep = (w_hi, w_lo, b.contiguous(), cout, cout + pad)
+        self._planes[i] = (key, prep)
+        return prep
+
+    def _scores_nhwc(self, x):
+        L.load()
+        if not x.is_cuda:
+            raise RuntimeError("ganecdotes_b200.OneShotSegmentor has no CPU path (input must be a CUDA tensor)")
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
+            raise NotImplementedError("OneShotSegmentor: the fine-tune backward is not implemented; call under "
+                                      "torch.no_grad() / .eval() for inference")
+        b, c, h, w = x.shape
+        x_nhwc = x.detach().float().permute(0, 2, 3, 1).contiguous()       # free for channels_last code maps
+        c_ld = L.pad64(c)
+        x_hi, x_lo = L._planes((b, h, w, c_ld), x.device, c_ld != c, self.passes == 3)
+        L.split_planes(x_nhwc.view(-1, c), out=(x_hi.view(-1, c_ld)[:, :c],
+                                               x_lo.view(-1, c_ld)[:, :c] if x_lo is not None else None))
+        convs = self._convs()
+        out = None
+        for n, (i, conv) in enumerate(convs):
+            w_hi, w_lo, bias, cout, cout_p = self._prepared(i, conv)
+            last = n + 1 == len(convs)
+            d = conv.dilation[0]
+            ones = None if last else torch.ones((b, cout_p), dtype=torch.float32, device=x.device)
+            out, x_hi, x_lo = L.modconv(x_hi, x_lo, w_hi, w_lo, cout_p, False, self.passes, bias=bias,
+                                        act=0 if last else 2, next_style=ones, want_next_lo=self.passes == 3,
+                                        tag="segmentor_conv", cin_true=conv.in_channels, dilation=d)
+        return out, cout                                                   # fp32 NHWC [b,h,w,cout_p]
+
+    def forward(self, x):
+        """[b, in_ch, h, w] -> class scores [b, C_out, h, w] (channels_last memory)"""
+        out, cout = self._scores_nhwc(x)
+        return out[..., :cout].permute(0, 3, 1, 2)
+
+    @torch.no_grad()
+    def predict_labels(self, x):
+        """scores + `pred.data.max(1)[1]` (src/one_shot_pipeline.py:664-665) without leaving the device:
+        int64 [b, h, w], first index on ties."""
+        out, cout = self._scores_nhwc(x)
+        b, h, w, cp = out.shape
+        return L.argmax_rows(out.view(-1, cp)[:, :cout]).view(b, h, w)

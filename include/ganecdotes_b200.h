@@ -97,7 +97,7 @@ typedef struct gx_conv_desc {
   long long noise_batch_stride; /* 0: shared across the batch                 */
   const float* noise_strength; /* device scalar (ref: NoiseInjection.weight) */
   const float* bias;           /* [Cout] or NULL                              */
-  int act;                     /* 0 none, 1 lrelu(0.2)*sqrt2                  */
+  int act;                     /* 0 none, 1 lrelu(0.2)*sqrt2, 2 lrelu(0.2) (nn.LeakyReLU, segmentor head) */
   float* out;                  /* fp32 NHWC [B,Ho,Wo,Cout]                    */
   const float* next_style;     /* [B,Cout] or NULL: also emit next conv input */
   void* next_hi;               /* bf16 NHWC [B,Ho,Wo,next_ld]                 */
@@ -105,11 +105,15 @@ typedef struct gx_conv_desc {
   int next_ld;                 /* channels per pixel of the next planes (>= cout; caller zero-fills the rest) */
   int block_n; /* 0 = auto (128 or 256) */
   int stages;  /* 0 = auto               */
+  int dilation; /* plain conv only: tap spacing d with padding d (0 = 1); ref: OneShotSegmentor's dilated
+                   Conv2d stack, hfc_with_swav/swav_clustering.py:716-742 */
 } gx_conv_desc;
 
 /* Modulated 3x3 conv as implicit GEMM on tcgen05 (TMA im2col boxes, TMEM accumulators),
  * ref: ModulatedConv2d.forward model.py:327-368 in the algebraic form
- * y = demod * conv(scale*W, s*x).  Requires cin_ld % 64 == 0 (channels zero-padded), cout % 4 == 0. */
+ * y = demod * conv(scale*W, s*x).  Requires cin_ld % 64 == 0 (channels zero-padded), cout % 4 == 0.
+ * With demod = noise = NULL and unmodulated planes it is a plain (optionally dilated) 3x3 conv + bias +
+ * activation: the layers of the one-shot segmentor head. */
 int gx_modconv(const gx_conv_desc* d, void* stream);
 
 /* Blur (upfirdn2d up=1, down=1, pad=(p0,p1)) of the transposed-conv output fused with

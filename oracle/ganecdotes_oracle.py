@@ -537,3 +537,32 @@ def kmeans_layer_maps(feats: List[torch.Tensor], centers: List[torch.Tensor], ou
         outs.append(F.interpolate(onehot, (out_size, out_size), mode="nearest") * 2 - 1)
         labels.append(lab)
     return torch.cat(outs, 1), labels
+
+
+# ----------------------------------------------------------------------------------------
+# one-shot segmentor head, inference forward (ref hfc_with_swav/swav_clustering.py:697-758)
+# ----------------------------------------------------------------------------------------
+
+SEGMENTOR_DILATIONS = {"XXS": [1], "XS": [1, 2, 1], "S": [1, 2, 1, 2, 1], "M": [1, 2, 4, 1, 2, 4, 1],
+                       "L": [1, 2, 4, 8, 1, 2, 4, 8, 1]}                  # ref :718-724
+SEGMENTOR_CHANNELS = {"XXS": [12], "XS": [16, 8], "S": [128, 64, 64, 32], "M": [128, 64, 64, 64, 64, 32],
+                      "L": [128, 64, 64, 64, 64, 64, 64, 32]}            # ref :726-732
+
+
+def segmentor_layers(in_ch, n_class, size):
+    """[(c_in, c_out, dilation, leaky_relu_after)] exactly as the reference builds them: `zip` stops at the
+    shorter list (for XXS that drops the n_class layer) and the final LeakyReLU is removed
+    (ref :733-742)."""
+    ch = [in_ch] + SEGMENTOR_CHANNELS[size] + [n_class]
+    convs = list(zip(SEGMENTOR_DILATIONS[size], ch[:-1], ch[1:]))
+    return [(ci, co, d, i + 1 < len(convs)) for i, (d, ci, co) in enumerate(convs)]
+
+
+def one_shot_segmentor(state, x, n_class, size):
+    """state: `layers.{2i}.weight/bias` (nn.Sequential of Conv2d, LeakyReLU pairs); x [b, in_ch, h, w]."""
+    y = x
+    for i, (ci, co, d, act) in enumerate(segmentor_layers(x.shape[1], n_class, size)):
+        y = F.conv2d(y, state[f"layers.{2 * i}.weight"], state[f"layers.{2 * i}.bias"], padding=d, dilation=d)
+        if act:
+            y = F.leaky_relu(y, 0.2)
+    return y

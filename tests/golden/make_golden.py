@@ -295,8 +295,36 @@ def golden_baggan():
     save("baggan", **out)
 
 
+# ---------------------------------------------------------------------------------------
+# G5: one-shot segmentor head (hfc_with_swav/swav_clustering.py:697-758), inference forward
+# ---------------------------------------------------------------------------------------
+
+def golden_segmentor():
+    """Weights and input are seeded (default nn.Conv2d init in construction order), so only the outputs and
+    a checksum of the parameters are stored: the tests rebuild both from the seeds."""
+    out = {}
+    x = torch.randn(2, 512, 24, 24, generator=torch.Generator().manual_seed(21))
+    for size, n_class in (("XXS", 5), ("XS", 6), ("S", 7)):
+        torch.manual_seed(100 + n_class)
+        net = ref.swav.OneShotSegmentor(512, n_class, size=size).eval()
+        sd = net.state_dict()
+        out[f"{size}_keys"] = np.array(list(sd.keys()))
+        out[f"{size}_shapes"] = np.array([";".join(str(d) for d in v.shape) for v in sd.values()])
+        out[f"{size}_param_sums"] = np.array([float(v.double().sum()) for v in sd.values()])
+        with torch.no_grad():
+            y = net(x)
+        out[f"{size}_y"] = y
+        out[f"{size}_labels"] = y.max(1)[1]
+        out[f"{size}_nclass"] = n_class
+    save("segmentor", **out)
+
+
 if __name__ == "__main__":
+    if len(sys.argv) > 1 and sys.argv[1] == "segmentor":
+        golden_segmentor()
+        sys.exit(0)
     golden_ops()
     golden_generator()
     golden_swav()
     golden_baggan()
+    golden_segmentor()

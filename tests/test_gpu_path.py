@@ -358,3 +358,37 @@ def test_baggan_generator_and_label_map():
         top2 = ref_p.topk(2, dim=1).values
         assert (top2[:, 0] - top2[:, 1])[mism].max().item() < 2e-3 * ref_p.abs().max().item()
     assert mism.float().mean().item() < 0.02, mism.float().mean().item()
+
+
+@pytest.mark.parametrize("size", ["XXS", "XS", "S"])
+def test_one_shot_segmentor_head_matches_reference(size):
+    """SURVEY §8(f) rank 1 (inference half): drop-in OneShotSegmentor on the tcgen05 conv kernel against the
+    outputs of the unmodified reference module (golden) - class scores and the arg-max label map."""
+    from ganecdotes_b200.hfc_with_swav import OneShotSegmentor
+    g = np.load(os.path.join(GOLD, "segmentor.npz"))
+    n_class = int(g[f"{size}_nclass"])
+    torch.manual_seed(100 + n_class)
+    net = OneShotSegmentor(512, n_class, size=size)                         # same default init, same RNG order
+    assert list(net.state_dict().keys()) == [str(k) for k in g[f"{size}_keys"]]
+    for v, ref_sum in zip(net.state_dict().values(), g[f"{size}_param_sums"]):
+        assert abs(float(v.double().sum()) - float(ref_sum)) < 1e-9
+    net = net.cuda().eval()
+    x = torch.randn(2, 512, 24, 24, generator=torch.Generator().manual_seed(21)).cuda()
+    ref = torch.from_numpy(g[f"{size}_y"])
+    with torch.no_grad():
+        y = net(x)
+        labels = net.predict_labels(x.contiguous(memory_format=torch.channels_last))
+    assert y.shape == ref.shape
+    scale = ref.abs().max().item()
+    assert (y.cpu() - ref).abs().max().item() < 2e-4 * scale
+    ref_l = torch.from_numpy(g[f"{size}_labels"])
+    assert labels.dtype == torch.int64 and labels.shape == ref_l.shape
+    mism = labels.cpu() != ref_l
+    if mism.any():      # only where the reference's own top-2 margin is inside the error band
+        top2 = ref.topk(2, dim=1).values
+        assert (top2[:, 0] - top2[:, 1])[mism].max().item() < 4e-4 * scale
+    assert mism.float().mean().item() < 0.01
+    # training with autograd is the (not yet built) second half of the row: it must fail loudly
+    net.train()
+    with pytest.raises(NotImplementedError):
+        net(x)
