@@ -1,4 +1,4 @@
-"""One configuration of the score GEMM for an ncu capture: MODE = f16 | x3 | x1"""
+"""One configuration of the score GEMM for an ncu capture: MODE = f16 (CTA pairs) | x3pair | x3 | x1"""
 import os
 import sys
 
@@ -16,7 +16,10 @@ out = torch.empty(n, k, device="cuda")
 u = torch.zeros(k, device="cuda")
 for _ in range(3):
     if mode == "f16":
-        L.gemm(z.half(), None, w.half(), None, n, k, c, 1, out=out, bias=b, colexp=(u, 20.0), force_m128=True)
+        L.gemm(z.half(), None, w.half(), None, n, k, c, 1, out=out, bias=b, colexp=(u, 20.0), pair=True)
+    elif mode == "x3pair":
+        zb, wb = z.bfloat16(), w.bfloat16()
+        L.gemm(zb, zb, wb, wb, n, k, c, 3, out=out, bias=b, colexp=(u, 20.0), pair=True)
     elif mode == "x1":
         L.gemm(z.bfloat16(), None, w.bfloat16(), None, n, k, c, 1, out=out, bias=b, force_m128=True)
     else:
