@@ -31,7 +31,8 @@ class gx_conv_desc(C.Structure):
         ("demod", C.c_void_p), ("noise", C.c_void_p), ("noise_batch_stride", C.c_longlong),
         ("noise_strength", C.c_void_p), ("bias", C.c_void_p), ("act", C.c_int),
         ("out", C.c_void_p), ("next_style", C.c_void_p), ("next_hi", C.c_void_p), ("next_lo", C.c_void_p),
-        ("next_ld", C.c_int), ("block_n", C.c_int), ("stages", C.c_int), ("dilation", C.c_int),
+        ("next_ld", C.c_int), ("block_n", C.c_int), ("stages", C.c_int), ("cluster_pair", C.c_int),
+        ("dilation", C.c_int),
     ]
 
 
@@ -337,7 +338,7 @@ def modulate_split(x_nhwc, s, batch, want_lo=True):
 
 
 def modconv(x_hi, x_lo, w_hi, w_lo, cout, upsample, passes, demod=None, noise=None, noise_strength=None, bias=None,
-            act=0, next_style=None, want_next_lo=True, block_n=0, stages=0, tag="modconv", cin_true=None, dilation=1):
+            act=0, next_style=None, want_next_lo=True, block_n=0, stages=0, tag="modconv", cin_true=None, dilation=1, pair=True):
     """Implicit-GEMM modulated conv.  x_*: [B,H,W,pad64(Cin)] bf16 planes.
     Returns (out fp32 NHWC [B,Ho,Wo,cout], next_hi, next_lo [B,Ho,Wo,pad64(cout)])."""
     lib = load()
@@ -366,6 +367,7 @@ def modconv(x_hi, x_lo, w_hi, w_lo, cout, upsample, passes, demod=None, noise=No
     d.next_ld = next_ld
     d.block_n, d.stages = block_n, stages
     d.dilation = int(dilation)
+    d.cluster_pair = int(pair)
     with timed(tag + ("_up" if upsample else ""), 2.0 * b * h * w * 9 * (cin_true or cin) * cout):
         _check(lib.gx_modconv(C.byref(d), _stream()), "gx_modconv")
     _count()

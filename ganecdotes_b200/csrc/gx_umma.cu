@@ -293,6 +293,16 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
               const CUtensorMap* mb = pl ? &tm_b_lo : &tm_b_hi;
               uint8_t* da = sa + pl * a_plane_bytes;
               uint8_t* db = sb + pl * b_plane_bytes;
+              if (p.mode == 1) {
+                // conv: this CTA's own pixel tile shifted by the tap, and its half of the weight tile
+                const int tap = kit / cblocks;
+                const int c0 = (kit - tap * cblocks) * BK;
+                const int dy = p.tap_dy[t.phase][tap], dx = p.tap_dx[t.phase][tap];
+                const int wk = p.tap_w[t.phase][tap];
+                tma_load_4d_pair(da, ma, lead_bar, c0, t.x0 + dx, t.y0 + dy, t.b0);
+                tma_load_2d_pair(db, mb, lead_bar, wk * p.Cin + c0, t.n0 + crank * half_rows);
+                continue;
+              }
               if (!p.a_mn) {
                 tma_load_2d_pair(da, ma, lead_bar, k0, t.m0);
               } else {
@@ -842,13 +852,29 @@ extern "C" int gx_modconv(const gx_conv_desc* d, void* stream) {
     p.phase_tile_start[4] = start;
   }
   p.tiles_m = p.phase_tile_start[p.nphases];
+  // CTA pairs (two adjacent pixel tiles of one phase on two SMs, half of the weight tile each): every
+  // phase gets an even number of tiles; the padding tile decodes to an image group past the batch
+  // (TMA zero fill, no stores)
+  p.pair = (d->cluster_pair && p.tiles_m >= 16) ? 1 : 0;
+  if (p.pair) {
+    int orig[5];
+    for (int ph = 0; ph <= p.nphases; ++ph) orig[ph] = p.phase_tile_start[ph];
+    int start = 0;
+    for (int ph = 0; ph < p.nphases; ++ph) {
+      p.phase_tile_start[ph] = start;
+      start += (orig[ph + 1] - orig[ph] + 1) & ~1;
+    }
+    p.phase_tile_start[p.nphases] = start;
+    p.tiles_m = start;
+  }
   // few pixel tiles (4x4 ... 16x16 layers): narrower channel tiles put more SMs on the layer, which is
   // bound by the serial K loop of a handful of CTAs otherwise
   if (d->block_n == 0) {
     while (bn > 64 && p.tiles_m * gx_cdiv(d->cout, bn) * 2 <= gx_sm_count()) bn >>= 1;
     p.block_n = bn;
-    p.stages = pick_stages(p.passes, bn, 1, d->stages);
   }
+  p.stages = pick_stages(p.passes, p.pair ? bn / 2 : bn, 1, d->stages);
+  GX_CHECK_ARG(p.stages >= 2);
   p.tiles_n = gx_cdiv(d->cout, bn);
   p.split_k = 1;
   p.demod = d->demod; p.noise = d->noise; p.noise_bstride = d->noise_batch_stride;
@@ -877,7 +903,7 @@ extern "C" int gx_modconv(const gx_conv_desc* d, void* stream) {
     if (rc != GX_OK) return rc;
     unsigned long long wd[2] = {(unsigned long long)9 * cin_ld, (unsigned long long)d->cout};
     unsigned long long ws[1] = {(unsigned long long)9 * cin_ld};
-    unsigned wb[2] = {BK, (unsigned)bn};
+    unsigned wb[2] = {BK, (unsigned)(p.pair ? bn / 2 : bn)};
     rc = make_tmap(&maps[2 + pl], wptr[pl], 2, wd, ws, wb);
     if (rc != GX_OK) return rc;
   }
@@ -885,7 +911,7 @@ extern "C" int gx_modconv(const gx_conv_desc* d, void* stream) {
     maps[1] = maps[0];
     maps[3] = maps[2];
   }
-  const int total = p.tiles_m * p.tiles_n;
+  const int total = (p.pair ? p.tiles_m / 2 : p.tiles_m) * p.tiles_n;
   return launch(p, maps, total, (cudaStream_t)stream);
 }
 

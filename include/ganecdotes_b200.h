@@ -105,6 +105,8 @@ typedef struct gx_conv_desc {
   int next_ld;                 /* channels per pixel of the next planes (>= cout; caller zero-fills the rest) */
   int block_n; /* 0 = auto (128 or 256) */
   int stages;  /* 0 = auto               */
+  int cluster_pair; /* != 0: CTA pairs (tcgen05 cta_group::2) on adjacent pixel tiles, half of the weight tile
+                       per SM (used when the layer has >= 16 pixel tiles) */
   int dilation; /* plain conv only: tap spacing d with padding d (0 = 1); ref: OneShotSegmentor's dilated
                    Conv2d stack, hfc_with_swav/swav_clustering.py:716-742 */
 } gx_conv_desc;
