@@ -826,6 +826,196 @@ swav_loss_kernel(const float* __restrict__ ss, const float* __restrict__ st, lon
 }
 
 // ---------------------------------------------------------------------------
+// Same stage when T / eps is 1 or 2 (every shipped config: eps 0.005 / 0.01, T 0.01).  Then
+//   exp(S/eps + log a_k) = exp(S/T)^RHO * a_k,
+// so the Sinkhorn code numerators are products of the softmax(S/T) numerators that are needed anyway:
+// 2 instead of 4 `ex2` per score pair, no maxima for the q branch (the common factors cancel in the row
+// normalisation), and only two register arrays per thread.  a_k is stored in shared memory divided by
+// its maximum, so every numerator is <= 1.
+// ---------------------------------------------------------------------------
+template <int J, int GT, int NT, int RHO>
+__global__ void __launch_bounds__(NT, 1)
+swav_loss_pow_kernel(const float* __restrict__ ss, const float* __restrict__ st, long long n, int k, long long lds,
+                     float inv_temp, const float* __restrict__ la_s, const float* __restrict__ la_t,
+                     float grad_scale, float* __restrict__ loss_parts, float* __restrict__ db_parts,
+                     __nv_bfloat16* __restrict__ ds_s_hi, __nv_bfloat16* __restrict__ ds_s_lo,
+                     __nv_bfloat16* __restrict__ ds_t_hi, __nv_bfloat16* __restrict__ ds_t_lo, long long ldd,
+                     float* __restrict__ ds_s_f32, float* __restrict__ ds_t_f32, int stages) {
+  constexpr int NG = NT / GT;
+  constexpr int NW = GT / 32;
+  extern __shared__ __align__(128) uint8_t sk_smem[];
+  __shared__ __align__(16) float red_max[NG][2 * NW];
+  __shared__ __align__(16) float red_sum[NG][6 * NW];
+  __shared__ float red_la[2][NT / 32];
+  __shared__ uint64_t full_bar[8];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int grp = tid / GT, gt = tid % GT, gwarp = gt >> 5;
+  const uint32_t row_bytes = (uint32_t)k * 4u;
+  const uint32_t stage_bytes = row_bytes * 2u;   // one row of S_s and one of S_t
+  if (tid == 0) {
+    for (int i = 0; i < stages; ++i) gxptx::mbar_init(&full_bar[i], 1);
+    gxptx::fence_mbar_init();
+  }
+  __syncthreads();
+  const int n_iters = (int)((n - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  auto issue = [&](int it) {
+    const int sg = it % stages;
+    const long long row = (long long)blockIdx.x + (long long)it * gridDim.x;
+    gxptx::mbar_arrive_expect_tx(&full_bar[sg], stage_bytes);
+    gxptx::bulk_load_1d(sk_smem + (size_t)sg * stage_bytes, ss + row * lds, row_bytes, &full_bar[sg]);
+    gxptx::bulk_load_1d(sk_smem + (size_t)sg * stage_bytes + row_bytes, st + row * lds, row_bytes, &full_bar[sg]);
+  };
+  if (tid == 0)
+    for (int it = 0; it < stages && it < n_iters; ++it) issue(it);
+
+  // a_k / max_k a_k of both views behind the ring (K floats each)
+  float* sa_s = reinterpret_cast<float*>(sk_smem + (size_t)stages * stage_bytes);
+  float* sa_t = sa_s + k;
+  {
+    float ms = -INFINITY, mt = -INFINITY;
+    for (int i = tid; i < k; i += NT) {
+      ms = fmaxf(ms, la_s[i]);
+      mt = fmaxf(mt, la_t[i]);
+    }
+    ms = gx_warp_max(ms);
+    mt = gx_warp_max(mt);
+    if (lane == 0) { red_la[0][tid >> 5] = ms; red_la[1][tid >> 5] = mt; }
+    __syncthreads();
+    ms = mt = -INFINITY;
+    for (int w = 0; w < NT / 32; ++w) { ms = fmaxf(ms, red_la[0][w]); mt = fmaxf(mt, red_la[1][w]); }
+    for (int i = tid; i < k; i += NT) {
+      sa_s[i] = ex2_fast((la_s[i] - ms) * LOG2E);
+      sa_t[i] = ex2_fast((la_t[i] - mt) * LOG2E);
+    }
+  }
+  __syncthreads();
+  const float ct = inv_temp * LOG2E;
+  float2 db[J][2];
+#pragma unroll
+  for (int j = 0; j < J; ++j) db[j][0] = db[j][1] = make_float2(0.f, 0.f);
+  const int col0 = gt * 4;
+  const float2 ct2 = make_float2(ct, ct);
+  float loss_acc = 0.f;
+  const float gs = grad_scale * 0.5f * inv_temp;
+  for (int it = grp; it < n_iters; it += NG) {
+    const long long row = (long long)blockIdx.x + (long long)it * gridDim.x;
+    const int sg = it % stages;
+    gxptx::mbar_wait(&full_bar[sg], (uint32_t)((it / stages) & 1));
+    const float* srow_s = reinterpret_cast<const float*>(sk_smem + (size_t)sg * stage_bytes);
+    const float* srow_t = srow_s + k;
+    float2 vs[J][2], vt[J][2];     // raw scores, later softmax(S/T) numerators
+    // pass 1: row maxima of the raw scores (clamped slots re-read valid columns)
+    float mx[2] = {-INFINITY, -INFINITY};
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int cofs = min(col0 + j * (GT * 4), k - 4);
+      const float4 a = *reinterpret_cast<const float4*>(srow_s + cofs);
+      const float4 b = *reinterpret_cast<const float4*>(srow_t + cofs);
+      vs[j][0] = make_float2(a.x, a.y); vs[j][1] = make_float2(a.z, a.w);
+      vt[j][0] = make_float2(b.x, b.y); vt[j][1] = make_float2(b.z, b.w);
+      mx[0] = fmaxf(mx[0], fmaxf(fmaxf(a.x, a.y), fmaxf(a.z, a.w)));
+      mx[1] = fmaxf(mx[1], fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
+    }
+    group_reduce<2, true, NW>(mx, red_max[grp], gwarp, lane, 1 + grp, GT);   // stage consumed after this barrier
+    if (gt == 0 && it + stages < n_iters) issue(it + stages);
+    // pass 2: sums  Z1_s, Z2_s, D_st = sum q_s*s_t, Z1_t, Z2_t, D_ts = sum q_t*s_s   (packed partials)
+    float2 s2[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) s2[i] = make_float2(0.f, 0.f);
+    const float m2s = mx[0] * ct, m2t = mx[1] * ct;   // log2 domain
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int cofs = min(col0 + j * (GT * 4), k - 4);
+      const float mskj = (col0 + j * (GT * 4) < k) ? 0.f : -INFINITY;
+      const float2 c2s = make_float2(mskj - m2s, mskj - m2s), c2t = make_float2(mskj - m2t, mskj - m2t);
+      const float4 as4 = *reinterpret_cast<const float4*>(sa_s + cofs);
+      const float4 at4 = *reinterpret_cast<const float4*>(sa_t + cofs);
+      const float2 as2[2] = {make_float2(as4.x, as4.y), make_float2(as4.z, as4.w)};
+      const float2 at2[2] = {make_float2(at4.x, at4.y), make_float2(at4.z, at4.w)};
+#pragma unroll
+      for (int h = 0; h < 2; ++h) {
+        const float2 rs = vs[j][h], rt = vt[j][h];
+        const float2 p2s = ex2_2(fma2(rs, ct2, c2s));
+        const float2 p2t = ex2_2(fma2(rt, ct2, c2t));
+        const float2 q1s = mul2(RHO == 2 ? mul2(p2s, p2s) : p2s, as2[h]);
+        const float2 q1t = mul2(RHO == 2 ? mul2(p2t, p2t) : p2t, at2[h]);
+        s2[0] = add2(s2[0], q1s);
+        s2[3] = add2(s2[3], q1t);
+        s2[2] = fma2(q1s, rt, s2[2]);
+        s2[5] = fma2(q1t, rs, s2[5]);
+        s2[1] = add2(s2[1], p2s);
+        s2[4] = add2(s2[4], p2t);
+        vs[j][h] = p2s; vt[j][h] = p2t;
+      }
+    }
+    float sm[6];
+#pragma unroll
+    for (int i = 0; i < 6; ++i) sm[i] = s2[i].x + s2[i].y;
+    group_reduce<6, false, NW>(sm, red_sum[grp], gwarp, lane, 1 + grp, GT);
+    const float iz1s = __fdividef(1.f, sm[0]), iz2s = __fdividef(1.f, sm[1]);
+    const float iz1t = __fdividef(1.f, sm[3]), iz2t = __fdividef(1.f, sm[4]);
+    if (gt == 0) {
+      const float ln2 = 0.69314718055994531f;
+      const float lse_s = (m2s + log2f(sm[1])) * ln2, lse_t = (m2t + log2f(sm[4])) * ln2;
+      const float qs_pt = sm[2] * iz1s * inv_temp - lse_t;  // sum_k q_s * log_softmax(p_t)
+      const float qt_ps = sm[5] * iz1t * inv_temp - lse_s;
+      loss_acc += -0.5f * (qs_pt + qt_ps);
+    }
+    // pass 3: gradients.  dL/dS_s uses q_t ; dL/dS_t uses q_s
+    const float2 a2s = make_float2(gs * iz2s, gs * iz2s), a1t = make_float2(-gs * iz1t, -gs * iz1t);
+    const float2 a2t = make_float2(gs * iz2t, gs * iz2t), a1s = make_float2(-gs * iz1s, -gs * iz1s);
+    __nv_bfloat16* ps_hi = ds_s_hi + row * ldd;
+    __nv_bfloat16* pt_hi = ds_t_hi + row * ldd;
+    const bool want_lo = (ds_s_lo != nullptr) || (ds_t_lo != nullptr);
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int col = col0 + j * (GT * 4);
+      if (col < k) {
+        const float4 as4 = *reinterpret_cast<const float4*>(sa_s + col);
+        const float4 at4 = *reinterpret_cast<const float4*>(sa_t + col);
+        // q numerators again from the p numerators in registers (two multiplies)
+        const float2 qs0 = mul2(RHO == 2 ? mul2(vs[j][0], vs[j][0]) : vs[j][0], mul2(make_float2(as4.x, as4.y), a1s));
+        const float2 qs1 = mul2(RHO == 2 ? mul2(vs[j][1], vs[j][1]) : vs[j][1], mul2(make_float2(as4.z, as4.w), a1s));
+        const float2 qt0 = mul2(RHO == 2 ? mul2(vt[j][0], vt[j][0]) : vt[j][0], mul2(make_float2(at4.x, at4.y), a1t));
+        const float2 qt1 = mul2(RHO == 2 ? mul2(vt[j][1], vt[j][1]) : vt[j][1], mul2(make_float2(at4.z, at4.w), a1t));
+        const float2 gs0 = fma2(vs[j][0], a2s, qt0), gs1 = fma2(vs[j][1], a2s, qt1);
+        const float2 gt0 = fma2(vt[j][0], a2t, qs0), gt1 = fma2(vt[j][1], a2t, qs1);
+        db[j][0] = add2(db[j][0], add2(gs0, gt0));
+        db[j][1] = add2(db[j][1], add2(gs1, gt1));
+        const float4 g_s = make_float4(gs0.x, gs0.y, gs1.x, gs1.y);
+        const float4 g_t = make_float4(gt0.x, gt0.y, gt1.x, gt1.y);
+        if (want_lo) {
+          uint2 h, l;
+          gx_split4(g_s, h, l);
+          *reinterpret_cast<uint2*>(ps_hi + col) = h;
+          if (ds_s_lo) *reinterpret_cast<uint2*>(ds_s_lo + row * ldd + col) = l;
+          gx_split4(g_t, h, l);
+          *reinterpret_cast<uint2*>(pt_hi + col) = h;
+          if (ds_t_lo) *reinterpret_cast<uint2*>(ds_t_lo + row * ldd + col) = l;
+        } else {
+          *reinterpret_cast<uint2*>(ps_hi + col) =
+              make_uint2(pack_bf16x2_rn(g_s.x, g_s.y), pack_bf16x2_rn(g_s.z, g_s.w));
+          *reinterpret_cast<uint2*>(pt_hi + col) =
+              make_uint2(pack_bf16x2_rn(g_t.x, g_t.y), pack_bf16x2_rn(g_t.z, g_t.w));
+        }
+        if (ds_s_f32) *reinterpret_cast<float4*>(ds_s_f32 + row * (long long)k + col) = g_s;
+        if (ds_t_f32) *reinterpret_cast<float4*>(ds_t_f32 + row * (long long)k + col) = g_t;
+      }
+    }
+  }
+  if (gt == 0) loss_parts[blockIdx.x * NG + grp] = loss_acc;
+  if (db_parts) {
+    float* prow = db_parts + ((long long)blockIdx.x * NG + grp) * k;
+#pragma unroll
+    for (int j = 0; j < J; ++j) {
+      const int col = j * (GT * 4) + gt * 4;
+      if (col < k)
+        *reinterpret_cast<float4*>(prow + col) = make_float4(db[j][0].x, db[j][0].y, db[j][1].x, db[j][1].y);
+    }
+  }
+}
+
+// ---------------------------------------------------------------------------
 // LARC + SGD(momentum)
 // ---------------------------------------------------------------------------
 __global__ void sq_norms_kernel(const float* __restrict__ p, const float* __restrict__ g, long long n,
@@ -1169,16 +1359,43 @@ static int launch_swav_loss(const float* s_s, const float* s_t, long long n, int
   if (stages > 8) stages = 8;
   stages -= stages % NG;                                   // fixed stage ownership per group (see sinkhorn pass)
   GX_CHECK_ARG(stages >= NG);   // a stage is refilled once its group holds the row in registers
-  static bool attr = false;
-  if (!attr) {
-    GX_CHECK_CUDA(cudaFuncSetAttribute(swav_loss_kernel<J, GT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       200 * 1024));
-    attr = true;
+  // exp(S/eps + log a) = exp(S/T)^rho * a when rho = T/eps is 1 or 2: half the exponentials
+  const float rho = inv_eps / inv_temp;
+  const int irho = (fabsf(rho - 2.f) < 1e-5f) ? 2 : ((fabsf(rho - 1.f) < 1e-5f) ? 1 : 0);
+  static const bool no_pow = getenv("GX_LOSS_GENERIC") != nullptr;   // profiling / tests: force the general kernel
+#define GX_LOSS_ARGS                                                                                           \
+  loss_parts, db_parts, reinterpret_cast<__nv_bfloat16*>(ds_s_hi), reinterpret_cast<__nv_bfloat16*>(ds_s_lo),    \
+      reinterpret_cast<__nv_bfloat16*>(ds_t_hi), reinterpret_cast<__nv_bfloat16*>(ds_t_lo), ldd, fs, ft, stages
+  const size_t smem = (size_t)(stages + 1) * stage_bytes;
+  if (irho == 2 && !no_pow) {
+    static bool attr2 = false;
+    if (!attr2) {
+      GX_CHECK_CUDA(cudaFuncSetAttribute(swav_loss_pow_kernel<J, GT, NT, 2>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr2 = true;
+    }
+    swav_loss_pow_kernel<J, GT, NT, 2><<<grid, NT, smem, st>>>(s_s, s_t, n, k, lds, inv_temp, la_s, la_t, grad_scale,
+                                                              GX_LOSS_ARGS);
+  } else if (irho == 1 && !no_pow) {
+    static bool attr1 = false;
+    if (!attr1) {
+      GX_CHECK_CUDA(cudaFuncSetAttribute(swav_loss_pow_kernel<J, GT, NT, 1>,
+                                         cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+      attr1 = true;
+    }
+    swav_loss_pow_kernel<J, GT, NT, 1><<<grid, NT, smem, st>>>(s_s, s_t, n, k, lds, inv_temp, la_s, la_t, grad_scale,
+                                                              GX_LOSS_ARGS);
+  } else {
+    static bool attr = false;
+    if (!attr) {
+      GX_CHECK_CUDA(cudaFuncSetAttribute(swav_loss_kernel<J, GT, NT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         200 * 1024));
+      attr = true;
+    }
+    swav_loss_kernel<J, GT, NT><<<grid, NT, smem, st>>>(s_s, s_t, n, k, lds, inv_eps, inv_temp, la_s, la_t,
+                                                       grad_scale, GX_LOSS_ARGS);
   }
-  swav_loss_kernel<J, GT, NT><<<grid, NT, (stages + 1) * stage_bytes, st>>>(
-      s_s, s_t, n, k, lds, inv_eps, inv_temp, la_s, la_t, grad_scale, loss_parts, db_parts,
-      reinterpret_cast<__nv_bfloat16*>(ds_s_hi), reinterpret_cast<__nv_bfloat16*>(ds_s_lo),
-      reinterpret_cast<__nv_bfloat16*>(ds_t_hi), reinterpret_cast<__nv_bfloat16*>(ds_t_lo), ldd, fs, ft, stages);
+#undef GX_LOSS_ARGS
   return GX_OK;
 }
 

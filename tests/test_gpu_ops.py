@@ -474,20 +474,23 @@ def test_sinkhorn_golden_and_image_pdf(L):
     torch.testing.assert_close(q.cpu(), ref, rtol=2e-3, atol=1e-9)
 
 
-@pytest.mark.parametrize("n,k", [(40, 24), (257, 5000), (300, 1500), (1000, 3000), (90, 8192)])
-def test_swav_loss_fwd_bwd_vs_oracle(L, n, k):
+@pytest.mark.parametrize("n,k,temp", [(40, 24, 0.01), (257, 5000, 0.01), (300, 1500, 0.01), (1000, 3000, 0.01),
+                                      (90, 8192, 0.01), (257, 5000, 0.005), (257, 5000, 0.013), (64, 520, 0.02)])
+def test_swav_loss_fwd_bwd_vs_oracle(L, n, k, temp):
+    """temp / eps = 2 and 1 take the kernel that derives the Sinkhorn code numerators from the softmax(S/T)
+    numerators (exp(S/eps + log a) = exp(S/T)^rho * a); other ratios the general kernel."""
     from ganecdotes_b200.hfc_with_swav import engine as E
     torch.manual_seed(n)
     s_s = (0.05 * torch.randn(n, k)).requires_grad_(True)
     s_t = (0.05 * torch.randn(n, k)).requires_grad_(True)
     q_s = O.sinkhorn_knopp(s_s.detach(), 10, 0.005)
     q_t = O.sinkhorn_knopp(s_t.detach(), 10, 0.005)
-    loss = O.swapped_prediction_loss(s_s / 0.01, s_t / 0.01, q_s, q_t)
+    loss = O.swapped_prediction_loss(s_s / temp, s_t / temp, q_s, q_t)
     loss.backward()
     ws = L.SinkhornWorkspace(k, "cuda")
     la_s = E.sinkhorn_log_a(s_s.detach().cuda(), 10, 0.005, ws, n)
     la_t = E.sinkhorn_log_a(s_t.detach().cuda(), 10, 0.005, ws, n)
-    parts, ds_s, ds_t, db, f32 = L.swav_loss(s_s.detach().cuda(), s_t.detach().cuda(), 200.0, 100.0, la_s, la_t,
+    parts, ds_s, ds_t, db, f32 = L.swav_loss(s_s.detach().cuda(), s_t.detach().cuda(), 200.0, 1.0 / temp, la_s, la_t,
                                               1.0 / n, want_lo=True, want_f32=True)
     got = parts.sum().item() / n
     assert abs(got - loss.item()) < 2e-4 * abs(loss.item()) + 1e-5, (got, loss.item())
