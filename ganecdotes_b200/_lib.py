@@ -86,8 +86,9 @@ _SIGNATURES = {
     "gx_round_f16": ([_P, _LL, _P, _LL, _LL, _P], _I),
     "gx_l2norm_bwd_split": ([_P, _P, _P, _P, _P, _P, _P, _LL, _I, _P], _I),
     "gx_segment_sum_rows": ([_P, _P, _P, _P, _P, _P, _LL, _I, _P], _I),
-    "gx_upsample_sum": ([_I, _P, _P, _P, _I, _I, _I, _I, _P, _P], _I),
+    "gx_upsample_sum": ([_I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P], _I),
     "gx_pool_sum": ([_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P], _I),
+    "gx_tap_sum": ([_P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _I, _P], _I),
     "gx_normalize_rows": ([_P, _LL, _I, _P], _I),
     "gx_sinkhorn_max_parts": ([], _I),
     "gx_sinkhorn_pass": ([_P, _LL, _I, _LL, _F, _I, _P, _P, _P, _LL, _P, C.POINTER(_I), _P], _I),
@@ -552,7 +553,7 @@ def segment_sum_rows(rows, order, seg_off, nseg, want_lo=False, want_planes=True
     return hi, lo, f
 
 
-def upsample_sum(parts, batch, out_h, out_w, out=None):
+def upsample_sum(parts, batch, out_h, out_w, out=None, planes=None):
     """parts: list of fp32 [batch, h_l, w_l, c] tensors -> fp32 [batch*out_h*out_w, c]"""
     lib = load()
     n = len(parts)
@@ -567,9 +568,28 @@ def upsample_sum(parts, batch, out_h, out_w, out=None):
     assert out.is_contiguous() and out.numel() == batch * out_h * out_w * c
     nbytes = 4.0 * c * (sum(p.shape[0] * p.shape[1] * p.shape[2] for p in parts) + batch * out_h * out_w)
     with timed("upsample_sum", nbytes):
-        _check(lib.gx_upsample_sum(n, ptrs, hs, ws, batch, out_h, out_w, c, _ptr(out), _stream()), "gx_upsample_sum")
+        hi, lo = planes if planes is not None else (None, None)
+        _check(lib.gx_upsample_sum(n, ptrs, hs, ws, batch, out_h, out_w, c, _ptr(out), _ptr(hi), _ptr(lo), _stream()),
+               "gx_upsample_sum")
     _count()
     return out
+
+
+def tap_sum(g, batch, h, w, cout, dilation, bias, act, want_out=True, want_planes=False, want_lo=True):
+    """g fp32 [batch*h*w, 9*cout] -> (out fp32 [batch,h,w,cout] or None, hi, lo [batch,h,w,pad64(cout)] or None)"""
+    lib = load()
+    _f32(g, "g"), _f32(bias, "bias")
+    dev = g.device
+    out = torch.empty((batch, h, w, cout), dtype=torch.float32, device=dev) if want_out else None
+    hi = lo = None
+    next_ld = pad64(cout)
+    if want_planes:
+        hi, lo = _planes((batch, h, w, next_ld), dev, next_ld != cout, want_lo)
+    with timed("tap_sum", 4.0 * batch * h * w * cout * 10):
+        _check(lib.gx_tap_sum(_ptr(g), batch, h, w, cout, int(dilation), _ptr(bias), int(act), _ptr(out), _ptr(hi),
+                              _ptr(lo), next_ld, _stream()), "gx_tap_sum")
+    _count()
+    return out, hi, lo
 
 
 def pool_sum(x_nhwc, out_h, out_w, want_f32=True, want_planes=True, want_lo=False):

@@ -227,7 +227,8 @@ struct UpsumDesc {
   int out_h, out_w, c;
   long long npix;   // B*out_h*out_w
 };
-__global__ void upsample_sum_kernel(const UpsumDesc d, float* __restrict__ out) {
+__global__ void upsample_sum_kernel(const UpsumDesc d, float* __restrict__ out, __nv_bfloat16* __restrict__ hi,
+                                    __nv_bfloat16* __restrict__ lo) {
   const int lane = threadIdx.x & 31;
   const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (pix >= d.npix) return;
@@ -256,7 +257,58 @@ __global__ void upsample_sum_kernel(const UpsumDesc d, float* __restrict__ out) 
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       const int i = lane + 32 * j;
-      if (c0 + i < cq) gx_stg_stream(reinterpret_cast<float4*>(out + pix * d.c) + c0 + i, acc[j]);
+      if (c0 + i < cq) {
+        if (out) gx_stg_stream(reinterpret_cast<float4*>(out + pix * d.c) + c0 + i, acc[j]);
+        if (hi) {      // operand planes of a consumer conv / GEMM, emitted in the same pass
+          uint2 h, l;
+          gx_split4(acc[j], h, l);
+          reinterpret_cast<uint2*>(hi + pix * d.c)[c0 + i] = h;
+          if (lo) reinterpret_cast<uint2*>(lo + pix * d.c)[c0 + i] = l;
+        }
+      }
+    }
+  }
+}
+
+// 3x3 (dilated) conv with few output channels as ONE GEMM + a stencil sum: G[pix, tap*cout + co] =
+// x[pix,:] . W[co,:,tap] for all nine taps at once (the input is read once instead of nine times), then
+// out[y,x,co] = act(bias[co] + sum_tap G[(y,x) + offset(tap), tap*cout + co]) with zeros outside the image.
+__global__ void tap_sum_kernel(const float* __restrict__ g, int batch, int h, int w, int cout, int dil,
+                               const float* __restrict__ bias, int act, float* __restrict__ out,
+                               __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo, int next_ld) {
+  const int cq = cout >> 2;
+  const long long total = (long long)batch * h * w * cq;
+  const long long ldg = 9LL * cout;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % cq);
+    const long long pix = i / cq;
+    const int x = (int)(pix % w);
+    const int y = (int)((pix / w) % h);
+    float4 acc = bias ? __ldg(reinterpret_cast<const float4*>(bias) + q) : make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < 3; ++ky) {
+      const int yy = y + (ky - 1) * dil;
+      if (yy < 0 || yy >= h) continue;
+#pragma unroll
+      for (int kx = 0; kx < 3; ++kx) {
+        const int xx = x + (kx - 1) * dil;
+        if (xx < 0 || xx >= w) continue;
+        const long long np = pix + (long long)(yy - y) * w + (xx - x);
+        const float4 v = __ldg(reinterpret_cast<const float4*>(g + np * ldg + (ky * 3 + kx) * cout) + q);
+        acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      }
+    }
+    if (act == 2) {
+      acc.x = acc.x > 0.f ? acc.x : acc.x * 0.2f; acc.y = acc.y > 0.f ? acc.y : acc.y * 0.2f;
+      acc.z = acc.z > 0.f ? acc.z : acc.z * 0.2f; acc.w = acc.w > 0.f ? acc.w : acc.w * 0.2f;
+    }
+    if (out) reinterpret_cast<float4*>(out + pix * cout)[q] = acc;
+    if (hi) {
+      uint2 hh, ll;
+      gx_split4(acc, hh, ll);
+      reinterpret_cast<uint2*>(hi + pix * next_ld)[q] = hh;
+      if (lo) reinterpret_cast<uint2*>(lo + pix * next_ld)[q] = ll;
     }
   }
 }
@@ -1177,8 +1229,9 @@ extern "C" int gx_segment_sum_rows(const float* rows, const int* order, const in
 }
 
 extern "C" int gx_upsample_sum(int nlevels, const float* const* p, const int* h, const int* w, int batch, int out_h,
-                               int out_w, int c, float* out, void* stream) {
-  GX_CHECK_ARG(nlevels > 0 && nlevels <= GX_MAX_LEVELS && p && h && w && out && batch > 0 && c % 4 == 0);
+                               int out_w, int c, float* out, void* hi, void* lo, void* stream) {
+  GX_CHECK_ARG(nlevels > 0 && nlevels <= GX_MAX_LEVELS && p && h && w && (out || hi) && batch > 0 && c % 4 == 0);
+  GX_CHECK_ARG(lo == nullptr || hi != nullptr);
   UpsumDesc d;
   d.nlevels = nlevels;
   for (int l = 0; l < nlevels; ++l) {
@@ -1187,7 +1240,25 @@ extern "C" int gx_upsample_sum(int nlevels, const float* const* p, const int* h,
   }
   d.out_h = out_h; d.out_w = out_w; d.c = c;
   d.npix = (long long)batch * out_h * out_w;
-  upsample_sum_kernel<<<gx_cdiv(d.npix, 8), 256, 0, (cudaStream_t)stream>>>(d, out);
+  upsample_sum_kernel<<<gx_cdiv(d.npix, 8), 256, 0, (cudaStream_t)stream>>>(
+      d, out, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo));
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_tap_sum(const float* g, int batch, int h, int w, int cout, int dilation, const float* bias, int act,
+                          float* out, void* next_hi, void* next_lo, int next_ld, void* stream) {
+  GX_CHECK_ARG(g && (out || next_hi) && batch > 0 && h > 0 && w > 0 && cout > 0 && cout % 4 == 0 && dilation >= 1);
+  GX_CHECK_ARG(act == 0 || act == 2);
+  GX_CHECK_ARG(next_lo == nullptr || next_hi != nullptr);
+  GX_CHECK_ARG(next_hi == nullptr || (next_ld >= cout && next_ld % 4 == 0));
+  const long long total = (long long)batch * h * w * (cout / 4);
+  int grid = gx_cdiv(total, 256);
+  const int cap = gx_sm_count() * 32;
+  if (grid > cap) grid = cap;
+  tap_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, batch, h, w, cout, dilation, bias, act, out,
+                                                         reinterpret_cast<__nv_bfloat16*>(next_hi),
+                                                         reinterpret_cast<__nv_bfloat16*>(next_lo), next_ld);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }

@@ -338,7 +338,8 @@ def resolution_groups(feats, hlen):
     return groups
 
 
-def project_all_pixels(wp_hi, wp_lo, feats, batch, out_h, out_w, hlen, passes, want_hi_only_planes=False, out=None):
+def project_all_pixels(wp_hi, wp_lo, feats, batch, out_h, out_w, hlen, passes, want_hi_only_planes=False, out=None,
+                       out_planes=None):
     """Z[pixel] = Wp . (nearest-upsampled, concatenated feature vector of the pixel) for EVERY
     pixel of `batch` images.  Upsampling and projection are both linear, so
     Z = sum_r upsample(F_r Wp[:, cols_r]^T): each resolution is projected at its native size
@@ -363,9 +364,10 @@ def project_all_pixels(wp_hi, wp_lo, feats, batch, out_h, out_w, hlen, passes, w
         parts.append(p.view(batch, g["h"], g["w"], c))
         levels.append(dict(a_hi=a_hi, a_lo=None if want_hi_only_planes else a_lo, h=g["h"], w=g["w"], off=g["off"],
                            keep=g["keep"]))
-    if len(parts) == 1 and parts[0].shape[1] == out_h and parts[0].shape[2] == out_w and out is None:
+    if len(parts) == 1 and parts[0].shape[1] == out_h and parts[0].shape[2] == out_w and out is None \
+            and out_planes is None:
         return parts[0].view(-1, c), levels
-    z = L.upsample_sum(parts, batch, out_h, out_w, out=out)
+    z = L.upsample_sum(parts, batch, out_h, out_w, out=out, planes=out_planes)
     return z, levels
 
 
@@ -636,10 +638,12 @@ def swav_train_step(gen, head: SwavHead, mean_latent, draws: StepDraws, cfg: Ste
 
 
 @torch.no_grad()
-def predict_codes(gen, w_proj, w, mean_latent, truncation, hlen, passes=3, images_per_chunk=4):
+def predict_codes(gen, w_proj, w, mean_latent, truncation, hlen, passes=3, images_per_chunk=4, want_planes=False):
     """predict_swav_codes (ref :659-693): generator forward with the fixed noise buffers,
     per-pixel vectors, projection only, arg-max over the code channels.
-    Returns (codes [B,C,H,W] fp32 in channels_last memory, labels int64 [B,H,W])."""
+    Returns (codes [B,C,H,W] fp32 in channels_last memory, labels int64 [B,H,W]); with want_planes also the
+    bf16 (hi, lo) planes [B*H*W, C] of the codes (operand of the one-shot segmentor head), emitted by the
+    same kernel that writes the codes."""
     if hlen % 8:
         raise ValueError("hlen must be a multiple of 8 (16-byte TMA row pitch of the bf16 operand planes)")
     dev = w_proj.device
@@ -654,11 +658,18 @@ def predict_codes(gen, w_proj, w, mean_latent, truncation, hlen, passes=3, image
     wp_hi, wp_lo = L.split_planes(w_proj.contiguous(), want_lo=passes == 3)
     z = torch.empty((b * h * wd, c), dtype=torch.float32, device=dev)
     labels = torch.empty((b * h * wd,), dtype=torch.int64, device=dev)
+    z_hi = z_lo = None
+    if want_planes:
+        z_hi = torch.empty((b * h * wd, c), dtype=torch.bfloat16, device=dev)
+        z_lo = torch.empty_like(z_hi)
     for i0 in range(0, b, images_per_chunk):
         i1 = min(b, i0 + images_per_chunk)
         sub = [f[i0:i1] for f in feats]
         zc = z[i0 * h * wd: i1 * h * wd]
-        project_all_pixels(wp_hi, wp_lo, sub, i1 - i0, h, wd, hlen, passes, out=zc)
+        pl = (z_hi[i0 * h * wd: i1 * h * wd], z_lo[i0 * h * wd: i1 * h * wd]) if want_planes else None
+        project_all_pixels(wp_hi, wp_lo, sub, i1 - i0, h, wd, hlen, passes, out=zc, out_planes=pl)
         labels[i0 * h * wd: i1 * h * wd] = L.argmax_rows(zc)
     preds = z.view(b, h, wd, c).permute(0, 3, 1, 2)
+    if want_planes:
+        return preds, labels.view(b, h, wd), (z_hi, z_lo)
     return preds, labels.view(b, h, wd)

@@ -48,24 +48,36 @@ class OneShotSegmentor(nn.Module):
         return [(i, m) for i, m in enumerate(self.layers) if isinstance(m, nn.Conv2d)]
 
     def _prepared(self, i, conv):
-        """bf16 operand planes of one conv, output channels zero-padded to a multiple of 4"""
+        """bf16 operand planes of one conv, output channels zero-padded to a multiple of 4.
+        Few output channels (9 * cout <= 256): all nine taps become columns of ONE GEMM operand
+        [9 * cout, cin] and the conv is that GEMM + `gx_tap_sum` (the input is read once, not nine times);
+        otherwise the implicit-GEMM conv kernel's [cout, 9 * cin] layout."""
         key = (conv.weight._version, conv.bias._version, conv.weight.data_ptr())
         hit = self._planes.get(i)
         if hit is not None and hit[0] == key:
             return hit[1]
         w = conv.weight.detach().float()
         b = conv.bias.detach().float()
-        cout = w.shape[0]
+        cout, cin = w.shape[0], w.shape[1]
         pad = (-cout) % 4
         if pad:
             w = torch.cat([w, w.new_zeros((pad,) + tuple(w.shape[1:]))])
             b = torch.cat([b, b.new_zeros(pad)])
-        w_hi, w_lo, _ = L.modconv_prepare(w.contiguous(), 1.0, want_lo=self.passes == 3)
-        prep = (w_hi, w_lo, b.contiguous(), cout, cout + pad)
+        cout_p = cout + pad
+        want_lo = self.passes == 3
+        if 9 * cout_p <= 256:
+            cin_ld = L.pad64(cin)
+            wall = w.new_zeros((9 * cout_p, cin_ld))
+            wall[:, :cin] = w.permute(2, 3, 0, 1).reshape(9 * cout_p, cin)       # row = (ky*3 + kx) * cout + co
+            w_hi, w_lo = L.split_planes(wall, want_lo=want_lo)
+            prep = ("taps", w_hi, w_lo, b.contiguous(), cout, cout_p)
+        else:
+            w_hi, w_lo, _ = L.modconv_prepare(w.contiguous(), 1.0, want_lo=want_lo)
+            prep = ("conv", w_hi, w_lo, b.contiguous(), cout, cout_p)
         self._planes[i] = (key, prep)
         return prep
 
-    def _scores_nhwc(self, x):
+    def _scores_nhwc(self, x, planes=None):
         L.load()
         if not x.is_cuda:
             raise RuntimeError("ganecdotes_b200.OneShotSegmentor has no CPU path (input must be a CUDA tensor)")
@@ -73,21 +85,32 @@ class OneShotSegmentor(nn.Module):
             raise NotImplementedError("OneShotSegmentor: the fine-tune backward is not implemented; call under "
                                       "torch.no_grad() / .eval() for inference")
         b, c, h, w = x.shape
-        x_nhwc = x.detach().float().permute(0, 2, 3, 1).contiguous()       # free for channels_last code maps
         c_ld = L.pad64(c)
-        x_hi, x_lo = L._planes((b, h, w, c_ld), x.device, c_ld != c, self.passes == 3)
-        L.split_planes(x_nhwc.view(-1, c), out=(x_hi.view(-1, c_ld)[:, :c],
-                                               x_lo.view(-1, c_ld)[:, :c] if x_lo is not None else None))
+        want_lo = self.passes == 3
+        if planes is not None and c_ld == c:          # operand planes emitted by the producer of x
+            x_hi, x_lo = planes[0].view(b, h, w, c), (planes[1].view(b, h, w, c) if want_lo else None)
+        else:
+            x_nhwc = x.detach().float().permute(0, 2, 3, 1).contiguous()   # free for channels_last code maps
+            x_hi, x_lo = L._planes((b, h, w, c_ld), x.device, c_ld != c, want_lo)
+            L.split_planes(x_nhwc.view(-1, c), out=(x_hi.view(-1, c_ld)[:, :c],
+                                                   x_lo.view(-1, c_ld)[:, :c] if x_lo is not None else None))
         convs = self._convs()
         out = None
         for n, (i, conv) in enumerate(convs):
-            w_hi, w_lo, bias, cout, cout_p = self._prepared(i, conv)
+            kind, w_hi, w_lo, bias, cout, cout_p = self._prepared(i, conv)
             last = n + 1 == len(convs)
             d = conv.dilation[0]
-            ones = None if last else torch.ones((b, cout_p), dtype=torch.float32, device=x.device)
-            out, x_hi, x_lo = L.modconv(x_hi, x_lo, w_hi, w_lo, cout_p, False, self.passes, bias=bias,
-                                        act=0 if last else 2, next_style=ones, want_next_lo=self.passes == 3,
-                                        tag="segmentor_conv", cin_true=conv.in_channels, dilation=d)
+            if kind == "taps":
+                npix, k_ld = b * h * w, x_hi.shape[3]
+                g = L.gemm(x_hi.view(npix, k_ld), x_lo.view(npix, k_ld) if want_lo else None, w_hi, w_lo, npix,
+                           9 * cout_p, k_ld, self.passes, tag="segmentor_taps_gemm", pair=True)
+                out, x_hi, x_lo = L.tap_sum(g, b, h, w, cout_p, d, bias, 0 if last else 2, want_out=last,
+                                            want_planes=not last, want_lo=want_lo)
+            else:
+                ones = None if last else torch.ones((b, cout_p), dtype=torch.float32, device=x.device)
+                out, x_hi, x_lo = L.modconv(x_hi, x_lo, w_hi, w_lo, cout_p, False, self.passes, bias=bias,
+                                            act=0 if last else 2, next_style=ones, want_next_lo=want_lo,
+                                            tag="segmentor_conv", cin_true=conv.in_channels, dilation=d)
         return out, cout                                                   # fp32 NHWC [b,h,w,cout_p]
 
     def forward(self, x):
@@ -96,9 +119,10 @@ class OneShotSegmentor(nn.Module):
         return out[..., :cout].permute(0, 3, 1, 2)
 
     @torch.no_grad()
-    def predict_labels(self, x):
+    def predict_labels(self, x, planes=None):
         """scores + `pred.data.max(1)[1]` (src/one_shot_pipeline.py:664-665) without leaving the device:
-        int64 [b, h, w], first index on ties."""
-        out, cout = self._scores_nhwc(x)
+        int64 [b, h, w], first index on ties.  `planes`: the bf16 (hi, lo) planes of x when its producer
+        (`engine.predict_codes(..., want_planes=True)`) already emitted them."""
+        out, cout = self._scores_nhwc(x, planes)
         b, h, w, cp = out.shape
         return L.argmax_rows(out.view(-1, cp)[:, :cout]).view(b, h, w)

@@ -228,9 +228,19 @@ int gx_segment_sum_rows(const float* rows, const int* order, const int* seg_off,
 
 /* Z[b,y,x,:] = sum_l P_l[b, y*h_l/out_h, x*w_l/out_w, :] (fp32 NHWC, c channels).  By linearity the
  * projection of the nearest-upsampled + concatenated per-pixel vector (ref swav_clustering.py:108-130,
- * :171) is the sum of per-level projections computed at each level's native resolution. */
+ * :171) is the sum of per-level projections computed at each level's native resolution.
+ * hi / lo (optional, out may then be NULL): the same values as bf16 split planes [batch*out_h*out_w, c]. */
 int gx_upsample_sum(int nlevels, const float* const* p, const int* h, const int* w, int batch, int out_h,
-                    int out_w, int c, float* out, void* stream);
+                    int out_w, int c, float* out, void* hi, void* lo, void* stream);
+
+/* Second half of a 3x3 (dilated, padding = dilation) conv with few output channels computed as one GEMM
+ * over all nine taps: g [batch*h*w, 9*cout] with column tap*cout + co (tap = ky*3 + kx);
+ * out[b,y,x,co] = act(bias[co] + sum_tap g[(y + (ky-1)*dilation, x + (kx-1)*dilation), tap*cout + co]),
+ * zeros outside the image; act 0 none, 2 lrelu(0.2).  out fp32 NHWC and / or bf16 split planes with
+ * next_ld channels per pixel for the next layer (caller zero-fills [cout, next_ld)).  cout % 4 == 0.
+ * ref: the Conv2d + LeakyReLU layers of OneShotSegmentor, hfc_with_swav/swav_clustering.py:733-742. */
+int gx_tap_sum(const float* g, int batch, int h, int w, int cout, int dilation, const float* bias, int act,
+               float* out, void* next_hi, void* next_lo, int next_ld, void* stream);
 
 /* out[b,y,x,:] = sum of the (in_h/out_h x in_w/out_w) block of `in` - the adjoint of nearest upsampling,
  * used to fold dZ onto a level's native resolution; fp32 out and/or bf16 planes (any may be NULL). */

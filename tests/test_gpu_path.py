@@ -378,6 +378,9 @@ def test_one_shot_segmentor_head_matches_reference(size):
     with torch.no_grad():
         y = net(x)
         labels = net.predict_labels(x.contiguous(memory_format=torch.channels_last))
+        from ganecdotes_b200 import _lib as L
+        planes = L.split_planes(x.permute(0, 2, 3, 1).reshape(-1, 512).contiguous(), want_lo=True)
+        assert torch.equal(labels, net.predict_labels(x, planes))          # operand planes handed over by the producer
     assert y.shape == ref.shape
     scale = ref.abs().max().item()
     assert (y.cpu() - ref).abs().max().item() < 2e-4 * scale

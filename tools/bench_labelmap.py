@@ -26,8 +26,8 @@ def main():
         w = gen.style(torch.randn(b, 512).cuda())
 
     def step():
-        preds, _ = E.predict_codes(gen, wp, w, mean_latent, 0.7, 5376)
-        return head.predict_labels(preds)
+        preds, _, planes = E.predict_codes(gen, wp, w, mean_latent, 0.7, 5376, want_planes=True)
+        return head.predict_labels(preds, planes)
 
     for _ in range(3):
         labels = step()
@@ -54,8 +54,8 @@ def main():
     for _ in range(5):
         with torch.no_grad():
             w2 = gen.style(zs.cuda(non_blocking=True))
-        preds, _ = E.predict_codes(gen, wp, w2, mean_latent, 0.7, 5376)
-        host = head.predict_labels(preds).cpu()
+        preds, _, planes = E.predict_codes(gen, wp, w2, mean_latent, 0.7, 5376, want_planes=True)
+        host = head.predict_labels(preds, planes).cpu()
     dt = (time.perf_counter() - t0) / 5
     # CPU port, one image
     from oracle import ganecdotes_oracle as O
