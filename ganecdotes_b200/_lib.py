@@ -89,6 +89,7 @@ _SIGNATURES = {
     "gx_upsample_sum": ([_I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P], _I),
     "gx_pool_sum": ([_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P], _I),
     "gx_tap_sum": ([_P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _I, _P], _I),
+    "gx_tap_spread": ([_P, _I, _I, _I, _I, _I, _P, _P, _P], _I),
     "gx_normalize_rows": ([_P, _LL, _I, _P], _I),
     "gx_sinkhorn_max_parts": ([], _I),
     "gx_sinkhorn_pass": ([_P, _LL, _I, _LL, _F, _I, _P, _P, _P, _LL, _P, C.POINTER(_I), _P], _I),
@@ -590,6 +591,20 @@ def tap_sum(g, batch, h, w, cout, dilation, bias, act, want_out=True, want_plane
                               _ptr(lo), next_ld, _stream()), "gx_tap_sum")
     _count()
     return out, hi, lo
+
+
+def tap_spread(dout_nhwc, dilation, want_lo=True):
+    """dout fp32 [b,h,w,cout] -> bf16 planes [b*h*w, 9*cout] (adjoint of tap_sum)"""
+    lib = load()
+    _f32(dout_nhwc, "dout")
+    b, h, w, cout = dout_nhwc.shape
+    hi = torch.empty((b * h * w, 9 * cout), dtype=torch.bfloat16, device=dout_nhwc.device)
+    lo = torch.empty_like(hi) if want_lo else None
+    with timed("tap_spread", float(b) * h * w * cout * (4 + 9 * (4 if want_lo else 2))):
+        _check(lib.gx_tap_spread(_ptr(dout_nhwc), b, h, w, cout, int(dilation), _ptr(hi), _ptr(lo), _stream()),
+               "gx_tap_spread")
+    _count()
+    return hi, lo
 
 
 def pool_sum(x_nhwc, out_h, out_w, want_f32=True, want_planes=True, want_lo=False):

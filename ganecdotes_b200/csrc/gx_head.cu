@@ -313,6 +313,34 @@ __global__ void tap_sum_kernel(const float* __restrict__ g, int batch, int h, in
   }
 }
 
+// Adjoint of tap_sum: dG[q, tap*cout + co] = dOut[q - offset(tap), co] (zero outside the image), emitted
+// as bf16 split planes - the operand of the weight-gradient GEMM dW_all = dG^T X and of dX = dG W_all.
+__global__ void tap_spread_kernel(const float* __restrict__ dout, int batch, int h, int w, int cout, int dil,
+                                  __nv_bfloat16* __restrict__ hi, __nv_bfloat16* __restrict__ lo) {
+  const int cq = cout >> 2;
+  const long long total = (long long)batch * h * w * 9 * cq;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
+       i += (long long)gridDim.x * blockDim.x) {
+    const int q = (int)(i % cq);
+    const int tap = (int)((i / cq) % 9);
+    const long long pix = i / (9 * cq);
+    const int x = (int)(pix % w);
+    const int y = (int)((pix / w) % h);
+    const int ky = tap / 3, kx = tap - 3 * ky;
+    const int yy = y - (ky - 1) * dil, xx = x - (kx - 1) * dil;
+    float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+    if (yy >= 0 && yy < h && xx >= 0 && xx < w) {
+      const long long sp = pix + (long long)(yy - y) * w + (xx - x);
+      v = __ldg(reinterpret_cast<const float4*>(dout + sp * cout) + q);
+    }
+    uint2 hh, ll;
+    gx_split4(v, hh, ll);
+    const long long o = (pix * 9 + tap) * cq + q;
+    reinterpret_cast<uint2*>(hi)[o] = hh;
+    if (lo) reinterpret_cast<uint2*>(lo)[o] = ll;
+  }
+}
+
 // out[b,y,x,:] = sum of the f x f block of in (f = H/h): the adjoint of nearest upsampling; also
 // emitted as bf16 planes (operand of the per-level weight-gradient GEMM).  Warp per output pixel.
 __global__ void pool_sum_kernel(const float* __restrict__ in, int H, int W, int h, int w, int c, long long nout,
@@ -1259,6 +1287,20 @@ extern "C" int gx_tap_sum(const float* g, int batch, int h, int w, int cout, int
   tap_sum_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(g, batch, h, w, cout, dilation, bias, act, out,
                                                          reinterpret_cast<__nv_bfloat16*>(next_hi),
                                                          reinterpret_cast<__nv_bfloat16*>(next_lo), next_ld);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_tap_spread(const float* dout, int batch, int h, int w, int cout, int dilation, void* dg_hi,
+                             void* dg_lo, void* stream) {
+  GX_CHECK_ARG(dout && dg_hi && batch > 0 && h > 0 && w > 0 && cout > 0 && cout % 4 == 0 && dilation >= 1);
+  const long long total = (long long)batch * h * w * 9 * (cout / 4);
+  int grid = gx_cdiv(total, 256);
+  const int cap = gx_sm_count() * 32;
+  if (grid > cap) grid = cap;
+  tap_spread_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(dout, batch, h, w, cout, dilation,
+                                                            reinterpret_cast<__nv_bfloat16*>(dg_hi),
+                                                            reinterpret_cast<__nv_bfloat16*>(dg_lo));
   GX_LAUNCH_CHECK();
   return GX_OK;
 }

@@ -11,8 +11,11 @@ unmodulated planes, bias + LeakyReLU in the epilogue, next layer's operand plane
 epilogue), on the NHWC code map `predict_swav_codes` produces - nothing goes back to the host, where the
 reference runs this head (`.to('cpu')`, src/one_shot_pipeline.py:610,662).
 
-Not here yet (second half): the one-shot fine-tune loop needs the weight gradients
-of these convs; calling the module with autograd enabled on parameters that require grad raises.
+Fine-tuning (src/one_shot_pipeline.py:540-578: CE loss + Adam through `self.segmentor(features)`): layers
+with few output channels (9 * C_out <= 256 - every layer of the shipped sizes 'XXS' and 'XS') are autograd
+functions whose backward is two more GEMMs on the same operands: dW_all = dG^T X (MN-major, split-K) and
+dX = dG W_all, with dG the 9-tap spread of the output gradient (`gx_tap_spread`).  Sizes with wider hidden
+layers ('S', 'M', 'L') run inference only; training them raises.
 """
 import torch
 import torch.nn as nn
@@ -23,6 +26,67 @@ _DILATIONS = {'XXS': [1], 'XS': [1, 2, 1], 'S': [1, 2, 1, 2, 1], 'M': [1, 2, 4, 
               'L': [1, 2, 4, 8, 1, 2, 4, 8, 1]}
 _CHANNELS = {'XXS': [12], 'XS': [16, 8], 'S': [128, 64, 64, 32], 'M': [128, 64, 64, 64, 64, 32],
              'L': [128, 64, 64, 64, 64, 64, 64, 32]}
+
+
+def _wall(weight, bias, cout_p, cin_ld):
+    """[cout,cin,3,3] -> W_all [9*cout_p, cin_ld] fp32 with row (ky*3+kx)*cout_p + co, bias padded to cout_p"""
+    cout, cin = weight.shape[0], weight.shape[1]
+    w = weight.detach().float()
+    if cout_p != cout:
+        w = torch.cat([w, w.new_zeros((cout_p - cout,) + tuple(w.shape[1:]))])
+    wall = w.new_zeros((9 * cout_p, cin_ld))
+    wall[:, :cin] = w.permute(2, 3, 0, 1).reshape(9 * cout_p, cin)
+    b = bias.detach().float()
+    if cout_p != cout:
+        b = torch.cat([b, b.new_zeros(cout_p - cout)])
+    return wall, b.contiguous()
+
+
+class _TapsConv(torch.autograd.Function):
+    """3x3 (dilated) conv + bias (+ LeakyReLU 0.2) with few output channels, NHWC fp32 in / out, as one 9-tap
+    GEMM + stencil sum; the backward re-uses the GEMM kernel on the saved operand planes."""
+
+    @staticmethod
+    def forward(ctx, x_nhwc, weight, bias, dilation, act):
+        b, h, w, cin = x_nhwc.shape
+        cout = weight.shape[0]
+        cout_p, cin_ld = (cout + 7) // 8 * 8, L.pad64(cin)
+        npix = b * h * w
+        x_hi, x_lo = L._planes((npix, cin_ld), x_nhwc.device, cin_ld != cin, True)
+        L.split_planes(x_nhwc.detach().float().contiguous().view(npix, cin), out=(x_hi[:, :cin], x_lo[:, :cin]))
+        wall, bias_p = _wall(weight, bias, cout_p, cin_ld)
+        w_hi, w_lo = L.split_planes(wall, want_lo=True)
+        g = L.gemm(x_hi, x_lo, w_hi, w_lo, npix, 9 * cout_p, cin_ld, 3, tag="segmentor_taps_gemm", pair=True)
+        out, _, _ = L.tap_sum(g, b, h, w, cout_p, dilation, bias_p, 2 if act else 0)
+        ctx.save_for_backward(x_hi, x_lo, wall, out if act else None)
+        ctx.meta = (b, h, w, cin, cout, cout_p, cin_ld, int(dilation), bool(act))
+        return out[..., :cout]
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        x_hi, x_lo, wall, out = ctx.saved_tensors
+        b, h, w, cin, cout, cout_p, cin_ld, dilation, act = ctx.meta
+        npix = b * h * w
+        g = grad_out.float()
+        if cout_p != cout:
+            g = torch.cat([g, g.new_zeros((b, h, w, cout_p - cout))], dim=3)
+        if act:
+            g = g * torch.where(out > 0, 1.0, 0.2)
+        g = g.contiguous()
+        db = g.sum(dim=(0, 1, 2))[:cout]
+        dg_hi, dg_lo = L.tap_spread(g, dilation)
+        dwall = torch.zeros((9 * cout_p, cin_ld), dtype=torch.float32, device=g.device)
+        kit = (npix + 63) // 64
+        sk = max(1, min(64, kit // 8))
+        L.gemm(dg_hi, dg_lo, x_hi, x_lo, 9 * cout_p, cin_ld, npix, 3, out=dwall, a_mn=True, b_mn=True, split_k=sk,
+               accumulate=True, tag="segmentor_dw_gemm", pair=True)
+        dweight = dwall[:, :cin].reshape(3, 3, cout_p, cin)[:, :, :cout].permute(2, 3, 0, 1).contiguous()
+        dx = None
+        if ctx.needs_input_grad[0]:
+            wt_hi, wt_lo = L.split_planes(wall, transpose=True, want_lo=True)      # [cin_ld, 9*cout_p]
+            dxp = L.gemm(dg_hi, dg_lo, wt_hi, wt_lo, npix, cin_ld, 9 * cout_p, 3, tag="segmentor_dx_gemm", pair=True)
+            dx = dxp[:, :cin].reshape(b, h, w, cin)
+        return dx, dweight, db, None, None
 
 
 class OneShotSegmentor(nn.Module):
@@ -81,9 +145,6 @@ class OneShotSegmentor(nn.Module):
         L.load()
         if not x.is_cuda:
             raise RuntimeError("ganecdotes_b200.OneShotSegmentor has no CPU path (input must be a CUDA tensor)")
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()) and self.training:
-            raise NotImplementedError("OneShotSegmentor: the fine-tune backward is not implemented; call under "
-                                      "torch.no_grad() / .eval() for inference")
         b, c, h, w = x.shape
         c_ld = L.pad64(c)
         want_lo = self.passes == 3
@@ -113,8 +174,24 @@ class OneShotSegmentor(nn.Module):
                                             tag="segmentor_conv", cin_true=conv.in_channels, dilation=d)
         return out, cout                                                   # fp32 NHWC [b,h,w,cout_p]
 
+    def _train_forward(self, x):
+        """autograd path of the one-shot fine-tune loop"""
+        L.load()
+        if not x.is_cuda:
+            raise RuntimeError("ganecdotes_b200.OneShotSegmentor has no CPU path (input must be a CUDA tensor)")
+        y = x.float().permute(0, 2, 3, 1)
+        convs = self._convs()
+        for n, (i, conv) in enumerate(convs):
+            if 9 * ((conv.out_channels + 7) // 8 * 8) > 256:
+                raise NotImplementedError(f"OneShotSegmentor(size={self.size!r}): the fine-tune backward exists for "
+                                          "layers with 9 * C_out <= 256 ('XXS', 'XS'); this size is inference only")
+            y = _TapsConv.apply(y, conv.weight, conv.bias, conv.dilation[0], n + 1 < len(convs))
+        return y.permute(0, 3, 1, 2)
+
     def forward(self, x):
         """[b, in_ch, h, w] -> class scores [b, C_out, h, w] (channels_last memory)"""
+        if torch.is_grad_enabled() and (x.requires_grad or any(p.requires_grad for p in self.parameters())):
+            return self._train_forward(x)
         out, cout = self._scores_nhwc(x)
         return out[..., :cout].permute(0, 3, 1, 2)
 

@@ -242,6 +242,12 @@ int gx_upsample_sum(int nlevels, const float* const* p, const int* h, const int*
 int gx_tap_sum(const float* g, int batch, int h, int w, int cout, int dilation, const float* bias, int act,
                float* out, void* next_hi, void* next_lo, int next_ld, void* stream);
 
+/* Adjoint of gx_tap_sum for the fine-tune backward of those layers: dg[pix, tap*cout + co] =
+ * dout[pix - offset(tap), co] (zero outside the image) as bf16 split planes [batch*h*w, 9*cout].
+ * Then dW_all [9*cout, cin] = dg^T x (one MN-major split-K GEMM) and dx = dg W_all. */
+int gx_tap_spread(const float* dout, int batch, int h, int w, int cout, int dilation, void* dg_hi, void* dg_lo,
+                  void* stream);
+
 /* out[b,y,x,:] = sum of the (in_h/out_h x in_w/out_w) block of `in` - the adjoint of nearest upsampling,
  * used to fold dZ onto a level's native resolution; fp32 out and/or bf16 planes (any may be NULL). */
 int gx_pool_sum(const float* in, int batch, int in_h, int in_w, int out_h, int out_w, int c, float* out, void* hi,

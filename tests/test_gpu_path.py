@@ -391,7 +391,38 @@ def test_one_shot_segmentor_head_matches_reference(size):
         top2 = ref.topk(2, dim=1).values
         assert (top2[:, 0] - top2[:, 1])[mism].max().item() < 4e-4 * scale
     assert mism.float().mean().item() < 0.01
-    # training with autograd is the (not yet built) second half of the row: it must fail loudly
-    net.train()
-    with pytest.raises(NotImplementedError):
-        net(x)
+    if size == "S":     # wider hidden layers: inference only, training must fail loudly
+        net.train()
+        with pytest.raises(NotImplementedError):
+            net(x)
+
+
+@pytest.mark.parametrize("size", ["XXS", "XS"])
+def test_one_shot_segmentor_finetune_gradients(size):
+    """SURVEY §8(f) rank 1, second half: one fine-tune step's gradients (CE loss through the segmentor,
+    src/one_shot_pipeline.py:559-570) against torch autograd of the same conv stack in fp64 (F.conv2d)."""
+    from ganecdotes_b200.hfc_with_swav import OneShotSegmentor
+    n_class = 6
+    torch.manual_seed(5)
+    net = OneShotSegmentor(512, n_class, size=size).cuda().train()
+    x = torch.randn(2, 512, 20, 28, generator=torch.Generator().manual_seed(8)).cuda()
+    ref_state = {k: v.detach().double().cpu().requires_grad_(True) for k, v in net.state_dict().items()}
+    y_ref = O.one_shot_segmentor(ref_state, x.double().cpu(), n_class, size)
+    labels = torch.randint(0, y_ref.shape[1], (2, 20, 28), generator=torch.Generator().manual_seed(9))
+    loss_ref = torch.nn.functional.cross_entropy(y_ref, labels)
+    loss_ref.backward()
+    y = net(x)
+    assert y.requires_grad and y.shape == y_ref.shape
+    loss = torch.nn.functional.cross_entropy(y, labels.cuda())
+    assert abs(loss.item() - loss_ref.item()) < 1e-4 * abs(loss_ref.item())
+    loss.backward()
+    for name, p in net.named_parameters():
+        gref = ref_state[name].grad.float()
+        rel = (p.grad.cpu() - gref).norm().item() / gref.norm().item()
+        assert rel < 2e-3, (name, rel)
+    # an Adam step through the public module works end to end
+    opt = torch.optim.Adam(net.parameters(), lr=1e-3)
+    opt.step()
+    with torch.no_grad():
+        loss2 = torch.nn.functional.cross_entropy(net.eval()(x), labels.cuda())
+    assert loss2.item() < loss.item()
