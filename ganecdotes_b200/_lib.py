@@ -101,7 +101,7 @@ _SIGNATURES = {
                       _P], _I),
     "gx_larc_sgd": ([_P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _P, _P], _I),
     "gx_argmax_rows": ([_P, _LL, _I, _LL, _P, _P], _I),
-    "gx_kmeans_assign": ([_P, _I, _P, _I, _LL, _P, _I, _P, _P], _I),
+    "gx_kmeans_assign": ([_P, _I, _P, _I, _LL, _P, _I, _P, _P, _P], _I),
     "gx_onehot_nearest": ([_P, _I, _I, _I, _I, _I, _I, _P, _P], _I),
 }
 
@@ -719,8 +719,9 @@ def argmax_rows(x):
     return labels
 
 
-def kmeans_assign(x, centers, x2=None):
-    """x [n,c1] (+ x2 [n,c2]) fp32 contiguous, centers [k,c1+c2] -> int32 labels [n]"""
+def kmeans_assign(x, centers, x2=None, want_dist=False):
+    """x [n,c1] (+ x2 [n,c2]) fp32 contiguous, centers [k,c1+c2] -> int32 labels [n]
+    (with want_dist: (labels, squared distance to the assigned centre [n]))"""
     lib = load()
     _f32(centers, "centers"), _f32(x, "x"), _f32(x2, "x2")
     n, c1 = x.shape
@@ -728,10 +729,11 @@ def kmeans_assign(x, centers, x2=None):
     if centers.shape[1] != c1 + c2:
         raise GxError("kmeans_assign: centers must have c1+c2 columns")
     labels = torch.empty((n,), dtype=torch.int32, device=x.device)
+    dist = torch.empty((n,), dtype=torch.float32, device=x.device) if want_dist else None
     _check(lib.gx_kmeans_assign(_ptr(x), c1, _ptr(x2), c2, n, _ptr(centers), centers.shape[0], _ptr(labels),
-                                _stream()), "gx_kmeans_assign")
+                                _ptr(dist), _stream()), "gx_kmeans_assign")
     _count()
-    return labels
+    return (labels, dist) if want_dist else labels
 
 
 def onehot_nearest(labels_bhw, k, out_h, out_w):

@@ -1162,7 +1162,7 @@ __global__ void argmax_rows_kernel(const float* __restrict__ x, long long n, int
 // resolution are never concatenated in memory
 __global__ void kmeans_assign_kernel(const float* __restrict__ x1, int c1, const float* __restrict__ x2, int c2,
                                      long long n, const float* __restrict__ centers, int k,
-                                     int* __restrict__ labels) {
+                                     int* __restrict__ labels, float* __restrict__ dist) {
   const int lane = threadIdx.x & 31;
   const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= n) return;
@@ -1185,7 +1185,10 @@ __global__ void kmeans_assign_kernel(const float* __restrict__ x1, int c1, const
     d = gx_warp_sum(d);
     if (d < best) { best = d; bi = kk; }
   }
-  if (lane == 0) labels[row] = bi;
+  if (lane == 0) {
+    if (labels) labels[row] = bi;
+    if (dist) dist[row] = best;      // squared distance to the assigned centre (k-means fit: inertia, k-means++)
+  }
 }
 
 // one-hot cluster maps resized with nearest neighbour (ref hfc_kmeans_clustering.py:190-206)
@@ -1595,10 +1598,11 @@ extern "C" int gx_argmax_rows(const float* x, long long n, int c, long long ldx,
 }
 
 extern "C" int gx_kmeans_assign(const float* x1, int c1, const float* x2, int c2, long long n, const float* centers,
-                                int k, int* labels, void* stream) {
-  GX_CHECK_ARG(x1 && centers && labels && n > 0 && c1 > 0 && k > 0 && c2 >= 0);
+                                int k, int* labels, float* dist, void* stream) {
+  GX_CHECK_ARG(x1 && centers && (labels || dist) && n > 0 && c1 > 0 && k > 0 && c2 >= 0);
   GX_CHECK_ARG((x2 != nullptr) == (c2 > 0));
-  kmeans_assign_kernel<<<gx_cdiv(n, 8), 256, 0, (cudaStream_t)stream>>>(x1, c1, x2, c2, n, centers, k, labels);
+  kmeans_assign_kernel<<<gx_cdiv(n, 8), 256, 0, (cudaStream_t)stream>>>(x1, c1, x2, c2, n, centers, k, labels,
+                                                                        dist);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }

@@ -313,9 +313,11 @@ int gx_argmax_rows(const float* x, long long n, int c, long long ldx, long long*
 
 /* k-means assignment: labels[n] = first argmin_k ||x_n - c_k||^2 with x_n = concat(x1[n,:c1], x2[n,:c2])
  * (the two same-resolution maps the reference concatenates, image_augmentor.py:80-90; x2 may be NULL)
- * (ref: clusterer.predict, baseline/hfc_kmeans/hfc_kmeans_clustering.py:184).  centers [k,c1+c2]; int32 out. */
+ * (ref: clusterer.predict, baseline/hfc_kmeans/hfc_kmeans_clustering.py:184).  centers [k,c1+c2]; int32 out.
+ * dist (optional, labels may then be NULL): squared distance to the assigned centre - inertia and the
+ * k-means++ potentials of the Lloyd fit (ref: KMeans.fit, hfc_kmeans_clustering.py:146-166). */
 int gx_kmeans_assign(const float* x1, int c1, const float* x2, int c2, long long n, const float* centers, int k,
-                     int* labels, void* stream);
+                     int* labels, float* dist, void* stream);
 
 /* one-hot cluster maps [b,k,out_h,out_w] from labels [b,h,w], nearest-neighbour resize
  * (ref: hfc_kmeans_clustering.py:190-206). */

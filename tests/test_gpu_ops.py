@@ -564,3 +564,28 @@ def test_split_planes(L):
     assert (hi.float() + lo.float() - x).abs().max().item() < 2e-5 * x.abs().max().item()
     hi_t, lo_t = L.split_planes(x, transpose=True)
     assert torch.equal(hi_t, hi.t().contiguous()) and torch.equal(lo_t, lo.t().contiguous())
+
+
+def test_kmeans_fit_statistical_parity_with_sklearn(L):
+    """Lloyd + greedy k-means++ on the GPU.  scikit-learn's fit depends on its version and
+    RNG, so parity is statistical: the inertia of the fit is within a few percent of scikit-learn's on the same
+    data, and the structural properties of a Lloyd fixed point hold exactly."""
+    from sklearn.cluster import KMeans
+    from ganecdotes_b200.hfc_kmeans.hfc_kmeans_clustering import kmeans_fit
+    rs = np.random.RandomState(0)
+    k, c, n = 16, 96, 6000
+    true_c = rs.randn(k, c) * 3
+    x = (true_c[rs.randint(k, size=n)] + rs.randn(n, c)).astype(np.float32)
+    ref = KMeans(n_clusters=k, n_init=1, random_state=0).fit(x)
+    xg = torch.from_numpy(x).cuda()
+    cen, labels, inertia, n_iter = kmeans_fit(xg[:, :64].contiguous(), k, seed=0, x2=xg[:, 64:].contiguous())
+    assert cen.shape == (k, c) and labels.dtype == torch.int32 and n_iter >= 1
+    assert abs(inertia - ref.inertia_) < 0.03 * ref.inertia_, (inertia, ref.inertia_)
+    # fixed-point properties: labels are the nearest centres, centres are the means of their points
+    d = torch.cdist(xg.double(), cen.double())
+    assert (labels.long() == d.argmin(1)).float().mean().item() > 0.999
+    for j in range(k):
+        m = labels == j
+        if m.any():
+            torch.testing.assert_close(cen[j], xg[m].mean(0), rtol=1e-3, atol=1e-3)
+    torch.testing.assert_close(torch.tensor(inertia), (d.min(1).values ** 2).sum().float().cpu(), rtol=1e-3, atol=0)
