@@ -3,7 +3,9 @@
 Mirrors `fused_leaky_relu(input, bias, negative_slope=0.2, scale=2**0.5)` and
 `FusedLeakyReLU(channel, ...)` of the reference (models/stylegan2/op/fused_act.py:11-40,
 models/stylegan2/model.py:15-43, lib/gan/optim/fused_act.py:171-253) and the pybind op
-`fused_bias_act` (lib/gan/optim/fused_bias_act.cpp:18-36).  Forward only.
+`fused_bias_act` (lib/gan/optim/fused_bias_act.cpp:18-36).  Differentiable to second order like the
+reference's FusedLeakyReLUFunction / ...Backward pair (lib/gan/optim/fused_act.py:27-167): the gradient
+modes (`grad=1`: multiply by the slope selected by the sign of the saved output) run on the same kernel.
 Bias is broadcast on dim 1; for 3-D inputs the `op/` variant of the reference
 broadcasts on the last dim (op/fused_act.py:26-32) - selected with `bias_last=True`.
 """
@@ -32,8 +34,52 @@ def fused_bias_act(input, bias, refer, act, grad, alpha, scale):
     return out if input.dtype == torch.float32 else out.to(input.dtype)
 
 
+def _bias_grad(g, channel_dim_size):
+    """sum over every dim but the channel dim (dim 1)"""
+    dims = [0] + list(range(2, g.dim()))
+    return g.sum(dim=dims) if g.dim() > 1 else g
+
+
+class _FusedLReLU(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, x, bias, negative_slope, scale):
+        out = fused_bias_act(x, bias, None, 3, 0, negative_slope, scale)
+        ctx.save_for_backward(out)
+        ctx.cfg = (negative_slope, scale, bias is not None)
+        return out
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (out,) = ctx.saved_tensors
+        negative_slope, scale, has_bias = ctx.cfg
+        gx, gb = _FusedLReLUGrad.apply(grad_out, out, negative_slope, scale)
+        return gx, (gb if has_bias else None), None, None
+
+
+class _FusedLReLUGrad(torch.autograd.Function):
+    """dx = dy * scale * (out > 0 ? 1 : slope),  db = sum over non-channel dims of dx"""
+
+    @staticmethod
+    def forward(ctx, grad_out, out, negative_slope, scale):
+        gx = fused_bias_act(grad_out.contiguous(), None, out, 3, 1, negative_slope, scale)
+        ctx.save_for_backward(out)
+        ctx.cfg = (negative_slope, scale)
+        return gx, _bias_grad(gx, out.shape[1] if out.dim() > 1 else 1)
+
+    @staticmethod
+    def backward(ctx, gg_x, gg_b):
+        (out,) = ctx.saved_tensors
+        negative_slope, scale = ctx.cfg
+        # linear in grad_out: the same map applied to (gg_x + gg_b broadcast); no dependence on `out` a.e.
+        gg = fused_bias_act(gg_x.contiguous(), gg_b, out, 3, 1, negative_slope, scale)
+        return gg, None, None, None
+
+
 def fused_leaky_relu(input, bias=None, negative_slope=0.2, scale=2 ** 0.5, bias_last=False):
     x = input.contiguous()
+    needs_grad = torch.is_grad_enabled() and (input.requires_grad or (bias is not None and bias.requires_grad))
+    if needs_grad and not (bias is not None and bias_last and x.dim() == 3):
+        return _FusedLReLU.apply(x, bias, negative_slope, scale)
     if bias is not None and bias_last and x.dim() == 3:
         # op/fused_act.py:26-32: bias on the last dim of a 3-D input
         shp = x.shape

@@ -3,8 +3,10 @@
 Mirrors `upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0))` of the reference
 (models/stylegan2/op/upfirdn2d.py:11-16, models/stylegan2/model.py:46-58,
 lib/gan/optim/upfirdn2d.py:146-162): `up`/`down` int or (x, y), `pad` a 2-tuple applied
-to both axes or a 4-tuple (x0, x1, y0, y1).  Forward only (the clustering path runs
-the generator under no_grad); a new tensor is returned and the input is untouched.
+to both axes or a 4-tuple (x0, x1, y0, y1).  A new tensor is returned and the input is untouched.
+Differentiable to any order like the reference's UpFirDn2d / UpFirDn2dBackward pair
+(lib/gan/optim/upfirdn2d.py:17-143): the adjoint of an upfirdn is the upfirdn with the flipped filter,
+up and down exchanged and complementary padding, so backward and double backward run on the same kernel.
 Errors surface as RuntimeError like the reference's TORCH_CHECKs
 (lib/gan/optim/upfirdn2d.cpp:9-15).
 """
@@ -39,6 +41,47 @@ def upfirdn2d_native_layout(input, kernel, up_x, up_y, down_x, down_y, pad_x0, p
     return out if input.dtype == torch.float32 else out.to(input.dtype)
 
 
+class _UpFirDn(torch.autograd.Function):
+    """y = upfirdn(x; k, up, down, pad) on [major, h, w, 1] tensors; params = (up_x, up_y, down_x, down_y,
+    pad_x0, pad_x1, pad_y0, pad_y1)."""
+
+    @staticmethod
+    def forward(ctx, x, kernel, params):
+        ctx.save_for_backward(kernel)
+        ctx.params = params
+        ctx.in_hw = (x.shape[1], x.shape[2])
+        return upfirdn2d_native_layout(x.contiguous(), kernel, *params)
+
+    @staticmethod
+    def backward(ctx, grad_out):
+        (kernel,) = ctx.saved_tensors
+        return _UpFirDnAdjoint.apply(grad_out, kernel, ctx.params, ctx.in_hw), None, None
+
+
+class _UpFirDnAdjoint(torch.autograd.Function):
+    """x_bar = upfirdn^T(y_bar): the upfirdn with the flipped filter, up <-> down, and the padding that maps
+    the output grid back onto the in_h x in_w input grid."""
+
+    @staticmethod
+    def forward(ctx, grad_out, kernel, params, in_hw):
+        up_x, up_y, down_x, down_y, px0, px1, py0, py1 = params
+        kh, kw = kernel.shape
+        in_h, in_w = in_hw
+        out_h, out_w = grad_out.shape[1], grad_out.shape[2]
+        adj = (down_x, down_y, up_x, up_y,
+               kw - px0 - 1, in_w * up_x - out_w * down_x + px0 - up_x + 1,
+               kh - py0 - 1, in_h * up_y - out_h * down_y + py0 - up_y + 1)
+        ctx.save_for_backward(kernel)
+        ctx.params = params
+        return upfirdn2d_native_layout(grad_out.contiguous(), torch.flip(kernel, [0, 1]).contiguous(), *adj)
+
+    @staticmethod
+    def backward(ctx, gg_in):
+        (kernel,) = ctx.saved_tensors
+        # the adjoint of the adjoint is the forward map
+        return _UpFirDn.apply(gg_in, kernel, ctx.params), None, None, None
+
+
 def upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0)):
     up_x, up_y = _pair(up)
     down_x, down_y = _pair(down)
@@ -51,5 +94,8 @@ def upfirdn2d(input, kernel, up=1, down=1, pad=(0, 0)):
         raise RuntimeError("upfirdn2d: expected a [N,C,H,W] input")
     n, c, h, w = input.shape
     x = input.contiguous().reshape(n * c, h, w, 1)
-    out = upfirdn2d_native_layout(x, kernel.contiguous(), up_x, up_y, down_x, down_y, *pad)
+    if torch.is_grad_enabled() and input.requires_grad:
+        out = _UpFirDn.apply(x, kernel.detach().contiguous(), (up_x, up_y, down_x, down_y) + tuple(int(p) for p in pad))
+    else:
+        out = upfirdn2d_native_layout(x, kernel.contiguous(), up_x, up_y, down_x, down_y, *pad)
     return out.view(n, c, out.shape[1], out.shape[2])

@@ -589,3 +589,48 @@ def test_kmeans_fit_statistical_parity_with_sklearn(L):
         if m.any():
             torch.testing.assert_close(cen[j], xg[m].mean(0), rtol=1e-3, atol=1e-3)
     torch.testing.assert_close(torch.tensor(inertia), (d.min(1).values ** 2).sum().float().cpu(), rtol=1e-3, atol=0)
+
+
+def test_upfirdn2d_and_fused_lrelu_backward_and_double_backward(L):
+    """the ops are differentiable to second order like the reference's autograd pairs
+    (lib/gan/optim/upfirdn2d.py:17-143, fused_act.py:27-167); checked against torch autograd of the native
+    formulas (the oracle's upfirdn2d / fused_leaky_relu)."""
+    from ganecdotes_b200.stylegan2.op import upfirdn2d, fused_leaky_relu
+    torch.manual_seed(0)
+    k = torch.tensor([1., 3., 3., 1.])
+    k2 = (k[:, None] * k[None, :] / 64).cuda()
+    for up, down, pad in [(1, 1, (2, 1)), (2, 1, (2, 1)), (1, 2, (1, 1)), (2, 2, (1, 2, 0, 1))]:
+        x = torch.randn(2, 3, 9, 11, device="cuda", requires_grad=True)
+        xr = x.detach().clone().requires_grad_(True)
+        y = upfirdn2d(x, k2, up=up, down=down, pad=pad)
+        yr = O.upfirdn2d(xr, k2, up=(up, up), down=(down, down), pad=pad if len(pad) == 4 else (pad[0], pad[1], pad[0], pad[1]))
+        torch.testing.assert_close(y, yr, rtol=1e-5, atol=1e-5)
+        g = torch.randn_like(y)
+        (gx,) = torch.autograd.grad(y, x, g, create_graph=True)
+        (gxr,) = torch.autograd.grad(yr, xr, g, create_graph=True)
+        torch.testing.assert_close(gx, gxr, rtol=1e-4, atol=1e-5)
+        # double backward: d/dg <gx, v> = upfirdn(v)
+        v = torch.randn_like(gx)
+        g2 = g.clone().requires_grad_(True)
+        (gx2,) = torch.autograd.grad(upfirdn2d(x, k2, up=up, down=down, pad=pad), x, g2, create_graph=True)
+        (gg,) = torch.autograd.grad(gx2, g2, v)
+        torch.testing.assert_close(gg, upfirdn2d(v, k2, up=up, down=down, pad=pad).detach(), rtol=1e-4, atol=1e-5)
+    # fused leaky relu
+    x = torch.randn(4, 6, 5, 7, device="cuda", requires_grad=True)
+    b = torch.randn(6, device="cuda", requires_grad=True)
+    xr, br = x.detach().clone().requires_grad_(True), b.detach().clone().requires_grad_(True)
+    y = fused_leaky_relu(x, b)
+    yr = O.fused_leaky_relu(xr, br)
+    torch.testing.assert_close(y, yr, rtol=1e-6, atol=1e-6)
+    g = torch.randn_like(y)
+    gx, gb = torch.autograd.grad(y, (x, b), g, create_graph=True)
+    gxr, gbr = torch.autograd.grad(yr, (xr, br), g)
+    torch.testing.assert_close(gx, gxr, rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(gb, gbr, rtol=1e-4, atol=1e-5)
+    # second order: gx is linear in g with the same slopes
+    g2 = g.clone().requires_grad_(True)
+    gx2, gb2 = torch.autograd.grad(fused_leaky_relu(x, b), (x, b), g2, create_graph=True)
+    v = torch.randn_like(gx2)
+    (gg,) = torch.autograd.grad(gx2, g2, v)
+    slope = torch.where(y.detach() > 0, 1.0, 0.2) * 2 ** 0.5
+    torch.testing.assert_close(gg, v * slope, rtol=1e-5, atol=1e-6)
