@@ -533,13 +533,15 @@ def _tensors_of(inp: StepInputs):
 
 
 @torch.no_grad()
-def view_wplus_device(gen, w, mean_latent, truncation, layer_no, pert_rows, perturb_std):
-    """`view_wplus` on device-resident draws (pert_rows [2B, D])."""
+def view_wplus_device(gen, w, mean_latent, truncation, layer_no, pert_rows, perturb_std, noise_w=None):
+    """`view_wplus` on device-resident draws (pert_rows [2B, D]); `noise_w`: style(pert_rows) if the caller
+    already ran the mapping network on them."""
     b, d = w.shape
     mean = mean_latent.reshape(-1).float().contiguous()
     wt = L.truncate(w.float().contiguous(), mean, truncation) if truncation < 1 else w
     wplus = wt.unsqueeze(1).repeat(1, gen.n_latent, 1).contiguous()
-    noise_w = gen.style(pert_rows.float().contiguous())
+    if noise_w is None:
+        noise_w = gen.style(pert_rows.float().contiguous())
     for i in range(b):
         l = layer_no[i]
         sg = float(perturb_std[l])
@@ -566,7 +568,11 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
     head.zero_grad()
     ws = ws or L.SinkhornWorkspace(head.k, dev)
 
-    w = gen.style(inp.z.float().contiguous())
+    # one pass of the mapping network over the latents and both views' perturbation draws
+    pert_s, pert_t = inp.views["s"][1], inp.views["t"][1]
+    styled = gen.style(torch.cat([inp.z.float(), pert_s.float(), pert_t.float()]).contiguous())
+    w = styled[:b].contiguous()
+    noise_ws = {"s": styled[b:b + pert_s.shape[0]], "t": styled[b + pert_s.shape[0]:]}
     feats = {}
     out_h = out_w = gen.size
     dedup = inp.dedup is not None
@@ -576,7 +582,8 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
     n_patch_rows = b * (cfg.patch_size if cfg.patch_size is not None else out_h * out_w)
     for name in ("s", "t"):
         layer_no, pert_rows = inp.views[name]
-        wplus = view_wplus_device(gen, w, mean_latent, cfg.truncation, layer_no, pert_rows, cfg.perturb_std)
+        wplus = view_wplus_device(gen, w, mean_latent, cfg.truncation, layer_no, pert_rows, cfg.perturb_std,
+                                  noise_ws[name])
         _, f = gen.synthesize(wplus, None, need_image=cfg.need_image)
         feats[name] = f
         if dedup:
