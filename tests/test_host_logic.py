@@ -1,0 +1,72 @@
+"""CPU tests of the host-side logic around the kernels (no device): resolution grouping of the feature
+pyramid, split-K choice, the all-pixel (dedup) decision, segmentor layer construction."""
+import types
+
+import pytest
+import torch
+
+from ganecdotes_b200.hfc_with_swav import engine as E
+
+
+def _feats(size, chans):
+    """NHWC feature list of a StyleGAN2 pyramid: one map at 4x4, two per further resolution"""
+    out, r = [], 4
+    out.append(torch.zeros(1, r, r, chans[0]))
+    for c in chans[1:]:
+        r *= 2
+        out += [torch.zeros(1, r, r, c), torch.zeros(1, r, r, c)]
+    assert r == size
+    return out
+
+
+def test_resolution_groups_ffhq_and_sliced():
+    feats = _feats(256, [512, 512, 512, 512, 512, 256, 128])
+    g = E.resolution_groups(feats, 5376)
+    assert [(x["h"], x["keep"], x["off"]) for x in g] == [(4, 512, 0), (8, 1024, 512), (16, 1024, 1536),
+                                                          (32, 1024, 2560), (64, 1024, 3584), (128, 512, 4608),
+                                                          (256, 256, 5120)]
+    assert sum(x["keep"] for x in g) == 5376 and all(len(x["maps"]) in (1, 2) for x in g)
+    # car-512: the 512^2 maps fall outside hlen; a cut inside a resolution keeps a partial map
+    feats = _feats(512, [512, 512, 512, 512, 512, 256, 128, 64])
+    g = E.resolution_groups(feats, 5376)
+    assert g[-1]["h"] == 256 and sum(x["keep"] for x in g) == 5376
+    g = E.resolution_groups(feats, 5376 - 200)
+    assert g[-1]["h"] == 256 and g[-1]["keep"] == 56 and len(g[-1]["maps"]) == 1
+    g = E.resolution_groups(feats, 5376 + 72)
+    assert g[-1]["h"] == 512 and g[-1]["keep"] == 72 and len(g[-1]["maps"]) == 2
+
+
+def test_pick_split_k_fills_the_grid():
+    for tiles, kit in [(40, 2500), (20, 313), (2, 79), (300, 100)]:
+        s = E.pick_split_k(tiles, kit, 148)
+        assert 1 <= s <= max(1, kit // 8)
+        work = tiles * s
+        eff = work / (148 * -(-work // 148))
+        assert eff >= 0.5 or s == max(1, min(64, kit // 8))       # at least half of the last wave busy
+
+
+def test_all_pixel_projection_decision():
+    cfg = types.SimpleNamespace(dedup=None, patch_size=20000, num_patches=5)
+    assert E.use_dedup(cfg, 256, 256)                      # ffhq: 5 x 20000 samples over 65536 pixels
+    cfg = types.SimpleNamespace(dedup=None, patch_size=1000, num_patches=2)
+    assert not E.use_dedup(cfg, 256, 256)                  # a small fraction of the image: gather rows instead
+    cfg = types.SimpleNamespace(dedup=None, patch_size=None, num_patches=1)
+    assert E.use_dedup(cfg, 512, 512)                      # full-image Sinkhorn problem
+    cfg = types.SimpleNamespace(dedup=False, patch_size=None, num_patches=1)
+    assert not E.use_dedup(cfg, 512, 512)                  # explicit override
+
+
+@pytest.mark.parametrize("size,n_class,expect", [
+    ("XXS", 7, [(512, 12, 1)]),                                           # quirk 11: n_class is ignored
+    ("XS", 7, [(512, 16, 1), (16, 8, 2), (8, 7, 1)]),
+    ("S", 5, [(512, 128, 1), (128, 64, 2), (64, 64, 1), (64, 32, 2), (32, 5, 1)]),
+])
+def test_segmentor_layer_stack_matches_reference_construction(size, n_class, expect):
+    from ganecdotes_b200.hfc_with_swav.one_shot_segmentor import OneShotSegmentor
+    net = OneShotSegmentor(512, n_class, size=size)
+    convs = [m for m in net.layers if isinstance(m, torch.nn.Conv2d)]
+    assert [(c.in_channels, c.out_channels, c.dilation[0]) for c in convs] == expect
+    assert all(c.padding[0] == c.dilation[0] for c in convs)
+    assert not isinstance(net.layers[-1], torch.nn.LeakyReLU)            # no activation after the last conv
+    with pytest.raises(RuntimeError):
+        net.eval()(torch.zeros(1, 512, 8, 8))                             # no CPU path
