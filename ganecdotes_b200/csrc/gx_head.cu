@@ -201,19 +201,35 @@ __global__ void segment_sum_rows_kernel(const float* __restrict__ rows, const in
   uint2* oh = hi ? reinterpret_cast<uint2*>(hi + seg * c) : nullptr;
   uint2* ol = lo ? reinterpret_cast<uint2*>(lo + seg * c) : nullptr;
   float4* of = out_f32 ? reinterpret_cast<float4*>(out_f32 + seg * c) : nullptr;
-  for (int i = lane; i < cq; i += 32) {
-    float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
+  // 512 channels per sweep: the four 128-bit loads of a row are independent and in flight together
+  for (int i0 = 0; i0 < cq; i0 += 128) {
+    float4 acc[4];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r = r0; r < r1; ++r) {
-      const float4 v = __ldg(reinterpret_cast<const float4*>(rows + (long long)order[r] * c) + i);
-      acc.x += v.x; acc.y += v.y; acc.z += v.z; acc.w += v.w;
+      const float4* src = reinterpret_cast<const float4*>(rows + (long long)order[r] * c) + i0;
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = lane + 32 * j;
+        if (i0 + i < cq) {
+          const float4 v = gx_ldg_stream(src + i);
+          acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w;
+        }
+      }
     }
-    if (oh) {
-      uint2 h, l;
-      gx_split4(acc, h, l);
-      oh[i] = h;
-      if (ol) ol[i] = l;
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      const int i = i0 + lane + 32 * j;
+      if (i < cq) {
+        if (oh) {
+          uint2 h, l;
+          gx_split4(acc[j], h, l);
+          oh[i] = h;
+          if (ol) ol[i] = l;
+        }
+        if (of) of[i] = acc[j];
+      }
     }
-    if (of) of[i] = acc;
   }
 }
 
@@ -355,6 +371,40 @@ __global__ void pool_sum_kernel(const float* __restrict__ in, int H, int W, int 
   const int oy = r / w, ox = r - oy * w;
   const int fy = H / h, fx = W / w;
   const int cq = c >> 2;
+  if (fy == 2 && fx == 2) {       // the 2x2 steps of the resolution chain: all loads of a sweep in flight at once
+    const float4* p00 = reinterpret_cast<const float4*>(in + (((long long)b * H + 2 * oy) * W + 2 * ox) * c);
+    const float4* p10 = p00 + (long long)W * cq;
+    for (int i0 = 0; i0 < cq; i0 += 128) {
+      float4 v[4][4];
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + lane + 32 * j;
+        if (i < cq) {
+          v[j][0] = gx_ldg_stream(p00 + i); v[j][1] = gx_ldg_stream(p00 + cq + i);
+          v[j][2] = gx_ldg_stream(p10 + i); v[j][3] = gx_ldg_stream(p10 + cq + i);
+        }
+      }
+#pragma unroll
+      for (int j = 0; j < 4; ++j) {
+        const int i = i0 + lane + 32 * j;
+        if (i < cq) {
+          float4 acc;
+          acc.x = (v[j][0].x + v[j][1].x) + (v[j][2].x + v[j][3].x);
+          acc.y = (v[j][0].y + v[j][1].y) + (v[j][2].y + v[j][3].y);
+          acc.z = (v[j][0].z + v[j][1].z) + (v[j][2].z + v[j][3].z);
+          acc.w = (v[j][0].w + v[j][1].w) + (v[j][2].w + v[j][3].w);
+          if (out) reinterpret_cast<float4*>(out + o * c)[i] = acc;
+          if (hi) {
+            uint2 hh, ll;
+            gx_split4(acc, hh, ll);
+            reinterpret_cast<uint2*>(hi + o * c)[i] = hh;
+            if (lo) reinterpret_cast<uint2*>(lo + o * c)[i] = ll;
+          }
+        }
+      }
+    }
+    return;
+  }
   for (int i = lane; i < cq; i += 32) {
     float4 acc = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int dy = 0; dy < fy; ++dy)
