@@ -205,7 +205,7 @@ def run_ours(args):
     proj = torch.nn.Linear(cfg["hlen"], cfg["nclasses"], bias=False).to(dev)
     proto = torch.nn.Linear(cfg["nclasses"], cfg["nprototypes"]).to(dev)
     head = E.SwavHead(proj.weight.data, proto.weight.data, proto.bias.data, cfg["lr"], cfg["momentum"], cfg["trust"],
-                      args.passes_fwd, args.passes_bwd, proto_f16=not args.proto_bf16x3)
+                      args.passes_fwd, args.passes_bwd, proto_f16=args.proto_f16)
     scfg = E.StepConfig(hlen=cfg["hlen"], patch_size=cfg["patch"], num_patches=cfg["npatch"], niters=cfg["niters"],
                         eps=cfg["eps"], temperature=cfg["temperature"], truncation=cfg["truncation"],
                         perturb_std=cfg["perturb_std"])
@@ -277,7 +277,7 @@ def run_ours(args):
     pk = peaks()
     tensor_bound = {"gemm", "modconv"}
     # tensor-core passes issued per algorithmic FLOP (split-bf16 = 3 MMAs per product)
-    issued = {"gemm_prototype_fwd": 3 if args.proto_bf16x3 else 1, "gemm_projection_fwd": args.passes_fwd,
+    issued = {"gemm_prototype_fwd": 1 if args.proto_f16 else 3, "gemm_projection_fwd": args.passes_fwd,
               "modconv": args.passes_fwd, "modconv_up": args.passes_fwd, "gemm_dzn_bwd": args.passes_bwd,
               "gemm_gproto_bwd": args.passes_bwd, "gemm_gproj_bwd": args.passes_bwd}
     stage_rows = []
@@ -307,6 +307,31 @@ def run_ours(args):
                     "peak_source": pk["src"],
                     "note": "algorithmic FLOPs/bytes per launch / mean CUDA-event launch time; a 3-pass "
                             "split-bf16 GEMM issues 3x its algorithmic FLOPs on the tensor pipe"}
+
+    # ---------------------------------------------------------------- the other score-GEMM operand mode
+    # (same steps, device-timed, reported next to the headline; see DESIGN.md §4.2 for the tolerances)
+    alt = None
+    if not args.no_alt:
+        head.proto_f16 = not args.proto_f16
+        alt_steps = max(1, min(args.steps, 5))
+        for i in range(2):
+            E.swav_train_step_device(gen, head, mean_latent, inputs[i % len(inputs)], scfg, group, ws)
+        sync()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for i in range(alt_steps):
+            E.swav_train_step_device(gen, head, mean_latent, inputs[args.warmup + i], scfg, group, ws)
+        a1.record()
+        sync()
+        alt_ms = a0.elapsed_time(a1)
+        if world > 1:
+            t = torch.tensor([alt_ms], device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            alt_ms = t.item()
+        alt = {"score_gemm": "fp16x1" if head.proto_f16 else "bf16x3", "steps": alt_steps,
+               "ms_per_step": alt_ms / alt_steps, "value": vec_per_step * alt_steps / (alt_ms * 1e-3),
+               "unit": "vectors/s"}
+        head.proto_f16 = args.proto_f16
 
     # ---------------------------------------------------------------- end-to-end region
     # public API from pinned host buffers: host bookkeeping + H2D of step i+1 are issued while
@@ -367,7 +392,7 @@ def run_ours(args):
             "metric": "per-pixel feature vectors/sec (ffhq-256 SwAV step)", "value": value, "unit": "vectors/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": f"bf16x{args.passes_fwd}-split fwd" + ("" if args.proto_bf16x3 else " (score GEMM fp16x1 on unit-norm operands)") +
+            "dtype": f"bf16x{args.passes_fwd}-split fwd" + (" (score GEMM fp16x1 on unit-norm operands)" if args.proto_f16 else "") +
                      f" / bf16x{args.passes_bwd} bwd operands, fp32 accumulate + fp32 everywhere else",
             "data": "synthetic",
             "config": {"workload": workload_name(b), "latents_per_gpu": b, "global_latents": b * world,
@@ -377,7 +402,7 @@ def run_ours(args):
             "e2e": {"value": e2e_value, "unit": "vectors/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps, "ms_per_step": dt * 1e3 / e2e_steps,
                     "host_ms_per_step": {k: v / e2e_steps for k, v in host_ms.items()}},
-            "gpu_launches": launches, "clocks": clocks, "final_loss": final_loss,
+            "gpu_launches": launches, "clocks": clocks, "final_loss": final_loss, "alt_score_gemm_mode": alt,
         }
         print(json.dumps(line), flush=True)
     if world > 1:
@@ -393,9 +418,10 @@ def main():
     ap.add_argument("--latents-per-gpu", type=int, default=8)
     ap.add_argument("--passes-fwd", type=int, default=3, choices=[1, 3])
     ap.add_argument("--passes-bwd", type=int, default=1, choices=[1, 3])
-    ap.add_argument("--proto-bf16x3", action="store_true",
-                    help="pixel x prototype score GEMM on the 3-plane bf16 split (|dS| ~ 1e-6) instead of single "
-                         "fp16 planes (|dS| ~ 1e-5 rms, the default)")
+    ap.add_argument("--no-alt", action="store_true", help="skip the extra timing of the other score-GEMM mode")
+    ap.add_argument("--proto-f16", action="store_true",
+                    help="pixel x prototype score GEMM on single fp16 planes of the unit-norm operands (|dS| 1.3e-5 "
+                         "rms, codes within 3e-3 rms) instead of the default 3-plane bf16 split (2e-7 / 5e-5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":

@@ -157,13 +157,15 @@ class SwavHead:
     their bf16 operand planes, gradients and LARC/SGD state.  Operates IN PLACE on the
     parameters of the nn.Modules the caller saves (ref :504-505)."""
 
-    def __init__(self, w_proj, w_proto, b_proto, lr, momentum, trust, passes_fwd=3, passes_bwd=1, proto_f16=True):
+    def __init__(self, w_proj, w_proto, b_proto, lr, momentum, trust, passes_fwd=3, passes_bwd=1, proto_f16=False):
         self.w_proj, self.w_proto, self.b_proto = w_proj, w_proto, b_proto
         self.lr, self.momentum, self.trust = lr, momentum, trust
         self.passes_fwd, self.passes_bwd = passes_fwd, passes_bwd
-        # score GEMM on single fp16 planes (default): both operands are unit-norm rows, so fp16 (11-bit
-        # significand, no range problem) gives |dS| ~ 1e-5 rms at a third of the tensor-core work;
-        # False selects the 3-plane bf16 split (|dS| ~ 1e-6)
+        # score GEMM operands.  Default: the 3-plane bf16 split, |dS| = 2e-7 rms -> codes Q within 5e-5 rms of
+        # fp64 at the shipped eps = 0.005 (scores are multiplied by 200 inside the exponential).
+        # proto_f16=True: single fp16 planes of the unit-norm operands (no range problem), a third of the
+        # tensor-core work, |dS| = 1.3e-5 rms -> Q within 3e-3 rms (1.7e-2 max): a "bf16-grade" fast mode,
+        # measured in tests/test_gpu_fullsize.py::test_score_gemm_precision_modes_at_config_eps
         self.proto_f16 = bool(proto_f16)
         dev = w_proj.device
         self.g_proj = torch.zeros_like(w_proj)

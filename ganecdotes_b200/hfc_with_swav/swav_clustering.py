@@ -78,7 +78,7 @@ class SwAVClustering(object):
         self.match_reference_rng = True
         self.passes_fwd = int(swav_args.get('passes_fwd', 3))
         self.passes_bwd = int(swav_args.get('passes_bwd', 1))
-        self.proto_f16 = bool(swav_args.get('proto_f16', True))
+        self.proto_f16 = bool(swav_args.get('proto_f16', False))
 
     # ------------------------------------------------------------------ helpers
     def _mean_latent(self, n):

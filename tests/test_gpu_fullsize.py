@@ -188,3 +188,32 @@ def test_kmeans_assign_full_shapes(c, h, k):
         top2 = d.topk(2, dim=1, largest=False).values
         assert ((top2[:, 1] - top2[:, 0])[mism] < 1e-4 * top2[:, 0][mism]).all()
     assert mism.float().mean().item() < 1e-3
+
+
+def test_score_gemm_precision_modes_at_config_eps():
+    """What the operand format of the pixel x prototype GEMM does to the codes at the shipped eps = 0.005
+    (scores are multiplied by 200 inside the exponential): fp16 single pass (default) vs the 3-plane bf16
+    split vs fp64, on the softmax_k(S/eps) of 4096 unit-norm rows x 5000 prototypes.  These are the stated
+    tolerances of DESIGN.md §4.2."""
+    from ganecdotes_b200 import _lib as L
+    torch.manual_seed(1)
+    n, k, c, eps = 4096, 5000, 512, 0.005
+    z = torch.nn.functional.normalize(torch.randn(n, c, device="cuda"), dim=1)
+    wk = torch.nn.functional.normalize(torch.randn(k, c, device="cuda"), dim=1)
+    s64 = z.double() @ wk.double().t()
+    s16 = L.gemm(L.round_f16(z), None, L.round_f16(wk), None, n, k, c, 1, pair=True)
+    zh, zl = L.split_planes(z, want_lo=True)
+    wh, wl = L.split_planes(wk, want_lo=True)
+    s3 = L.gemm(zh, zl, wh, wl, n, k, c, 3, pair=True)
+    e16, e3 = (s16.double() - s64).abs(), (s3.double() - s64).abs()
+    print("|dS| fp16x1 max/rms", e16.max().item(), e16.pow(2).mean().sqrt().item(), " bf16x3", e3.max().item(),
+          e3.pow(2).mean().sqrt().item())
+    assert e16.max().item() < 1.5e-4 and e16.pow(2).mean().sqrt().item() < 2e-5
+    assert e3.max().item() < 1e-5 and e3.pow(2).mean().sqrt().item() < 2e-6
+    q64 = torch.softmax(s64 / eps, dim=1)
+    big = q64 > 1e-4                                       # the entries that carry the assignment
+    for s_, rms_tol, max_tol in ((s16, 6e-3, 4e-2), (s3, 6e-4, 4e-3)):
+        q = torch.softmax(s_.double() / eps, dim=1)
+        rel = ((q - q64).abs() / q64)[big]
+        print("rel dQ rms/max", rel.pow(2).mean().sqrt().item(), rel.max().item())
+        assert rel.pow(2).mean().sqrt().item() < rms_tol and rel.max().item() < max_tol, (rel.max().item(),)
