@@ -217,3 +217,24 @@ def test_score_gemm_precision_modes_at_config_eps():
         rel = ((q - q64).abs() / q64)[big]
         print("rel dQ rms/max", rel.pow(2).mean().sqrt().item(), rel.max().item())
         assert rel.pow(2).mean().sqrt().item() < rms_tol and rel.max().item() < max_tol, (rel.max().item(),)
+
+
+def test_pretrain_and_evaluate_entry_points(tmp_path):
+    """the reference's CLI surface (pretrain.py / evaluate.py arguments) on the ffhq-256 config: two
+    optimiser steps, artefacts written like the reference's, then label maps from the saved head."""
+    import os
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import evaluate
+    import pretrain
+    out = str(tmp_path / "run")
+    swav = pretrain.main(["--model", "ffhq-256", "--out_dir", out, "--num_epochs", "2", "--num_test_samples", "1"])
+    assert os.path.exists(os.path.join(out, "projection.pt")) and os.path.exists(os.path.join(out, "prototypes.pt"))
+    proj = torch.load(os.path.join(out, "projection.pt"), weights_only=False)
+    assert proj[0].weight.shape == (512, 5376) and torch.isfinite(proj[0].weight).all()
+    res = evaluate.main(["--model", "ffhq-256", "--out_dir", out, "--num_test_samples", "2"])
+    assert tuple(res["code_labels"].shape) == (2, 256, 256) and res["code_labels"].dtype == torch.int64
+    assert os.path.exists(os.path.join(out, "tests", "labels.pt"))
+    # same seed -> the same label maps (deterministic path)
+    res2 = evaluate.main(["--model", "ffhq-256", "--out_dir", out, "--num_test_samples", "2"])
+    assert torch.equal(res["code_labels"], res2["code_labels"])

@@ -70,3 +70,24 @@ def test_segmentor_layer_stack_matches_reference_construction(size, n_class, exp
     assert not isinstance(net.layers[-1], torch.nn.LeakyReLU)            # no activation after the last conv
     with pytest.raises(RuntimeError):
         net.eval()(torch.zeros(1, 512, 8, 8))                             # no CPU path
+
+
+def test_config_tables_match_the_reference_configs():
+    """numbers of configs/segmentors/hfc_with_swav_*_config.py and configs/models/*.py"""
+    from ganecdotes_b200 import configs
+    c = configs.swav_config("ffhq-256")
+    assert c["swav_args"]["hlen"] == 5376 and c["swav_args"]["nprototypes"] == 5000
+    assert c["swav_args"]["patch_size"] == 20000 and c["swav_args"]["num_patches"] == 5
+    assert c["sinkhorn_args"] == dict(source_pdf="uniform", niters=10, eps=0.005)
+    assert c["swav_args"]["temperature"] == 0.01 and c["swav_args"]["trust_coeff"] == 0.01
+    assert configs.seg_args("ffhq-256") == dict(size="XXS", in_ch=512)
+    car = configs.swav_config("car-512")
+    assert car["swav_args"]["nprototypes"] == 4000 and car["sinkhorn_args"]["eps"] == 0.01
+    assert configs.seg_args("car-512")["size"] == "XS"
+    assert configs.swav_config("cat-256")["sinkhorn_args"] == dict(source_pdf="image", niters=10, eps=0.003)
+    pid = configs.swav_config("pidray-wrench-256")
+    assert pid["swav_args"]["hlen"] == 2528 and configs.model_config("pidray-256").truncation == 0.9
+    assert configs.method_for("horse-256") == "hfc_with_swav_horse"
+    import pretrain
+    a = pretrain.parse(["--model", "pidray-256", "--num_test_samples", "3"])
+    assert a.model == "pidray-256" and a.num_test_samples == 3 and a.out_dir == "results/pretrain_default_ffhq/"
