@@ -582,11 +582,13 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
     if cfg.hlen % 8:
         raise ValueError("hlen must be a multiple of 8 (16-byte TMA row pitch of the bf16 operand planes)")
     n_patch_rows = b * (cfg.patch_size if cfg.patch_size is not None else out_h * out_w)
-    for name in ("s", "t"):
-        layer_no, pert_rows = inp.views[name]
-        wplus = view_wplus_device(gen, w, mean_latent, cfg.truncation, layer_no, pert_rows, cfg.perturb_std,
-                                  noise_ws[name])
-        _, f = gen.synthesize(wplus, None, need_image=cfg.need_image)
+    # both views go through the synthesis network as ONE batch of 2b images (they differ only in W+):
+    # half the launches, and the latency-bound 4x4 ... 16x16 layers do twice the work per launch
+    wplus = torch.cat([view_wplus_device(gen, w, mean_latent, cfg.truncation, inp.views[name][0], inp.views[name][1],
+                                         cfg.perturb_std, noise_ws[name]) for name in ("s", "t")])
+    _, f_both = gen.synthesize(wplus, None, need_image=cfg.need_image)
+    for vi, name in enumerate(("s", "t")):
+        f = [t[vi * b:(vi + 1) * b] for t in f_both]
         feats[name] = f
         if dedup:
             z_all, levels = project_all_pixels(head.wp_hi, head.wp_lo, f, b, out_h, out_w, cfg.hlen, head.passes_fwd,
