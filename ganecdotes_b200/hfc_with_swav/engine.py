@@ -20,7 +20,7 @@ host arithmetic is the data-independent index bookkeeping (rotation/flip index m
 random permutations), a few KB per latent.
 """
 import math
-from dataclasses import dataclass, field
+from dataclasses import dataclass
 from typing import List, Optional
 
 import torch
