@@ -11,11 +11,11 @@ unmodulated planes, bias + LeakyReLU in the epilogue, next layer's operand plane
 epilogue), on the NHWC code map `predict_swav_codes` produces - nothing goes back to the host, where the
 reference runs this head (`.to('cpu')`, src/one_shot_pipeline.py:610,662).
 
-Fine-tuning (src/one_shot_pipeline.py:540-578: CE loss + Adam through `self.segmentor(features)`): layers
-with few output channels (9 * C_out <= 256 - every layer of the shipped sizes 'XXS' and 'XS') are autograd
-functions whose backward is two more GEMMs on the same operands: dW_all = dG^T X (MN-major, split-K) and
-dX = dG W_all, with dG the 9-tap spread of the output gradient (`gx_tap_spread`).  Sizes with wider hidden
-layers ('S', 'M', 'L') run inference only; training them raises.
+Fine-tuning (src/one_shot_pipeline.py:540-578: CE loss + Adam through `self.segmentor(features)`): every
+layer is an autograd function in the 9-tap GEMM form (forward: G = X W_all^T + stencil sum), whose backward
+is two more GEMMs on the same operands: dW_all = dG^T X (MN-major, split-K) and dX = dG W_all, with dG the
+9-tap spread of the output gradient (`gx_tap_spread`).  The 9-tap form stores 9 * C_out values per pixel,
+which is what bounds the wide layers of sizes 'S' / 'M' / 'L' (a guard raises above 2 GB per layer).
 """
 import torch
 import torch.nn as nn
@@ -182,9 +182,11 @@ class OneShotSegmentor(nn.Module):
         y = x.float().permute(0, 2, 3, 1)
         convs = self._convs()
         for n, (i, conv) in enumerate(convs):
-            if 9 * ((conv.out_channels + 7) // 8 * 8) > 256:
-                raise NotImplementedError(f"OneShotSegmentor(size={self.size!r}): the fine-tune backward exists for "
-                                          "layers with 9 * C_out <= 256 ('XXS', 'XS'); this size is inference only")
+            g_bytes = 4 * 9 * ((conv.out_channels + 7) // 8 * 8) * y.shape[0] * y.shape[1] * y.shape[2]
+            if g_bytes > 2 << 30:
+                raise NotImplementedError(f"OneShotSegmentor(size={self.size!r}): the 9-tap training form of a "
+                                          f"{conv.out_channels}-channel layer needs {g_bytes >> 20} MB for this "
+                                          "input; fine-tune on smaller batches / crops")
             y = _TapsConv.apply(y, conv.weight, conv.bias, conv.dilation[0], n + 1 < len(convs))
         return y.permute(0, 3, 1, 2)
 
