@@ -86,7 +86,8 @@ _SIGNATURES = {
     "gx_round_f16": ([_P, _LL, _P, _LL, _LL, _P], _I),
     "gx_l2norm_bwd_split": ([_P, _P, _P, _P, _P, _P, _P, _LL, _I, _P], _I),
     "gx_segment_sum_rows": ([_P, _P, _P, _P, _P, _P, _LL, _I, _P], _I),
-    "gx_upsample_sum": ([_I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P], _I),
+    "gx_upsample_sum": ([_I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P], _I),
+    "gx_pool1d_bilinear": ([_P, _LL, _I, _I, _LL, _P, _P], _I),
     "gx_pool_sum": ([_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P], _I),
     "gx_tap_sum": ([_P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _I, _P], _I),
     "gx_tap_spread": ([_P, _I, _I, _I, _I, _I, _P, _P, _P], _I),
@@ -554,7 +555,7 @@ def segment_sum_rows(rows, order, seg_off, nseg, want_lo=False, want_planes=True
     return hi, lo, f
 
 
-def upsample_sum(parts, batch, out_h, out_w, out=None, planes=None):
+def upsample_sum(parts, batch, out_h, out_w, out=None, planes=None, bilinear=False):
     """parts: list of fp32 [batch, h_l, w_l, c] tensors -> fp32 [batch*out_h*out_w, c]"""
     lib = load()
     n = len(parts)
@@ -570,8 +571,8 @@ def upsample_sum(parts, batch, out_h, out_w, out=None, planes=None):
     nbytes = 4.0 * c * (sum(p.shape[0] * p.shape[1] * p.shape[2] for p in parts) + batch * out_h * out_w)
     with timed("upsample_sum", nbytes):
         hi, lo = planes if planes is not None else (None, None)
-        _check(lib.gx_upsample_sum(n, ptrs, hs, ws, batch, out_h, out_w, c, _ptr(out), _ptr(hi), _ptr(lo), _stream()),
-               "gx_upsample_sum")
+        _check(lib.gx_upsample_sum(n, ptrs, hs, ws, batch, out_h, out_w, c, _ptr(out), _ptr(hi), _ptr(lo),
+                                   int(bool(bilinear)), _stream()), "gx_upsample_sum")
     _count()
     return out
 
@@ -605,6 +606,30 @@ def tap_spread(dout_nhwc, dilation, want_lo=True):
                "gx_tap_spread")
     _count()
     return hi, lo
+
+
+def pool_bilinear_adjoint(x_nhwc, out_h, out_w):
+    """adjoint of F.interpolate(mode='bilinear', align_corners=False) from [b,out_h,out_w,c] to x's resolution:
+    fp32 [b,H,W,c] -> fp32 [b,out_h,out_w,c] (x then y, separable)"""
+    lib = load()
+    _f32(x_nhwc, "x")
+    b, h, w, c = x_nhwc.shape
+    dev = x_nhwc.device
+    t = x_nhwc
+    if out_w != w:
+        t2 = torch.empty((b, h, out_w, c), dtype=torch.float32, device=dev)
+        with timed("pool_bilinear", 4.0 * b * h * c * (w + out_w)):
+            _check(lib.gx_pool1d_bilinear(_ptr(t), b * h, w, out_w, c, _ptr(t2), _stream()), "gx_pool1d_bilinear")
+        _count()
+        t = t2
+    if out_h != h:
+        t2 = torch.empty((b, out_h, out_w, c), dtype=torch.float32, device=dev)
+        with timed("pool_bilinear", 4.0 * b * out_w * c * (h + out_h)):
+            _check(lib.gx_pool1d_bilinear(_ptr(t), b, h, out_h, out_w * c, _ptr(t2), _stream()),
+                   "gx_pool1d_bilinear")
+        _count()
+        t = t2
+    return t
 
 
 def pool_sum(x_nhwc, out_h, out_w, want_f32=True, want_planes=True, want_lo=False):

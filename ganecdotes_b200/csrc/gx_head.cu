@@ -241,8 +241,21 @@ struct UpsumDesc {
   const float* p[GX_MAX_LEVELS];
   int h[GX_MAX_LEVELS], w[GX_MAX_LEVELS];
   int out_h, out_w, c;
+  int bilinear;     // 0: nearest (floor(dst * in / out)), 1: F.interpolate(mode='bilinear', align_corners=False)
   long long npix;   // B*out_h*out_w
 };
+
+// source coordinate of torch's upsample_bilinear2d with align_corners = False:
+// src = max(0, scale * (dst + 0.5) - 0.5), i0 = floor(src), i1 = i0 + (i0 < n - 1), lambda = src - i0
+__device__ __forceinline__ void bilinear_src(int dst, int n_in, int n_out, int& i0, int& i1, float& lam) {
+  const float scale = (float)n_in / (float)n_out;
+  float src = scale * ((float)dst + 0.5f) - 0.5f;
+  if (src < 0.f) src = 0.f;
+  i0 = (int)src;
+  if (i0 > n_in - 1) i0 = n_in - 1;
+  i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
+  lam = src - (float)i0;
+}
 __global__ void upsample_sum_kernel(const UpsumDesc d, float* __restrict__ out, __nv_bfloat16* __restrict__ hi,
                                     __nv_bfloat16* __restrict__ lo) {
   const int lane = threadIdx.x & 31;
@@ -258,6 +271,30 @@ __global__ void upsample_sum_kernel(const UpsumDesc d, float* __restrict__ out, 
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int l = 0; l < d.nlevels; ++l) {
+      if (d.bilinear && (d.h[l] != d.out_h || d.w[l] != d.out_w)) {
+        int y0, y1, x0, x1;
+        float ly, lx;
+        bilinear_src(y, d.h[l], d.out_h, y0, y1, ly);
+        bilinear_src(x, d.w[l], d.out_w, x0, x1, lx);
+        const float* base = d.p[l] + (long long)b * d.h[l] * d.w[l] * d.c;
+        const float4* p00 = reinterpret_cast<const float4*>(base + ((long long)y0 * d.w[l] + x0) * d.c) + c0;
+        const float4* p01 = reinterpret_cast<const float4*>(base + ((long long)y0 * d.w[l] + x1) * d.c) + c0;
+        const float4* p10 = reinterpret_cast<const float4*>(base + ((long long)y1 * d.w[l] + x0) * d.c) + c0;
+        const float4* p11 = reinterpret_cast<const float4*>(base + ((long long)y1 * d.w[l] + x1) * d.c) + c0;
+        const float w00 = (1.f - ly) * (1.f - lx), w01 = (1.f - ly) * lx, w10 = ly * (1.f - lx), w11 = ly * lx;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const int i = lane + 32 * j;
+          if (c0 + i < cq) {
+            const float4 a = __ldg(p00 + i), bq = __ldg(p01 + i), cc = __ldg(p10 + i), dd = __ldg(p11 + i);
+            acc[j].x += w00 * a.x + w01 * bq.x + w10 * cc.x + w11 * dd.x;
+            acc[j].y += w00 * a.y + w01 * bq.y + w10 * cc.y + w11 * dd.y;
+            acc[j].z += w00 * a.z + w01 * bq.z + w10 * cc.z + w11 * dd.z;
+            acc[j].w += w00 * a.w + w01 * bq.w + w10 * cc.w + w11 * dd.w;
+          }
+        }
+        continue;
+      }
       const int ly = (y * d.h[l]) / d.out_h, lx = (x * d.w[l]) / d.out_w;
       const float4* src =
           reinterpret_cast<const float4*>(d.p[l] + (((long long)b * d.h[l] + ly) * d.w[l] + lx) * d.c) + c0;
@@ -283,6 +320,54 @@ __global__ void upsample_sum_kernel(const UpsumDesc d, float* __restrict__ out, 
         }
       }
     }
+  }
+}
+
+// Adjoint of 1-D bilinear upsampling along one axis: in [outer, n_in(fine), inner] -> out [outer, n_out(coarse),
+// inner], out[o, J, :] = sum_j w(j -> J) in[o, j, :] with the forward weights of `bilinear_src`.  Two calls
+// (x then y) give the adjoint of the separable 2-D bilinear upsampling - the weight-gradient fold of dZ onto a
+// coarser level when hf_interp = 'bilinear'.  One warp per (o, J, 512-float slice of inner).
+__global__ void pool1d_bilinear_kernel(const float* __restrict__ in, long long outer, int n_in, int n_out,
+                                       long long inner, float* __restrict__ out) {
+  const int lane = threadIdx.x & 31;
+  const long long iq = inner >> 2;                      // float4 per (o, j)
+  const long long slices = (iq + 127) / 128;
+  const long long wid = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (wid >= outer * n_out * slices) return;
+  const long long sl = wid % slices;
+  const int J = (int)((wid / slices) % n_out);
+  const long long o = wid / (slices * n_out);
+  // fine indices whose source coordinate falls in (J - 1, J + 1): a superset is enough, weights decide
+  const float inv = (float)n_in / (float)n_out;         // fine per coarse
+  int jlo = (int)floorf(((float)J - 0.5f) * inv - 0.5f) - 1;
+  int jhi = (int)ceilf(((float)J + 1.5f) * inv - 0.5f) + 1;
+  if (jlo < 0) jlo = 0;
+  if (jhi > n_in - 1) jhi = n_in - 1;
+  float4 acc[4];
+#pragma unroll
+  for (int t = 0; t < 4; ++t) acc[t] = make_float4(0.f, 0.f, 0.f, 0.f);
+  for (int j = jlo; j <= jhi; ++j) {
+    int i0, i1;
+    float lam;
+    bilinear_src(j, n_out, n_in, i0, i1, lam);
+    const float wj = (i0 == J ? 1.f - lam : 0.f) + (i1 == J ? lam : 0.f);
+    if (wj == 0.f) continue;                            // warp-uniform
+    const float4* src = reinterpret_cast<const float4*>(in + (o * n_in + j) * inner) + sl * 128;
+#pragma unroll
+    for (int t = 0; t < 4; ++t) {
+      const long long i = sl * 128 + lane + 32 * t;
+      if (i < iq) {
+        const float4 v = __ldg(src + lane + 32 * t);
+        acc[t].x = fmaf(wj, v.x, acc[t].x); acc[t].y = fmaf(wj, v.y, acc[t].y);
+        acc[t].z = fmaf(wj, v.z, acc[t].z); acc[t].w = fmaf(wj, v.w, acc[t].w);
+      }
+    }
+  }
+  float4* dst = reinterpret_cast<float4*>(out + (o * n_out + J) * inner) + sl * 128;
+#pragma unroll
+  for (int t = 0; t < 4; ++t) {
+    const long long i = sl * 128 + lane + 32 * t;
+    if (i < iq) dst[lane + 32 * t] = acc[t];
   }
 }
 
@@ -1309,8 +1394,19 @@ extern "C" int gx_segment_sum_rows(const float* rows, const int* order, const in
   return GX_OK;
 }
 
+extern "C" int gx_pool1d_bilinear(const float* in, long long outer, int n_in, int n_out, long long inner, float* out,
+                                  void* stream) {
+  GX_CHECK_ARG(in && out && outer > 0 && n_in > 0 && n_out > 0 && n_out <= n_in && inner > 0 && inner % 4 == 0);
+  const long long warps = outer * n_out * (((inner >> 2) + 127) / 128);
+  GX_CHECK_ARG(gx_cdiv(warps, 8) < 2147483647LL);
+  pool1d_bilinear_kernel<<<(unsigned)gx_cdiv(warps, 8), 256, 0, (cudaStream_t)stream>>>(in, outer, n_in, n_out, inner,
+                                                                                       out);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
 extern "C" int gx_upsample_sum(int nlevels, const float* const* p, const int* h, const int* w, int batch, int out_h,
-                               int out_w, int c, float* out, void* hi, void* lo, void* stream) {
+                               int out_w, int c, float* out, void* hi, void* lo, int bilinear, void* stream) {
   GX_CHECK_ARG(nlevels > 0 && nlevels <= GX_MAX_LEVELS && p && h && w && (out || hi) && batch > 0 && c % 4 == 0);
   GX_CHECK_ARG(lo == nullptr || hi != nullptr);
   UpsumDesc d;
@@ -1320,6 +1416,7 @@ extern "C" int gx_upsample_sum(int nlevels, const float* const* p, const int* h,
     d.p[l] = p[l]; d.h[l] = h[l]; d.w[l] = w[l];
   }
   d.out_h = out_h; d.out_w = out_w; d.c = c;
+  d.bilinear = bilinear ? 1 : 0;
   d.npix = (long long)batch * out_h * out_w;
   upsample_sum_kernel<<<gx_cdiv(d.npix, 8), 256, 0, (cudaStream_t)stream>>>(
       d, out, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo));

@@ -341,7 +341,7 @@ def resolution_groups(feats, hlen):
 
 
 def project_all_pixels(wp_hi, wp_lo, feats, batch, out_h, out_w, hlen, passes, want_hi_only_planes=False, out=None,
-                       out_planes=None):
+                       out_planes=None, bilinear=False):
     """Z[pixel] = Wp . (nearest-upsampled, concatenated feature vector of the pixel) for EVERY
     pixel of `batch` images.  Upsampling and projection are both linear, so
     Z = sum_r upsample(F_r Wp[:, cols_r]^T): each resolution is projected at its native size
@@ -369,11 +369,12 @@ def project_all_pixels(wp_hi, wp_lo, feats, batch, out_h, out_w, hlen, passes, w
     if len(parts) == 1 and parts[0].shape[1] == out_h and parts[0].shape[2] == out_w and out is None \
             and out_planes is None:
         return parts[0].view(-1, c), levels
-    z = L.upsample_sum(parts, batch, out_h, out_w, out=out, planes=out_planes)
+    # nearest or bilinear (hf_interp): both are linear, so the per-resolution identity holds for either
+    z = L.upsample_sum(parts, batch, out_h, out_w, out=out, planes=out_planes, bilinear=bilinear)
     return z, levels
 
 
-def project_backward_dedup(head: SwavHead, dz_rows, order, seg_off, levels, batch, out_h, out_w):
+def project_backward_dedup(head: SwavHead, dz_rows, order, seg_off, levels, batch, out_h, out_w, bilinear=False):
     """gWp[:, cols_r] += pool_r(dZ_pix)^T F_r per resolution, with dZ_pix[pixel] = sum of the dZ rows
     of all samples of that pixel and pool_r = block sums (the adjoint of nearest upsampling)."""
     pb = head.passes_bwd
@@ -387,8 +388,16 @@ def project_backward_dedup(head: SwavHead, dz_rows, order, seg_off, levels, batc
     bm = 256 if pb == 1 else 128
     sms = L.load().gx_sinkhorn_max_parts()
     order_lv = sorted(levels, key=lambda lv: -lv["h"] * lv["w"])
+    full = cur
     for i, lv in enumerate(order_lv):
-        if lv["h"] != cur["h"] or lv["w"] != cur["w"]:
+        if bilinear and (lv["h"] != out_h or lv["w"] != out_w):
+            if lv["h"] != cur["h"] or lv["w"] != cur["w"] or cur is full:
+                # bilinear upsampling from different resolutions does not compose: every level folds the
+                # full-resolution dZ with its own adjoint (x then y)
+                f = L.pool_bilinear_adjoint(full["f32"], lv["h"], lv["w"])
+                hi, lo = L.split_planes(f.view(-1, c), want_lo=pb == 3)
+                cur = dict(h=lv["h"], w=lv["w"], f32=None, hi=hi, lo=lo)
+        elif lv["h"] != cur["h"] or lv["w"] != cur["w"]:
             more = any(o["h"] * o["w"] < lv["h"] * lv["w"] for o in order_lv[i + 1:])
             f, hi, lo = L.pool_sum(cur["f32"], lv["h"], lv["w"], want_f32=more, want_planes=True, want_lo=pb == 3)
             cur = dict(h=lv["h"], w=lv["w"], f32=f, hi=hi, lo=lo)
@@ -435,6 +444,7 @@ class StepConfig:
     need_image: bool = False
     source_pdf: str = 'uniform'
     dedup: Optional[bool] = None   # project every pixel once (None: automatic, when P*N > H*W)
+    hf_interp: str = 'nearest'     # 'nearest' | 'bilinear' (ref :112-126); bilinear needs the all-pixel path
 
 
 @dataclass
@@ -454,6 +464,11 @@ def use_dedup(cfg: StepConfig, out_h, out_w) -> bool:
     at each level's native resolution (`project_all_pixels`, ~11x cheaper per pixel than projecting
     gathered rows for the ffhq pyramid): project every pixel once and let the patches gather rows
     of Z unless the patches touch only a small fraction of the image."""
+    if getattr(cfg, "hf_interp", "nearest") == 'bilinear':
+        if cfg.dedup is False:
+            raise ValueError("hf_interp='bilinear' runs on the all-pixel projection path (dedup=False gathers "
+                             "nearest-upsampled rows)")
+        return True
     if cfg.dedup is not None:
         return bool(cfg.dedup)
     n = cfg.patch_size if cfg.patch_size is not None else out_h * out_w
@@ -592,7 +607,8 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
         feats[name] = f
         if dedup:
             z_all, levels = project_all_pixels(head.wp_hi, head.wp_lo, f, b, out_h, out_w, cfg.hlen, head.passes_fwd,
-                                               want_hi_only_planes=head.passes_bwd != 3)
+                                               want_hi_only_planes=head.passes_bwd != 3,
+                                               bilinear=cfg.hf_interp == 'bilinear')
             dz_rows = torch.empty((cfg.num_patches * n_patch_rows, head.c), dtype=torch.float32, device=dev)
             allpix[name] = dict(levels=levels, z=z_all, dz_rows=dz_rows)
 
@@ -630,7 +646,7 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
         for name in ("s", "t"):
             ap = allpix[name]
             project_backward_dedup(head, ap["dz_rows"], inp.dedup[name][1], inp.dedup[name][2], ap["levels"], b,
-                                   out_h, out_w)
+                                   out_h, out_w, bilinear=cfg.hf_interp == 'bilinear')
     loss = loss_acc / (n_total * cfg.num_patches)
     if group is not None:
         for g in (head.g_proj, head.g_proto, head.g_bias):
@@ -649,7 +665,8 @@ def swav_train_step(gen, head: SwavHead, mean_latent, draws: StepDraws, cfg: Ste
 
 
 @torch.no_grad()
-def predict_codes(gen, w_proj, w, mean_latent, truncation, hlen, passes=3, images_per_chunk=4, want_planes=False):
+def predict_codes(gen, w_proj, w, mean_latent, truncation, hlen, passes=3, images_per_chunk=4, want_planes=False,
+                  hf_interp='nearest'):
     """predict_swav_codes (ref :659-693): generator forward with the fixed noise buffers,
     per-pixel vectors, projection only, arg-max over the code channels.
     Returns (codes [B,C,H,W] fp32 in channels_last memory, labels int64 [B,H,W]); with want_planes also the
@@ -678,7 +695,8 @@ def predict_codes(gen, w_proj, w, mean_latent, truncation, hlen, passes=3, image
         sub = [f[i0:i1] for f in feats]
         zc = z[i0 * h * wd: i1 * h * wd]
         pl = (z_hi[i0 * h * wd: i1 * h * wd], z_lo[i0 * h * wd: i1 * h * wd]) if want_planes else None
-        project_all_pixels(wp_hi, wp_lo, sub, i1 - i0, h, wd, hlen, passes, out=zc, out_planes=pl)
+        project_all_pixels(wp_hi, wp_lo, sub, i1 - i0, h, wd, hlen, passes, out=zc, out_planes=pl,
+                           bilinear=hf_interp == 'bilinear')
         labels[i0 * h * wd: i1 * h * wd] = L.argmax_rows(zc)
     preds = z.view(b, h, wd, c).permute(0, 3, 1, 2)
     if want_planes:

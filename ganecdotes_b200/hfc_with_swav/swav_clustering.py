@@ -105,7 +105,17 @@ class SwAVClustering(object):
                             num_patches=self.swav_args['num_patches'], niters=self.niters, eps=self.eps,
                             temperature=self.swav_args['temperature'], truncation=self.truncation,
                             perturb_std=list(self.perturb_args['perturb_std']),
-                            source_pdf=self.sinkhorn_args.get('source_pdf', 'uniform'))
+                            source_pdf=self.sinkhorn_args.get('source_pdf', 'uniform'),
+                            hf_interp=self._hf_interp())
+
+    def _hf_interp(self):
+        mode = self.swav_args.get('hf_interp', 'nearest')
+        if mode not in ('nearest', 'bilinear'):
+            raise NotImplementedError("hf_interp: 'nearest' (every shipped config) or 'bilinear'")
+        if mode == 'bilinear' and self.sinkhorn_args.get('source_pdf', 'uniform') == 'image':
+            raise NotImplementedError("hf_interp='bilinear' with source_pdf='image' (the norm image is gathered "
+                                      "from nearest-upsampled rows)")
+        return mode
 
     def _draw_view(self, b, layer_no):
         n_layers = self.perturb_args['n_layers']
@@ -170,7 +180,8 @@ class SwAVClustering(object):
         h = max(f.shape[1] for f in feats)
         w = max(f.shape[2] for f in feats)
         if self.swav_args['hf_interp'] != 'nearest':
-            raise NotImplementedError("hf_interp: only 'nearest' (every shipped config)")
+            raise NotImplementedError("create_pixel_feature_vectors materialises nearest-upsampled vectors only; "
+                                      "hf_interp='bilinear' is applied inside the training / prediction paths")
         b = feats[0].shape[0]
         hlen = min(self.swav_args['hlen'], sum(f.shape[3] for f in feats))
         _, _, a = L.gather_rows(feats, h, w, hlen, None, None, b * h * w, want_lo=False, want_f32=True)
@@ -324,4 +335,5 @@ class SwAVClustering(object):
     def predict_swav_codes(self, input_latent, input_is_latent=True):
         """ref :659-693 (the reference ignores `input_is_latent`: always a W latent)."""
         return E.predict_codes(self.model, self.projection[0].weight.data, input_latent, self.mean_latent,
-                               self.model_config.truncation, self.swav_args['hlen'], self.passes_fwd)
+                               self.model_config.truncation, self.swav_args['hlen'], self.passes_fwd,
+                               hf_interp=self._hf_interp())

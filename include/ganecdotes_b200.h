@@ -229,9 +229,17 @@ int gx_segment_sum_rows(const float* rows, const int* order, const int* seg_off,
 /* Z[b,y,x,:] = sum_l P_l[b, y*h_l/out_h, x*w_l/out_w, :] (fp32 NHWC, c channels).  By linearity the
  * projection of the nearest-upsampled + concatenated per-pixel vector (ref swav_clustering.py:108-130,
  * :171) is the sum of per-level projections computed at each level's native resolution.
- * hi / lo (optional, out may then be NULL): the same values as bf16 split planes [batch*out_h*out_w, c]. */
+ * hi / lo (optional, out may then be NULL): the same values as bf16 split planes [batch*out_h*out_w, c].
+ * bilinear != 0: the levels are upsampled like F.interpolate(mode='bilinear', align_corners=False) instead of
+ * nearest (swav_args['hf_interp'], ref :112-126) - still linear, so the per-level projection identity holds. */
 int gx_upsample_sum(int nlevels, const float* const* p, const int* h, const int* w, int batch, int out_h,
-                    int out_w, int c, float* out, void* hi, void* lo, void* stream);
+                    int out_w, int c, float* out, void* hi, void* lo, int bilinear, void* stream);
+
+/* Adjoint of 1-D bilinear upsampling (align_corners = False) along the middle axis:
+ * in [outer, n_in, inner] -> out [outer, n_out, inner], n_out <= n_in, inner % 4 == 0.  Applied along x and
+ * then y it folds dZ onto a coarser level when swav_args['hf_interp'] == 'bilinear'. */
+int gx_pool1d_bilinear(const float* in, long long outer, int n_in, int n_out, long long inner, float* out,
+                       void* stream);
 
 /* Second half of a 3x3 (dilated, padding = dilation) conv with few output channels computed as one GEMM
  * over all nine taps: g [batch*h*w, 9*cout] with column tap*cout + co (tap = ky*3 + kx);

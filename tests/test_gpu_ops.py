@@ -634,3 +634,28 @@ def test_upfirdn2d_and_fused_lrelu_backward_and_double_backward(L):
     (gg,) = torch.autograd.grad(gx2, g2, v)
     slope = torch.where(y.detach() > 0, 1.0, 0.2) * 2 ** 0.5
     torch.testing.assert_close(gg, v * slope, rtol=1e-5, atol=1e-6)
+
+
+def test_bilinear_upsample_sum_and_its_adjoint(L):
+    """hf_interp='bilinear' (ref swav_clustering.py:112-126): upsample_sum with F.interpolate(mode='bilinear',
+    align_corners=False) semantics, and `pool_bilinear_adjoint` as its exact adjoint (<U p, x> = <p, U^T x>)."""
+    torch.manual_seed(4)
+    b, c = 2, 24
+    parts = [torch.randn(b, 4, 4, c), torch.randn(b, 8, 8, c), torch.randn(b, 32, 32, c)]
+    ref = sum(torch.nn.functional.interpolate(p.permute(0, 3, 1, 2), size=(32, 32), mode="bilinear",
+                                              align_corners=False) for p in parts)
+    got = L.upsample_sum([p.cuda() for p in parts], b, 32, 32, bilinear=True)
+    torch.testing.assert_close(got.view(b, 32, 32, c).cpu(), ref.permute(0, 2, 3, 1), rtol=1e-5, atol=1e-5)
+    x = torch.randn(b, 32, 32, c)
+    for p in parts[:2]:
+        h = p.shape[1]
+        up = torch.nn.functional.interpolate(p.permute(0, 3, 1, 2), size=(32, 32), mode="bilinear",
+                                             align_corners=False).permute(0, 2, 3, 1)
+        adj = L.pool_bilinear_adjoint(x.cuda(), h, h).cpu()
+        torch.testing.assert_close((up.double() * x.double()).sum(), (p.double() * adj.double()).sum(),
+                                   rtol=1e-5, atol=1e-4)
+        # and against autograd of F.interpolate
+        pr = p.clone().requires_grad_(True)
+        torch.nn.functional.interpolate(pr.permute(0, 3, 1, 2), size=(32, 32), mode="bilinear",
+                                        align_corners=False).backward(x.permute(0, 3, 1, 2))
+        torch.testing.assert_close(adj, pr.grad, rtol=1e-4, atol=1e-5)

@@ -163,13 +163,15 @@ def make_draws(b, d, n_layers, hw, npatch, seed):
                        perms=[[torch.randperm(hw, generator=g) for _ in range(b)] for _ in range(npatch)])
 
 
-def oracle_step(sd, mean_latent, draws, wp, wk, bk, hlen, patch, npatch, pstd, niters, eps, temp, bufs=None):
+def oracle_step(sd, mean_latent, draws, wp, wk, bk, hlen, patch, npatch, pstd, niters, eps, temp, bufs=None,
+                mode="nearest"):
     b = draws.z.shape[0]
     w = O.style_mlp(sd, draws.z)
     rows = {"s": [[] for _ in range(npatch)], "t": [[] for _ in range(npatch)]}
     for name, view in (("s", draws.view_s), ("t", draws.view_t)):
         for i in range(b):
-            hf, _ = O.view_features(sd, w[i:i + 1], mean_latent, 0.7, view.layer_no[i], view.pert_z[i], 3, pstd, hlen)
+            hf, _ = O.view_features(sd, w[i:i + 1], mean_latent, 0.7, view.layer_no[i], view.pert_z[i], 3, pstd, hlen,
+                                    mode)
             hf = O.rotate_flip(hf, view.angle[i], view.flip[i])
             for p in range(npatch):
                 rows[name][p].append(O.sample_rows(hf, draws.perms[p][i], patch))
@@ -178,8 +180,9 @@ def oracle_step(sd, mean_latent, draws, wp, wk, bk, hlen, patch, npatch, pstd, n
     return O.swav_step(rs, rt, wp, wk, bk, niters, eps, temp, bufs)
 
 
-@pytest.mark.parametrize("dedup,proto_f16", [(False, True), (True, True), (True, False)])
-def test_batched_joint_step_matches_oracle(gen, dedup, proto_f16):
+@pytest.mark.parametrize("dedup,proto_f16,interp", [(False, True, "nearest"), (True, True, "nearest"),
+                                                      (True, False, "nearest"), (True, False, "bilinear")])
+def test_batched_joint_step_matches_oracle(gen, dedup, proto_f16, interp):
     """B = 3 latents per step: joint-batch Sinkhorn over the row-concatenation.
     dedup=True: every pixel is projected once and the patches gather rows of Z (the path the
     full-size ffhq step takes, where 5 x 20000 samples > 65536 pixels).
@@ -198,12 +201,13 @@ def test_batched_joint_step_matches_oracle(gen, dedup, proto_f16):
     head = E.SwavHead(wp.clone().cuda(), wk.clone().cuda(), bk.clone().cuda(), 0.01, 0.9, 0.01, 3, 1,
                       proto_f16=proto_f16)
     cfg = E.StepConfig(hlen=hlen, patch_size=patch, num_patches=npatch, niters=10, eps=0.02, temperature=0.02,
-                       truncation=0.7, perturb_std=pstd, dedup=dedup)
+                       truncation=0.7, perturb_std=pstd, dedup=dedup, hf_interp=interp)
     bufs = None
     rwp, rwk, rbk = wp, wk, bk
     for step in range(2):
         draws = make_draws(3, 64, 3, 256, npatch, 100 + step)
-        ref = oracle_step(sd, mean_latent, draws, rwp, rwk, rbk, hlen, patch, npatch, pstd, 10, 0.02, 0.02, bufs)
+        ref = oracle_step(sd, mean_latent, draws, rwp, rwk, rbk, hlen, patch, npatch, pstd, 10, 0.02, 0.02, bufs,
+                          mode=interp)
         loss = E.swav_train_step(gen, head, mean_latent.cuda(), draws, cfg)
         assert abs(loss.item() - ref["loss"].item()) < 2e-3 * abs(ref["loss"].item()), (loss.item(), ref["loss"])
         # gradients (bf16 backward GEMMs): relative Frobenius error
