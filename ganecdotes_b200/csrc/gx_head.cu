@@ -323,6 +323,85 @@ __global__ void upsample_sum_kernel(const UpsumDesc d, float* __restrict__ out, 
   }
 }
 
+// Nearest upsampling on a pyramid: a level whose upsampling factor is an even integer in both directions gives the
+// same source vector to the four pixels of an aligned 2x2 output quad.  One warp per quad: the `n_shared` coarse
+// levels (they come first) are loaded and summed once, in level order, the remaining (at most two) levels are loaded
+// per pixel and added on top - the same additions in the same order as the per-pixel kernel above, so the result is
+// bit-identical, with 2.3x fewer 128-bit loads through L1 (the per-pixel kernel is bound by L1 wavefronts, not by
+// HBM: 7 loads + 1 store of 2 KB per pixel).  All loads of a 128-channel sweep are in flight together.
+constexpr int UPQ_SHARED = 8;
+constexpr int UPQ_FINE = 2;
+template <int UPQ_S, int UPQ_F>
+__global__ void __launch_bounds__(256, 2)
+upsample_sum_quad_kernel(const UpsumDesc d, int n_shared, float* __restrict__ out, __nv_bfloat16* __restrict__ hi,
+                         __nv_bfloat16* __restrict__ lo) {
+  const int lane = threadIdx.x & 31;
+  const int qh = d.out_h >> 1, qw = d.out_w >> 1;
+  const long long quad = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (quad >= (d.npix >> 2)) return;
+  const int per = qh * qw;
+  const int b = (int)(quad / per);
+  const int r = (int)(quad - (long long)b * per);
+  const int y = (r / qw) * 2, x = (r - (r / qw) * qw) * 2;
+  const int cq = d.c >> 2;
+  const int n_fine = d.nlevels - n_shared;
+  const float4* src[UPQ_S];
+#pragma unroll
+  for (int l = 0; l < UPQ_S; ++l) {
+    src[l] = nullptr;
+    if (l < n_shared) {
+      const int ly = (y * d.h[l]) / d.out_h, lx = (x * d.w[l]) / d.out_w;
+      src[l] = reinterpret_cast<const float4*>(d.p[l] + (((long long)b * d.h[l] + ly) * d.w[l] + lx) * d.c);
+    }
+  }
+  const float4* fsrc[UPQ_F];
+  int foff[UPQ_F][4];        // float4 offsets of the four pixels' sources from fsrc
+#pragma unroll
+  for (int m = 0; m < UPQ_F; ++m) {
+    fsrc[m] = nullptr;
+    if (m < n_fine) {
+      const int l = n_shared + m;
+      fsrc[m] = reinterpret_cast<const float4*>(d.p[l] + (long long)b * d.h[l] * d.w[l] * d.c);
+#pragma unroll
+      for (int p = 0; p < 4; ++p) {
+        const int ly = ((y + (p >> 1)) * d.h[l]) / d.out_h, lx = ((x + (p & 1)) * d.w[l]) / d.out_w;
+        foff[m][p] = (ly * d.w[l] + lx) * cq;
+      }
+    }
+  }
+  const long long pix0 = ((long long)b * d.out_h + y) * d.out_w + x;
+  for (int i = lane; i < cq; i += 32) {
+    float4 v[UPQ_S], f[UPQ_F][4];
+#pragma unroll
+    for (int l = 0; l < UPQ_S; ++l)
+      if (l < n_shared) v[l] = __ldg(src[l] + i);
+#pragma unroll
+    for (int m = 0; m < UPQ_F; ++m)
+#pragma unroll
+      for (int p = 0; p < 4; ++p)
+        if (m < n_fine) f[m][p] = gx_ldg_stream(fsrc[m] + foff[m][p] + i);
+    float4 acc_s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+    for (int l = 0; l < UPQ_S; ++l)
+      if (l < n_shared) { acc_s.x += v[l].x; acc_s.y += v[l].y; acc_s.z += v[l].z; acc_s.w += v[l].w; }
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      float4 acc = acc_s;
+#pragma unroll
+      for (int m = 0; m < UPQ_F; ++m)
+        if (m < n_fine) { acc.x += f[m][p].x; acc.y += f[m][p].y; acc.z += f[m][p].z; acc.w += f[m][p].w; }
+      const long long pix = pix0 + (p >> 1) * d.out_w + (p & 1);
+      if (out) gx_stg_stream(reinterpret_cast<float4*>(out + pix * d.c) + i, acc);
+      if (hi) {
+        uint2 h2, l2;
+        gx_split4(acc, h2, l2);
+        reinterpret_cast<uint2*>(hi + pix * d.c)[i] = h2;
+        if (lo) reinterpret_cast<uint2*>(lo + pix * d.c)[i] = l2;
+      }
+    }
+  }
+}
+
 // Adjoint of 1-D bilinear upsampling along one axis: in [outer, n_in(fine), inner] -> out [outer, n_out(coarse),
 // inner], out[o, J, :] = sum_j w(j -> J) in[o, j, :] with the forward weights of `bilinear_src`.  Two calls
 // (x then y) give the adjoint of the separable 2-D bilinear upsampling - the weight-gradient fold of dZ onto a
@@ -540,15 +619,27 @@ __global__ void split_planes_kernel(const float* __restrict__ x, long long ld, _
 __global__ void split_planes_v4_kernel(const float* __restrict__ x, long long ld, __nv_bfloat16* __restrict__ hi,
                                        __nv_bfloat16* __restrict__ lo, long long rows, int cq, long long ldo) {
   const long long total = rows * cq;
-  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
-       i += (long long)gridDim.x * blockDim.x) {
-    const long long r = i / cq;
-    const int q = (int)(i - r * cq);
-    const float4 v = gx_ldg_stream(reinterpret_cast<const float4*>(x + r * ld) + q);
-    uint2 h, l;
-    gx_split4(v, h, l);
-    reinterpret_cast<uint2*>(hi + r * ldo)[q] = h;
-    if (lo) reinterpret_cast<uint2*>(lo + r * ldo)[q] = l;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  // four independent 128-bit loads in flight per thread
+  for (long long i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x; i0 < total; i0 += 4 * stride) {
+    float4 v[4];
+    long long r[4];
+    int q[4];
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      const long long i = i0 + u * stride;
+      r[u] = i / cq;
+      q[u] = (int)(i - r[u] * cq);
+      if (i < total) v[u] = gx_ldg_stream(reinterpret_cast<const float4*>(x + r[u] * ld) + q[u]);
+    }
+#pragma unroll
+    for (int u = 0; u < 4; ++u) {
+      if (i0 + u * stride >= total) break;
+      uint2 h, l;
+      gx_split4(v[u], h, l);
+      reinterpret_cast<uint2*>(hi + r[u] * ldo)[q[u]] = h;
+      if (lo) reinterpret_cast<uint2*>(lo + r[u] * ldo)[q[u]] = l;
+    }
   }
 }
 
@@ -1418,8 +1509,31 @@ extern "C" int gx_upsample_sum(int nlevels, const float* const* p, const int* h,
   d.out_h = out_h; d.out_w = out_w; d.c = c;
   d.bilinear = bilinear ? 1 : 0;
   d.npix = (long long)batch * out_h * out_w;
-  upsample_sum_kernel<<<gx_cdiv(d.npix, 8), 256, 0, (cudaStream_t)stream>>>(
-      d, out, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo));
+  // pyramid fast path: leading levels shared by aligned 2x2 output quads, at most UPQ_FINE per-pixel levels after them
+  int n_shared = 0;
+  bool quad_ok = !bilinear && out_h % 2 == 0 && out_w % 2 == 0 && (long long)out_h * out_w * (c / 4) < (1LL << 31);
+  if (quad_ok) {
+    auto shared = [&](int l) {
+      return out_h % h[l] == 0 && (out_h / h[l]) % 2 == 0 && out_w % w[l] == 0 && (out_w / w[l]) % 2 == 0;
+    };
+    while (n_shared < nlevels && shared(n_shared)) ++n_shared;
+    quad_ok = n_shared <= UPQ_SHARED && nlevels - n_shared <= UPQ_FINE;
+    for (int l = n_shared; l < nlevels && quad_ok; ++l)
+      quad_ok = (long long)h[l] * w[l] * (c / 4) < (1LL << 31);
+  }
+  const char* quad_env = getenv("GX_UPSUM_QUAD");   // GX_UPSUM_QUAD=0: per-pixel kernel (A/B timing)
+  if (quad_env && atoi(quad_env) == 0) quad_ok = false;
+  if (quad_ok) {
+    if (n_shared <= 6 && nlevels - n_shared <= 1)
+      upsample_sum_quad_kernel<6, 1><<<gx_cdiv(d.npix / 4, 8), 256, 0, (cudaStream_t)stream>>>(
+          d, n_shared, out, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo));
+    else
+      upsample_sum_quad_kernel<UPQ_SHARED, UPQ_FINE><<<gx_cdiv(d.npix / 4, 8), 256, 0, (cudaStream_t)stream>>>(
+          d, n_shared, out, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo));
+  } else {
+    upsample_sum_kernel<<<gx_cdiv(d.npix, 8), 256, 0, (cudaStream_t)stream>>>(
+        d, out, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo));
+  }
   GX_LAUNCH_CHECK();
   return GX_OK;
 }

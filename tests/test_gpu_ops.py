@@ -405,6 +405,39 @@ def test_upsample_sum_and_pool_sum(L):
     torch.testing.assert_close((up * x).sum(), (p * f.cpu()).sum(), rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("sizes,out_hw,c", [
+    ((4, 8, 16, 32), (32, 32), 24),          # pyramid: three levels shared by 2x2 quads + one per-pixel level
+    ((4, 8, 16), (32, 32), 516),             # every level shared; channel count not a multiple of 128
+    ((8, 32, 32), (32, 32), 64),             # two per-pixel levels
+    ((3, 6, 12), (12, 12), 8),               # odd coarse size
+    ((4, 6, 12), (12, 12), 8),               # 12/4 = 3: odd factor first -> no shared level
+    ((16, 8), (16, 16), 8),                  # coarse level after the fine one: both loaded per pixel
+    ((16, 4, 8), (16, 16), 8),               # three levels after a per-pixel one -> per-pixel kernel
+    ((5, 10), (10, 14), 8),                  # non-integer factor in x -> per-pixel kernel
+])
+def test_upsample_sum_quad_kernel_is_bit_identical_to_per_pixel_kernel(L, monkeypatch, sizes, out_hw, c):
+    """The 2x2-quad kernel of gx_upsample_sum (levels shared by an aligned output quad are loaded once) performs
+    the per-pixel kernel's additions in the same order: identical bits, and both equal the level-ordered sum of
+    F.interpolate(mode='nearest') (ref swav_clustering.py:112-126)."""
+    torch.manual_seed(11)
+    b = 3
+    oh, ow = out_hw
+    parts = [torch.randn(b, s, s, c).cuda() for s in sizes]
+    res = {}
+    for quad in ("0", "1"):
+        monkeypatch.setenv("GX_UPSUM_QUAD", quad)
+        hi = torch.empty(b * oh * ow, c, dtype=torch.bfloat16, device="cuda")
+        lo = torch.empty_like(hi)
+        res[quad] = (L.upsample_sum(parts, b, oh, ow, planes=(hi, lo)), hi, lo)
+    for x, y in zip(res["0"], res["1"]):
+        assert torch.equal(x, y)
+    ref = torch.zeros(b, oh, ow, c, device="cuda")
+    for p in parts:
+        ref += torch.nn.functional.interpolate(p.permute(0, 3, 1, 2), size=(oh, ow), mode="nearest").permute(0, 2, 3, 1)
+    assert torch.equal(res["1"][0].view(b, oh, ow, c), ref)
+    torch.testing.assert_close(res["1"][1].float() + res["1"][2].float(), ref.view(-1, c), rtol=2e-5, atol=1e-5)
+
+
 @pytest.mark.parametrize("hlen,passes", [(32, 3), (24, 3), (32, 1)])
 def test_per_level_projection_equals_projection_of_upsampled_vectors(L, hlen, passes):
     """Z = Wp . concat_l(upsample(F_l)) computed per resolution (engine.project_all_pixels) against the
