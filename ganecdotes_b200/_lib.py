@@ -17,6 +17,8 @@ GX_MAX_LEVELS = 16
 
 # number of CUDA kernels launched through this module (claimed in bench.py's gpu_launches)
 launch_count = 0
+# separable blur kernel for separable filters (GX_BLUR_SEP=0 / 1 overrides; A/B timing and tests)
+BLUR_SEP_DEFAULT = "1"
 
 
 class GxError(RuntimeError):
@@ -77,6 +79,7 @@ _SIGNATURES = {
     "gx_modulate_split": ([_P, _LL, _P, _P, _P, _I, _LL, _I, _I, _P], _I),
     "gx_modconv": ([C.POINTER(gx_conv_desc), _P], _I),
     "gx_blur_noise_bias_act": ([_P, _P, _I, _I, _I, _I, _P, _LL, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
+    "gx_blur_sep_noise_bias_act": ([_P, _P, _P, _I, _I, _I, _P, _LL, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
     "gx_torgb": ([_P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _P], _I),
     "gx_gemm": ([C.POINTER(gx_gemm_desc), _P], _I),
     "gx_gemm_check": ([C.POINTER(gx_gemm_desc), _P], _I),
@@ -377,7 +380,25 @@ def modconv(x_hi, x_lo, w_hi, w_lo, cout, upsample, passes, demod=None, noise=No
     return out, next_hi, next_lo
 
 
-def blur_noise_bias_act(x_nhwc, fir, pad0, pad1, noise, noise_strength, bias, act, next_style, want_next_lo=True):
+def separable_factors(fir):
+    """(fir_x, fir_y) device vectors with fir = outer(fir_y, fir_x) to fp32 rounding, or None.  One host read of the
+    4x4 filter; callers cache the result (Blur.separable)."""
+    k = fir.detach().double().cpu()
+    if k.dim() != 2 or k.abs().max() == 0:
+        return None
+    i, j = divmod(int(k.abs().argmax()), k.shape[1])
+    piv = k[i, j]
+    root = piv.abs().sqrt()
+    fy = k[:, j] / piv * root * (1.0 if piv > 0 else -1.0)
+    fx = k[i, :] / root
+    if (torch.outer(fy, fx) - k).abs().max() > 1e-7 * k.abs().max():
+        return None
+    return fx.float().to(fir.device).contiguous(), fy.float().to(fir.device).contiguous()
+
+
+def blur_noise_bias_act(x_nhwc, fir, pad0, pad1, noise, noise_strength, bias, act, next_style, want_next_lo=True,
+                        sep=None):
+    """`sep=(fir_x, fir_y)` (separable_factors(fir)): the separable kernel, 4x fewer multiply-adds."""
     lib = load()
     _f32(x_nhwc, "x"), _f32(fir, "fir")
     b, hi, wi, c = x_nhwc.shape
@@ -394,6 +415,14 @@ def blur_noise_bias_act(x_nhwc, fir, pad0, pad1, noise, noise_strength, bias, ac
         nbs = 0 if noise.shape[0] == 1 else ho * wo
     nbytes = 4.0 * b * c * (hi * wi + ho * wo) + (2.0 * b * c * ho * wo * (2 if next_lo is not None else 1)
                                                    if next_hi is not None else 0.0)
+    if sep is not None and kh == 4 and kw == 4 and os.environ.get("GX_BLUR_SEP", BLUR_SEP_DEFAULT) != "0":
+        with timed("blur_noise_bias_act", nbytes):
+            _check(lib.gx_blur_sep_noise_bias_act(_ptr(x_nhwc), _ptr(sep[0]), _ptr(sep[1]), 4, pad0, pad1, _ptr(noise),
+                                                  nbs, _ptr(noise_strength), _ptr(bias), int(act), _ptr(out),
+                                                  _ptr(next_style), _ptr(next_hi), _ptr(next_lo), next_ld, b, hi, wi,
+                                                  c, _stream()), "gx_blur_sep_noise_bias_act")
+        _count()
+        return out, next_hi, next_lo
     with timed("blur_noise_bias_act", nbytes):
         _check(lib.gx_blur_noise_bias_act(_ptr(x_nhwc), _ptr(fir), kh, kw, pad0, pad1, _ptr(noise), nbs,
                                           _ptr(noise_strength), _ptr(bias), int(act), _ptr(out), _ptr(next_style),

@@ -195,6 +195,105 @@ blur_fused_kernel(const float* __restrict__ in, const float* __restrict__ fir, i
   }
 }
 
+// Separable variant (the shipped blur is outer([1,3,3,1]) * const): out = sum_ky gy[ky] * (sum_kx gx[kx] * in).  The kernel
+// above is bound by instruction issue (64 FFMA per 4 channels + a 127-register window that limits occupancy), not
+// by HBM; here a row costs 8 + 8 packed FFMA2 per 4 channels, the register window holds 4 filtered vectors instead
+// of 16 raw ones, and the next row's raw vectors are requested before the current row's epilogue.
+// Threads: channel quad fastest (32 quads or all of them), then x, so the 4-tap horizontal re-reads hit L1.
+template <int KT>
+__global__ void __launch_bounds__(256, 3)
+blur_sep_kernel(const float* __restrict__ in, const float* __restrict__ fir_x, const float* __restrict__ fir_y, int pad0,
+                const float* __restrict__ noise, long long noise_bstride, const float* __restrict__ noise_strength,
+                const float* __restrict__ bias, int act, float* __restrict__ out, const float* __restrict__ next_style,
+                __nv_bfloat16* __restrict__ next_hi, __nv_bfloat16* __restrict__ next_lo, int next_ld, int hi, int wi,
+                int ho, int wo, int c, int cqb) {
+  const int cq = c >> 2;
+  const int cq_groups = cq / cqb;
+  const int g = blockIdx.z % cq_groups, b = blockIdx.z / cq_groups;
+  const int qi = threadIdx.x % cqb, xi = threadIdx.x / cqb;
+  const int q = g * cqb + qi;
+  const int ox = blockIdx.x * (256 / cqb) + xi;
+  if (ox >= wo) return;
+  const int oy0 = blockIdx.y * BLUR_STRIP;
+  const int oy1 = min(ho, oy0 + BLUR_STRIP);
+  float2 gx2[KT], gy2[KT];     // flipped taps (correlation with the flipped filter, ref upfirdn2d_native)
+#pragma unroll
+  for (int i = 0; i < KT; ++i) {
+    const float a = __ldg(fir_x + KT - 1 - i), bq = __ldg(fir_y + KT - 1 - i);
+    gx2[i] = make_float2(a, a);
+    gy2[i] = make_float2(bq, bq);
+  }
+  const float4* src = reinterpret_cast<const float4*>(in) + (long long)b * hi * wi * cq + q;
+  bool col_ok[KT];
+#pragma unroll
+  for (int kx = 0; kx < KT; ++kx) col_ok[kx] = (ox + kx - pad0 >= 0) && (ox + kx - pad0 < wi);
+  auto load_raw = [&](int iy, float4 (&v)[KT]) {
+    const bool row_ok = iy >= 0 && iy < hi;
+#pragma unroll
+    for (int kx = 0; kx < KT; ++kx)
+      v[kx] = (row_ok && col_ok[kx]) ? __ldg(src + ((long long)iy * wi + (ox + kx - pad0)) * cq)
+                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+  };
+  auto hfilter = [&](const float4 (&v)[KT]) {
+    float2 a = make_float2(0.f, 0.f), bq = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int kx = 0; kx < KT; ++kx) {
+      a = fma2(make_float2(v[kx].x, v[kx].y), gx2[kx], a);
+      bq = fma2(make_float2(v[kx].z, v[kx].w), gx2[kx], bq);
+    }
+    return make_float4(a.x, a.y, bq.x, bq.y);
+  };
+  float4 hw[KT], raw[KT];
+  hw[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll
+  for (int ky = 0; ky < KT - 1; ++ky) {
+    load_raw(oy0 + ky - pad0, raw);
+    hw[ky + 1] = hfilter(raw);
+  }
+  load_raw(oy0 + KT - 1 - pad0, raw);
+  const float nstr = noise ? __ldg(noise_strength) : 0.f;
+  float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
+  if (bias) bs = __ldg(reinterpret_cast<const float4*>(bias) + q);
+  float4 st = make_float4(1.f, 1.f, 1.f, 1.f);
+  if (next_style) st = __ldg(reinterpret_cast<const float4*>(next_style) + (long long)b * cq + q);
+  for (int oy = oy0; oy < oy1; ++oy) {
+#pragma unroll
+    for (int ky = 0; ky < KT - 1; ++ky) hw[ky] = hw[ky + 1];
+    hw[KT - 1] = hfilter(raw);
+    float nz = 0.f;
+    if (noise) nz = __ldg(noise + (long long)b * noise_bstride + (long long)oy * wo + ox);
+    if (oy + 1 < oy1) load_raw(oy + KT - pad0, raw);      // next row: in flight during this row's epilogue
+    float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
+#pragma unroll
+    for (int ky = 0; ky < KT; ++ky) {
+      a01 = fma2(make_float2(hw[ky].x, hw[ky].y), gy2[ky], a01);
+      a23 = fma2(make_float2(hw[ky].z, hw[ky].w), gy2[ky], a23);
+    }
+    float4 acc = make_float4(a01.x, a01.y, a23.x, a23.y);
+    if (noise) {
+      nz *= nstr;
+      acc.x += nz; acc.y += nz; acc.z += nz; acc.w += nz;
+    }
+    acc.x += bs.x; acc.y += bs.y; acc.z += bs.z; acc.w += bs.w;
+    if (act) {
+      const float s2 = 1.41421356237309515f;
+      acc.x = (acc.x > 0.f ? acc.x : acc.x * 0.2f) * s2;
+      acc.y = (acc.y > 0.f ? acc.y : acc.y * 0.2f) * s2;
+      acc.z = (acc.z > 0.f ? acc.z : acc.z * 0.2f) * s2;
+      acc.w = (acc.w > 0.f ? acc.w : acc.w * 0.2f) * s2;
+    }
+    const long long o = (((long long)b * ho + oy) * wo + ox) * cq + q;
+    gx_stg_stream(reinterpret_cast<float4*>(out) + o, acc);
+    if (next_hi) {
+      uint2 h, l;
+      gx_split4(make_float4(acc.x * st.x, acc.y * st.y, acc.z * st.z, acc.w * st.w), h, l);
+      const long long on = (((long long)b * ho + oy) * wo + ox) * (next_ld >> 2) + q;
+      reinterpret_cast<uint2*>(next_hi)[on] = h;
+      if (next_lo) reinterpret_cast<uint2*>(next_lo)[on] = l;
+    }
+  }
+}
+
 // ToRGB: warp per pixel, 3 dot products over C with the per-sample modulated 1x1 weights.
 __global__ void torgb_kernel(const float* __restrict__ x, const float* __restrict__ w, float w_scale,
                              const float* __restrict__ s, const float* __restrict__ bias,
@@ -296,6 +395,33 @@ extern "C" int gx_blur_noise_bias_act(const float* in, const float* fir, int kh,
       in, fir, pad0, noise, noise_batch_stride, noise_strength, bias, act, out, next_style,
       reinterpret_cast<__nv_bfloat16*>(next_hi), reinterpret_cast<__nv_bfloat16*>(next_lo), next_ld, batch, hi, wi, ho,
       wo, c);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_blur_sep_noise_bias_act(const float* in, const float* fir_x, const float* fir_y, int ntaps, int pad0,
+                                          int pad1, const float* noise, long long noise_batch_stride,
+                                          const float* noise_strength, const float* bias, int act, float* out,
+                                          const float* next_style, void* next_hi, void* next_lo, int next_ld,
+                                          int batch, int hi, int wi, int c, void* stream) {
+  if (next_ld <= 0) next_ld = c;
+  GX_CHECK_ARG(next_ld >= c && next_ld % 4 == 0);
+  GX_CHECK_ARG(in && fir_x && fir_y && out && batch > 0 && hi > 0 && wi > 0);
+  GX_CHECK_ARG(c % 4 == 0 && ntaps == 4);
+  GX_CHECK_ARG(noise == nullptr || noise_strength != nullptr);
+  GX_CHECK_ARG(next_style == nullptr || next_hi != nullptr);
+  const int ho = hi + pad0 + pad1 - ntaps + 1, wo = wi + pad0 + pad1 - ntaps + 1;
+  GX_CHECK_ARG(ho > 0 && wo > 0);
+  const int cq = c / 4;
+  int cqb = cq < 32 ? cq : 32;
+  while (cqb > 1 && (cq % cqb != 0 || 256 % cqb != 0)) --cqb;
+  const int tx = 256 / cqb;
+  dim3 grid(gx_cdiv(wo, tx), gx_cdiv(ho, BLUR_STRIP), batch * (cq / cqb));
+  GX_CHECK_ARG(grid.y <= 65535 && grid.z <= 65535);
+  blur_sep_kernel<4><<<grid, 256, 0, (cudaStream_t)stream>>>(
+      in, fir_x, fir_y, pad0, noise, noise_batch_stride, noise_strength, bias, act, out, next_style,
+      reinterpret_cast<__nv_bfloat16*>(next_hi), reinterpret_cast<__nv_bfloat16*>(next_lo), next_ld, hi, wi, ho, wo, c,
+      cqb);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }

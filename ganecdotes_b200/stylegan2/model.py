@@ -79,6 +79,15 @@ class Blur(nn.Module):
             kernel = kernel * (upsample_factor ** 2)
         self.register_buffer("kernel", kernel)
         self.pad = pad
+        self._sep = None
+
+    def separable(self):
+        """(fir_x, fir_y) of the current `kernel` buffer if it is an outer product (every filter built by
+        make_kernel from a 1-D list is), else None; recomputed when the buffer changes (load_state_dict, .to())."""
+        key = (self.kernel.data_ptr(), self.kernel._version, self.kernel.device)
+        if self._sep is None or self._sep[0] != key:
+            self._sep = (key, L.separable_factors(self.kernel))
+        return self._sep[1]
 
     def forward(self, input):
         return upfirdn2d(input, self.kernel, pad=self.pad)
@@ -171,7 +180,7 @@ class ModulatedConv2d(nn.Module):
         out, _, _ = L.modconv(x_hi, x_lo, w_hi, w_lo, self.out_channel, self.upsample, passes, demod=demod)
         if self.upsample:
             out, _, _ = L.blur_noise_bias_act(out, self.blur.kernel, self.blur.pad[0], self.blur.pad[1], None, None,
-                                              None, 0, None)
+                                              None, 0, None, sep=self.blur.separable())
         return out.permute(0, 3, 1, 2)
 
     def __repr__(self):
@@ -348,7 +357,7 @@ class Generator(nn.Module):
                 tmp, _, _ = L.modconv(x_hi, x_lo, w_hi, w_lo, conv.out_channel, True, passes, demod=demods[n],
                                       cin_true=conv.in_channel, tag=self._conv_tag(x_hi))
                 f, x_hi, x_lo = L.blur_noise_bias_act(tmp, conv.blur.kernel, conv.blur.pad[0], conv.blur.pad[1], nz,
-                                                      strength, bias, 1, nxt, want_lo)
+                                                      strength, bias, 1, nxt, want_lo, sep=conv.blur.separable())
             else:
                 f, x_hi, x_lo = L.modconv(x_hi, x_lo, w_hi, w_lo, conv.out_channel, False, passes, demod=demods[n],
                                           noise=nz, noise_strength=strength, bias=bias, act=1, next_style=nxt,

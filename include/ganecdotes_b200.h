@@ -127,6 +127,15 @@ int gx_blur_noise_bias_act(const float* in, const float* fir, int kh, int kw, in
                            const float* bias, int act, float* out, const float* next_style, void* next_hi,
                            void* next_lo, int next_ld, int batch, int hi, int wi, int c, void* stream);
 
+/* The same stage for a separable filter fir[ky][kx] = fir_y[ky] * fir_x[kx] (the shipped blur, make_kernel of a
+ * 1-D kernel, ref model.py:113-121): horizontal then vertical 4-tap pass, 16 instead of 64 multiply-adds per 4
+ * channels (the 2-D form is bound by instruction issue).  fir_x, fir_y: device fp32 [ntaps], unflipped; ntaps = 4.
+ * Results differ from the 2-D form by rounding only. */
+int gx_blur_sep_noise_bias_act(const float* in, const float* fir_x, const float* fir_y, int ntaps, int pad0, int pad1,
+                               const float* noise, long long noise_batch_stride, const float* noise_strength,
+                               const float* bias, int act, float* out, const float* next_style, void* next_hi,
+                               void* next_lo, int next_ld, int batch, int hi, int wi, int c, void* stream);
+
 /* ToRGB: 1x1 modulated conv without demodulation + bias (+ skip), ref: model.py:435-454.
  * x fp32 NHWC [B,H,W,C]; w [3,C]; s [B,C]; bias [3]; skip (already upsampled) [B,3,H,W] or NULL;
  * out [B,3,H,W] NCHW fp32. */

@@ -405,6 +405,45 @@ def test_upsample_sum_and_pool_sum(L):
     torch.testing.assert_close((up * x).sum(), (p * f.cpu()).sum(), rtol=1e-4, atol=1e-3)
 
 
+@pytest.mark.parametrize("b,res,c,pads", [(2, 8, 512, (1, 1)), (3, 16, 128, (1, 1)), (2, 33, 16, (1, 1)),
+                                          (1, 12, 24, (2, 1)), (2, 64, 64, (1, 1)), (1, 9, 4, (0, 3))])
+def test_blur_separable_kernel_matches_2d_kernel_and_oracle(L, monkeypatch, b, res, c, pads):
+    """gx_blur_sep_noise_bias_act (horizontal + vertical 4-tap pass) against the 2-D kernel and against the oracle's
+    upfirdn2d + noise + bias + leaky-relu (ref model.py:166-182, 371-382, 15-43)."""
+    torch.manual_seed(res + c)
+    fir = (O.make_fir_kernel([1, 3, 3, 1]) * 4)
+    x = torch.randn(b, res, res, c)
+    ho = res + pads[0] + pads[1] - 3
+    noise = torch.randn(1, ho, ho)
+    strength = torch.tensor([0.37])
+    bias = torch.randn(c)
+    style = torch.randn(b, c)
+    sep = L.separable_factors(fir.cuda())
+    assert sep is not None
+    outs = {}
+    # the 2-D kernel maps min(C/4, 256) channel quads onto a 256-thread block: C/4 must divide 256
+    modes = ("0", "1") if 256 % min(c // 4, 256) == 0 else ("1",)
+    for mode in modes:
+        monkeypatch.setenv("GX_BLUR_SEP", mode)
+        outs[mode] = L.blur_noise_bias_act(x.cuda(), fir.cuda(), pads[0], pads[1], noise.cuda(), strength.cuda(),
+                                           bias.cuda(), 1, style.cuda(), sep=sep)
+    if "0" in outs:
+        torch.testing.assert_close(outs["0"][0], outs["1"][0], rtol=2e-6, atol=4e-6)
+        torch.testing.assert_close(outs["0"][1].float() + outs["0"][2].float(),
+                                   outs["1"][1].float() + outs["1"][2].float(), rtol=3e-5, atol=1e-5)
+    ref = O.upfirdn2d(x.permute(0, 3, 1, 2).contiguous(), fir, pad=pads) + strength * noise[None]
+    ref = O.fused_leaky_relu(ref, bias)
+    torch.testing.assert_close(outs["1"][0].cpu().permute(0, 3, 1, 2), ref, rtol=1e-5, atol=2e-6)
+    planes_sum = outs["1"][1].float() + outs["1"][2].float()
+    torch.testing.assert_close(planes_sum[..., :c].cpu(), (ref * style[:, :, None, None]).permute(0, 2, 3, 1),
+                               rtol=3e-5, atol=1e-5)
+    # no noise / bias / activation (the up-conv of ToRGB-free callers)
+    monkeypatch.setenv("GX_BLUR_SEP", "1")
+    o = L.blur_noise_bias_act(x.cuda(), fir.cuda(), pads[0], pads[1], None, None, None, 0, None, sep=sep)[0]
+    torch.testing.assert_close(o.cpu().permute(0, 3, 1, 2),
+                               O.upfirdn2d(x.permute(0, 3, 1, 2).contiguous(), fir, pad=pads), rtol=1e-5, atol=2e-6)
+
+
 @pytest.mark.parametrize("sizes,out_hw,c", [
     ((4, 8, 16, 32), (32, 32), 24),          # pyramid: three levels shared by 2x2 quads + one per-pixel level
     ((4, 8, 16), (32, 32), 516),             # every level shared; channel count not a multiple of 128

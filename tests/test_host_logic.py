@@ -91,3 +91,19 @@ def test_config_tables_match_the_reference_configs():
     import pretrain
     a = pretrain.parse(["--model", "pidray-256", "--num_test_samples", "3"])
     assert a.model == "pidray-256" and a.num_test_samples == 3 and a.out_dir == "results/pretrain_default_ffhq/"
+
+
+def test_separable_factors_of_blur_filters():
+    """host side of the separable blur kernel: make_kernel filters factor exactly, a generic 4x4 filter does not"""
+    from ganecdotes_b200._lib import separable_factors
+    k = torch.tensor([1., 3., 3., 1.])
+    k2 = k[None, :] * k[:, None]
+    k2 = k2 / k2.sum() * 4
+    fx, fy = separable_factors(k2)
+    assert torch.equal(torch.outer(fy, fx), k2)
+    a, b = torch.tensor([1., -2., 0.5, 3.]), torch.tensor([0.1, 0.2, -0.3, 0.4])
+    fx, fy = separable_factors(torch.outer(a, b))
+    torch.testing.assert_close(torch.outer(fy, fx), torch.outer(a, b), rtol=1e-6, atol=1e-7)
+    torch.manual_seed(0)
+    assert separable_factors(torch.randn(4, 4)) is None
+    assert separable_factors(torch.zeros(4, 4)) is None

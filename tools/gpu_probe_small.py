@@ -27,19 +27,27 @@ def med_ms(fn, n=20):
 fir = torch.tensor([1., 3., 3., 1.])
 fir = (fir[:, None] * fir[None, :] / 64 * 4).to(dev)
 B = 16
-total = 0.0
+total = {"0": 0.0, "1": 0.0}
+sep = L.separable_factors(fir)
 for res, c in ((8, 512), (16, 512), (32, 512), (64, 512), (128, 256), (256, 128)):
     x = torch.randn(B, res + 1, res + 1, c, device=dev)
     noise = torch.randn(1, res, res, device=dev)
     strength = torch.full((1,), 0.3, device=dev)
     bias = torch.randn(c, device=dev)
     style = torch.randn(B, c, device=dev)
-    ms = med_ms(lambda: L.blur_noise_bias_act(x, fir, 1, 1, noise, strength, bias, 1, style))
     nbytes = 4.0 * B * c * ((res + 1) ** 2 + res * res) + 4.0 * B * c * res * res
-    total += ms
-    print(f"blur {res:4d}^2 c={c:3d}: {ms:.4f} ms  {nbytes / ms / 1e6:7.0f} GB/s ({nbytes / ms / 1e6 / PEAK:.0%})")
-    del x
-print(f"blur total per 16 image-views: {total:.3f} ms")
+    outs = {}
+    for mode in ("0", "1"):            # 2-D kernel / separable kernel
+        os.environ["GX_BLUR_SEP"] = mode
+        f = lambda: L.blur_noise_bias_act(x, fir, 1, 1, noise, strength, bias, 1, style, sep=sep)
+        outs[mode] = f()[0]
+        ms = med_ms(f)
+        total[mode] += ms
+        print(f"blur {res:4d}^2 c={c:3d} sep={mode}: {ms:.4f} ms  {nbytes / ms / 1e6:7.0f} GB/s ({nbytes / ms / 1e6 / PEAK:.0%})")
+    print("   max |sep - 2d|:", (outs["0"] - outs["1"]).abs().max().item())
+    del x, outs
+os.environ.pop("GX_BLUR_SEP")
+print(f"blur total per 16 image-views: 2-D {total['0']:.3f} ms, separable {total['1']:.3f} ms")
 
 # upsample_sum: 7 levels 4^2..256^2, 512 channels, 8 images (one view of the bench step); quad kernel vs per-pixel
 b = 8
