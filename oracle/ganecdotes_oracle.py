@@ -28,7 +28,6 @@ Reference citations are relative to /root/reference.
 import math
 from typing import Dict, List, Optional, Sequence, Tuple
 
-import numpy as np
 import torch
 import torch.nn.functional as F
 

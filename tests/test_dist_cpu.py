@@ -5,7 +5,6 @@ same contract; the product's own loop / all-reduce code is what runs."""
 import os
 import socket
 
-import numpy as np
 import pytest
 import torch
 import torch.distributed as dist

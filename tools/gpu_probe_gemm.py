@@ -1,6 +1,6 @@
 """First-contact probe of the tcgen05 engine on a B200: runs each GEMM / conv variant and
 prints max errors against fp64 torch.  Run under `timeout`; a protocol bug traps."""
-import sys, os, time
+import sys, os
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import torch
 from ganecdotes_b200 import _lib as L
