@@ -76,6 +76,15 @@ def _map_pool():
     return _MAP_POOL
 
 
+def patch_pick_rows(h: int, w: int, pick: int, patch_size: int) -> torch.Tensor:
+    """Pixel indices (row-major, int64) of the square crop [pick:pick+P, pick:pick+P] - what
+    sampling_method == 'patch' feeds the projection (ref swav_clustering.py:150-158: the same offset on both
+    axes, slices clipped at the border like Python's).  Used in place of a permutation: the P*P rows of a patch."""
+    ys = torch.arange(pick, min(pick + patch_size, h))
+    xs = torch.arange(pick, min(pick + patch_size, w))
+    return (ys[:, None] * w + xs[None, :]).reshape(-1)
+
+
 def build_row_indices(h, w, view: ViewDraws, perms, patch_size, device, count_fill=False):
     """[P, B*N] int32 (row_src), [B*N] int32 (row_img) for one view; with count_fill also the number
     of samples that fall on rotation fill (row_src == -1), counted on the host."""

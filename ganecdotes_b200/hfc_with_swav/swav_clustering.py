@@ -10,7 +10,7 @@ Differences that are deliberate and documented:
   * `swav_args['batch_latents']` (default 1 = the reference) trains on several latents per
     optimiser step with joint-batch Sinkhorn; with torch.distributed initialised the batch
     is sharded over ranks and only the Sinkhorn marginals and the gradients are all-reduced;
-  * only `projn_nw == 'linear'` and `sampling_method == 'random'` (every shipped config).
+  * only `projn_nw == 'linear'` (every shipped config); `sampling_method` 'random' (shipped) and 'patch'.
 All random draws are made on the CPU generators (torch / numpy), a few KB per step.
 """
 import os
@@ -100,8 +100,16 @@ class SwAVClustering(object):
             return E.DistGroup(dist.group.WORLD, dist.get_rank(), dist.get_world_size())
         return None
 
+    def _rows_per_patch(self):
+        """rows one latent contributes per patch: patch_size pixels ('random') or a patch_size x patch_size
+        crop ('patch', ref :150-158); None = every pixel."""
+        ps = self.swav_args['patch_size']
+        if ps is None or ps == self.model.size:
+            return None
+        return ps * ps if self.swav_args['sampling_method'] == 'patch' else ps
+
     def _step_config(self):
-        return E.StepConfig(hlen=self.swav_args['hlen'], patch_size=self.swav_args['patch_size'],
+        return E.StepConfig(hlen=self.swav_args['hlen'], patch_size=self._rows_per_patch(),
                             num_patches=self.swav_args['num_patches'], niters=self.niters, eps=self.eps,
                             temperature=self.swav_args['temperature'], truncation=self.truncation,
                             perturb_std=list(self.perturb_args['perturb_std']),
@@ -150,8 +158,15 @@ class SwAVClustering(object):
             rot.append(one)
         perms = []
         full = self.swav_args['patch_size'] is None or self.swav_args['patch_size'] == h
+        by_patch = self.swav_args['sampling_method'] == 'patch'
         for _p in range(self.swav_args['num_patches']):
-            perms.append([torch.arange(h * w) if full else torch.randperm(h * w) for _ in range(b_global)])
+            if full:
+                perms.append([torch.arange(h * w) for _ in range(b_global)])
+            elif by_patch:      # ref :383-385: one offset per patch, used on both axes
+                perms.append([E.patch_pick_rows(h, w, int(np.random.choice(h - self.swav_args['patch_size'])),
+                                                self.swav_args['patch_size']) for _ in range(b_global)])
+            else:
+                perms.append([torch.randperm(h * w) for _ in range(b_global)])
 
         def mk(views, vi):
             return E.ViewDraws(layer_no=[v[0][0] for v in views], pert_z=torch.cat([v[1] for v in views], 0),
@@ -191,15 +206,19 @@ class SwAVClustering(object):
         return self.projection[0].weight.data
 
     def get_swav_codes_from_hidden_features(self, hfeat, new_shape=None, picks=None, train=False):
-        """ref :133-182 (sampling_method == 'random').  hfeat [1, D, H, W]."""
-        if self.swav_args['sampling_method'] != 'random':
-            raise NotImplementedError("sampling_method: only 'random' (every shipped config)")
+        """ref :133-182.  hfeat [1, D, H, W]; picks: a permutation ('random') or the crop offset ('patch')."""
+        if self.swav_args['sampling_method'] not in ('random', 'patch'):
+            raise NotImplementedError("sampling_method: 'random' or 'patch'")
         b, d, h, w = hfeat.shape
         x = hfeat.permute(0, 2, 3, 1).contiguous().float()
         row_src = row_img = None
         n = b * h * w
         if picks is not None:
-            n = self.swav_args['patch_size']
+            if self.swav_args['sampling_method'] == 'patch':
+                picks = E.patch_pick_rows(h, w, int(picks), self.swav_args['patch_size'])
+                n = picks.numel()
+            else:
+                n = self.swav_args['patch_size']
             row_src = picks[:n].to(torch.int32).to(self.device)
             row_img = torch.zeros(n, dtype=torch.int32, device=self.device)
         w_proj = self.projection[0].weight.data
@@ -235,8 +254,8 @@ class SwAVClustering(object):
         if self.swav_args.get('add_local_loss', False):
             raise NotImplementedError("add_local_loss is broken in the reference (SURVEY §8 quirk 9) and off "
                                       "in every shipped config")
-        if self.swav_args['sampling_method'] != 'random':
-            raise NotImplementedError("sampling_method: only 'random' (every shipped config)")
+        if self.swav_args['sampling_method'] not in ('random', 'patch'):
+            raise NotImplementedError("sampling_method: 'random' (every shipped config) or 'patch'")
         # test latents + their (unused) images: draws only (ref :222-238)
         for _ in range(num_test_samples):
             torch.randn(1, self.model_config.latent_dim)

@@ -404,6 +404,13 @@ def sample_rows(hfeat: torch.Tensor, perm: torch.Tensor, patch_size: int) -> tor
     return flat[:, perm][:, :patch_size].t()
 
 
+def sample_patch_rows(hfeat: torch.Tensor, pick: int, patch_size: int) -> torch.Tensor:
+    """sampling_method == 'patch': hfeat[:, :, pick:pick+P, pick:pick+P] flattened row-major -> [P*P, D]
+    (swav_clustering.py:150-158; the same offset `pick = np.random.choice(h - P)` on both axes, :383-385)."""
+    crop = hfeat[:, :, pick:pick + patch_size, pick:pick + patch_size]
+    return crop[0].flatten(1).t()
+
+
 def swav_scores(rows, w_proj, w_proto, b_proto):
     """projection -> L2 normalise -> prototype (with bias)  (swav_clustering.py:171-175)."""
     z = rows @ w_proj.t()

@@ -138,15 +138,17 @@ class Recorder:
         return inner
 
 
-def golden_swav():
+def golden_swav(name="swav", sampling_method='random', patch=100):
+    """sampling_method='patch' (ref swav_clustering.py:150-158, 383-385): `patch` is the side of a square crop at
+    (pick, pick), pick = np.random.choice(h - patch) per patch; saved as swav_patch.npz (training part only)."""
     gen, sd = build_reference_generator()
     swav = ref.swav
     hlen = 512 + 1024 + 1024
-    nclasses, nproto, patch, npatch, nepochs = 64, 48, 100, 2, 2
+    nclasses, nproto, npatch, nepochs = 64, 48, 2, 2
     cfg = dict(
         perturb_args=dict(truncation=0.7, n_layers=3, n_samples=1, layer_no=None,
                           perturb_std=[1.0, 0.5, 1.0]),
-        swav_args=dict(num_epochs=nepochs, num_samples=1, num_patches=npatch, sampling_method='random',
+        swav_args=dict(num_epochs=nepochs, num_samples=1, num_patches=npatch, sampling_method=sampling_method,
                        patch_size=patch, hf_interp='nearest', warmup_epochs=nepochs, start_warmup=0.01,
                        use_scheduler=False, base_lr=0.01, final_lr=0.0001, trust_coeff=0.01,
                        freeze_prototype_niters=313, train_args=dict(lr=0.01, momentum=0.9),
@@ -224,35 +226,44 @@ def golden_swav():
                perturb_std=np.array([1.0, 0.5, 1.0]))
     it = iter(train_log)
     for e in range(nepochs):
-        name, z = next(it)
-        assert name == "randn" and tuple(z.shape) == (1, GEN_STYLE), (name, z.shape)
+        kind, z = next(it)
+        assert kind == "randn" and tuple(z.shape) == (1, GEN_STYLE), (kind, z.shape)
         out[f"s{e}_z"] = z
         for v in "st":
-            name, layer = next(it)
-            assert name == "choice", name
+            kind, layer = next(it)
+            assert kind == "choice", kind
             out[f"s{e}_{v}_layer"] = np.int64(layer)
             pz = []
             for _ in range(6):
-                name, d = next(it)
-                assert name == "randn_like", name
+                kind, d = next(it)
+                assert kind == "randn_like", kind
                 pz.append(d)
             out[f"s{e}_{v}_pert_z"] = torch.cat(pz, 0)
         for v in "st":
-            name, ang = next(it)
-            assert name == "angle", name
+            kind, ang = next(it)
+            assert kind == "angle", kind
             out[f"s{e}_{v}_angle"] = np.float64(ang)
-            name, r = next(it)
-            assert name == "rand", name
+            kind, r = next(it)
+            assert kind == "rand", kind
             out[f"s{e}_{v}_flip"] = np.bool_(bool(r < 0.5))
             out[f"s{e}_{v}_flip_u"] = r
         for p in range(npatch):
-            name, perm = next(it)
-            assert name == "randperm", name
-            out[f"s{e}_perm{p}"] = perm
+            kind, perm = next(it)
+            if sampling_method == 'patch':
+                assert kind == "choice", kind
+                out[f"s{e}_pick{p}"] = np.int64(perm)
+            else:
+                assert kind == "randperm", kind
+                out[f"s{e}_perm{p}"] = perm
     rest = list(it)
     assert not rest, [n for n, _ in rest]
-    save("swav", **out)
-    print("losses", losses)
+    if sampling_method == 'patch':     # the training part is what differs; drop the (large) inference arrays
+        # (the initial projection weights equal swav.npz's: same seed, same constructor)
+        for k in ("preds", "labels", "pred_w", "sk_scores_s", "sk_scores_t", "sk_q_s", "sk_q_t", "sk_loss",
+                  "init_w_proj", "mean_latent_z"):
+            out.pop(k)
+    save(name, **out)
+    print(name, "losses", losses)
 
 
 # ---------------------------------------------------------------------------------------
@@ -323,8 +334,12 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "segmentor":
         golden_segmentor()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "swav_patch":
+        golden_swav("swav_patch", 'patch', 10)
+        sys.exit(0)
     golden_ops()
     golden_generator()
     golden_swav()
+    golden_swav("swav_patch", 'patch', 10)
     golden_baggan()
     golden_segmentor()

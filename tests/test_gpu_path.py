@@ -149,6 +149,42 @@ def test_pretrain_matches_reference_golden(gen, tmp_path):
     assert mism.float().mean().item() < 0.02
 
 
+def test_pretrain_with_patch_sampling_matches_reference_golden(gen, tmp_path):
+    """sampling_method='patch' (square crops at a random offset, ref swav_clustering.py:150-158, 383-385): seeded
+    SwAVClustering.pretrain vs the seeded CPU run of the unmodified reference (tests/golden/swav_patch.npz)."""
+    from ganecdotes_b200.hfc_with_swav import SwAVClustering
+    g = load("swav_patch")
+    base = load("swav")
+    cfg, mc = golden_cfg(g)
+    cfg["swav_args"]["sampling_method"] = 'patch'
+    assert cfg["swav_args"]["patch_size"] == 10
+    losses = []
+    tb = types.SimpleNamespace(add_scalar=lambda name, val, step: losses.append(float(val)))
+    torch.manual_seed(11)
+    np.random.seed(11)
+    obj = SwAVClustering(gen, mc, out_dir=str(tmp_path), device='cuda', tb=tb, **cfg)
+    recorded = []
+    orig = obj.draw_step
+    obj.draw_step = lambda b: recorded.append(orig(b)) or recorded[-1]
+    obj.pretrain(None, num_test_samples=0)
+    from ganecdotes_b200.hfc_with_swav.engine import patch_pick_rows
+    for e, d in enumerate(recorded):        # identical random stream, crops at the recorded offsets
+        assert torch.equal(d.z, g[f"s{e}_z"])
+        assert d.view_t.angle[0] == float(g[f"s{e}_t_angle"])
+        for p in range(2):
+            assert torch.equal(d.perms[p][0], patch_pick_rows(16, 16, int(g[f"s{e}_pick{p}"]), 10))
+    ref_losses = g["losses"].tolist()
+    assert len(losses) == len(ref_losses)
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) < 2e-3 * abs(b), (losses, ref_losses)
+    fin = [obj.projection[0].weight.data.cpu(), obj.prototype.weight.data.cpu(), obj.prototype.bias.data.cpu()]
+    ref_fin = [g["final_w_proj"], g["final_w_proto"], g["final_b_proto"]]
+    ref_init = [base["init_w_proj"], torch.nn.functional.normalize(g["init_w_proto"], dim=1), g["init_b_proto"]]
+    for f, rf, ri in zip(fin, ref_fin, ref_init):
+        upd = (rf - ri).norm().item()
+        assert (f - rf).norm().item() < 3e-2 * upd, ((f - rf).norm().item(), upd)
+
+
 def make_draws(b, d, n_layers, hw, npatch, seed):
     from ganecdotes_b200.hfc_with_swav import engine as E
     g = torch.Generator().manual_seed(seed)

@@ -107,3 +107,18 @@ def test_separable_factors_of_blur_filters():
     torch.manual_seed(0)
     assert separable_factors(torch.randn(4, 4)) is None
     assert separable_factors(torch.zeros(4, 4)) is None
+
+
+def test_patch_pick_rows_are_the_reference_crop():
+    """sampling_method='patch': the rows of hfeat[:, :, pick:pick+P, pick:pick+P].flatten(1) (ref
+    swav_clustering.py:150-158) are the pixels engine.patch_pick_rows lists, in the same order."""
+    from ganecdotes_b200.hfc_with_swav.engine import patch_pick_rows
+    from oracle import ganecdotes_oracle as O
+    torch.manual_seed(3)
+    h = w = 16
+    hf = torch.randn(1, 7, h, w)
+    for pick, p in [(0, 10), (3, 10), (5, 10), (12, 4), (14, 5)]:      # the last one is clipped at the border
+        idx = patch_pick_rows(h, w, pick, p)
+        ref = O.sample_patch_rows(hf, pick, p)
+        assert torch.equal(hf[0].flatten(1)[:, idx].t(), ref)
+    assert patch_pick_rows(h, w, 3, 10).numel() == 100
