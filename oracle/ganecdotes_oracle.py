@@ -506,6 +506,79 @@ def swav_step(rows_s: List[torch.Tensor], rows_t: List[torch.Tensor], w_proj, w_
 
 
 # --------------------------------------------------------------------------------------
+# SimCLR baseline head  (baseline/hfc_with_simclr/simclr_clustering.py)
+# --------------------------------------------------------------------------------------
+
+def simclr_projection(x, w1, bn_w, bn_b, w2, bn_mean=None, bn_var=None, train=True, bn_eps=1e-5):
+    """Linear(no bias) -> BatchNorm1d -> LeakyReLU(0.01) -> Linear(no bias)  (simclr_clustering.py:150-160).
+    train: batch statistics (biased variance), returns also the batch mean / unbiased variance that update the
+    running statistics (momentum 0.1); eval: the running statistics."""
+    h = x @ w1.t()
+    if train:
+        mean = h.mean(0)
+        var_b = h.var(0, unbiased=False)
+        hn = (h - mean) / torch.sqrt(var_b + bn_eps)
+        stats = (mean.detach(), h.var(0, unbiased=True).detach())
+    else:
+        hn = (h - bn_mean) / torch.sqrt(bn_var + bn_eps)
+        stats = None
+    hn = hn * bn_w + bn_b
+    return F.leaky_relu(hn, 0.01) @ w2.t(), stats
+
+
+def simclr_loss(scores, temperature: float):
+    """The reference's loops (simclr_clustering.py:235-265) in closed form.  scores [2B, C] = projection output,
+    rows interleaved s_0, t_0, s_1, t_1, ...;  sim = cosine similarity / T (nn.CosineSimilarity(dim=0), eps 1e-8);
+    l[i, j] = -log(exp(sim_ij) / sum_{m != i} exp(sim_im));
+    loss = sum_k (l[2k-1, 2k] + l[2k, 2k-1]) / (2B).  Quirk kept: the pairs are (2k-1, 2k) - for k = 0 row -1 is
+    the LAST row (Python indexing) - i.e. t_{k-1} with s_k, not the two views of one pixel."""
+    n2 = scores.shape[0]
+    # Second quirk kept: the reference transposes the scores to [C, 2B] (:235) and then indexes ROWS with the sample
+    # counters i, j (:240) - the "sample" vectors of the similarity are the first 2B CHANNELS, each a vector over
+    # the 2B samples (needs C >= 2B: 512 >= 40 in the shipped config).
+    assert scores.shape[1] >= n2
+    vec = scores.t()[:n2]
+    nrm = vec.norm(dim=1)
+    sim = (vec @ vec.t()) / torch.clamp(nrm[:, None] * nrm[None, :], min=1e-8) / temperature
+    e = torch.exp(sim)
+    den = e.sum(1) - e.diagonal()
+    lmat = -(sim - torch.log(den)[:, None])
+    k = torch.arange(n2 // 2)
+    a = (2 * k - 1) % n2
+    return (lmat[a, 2 * k] + lmat[2 * k, a]).sum() / n2
+
+
+def simclr_step(rows_s, rows_t, params, temperature, bufs=None, bn_running=None, lr=0.01, momentum=0.9, trust=0.01):
+    """One iteration of SimCLRClustering.pretrain (simclr_clustering.py:175-273) given the sampled, channel-
+    normalised per-pixel rows of the two views ([B, D] each).  params = [w1, bn_w, bn_b, w2]."""
+    p = [t.detach().clone().requires_grad_(True) for t in params]
+    x = torch.stack([rows_s, rows_t], 1).reshape(-1, rows_s.shape[1])       # [:, ::2] = s, [:, 1::2] = t
+    scores, stats = simclr_projection(x, *p)
+    loss = simclr_loss(scores, temperature)
+    loss.backward()
+    grads = [t.grad for t in p]
+    new_p, new_b = larc_sgd_step([t.detach() for t in p], grads, bufs or [None] * 4, lr, momentum, trust)
+    if bn_running is None:
+        bn_running = (torch.zeros_like(stats[0]), torch.ones_like(stats[1]))
+    run = (0.9 * bn_running[0] + 0.1 * stats[0], 0.9 * bn_running[1] + 0.1 * stats[1])
+    return dict(loss=loss.detach(), grads=grads, params=new_p, bufs=new_b, bn_running=run, scores=scores.detach())
+
+
+def simclr_predict_codes(sd, w, mean_latent, truncation, params, bn_running, hlen):
+    """predict_simclr_codes (simclr_clustering.py:362-401) with the projection in eval mode: channel-normalised
+    per-pixel vectors -> projection -> codes [B,C,H,W], first arg-max label map."""
+    wt = mean_latent + truncation * (w - mean_latent) if truncation < 1 else w
+    latent = wt.unsqueeze(1).repeat(1, n_latent_of(sd), 1)
+    _, feats = synthesis(sd, latent)
+    hf = F.normalize(pixel_feature_vectors(feats, hlen), dim=1)
+    b, d, h, ww = hf.shape
+    rows = hf.permute(0, 2, 3, 1).reshape(-1, d)
+    z, _ = simclr_projection(rows, *params, bn_mean=bn_running[0], bn_var=bn_running[1], train=False)
+    preds = z.view(b, h, ww, -1).permute(0, 3, 1, 2)
+    return preds, preds.max(1)[1]
+
+
+# --------------------------------------------------------------------------------------
 # Inference  (SURVEY §8 a19, a20)
 # --------------------------------------------------------------------------------------
 

@@ -267,6 +267,102 @@ def golden_swav(name="swav", sampling_method='random', patch=100):
 
 
 # ---------------------------------------------------------------------------------------
+# G3b: SimCLR baseline head (baseline/hfc_with_simclr/simclr_clustering.py:133-281), SURVEY §8(f) rank 4
+# ---------------------------------------------------------------------------------------
+def golden_simclr():
+    import importlib
+    simclr = importlib.import_module('baseline.hfc_with_simclr.simclr_clustering')
+    gen, sd = build_reference_generator()
+    hlen = 512 + 1024 + 1024
+    nclasses, batch, niters = 32, 6, 2
+    cfg = dict(
+        perturb_args=dict(truncation=0.7, n_layers=3, n_samples=1, layer_no=None, perturb_std=[1.0, 0.5, 1.0]),
+        simclr_args=dict(num_iters=niters, batch_size=batch, patch_size=100, hf_interp='nearest', trust_coeff=0.01,
+                         train_args=dict(lr=0.01, momentum=0.9), temperature=1.0, nclasses=nclasses, hlen=hlen,
+                         epoch_print_freq=1, max_masks=4),
+        train=True, layer_hf_dim=[512, 1024, 1024])
+    model_config = types.SimpleNamespace(num_latents_for_mean=64, truncation=0.7,
+                                         latent_dim=GEN_STYLE, image_size=GEN_SIZE)
+    rec = Recorder()
+    losses = []
+    tb = types.SimpleNamespace(add_scalar=lambda name, val, step: losses.append(float(val)))
+    logger = types.SimpleNamespace(info=lambda *a, **k: None)
+    torch.manual_seed(13)
+    np.random.seed(13)
+    orig = dict(randn=torch.randn, randn_like=torch.randn_like, randperm=torch.randperm,
+                choice=np.random.choice, rand=torch.rand)
+    torch.randn = rec.wrap("randn", orig["randn"])
+    torch.randn_like = rec.wrap("randn_like", orig["randn_like"])
+    torch.randperm = rec.wrap("randperm", orig["randperm"])
+    torch.rand = rec.wrap("rand", orig["rand"])
+    np.random.choice = rec.wrap("choice", orig["choice"])
+    from torchvision import transforms as T
+    orig_gp = T.RandomRotation.get_params
+    T.RandomRotation.get_params = staticmethod(rec.wrap("angle", orig_gp))
+    init = {}
+    orig_sgd = torch.optim.SGD
+
+    def sgd_spy(params, **kw):
+        params = list(params)
+        init["params"] = [p.detach().clone() for p in params]
+        return orig_sgd(params, **kw)
+    torch.optim.SGD = sgd_spy
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            obj = simclr.SimCLRClustering(gen, model_config, logger=logger, out_dir=td, device='cpu', tb=tb, **cfg)
+            mean_latent = obj.mean_latent.clone()
+            n_ctor = len(rec.log)
+            obj.pretrain(None)
+            n_train = len(rec.log)
+            state = {k: v.detach().clone() for k, v in obj.projection.state_dict().items()}
+            wlat = gen.style(orig["randn"](1, GEN_STYLE, generator=torch.Generator().manual_seed(5)))
+            obj.projection.eval()          # inference uses the running statistics
+            preds, labels = obj.predict_simclr_codes(wlat.detach())
+    finally:
+        torch.randn, torch.randn_like, torch.randperm = orig["randn"], orig["randn_like"], orig["randperm"]
+        torch.rand = orig["rand"]
+        np.random.choice = orig["choice"]
+        T.RandomRotation.get_params = orig_gp
+        torch.optim.SGD = orig_sgd
+    assert len(init["params"]) == 4, [tuple(p.shape) for p in init["params"]]
+    out = dict(mean_latent=mean_latent, losses=np.array(losses),
+               init_w1=init["params"][0], init_bn_w=init["params"][1], init_bn_b=init["params"][2],
+               init_w2=init["params"][3],
+               final_w1=state["0.weight"], final_bn_w=state["1.weight"], final_bn_b=state["1.bias"],
+               final_bn_mean=state["1.running_mean"], final_bn_var=state["1.running_var"], final_w2=state["3.weight"],
+               pred_w=wlat, preds=preds, labels=labels,
+               cfg=np.array([hlen, nclasses, batch, niters, 3], dtype=np.int64), perturb_std=np.array([1.0, 0.5, 1.0]))
+    it = iter(rec.log[n_ctor:n_train])
+    for e in range(niters):
+        kind, z = next(it)
+        assert kind == "randn" and tuple(z.shape) == (1, GEN_STYLE), (kind, z.shape)
+        out[f"s{e}_z"] = z
+        for v in "st":            # per view: layer choice, 6 perturbation draws, then ITS rotation / flip (ref :187-201)
+            kind, layer = next(it)
+            assert kind == "choice", kind
+            out[f"s{e}_{v}_layer"] = np.int64(layer)
+            pz = []
+            for _ in range(6):
+                kind, d = next(it)
+                assert kind == "randn_like", kind
+                pz.append(d)
+            out[f"s{e}_{v}_pert_z"] = torch.cat(pz, 0)
+            kind, ang = next(it)
+            assert kind == "angle", kind
+            out[f"s{e}_{v}_angle"] = np.float64(ang)
+            kind, r = next(it)
+            assert kind == "rand", kind
+            out[f"s{e}_{v}_flip"] = np.bool_(bool(r < 0.5))
+        kind, perm = next(it)
+        assert kind == "randperm", kind
+        out[f"s{e}_perm"] = perm
+    rest = list(it)
+    assert not rest, [n for n, _ in rest]
+    save("simclr", **out)
+    print("simclr losses", losses)
+
+
+# ---------------------------------------------------------------------------------------
 # G4: BagGAN generator (models/baggan/models.py:86-379), pidray channel map
 # ---------------------------------------------------------------------------------------
 def golden_baggan():
@@ -334,6 +430,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "segmentor":
         golden_segmentor()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "simclr":
+        golden_simclr()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "swav_patch":
         golden_swav("swav_patch", 'patch', 10)
         sys.exit(0)
@@ -341,5 +440,6 @@ if __name__ == "__main__":
     golden_generator()
     golden_swav()
     golden_swav("swav_patch", 'patch', 10)
+    golden_simclr()
     golden_baggan()
     golden_segmentor()
