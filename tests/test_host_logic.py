@@ -122,3 +122,20 @@ def test_patch_pick_rows_are_the_reference_crop():
         ref = O.sample_patch_rows(hf, pick, p)
         assert torch.equal(hf[0].flatten(1)[:, idx].t(), ref)
     assert patch_pick_rows(h, w, 3, 10).numel() == 100
+
+
+def test_blur_module_caches_and_refreshes_its_separable_factors():
+    """Blur.separable(): factors of the registered buffer, recomputed when the buffer is overwritten (a checkpoint
+    with a different filter) and None for a filter that is not an outer product (then the 2-D kernel runs)."""
+    from ganecdotes_b200.stylegan2.model import Blur
+    blur = Blur([1, 3, 3, 1], pad=(1, 1), upsample_factor=2)
+    fx, fy = blur.separable()
+    assert torch.equal(torch.outer(fy, fx), blur.kernel)
+    assert blur.separable()[0] is fx                      # cached
+    with torch.no_grad():
+        blur.kernel.copy_(torch.outer(torch.tensor([1., 2., 2., 1.]), torch.tensor([1., 4., 4., 1.])) / 60)
+    fx2, fy2 = blur.separable()
+    torch.testing.assert_close(torch.outer(fy2, fx2), blur.kernel, rtol=1e-6, atol=1e-8)
+    with torch.no_grad():
+        blur.kernel.copy_(torch.eye(4))
+    assert blur.separable() is None
