@@ -363,6 +363,62 @@ def golden_simclr():
 
 
 # ---------------------------------------------------------------------------------------
+# G3c: full-size ffhq-256 label map (BASELINE config 1 geometry): predict_swav_codes of the unmodified reference,
+# Generator(256, 512, 8) with seeded random-init weights, hlen 5376, 512 code channels.  The 11 MB projection
+# matrix is regenerated from its seed by the tests (full_size_projection below), only the label map, the
+# top-2 margins (to qualify near-ties) and a strided sample of the codes are stored.
+# ---------------------------------------------------------------------------------------
+FULL_GEN_SEED, FULL_PROJ_SEED, FULL_W_SEED = 42, 1234, 77
+
+
+def full_size_projection():
+    g = torch.Generator().manual_seed(FULL_PROJ_SEED)
+    return torch.randn(512, 5376, generator=g) / 5376 ** 0.5
+
+
+def golden_labelmap_full():
+    sd = O.init_generator_state(256, 512, 8, FULL_GEN_SEED)
+    gen = ref.model.Generator(256, 512, 8)
+    gen.load_state_dict(sd, strict=True)
+    gen.eval()
+    swav = ref.swav
+    cfg = dict(perturb_args=dict(truncation=0.7, n_layers=6, n_samples=1, layer_no=None, perturb_std=[1.0] * 6),
+               swav_args=dict(hf_interp='nearest', hlen=5376, nclasses=512, nprototypes=5000,
+                              sampling_method='random', patch_size=20000, num_patches=5, projn_nw='linear',
+                              temperature=0.01),
+               sinkhorn_args=dict(source_pdf='uniform', niters=10, eps=0.005),
+               train=False, layer_hf_dim=[512, 1024, 1024, 1024, 1024, 512, 256])
+    model_config = types.SimpleNamespace(num_latents_for_mean=256, truncation=0.7, latent_dim=512, image_size=256)
+    logger = types.SimpleNamespace(info=lambda *a, **k: None)
+    g = torch.Generator().manual_seed(FULL_W_SEED)
+    zm = torch.randn(256, 512, generator=g)
+    z = torch.randn(2, 512, generator=g)
+    orig_randn = torch.randn
+    torch.randn = lambda *a, **k: zm.clone() if a[:2] == (256, 512) else orig_randn(*a, **k)   # mean_latent draws
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            obj = swav.SwAVClustering(gen, model_config, logger=logger, out_dir=td, device='cpu', tb=None, **cfg)
+    finally:
+        torch.randn = orig_randn
+    obj.projection = torch.nn.Sequential(torch.nn.Linear(5376, 512, bias=False))
+    with torch.no_grad():
+        obj.projection[0].weight.copy_(full_size_projection())
+    # zm and z are the first two draws of torch.Generator().manual_seed(FULL_W_SEED): the tests regenerate them
+    out = dict(mean_latent=obj.mean_latent,
+               seeds=np.array([FULL_GEN_SEED, FULL_PROJ_SEED, FULL_W_SEED], dtype=np.int64))
+    with torch.no_grad():
+        wl = gen.style(z)
+        for i in range(z.shape[0]):
+            preds, labels = obj.predict_swav_codes(wl[i:i + 1])
+            top2 = preds.topk(2, dim=1).values
+            out[f"labels{i}"] = labels.to(torch.int16)
+            out[f"margin{i}"] = (top2[:, 0] - top2[:, 1]).to(torch.float16)
+            out[f"absmax{i}"] = preds.abs().max()
+            out[f"preds{i}_sample"] = preds[:, ::16, ::8, ::8]
+    save("labelmap_ffhq256", **out)
+
+
+# ---------------------------------------------------------------------------------------
 # G4: BagGAN generator (models/baggan/models.py:86-379), pidray channel map
 # ---------------------------------------------------------------------------------------
 def golden_baggan():
@@ -430,6 +486,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "segmentor":
         golden_segmentor()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "labelmap_full":
+        golden_labelmap_full()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "simclr":
         golden_simclr()
         sys.exit(0)
@@ -441,5 +500,6 @@ if __name__ == "__main__":
     golden_swav()
     golden_swav("swav_patch", 'patch', 10)
     golden_simclr()
+    golden_labelmap_full()
     golden_baggan()
     golden_segmentor()
