@@ -419,6 +419,119 @@ def golden_labelmap_full():
 
 
 # ---------------------------------------------------------------------------------------
+# G3d: BASELINE config 1 at full size - ONE pretrain step of the unmodified reference on CPU: ffhq-256 geometry
+# (Generator(256, 512, 8), hlen 5376, 512 classes, 5000 prototypes, 5 patches x 20000 px, eps 0.005, T 0.01),
+# random-init weights from seeds.  The 21 MB of head weights are regenerated from their seeds by the tests; the
+# file holds the recorded draws (perms truncated to the 20000 picks that are used), the loss, strided samples of
+# the updated weights and the update norms.
+# ---------------------------------------------------------------------------------------
+def full_size_head():
+    g = torch.Generator().manual_seed(FULL_PROJ_SEED)
+    w_proj = torch.randn(512, 5376, generator=g) / 5376 ** 0.5
+    w_proto = torch.randn(5000, 512, generator=g) / 512 ** 0.5
+    b_proto = 0.01 * torch.randn(5000, generator=g)
+    return w_proj, w_proto, b_proto
+
+
+def golden_pretrain_full():
+    sd = O.init_generator_state(256, 512, 8, FULL_GEN_SEED)
+    gen = ref.model.Generator(256, 512, 8)
+    gen.load_state_dict(sd, strict=True)
+    gen.eval()
+    swav = ref.swav
+    cfg = dict(perturb_args=dict(truncation=0.7, n_layers=6, n_samples=1, layer_no=None, perturb_std=[1.0] * 6),
+               swav_args=dict(num_epochs=1, num_samples=1, num_patches=5, sampling_method='random', patch_size=20000,
+                              hf_interp='nearest', warmup_epochs=1, start_warmup=0.01, use_scheduler=False,
+                              base_lr=0.01, final_lr=0.0001, trust_coeff=0.01, freeze_prototype_niters=313,
+                              train_args=dict(lr=0.01, momentum=0.9), projn_nw='linear', temperature=0.01,
+                              nprototypes=5000, nclasses=512, hlen=5376, add_local_loss=False,
+                              plot_test_images=False, epoch_print_freq=1, max_masks=4),
+               sinkhorn_args=dict(source_pdf='uniform', niters=10, eps=0.005),
+               train=True, layer_hf_dim=[512, 1024, 1024, 1024, 1024, 512, 256])
+    model_config = types.SimpleNamespace(num_latents_for_mean=256, truncation=0.7, latent_dim=512, image_size=256)
+    init = full_size_head()          # before the recorder wraps torch.randn
+    rec = Recorder()
+    losses = []
+    tb = types.SimpleNamespace(add_scalar=lambda name, val, step: losses.append(float(val)))
+    logger = types.SimpleNamespace(info=lambda *a, **k: None)
+    torch.manual_seed(21)
+    np.random.seed(21)
+    orig = dict(randn=torch.randn, randn_like=torch.randn_like, randperm=torch.randperm,
+                choice=np.random.choice, rand=torch.rand)
+    torch.randn = rec.wrap("randn", orig["randn"])
+    torch.randn_like = rec.wrap("randn_like", orig["randn_like"])
+    torch.randperm = rec.wrap("randperm", orig["randperm"])
+    torch.rand = rec.wrap("rand", orig["rand"])
+    np.random.choice = rec.wrap("choice", orig["choice"])
+    from torchvision import transforms as T
+    orig_gp = T.RandomRotation.get_params
+    T.RandomRotation.get_params = staticmethod(rec.wrap("angle", orig_gp))
+    orig_sgd = torch.optim.SGD
+
+    def sgd_spy(params, **kw):      # the head starts from the seeded weights (as if loaded from a checkpoint)
+        params = list(params)
+        with torch.no_grad():
+            for p, v in zip(params, init):
+                p.copy_(v)
+        return orig_sgd(params, **kw)
+    torch.optim.SGD = sgd_spy
+    try:
+        with tempfile.TemporaryDirectory() as td:
+            obj = swav.SwAVClustering(gen, model_config, logger=logger, out_dir=td, device='cpu', tb=tb, **cfg)
+            mean_latent = obj.mean_latent.clone()
+            n_ctor = len(rec.log)
+            obj.pretrain(None, num_test_samples=0)
+            n_train = len(rec.log)
+            fin = [obj.projection[0].weight.detach().clone(), obj.prototype.weight.detach().clone(),
+                   obj.prototype.bias.detach().clone()]
+    finally:
+        torch.randn, torch.randn_like, torch.randperm = orig["randn"], orig["randn_like"], orig["randperm"]
+        torch.rand = orig["rand"]
+        np.random.choice = orig["choice"]
+        T.RandomRotation.get_params = orig_gp
+        torch.optim.SGD = orig_sgd
+    ref_init = [init[0], torch.nn.functional.normalize(init[1], dim=1), init[2]]
+    # the mean-latent draws are torch.randn(256, 512) right after torch.manual_seed(21): the tests regenerate them
+    assert tuple(rec.log[0][1].shape) == (256, 512)
+    out = dict(mean_latent=mean_latent, losses=np.array(losses),
+               seeds=np.array([FULL_GEN_SEED, FULL_PROJ_SEED, 21], dtype=np.int64),
+               final_w_proj_sample=fin[0][::16, ::64], final_w_proto_sample=fin[1][::50, ::16],
+               final_b_proto_sample=fin[2][::10],
+               update_norms=np.array([(f - i).norm().item() for f, i in zip(fin, ref_init)]),
+               delta_w_proj_sample=(fin[0] - ref_init[0])[::16, ::64],
+               delta_w_proto_sample=(fin[1] - ref_init[1])[::50, ::16])
+    it = iter(rec.log[n_ctor:n_train])
+    kind, z = next(it)
+    assert kind == "randn" and tuple(z.shape) == (1, 512), (kind, z.shape)
+    out["z"] = z
+    for v in "st":
+        kind, layer = next(it)
+        assert kind == "choice", kind
+        out[f"{v}_layer"] = np.int64(layer)
+        pz = []
+        for _ in range(12):
+            kind, d = next(it)
+            assert kind == "randn_like", kind
+            pz.append(d)
+        out[f"{v}_pert_z"] = torch.cat(pz, 0)
+    for v in "st":
+        kind, ang = next(it)
+        assert kind == "angle", kind
+        out[f"{v}_angle"] = np.float64(ang)
+        kind, r = next(it)
+        assert kind == "rand", kind
+        out[f"{v}_flip"] = np.bool_(bool(r < 0.5))
+    for p in range(5):
+        kind, perm = next(it)
+        assert kind == "randperm", kind
+        out[f"perm{p}"] = perm[:20000].to(torch.int32)
+    rest = list(it)
+    assert not rest, [n for n, _ in rest]
+    save("pretrain_ffhq256", **out)
+    print("full-size losses", losses, "update norms", out["update_norms"])
+
+
+# ---------------------------------------------------------------------------------------
 # G4: BagGAN generator (models/baggan/models.py:86-379), pidray channel map
 # ---------------------------------------------------------------------------------------
 def golden_baggan():
@@ -486,6 +599,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "segmentor":
         golden_segmentor()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "pretrain_full":
+        golden_pretrain_full()
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "labelmap_full":
         golden_labelmap_full()
         sys.exit(0)
@@ -501,5 +617,6 @@ if __name__ == "__main__":
     golden_swav("swav_patch", 'patch', 10)
     golden_simclr()
     golden_labelmap_full()
+    golden_pretrain_full()
     golden_baggan()
     golden_segmentor()

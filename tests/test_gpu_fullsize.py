@@ -275,3 +275,44 @@ def test_ffhq256_label_map_matches_reference_golden():
         assert mism.float().mean().item() < 5e-3
         if mism.any():
             assert g[f"margin{i}"][0].float()[mism].max().item() < 1e-3 * absmax
+
+
+@pytest.mark.skipif(__import__("os").environ.get("GX_RUN_UNVERIFIED") != "1",
+                    reason="written after the round's GPU budget was spent: not yet run on a B200 "
+                           "(GX_RUN_UNVERIFIED=1 runs it; the CPU oracle passes the same golden)")
+def test_ffhq256_pretrain_step_matches_reference_golden():
+    """BASELINE config 1 at full size against the UNMODIFIED reference (tests/golden/pretrain_ffhq256.npz: one
+    CPU pretrain step of the reference, ffhq-256 geometry, recorded draws): loss within 2e-3, weight updates
+    within 3 % (bf16 backward operands), like the small seeded run of test_pretrain_matches_reference_golden."""
+    import os
+    from oracle import ganecdotes_oracle as O
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    from ganecdotes_b200.stylegan2.model import Generator
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "pretrain_ffhq256.npz"))
+    g = {k: torch.from_numpy(np.asarray(d[k])) for k in d.files}
+    gen_seed, head_seed, _ = [int(v) for v in g["seeds"]]
+    gen = Generator(256, 512, 8)
+    gen.load_state_dict(O.init_generator_state(256, 512, 8, gen_seed), strict=True)
+    gen = gen.cuda()
+    hg = torch.Generator().manual_seed(head_seed)
+    wp = torch.randn(512, 5376, generator=hg) / 5376 ** 0.5
+    wk = torch.randn(5000, 512, generator=hg) / 512 ** 0.5
+    bk = 0.01 * torch.randn(5000, generator=hg)
+    head = E.SwavHead(wp.clone().cuda(), wk.clone().cuda(), bk.clone().cuda(), 0.01, 0.9, 0.01, 3, 1)
+
+    def view(v):
+        return E.ViewDraws(layer_no=[int(g[f"{v}_layer"])], pert_z=g[f"{v}_pert_z"].unsqueeze(0),
+                           angle=[float(g[f"{v}_angle"])], flip=[bool(g[f"{v}_flip"])])
+    draws = E.StepDraws(z=g["z"], view_s=view("s"), view_t=view("t"),
+                        perms=[[g[f"perm{p}"].long()] for p in range(5)])
+    cfg = E.StepConfig(hlen=5376, patch_size=20000, num_patches=5, niters=10, eps=0.005, temperature=0.01,
+                       truncation=0.7, perturb_std=[1.0] * 6)
+    loss = E.swav_train_step(gen, head, g["mean_latent"].cuda(), draws, cfg)
+    ref_loss = float(g["losses"][0])
+    assert abs(loss.item() - ref_loss) < 2e-3 * abs(ref_loss), (loss.item(), ref_loss)
+    init = [wp, torch.nn.functional.normalize(wk, dim=1), bk]
+    fin = [head.w_proj.cpu(), head.w_proto.cpu(), head.b_proto.cpu()]
+    for f, i0, ref_norm in zip(fin, init, g["update_norms"].tolist()):
+        assert abs((f - i0).norm().item() - ref_norm) < 3e-2 * ref_norm
+    d_proj = (fin[0] - init[0])[::16, ::64]
+    assert (d_proj - g["delta_w_proj_sample"]).norm().item() < 5e-2 * g["delta_w_proj_sample"].norm().item()
