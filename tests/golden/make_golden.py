@@ -376,9 +376,12 @@ def full_size_projection():
     return torch.randn(512, 5376, generator=g) / 5376 ** 0.5
 
 
-def golden_labelmap_full():
-    sd = O.init_generator_state(256, 512, 8, FULL_GEN_SEED)
-    gen = ref.model.Generator(256, 512, 8)
+def golden_labelmap_full(size=256, name="labelmap_ffhq256", nimg=2):
+    """size=512: BASELINE config 3 geometry (car-512): a 512^2 generator whose features sum to 5504 channels, sliced
+    to hlen = 5376 AFTER upsampling to 512^2 (the two 512^2-native 64-channel maps lose all but
+    their first channels, everything is sampled at 512^2)."""
+    sd = O.init_generator_state(size, 512, 8, FULL_GEN_SEED)
+    gen = ref.model.Generator(size, 512, 8)
     gen.load_state_dict(sd, strict=True)
     gen.eval()
     swav = ref.swav
@@ -388,11 +391,11 @@ def golden_labelmap_full():
                               temperature=0.01),
                sinkhorn_args=dict(source_pdf='uniform', niters=10, eps=0.005),
                train=False, layer_hf_dim=[512, 1024, 1024, 1024, 1024, 512, 256])
-    model_config = types.SimpleNamespace(num_latents_for_mean=256, truncation=0.7, latent_dim=512, image_size=256)
+    model_config = types.SimpleNamespace(num_latents_for_mean=256, truncation=0.7, latent_dim=512, image_size=size)
     logger = types.SimpleNamespace(info=lambda *a, **k: None)
     g = torch.Generator().manual_seed(FULL_W_SEED)
     zm = torch.randn(256, 512, generator=g)
-    z = torch.randn(2, 512, generator=g)
+    z = torch.randn(2, 512, generator=g)[:nimg]
     orig_randn = torch.randn
     torch.randn = lambda *a, **k: zm.clone() if a[:2] == (256, 512) else orig_randn(*a, **k)   # mean_latent draws
     try:
@@ -412,10 +415,14 @@ def golden_labelmap_full():
             preds, labels = obj.predict_swav_codes(wl[i:i + 1])
             top2 = preds.topk(2, dim=1).values
             out[f"labels{i}"] = labels.to(torch.int16)
-            out[f"margin{i}"] = (top2[:, 0] - top2[:, 1]).to(torch.float16)
+            margin = top2[:, 0] - top2[:, 1]
+            if size == 256:
+                out[f"margin{i}"] = margin.to(torch.float16)
+            else:                       # 512^2: only whether a pixel is a near-tie (packed bits)
+                out[f"neartie{i}"] = np.packbits((margin < 1e-3 * preds.abs().max()).numpy())
             out[f"absmax{i}"] = preds.abs().max()
-            out[f"preds{i}_sample"] = preds[:, ::16, ::8, ::8]
-    save("labelmap_ffhq256", **out)
+            out[f"preds{i}_sample"] = preds[:, ::16, ::8, ::8] if size == 256 else preds[:, ::16, ::16, ::16]
+    save(name, **out)
 
 
 # ---------------------------------------------------------------------------------------
@@ -605,6 +612,9 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "labelmap_full":
         golden_labelmap_full()
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "labelmap_car512":
+        golden_labelmap_full(512, "labelmap_car512", 1)
+        sys.exit(0)
     if len(sys.argv) > 1 and sys.argv[1] == "simclr":
         golden_simclr()
         sys.exit(0)
@@ -617,6 +627,7 @@ if __name__ == "__main__":
     golden_swav("swav_patch", 'patch', 10)
     golden_simclr()
     golden_labelmap_full()
+    golden_labelmap_full(512, "labelmap_car512", 1)
     golden_pretrain_full()
     golden_baggan()
     golden_segmentor()
