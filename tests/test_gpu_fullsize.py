@@ -316,3 +316,36 @@ def test_ffhq256_pretrain_step_matches_reference_golden():
         assert abs((f - i0).norm().item() - ref_norm) < 3e-2 * ref_norm
     d_proj = (fin[0] - init[0])[::16, ::64]
     assert (d_proj - g["delta_w_proj_sample"]).norm().item() < 5e-2 * g["delta_w_proj_sample"].norm().item()
+
+
+@pytest.mark.skipif(__import__("os").environ.get("GX_RUN_UNVERIFIED") != "1",
+                    reason="written after the round's GPU budget was spent: not yet run on a B200 "
+                           "(GX_RUN_UNVERIFIED=1 runs it; the CPU oracle passes the same golden)")
+def test_car512_label_map_matches_reference_golden():
+    """BASELINE config 3 geometry against the UNMODIFIED reference (tests/golden/labelmap_car512.npz): 512^2
+    generator, 5504 feature channels sliced to hlen 5376 after upsampling."""
+    import os
+    from oracle import ganecdotes_oracle as O
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    from ganecdotes_b200.stylegan2.model import Generator
+    d = np.load(os.path.join(os.path.dirname(__file__), "golden", "labelmap_car512.npz"))
+    g = {k: torch.from_numpy(np.asarray(d[k])) for k in d.files}
+    gen_seed, proj_seed, w_seed = [int(v) for v in g["seeds"]]
+    gen = Generator(512, 512, 8)
+    gen.load_state_dict(O.init_generator_state(512, 512, 8, gen_seed), strict=True)
+    gen = gen.cuda()
+    rg = torch.Generator().manual_seed(w_seed)
+    torch.randn(256, 512, generator=rg)                 # the mean-latent draws come first
+    z = torch.randn(2, 512, generator=rg)[:1]
+    w_proj = (torch.randn(512, 5376, generator=torch.Generator().manual_seed(proj_seed)) / 5376 ** 0.5).cuda()
+    with torch.no_grad():
+        w = gen.style(z.cuda())
+    preds, labels = E.predict_codes(gen, w_proj, w, g["mean_latent"].cuda(), 0.7, 5376)
+    assert tuple(preds.shape) == (1, 512, 512, 512) and tuple(labels.shape) == (1, 512, 512)
+    absmax = float(g["absmax0"])
+    assert (preds[:, ::16, ::16, ::16].cpu() - g["preds0_sample"]).abs().max().item() < 5e-4 * absmax
+    mism = (labels.cpu() != g["labels0"].long()).flatten()
+    assert mism.float().mean().item() < 5e-3
+    if mism.any():
+        neartie = torch.from_numpy(np.unpackbits(g["neartie0"].numpy())[:mism.numel()].astype(bool))
+        assert bool(neartie[mism].all())
