@@ -14,21 +14,33 @@ MODELS = {
     'cat-256': dict(size=256, baggan=False, truncation=0.7),
     'afhq-256': dict(size=256, baggan=False, truncation=0.7),
     'horse-256': dict(size=256, baggan=False, truncation=0.7),
+    'horse-256-rp': dict(size=256, baggan=False, truncation=0.7),
+    'church-256': dict(size=256, baggan=False, truncation=0.7),
+    'ffhq-256-eg': dict(size=256, baggan=False, truncation=0.7),
+    'p-horse-256': dict(size=256, baggan=False, truncation=0.7),
+    'p-car-512': dict(size=256, baggan=False, truncation=0.7),      # pascal_car_512.py:8 builds a 256 generator
     # lsun_car_512.py builds a 256 generator (:8,11); BASELINE.json's car-512 config asks for 512^2 features
     'car-512': dict(size=512, baggan=False, truncation=0.7),
     'pidray-256': dict(size=256, baggan=True, truncation=0.9),
 }
-for _n in ('pliers', 'hammer', 'powerbank', 'wrench', 'handcuffs'):
-    MODELS[f'pidray-{_n}-256'] = dict(size=256, baggan=True, truncation=0.9)
+for _n in ('pliers', 'hammer', 'powerbank', 'wrench', 'handcuffs'):     # configs/models/pidray_<tool>_256.py:8
+    MODELS[f'pidray-{_n}-256'] = dict(size=256, baggan=True, truncation=0.95)
 
-# per-method differences of hfc_with_swav_{ffhq,cat,car,horse,pidray}_config.py (:52,:63-65,:77-79)
+# per-method differences of hfc_with_swav_{ffhq,cat,car,horse,pidray}_config.py and the generic
+# hfc_with_swav_config.py (:22 num_epochs, :52 nprototypes, :63-65 sinkhorn_args, :77-79 seg_args)
 _METHOD = {
-    'hfc_with_swav_ffhq': dict(nprototypes=5000, eps=0.005, source_pdf='uniform', seg='XXS', layers=_FFHQ_LAYERS),
-    'hfc_with_swav_cat': dict(nprototypes=5000, eps=0.003, source_pdf='image', seg='XS', layers=_FFHQ_LAYERS),
-    'hfc_with_swav_car': dict(nprototypes=4000, eps=0.01, source_pdf='uniform', seg='XS', layers=_FFHQ_LAYERS),
-    'hfc_with_swav_horse': dict(nprototypes=5000, eps=0.003, source_pdf='uniform', seg='XXS', layers=_FFHQ_LAYERS),
-    'hfc_with_swav_pidray': dict(nprototypes=4000, eps=0.005, source_pdf='uniform', seg='XXS', layers=_PIDRAY_LAYERS),
-    'hfc_with_swav': dict(nprototypes=5000, eps=0.005, source_pdf='uniform', seg='XXS', layers=_FFHQ_LAYERS),
+    'hfc_with_swav_ffhq': dict(nprototypes=5000, eps=0.005, source_pdf='uniform', seg='XXS', layers=_FFHQ_LAYERS,
+                               num_epochs=100),
+    'hfc_with_swav_cat': dict(nprototypes=5000, eps=0.003, source_pdf='image', seg='XS', layers=_FFHQ_LAYERS,
+                              num_epochs=100),
+    'hfc_with_swav_car': dict(nprototypes=4000, eps=0.01, source_pdf='uniform', seg='XS', layers=_FFHQ_LAYERS,
+                              num_epochs=100),
+    'hfc_with_swav_horse': dict(nprototypes=5000, eps=0.003, source_pdf='uniform', seg='XXS', layers=_FFHQ_LAYERS,
+                                num_epochs=50),
+    'hfc_with_swav_pidray': dict(nprototypes=4000, eps=0.005, source_pdf='uniform', seg='XXS', layers=_PIDRAY_LAYERS,
+                                 num_epochs=100),
+    'hfc_with_swav': dict(nprototypes=8000, eps=0.005, source_pdf='uniform', seg='XXS', layers=_FFHQ_LAYERS,
+                          num_epochs=100),
 }
 
 
@@ -53,12 +65,12 @@ def model_config(model):
 
 def swav_config(model, method='hfc_with_swav'):
     md = copy.deepcopy(_METHOD[method_for(model, method)])
-    n_hfc_layers = 6 if MODELS[model]['size'] <= 256 else 7
+    n_hfc_layers = 6          # every shipped segmentor config (:2); the 512^2 generator is only the geometry override
     hlen = sum(md['layers'])
     return dict(
         perturb_args=dict(truncation=0.7, n_layers=n_hfc_layers, n_samples=1, layer_no=None,
                           perturb_std=[1.0] * n_hfc_layers),
-        swav_args=dict(num_epochs=100, num_samples=1, num_patches=5, sampling_method='random', patch_size=20000,
+        swav_args=dict(num_epochs=md['num_epochs'], num_samples=1, num_patches=5, sampling_method='random', patch_size=20000,
                        hf_interp='nearest', warmup_epochs=100, start_warmup=0.01, use_scheduler=False, base_lr=0.01,
                        final_lr=0.0001, trust_coeff=0.01, freeze_prototype_niters=313,
                        train_args=dict(lr=0.01, momentum=0.9), projn_nw='linear', temperature=0.01,

@@ -166,9 +166,10 @@ class SwavHead:
     their bf16 operand planes, gradients and LARC/SGD state.  Operates IN PLACE on the
     parameters of the nn.Modules the caller saves (ref :504-505)."""
 
-    def __init__(self, w_proj, w_proto, b_proto, lr, momentum, trust, passes_fwd=3, passes_bwd=1, proto_f16=False):
+    def __init__(self, w_proj, w_proto, b_proto, lr, momentum, trust, passes_fwd=3, passes_bwd=1, proto_f16=False,
+                 weight_decay=0.0):
         self.w_proj, self.w_proto, self.b_proto = w_proj, w_proto, b_proto
-        self.lr, self.momentum, self.trust = lr, momentum, trust
+        self.lr, self.momentum, self.trust, self.weight_decay = lr, momentum, trust, float(weight_decay)
         self.passes_fwd, self.passes_bwd = passes_fwd, passes_bwd
         # score GEMM operands.  Default: the 3-plane bf16 split, |dS| = 2e-7 rms -> codes Q within 5e-5 rms of
         # fp64 at the shipped eps = 0.005 (scores are multiplied by 200 inside the exponential).
@@ -219,7 +220,7 @@ class SwavHead:
         first = 1 if self.steps == 0 else 0
         for p, g, m in ((self.w_proj, self.g_proj, self.m_proj), (self.w_proto, self.g_proto, self.m_proto),
                         (self.b_proto, self.g_bias, self.m_bias)):
-            L.larc_sgd_(p, g, m, self.lr, self.momentum, self.trust, 0.0, 1e-8, first, self.norms)
+            L.larc_sgd_(p, g, m, self.lr, self.momentum, self.trust, self.weight_decay, 1e-8, first, self.norms)
         self.steps += 1
         self.planes_ready = False
 

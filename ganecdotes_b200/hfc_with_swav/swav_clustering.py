@@ -173,6 +173,25 @@ class SwAVClustering(object):
                                angle=[r[vi][0] for r in rot], flip=[r[vi][1] for r in rot])
         return E.StepDraws(z=torch.cat(z, 0), view_s=mk(vs, 0), view_t=mk(vt, 1), perms=perms)
 
+    def lr_schedule(self, num_epochs, num_samples):
+        """ref :303-317 (use_scheduler): linear warm-up from start_warmup to base_lr over warmup_epochs, then the
+        reference's cosine to final_lr (its period is num_epochs - warmup_epochs *iterations*, as written there)."""
+        import math
+        a = self.swav_args
+        warm = np.linspace(a['start_warmup'], a['base_lr'], num_samples * a['warmup_epochs'])
+        iters = np.arange(num_samples * (a['num_epochs'] - a['warmup_epochs']))
+        cos = np.array([a['final_lr'] + 0.5 * (a['base_lr'] - a['final_lr'])
+                        * (1 + math.cos(math.pi * t / (a['num_epochs'] - a['warmup_epochs']))) for t in iters])
+        return np.concatenate((warm, cos))
+
+    @staticmethod
+    def broadcast_draws(draws: E.StepDraws, group):
+        """rank 0's draws of the global batch replace every other rank's (one small object broadcast per step)"""
+        import torch.distributed as dist
+        box = [draws if group.rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group.pg)
+        return box[0]
+
     @staticmethod
     def shard_draws(draws: E.StepDraws, rank, world):
         b = draws.z.shape[0]
@@ -256,6 +275,14 @@ class SwAVClustering(object):
                                       "in every shipped config")
         if self.swav_args['sampling_method'] not in ('random', 'patch'):
             raise NotImplementedError("sampling_method: 'random' (every shipped config) or 'patch'")
+        if int(self.perturb_args.get('n_samples', 1)) != 1:
+            raise NotImplementedError("perturb_args['n_samples'] != 1: the reference would synthesise n_samples "
+                                      "images per view (every shipped config uses 1)")
+        ta = dict(self.swav_args['train_args'])
+        unknown = set(ta) - {'lr', 'momentum', 'weight_decay'}
+        if unknown or not ta.get('momentum', 0.0) >= 0:
+            raise NotImplementedError(f"train_args {sorted(unknown)}: the fused LARC+SGD kernel implements lr, momentum "
+                                      "and weight_decay (every shipped config: lr + momentum)")
         # test latents + their (unused) images: draws only (ref :222-238)
         for _ in range(num_test_samples):
             torch.randn(1, self.model_config.latent_dim)
@@ -271,13 +298,20 @@ class SwAVClustering(object):
             self.logger.info(self.projection.__str__())
             self.logger.info("Prototype Matrix:")
             self.logger.info(self.prototype.__str__())
-        ta = self.swav_args['train_args']
-        self._head = E.SwavHead(self.projection[0].weight.data, self.prototype.weight.data,
-                                self.prototype.bias.data, ta['lr'], ta.get('momentum', 0.0),
-                                self.swav_args['trust_coeff'], self.passes_fwd, self.passes_bwd, self.proto_f16)
-        self._sk_ws = L.SinkhornWorkspace(self.nprototypes, self.device)
         group = self._dist_group()
         world = group.world if group is not None else 1
+        if group is not None:
+            # replicas must start from identical weights / mean latent whatever each rank's CPU RNG state is
+            import torch.distributed as dist
+            for t in (self.projection[0].weight.data, self.prototype.weight.data, self.prototype.bias.data,
+                      self.mean_latent):
+                dist.broadcast(t, src=0, group=group.pg)
+        self._head = E.SwavHead(self.projection[0].weight.data, self.prototype.weight.data,
+                                self.prototype.bias.data, ta['lr'], ta.get('momentum', 0.0),
+                                self.swav_args['trust_coeff'], self.passes_fwd, self.passes_bwd, self.proto_f16,
+                                weight_decay=ta.get('weight_decay', 0.0))
+        self._sk_ws = L.SinkhornWorkspace(self.nprototypes, self.device)
+        lr_schedule = self.lr_schedule(num_epochs, num_samples) if self.swav_args.get('use_scheduler', False) else None
         b_global = int(self.swav_args.get('batch_latents', 1))
         cfg = self._step_config()
         t0 = time.time()
@@ -289,6 +323,9 @@ class SwAVClustering(object):
         def stage_next():
             draws = self.draw_step(b_global)
             if group is not None:
+                # every rank draws the whole global batch from its own CPU generators; rank 0's draws are the ones
+                # that count (identical seeding is not assumed), each rank then keeps its shard
+                draws = self.broadcast_draws(draws, group)
                 draws = self.shard_draws(draws, group.rank, world)
             return E.prepare_step_inputs(self.model, draws, cfg, self.device, stream=side)
 
@@ -298,6 +335,8 @@ class SwAVClustering(object):
         for e in range(num_epochs):
             for i in range(num_samples):
                 inp, done = nxt, done + 1
+                if lr_schedule is not None:                      # ref :323-326
+                    self._head.lr = float(lr_schedule[e * num_samples + i])
                 loss = E.swav_train_step_device(self.model, self._head, self.mean_latent, inp, cfg, group,
                                                 self._sk_ws)
                 nxt = stage_next() if done < total else None

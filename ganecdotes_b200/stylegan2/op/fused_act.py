@@ -6,8 +6,9 @@ models/stylegan2/model.py:15-43, lib/gan/optim/fused_act.py:171-253) and the pyb
 `fused_bias_act` (lib/gan/optim/fused_bias_act.cpp:18-36).  Differentiable to second order like the
 reference's FusedLeakyReLUFunction / ...Backward pair (lib/gan/optim/fused_act.py:27-167): the gradient
 modes (`grad=1`: multiply by the slope selected by the sign of the saved output) run on the same kernel.
-Bias is broadcast on dim 1; for 3-D inputs the `op/` variant of the reference
-broadcasts on the last dim (op/fused_act.py:26-32) - selected with `bias_last=True`.
+Bias broadcast follows models/stylegan2/op/fused_act.py:23-40 (the module this file replaces): on the LAST
+dim for a 3-D input, on dim 1 otherwise.  `bias_last=False` forces dim 1 for 3-D inputs too, which is what
+the BagGAN copy of the op does (lib/gan/optim/fused_act.py:171-253).
 """
 import torch
 from torch import nn
@@ -75,16 +76,20 @@ class _FusedLReLUGrad(torch.autograd.Function):
         return gg, None, None, None
 
 
-def fused_leaky_relu(input, bias=None, negative_slope=0.2, scale=2 ** 0.5, bias_last=False):
+def fused_leaky_relu(input, bias=None, negative_slope=0.2, scale=2 ** 0.5, bias_last=None):
     x = input.contiguous()
+    if bias_last is None:
+        bias_last = x.dim() == 3                      # op/fused_act.py:26-32
     needs_grad = torch.is_grad_enabled() and (input.requires_grad or (bias is not None and bias.requires_grad))
-    if needs_grad and not (bias is not None and bias_last and x.dim() == 3):
-        return _FusedLReLU.apply(x, bias, negative_slope, scale)
     if bias is not None and bias_last and x.dim() == 3:
-        # op/fused_act.py:26-32: bias on the last dim of a 3-D input
+        # bias on the last dim of a 3-D input = the 2-D op on the flattened leading dims (channel dim 1)
         shp = x.shape
-        y = fused_bias_act(x.reshape(-1, shp[-1]), bias, None, 3, 0, negative_slope, scale)
+        x2 = x.reshape(-1, shp[-1])
+        y = _FusedLReLU.apply(x2, bias, negative_slope, scale) if needs_grad else \
+            fused_bias_act(x2, bias, None, 3, 0, negative_slope, scale)
         return y.view(shp)
+    if needs_grad:
+        return _FusedLReLU.apply(x, bias, negative_slope, scale)
     return fused_bias_act(x, bias, None, 3, 0, negative_slope, scale)
 
 

@@ -189,6 +189,17 @@ def fused_leaky_relu(x: torch.Tensor, bias: Optional[torch.Tensor], negative_slo
     return F.leaky_relu(x, negative_slope) * scale
 
 
+def fused_leaky_relu_op(x: torch.Tensor, bias: torch.Tensor, negative_slope: float = 0.2,
+                        scale: float = SQRT2) -> torch.Tensor:
+    """The `op/` copy of the function (models/stylegan2/op/fused_act.py:23-40): bias on the LAST dim for a
+    3-D input, on dim 1 otherwise.  (That file calls input.cuda(), so it cannot run in the build container:
+    restated, parity for the 3-D branch unpinned.)"""
+    rest = [1] * (x.ndim - bias.ndim - 1)
+    if x.ndim == 3:
+        return F.leaky_relu(x + bias.view(1, *rest, bias.shape[0]), negative_slope) * scale
+    return F.leaky_relu(x + bias.view(1, bias.shape[0], *rest), negative_slope) * scale
+
+
 def fused_bias_act(x, bias, refer, act: int, grad: int, alpha: float, scale: float):
     """All modes of lib/gan/optim/fused_bias_act_kernel.cu:60-81 (flat tensors;
     bias indexed by dim 1)."""

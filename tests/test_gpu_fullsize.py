@@ -56,9 +56,10 @@ def ffhq():
 
 
 def test_ffhq256_full_step_properties(ffhq):
-    """config 2 shape per GPU, 2 latents: D=5376, C=512, K=5000, 5 patches x 20000 px, eps 0.05-scale"""
+    """config 2 shape per GPU, 2 latents: D=5376, C=512, K=5000, 5 patches x 20000 px, at the SHIPPED
+    hyper-parameters of hfc_with_swav_ffhq_config.py (eps 0.005, temperature 0.01: T/eps = 2 -> swav_loss_pow_kernel)"""
     E, gen, mean_latent = ffhq
-    cfg = E.StepConfig(hlen=5376, patch_size=20000, num_patches=5, niters=10, eps=0.05, temperature=0.1,
+    cfg = E.StepConfig(hlen=5376, patch_size=20000, num_patches=5, niters=10, eps=0.005, temperature=0.01,
                        truncation=0.7, perturb_std=[1.0] * 6)
     draws = _draws(E, 2, 512, 6, 65536, 5, 7)
     losses = {}
@@ -74,11 +75,14 @@ def test_ffhq256_full_step_properties(ffhq):
         for g in (head.g_proj, head.g_proto):
             assert torch.isfinite(g).all() and g.abs().max().item() > 0
         assert not torch.equal(head.w_proj, w0)           # the LARC/SGD step moved the weights
-    assert abs(losses[True] - losses[False]) < 2e-4 * abs(losses[False]), losses
+    # fp16x1 vs bf16x3 score GEMM at eps = 0.005 (scores x200 in the exponent): inside the stated 2e-3 loss tolerance
+    assert abs(losses[True] - losses[False]) < 2e-3 * abs(losses[False]), losses
 
 
-def test_ffhq256_sinkhorn_marginals_full_size(ffhq):
-    """Q = softmax_k(S/eps + log a) of a 40000 x 5000 score matrix: unit rows, uniform prototype marginals"""
+@pytest.mark.parametrize("eps", [0.05, 0.005])
+def test_ffhq256_sinkhorn_marginals_full_size(ffhq, eps):
+    """Q = softmax_k(S/eps + log a) of a 40000 x 5000 score matrix: unit rows, uniform prototype marginals
+    (eps = 0.005 is the shipped value: after 10 iterations the marginals are not converged there, as in the reference)"""
     E, gen, mean_latent = ffhq
     from ganecdotes_b200 import _lib as L
     torch.manual_seed(0)
@@ -87,18 +91,17 @@ def test_ffhq256_sinkhorn_marginals_full_size(ffhq):
     wk = torch.nn.functional.normalize(torch.randn(k, c, device="cuda"), dim=1)
     zf, wf = L.round_f16(z), L.round_f16(wk)
     u0 = torch.zeros(k, device="cuda")
-    eps = 0.05
     s = L.gemm(zf, None, wf, None, n, k, c, 1, colexp=(u0, E.LOG2E / eps), pair=True)
     ws = L.SinkhornWorkspace(k, "cuda")
     la = E.sinkhorn_log_a(s, 10, eps, ws, n, u_first=u0)
     la_ref = E.sinkhorn_log_a(s, 10, eps, ws, n)                      # first pass by the streaming kernel
-    torch.testing.assert_close(la, la_ref, rtol=0, atol=2e-4)
+    torch.testing.assert_close(la, la_ref, rtol=0, atol=2e-4 if eps > 0.01 else 2e-3)
     q = L.sinkhorn_q(s, 1.0 / eps, la)
     torch.testing.assert_close(q.sum(1), torch.ones(n, device="cuda"), rtol=1e-4, atol=0)
     col = q.sum(0)
     # 10 iterations from random scores: marginals within a few percent of N/K, mean exactly N/K
     assert abs(col.mean().item() - n / k) < 1e-3 * n / k
-    assert (col - n / k).abs().max().item() < 0.05 * n / k
+    assert (col - n / k).abs().max().item() < (0.05 if eps > 0.01 else 0.5) * n / k
     assert (q >= 0).all()
 
 
@@ -125,14 +128,15 @@ def test_ffhq256_projection_routes_agree(ffhq):
 
 def test_car512_steps_and_label_map():
     """config 3: 512^2 generator, the 512^2-native maps fall outside hlen=5376, K=4000,
-    eps=0.01; N=20000 as configured and the full-image Sinkhorn problem N=262144."""
+    eps=0.01, temperature=0.01 as shipped (hfc_with_swav_car_config.py:51-65; T/eps = 1 -> swav_loss_pow_kernel),
+    6 perturbable layers; N=20000 as configured and the full-image Sinkhorn problem N=262144."""
     from ganecdotes_b200.hfc_with_swav import engine as E
     gen = _generator(512)
     with torch.no_grad():
         mean_latent = gen.style(torch.randn(512, 512, generator=torch.Generator().manual_seed(3)).cuda()).mean(0, keepdim=True)
-    n_layers = 7
+    n_layers = 6
     for patch, npatch in ((20000, 5), (None, 1)):
-        cfg = E.StepConfig(hlen=5376, patch_size=patch, num_patches=npatch, niters=10, eps=0.01, temperature=0.1,
+        cfg = E.StepConfig(hlen=5376, patch_size=patch, num_patches=npatch, niters=10, eps=0.01, temperature=0.01,
                            truncation=0.7, perturb_std=[1.0] * n_layers)
         head = _head(E, 5376, 512, 4000)
         draws = _draws(E, 1, 512, n_layers, 512 * 512, npatch, 11)
@@ -240,9 +244,6 @@ def test_pretrain_and_evaluate_entry_points(tmp_path):
     assert torch.equal(res["code_labels"], res2["code_labels"])
 
 
-@pytest.mark.skipif(__import__("os").environ.get("GX_RUN_UNVERIFIED") != "1",
-                    reason="written after the round's GPU budget was spent: not yet run on a B200 "
-                           "(GX_RUN_UNVERIFIED=1 runs it; the CPU oracle passes the same golden)")
 def test_ffhq256_label_map_matches_reference_golden():
     """Full-size label map against the UNMODIFIED reference (tests/golden/labelmap_ffhq256.npz: predict_swav_codes of
     the reference on Generator(256, 512, 8) with seeded random-init weights, hlen 5376, 512 code channels):
@@ -277,9 +278,6 @@ def test_ffhq256_label_map_matches_reference_golden():
             assert g[f"margin{i}"][0].float()[mism].max().item() < 1e-3 * absmax
 
 
-@pytest.mark.skipif(__import__("os").environ.get("GX_RUN_UNVERIFIED") != "1",
-                    reason="written after the round's GPU budget was spent: not yet run on a B200 "
-                           "(GX_RUN_UNVERIFIED=1 runs it; the CPU oracle passes the same golden)")
 def test_ffhq256_pretrain_step_matches_reference_golden():
     """BASELINE config 1 at full size against the UNMODIFIED reference (tests/golden/pretrain_ffhq256.npz: one
     CPU pretrain step of the reference, ffhq-256 geometry, recorded draws): loss within 2e-3, weight updates
@@ -318,9 +316,6 @@ def test_ffhq256_pretrain_step_matches_reference_golden():
     assert (d_proj - g["delta_w_proj_sample"]).norm().item() < 5e-2 * g["delta_w_proj_sample"].norm().item()
 
 
-@pytest.mark.skipif(__import__("os").environ.get("GX_RUN_UNVERIFIED") != "1",
-                    reason="written after the round's GPU budget was spent: not yet run on a B200 "
-                           "(GX_RUN_UNVERIFIED=1 runs it; the CPU oracle passes the same golden)")
 def test_car512_label_map_matches_reference_golden():
     """BASELINE config 3 geometry against the UNMODIFIED reference (tests/golden/labelmap_car512.npz): 512^2
     generator, 5504 feature channels sliced to hlen 5376 after upsampling."""

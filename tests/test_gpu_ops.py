@@ -71,6 +71,22 @@ def test_fused_leaky_relu_golden(L):
     torch.testing.assert_close(y.cpu(), g["flr_y_nobias"], rtol=1e-6, atol=1e-7)
     y = fused_leaky_relu(g["flr2_x"].cuda(), g["flr_b"].cuda())
     torch.testing.assert_close(y.cpu(), g["flr2_y"], rtol=1e-6, atol=1e-7)
+    # 3-D input: the op/ module this file replaces broadcasts the bias on the LAST dim by default
+    # (models/stylegan2/op/fused_act.py:23-40); bias_last=False is the lib/gan/optim (dim 1) behaviour
+    from oracle import ganecdotes_oracle as O
+    x3 = torch.randn(4, 6, 6, generator=torch.Generator().manual_seed(3))
+    b6 = g["flr_b"]
+    torch.testing.assert_close(fused_leaky_relu(x3.cuda(), b6.cuda()).cpu(), O.fused_leaky_relu_op(x3, b6),
+                               rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(fused_leaky_relu(x3.cuda(), b6.cuda(), bias_last=False).cpu(),
+                               O.fused_leaky_relu(x3, b6), rtol=1e-6, atol=1e-7)
+    xg, bg = x3.cuda().requires_grad_(True), b6.cuda().requires_grad_(True)
+    xr, br = x3.clone().requires_grad_(True), b6.clone().requires_grad_(True)
+    go = torch.randn(4, 6, 6, generator=torch.Generator().manual_seed(4))
+    fused_leaky_relu(xg, bg).backward(go.cuda())
+    O.fused_leaky_relu_op(xr, br).backward(go)
+    torch.testing.assert_close(xg.grad.cpu(), xr.grad, rtol=1e-6, atol=1e-7)
+    torch.testing.assert_close(bg.grad.cpu(), br.grad, rtol=1e-5, atol=1e-6)
     m = FusedLeakyReLU(6).cuda()
     assert "bias" in dict(m.named_parameters())
     with torch.no_grad():

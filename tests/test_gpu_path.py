@@ -462,3 +462,53 @@ def test_one_shot_segmentor_finetune_gradients(size):
     with torch.no_grad():
         loss2 = torch.nn.functional.cross_entropy(net.eval()(x), labels.cuda())
     assert loss2.item() < loss.item()
+
+
+def test_create_hidden_features_from_perturbed_vectors_matches_oracle(gen, tmp_path):
+    """SwAVClustering.create_hidden_features_from_perturbed_vectors (ref swav_clustering.py:574-656) and the
+    lib/oneshot drop-ins (ref image_augmentor.py:8-104) against the oracle's view_features on the same draws."""
+    from ganecdotes_b200.hfc_with_swav import SwAVClustering
+    from ganecdotes_b200 import oneshot
+    g = load("swav")
+    cfg, mc = golden_cfg(g)
+    obj = SwAVClustering(gen, mc, out_dir=str(tmp_path), device='cuda', tb=None, **cfg)
+    obj.match_reference_rng = False
+    sd = O.init_generator_state(16, 64, 2, 7)
+    mean_latent = obj.mean_latent.cpu()
+    nl, pstd = cfg["perturb_args"]["n_layers"], cfg["perturb_args"]["perturb_std"]
+    torch.manual_seed(11)
+    z = torch.randn(1, 64)
+    w = O.style_mlp(sd, z)
+    for layer_no in (0, nl - 1):
+        torch.manual_seed(100 + layer_no)
+        pert_z = torch.cat([torch.randn(1, 64) for _ in range(2 * nl)], 0)      # the draws _draw_view makes
+        hf_ref, img_ref = O.view_features(sd, w, mean_latent, 0.7, layer_no, pert_z, nl, pstd, cfg["swav_args"]["hlen"])
+        torch.manual_seed(100 + layer_no)
+        hf, img, l = obj.create_hidden_features_from_perturbed_vectors(layer_no=layer_no, input_latent=w.cuda())
+        assert l == layer_no and tuple(hf.shape) == tuple(hf_ref.shape)
+        scale = hf_ref.abs().max().item()
+        assert (hf.cpu() - hf_ref).abs().max().item() < 5e-4 * scale
+        assert (img.cpu() - img_ref).abs().max().item() < 5e-4 * max(1.0, img_ref.abs().max().item())
+        # the same view through the lib/oneshot functions, called the way the reference calls them (:617-650)
+        wt = mean_latent + 0.7 * (w - mean_latent)
+        wplus = wt.unsqueeze(1).repeat(1, gen.n_latent, 1)
+        stds = [0] * (2 * nl)
+        stds[2 * layer_no] = stds[2 * layer_no + 1] = pstd[layer_no]
+        torch.manual_seed(100 + layer_no)
+        pl = oneshot.create_perturbed_vectors_from_latents(wplus, gen, n_samples=1, n_layers=nl, perturb_std=stds)
+        assert len(pl) == 2 * nl and all(tuple(p.shape) == (1, 64) for p in pl)
+        new = wplus.clone()
+        new[:, 2 * layer_no, :], new[:, 2 * layer_no + 1, :] = pl[2 * layer_no], pl[2 * layer_no + 1]
+        ref_new = O.perturbed_wplus(sd, w, mean_latent, 0.7, layer_no, pert_z, nl, pstd)
+        torch.testing.assert_close(new, ref_new, rtol=1e-4, atol=1e-5)
+        imgs, feats = oneshot.create_images_and_features_from_perturbed_latents(
+            new.cuda(), gen, {'truncation': 0.7, 'mean_latent': obj.mean_latent})
+        assert len(feats) == (len(O.regroup_features([0] * gen.num_layers)))
+        hf2 = obj.create_pixel_feature_vectors(feats)
+        assert (hf2.cpu() - hf_ref).abs().max().item() < 5e-4 * scale
+        only = oneshot.create_images_and_features_from_perturbed_latents(
+            new.cuda(), gen, {'truncation': 0.7, 'mean_latent': obj.mean_latent}, layer_no=1, return_image=False)
+        assert torch.equal(only, feats[1])
+        skip = oneshot.create_images_and_features_from_perturbed_latents(
+            new.cuda(), gen, {'truncation': 0.7, 'mean_latent': obj.mean_latent}, return_image=False, skip_const=True)
+        assert len(skip) == len(feats) - 1 and torch.equal(skip[0], feats[1])

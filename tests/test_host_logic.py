@@ -93,6 +93,43 @@ def test_config_tables_match_the_reference_configs():
     assert a.model == "pidray-256" and a.num_test_samples == 3 and a.out_dir == "results/pretrain_default_ffhq/"
 
 
+def test_config_tables_against_the_reference_config_files():
+    """every per-model / per-method number of ganecdotes_b200.configs against tests/golden/reference_configs.json
+    (written by tests/golden/make_config_table.py from the reference's own config files)."""
+    import json
+    import os
+    from ganecdotes_b200 import configs
+    table = json.load(open(os.path.join(os.path.dirname(__file__), "golden", "reference_configs.json")))
+    assert set(table["models"]) <= set(configs.MODELS)
+    for name, ref in table["models"].items():
+        mc = configs.model_config(name)
+        assert mc.truncation == ref["truncation"], name
+        assert mc.num_latents_for_mean == ref["num_latents_for_mean"] and mc.latent_dim == ref.get("latent_dim", 512)
+        assert mc.is_baggan == ref.get("is_baggan", False), name
+        if name == "car-512":       # documented override: BASELINE.json asks for 512^2 features, lsun_car_512.py:8 says 256
+            assert mc.image_size == 512 and ref["image_size"] == 256
+        else:
+            assert mc.image_size == ref["image_size"], name
+        assert mc.gen_args["style_dim"] == ref["gen_args"]["style_dim"] and mc.gen_args["n_mlp"] == ref["gen_args"]["n_mlp"]
+    model_of = {"hfc_with_swav_ffhq": "ffhq-256", "hfc_with_swav_cat": "cat-256", "hfc_with_swav_car": "car-512",
+                "hfc_with_swav_horse": "horse-256", "hfc_with_swav_pidray": "pidray-256", "hfc_with_swav": "afhq-256"}
+    assert set(table["segmentors"]) == set(model_of)
+    for method, ref in table["segmentors"].items():
+        model = model_of[method]
+        assert configs.method_for(model) == method
+        c = configs.swav_config(model)
+        assert c["perturb_args"] == ref["perturb_args"], method
+        assert c["perturb_args"]["n_layers"] == ref["n_hfc_layers"] == 6
+        assert c["swav_args"] == ref["swav_args"], (method, {k: (c["swav_args"].get(k), v) for k, v in
+                                                             ref["swav_args"].items() if c["swav_args"].get(k) != v})
+        assert c["sinkhorn_args"] == ref["sinkhorn_args"], method
+        assert c["layer_hf_dim"] == ref["layer_hf_dim"]
+        assert configs.seg_args(model) == ref["seg_args"], method
+    for tool in ("pliers", "hammer", "powerbank", "wrench", "handcuffs"):
+        assert configs.model_config(f"pidray-{tool}-256").truncation == 0.95
+        assert configs.method_for(f"pidray-{tool}-256") == "hfc_with_swav_pidray"
+
+
 def test_separable_factors_of_blur_filters():
     """host side of the separable blur kernel: make_kernel filters factor exactly, a generic 4x4 filter does not"""
     from ganecdotes_b200._lib import separable_factors
