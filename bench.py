@@ -1,17 +1,22 @@
 #!/usr/bin/env python
-"""Benchmark of the ffhq-256 hfc_with_swav pretrain step (BASELINE.json metric:
-per-pixel feature vectors / s).
+"""Benchmarks of the per-pixel hidden-feature clustering path (BASELINE.json).
 
-    python bench.py --gpus N --steps K --warmup W              # this repo's CUDA path
-    python bench.py --impl reference --gpus N --steps K ...    # CPU oracle port on the host cores
+    python bench.py --gpus N --steps K --warmup W                 # headline: ffhq-256 hfc_with_swav step
+    python bench.py --workload car-512 | pidray-256-labelmap | kmeans-assign      # BASELINE configs 3 / 4 / 5
+    python bench.py --impl reference [--workload ...]             # the same workload on the host CPU (oracle port)
 
-One "step" = one optimiser step of SwAVClustering.pretrain over B latents per GPU
-(weak scaling): 2 latent-perturbed views x 5 patches x 20000 random pixels per latent,
-D = 5376, C = 512, K = 5000 prototypes, 10 Sinkhorn iterations, LARC+SGD - i.e.
-B * 200000 per-pixel feature vectors per GPU per step, synthetic latents, random-init
-StyleGAN2-256 + head (seed 42).  `value` is timed on the device with inputs resident in
-HBM; `e2e` goes through the public step API from pinned host buffers (latents, random
+Headline (BASELINE metric, per-pixel feature vectors / s): one "step" = one optimiser step of
+SwAVClustering.pretrain over B latents per GPU (weak scaling): 2 latent-perturbed views x 5 patches x 20000
+random pixels per latent, D = 5376, C = 512, K = 5000 prototypes, 10 Sinkhorn iterations, LARC+SGD - i.e.
+B * 200000 per-pixel feature vectors per GPU per step, synthetic latents, random-init StyleGAN2-256 + head
+(seed 42).  `value` is timed on the device with the step's raw inputs resident in HBM (the index bookkeeping
+kernels are part of the step); `e2e` goes through the public step API from pinned host buffers (latents, random
 draws, sampled-pixel indices) and reads the loss back every step.
+
+Every line carries `roofline` (dominant kernel, live CUDA-event timing), `cpu_baseline` (the oracle port on the
+host cores, bounded sample) and `e2e`.  The headline line also carries `eager_gpu` (the same step in eager
+PyTorch on the same B200 and the reference's own upfirdn2d / fused_bias_act CUDA kernels built for sm_100a,
+beside the gx_ kernels), `alt_score_gemm_mode`, `alt_bwd_passes3`, and - on several GPUs - `dist_parity`.
 """
 import argparse
 import json
@@ -26,9 +31,15 @@ import torch
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
-FFHQ = dict(size=256, style_dim=512, n_mlp=8, hlen=5376, nclasses=512, nprototypes=5000, patch=20000, npatch=5,
-            niters=10, eps=0.005, temperature=0.01, truncation=0.7, n_layers=6, perturb_std=[1.0] * 6,
+FFHQ = dict(name="ffhq-256", size=256, style_dim=512, n_mlp=8, hlen=5376, nclasses=512, nprototypes=5000, patch=20000,
+            npatch=5, niters=10, eps=0.005, temperature=0.01, truncation=0.7, n_layers=6, perturb_std=[1.0] * 6,
             lr=0.01, momentum=0.9, trust=0.01)
+# configs/segmentors/hfc_with_swav_car_config.py:51-65 on BASELINE.json's 512^2 generator
+CAR = dict(FFHQ, name="car-512", size=512, nprototypes=4000, eps=0.01, temperature=0.01)
+METRIC = {"ffhq-256": "per-pixel feature vectors/sec (ffhq-256 SwAV step)",
+          "car-512": "per-pixel feature vectors/sec (car-512 SwAV step)",
+          "pidray-256-labelmap": "label-map pixels/sec (pidray-256 predict_swav_codes + argmax)",
+          "kmeans-assign": "per-pixel k-means assignments/sec (ffhq-256 hfc_kmeans, 5 layers)"}
 
 
 def peaks():
@@ -91,100 +102,257 @@ class ClockSampler:
                 "reasons": reasons, "samples": len(rows)}
 
 
+def dist_env():
+    return (int(os.environ.get("WORLD_SIZE", "1")), int(os.environ.get("RANK", "0")),
+            int(os.environ.get("LOCAL_RANK", "0")))
+
+
+def stage_table(log, steps, total_ms, issued=None):
+    """per-kernel totals from the CUDA events recorded around every launch of the timed region"""
+    issued = issued or {}
+    stages = {}
+    for name, a, c, work in log:
+        s = stages.setdefault(name, [0.0, 0.0, 0])
+        s[0] += a.elapsed_time(c)
+        s[1] += work
+        s[2] += 1
+    pk = peaks()
+    rows = []
+    for name, (tms, work, cnt) in sorted(stages.items(), key=lambda kv: -kv[1][0]):
+        is_tensor = name.split("_")[0].split("@")[0] in {"gemm", "modconv", "segmentor"}
+        peak = pk["tf_sustained"] if is_tensor else pk["hbm"]
+        achieved = (work / (tms * 1e-3)) / (1e12 if is_tensor else 1e9) if tms > 0 else 0.0
+        row = {"kernel": name, "bound": "tensor" if is_tensor else "hbm", "launches": cnt,
+               "ms_per_step": tms / steps, "share": tms / total_ms, "achieved": achieved, "peak": peak,
+               "unit": "TFLOP/s" if is_tensor else "GB/s", "frac": achieved / peak}
+        if is_tensor:
+            p = issued.get(name.split("@")[0], 1)
+            row["mma_passes"] = p
+            row["frac_issued"] = p * achieved / peak
+            if p > 1:   # precision-adjusted ceiling of the algorithmic fraction (DESIGN.md §4.2)
+                row["ceiling"] = f"{p}-pass split-bf16 (fp32-grade products) => algorithmic cap {1.0 / p:.0%} of the bf16 peak"
+        rows.append(row)
+    return rows, stages, pk
+
+
+def roofline_of(rows, stages, pk):
+    if not rows:
+        return None
+    top = rows[0]
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "ncu_traffic.json")
+    if os.path.exists(tpath):
+        with open(tpath) as f:
+            traffic = json.load(f).get(top["kernel"], {}).get("dram_bytes_per_launch")
+    tms, work, cnt = stages[top["kernel"]]
+    return {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
+            "unit": top["unit"], "frac": top["frac"], "traffic": traffic, "algorithmic_per_launch": work / cnt,
+            "launches": cnt, "ms_per_launch": tms / cnt, "peak_source": pk["src"],
+            "note": "algorithmic FLOPs/bytes per launch / mean CUDA-event launch time; a 3-pass split-bf16 GEMM "
+                    "issues 3x its algorithmic FLOPs on the tensor pipe"}
+
+
 # ----------------------------------------------------------------------------------------
-# reference arm / cpu baseline: the oracle port on the host cores
+# CPU legs (reference arm / cpu_baseline): the oracle port on the host cores
 # ----------------------------------------------------------------------------------------
 
-def cpu_reference_step(state, cfg, seed):
-    """A bounded sample of the workload on the CPU: 1 latent, 2 views, 1 of the 5 patches
-    (20000 px) through the full step (synthesis, upsample+concat, rotate/flip, sampling,
-    projection, prototypes, 2x Sinkhorn, loss, backward, LARC+SGD).  Returns vectors done."""
-    from oracle import ganecdotes_oracle as O
-    sd, mean_latent, wp, wk, bk = state
-    g = torch.Generator().manual_seed(seed)
-    rs = np.random.RandomState(seed)
-    z = torch.randn(1, cfg["style_dim"], generator=g)
-    w = O.style_mlp(sd, z)
-    rows = {}
-    hw = cfg["size"] ** 2
-    perm = torch.randperm(hw, generator=g)
-    for v in "st":
-        hf, _ = O.view_features(sd, w, mean_latent, cfg["truncation"], int(rs.randint(cfg["n_layers"])),
-                                torch.randn(2 * cfg["n_layers"], cfg["style_dim"], generator=g), cfg["n_layers"],
-                                cfg["perturb_std"], cfg["hlen"])
-        hf = O.rotate_flip(hf, float(rs.uniform(-10, 10)), bool(rs.rand() < 0.5))
-        rows[v] = [O.sample_rows(hf, perm, cfg["patch"])]
-        del hf
-    out = O.swav_step(rows["s"], rows["t"], wp, wk, bk, cfg["niters"], cfg["eps"], cfg["temperature"], None,
-                      cfg["lr"], cfg["momentum"], cfg["trust"])
-    state[2], state[3], state[4] = out["params"]
-    return 2 * cfg["patch"]
-
-
-def make_cpu_state(cfg):
+def make_cpu_state(cfg, device="cpu"):
     from oracle import ganecdotes_oracle as O
     torch.manual_seed(42)
     sd = O.init_generator_state(cfg["size"], cfg["style_dim"], cfg["n_mlp"], 42, randomize_small=False)
     mean_latent = O.style_mlp(sd, torch.randn(4096, cfg["style_dim"])).mean(0, keepdim=True)
     proj = torch.nn.Linear(cfg["hlen"], cfg["nclasses"], bias=False)
     proto = torch.nn.Linear(cfg["nclasses"], cfg["nprototypes"])
-    return [sd, mean_latent, proj.weight.data.clone(), proto.weight.data.clone(), proto.bias.data.clone()]
+    st = [sd, mean_latent, proj.weight.data.clone(), proto.weight.data.clone(), proto.bias.data.clone()]
+    if device != "cpu":
+        st = [{k: v.to(device) for k, v in sd.items()}] + [t.to(device) for t in st[1:]]
+    return st
 
 
-def time_cpu(cfg, steps, warmup):
-    torch.set_num_threads(os.cpu_count() or 1)
-    state = make_cpu_state(cfg)
-    with torch.no_grad():
-        pass
+def oracle_swav_step(state, cfg, seed, npatch=None, device="cpu"):
+    """The reference's step (ref swav_clustering.py:320-460) as restated by the oracle: 1 latent, 2 views, `npatch`
+    patches of 20000 px through synthesis, upsample+concat, rotate/flip, sampling, projection, prototypes,
+    2 x Sinkhorn per patch, loss, backward, LARC+SGD.  Synthesis and rotation are done once per view and shared
+    by the patches, as in the reference.  Returns the number of per-pixel feature vectors processed."""
+    from oracle import ganecdotes_oracle as O
+    sd, mean_latent, wp, wk, bk = state
+    npatch = npatch or cfg["npatch"]
+    g = torch.Generator().manual_seed(seed)
+    rs = np.random.RandomState(seed)
+    z = torch.randn(1, cfg["style_dim"], generator=g).to(device)
+    w = O.style_mlp(sd, z)
+    hw = cfg["size"] ** 2
+    perms = [torch.randperm(hw, generator=g).to(device) for _ in range(npatch)]
+    rows = {}
+    for v in "st":
+        hf, _ = O.view_features(sd, w, mean_latent, cfg["truncation"], int(rs.randint(cfg["n_layers"])),
+                                torch.randn(2 * cfg["n_layers"], cfg["style_dim"], generator=g).to(device),
+                                cfg["n_layers"], cfg["perturb_std"], cfg["hlen"])
+        hf = O.rotate_flip(hf, float(rs.uniform(-10, 10)), bool(rs.rand() < 0.5))
+        rows[v] = [O.sample_rows(hf, perms[p], cfg["patch"]) for p in range(npatch)]
+        del hf
+    out = O.swav_step(rows["s"], rows["t"], wp, wk, bk, cfg["niters"], cfg["eps"], cfg["temperature"], None,
+                      cfg["lr"], cfg["momentum"], cfg["trust"])
+    state[2], state[3], state[4] = out["params"]
+    return 2 * npatch * cfg["patch"]
+
+
+def time_oracle_swav(cfg, steps, warmup, device="cpu"):
+    if device == "cpu":
+        torch.set_num_threads(os.cpu_count() or 1)
+    state = make_cpu_state(cfg, device)
+    sync = (lambda: torch.cuda.synchronize()) if device != "cpu" else (lambda: None)
     for i in range(warmup):
-        cpu_reference_step(state, cfg, 1000 + i)
+        oracle_swav_step(state, cfg, 1000 + i, device=device)
+    sync()
     t0 = time.perf_counter()
     vecs = 0
     for i in range(steps):
-        vecs += cpu_reference_step(state, cfg, 2000 + i)
+        vecs += oracle_swav_step(state, cfg, 2000 + i, device=device)
+    sync()
     dt = time.perf_counter() - t0
     return vecs / dt, dt / max(steps, 1), torch.get_num_threads()
 
 
-def workload_name(b):
-    return (f"ffhq-256 hfc_with_swav pretrain step: {b} latents/GPU x 2 views x 5 patches x 20000 px, "
-            f"D=5376 C=512 K=5000, Sinkhorn 10 it, fwd+bwd+LARC/SGD")
+def swav_workload_name(cfg, b):
+    return (f"{cfg['name']} hfc_with_swav pretrain step: {b} latents/GPU x 2 views x {cfg['npatch']} patches x "
+            f"{cfg['patch']} px, D={cfg['hlen']} C={cfg['nclasses']} K={cfg['nprototypes']}, eps={cfg['eps']} "
+            f"T={cfg['temperature']}, Sinkhorn {cfg['niters']} it, fwd+bwd+LARC/SGD")
+
+
+CPU_SWAV_SAMPLE = ("per step: ONE latent x 2 views x all 5 patches x 20000 px (200000 vectors) through the full step "
+                   "of the reference as restated by the oracle, on the host CPU; the GPU arm runs the same step on "
+                   "{b} latents per GPU")
 
 
 def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
+    """`--impl reference`: the reference's CPU path (oracle port; the reference is a script repository, not
+    installable) with all host threads, rank 0 only."""
+    world, rank, _ = dist_env()
     if rank != 0:
         return
-    cfg = FFHQ
-    value, sec_per_step, cores = time_cpu(cfg, args.steps, max(args.warmup, 1))
-    sample = "per step: 1 latent x 2 views x 1 of 5 patches (20000 px) through the full step on the host CPU"
-    line = {
-        "impl": "reference", "metric": "per-pixel feature vectors/sec (ffhq-256 SwAV step)", "value": value,
-        "unit": "vectors/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": max(args.warmup, 1),
-        "ms_per_step": sec_per_step * 1e3, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-        "dtype": "f32", "data": "synthetic",
-        "config": {"workload": workload_name(args.latents_per_gpu), "sample": sample},
-        "cpu_baseline": {"value": value, "unit": "vectors/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
-    }
+    wl = args.workload
+    if wl in ("ffhq-256", "car-512"):
+        cfg = FFHQ if wl == "ffhq-256" else CAR
+        b = args.latents_per_gpu or (8 if wl == "ffhq-256" else 2)
+        warm = 1 if args.warmup > 0 else 0
+        value, sec, cores = time_oracle_swav(cfg, args.steps, warm)
+        sample = CPU_SWAV_SAMPLE.format(b=b)
+        line = {"impl": "reference", "metric": METRIC[wl], "value": value, "unit": "vectors/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
+                "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": swav_workload_name(cfg, b), "sample": sample},
+                "cpu_baseline": {"value": value, "unit": "vectors/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": value, "unit": "vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+    elif wl == "pidray-256-labelmap":
+        v, sec, cores, sample = cpu_labelmap(args.steps, 1 if args.warmup > 0 else 0)
+        line = {"impl": "reference", "metric": METRIC[wl], "value": v, "unit": "pixels/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": 1 if args.warmup > 0 else 0, "ms_per_step": sec * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": labelmap_workload_name(args.images_per_gpu), "sample": sample},
+                "cpu_baseline": {"value": v, "unit": "pixels/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": v, "unit": "pixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
+    else:
+        v, sec, cores, sample = cpu_kmeans(args.steps, 1 if args.warmup > 0 else 0)
+        line = {"impl": "reference", "metric": METRIC[wl], "value": v, "unit": "pixels/s", "n_gpus": args.gpus,
+                "steps": args.steps, "warmup": 1 if args.warmup > 0 else 0, "ms_per_step": sec * 1e3,
+                "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                "config": {"workload": kmeans_workload_name(args.images_per_gpu), "sample": sample},
+                "cpu_baseline": {"value": v, "unit": "pixels/s", "cores": cores, "kind": "port", "sample": sample},
+                "e2e": {"value": v, "unit": "pixels/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+                "gpu_launches": 0}
     print(json.dumps(line), flush=True)
 
 
 # ----------------------------------------------------------------------------------------
-# this repo's arm
+# GPU-side baselines on the same B200 (headline workload only)
 # ----------------------------------------------------------------------------------------
 
-def run_ours(args):
+def _cuda_ms(fn, iters=20, warm=3):
+    for _ in range(warm):
+        fn()
+    torch.cuda.synchronize()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(iters):
+        fn()
+    e1.record()
+    torch.cuda.synchronize()
+    return e0.elapsed_time(e1) / iters
+
+
+def eager_gpu_block(cfg, ours_vectors_per_s_per_gpu):
+    """(1) the oracle's step - eager PyTorch: cuDNN convs, torch.matmul (fp32, TF32 off), ATen Sinkhorn / loss /
+    autograd - on the same B200, one latent per step like the reference; (2) the reference's own CUDA kernels
+    (lib/gan/optim/upfirdn2d_kernel.cu, fused_bias_act_kernel.cu, built unmodified for sm_100a into oracle/_ref/)
+    beside gx_upfirdn2d / gx_fused_bias_act on a StyleGAN2 256^2 layer shape.  Baselines, not the product."""
+    from ganecdotes_b200 import _lib as L
+    out = {}
+    try:
+        torch.backends.cuda.matmul.allow_tf32 = False
+        torch.backends.cudnn.allow_tf32 = False
+        v, sec, _ = time_oracle_swav(cfg, 2, 1, device="cuda")
+        out["eager_step"] = {"value": v, "unit": "vectors/s", "sec_per_step": sec,
+                             "what": "oracle step (eager PyTorch fp32: cuDNN / cuBLAS / ATen) on cuda:0, 1 latent x 2 "
+                                     "views x 5 patches x 20000 px per step",
+                             "ours_over_eager": ours_vectors_per_s_per_gpu / v}
+    except Exception as e:  # baseline only: never fails the bench
+        out["eager_step"] = {"error": repr(e)[:200]}
+    torch.cuda.empty_cache()
+    try:
+        from oracle import build_ref
+        up, fb = build_ref.load("ref_upfirdn2d"), build_ref.load("ref_fused_bias_act")
+        if up is None or fb is None:
+            out["reference_cuda_ops"] = {"unavailable": "oracle/_ref not built (python oracle/build_ref.py)"}
+            return out
+        # the blur after the 128 -> 256 up-conv of StyleGAN2-256 (ref model.py:166-182): [B*C, 257, 257, 1], pad (1,1)
+        b, c, h = 16, 128, 257
+        x = torch.randn(b * c, h, h, 1, device="cuda")
+        k1 = torch.tensor([1., 3., 3., 1.], device="cuda")
+        k = (k1[None, :] * k1[:, None]) / k1.sum() ** 2 * 4
+        y_ref = up.upfirdn2d(x, k, 1, 1, 1, 1, 1, 1, 1, 1)
+        y_gx = L.upfirdn2d_raw(x, k, 1, 1, 1, 1, 1, 1, 1, 1)
+        err_up = (y_ref - y_gx).abs().max().item()
+        nbytes = (x.numel() + y_ref.numel()) * 4
+        t_ref = _cuda_ms(lambda: up.upfirdn2d(x, k, 1, 1, 1, 1, 1, 1, 1, 1))
+        t_gx = _cuda_ms(lambda: L.upfirdn2d_raw(x, k, 1, 1, 1, 1, 1, 1, 1, 1))
+        xa = torch.randn(b, c, 256, 256, device="cuda")
+        bias = torch.randn(c, device="cuda")
+        empty = torch.empty(0, device="cuda")
+        z_ref = fb.fused_bias_act(xa, bias, empty, 3, 0, 0.2, 2 ** 0.5)
+        z_gx = L.fused_bias_act_raw(xa, bias, None, 3, 0, 0.2, 2 ** 0.5)
+        err_fb = (z_ref - z_gx).abs().max().item()
+        t_ref2 = _cuda_ms(lambda: fb.fused_bias_act(xa, bias, empty, 3, 0, 0.2, 2 ** 0.5))
+        t_gx2 = _cuda_ms(lambda: L.fused_bias_act_raw(xa, bias, None, 3, 0, 0.2, 2 ** 0.5))
+        nb2 = 2 * xa.numel() * 4
+        hbm = peaks()["hbm"]
+        out["reference_cuda_ops"] = {
+            "upfirdn2d_blur_256": {"shape": [b * c, h, h, 1], "reference_ms": t_ref, "gx_ms": t_gx,
+                                   "reference_gbs": nbytes / t_ref / 1e6, "gx_gbs": nbytes / t_gx / 1e6,
+                                   "gx_frac_hbm": nbytes / t_gx / 1e6 / hbm, "max_abs_diff": err_up},
+            "fused_bias_act_256": {"shape": [b, c, 256, 256], "reference_ms": t_ref2, "gx_ms": t_gx2,
+                                   "reference_gbs": nb2 / t_ref2 / 1e6, "gx_gbs": nb2 / t_gx2 / 1e6,
+                                   "gx_frac_hbm": nb2 / t_gx2 / 1e6 / hbm, "max_abs_diff": err_fb},
+            "what": "the reference's lib/gan/optim kernels compiled unmodified for sm_100a (oracle/_ref) vs the gx_ ops"}
+    except Exception as e:
+        out["reference_cuda_ops"] = {"error": repr(e)[:200]}
+    return out
+
+
+# ----------------------------------------------------------------------------------------
+# SwAV training step (ffhq-256 headline, car-512)
+# ----------------------------------------------------------------------------------------
+
+def run_swav(args, cfg):
     import torch.distributed as dist
     from ganecdotes_b200 import _lib as L
     from ganecdotes_b200.hfc_with_swav import engine as E
+    from ganecdotes_b200.hfc_with_swav.swav_clustering import SwAVClustering
     from ganecdotes_b200.stylegan2.model import Generator
 
-    cfg = FFHQ
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world, rank, local_rank = dist_env()
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     group = None
@@ -192,7 +360,8 @@ def run_ours(args):
         dist.init_process_group("nccl", device_id=dev)
         group = E.DistGroup(dist.group.WORLD, rank, world)
     L.load()
-    b = args.latents_per_gpu
+    headline = cfg["name"] == "ffhq-256"
+    b = args.latents_per_gpu or (8 if headline else 2)
 
     # ---- model + head, identical on every rank (seed 42 = the reference's seed, lib/util/util.py:21-24)
     torch.manual_seed(42)
@@ -203,25 +372,32 @@ def run_ours(args):
         mean_latent = gen.style(torch.randn(4096, cfg["style_dim"]).to(dev)).mean(0, keepdim=True)
     proj = torch.nn.Linear(cfg["hlen"], cfg["nclasses"], bias=False).to(dev)
     proto = torch.nn.Linear(cfg["nclasses"], cfg["nprototypes"]).to(dev)
-    head = E.SwavHead(proj.weight.data, proto.weight.data, proto.bias.data, cfg["lr"], cfg["momentum"], cfg["trust"],
-                      args.passes_fwd, args.passes_bwd, proto_f16=args.proto_f16)
+    w_init = [proj.weight.data.clone(), proto.weight.data.clone(), proto.bias.data.clone()]
+
+    def new_head(passes_bwd=None):
+        return E.SwavHead(w_init[0].clone(), w_init[1].clone(), w_init[2].clone(), cfg["lr"], cfg["momentum"],
+                          cfg["trust"], args.passes_fwd, passes_bwd or args.passes_bwd, proto_f16=args.proto_f16)
+
+    head = new_head()
     scfg = E.StepConfig(hlen=cfg["hlen"], patch_size=cfg["patch"], num_patches=cfg["npatch"], niters=cfg["niters"],
                         eps=cfg["eps"], temperature=cfg["temperature"], truncation=cfg["truncation"],
                         perturb_std=cfg["perturb_std"])
     ws = L.SinkhornWorkspace(cfg["nprototypes"], dev)
+    if group is not None and os.environ.get("GX_SINKHORN_EXCHANGE", "ll") != "nccl":
+        group.ensure_ll(cfg["nprototypes"], dev)
 
-    def draw(seed):
+    def draw(seed, nb=b):
         g = torch.Generator().manual_seed(seed)
         rs = np.random.RandomState(seed)
         hw = cfg["size"] ** 2
 
         def view():
-            return E.ViewDraws(layer_no=[int(rs.randint(cfg["n_layers"])) for _ in range(b)],
-                               pert_z=torch.randn(b, 2 * cfg["n_layers"], cfg["style_dim"], generator=g).pin_memory(),
-                               angle=[float(rs.uniform(-10, 10)) for _ in range(b)],
-                               flip=[bool(rs.rand() < 0.5) for _ in range(b)])
-        return E.StepDraws(z=torch.randn(b, cfg["style_dim"], generator=g).pin_memory(), view_s=view(), view_t=view(),
-                           perms=[[torch.randperm(hw, generator=g) for _ in range(b)] for _ in range(cfg["npatch"])])
+            return E.ViewDraws(layer_no=[int(rs.randint(cfg["n_layers"])) for _ in range(nb)],
+                               pert_z=torch.randn(nb, 2 * cfg["n_layers"], cfg["style_dim"], generator=g).pin_memory(),
+                               angle=[float(rs.uniform(-10, 10)) for _ in range(nb)],
+                               flip=[bool(rs.rand() < 0.5) for _ in range(nb)])
+        return E.StepDraws(z=torch.randn(nb, cfg["style_dim"], generator=g).pin_memory(), view_s=view(), view_t=view(),
+                           perms=[[torch.randperm(hw, generator=g) for _ in range(nb)] for _ in range(cfg["npatch"])])
 
     nsteps = args.warmup + args.steps
     draws = [draw(10_000 * (rank + 1) + i) for i in range(nsteps)]
@@ -232,8 +408,29 @@ def run_ours(args):
             dist.barrier()
             torch.cuda.synchronize()
 
+    def max_over_ranks(x):
+        if world > 1:
+            t = torch.tensor([x], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            return t.item()
+        return x
+
+    def timed_steps(hd, first, count):
+        """`count` steps on fresh inputs (index bookkeeping included), device-timed; max over ranks"""
+        inp = [E.prepare_step_inputs(gen, draws[first + i], scfg, dev) for i in range(count)]
+        sync()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        loss = None
+        for i in range(count):
+            loss = E.swav_train_step_device(gen, hd, mean_latent, inp[i], scfg, group, ws)
+        a1.record()
+        sync()
+        return max_over_ranks(a0.elapsed_time(a1)), loss
+
     # ---------------------------------------------------------------- device-timed region
-    inputs = [E.prepare_step_inputs(gen, d, scfg, dev) for d in draws]       # resident in HBM
+    # raw inputs (latents, draws, sampled-pixel source indices) resident in HBM; everything else is in the step
+    inputs = [E.prepare_step_inputs(gen, d, scfg, dev) for d in draws]
     for i in range(args.warmup):
         E.swav_train_step_device(gen, head, mean_latent, inputs[i], scfg, group, ws)
     sync()
@@ -254,92 +451,49 @@ def run_ours(args):
     sync()
     sampler.mark_end()
     clocks = sampler.summary() if rank == 0 else None
-    ms = e0.elapsed_time(e1)
+    ms = max_over_ranks(e0.elapsed_time(e1))
     launches = L.launch_count
     log = L.event_log
     L.event_log = None
-    if world > 1:
-        t = torch.tensor([ms], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms = t.item()
+    del inputs
     vec_per_step = world * b * 2 * cfg["npatch"] * cfg["patch"]
     value = vec_per_step * args.steps / (ms * 1e-3)
     final_loss = float(loss)
+    if group is not None and group.ll is not None:
+        group.ll.check()
 
-    # per-kernel totals (CUDA events recorded around every launch of the timed region)
-    stages = {}
-    for name, a, c, work in log:
-        s = stages.setdefault(name, [0.0, 0.0, 0])
-        s[0] += a.elapsed_time(c)
-        s[1] += work
-        s[2] += 1
-    pk = peaks()
-    tensor_bound = {"gemm", "modconv"}
-    # tensor-core passes issued per algorithmic FLOP (split-bf16 = 3 MMAs per product)
     issued = {"gemm_prototype_fwd": 1 if args.proto_f16 else 3, "gemm_projection_fwd": args.passes_fwd,
               "modconv": args.passes_fwd, "modconv_up": args.passes_fwd, "gemm_dzn_bwd": args.passes_bwd,
               "gemm_gproto_bwd": args.passes_bwd, "gemm_gproj_bwd": args.passes_bwd}
-    stage_rows = []
-    for name, (tms, work, cnt) in sorted(stages.items(), key=lambda kv: -kv[1][0]):
-        is_tensor = name.split("_")[0] in tensor_bound
-        peak = pk["tf_sustained"] if is_tensor else pk["hbm"]
-        achieved = (work / (tms * 1e-3)) / (1e12 if is_tensor else 1e9) if tms > 0 else 0.0
-        stage_rows.append({"kernel": name, "bound": "tensor" if is_tensor else "hbm", "launches": cnt,
-                           "ms_per_step": tms / args.steps, "share": tms / ms, "achieved": achieved, "peak": peak,
-                           "unit": "TFLOP/s" if is_tensor else "GB/s", "frac": achieved / peak})
-        if is_tensor:
-            stage_rows[-1]["mma_passes"] = issued.get(name, 1)
-            stage_rows[-1]["frac_issued"] = issued.get(name, 1) * achieved / peak
-    top = stage_rows[0] if stage_rows else None
-    roofline = None
-    if top:
-        # DRAM bytes per launch of the dominant kernel from the committed `ncu --set full` capture
-        traffic = None
-        tpath = os.path.join(os.path.dirname(os.path.abspath(__file__)), "profiles", "ncu_traffic.json")
-        if os.path.exists(tpath):
-            with open(tpath) as f:
-                traffic = json.load(f).get(top["kernel"], {}).get("dram_bytes_per_launch")
-        tms, work, cnt = stages[top["kernel"]]
-        roofline = {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
-                    "unit": top["unit"], "frac": top["frac"], "traffic": traffic,
-                    "algorithmic_per_launch": work / cnt, "launches": cnt, "ms_per_launch": tms / cnt,
-                    "peak_source": pk["src"],
-                    "note": "algorithmic FLOPs/bytes per launch / mean CUDA-event launch time; a 3-pass "
-                            "split-bf16 GEMM issues 3x its algorithmic FLOPs on the tensor pipe"}
+    stage_rows, stages, pk = stage_table(log, args.steps, ms, issued)
+    roofline = roofline_of(stage_rows, stages, pk)
 
-    # ---------------------------------------------------------------- the other score-GEMM operand mode
-    # (same steps, device-timed, reported next to the headline; see DESIGN.md §4.2 for the tolerances)
-    alt = None
+    # ---------------------------------------------------------------- alternative precisions, device-timed
+    alt = alt_bwd = None
     if not args.no_alt:
-        head.proto_f16 = not args.proto_f16
         alt_steps = max(1, min(args.steps, 5))
-        for i in range(2):
-            E.swav_train_step_device(gen, head, mean_latent, inputs[i % len(inputs)], scfg, group, ws)
-        sync()
-        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        a0.record()
-        for i in range(alt_steps):
-            E.swav_train_step_device(gen, head, mean_latent, inputs[args.warmup + i], scfg, group, ws)
-        a1.record()
-        sync()
-        alt_ms = a0.elapsed_time(a1)
-        if world > 1:
-            t = torch.tensor([alt_ms], device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            alt_ms = t.item()
+        head.proto_f16 = not args.proto_f16          # the other score-GEMM operand mode
+        timed_steps(head, 0, min(2, nsteps))
+        alt_ms, _ = timed_steps(head, args.warmup, alt_steps)
         alt = {"score_gemm": "fp16x1" if head.proto_f16 else "bf16x3", "steps": alt_steps,
                "ms_per_step": alt_ms / alt_steps, "value": vec_per_step * alt_steps / (alt_ms * 1e-3),
                "unit": "vectors/s"}
         head.proto_f16 = args.proto_f16
+        if args.passes_bwd != 3:                      # what fp32-grade gradients cost (3-pass split-bf16 backward)
+            h3 = new_head(passes_bwd=3)
+            timed_steps(h3, 0, min(2, nsteps))
+            b3_ms, _ = timed_steps(h3, args.warmup, alt_steps)
+            alt_bwd = {"passes_bwd": 3, "steps": alt_steps, "ms_per_step": b3_ms / alt_steps,
+                       "value": vec_per_step * alt_steps / (b3_ms * 1e-3), "unit": "vectors/s",
+                       "note": "backward GEMMs on 3-plane split-bf16 operands: gradients within 3e-3 of fp32 "
+                               "instead of 2e-2 (default bf16x1)"}
+            del h3
 
     # ---------------------------------------------------------------- end-to-end region
-    # public API from pinned host buffers: host bookkeeping + H2D of step i+1 are issued while
-    # the GPU runs step i; the loss of every step is read back to the host.
-    # Same schedule as SwAVClustering.pretrain: inputs of step i+1 go through pinned memory on a side
-    # stream while step i computes; the loss of step i is read back once step i+1 has been launched.
-    # The pipeline first runs `warmup` untimed steps (allocator pools of the side stream, pinned staging
-    # buffers), then K timed steps in steady state: every timed step contains one staging (host bookkeeping
-    # + pinned H2D of the NEXT step's inputs), one optimiser step and one device->host loss read.
+    # Same schedule as SwAVClustering.pretrain: host bookkeeping + pinned H2D of step i+1 go on a side stream while
+    # step i computes; the loss of step i is read back once step i+1 has been launched.  `warmup` untimed steps
+    # (allocator pools of the side stream, pinned staging buffers), then K timed steps in steady state: every timed
+    # step contains one staging, one optimiser step and one device->host loss read.
     e2e_steps = max(1, args.steps)
     e2e_warm = max(1, args.warmup)
     side = torch.cuda.Stream(device=dev)
@@ -355,8 +509,6 @@ def run_ours(args):
                 _ = float(pending)
                 pending = None
             sync()
-            if world > 1:
-                dist.barrier()
             t0 = time.perf_counter()
         ta = time.perf_counter()
         l = E.swav_train_step_device(gen, head, mean_latent, inp, scfg, group, ws)
@@ -373,37 +525,322 @@ def run_ours(args):
             host_ms["wait"] += (td - tc) * 1e3
     _ = float(pending)
     sync()
-    dt = time.perf_counter() - t0
-    if world > 1:
-        t = torch.tensor([dt], device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dt = t.item()
+    dt = max_over_ranks(time.perf_counter() - t0)
     e2e_value = vec_per_step * e2e_steps / dt
+    del inp
 
-    cpu_base = None
+    # ---------------------------------------------------------------- multi-GPU parity, driver-visible
+    dist_parity = None
+    if world > 1:
+        # one latent per rank, sharded over the ranks (distributed Sinkhorn over the NVLink exchange + gradient
+        # all-reduce) against the SAME global batch in one process on rank 0 (no group): loss and weight updates
+        gdraws = draw(777, nb=world)                   # identical on every rank (same seed)
+        h_sh = new_head(passes_bwd=3)
+        l_sh = E.swav_train_step(gen, h_sh, mean_latent, SwAVClustering.shard_draws(gdraws, rank, world), scfg, group,
+                                 ws)
+        torch.cuda.synchronize()
+        if rank == 0:
+            h_one = new_head(passes_bwd=3)
+            l_one = E.swav_train_step(gen, h_one, mean_latent, gdraws, scfg, None, ws)
+            torch.cuda.synchronize()
+            upd = []
+            for a, r_, w0 in zip((h_sh.w_proj, h_sh.w_proto, h_sh.b_proto), (h_one.w_proj, h_one.w_proto, h_one.b_proto),
+                                 w_init):
+                w0n = torch.nn.functional.normalize(w0, dim=1) if w0.dim() == 2 and w0.shape[0] == cfg["nprototypes"] else w0
+                upd.append(((a - r_).norm() / (r_ - w0n).norm().clamp_min(1e-30)).item())
+            rel_loss = abs(l_sh.item() - l_one.item()) / abs(l_one.item())
+            dist_parity = {"what": f"{world} latents sharded 1 per rank vs the same batch in one process on rank 0",
+                           "loss_sharded": l_sh.item(), "loss_single": l_one.item(), "rel_loss_diff": rel_loss,
+                           "rel_update_diff": {"w_proj": upd[0], "w_proto": upd[1], "b_proto": upd[2]},
+                           "exchange": "ll-nvlink" if group.ll is not None else "nccl",
+                           "ok": bool(rel_loss < 1e-4 and max(upd) < 1e-2)}
+            del h_one
+        del h_sh
+        sync()
+
+    cpu_base = eager = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        v, sec, cores = time_cpu(cfg, 1, 1)
+        v, sec, cores = time_oracle_swav(cfg, 1, 0)
         cpu_base = {"value": v, "unit": "vectors/s", "cores": cores, "kind": "port",
-                    "sample": "1 latent x 2 views x 1 of 5 patches (20000 px), full step, after 1 warm-up step",
-                    "sec_per_sample_step": sec}
+                    "sample": CPU_SWAV_SAMPLE.format(b=b) + " - 1 step, no warm-up", "sec_per_sample_step": sec}
+    if rank == 0 and world == 1 and headline and not args.no_eager:
+        del head
+        torch.cuda.empty_cache()
+        eager = eager_gpu_block(cfg, value)
     if rank == 0:
         line = {
-            "metric": "per-pixel feature vectors/sec (ffhq-256 SwAV step)", "value": value, "unit": "vectors/s",
+            "metric": METRIC[cfg["name"]], "value": value, "unit": "vectors/s",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": f"bf16x{args.passes_fwd}-split fwd" + (" (score GEMM fp16x1 on unit-norm operands)" if args.proto_f16 else "") +
                      f" / bf16x{args.passes_bwd} bwd operands, fp32 accumulate + fp32 everywhere else",
             "data": "synthetic",
-            "config": {"workload": workload_name(b), "latents_per_gpu": b, "global_latents": b * world,
-                       "vectors_per_step": vec_per_step, "l2": "inputs_larger_than_l2 (3.2 GB score matrices)",
-                       "generator": "StyleGAN2-256 random init seed 42", "sinkhorn": "joint-batch (distributed)"},
+            "config": {"workload": swav_workload_name(cfg, b), "latents_per_gpu": b, "global_latents": b * world,
+                       "vectors_per_step": vec_per_step,
+                       "l2": f"inputs_larger_than_l2 ({4e-9 * b * cfg['patch'] * cfg['nprototypes']:.1f} GB score matrices)",
+                       "generator": f"StyleGAN2-{cfg['size']} random init seed 42",
+                       "sinkhorn": "joint-batch (distributed)",
+                       "exchange": None if world == 1 else ("ll-nvlink" if group.ll is not None else "nccl")},
             "roofline": roofline, "roofline_stages": stage_rows, "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": "vectors/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps, "ms_per_step": dt * 1e3 / e2e_steps,
                     "host_ms_per_step": {k: v / e2e_steps for k, v in host_ms.items()}},
             "gpu_launches": launches, "clocks": clocks, "final_loss": final_loss, "alt_score_gemm_mode": alt,
+            "alt_bwd_passes3": alt_bwd, "dist_parity": dist_parity, "eager_gpu": eager,
         }
         print(json.dumps(line), flush=True)
+    if world > 1:
+        if group.ll is not None:
+            dist.barrier()
+            group.ll.close()
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------
+# BASELINE config 4: pidray-256 label maps (evaluate.py inference: predict_swav_codes + argmax)
+# ----------------------------------------------------------------------------------------
+
+def labelmap_workload_name(b):
+    return (f"pidray-256 predict_swav_codes: {b} images/GPU per step, BagGAN generator (sum C = 2528) -> per-pixel "
+            f"codes (projection 2528 -> 512) -> arg-max int64 label maps 256x256, truncation 0.9")
+
+
+def cpu_labelmap(steps, warmup):
+    from oracle import ganecdotes_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(42)
+    sd = O.init_generator_state(256, 512, 8, 42, channels=O.baggan_channels(), randomize_small=False)
+    mean_latent = O.style_mlp(sd, torch.randn(1024, 512)).mean(0, keepdim=True)
+    wp = torch.randn(512, 2528) / 2528 ** 0.5
+    n = 0
+    t0 = None
+    for i in range(warmup + steps):
+        if i == warmup:
+            t0 = time.perf_counter()
+        w = O.style_mlp(sd, torch.randn(1, 512))
+        O.predict_codes(sd, w, mean_latent, 0.9, wp, 2528)
+        n += 65536 if i >= warmup else 0
+    dt = time.perf_counter() - t0
+    return n / dt, dt / max(steps, 1), torch.get_num_threads(), "per step: 1 image (65536 label pixels) on the host CPU"
+
+
+def run_labelmap(args):
+    import torch.distributed as dist
+    from ganecdotes_b200 import _lib as L
+    from ganecdotes_b200.baggan import baggan_channels
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    from ganecdotes_b200.stylegan2.model import Generator
+    world, rank, local_rank = dist_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)      # replicas: only the timing barrier / max uses it
+    L.load()
+    b = args.images_per_gpu
+    torch.manual_seed(42)
+    gen = Generator(256, 512, 8, channels=baggan_channels()).to(dev)
+    hlen, trunc = 2528, 0.9
+    wp = (torch.randn(512, hlen) / hlen ** 0.5).to(dev)
+    with torch.no_grad():
+        mean_latent = gen.style(torch.randn(1024, 512).to(dev)).mean(0, keepdim=True)
+    zs = [torch.randn(b, 512, generator=torch.Generator().manual_seed(100 * rank + i)).pin_memory()
+          for i in range(args.warmup + args.steps)]
+    ws_dev = [gen.style(z.to(dev)) for z in zs]
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def step(w):
+        return E.predict_codes(gen, wp, w, mean_latent, trunc, hlen)[1]
+
+    for i in range(args.warmup):
+        step(ws_dev[i])
+    sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    sampler.mark_begin()
+    L.launch_count = 0
+    L.event_log = []
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        labels = step(ws_dev[args.warmup + i])
+    e1.record()
+    sync()
+    sampler.mark_end()
+    clocks = sampler.summary() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    launches, log = L.launch_count, L.event_log
+    L.event_log = None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    px = world * b * 65536
+    value = px * args.steps / (ms * 1e-3)
+    rows, stages, pk = stage_table(log, args.steps, ms, {"gemm_projection_fwd": 3, "modconv": 3, "modconv_up": 3})
+    # e2e: pinned host z in, int64 label maps back on the host, every step
+    sync()
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        with torch.no_grad():
+            w = gen.style(zs[args.warmup + i].to(dev, non_blocking=True))
+        host = step(w).cpu()
+    sync()
+    dt = time.perf_counter() - t0
+    if world > 1:
+        t = torch.tensor([dt], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        dt = t.item()
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, sec, cores, sample = cpu_labelmap(3, 1)
+        cpu_base = {"value": v, "unit": "pixels/s", "cores": cores, "kind": "port", "sample": sample + ", 3 steps"}
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC["pidray-256-labelmap"], "value": value, "unit": "pixels/s", "n_gpus": world,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "bf16x3-split (fp32-grade) convs + projection, fp32 elsewhere",
+            "data": "synthetic",
+            "config": {"workload": labelmap_workload_name(b), "images_per_gpu": b,
+                       "l2": "inputs_larger_than_l2 (codes 512 x 65536 x 4 B = 134 MB per image)",
+                       "parallelism": "replicas (no collective)"},
+            "roofline": roofline_of(rows, stages, pk), "roofline_stages": rows, "cpu_baseline": cpu_base,
+            "e2e": {"value": px * args.steps / dt, "unit": "pixels/s", "h2d_bytes_per_step": b * 512 * 4,
+                    "d2h_bytes_per_step": b * 65536 * 8, "ms_per_step": dt * 1e3 / args.steps},
+            "gpu_launches": launches, "clocks": clocks, "label_checksum": int(labels.sum().item())}), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+# ----------------------------------------------------------------------------------------
+# BASELINE config 5: per-pixel k-means assignment on GAN features (hfc_kmeans predict)
+# ----------------------------------------------------------------------------------------
+KM_CLUSTERS = [4, 8, 16, 32, 64]       # clusters_per_layer of the five layers (8^2 ... 128^2)
+
+
+def kmeans_workload_name(b):
+    return (f"ffhq-256 hfc_kmeans predict: {b} images/GPU per step, layers 8^2..128^2 (C = 1024,1024,1024,1024,512; "
+            f"K = {KM_CLUSTERS}), nearest-centre assignment + one-hot NEAREST maps at 256^2; features resident")
+
+
+def cpu_kmeans(steps, warmup):
+    from oracle import ganecdotes_oracle as O
+    torch.set_num_threads(os.cpu_count() or 1)
+    torch.manual_seed(42)
+    sd = O.init_generator_state(256, 512, 8, 42, randomize_small=False)
+    _, feats, _ = O.generator_forward(sd, torch.randn(1, 512), 1.0, None, False)
+    layers = O.regroup_features(feats)[1:1 + len(KM_CLUSTERS)]        # maps (2n+1, 2n+2) concatenated per layer
+    cen = [torch.randn(k, f.shape[1]) for f, k in zip(layers, KM_CLUSTERS)]
+    px = sum(f.shape[2] ** 2 for f in layers)
+    t0 = None
+    for i in range(warmup + steps):
+        if i == warmup:
+            t0 = time.perf_counter()
+        O.kmeans_layer_maps(layers, cen, 256)
+    dt = time.perf_counter() - t0
+    return px * steps / dt, dt / max(steps, 1), torch.get_num_threads(), "per step: 1 image, 5 layers, on the host CPU"
+
+
+def run_kmeans(args):
+    import torch.distributed as dist
+    from ganecdotes_b200 import _lib as L
+    from ganecdotes_b200.hfc_kmeans import FlatKMeansAssign
+    from ganecdotes_b200.stylegan2.model import Generator
+    world, rank, local_rank = dist_env()
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    L.load()
+    b = args.images_per_gpu
+    torch.manual_seed(42)
+    gen = Generator(256, 512, 8).to(dev)
+    lat = torch.randn(b, gen.n_latent, 512, generator=torch.Generator().manual_seed(rank)).to(dev)
+    _, feats = gen.synthesize(lat, None, need_image=False)
+    feats_nchw = [f.permute(0, 3, 1, 2) for f in feats]
+    cen = [torch.randn(k, feats[2 * n + 1].shape[3] * 2, generator=torch.Generator().manual_seed(n))
+           for n, k in enumerate(KM_CLUSTERS)]
+    km = FlatKMeansAssign(cen, 256, dev)
+    px_img = sum(feats[2 * n + 1].shape[1] ** 2 for n in range(len(KM_CLUSTERS)))
+    alg_bytes = sum(feats[2 * n + 1].numel() * 8 for n in range(len(KM_CLUSTERS)))      # both maps read once, fp32
+
+    def sync():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+            torch.cuda.synchronize()
+
+    def assign_only():
+        for n in range(len(KM_CLUSTERS)):
+            f1, f2 = feats[2 * n + 1], feats[2 * n + 2]
+            with L.timed("kmeans_assign", (f1.numel() + f2.numel()) * 4.0):
+                L.kmeans_assign(f1.reshape(-1, f1.shape[3]), km.centers[n], f2.reshape(-1, f2.shape[3]))
+
+    for _ in range(args.warmup):
+        km.predict(feats_nchw)
+    sync()
+    sampler = ClockSampler(local_rank)
+    if rank == 0:
+        sampler.start()
+        time.sleep(0.3)
+    sampler.mark_begin()
+    L.launch_count = 0
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(args.steps):
+        maps, labs = km.predict(feats_nchw)
+    e1.record()
+    sync()
+    sampler.mark_end()
+    clocks = sampler.summary() if rank == 0 else None
+    ms = e0.elapsed_time(e1)
+    launches = L.launch_count
+    L.event_log = []
+    for _ in range(args.steps):
+        assign_only()
+    torch.cuda.synchronize()
+    rows, stages, pk = stage_table(L.event_log, args.steps, ms, {})
+    L.event_log = None
+    if world > 1:
+        t = torch.tensor([ms], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = t.item()
+    px = world * b * px_img
+    # e2e: features from pinned host memory (the reference's clusterer.predict takes host arrays), labels back
+    host_feats = [feats[i].cpu().pin_memory() for i in range(1, 2 * len(KM_CLUSTERS) + 1)]
+    sync()
+    t0 = time.perf_counter()
+    e2e_steps = max(1, min(args.steps, 5))
+    for _ in range(e2e_steps):
+        dfe = [feats_nchw[0]] + [h.to(dev, non_blocking=True).permute(0, 3, 1, 2) for h in host_feats] + feats_nchw[11:]
+        _, labs = km.predict(dfe)
+        host = [l.cpu() for l in labs]
+    sync()
+    dt = time.perf_counter() - t0
+    cpu_base = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        v, sec, cores, sample = cpu_kmeans(3, 1)
+        cpu_base = {"value": v, "unit": "pixels/s", "cores": cores, "kind": "port", "sample": sample + ", 3 steps"}
+    if rank == 0:
+        print(json.dumps({
+            "metric": METRIC["kmeans-assign"], "value": px * args.steps / (ms * 1e-3), "unit": "pixels/s",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
+            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": kmeans_workload_name(b), "images_per_gpu": b,
+                       "l2": f"inputs_larger_than_l2 ({alg_bytes / 1e6:.0f} MB of features per step)" if alg_bytes > 126e6
+                       else f"flush: none; {alg_bytes / 1e6:.0f} MB of features per step (< L2: raise --images-per-gpu)",
+                       "parallelism": "replicas (no collective)"},
+            "roofline": roofline_of(rows, stages, pk), "roofline_stages": rows, "cpu_baseline": cpu_base,
+            "e2e": {"value": px * e2e_steps / dt, "unit": "pixels/s",
+                    "h2d_bytes_per_step": sum(h.numel() * 4 for h in host_feats),
+                    "d2h_bytes_per_step": b * px_img * 4, "ms_per_step": dt * 1e3 / e2e_steps},
+            "gpu_launches": launches, "clocks": clocks, "label_checksum": int(sum(int(l.sum()) for l in labs))}), flush=True)
     if world > 1:
         dist.destroy_process_group()
 
@@ -414,10 +851,13 @@ def main():
     ap.add_argument("--steps", type=int, default=10)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--latents-per-gpu", type=int, default=8)
+    ap.add_argument("--workload", default="ffhq-256", choices=list(METRIC))
+    ap.add_argument("--latents-per-gpu", type=int, default=0, help="SwAV workloads (default 8 for ffhq-256, 2 for car-512)")
+    ap.add_argument("--images-per-gpu", type=int, default=16, help="label-map / k-means workloads")
     ap.add_argument("--passes-fwd", type=int, default=3, choices=[1, 3])
     ap.add_argument("--passes-bwd", type=int, default=1, choices=[1, 3])
-    ap.add_argument("--no-alt", action="store_true", help="skip the extra timing of the other score-GEMM mode")
+    ap.add_argument("--no-alt", action="store_true", help="skip the extra timings of the other precision modes")
+    ap.add_argument("--no-eager", action="store_true", help="skip the eager-PyTorch / reference-kernel GPU baselines")
     ap.add_argument("--proto-f16", action="store_true",
                     help="pixel x prototype score GEMM on single fp16 planes of the unit-norm operands (|dS| 1.3e-5 "
                          "rms, codes within 3e-3 rms) instead of the default 3-plane bf16 split (2e-7 / 5e-5)")
@@ -425,8 +865,14 @@ def main():
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)
+    elif args.workload == "ffhq-256":
+        run_swav(args, FFHQ)
+    elif args.workload == "car-512":
+        run_swav(args, CAR)
+    elif args.workload == "pidray-256-labelmap":
+        run_labelmap(args)
     else:
-        run_ours(args)
+        run_kmeans(args)
 
 
 if __name__ == "__main__":

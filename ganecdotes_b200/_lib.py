@@ -61,10 +61,20 @@ class gx_gather_desc(C.Structure):
     ]
 
 
+GX_MAX_PEERS = 16
+
+
+class gx_ll_desc(C.Structure):
+    _fields_ = [("peers", C.c_void_p * GX_MAX_PEERS), ("world", C.c_int), ("rank", C.c_int),
+                ("block_words", C.c_longlong), ("seq", C.c_uint), ("err", C.c_void_p)]
+
+
 _I, _LL, _F, _P = C.c_int, C.c_longlong, C.c_float, C.c_void_p
+_LLD = C.POINTER(gx_ll_desc)
 
 _SIGNATURES = {
     "gx_version": ([], _I),
+    "gx_abi_sizeof": ([_I], _I),
     "gx_last_cuda_error": ([], _I),
     "gx_error_string": ([_I], C.c_char_p),
     "gx_device_ok": ([], _I),
@@ -72,8 +82,12 @@ _SIGNATURES = {
     "gx_upfirdn2d": ([_P, _P, _P] + [_I] * 14 + [_P], _I),
     "gx_fused_bias_act": ([_P, _P, _P, _P, _LL, _I, _I, _I, _I, _F, _F, _P], _I),
     "gx_pixel_norm": ([_P, _P, _I, _I, _P], _I),
-    "gx_equal_linear": ([_P, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P], _I),
+    "gx_equal_linear": ([_P, _LL, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P], _I),
     "gx_truncate": ([_P, _P, _P, _LL, _I, _F, _P], _I),
+    "gx_view_wplus": ([_P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _P, _P], _I),
+    "gx_pixel_segments_scratch": ([_LL], _I),
+    "gx_pixel_segments": ([_P, _P, _I, _LL, _I, _LL, _P, _P, _P, _P, _P, _P], _I),
+    "gx_colsum": ([_P, _I, _I, _F, _I, _P, _P], _I),
     "gx_modconv_prepare": ([_P, _F, _P, _P, _P, _I, _I, _I, _I, _P], _I),
     "gx_modconv_demod": ([_P, _P, _P, _I, _I, _I, _P], _I),
     "gx_modulate_split": ([_P, _LL, _P, _P, _P, _I, _LL, _I, _I, _P], _I),
@@ -96,9 +110,16 @@ _SIGNATURES = {
     "gx_tap_spread": ([_P, _I, _I, _I, _I, _I, _P, _P, _P], _I),
     "gx_normalize_rows": ([_P, _LL, _I, _P], _I),
     "gx_sinkhorn_max_parts": ([], _I),
-    "gx_sinkhorn_pass": ([_P, _LL, _I, _LL, _F, _I, _P, _P, _P, _LL, _P, C.POINTER(_I), _P], _I),
+    "gx_peer_alloc": ([_LL, C.POINTER(_P)], _I),
+    "gx_peer_free": ([_P], _I),
+    "gx_peer_export": ([_P, _P], _I),
+    "gx_peer_open": ([_P, C.POINTER(_P)], _I),
+    "gx_peer_close": ([_P], _I),
+    "gx_sinkhorn_pass": ([_P, _LL, _I, _LL, _F, _I, _P, _LLD, _P, _P, _LL, _I, _P, C.POINTER(_I), _P], _I),
     "gx_sinkhorn_reduce": ([_P, _I, _I, _P, _P], _I),
-    "gx_sinkhorn_log_a": ([_P, _P, _I, _P, _P], _I),
+    "gx_sinkhorn_reduce_send": ([_P, _I, _I, _LLD, _P, _P], _I),
+    "gx_ll_recv_sum": ([_LLD, _I, _P, _P], _I),
+    "gx_sinkhorn_log_a": ([_P, _LLD, _P, _I, _P, _P], _I),
     "gx_sinkhorn_q": ([_P, _LL, _I, _LL, _F, _P, _P, _P], _I),
     "gx_loss_max_parts": ([], _I),
     "gx_swav_loss": ([_P, _P, _LL, _I, _LL, _F, _F, _P, _P, _F, _P, _P, C.POINTER(_I), _P, _P, _P, _P, _LL, _P, _P,
@@ -116,22 +137,38 @@ def lib_path() -> str:
     return _build.LIB_PATH
 
 
+GX_ABI_VERSION = 200        # include/ganecdotes_b200.h
+
+
 def load(require_device: bool = True):
-    """Load (building if stale and nvcc is available) the CUDA library."""
+    """Load the CUDA library, rebuilding it first when it is missing or older than its sources (nvcc
+    permitting), then check the ABI handshake: version + sizeof of every descriptor struct."""
     global _LIB
     with _LOCK:
         if _LIB is None:
             path = _build.LIB_PATH
-            if not os.path.exists(path):
-                try:
-                    _build.build()
-                except Exception as e:  # pragma: no cover
+            try:
+                _build.build()          # returns at once when the .so is newer than every source / header
+            except Exception as e:
+                if not os.path.exists(path):
                     raise GxError(f"ganecdotes_b200: CUDA library missing and could not be built: {e}")
+                # no nvcc on this box: a shipped .so is used as is, the handshake below still applies
             lib = C.CDLL(path)
             for name, (argt, rest) in _SIGNATURES.items():
-                fn = getattr(lib, name)
+                try:
+                    fn = getattr(lib, name)
+                except AttributeError:
+                    raise GxError(f"ganecdotes_b200: {path} is stale (no symbol {name}); rebuild with "
+                                  f"`python -m ganecdotes_b200.build`")
                 fn.argtypes = argt
                 fn.restype = rest
+            if lib.gx_version() != GX_ABI_VERSION:
+                raise GxError(f"ganecdotes_b200: library ABI {lib.gx_version()} != binding ABI {GX_ABI_VERSION}; "
+                              f"rebuild with `python -m ganecdotes_b200.build`")
+            for which, st in enumerate((gx_conv_desc, gx_gemm_desc, gx_gather_desc, gx_ll_desc)):
+                if lib.gx_abi_sizeof(which) != C.sizeof(st):
+                    raise GxError(f"ganecdotes_b200: sizeof({st.__name__}) is {lib.gx_abi_sizeof(which)} in the library "
+                                  f"and {C.sizeof(st)} in the binding")
             _LIB = lib
     if require_device:
         if not torch.cuda.is_available():
@@ -264,9 +301,13 @@ def pixel_norm(x):
 
 
 def equal_linear(x, w, b, w_scale, b_scale, act):
+    """x [n, in_dim] fp32 with unit inner stride (rows may be strided: a row of W+ is read in place)"""
     lib = load()
-    _f32(x, "x"), _f32(w, "w"), _f32(b, "b")
+    _f32(w, "w"), _f32(b, "b")
+    if not x.is_cuda or x.dtype != torch.float32 or x.dim() != 2 or x.stride(1) != 1:
+        raise GxError("equal_linear: x must be a 2-D float32 CUDA tensor with unit inner stride")
     n, in_dim = x.shape
+    ldx = x.stride(0) if n > 1 else in_dim
     out_dim = w.shape[0]
     y = torch.empty((n, out_dim), dtype=torch.float32, device=x.device)
     # grid.y limit: chunk rows
@@ -274,10 +315,53 @@ def equal_linear(x, w, b, w_scale, b_scale, act):
     for r0 in range(0, n, step):
         xs = x[r0:r0 + step]
         ys = y[r0:r0 + step]
-        _check(lib.gx_equal_linear(_ptr(xs), _ptr(w), _ptr(b), _ptr(ys), xs.shape[0], in_dim, out_dim,
+        _check(lib.gx_equal_linear(_ptr(xs), ldx, _ptr(w), _ptr(b), _ptr(ys), xs.shape[0], in_dim, out_dim,
                                    float(w_scale), float(b_scale), int(act), _stream()), "gx_equal_linear")
         _count()
     return y
+
+
+def view_wplus(w, noise_w, layer_no, sigma, mean, psi, n_latent):
+    """W+ [rows, n_latent, D] of both perturbed views (gx_view_wplus): w [b, D], noise_w [2*rows, D],
+    layer_no int32 [rows], sigma fp32 [rows] (device tensors)"""
+    lib = load()
+    _f32(w, "w"), _f32(noise_w, "noise_w"), _f32(sigma, "sigma"), _f32(mean, "mean")
+    b, d = w.shape
+    rows = layer_no.numel()
+    if layer_no.dtype != torch.int32 or noise_w.shape[0] != 2 * rows or sigma.numel() != rows or rows % b:
+        raise GxError("view_wplus: layer_no int32 [rows], sigma [rows], noise_w [2*rows, D], rows a multiple of b")
+    out = torch.empty((rows, n_latent, d), dtype=torch.float32, device=w.device)
+    _check(lib.gx_view_wplus(_ptr(w), _ptr(noise_w), _ptr(layer_no), _ptr(sigma), _ptr(mean), float(psi), b, rows,
+                             int(n_latent), d, _ptr(out), _stream()), "gx_view_wplus")
+    _count()
+    return out
+
+
+def pixel_segments(row_src, row_img, hw, npix):
+    """(ridx [P, bn], order [P*bn], seg_off [npix+1]) - gx_pixel_segments; int32 device tensors"""
+    lib = load()
+    patches, bn = row_src.shape
+    dev = row_src.device
+    if row_src.dtype != torch.int32 or row_img.dtype != torch.int32 or not row_src.is_contiguous():
+        raise GxError("pixel_segments: int32 contiguous row_src / row_img")
+    ridx = torch.empty((patches, bn), dtype=torch.int32, device=dev)
+    order = torch.empty((patches * bn,), dtype=torch.int32, device=dev)
+    seg_off = torch.empty((npix + 1,), dtype=torch.int32, device=dev)
+    counts = torch.empty((npix,), dtype=torch.int32, device=dev)
+    scratch = torch.empty((lib.gx_pixel_segments_scratch(npix),), dtype=torch.int32, device=dev)
+    _check(lib.gx_pixel_segments(_ptr(row_src), _ptr(row_img), patches, bn, int(hw), int(npix), _ptr(ridx),
+                                 _ptr(counts), _ptr(scratch), _ptr(seg_off), _ptr(order), _stream()),
+           "gx_pixel_segments")
+    _count(6)
+    return ridx, order, seg_off
+
+
+def colsum(parts, nparts, k, out, scale=1.0, accumulate=False):
+    """out[k] (+)= scale * sum_p parts[p, k]  (gx_colsum)"""
+    _check(load().gx_colsum(_ptr(parts), int(nparts), int(k), float(scale), int(bool(accumulate)), _ptr(out),
+                            _stream()), "gx_colsum")
+    _count()
+    return out
 
 
 def truncate(w, mean, psi):
@@ -694,25 +778,151 @@ class SinkhornWorkspace:
         self.u = torch.empty((k,), dtype=torch.float32, device=device)
 
 
-def sinkhorn_pass(s, inv_eps, first, u_in, r, c, n_total, ws: SinkhornWorkspace):
-    """One streaming pass over S [n,k]; afterwards ws.u holds the LOCAL column sums."""
+class LLExchange:
+    """Exchange buffers of the distributed Sinkhorn on one box (gx_ll_desc, include/ganecdotes_b200.h): one
+    cudaMalloc'ed buffer per rank, mapped into every rank with CUDA IPC; `channels` independent chains (the s and t
+    views), each with two alternating blocks of [world][k] tagged words.  torch.distributed only carries the
+    64-byte IPC handles at construction; the data path is plain NVLink stores issued by the kernels."""
+
+    def __init__(self, pg, rank, world, k, device, channels=2):
+        import torch.distributed as dist
+        lib = load()
+        if world > GX_MAX_PEERS:
+            raise GxError(f"LLExchange: at most {GX_MAX_PEERS} ranks")
+        if k % 4:
+            raise GxError("LLExchange: k must be a multiple of 4")
+        self.rank, self.world, self.k, self.channels = rank, world, k, channels
+        self.block = world * k                                    # words per block
+        nbytes = channels * 2 * self.block * 8
+        own = C.c_void_p()
+        _check(lib.gx_peer_alloc(nbytes, C.byref(own)), "gx_peer_alloc")
+        self.own = own.value
+        handle = (C.c_char * 64)()
+        _check(lib.gx_peer_export(self.own, handle), "gx_peer_export")
+        handles = [None] * world
+        dist.all_gather_object(handles, bytes(handle), group=pg)
+        self.ptrs = []
+        for r in range(world):
+            if r == rank:
+                self.ptrs.append(self.own)
+                continue
+            p = C.c_void_p()
+            buf = (C.c_char * 64).from_buffer_copy(handles[r])
+            _check(lib.gx_peer_open(buf, C.byref(p)), "gx_peer_open")
+            self.ptrs.append(p.value)
+        self.err = torch.zeros(1, dtype=torch.int32, device=device)
+        self.seq = [0] * channels
+        dist.barrier(group=pg)         # every buffer is zeroed and mapped before the first store
+
+    @classmethod
+    def simulated(cls, world, k, device, channels=2):
+        """`world` endpoints inside ONE process (all buffers on `device`, no IPC): exercises the slot / parity /
+        sequence protocol of the kernels on a single GPU.  The caller must issue every endpoint's send before any
+        endpoint's receive on the stream (a receive spins until all sends of its exchange have landed)."""
+        lib = load()
+        ptrs = []
+        for _ in range(world):
+            p = C.c_void_p()
+            _check(lib.gx_peer_alloc(channels * 2 * world * k * 8, C.byref(p)), "gx_peer_alloc")
+            ptrs.append(p.value)
+        ends = []
+        for r in range(world):
+            e = cls.__new__(cls)
+            e.rank, e.world, e.k, e.channels, e.block = r, world, k, channels, world * k
+            e.ptrs, e.own = list(ptrs), None         # buffers are owned by endpoint 0's `_sim_owned`
+            e.err = torch.zeros(1, dtype=torch.int32, device=device)
+            e.seq = [0] * channels
+            ends.append(e)
+        ends[0]._sim_owned = ptrs
+        return ends
+
+    def _desc(self, channel, seq):
+        d = gx_ll_desc()
+        for r in range(self.world):
+            d.peers[r] = self.ptrs[r]
+        d.world, d.rank = self.world, self.rank
+        d.block_words = (channel * 2 + (seq & 1)) * self.block
+        d.seq = seq
+        d.err = self.err.data_ptr()
+        return d
+
+    def next_send(self, channel):
+        """descriptor of the next exchange of `channel` (advances its sequence number)"""
+        self.seq[channel] += 1
+        return self._desc(channel, self.seq[channel])
+
+    def last(self, channel):
+        """descriptor of the most recent exchange of `channel` (what a consumer receives)"""
+        return self._desc(channel, self.seq[channel])
+
+    def check(self):
+        """raises if a consumer gave up waiting for a peer (synchronises)"""
+        if int(self.err.item()) != 0:
+            raise GxError("LLExchange: a rank did not receive its peers' marginals within the time-out")
+
+    def close(self):
+        lib = load()
+        if getattr(self, "_sim_owned", None):
+            for p in self._sim_owned:
+                lib.gx_peer_free(p)
+            self._sim_owned, self.ptrs = None, []
+            return
+        if self.own is None:
+            return
+        for r, p in enumerate(self.ptrs):
+            if r != self.rank and p:
+                lib.gx_peer_close(p)
+        if self.own:
+            lib.gx_peer_free(self.own)
+        self.ptrs, self.own = [], None
+
+
+def sinkhorn_pass_parts(s, inv_eps, first, u_in, r, c, n_total, ws: SinkhornWorkspace, u_ll=None, reverse=False):
+    """One streaming pass over S [n,k]: per-CTA partial column sums in ws.partials; returns their count."""
     lib = load()
     n, k = s.shape
     nparts = C.c_int(0)
     with timed("sinkhorn_pass", 4.0 * n * k):
-        _check(lib.gx_sinkhorn_pass(_ptr(s), n, k, s.stride(0), float(inv_eps), int(first), _ptr(u_in), _ptr(r),
-                                    _ptr(c), int(n_total), _ptr(ws.partials), C.byref(nparts), _stream()),
+        _check(lib.gx_sinkhorn_pass(_ptr(s), n, k, s.stride(0), float(inv_eps), int(first), _ptr(u_in),
+                                    C.byref(u_ll) if u_ll is not None else None, _ptr(r), _ptr(c), int(n_total),
+                                    int(bool(reverse)), _ptr(ws.partials), C.byref(nparts), _stream()),
                "gx_sinkhorn_pass")
-    _check(lib.gx_sinkhorn_reduce(_ptr(ws.partials), nparts.value, k, _ptr(ws.u), _stream()), "gx_sinkhorn_reduce")
-    _count(2)
-    return ws.u
+    _count()
+    return nparts.value
 
 
-def sinkhorn_log_a(u, r):
+def sinkhorn_reduce(parts, nparts, k, out):
+    _check(load().gx_sinkhorn_reduce(_ptr(parts), int(nparts), int(k), _ptr(out), _stream()), "gx_sinkhorn_reduce")
+    _count()
+    return out
+
+
+def sinkhorn_reduce_send(parts, nparts, k, ll_desc, u_local=None):
+    """column sums of the partials, pushed into this rank's slot of the exchange block on every rank"""
+    _check(load().gx_sinkhorn_reduce_send(_ptr(parts), int(nparts), int(k), C.byref(ll_desc), _ptr(u_local), _stream()),
+           "gx_sinkhorn_reduce_send")
+    _count()
+
+
+def ll_recv_sum(ll_desc, k, device):
+    u = torch.empty((k,), dtype=torch.float32, device=device)
+    _check(load().gx_ll_recv_sum(C.byref(ll_desc), int(k), _ptr(u), _stream()), "gx_ll_recv_sum")
+    _count()
+    return u
+
+
+def sinkhorn_pass(s, inv_eps, first, u_in, r, c, n_total, ws: SinkhornWorkspace, reverse=False):
+    """One streaming pass over S [n,k]; afterwards ws.u holds the LOCAL column sums."""
+    nparts = sinkhorn_pass_parts(s, inv_eps, first, u_in, r, c, n_total, ws, reverse=reverse)
+    return sinkhorn_reduce(ws.partials, nparts, s.shape[1], ws.u)
+
+
+def sinkhorn_log_a(u, r, u_ll=None, k=None, device=None):
     lib = load()
-    k = u.numel()
-    la = torch.empty((k,), dtype=torch.float32, device=u.device)
-    _check(lib.gx_sinkhorn_log_a(_ptr(u), _ptr(r), k, _ptr(la), _stream()), "gx_sinkhorn_log_a")
+    k = u.numel() if u is not None else k
+    la = torch.empty((k,), dtype=torch.float32, device=u.device if u is not None else device)
+    _check(lib.gx_sinkhorn_log_a(_ptr(u), C.byref(u_ll) if u_ll is not None else None, _ptr(r), k, _ptr(la),
+                                 _stream()), "gx_sinkhorn_log_a")
     _count()
     return la
 
@@ -727,13 +937,17 @@ def sinkhorn_q(s, inv_eps, log_a):
     return q
 
 
-def swav_loss(s_s, s_t, inv_eps, inv_temp, la_s, la_t, grad_scale, want_lo=False, want_f32=False, want_db=True):
-    """Returns (loss_sum tensor [1] (not divided by N), dS_s planes, dS_t planes, db [k], f32 grads)."""
+def swav_loss(s_s, s_t, inv_eps, inv_temp, la_s, la_t, grad_scale, want_lo=False, want_f32=False, want_db=True,
+              loss_parts=None, db_accum=None):
+    """Returns (loss_parts [gx_loss_max_parts()] per-CTA sums (not divided by N), dS_s planes, dS_t planes, db [k],
+    f32 grads).  loss_parts: a zeroed caller buffer to fill (else allocated); db_accum: the bias gradient is
+    accumulated into it (db_accum += column sums of dS_s + dS_t) instead of being returned."""
     lib = load()
     n, k = s_s.shape
     dev = s_s.device
     maxp = lib.gx_loss_max_parts()
-    loss_parts = torch.zeros((maxp,), dtype=torch.float32, device=dev)
+    if loss_parts is None:
+        loss_parts = torch.zeros((maxp,), dtype=torch.float32, device=dev)
     db_parts = torch.empty((maxp, k), dtype=torch.float32, device=dev) if want_db else None
     ds_s_hi = torch.empty((n, k), dtype=torch.bfloat16, device=dev)
     ds_t_hi = torch.empty((n, k), dtype=torch.bfloat16, device=dev)
@@ -749,7 +963,9 @@ def swav_loss(s_s, s_t, inv_eps, inv_temp, la_s, la_t, grad_scale, want_lo=False
                                 _ptr(fs), _ptr(ft), _stream()), "gx_swav_loss")
     _count()
     db = None
-    if want_db:
+    if want_db and db_accum is not None:
+        colsum(db_parts, nparts.value, k, db_accum, 1.0, True)
+    elif want_db:
         db = torch.empty((k,), dtype=torch.float32, device=dev)
         _check(lib.gx_sinkhorn_reduce(_ptr(db_parts), nparts.value, k, _ptr(db), _stream()), "gx_sinkhorn_reduce")
         _count()

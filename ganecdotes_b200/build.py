@@ -6,8 +6,8 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libganecdotes_b200.so")
-SOURCES = ["gx_api.cu", "gx_umma.cu", "gx_fir.cu", "gx_synthesis.cu", "gx_head.cu"]
-HEADERS = ["gx_common.cuh", "gx_ptx.cuh", os.path.join("..", "..", "include", "ganecdotes_b200.h")]
+SOURCES = ["gx_api.cu", "gx_umma.cu", "gx_fir.cu", "gx_synthesis.cu", "gx_head.cu", "gx_exchange.cu", "gx_index.cu"]
+HEADERS = ["gx_common.cuh", "gx_ptx.cuh", "gx_ll.cuh", os.path.join("..", "..", "include", "ganecdotes_b200.h")]
 
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",

@@ -29,7 +29,20 @@ extern "C" int gx_set_sm_budget(int umma_ctas, int stream_ctas) {
   return GX_OK;
 }
 
-extern "C" int gx_version(void) { return 100; }
+// bumped whenever a descriptor struct or an exported signature changes
+extern "C" int gx_version(void) { return GX_ABI_VERSION; }
+
+// sizeof() of descriptor `which` (0 conv, 1 gemm, 2 gather, 3 ll): a binding compares it with its own layout at
+// load time, so a stale library is an error and not a silent misread of the struct fields
+extern "C" int gx_abi_sizeof(int which) {
+  switch (which) {
+    case 0: return (int)sizeof(gx_conv_desc);
+    case 1: return (int)sizeof(gx_gemm_desc);
+    case 2: return (int)sizeof(gx_gather_desc);
+    case 3: return (int)sizeof(gx_ll_desc);
+    default: return -1;
+  }
+}
 
 extern "C" int gx_last_cuda_error(void) { return g_last_cuda_error; }
 

@@ -3,8 +3,10 @@
 // maps and k-means assignment.  All kernels use 128-bit coalesced accesses and
 // warp-shuffle + shared-memory reductions; none of them is reshaped into a GEMM.
 #include <stdlib.h>
+#include <string.h>
 
 #include "gx_common.cuh"
+#include "gx_ll.cuh"
 #include "gx_ptx.cuh"
 
 namespace {
@@ -693,8 +695,9 @@ __device__ __forceinline__ void group_bar(int id, int nthreads) {
 template <int J, int R, int GT>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long lds, float scale_log2, int first,
-                     const float* __restrict__ u_in, const float* __restrict__ r, const float* __restrict__ cvec,
-                     float c_uniform, float* __restrict__ partials, int stages) {
+                     const float* __restrict__ u_in, const gx_ll_desc u_ll, const float* __restrict__ r,
+                     const float* __restrict__ cvec, float c_uniform, float* __restrict__ partials, int stages,
+                     int reverse) {
   constexpr int NG = SK_THREADS / GT;   // groups per CTA
   constexpr int NW = GT / 32;           // warps per group
   extern __shared__ __align__(128) uint8_t sk_smem[];
@@ -709,12 +712,17 @@ sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long 
     gxptx::fence_mbar_init();
   }
   __syncthreads();
-  // iteration `it` of this CTA covers rows [(blockIdx.x + it*gridDim.x) * R, +R)
+  // iteration `it` of this CTA covers the row group g = blockIdx.x + it*gridDim.x (rows [g*R, +R)), or - in a
+  // reverse pass - the mirrored group, so that consecutive passes sweep S in opposite directions
   const long long groups_total = (n + R - 1) / R;
   const int n_iters = (int)((groups_total - blockIdx.x + gridDim.x - 1) / gridDim.x);
+  auto first_row = [&](int it) -> long long {
+    const long long g = (long long)blockIdx.x + (long long)it * gridDim.x;
+    return (reverse ? groups_total - 1 - g : g) * R;
+  };
   auto issue = [&](int it) {
     const int st = it % stages;
-    const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * R;
+    const long long row0 = first_row(it);
     const int valid = (int)min((long long)R, n - row0);
     gxptx::mbar_arrive_expect_tx(&full_bar[st], row_bytes * valid);
     for (int rr = 0; rr < valid; ++rr)
@@ -734,14 +742,23 @@ sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long 
   for (int j = 0; j < J; ++j) {
     const int col = j * (GT * 4) + gt * 4;
     coff[j] = min(col, k - 4);
-    float l4[4];
+    float l4[4], u4[4] = {1.f, 1.f, 1.f, 1.f};
+    if (!first && col < k) {
+      // marginals of the previous pass: local vector, or the tagged slots the peers pushed into this rank's
+      // exchange buffer (they arrived while the pass in between was running; the rows above are already in flight)
+      if (u_ll.world > 0) gxll::recv4(u_ll, k, col, u4);
+      else {
+        const float4 uu = *reinterpret_cast<const float4*>(u_in + col);
+        u4[0] = uu.x; u4[1] = uu.y; u4[2] = uu.z; u4[3] = uu.w;
+      }
+    }
 #pragma unroll
     for (int e = 0; e < 4; ++e) {
       if (col < k) {
         l4[e] = 0.f;
         if (!first) {
           const float rk = r ? r[col + e] : 1.f / (float)k;
-          l4[e] = log2f(rk / u_in[col + e]);
+          l4[e] = log2f(rk / u4[e]);
         }
       } else {
         l4[e] = -INFINITY;
@@ -755,7 +772,7 @@ sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long 
   int buf = 0;
   for (int it = grp; it < n_iters; it += NG) {
     const int st = it % stages;
-    const long long row0 = ((long long)blockIdx.x + (long long)it * gridDim.x) * R;
+    const long long row0 = first_row(it);
     gxptx::mbar_wait(&full_bar[st], (uint32_t)((it / stages) & 1));
     const float* srow = reinterpret_cast<const float*>(sk_smem + (size_t)st * stage_bytes);
     float2 p[R][J][2];
@@ -847,12 +864,39 @@ colsum_parts_kernel(const float* __restrict__ parts, int nparts, int k, float* _
   }
 }
 
-__global__ void log_a_kernel(const float* __restrict__ u, const float* __restrict__ r, int k,
+// the same sums, pushed as tagged words into this rank's slot of the exchange block on every rank
+__global__ void __launch_bounds__(256)
+colsum_send_kernel(const float* __restrict__ parts, int nparts, int k, const gx_ll_desc ll,
+                   float* __restrict__ u_local) {
+  __shared__ float red[8][33];
+  const int tx = threadIdx.x & 31, ty = threadIdx.x >> 5;
+  const int col = blockIdx.x * 32 + tx;
+  float acc = 0.f;
+  if (col < k)
+    for (int p = ty; p < nparts; p += 8) acc += parts[(long long)p * k + col];
+  red[ty][tx] = acc;
+  __syncthreads();
+  if (ty == 0 && col < k) {
+    float t = 0.f;
+#pragma unroll
+    for (int i = 0; i < 8; ++i) t += red[i][tx];
+    if (u_local) u_local[col] = t;
+    gxll::send1(ll, k, col, t);
+  }
+}
+
+__global__ void ll_recv_sum_kernel(const gx_ll_desc ll, int k, float* __restrict__ u) {
+  const int col = blockIdx.x * blockDim.x + threadIdx.x;
+  if (col < k) u[col] = gxll::recv1(ll, k, col);
+}
+
+__global__ void log_a_kernel(const float* __restrict__ u, const gx_ll_desc u_ll, const float* __restrict__ r, int k,
                              float* __restrict__ log_a) {
   const int col = blockIdx.x * blockDim.x + threadIdx.x;
   if (col >= k) return;
   const float rk = r ? r[col] : 1.f / (float)k;
-  log_a[col] = logf(rk / u[col]);
+  const float uk = u_ll.world > 0 ? gxll::recv1(u_ll, k, col) : u[col];
+  log_a[col] = logf(rk / uk);
 }
 
 // block-wide reductions of NV values at once (512 threads)
@@ -1644,8 +1688,8 @@ extern "C" int gx_loss_max_parts(void) { return 2 * gx_sm_count(); }
 
 template <int J, int R, int GT>
 static int launch_sinkhorn_pass(const float* s, long long n, int k, long long lds, float scale_log2, int first,
-                                const float* u_in, const float* r, const float* c, float cu, float* partials,
-                                int grid, cudaStream_t st) {
+                                const float* u_in, const gx_ll_desc& u_ll, const float* r, const float* c, float cu,
+                                float* partials, int grid, int reverse, cudaStream_t st) {
   const int stage_bytes = k * 4 * R;
   // Each of the NG groups must own a fixed subset of the ring (stage index parity == iteration
   // parity): with a stage shared between groups, a group running ahead would observe the
@@ -1661,16 +1705,34 @@ static int launch_sinkhorn_pass(const float* s, long long n, int k, long long ld
                                        200 * 1024));
     attr = true;
   }
-  sinkhorn_pass_kernel<J, R, GT><<<grid, SK_THREADS, stages * stage_bytes, st>>>(s, n, k, lds, scale_log2, first, u_in,
-                                                                               r, c, cu, partials, stages);
+  sinkhorn_pass_kernel<J, R, GT><<<grid, SK_THREADS, stages * stage_bytes, st>>>(
+      s, n, k, lds, scale_log2, first, u_in, u_ll, r, c, cu, partials, stages, reverse);
   return GX_OK;
 }
 
+static int ll_desc_ok(const gx_ll_desc* d) {
+  if (!d || d->world == 0) return 1;
+  if (d->world < 0 || d->world > GX_MAX_PEERS || d->rank < 0 || d->rank >= d->world || d->seq == 0 ||
+      d->block_words < 0 || (d->block_words & 3))
+    return 0;
+  for (int r = 0; r < d->world; ++r)
+    if (!d->peers[r] || (reinterpret_cast<uintptr_t>(d->peers[r]) & 31)) return 0;
+  return 1;
+}
+static gx_ll_desc ll_or_none(const gx_ll_desc* d) {
+  gx_ll_desc z;
+  memset(&z, 0, sizeof(z));
+  return (d && d->world > 0) ? *d : z;
+}
+
 extern "C" int gx_sinkhorn_pass(const float* s, long long n, int k, long long lds, float inv_eps, int first,
-                                const float* u_in, const float* r, const float* c, long long n_total,
-                                float* partials, int* nparts_out, void* stream) {
+                                const float* u_in, const gx_ll_desc* u_ll_p, const float* r, const float* c,
+                                long long n_total, int reverse, float* partials, int* nparts_out, void* stream) {
   GX_CHECK_ARG(s && partials && n > 0 && k >= 4 && k % 4 == 0 && lds % 4 == 0 && lds >= k);
-  GX_CHECK_ARG(first || u_in);
+  GX_CHECK_ARG(ll_desc_ok(u_ll_p));
+  const gx_ll_desc u_ll = ll_or_none(u_ll_p);
+  GX_CHECK_ARG(first || u_in || u_ll.world > 0);
+  GX_CHECK_ARG(!u_in || (reinterpret_cast<uintptr_t>(u_in) & 15) == 0);
   GX_CHECK_ARG((reinterpret_cast<uintptr_t>(s) & 15) == 0);
   GX_CHECK_ARG(k <= 8192);
   const int grid = sk_grid(n, SK_ROWS);
@@ -1679,7 +1741,8 @@ extern "C" int gx_sinkhorn_pass(const float* s, long long n, int k, long long ld
   cudaStream_t st = (cudaStream_t)stream;
   int rc;
   const int j256 = gx_cdiv(k, 1024);
-#define GX_SK(J_, GT_) rc = launch_sinkhorn_pass<J_, SK_ROWS, GT_>(s, n, k, lds, sl, first, u_in, r, c, cu, partials, grid, st)
+#define GX_SK(J_, GT_) \
+  rc = launch_sinkhorn_pass<J_, SK_ROWS, GT_>(s, n, k, lds, sl, first, u_in, u_ll, r, c, cu, partials, grid, reverse != 0, st)
   if (j256 <= 5) {
     if (nparts_out) *nparts_out = grid * 2;
     switch (j256) {
@@ -1707,9 +1770,28 @@ extern "C" int gx_sinkhorn_reduce(const float* partials, int nparts, int k, floa
   return GX_OK;
 }
 
-extern "C" int gx_sinkhorn_log_a(const float* u, const float* r, int k, float* log_a, void* stream) {
-  GX_CHECK_ARG(u && log_a && k > 0);
-  log_a_kernel<<<gx_cdiv(k, 256), 256, 0, (cudaStream_t)stream>>>(u, r, k, log_a);
+extern "C" int gx_sinkhorn_reduce_send(const float* partials, int nparts, int k, const gx_ll_desc* ll,
+                                       float* u_local, void* stream) {
+  GX_CHECK_ARG(partials && nparts > 0 && k > 0 && k % 4 == 0 && ll && ll->world > 0 && ll_desc_ok(ll));
+  colsum_send_kernel<<<gx_cdiv(k, 32), 256, 0, (cudaStream_t)stream>>>(partials, nparts, k, *ll, u_local);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_ll_recv_sum(const gx_ll_desc* ll, int k, float* u, void* stream) {
+  GX_CHECK_ARG(u && k > 0 && k % 4 == 0 && ll && ll->world > 0 && ll_desc_ok(ll));
+  ll_recv_sum_kernel<<<gx_cdiv(k, 128), 128, 0, (cudaStream_t)stream>>>(*ll, k, u);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_sinkhorn_log_a(const float* u, const gx_ll_desc* u_ll_p, const float* r, int k, float* log_a,
+                                 void* stream) {
+  GX_CHECK_ARG(log_a && k > 0 && ll_desc_ok(u_ll_p));
+  const gx_ll_desc u_ll = ll_or_none(u_ll_p);
+  GX_CHECK_ARG(u || u_ll.world > 0);
+  GX_CHECK_ARG(u_ll.world == 0 || k % 4 == 0);
+  log_a_kernel<<<gx_cdiv(k, 256), 256, 0, (cudaStream_t)stream>>>(u, u_ll, r, k, log_a);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }

@@ -17,7 +17,7 @@ __global__ void pixel_norm_kernel(const float* __restrict__ x, float* __restrict
 }
 
 // one warp per output element (row, o); 8 rows share one weight row per block
-__global__ void equal_linear_kernel(const float* __restrict__ x, const float* __restrict__ w,
+__global__ void equal_linear_kernel(const float* __restrict__ x, long long ldx, const float* __restrict__ w,
                                     const float* __restrict__ b, float* __restrict__ y, int n, int in_dim, int out_dim,
                                     float w_scale, float b_scale, int act) {
   const int lane = threadIdx.x & 31;
@@ -25,7 +25,7 @@ __global__ void equal_linear_kernel(const float* __restrict__ x, const float* __
   const int o = blockIdx.x;
   const int row = blockIdx.y * (blockDim.x >> 5) + wi;
   if (row >= n) return;
-  const float* xr = x + (long long)row * in_dim;
+  const float* xr = x + (long long)row * ldx;
   const float* wr = w + (long long)o * in_dim;
   float acc = 0.f;
   for (int i = lane; i < in_dim; i += 32) acc = fmaf(xr[i], wr[i] * w_scale, acc);
@@ -110,12 +110,13 @@ extern "C" int gx_pixel_norm(const float* x, float* y, int n, int dim, void* str
   return GX_OK;
 }
 
-extern "C" int gx_equal_linear(const float* x, const float* w, const float* b, float* y, int n, int in_dim,
-                               int out_dim, float w_scale, float b_scale, int act, void* stream) {
-  GX_CHECK_ARG(x && w && y && n > 0 && in_dim > 0 && out_dim > 0);
+extern "C" int gx_equal_linear(const float* x, long long ldx, const float* w, const float* b, float* y, int n,
+                               int in_dim, int out_dim, float w_scale, float b_scale, int act, void* stream) {
+  GX_CHECK_ARG(x && w && y && n > 0 && in_dim > 0 && out_dim > 0 && ldx >= in_dim);
   GX_CHECK_ARG(gx_cdiv(n, 8) <= 65535);
   dim3 grid(out_dim, gx_cdiv(n, 8));
-  equal_linear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, w, b, y, n, in_dim, out_dim, w_scale, b_scale, act);
+  equal_linear_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(x, ldx, w, b, y, n, in_dim, out_dim, w_scale, b_scale,
+                                                              act);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }

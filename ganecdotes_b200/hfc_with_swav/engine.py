@@ -20,6 +20,7 @@ host arithmetic is the data-independent index bookkeeping (rotation/flip index m
 random permutations), a few KB per latent.
 """
 import math
+import os
 from dataclasses import dataclass
 from typing import List, Optional
 
@@ -179,8 +180,16 @@ class SwavHead:
         self.proto_f16 = bool(proto_f16)
         dev = w_proj.device
         self.g_proj = torch.zeros_like(w_proj)
-        self.g_proto = torch.zeros_like(w_proto)
-        self.g_bias = torch.zeros_like(b_proto)
+        # prototype gradients and the loss share one flat buffer [g_proto | g_bias | pad | loss]: one fill per step,
+        # and - on several GPUs - one all-reduce that can start before the projection-weight gradient is folded
+        kc, k = w_proto.numel(), b_proto.numel()
+        off_b = (kc + 3) // 4 * 4
+        off_l = off_b + (k + 3) // 4 * 4
+        self.g_flat = torch.zeros(off_l + 4, dtype=torch.float32, device=dev)
+        self.g_proto = self.g_flat[:kc].view_as(w_proto)
+        self.g_bias = self.g_flat[off_b:off_b + k]
+        self.loss_slot = self.g_flat[off_l:off_l + 1]
+        self.loss_ring = torch.zeros(16, dtype=torch.float32, device=dev)     # losses of the last 16 steps
         self.m_proj = torch.zeros_like(w_proj)
         self.m_proto = torch.zeros_like(w_proto)
         self.m_bias = torch.zeros_like(b_proto)
@@ -213,8 +222,7 @@ class SwavHead:
 
     def zero_grad(self):
         self.g_proj.zero_()
-        self.g_proto.zero_()
-        self.g_bias.zero_()
+        self.g_flat.zero_()
 
     def optimizer_step(self):
         first = 1 if self.steps == 0 else 0
@@ -276,26 +284,78 @@ def scores_forward(head: SwavHead, feats, out_h, out_w, hlen, row_img, row_src, 
 
 def sinkhorn_log_a(s, niters, eps, ws, n_total, group=None, r=None, c=None, pass_fn=None, log_a_fn=None,
                    u_first=None):
-    """Sinkhorn-Knopp in scaling-vector form (ref :509-544): niters streaming passes over
-    the LOCAL rows of S; only u[K] crosses ranks (all-reduce SUM, as in SwAV's distributed
-    Sinkhorn), and c_n = 1/n_total uses the GLOBAL row count.  Returns log a[K];
-    Q = softmax_k(S/eps + log a).
+    """Sinkhorn-Knopp in scaling-vector form (ref :509-544) for ONE score matrix: niters streaming passes over
+    the LOCAL rows of S; only u[K] crosses ranks (as in SwAV's distributed Sinkhorn), and c_n = 1/n_total uses
+    the GLOBAL row count.  Returns log a[K]; Q = softmax_k(S/eps + log a).
 
-    `pass_fn(s, inv_eps, first, u_in, r, c, n_total, ws) -> local column sums u[K]` and
-    `log_a_fn(u, r)` default to the CUDA kernels; the CPU tests of the multi-rank logic
-    inject torch stand-ins.  `u_first`: the result of the first pass if already available."""
-    pass_fn = pass_fn or L.sinkhorn_pass
-    log_a_fn = log_a_fn or L.sinkhorn_log_a
+    With `pass_fn` / `log_a_fn` (the CPU tests of the multi-rank logic inject torch stand-ins with the contract
+    `pass_fn(s, inv_eps, first, u_in, r, c, n_total, ws) -> local column sums u[K]`, `log_a_fn(u, r)`) the
+    exchange is a torch.distributed all-reduce; the CUDA path is `sinkhorn_multi`."""
+    if pass_fn is None and log_a_fn is None:
+        return sinkhorn_multi([dict(s=s, r=r, c=c, u_first=u_first)], niters, eps, ws, n_total, group)[0]
     inv_eps = 1.0 / eps
     u = None
     for it in range(niters):
         if it == 0 and u_first is not None:
-            u = u_first          # local u_k = sum_n exp(S_nk/eps), produced by the score GEMM's epilogue
+            u = u_first
         else:
             u = pass_fn(s, inv_eps, it == 0, u, r, c, n_total, ws)
         if group is not None:
             torch.distributed.all_reduce(u, group=group.pg)
     return log_a_fn(u, r)
+
+
+def sinkhorn_multi(problems, niters, eps, ws, n_total, group=None):
+    """Sinkhorn-Knopp (ref :509-544) on several independent score matrices (the s and t views of a patch):
+    `problems` = [dict(s=S [n,K], r=, c=, u_first=)], returns [log a] per problem.
+
+    One rank: the chains run one after the other, consecutive passes of a chain sweeping S in opposite directions
+    (the tail of S that the L2 still holds is re-used).  Several ranks: the chains are interleaved pass by pass and
+    the K-vector of column marginals goes through the low-latency NVLink exchange (`L.LLExchange`): the reduce
+    kernel of chain A pushes its sums into every peer's buffer, chain B's pass runs meanwhile, and the next pass of
+    chain A picks the peers' values up in its prologue - no collective call, no exposed latency, and a whole
+    pass of slack against rank-to-rank jitter.  Without an exchange object the fallback is an NCCL all-reduce."""
+    inv_eps = 1.0 / eps
+    ll = group.ll if group is not None else None
+    k = problems[0]["s"].shape[1]
+    dev = problems[0]["s"].device
+    if ll is not None and len(problems) > ll.channels:
+        raise ValueError("more Sinkhorn chains than exchange channels")
+    us = [None] * len(problems)
+
+    def advance(ch, it):
+        pb = problems[ch]
+        if it == 0 and pb.get("u_first") is not None:
+            parts, nparts = pb["u_first"], 1       # local u_k = sum_n exp(S_nk/eps) from the score GEMM's epilogue
+        else:
+            u_ll = ll.last(ch) if (ll is not None and it > 0) else None
+            nparts = L.sinkhorn_pass_parts(pb["s"], inv_eps, it == 0, None if u_ll is not None else us[ch],
+                                           pb.get("r"), pb.get("c"), n_total, ws, u_ll=u_ll, reverse=(it & 1) == 1)
+            parts = ws.partials
+        if ll is not None:
+            L.sinkhorn_reduce_send(parts, nparts, k, ll.next_send(ch))
+            return
+        if nparts == 1 and parts is pb.get("u_first"):
+            us[ch] = parts
+        else:
+            if us[ch] is None or us[ch] is pb.get("u_first"):
+                us[ch] = torch.empty((k,), dtype=torch.float32, device=dev)
+            L.sinkhorn_reduce(parts, nparts, k, us[ch])
+        if group is not None:
+            torch.distributed.all_reduce(us[ch], group=group.pg)
+
+    if group is None:
+        for ch in range(len(problems)):
+            for it in range(niters):
+                advance(ch, it)
+    else:
+        for it in range(niters):
+            for ch in range(len(problems)):
+                advance(ch, it)
+    if ll is not None:
+        return [L.sinkhorn_log_a(None, pb.get("r"), u_ll=ll.last(ch), k=k, device=dev)
+                for ch, pb in enumerate(problems)]
+    return [L.sinkhorn_log_a(us[ch], pb.get("r")) for ch, pb in enumerate(problems)]
 
 
 def scores_forward_dedup(head: SwavHead, z_all, row_idx, eps=None):
@@ -423,6 +483,15 @@ class DistGroup:
     pg: object
     rank: int
     world: int
+    ll: Optional[object] = None          # L.LLExchange: NVLink exchange of the Sinkhorn marginals (CUDA ranks)
+
+    def ensure_ll(self, k, device):
+        """create the low-latency exchange for K prototypes (collective: every rank must call it)"""
+        if self.ll is None or self.ll.k != k:
+            if self.ll is not None:
+                self.ll.close()
+            self.ll = L.LLExchange(self.pg, self.rank, self.world, k, device)
+        return self.ll
 
 
 def image_marginals(feats, out_h, out_w, hlen, index_map, k, n):
@@ -460,13 +529,17 @@ class StepConfig:
 @dataclass
 class StepInputs:
     """Device-resident inputs of one optimiser step (what `prepare_step_inputs` uploads)."""
-    z: torch.Tensor                    # [B, D]
-    views: dict                        # name -> (layer_no list, pert rows [2B, D] on device)
+    z: torch.Tensor                    # [B, D]  (view of zcat)
+    views: dict                        # name -> (layer_no list, pert rows [2B, D] on device (view of zcat))
     rows: dict                         # name -> (row_src [P, B*N] int32, row_img [B*N] int32)
     h2d_bytes: int = 0
     index_maps: Optional[dict] = None  # name -> int32 [H*W] (source_pdf == 'image', single latent)
-    dedup: Optional[dict] = None       # name -> (row_idx [P, B*N] int32, order int32, seg_off int32 [B*H*W+1])
+    dedup: Optional[dict] = None       # name -> (row_idx [P, B*N] int32, order int32, seg_off int32 [B*H*W+1]);
+    #                                    {} = "all-pixel path, segments not built yet" (built on the device by the step)
     ready: Optional[object] = None     # CUDA event recorded on the upload stream (None: same stream)
+    zcat: Optional[torch.Tensor] = None      # [B + 2B + 2B, D]: latents, view-s draws, view-t draws (one upload)
+    layer_no: Optional[torch.Tensor] = None  # int32 [2B]: perturbed layer per (view, latent)
+    sigma: Optional[torch.Tensor] = None     # fp32 [2B]: perturb_std of that layer
 
 
 def use_dedup(cfg: StepConfig, out_h, out_w) -> bool:
@@ -501,37 +574,24 @@ def prepare_step_inputs(gen, draws: StepDraws, cfg: StepConfig, device, stream=N
             t.record_stream(main)
         return inp
     out_h = out_w = gen.size
-    views, rows, nbytes, n_fill = {}, {}, 0, {}
-    z = _upload(draws.z, device)
-    nbytes += draws.z.numel() * 4
+    views, rows, nbytes = {}, {}, 0
+    b = draws.z.shape[0]
+    prs, lno, sig = [], [], []
     for name, view in (("s", draws.view_s), ("t", draws.view_t)):
-        pr = []
         for i, l in enumerate(view.layer_no):
-            pr += [view.pert_z[i, 2 * l], view.pert_z[i, 2 * l + 1]]
-        pr = torch.stack(pr)
-        views[name] = (list(view.layer_no), _upload(pr, device))
-        rs, ri, n_fill[name] = build_row_indices(out_h, out_w, view, draws.perms, cfg.patch_size, device, True)
+            prs += [view.pert_z[i, 2 * l], view.pert_z[i, 2 * l + 1]]
+            lno.append(int(l))
+            sig.append(float(cfg.perturb_std[l]))
+    zcat = _upload(torch.cat([draws.z.float(), torch.stack(prs).float()]), device)       # one copy: [5B, D]
+    layer_no = _upload(torch.tensor(lno, dtype=torch.int32), device)
+    sigma = _upload(torch.tensor(sig, dtype=torch.float32), device)
+    nbytes += zcat.numel() * 4 + 8 * len(lno)
+    for vi, (name, view) in enumerate((("s", draws.view_s), ("t", draws.view_t))):
+        views[name] = (list(view.layer_no), zcat[b + 2 * b * vi: b + 2 * b * (vi + 1)])
+        rs, ri = build_row_indices(out_h, out_w, view, draws.perms, cfg.patch_size, device)
         rows[name] = (rs, ri)
-        nbytes += pr.numel() * 4 + rs.numel() * 4 + ri.numel() * 4
-    dedup = None
-    if use_dedup(cfg, out_h, out_w):
-        dedup = {}
-        hw = out_h * out_w
-        for name in ("s", "t"):
-            rs, ri = rows[name]
-            ridx = torch.where(rs >= 0, ri.unsqueeze(0) * hw + rs, torch.full_like(rs, -1))      # [P, B*N]
-            keys = ridx.flatten().long()
-            order = torch.argsort(keys)
-            n_invalid = n_fill[name]          # counted on the host: no device synchronisation here
-            # samples per pixel without host synchronisation (boolean indexing / bincount would sync):
-            # rotation-fill samples go to an extra bin that is dropped
-            npix = draws.z.shape[0] * hw
-            counts = torch.zeros(npix + 1, dtype=torch.int32, device=device)
-            counts.index_add_(0, torch.where(keys >= 0, keys, torch.full_like(keys, npix)),
-                              torch.ones(keys.numel(), dtype=torch.int32, device=device))
-            seg_off = torch.zeros(npix + 1, dtype=torch.int32, device=device)
-            seg_off[1:] = torch.cumsum(counts[:npix], 0).to(torch.int32)
-            dedup[name] = (ridx.contiguous(), order[n_invalid:].to(torch.int32).contiguous(), seg_off)
+        nbytes += rs.numel() * 4 + ri.numel() * 4
+    dedup = {} if use_dedup(cfg, out_h, out_w) else None
     index_maps = None
     if cfg.source_pdf == 'image':
         if draws.z.shape[0] != 1:
@@ -541,13 +601,22 @@ def prepare_step_inputs(gen, draws: StepDraws, cfg: StepConfig, device, stream=N
             m = rotate_flip_index_map(out_h, out_w, view.angle[0], view.flip[0]).to(torch.int32)
             index_maps[name] = _upload(m, device)
             nbytes += m.numel() * 4
-    return StepInputs(z=z, views=views, rows=rows, h2d_bytes=nbytes, index_maps=index_maps, dedup=dedup)
+    return StepInputs(z=zcat[:b], views=views, rows=rows, h2d_bytes=nbytes, index_maps=index_maps, dedup=dedup,
+                      zcat=zcat, layer_no=layer_no, sigma=sigma)
+
+
+def build_pixel_segments(inp: StepInputs, batch, hw):
+    """Device bookkeeping of the all-pixel path (part of the step): for each view the row of Z every sample reads
+    and the CSR list of the samples of every pixel (`gx_pixel_segments`: counting sort, deterministic order)."""
+    if inp.dedup is None or inp.dedup:
+        return
+    for name in ("s", "t"):
+        rs, ri = inp.rows[name]
+        inp.dedup[name] = L.pixel_segments(rs, ri, hw, batch * hw)
 
 
 def _tensors_of(inp: StepInputs):
-    out = [inp.z]
-    for _, pr in inp.views.values():
-        out.append(pr)
+    out = [inp.zcat, inp.layer_no, inp.sigma]
     for rs, ri in inp.rows.values():
         out += [rs, ri]
     for d in (inp.index_maps, ):
@@ -594,14 +663,11 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
     head.refresh_planes()
     head.zero_grad()
     ws = ws or L.SinkhornWorkspace(head.k, dev)
-
     # one pass of the mapping network over the latents and both views' perturbation draws
-    pert_s, pert_t = inp.views["s"][1], inp.views["t"][1]
-    styled = gen.style(torch.cat([inp.z.float(), pert_s.float(), pert_t.float()]).contiguous())
-    w = styled[:b].contiguous()
-    noise_ws = {"s": styled[b:b + pert_s.shape[0]], "t": styled[b + pert_s.shape[0]:]}
+    styled = gen.style(inp.zcat)
     feats = {}
     out_h = out_w = gen.size
+    build_pixel_segments(inp, b, out_h * out_w)
     dedup = inp.dedup is not None
     allpix = {}
     if cfg.hlen % 8:
@@ -609,8 +675,8 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
     n_patch_rows = b * (cfg.patch_size if cfg.patch_size is not None else out_h * out_w)
     # both views go through the synthesis network as ONE batch of 2b images (they differ only in W+):
     # half the launches, and the latency-bound 4x4 ... 16x16 layers do twice the work per launch
-    wplus = torch.cat([view_wplus_device(gen, w, mean_latent, cfg.truncation, inp.views[name][0], inp.views[name][1],
-                                         cfg.perturb_std, noise_ws[name]) for name in ("s", "t")])
+    wplus = L.view_wplus(styled[:b], styled[b:], inp.layer_no, inp.sigma, mean_latent.reshape(-1).float().contiguous(),
+                         cfg.truncation, gen.n_latent)
     _, f_both = gen.synthesize(wplus, None, need_image=cfg.need_image)
     for vi, name in enumerate(("s", "t")):
         f = [t[vi * b:(vi + 1) * b] for t in f_both]
@@ -625,7 +691,10 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
     n_local = b * (cfg.patch_size if cfg.patch_size is not None else out_h * out_w)
     n_total = n_local * world
     grad_scale = 1.0 / (n_total * cfg.num_patches)
-    loss_acc = torch.zeros((), dtype=torch.float32, device=dev)
+    maxp = L.load().gx_loss_max_parts()
+    loss_parts = torch.zeros((cfg.num_patches, maxp), dtype=torch.float32, device=dev)
+    if group is not None and group.ll is None and os.environ.get("GX_SINKHORN_EXCHANGE", "ll") != "nccl":
+        group.ensure_ll(head.k, dev)           # NVLink exchange of the marginals (GX_SINKHORN_EXCHANGE=nccl: A/B)
     for p in range(cfg.num_patches):
         fw = {}
         for name in ("s", "t"):
@@ -639,31 +708,35 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
         if cfg.source_pdf == 'image':
             rc_s = image_marginals(feats["s"], out_h, out_w, cfg.hlen, inp.index_maps["s"], head.k, n_local)
             rc_t = image_marginals(feats["t"], out_h, out_w, cfg.hlen, inp.index_maps["t"], head.k, n_local)
-        la_s = sinkhorn_log_a(fw["s"]["s"], cfg.niters, cfg.eps, ws, n_total, group, rc_s[0], rc_s[1],
-                              u_first=fw["s"]["u0"])
-        la_t = sinkhorn_log_a(fw["t"]["s"], cfg.niters, cfg.eps, ws, n_total, group, rc_t[0], rc_t[1],
-                              u_first=fw["t"]["u0"])
+        la_s, la_t = sinkhorn_multi([dict(s=fw["s"]["s"], r=rc_s[0], c=rc_s[1], u_first=fw["s"]["u0"]),
+                                     dict(s=fw["t"]["s"], r=rc_t[0], c=rc_t[1], u_first=fw["t"]["u0"])],
+                                    cfg.niters, cfg.eps, ws, n_total, group)
         lo = head.passes_bwd == 3
-        loss_parts, ds_s, ds_t, db, _ = L.swav_loss(fw["s"]["s"], fw["t"]["s"], 1.0 / cfg.eps, 1.0 / cfg.temperature,
-                                                    la_s, la_t, grad_scale, want_lo=lo)
-        loss_acc += loss_parts.sum()
-        head.g_bias += db
+        _, ds_s, ds_t, _, _ = L.swav_loss(fw["s"]["s"], fw["t"]["s"], 1.0 / cfg.eps, 1.0 / cfg.temperature,
+                                          la_s, la_t, grad_scale, want_lo=lo, loss_parts=loss_parts[p],
+                                          db_accum=head.g_bias)
         fw["s"].pop("s"), fw["t"].pop("s")
         for name, ds in (("s", ds_s), ("t", ds_t)):
             out = allpix[name]["dz_rows"][p * n_local:(p + 1) * n_local] if dedup else None
             scores_backward(head, fw[name], ds[0], ds[1], out)
+    # loss = sum of the per-CTA partial sums of every patch / (N_global * P), into the tail of the flat gradient
+    L.colsum(loss_parts, cfg.num_patches * maxp, 1, head.loss_slot, scale=grad_scale)
+    pending = None
+    if group is not None:
+        # prototype gradients + loss travel while the projection-weight gradient is still being folded
+        pending = torch.distributed.all_reduce(head.g_flat, group=group.pg, async_op=True)
     if dedup:
         for name in ("s", "t"):
             ap = allpix[name]
             project_backward_dedup(head, ap["dz_rows"], inp.dedup[name][1], inp.dedup[name][2], ap["levels"], b,
                                    out_h, out_w, bilinear=cfg.hf_interp == 'bilinear')
-    loss = loss_acc / (n_total * cfg.num_patches)
     if group is not None:
-        for g in (head.g_proj, head.g_proto, head.g_bias):
-            torch.distributed.all_reduce(g, group=group.pg)
-        torch.distributed.all_reduce(loss, group=group.pg)
+        torch.distributed.all_reduce(head.g_proj, group=group.pg)
+        pending.wait()
+    loss = head.loss_ring[head.steps % head.loss_ring.numel():][:1]
+    L.colsum(head.loss_slot, 1, 1, loss)           # keep the step's loss while the next step re-uses the buffer
     head.optimizer_step()
-    return loss
+    return loss.view(())
 
 
 @torch.no_grad()

@@ -107,7 +107,9 @@ class EqualLinear(nn.Module):
 
     def forward(self, input):
         shp = input.shape
-        x = input.reshape(-1, shp[-1]).contiguous().float()
+        x = input.reshape(-1, shp[-1])
+        if x.dtype != torch.float32 or x.stride(1) != 1:      # strided rows (a W+ row) are read in place
+            x = x.contiguous().float()
         y = L.equal_linear(x, self.weight.detach(), None if self.bias is None else self.bias.detach(), self.scale,
                            self.lr_mul, 1 if self.activation else 0)
         return y.view(*shp[:-1], y.shape[-1])
@@ -331,7 +333,7 @@ class Generator(nn.Module):
         # modulation styles + demodulation coefficients for every conv (small SIMT kernels)
         styles, demods, preps = [], [], []
         for layer, li in zip(layers, lat_idx):
-            s = layer.conv.modulation(latent[:, li].contiguous())
+            s = layer.conv.modulation(latent[:, li])
             w_hi, w_lo, wsq = layer.conv.prepared()
             styles.append(s)
             demods.append(L.modconv_demod(wsq, s))
@@ -365,7 +367,7 @@ class Generator(nn.Module):
             feats.append(f)
             if need_image and n % 2 == 0:
                 rgb = self.to_rgb1 if n == 0 else self.to_rgbs[n // 2 - 1]
-                s_rgb = rgb.conv.modulation(latent[:, n + 1].contiguous())
+                s_rgb = rgb.conv.modulation(latent[:, n + 1])
                 skip_up = None
                 if image is not None:
                     skip_up = rgb.upsample(image).contiguous()

@@ -23,7 +23,9 @@ extern "C" {
 #define GX_ERR_CUDA (-2)        /* CUDA runtime/driver error: gx_last_cuda_error */
 #define GX_ERR_UNSUPPORTED (-3) /* device is not sm_100                           */
 
-int gx_version(void);
+#define GX_ABI_VERSION 200
+int gx_version(void);              /* == GX_ABI_VERSION of the header the library was built from */
+int gx_abi_sizeof(int which);      /* sizeof of gx_conv_desc (0), gx_gemm_desc (1), gx_gather_desc (2), gx_ll_desc (3); -1 otherwise */
 int gx_last_cuda_error(void);             /* cudaError_t of the last GX_ERR_CUDA  */
 const char* gx_error_string(int gx_code); /* static string                        */
 int gx_device_ok(void);                   /* 1 if the current device is sm_100    */
@@ -58,9 +60,10 @@ int gx_fused_bias_act(const float* input, const float* bias, const float* refer,
 int gx_pixel_norm(const float* x, float* y, int n, int dim, void* stream);
 
 /* EqualLinear, ref: model.py:223-252.  y[n,o] = act(sum_i x[n,i]*w[o,i]*w_scale + b[o]*b_scale);
- * act: 0 none, 1 fused leaky relu (0.2, *sqrt2).  b may be NULL. */
-int gx_equal_linear(const float* x, const float* w, const float* b, float* y, int n, int in_dim, int out_dim,
-                    float w_scale, float b_scale, int act, void* stream);
+ * act: 0 none, 1 fused leaky relu (0.2, *sqrt2).  b may be NULL.  ldx: row pitch of x in floats (>= in_dim;
+ * a row of W+ [B, n_latent, D] is addressed in place with ldx = n_latent*D). */
+int gx_equal_linear(const float* x, long long ldx, const float* w, const float* b, float* y, int n, int in_dim,
+                    int out_dim, float w_scale, float b_scale, int act, void* stream);
 
 /* out[i,:] = mean + psi*(w[i,:]-mean): the truncation trick, ref: model.py:594-602. */
 int gx_truncate(const float* w, const float* mean, float* out, long long rows, int dim, float psi, void* stream);
@@ -274,6 +277,28 @@ int gx_pool_sum(const float* in, int batch, int in_h, int in_w, int out_h, int o
  * ref: swav_clustering.py:328-331. w [k,c]. */
 int gx_normalize_rows(float* w, long long rows, int cols, void* stream);
 
+/* W+ latents of BOTH perturbed views in one launch (ref: swav_clustering.py:593-640 with
+ * lib/oneshot/image_augmentor.py:42-53,75-79): out[row, r, :] for row < rows (= 2*b: view s then view t),
+ * r < n_latent: v = trunc(w[row % b]); rows 2l, 2l+1 (l = layer_no[row]) are blended with the mapped
+ * perturbation draws, v = (1 - sigma[row]) v + sigma[row] noise_w[2 row + (r - 2l)]; then the second
+ * truncation (trunc(x) = mean + psi (x - mean), skipped for psi >= 1). */
+int gx_view_wplus(const float* w, const float* noise_w, const int* layer_no, const float* sigma, const float* mean,
+                  float psi, int b, int rows, int n_latent, int dim, float* out, void* stream);
+
+/* Sampled-pixel bookkeeping of one view (ref: swav_clustering.py:158-167 on the rotated / flipped tensor,
+ * :358-359): row_src [patches, bn] = source pixel of every sample inside its image (-1: rotation fill),
+ * row_img [bn] = image of the sample.  Outputs: ridx [patches, bn] = row of Z (image*hw + pixel, or -1),
+ * and the CSR list of the samples of every pixel: seg_off [npix + 1], order [patches*bn] (first seg_off[npix]
+ * entries valid; ascending sample index inside a segment - deterministic).  counts [npix] and tile_scratch
+ * [gx_pixel_segments_scratch(npix)] are int scratch. */
+int gx_pixel_segments_scratch(long long npix);
+int gx_pixel_segments(const int* row_src, const int* row_img, int patches, long long bn, int hw, long long npix,
+                      int* ridx, int* counts, int* tile_scratch, int* seg_off, int* order, void* stream);
+
+/* out[k] = (accumulate ? out[k] : 0) + scale * sum_p parts[p,k]  (deterministic order): loss and bias-gradient
+ * reductions of the per-CTA partials of gx_swav_loss. */
+int gx_colsum(const float* parts, int nparts, int k, float scale, int accumulate, float* out, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * Sinkhorn-Knopp (ref: hfc_with_swav/swav_clustering.py:509-544)
  *
@@ -283,18 +308,51 @@ int gx_normalize_rows(float* w, long long rows, int cols, void* stream);
  * normalisation removes b, so the result is q[n,:] = softmax_k(S[n,k]/eps + log a_k).
  * ---------------------------------------------------------------------------------- */
 
-/* One pass.  first != 0: u'_k = sum_n e_nk (a and b are 1).  Otherwise a_k = r_k/u_in[k]
- * (r == NULL: 1/K) and c == NULL: c_n = 1/n_total.  Writes per-CTA partials
- * [nparts,K]; returns the number of partials through *nparts_out (host int).
- * partials must hold at least gx_sinkhorn_max_parts()*K floats. */
+/* Low-latency exchange of the K-vector of column marginals between the GPUs of one box - the only exchange
+ * step of the distributed Sinkhorn (ref: swav_clustering.py:519-544 with SwAV's all-reduce of the marginals).
+ * Every rank owns one exchange buffer of 8-byte words {fp32 value, u32 sequence number}; all buffers are
+ * mapped into every process (gx_peer_*: CUDA IPC).  A block of the buffer is [world][K] words: the sender of
+ * rank r stores its K values, tagged with `seq`, into slot r of the block in EVERY rank's buffer (plain 8-byte
+ * stores over NVLink, single-copy atomic, no fence); a consumer spins on the tags of its OWN buffer and adds the
+ * `world` slots in rank order, so every rank gets the bit-identical sum.  Blocks alternate (parity of the
+ * sequence number) so that a fast rank cannot overwrite a slot a slow rank is still reading.
+ * world == 0 means "no exchange" wherever a gx_ll_desc is accepted. */
+#define GX_MAX_PEERS 16
+typedef struct gx_ll_desc {
+  void* peers[GX_MAX_PEERS]; /* base of rank r's exchange buffer as mapped in THIS process (own buffer at [rank]) */
+  int world, rank;
+  long long block_words;     /* offset of the block, in 8-byte words, from the buffer base */
+  unsigned int seq;          /* tag of this exchange (non-zero, increases by one per exchange of a channel) */
+  int* err;                  /* device int: set to 1 if a consumer gave up waiting (~10 s); may be NULL */
+} gx_ll_desc;
+
+/* exchange buffers: cudaMalloc'ed + zeroed / exported as a 64-byte CUDA IPC handle / mapped from a peer's handle */
+int gx_peer_alloc(long long bytes, void** ptr);
+int gx_peer_free(void* ptr);
+int gx_peer_export(void* ptr, void* handle64);
+int gx_peer_open(const void* handle64, void** ptr);
+int gx_peer_close(void* ptr);
+
+/* One pass.  first != 0: u'_k = sum_n e_nk (a and b are 1).  Otherwise a_k = r_k/u_k with u = u_in, or - when
+ * u_ll (may be NULL) has world > 0 - the sum over ranks of the tagged slots of u_ll's block, received in the
+ * kernel prologue while the first rows are already in flight.  r == NULL: 1/K; c == NULL: c_n = 1/n_total.
+ * reverse != 0 streams the rows last-to-first (alternating the direction from pass to pass turns the tail of S
+ * the 126 MB L2 still holds into hits).  Writes per-CTA partials [nparts,K]; returns the number of partials
+ * through *nparts_out (host int).  partials must hold at least gx_sinkhorn_max_parts()*K floats. */
 int gx_sinkhorn_max_parts(void);
 int gx_sinkhorn_pass(const float* s, long long n, int k, long long lds, float inv_eps, int first, const float* u_in,
-                     const float* r, const float* c, long long n_total, float* partials, int* nparts_out,
-                     void* stream);
+                     const gx_ll_desc* u_ll, const float* r, const float* c, long long n_total, int reverse,
+                     float* partials, int* nparts_out, void* stream);
 /* u[k] = sum_p partials[p,k] (deterministic order). */
 int gx_sinkhorn_reduce(const float* partials, int nparts, int k, float* u, void* stream);
-/* log_a[k] = log(r_k / u[k]). */
-int gx_sinkhorn_log_a(const float* u, const float* r, int k, float* log_a, void* stream);
+/* The same column sums, pushed as tagged words into slot `rank` of ll's block on every rank (fused reduce +
+ * exchange over NVLink peer memory; replaces reduce + NCCL all-reduce).  u_local (optional): the local sums. */
+int gx_sinkhorn_reduce_send(const float* partials, int nparts, int k, const gx_ll_desc* ll, float* u_local,
+                            void* stream);
+/* u[k] = sum over ranks of ll's block (waits for the tags). */
+int gx_ll_recv_sum(const gx_ll_desc* ll, int k, float* u, void* stream);
+/* log_a[k] = log(r_k / u[k]); u from u (u_ll NULL / world 0) or received from u_ll's block. */
+int gx_sinkhorn_log_a(const float* u, const gx_ll_desc* u_ll, const float* r, int k, float* log_a, void* stream);
 /* Materialise Q [N,K] = softmax_k(S/eps + log_a) (API parity with sinkhorn_knopp's return). */
 int gx_sinkhorn_q(const float* s, long long n, int k, long long lds, float inv_eps, const float* log_a, float* q,
                   void* stream);

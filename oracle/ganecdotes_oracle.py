@@ -173,7 +173,7 @@ def upfirdn2d(x: torch.Tensor, kernel: torch.Tensor, up=1, down=1, pad=(0, 0)) -
     y[:, :, ::uy, ::ux] = x.reshape(n * c, 1, h, w)
     y = F.pad(y, [max(px0, 0), max(px1, 0), max(py0, 0), max(py1, 0)])
     y = y[:, :, max(-py0, 0): y.shape[2] - max(-py1, 0), max(-px0, 0): y.shape[3] - max(-px1, 0)]
-    y = F.conv2d(y, torch.flip(kernel, [0, 1]).to(x.dtype).view(1, 1, kh, kw))
+    y = F.conv2d(y, torch.flip(kernel, [0, 1]).to(device=x.device, dtype=x.dtype).view(1, 1, kh, kw))
     y = y[:, :, ::dy, ::dx]
     out_h = (h * uy + py0 + py1 - kh + dy) // dy
     out_w = (w * ux + px0 + px1 - kw + dx) // dx
@@ -435,8 +435,8 @@ def sinkhorn_knopp(scores, niters: int, eps: float, r=None, c=None):
     q = torch.exp(scores / eps).t()
     q = q / torch.sum(q)
     k, n = q.shape
-    r = torch.ones(k, dtype=q.dtype) / k if r is None else r
-    c = torch.ones(n, dtype=q.dtype) / n if c is None else c
+    r = torch.ones(k, dtype=q.dtype, device=q.device) / k if r is None else r
+    c = torch.ones(n, dtype=q.dtype, device=q.device) / n if c is None else c
     for _ in range(niters):
         u = torch.sum(q, dim=1)
         q = q * (r / u).unsqueeze(1)

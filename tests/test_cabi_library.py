@@ -26,7 +26,11 @@ def test_library_exports_every_declared_symbol():
         assert hasattr(lib, n), f"{n} declared in the header but not exported"
     # and the ctypes binding covers exactly the declared surface
     assert sorted(_lib.EXPORTED_SYMBOLS) == names
-    assert lib.gx_version() == 100
+    assert lib.gx_version() == _lib.GX_ABI_VERSION
+    header = open(os.path.join(ROOT, "include", "ganecdotes_b200.h")).read()
+    assert f"#define GX_ABI_VERSION {_lib.GX_ABI_VERSION}" in header
+    for which, st in enumerate((_lib.gx_conv_desc, _lib.gx_gemm_desc, _lib.gx_gather_desc, _lib.gx_ll_desc)):
+        assert lib.gx_abi_sizeof(which) == ctypes.sizeof(st)      # the handshake load() performs
     lib.gx_error_string.restype = ctypes.c_char_p
     assert b"argument" in lib.gx_error_string(-1)
 
@@ -36,7 +40,7 @@ def test_argument_validation_without_gpu():
     from ganecdotes_b200 import _lib
     lib = _lib.load(require_device=False)
     assert lib.gx_upfirdn2d(None, None, None, 1, 4, 4, 1, 4, 4, 1, 1, 1, 1, 0, 0, 0, 0, None) == -1
-    assert lib.gx_sinkhorn_pass(None, 10, 7, 7, 1.0, 1, None, None, None, 10, None, None, None) == -1
+    assert lib.gx_sinkhorn_pass(None, 10, 7, 7, 1.0, 1, None, None, None, None, 10, 0, None, None, None) == -1
     d = _lib.gx_gemm_desc()
     assert lib.gx_gemm(ctypes.byref(d), None) == -1
 

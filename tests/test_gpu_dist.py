@@ -18,4 +18,4 @@ def test_sharded_step_matches_single_process():
            "127.0.0.1", "--master-port", "29533", os.path.join(ROOT, "tools", "dist_check.py")]
     out = subprocess.run(cmd, capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-2000:]
-    assert "DIST_CHECK" in out.stdout and "OK" in out.stdout
+    assert "DIST_CHECK OK" in out.stdout, out.stdout[-2000:]

@@ -747,3 +747,168 @@ def test_bilinear_upsample_sum_and_its_adjoint(L):
         torch.nn.functional.interpolate(pr.permute(0, 3, 1, 2), size=(32, 32), mode="bilinear",
                                         align_corners=False).backward(x.permute(0, 3, 1, 2))
         torch.testing.assert_close(adj, pr.grad, rtol=1e-4, atol=1e-5)
+
+
+# ----------------------------------------------------------------------------------------
+# round 2: exchange over peer memory, index bookkeeping, fused W+ construction
+# ----------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("world,n,k", [(2, 600, 48), (3, 999, 5000), (4, 64, 4000)])
+def test_sinkhorn_ll_exchange_simulated_ranks(L, world, n, k):
+    """Distributed Sinkhorn through the tagged-word exchange (gx_sinkhorn_reduce_send + the receiving prologue
+    of gx_sinkhorn_pass / gx_sinkhorn_log_a) with `world` endpoints simulated in one process: the rows of S are
+    split into `world` shards, every shard's pass pushes its marginals into all buffers, the next pass of every
+    shard receives the sum.  Result == the oracle's Sinkhorn on the whole matrix, and == the single-rank kernel
+    path bit for bit in log a up to the summation order of the shards."""
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    torch.manual_seed(world * 1000 + n + k)
+    s = (0.05 * torch.randn(n, k)).cuda()
+    bounds = [n * r // world for r in range(world + 1)]
+    shards = [s[bounds[r]:bounds[r + 1]].contiguous() for r in range(world)]
+    ends = L.LLExchange.simulated(world, k, "cuda")
+    ws = L.SinkhornWorkspace(k, "cuda")
+    inv_eps, niters = 1 / 0.005, 10
+    try:
+        for it in range(niters):
+            for ch in (0, 1):                                   # two independent chains on two channels
+                descs = []
+                for r, e in enumerate(ends):                    # every endpoint sends ...
+                    u_ll = e.last(ch) if it > 0 else None       # ... after receiving the previous exchange
+                    nparts = L.sinkhorn_pass_parts(shards[r], inv_eps, it == 0, None, None, None, n, ws, u_ll=u_ll,
+                                                   reverse=(it & 1) == 1)
+                    descs.append(e.next_send(ch))
+                    # NB: a receive only completes once ALL sends of its exchange are on the stream: sends of
+                    # exchange `it` are issued below, receives of exchange `it` at iteration it + 1
+                    L.sinkhorn_reduce_send(ws.partials, nparts, k, descs[-1])
+        las = [[L.sinkhorn_log_a(None, None, u_ll=e.last(ch), k=k, device="cuda") for e in ends] for ch in (0, 1)]
+        torch.cuda.synchronize()
+        for e in ends:
+            e.check()
+        for ch in (0, 1):
+            for r in range(1, world):                           # every rank computes the bit-identical sum
+                assert torch.equal(las[ch][0], las[ch][r])
+        assert torch.equal(las[0][0], las[1][0])
+        la_one = E.sinkhorn_log_a(s, niters, 0.005, ws, n)
+        torch.testing.assert_close(las[0][0], la_one, rtol=0, atol=2e-4)
+        q = L.sinkhorn_q(s, inv_eps, las[0][0])
+        ref = O.sinkhorn_knopp(s.cpu().double(), niters, 0.005).float()
+        torch.testing.assert_close(q.cpu(), ref, rtol=2e-3, atol=1e-9)
+        u = L.ll_recv_sum(ends[0].last(0), k, "cuda")           # stand-alone receive kernel == the fused prologue
+        assert torch.isfinite(u).all() and (u > 0).all()
+    finally:
+        ends[0].close()
+
+
+def test_sinkhorn_reverse_pass_is_the_same_sum(L):
+    """serpentine passes: streaming the rows last-to-first changes only the summation order"""
+    torch.manual_seed(5)
+    n, k = 1237, 5000
+    s = (0.05 * torch.randn(n, k)).cuda()
+    ws = L.SinkhornWorkspace(k, "cuda")
+    u0 = L.sinkhorn_pass(s, 200.0, True, None, None, None, n, ws).clone()
+    uf = L.sinkhorn_pass(s, 200.0, False, u0, None, None, n, ws, reverse=False).clone()
+    ur = L.sinkhorn_pass(s, 200.0, False, u0, None, None, n, ws, reverse=True).clone()
+    torch.testing.assert_close(uf, ur, rtol=2e-5, atol=0)
+    ur0 = L.sinkhorn_pass(s, 200.0, True, None, None, None, n, ws, reverse=True)
+    torch.testing.assert_close(ur0, u0, rtol=2e-5, atol=0)
+
+
+@pytest.mark.parametrize("b,hw,patches,n", [(1, 256, 2, 100), (3, 4096, 5, 3000), (8, 65536, 5, 20000)])
+def test_pixel_segments_vs_torch(L, b, hw, patches, n):
+    """gx_pixel_segments (counting sort) against a stable torch argsort: ridx, CSR offsets, and the sample order
+    inside every segment (ascending sample index)."""
+    g = torch.Generator().manual_seed(b + hw)
+    row_src = torch.stack([torch.cat([torch.randperm(hw, generator=g)[:n] for _ in range(b)]) for _ in range(patches)])
+    fill = torch.rand(row_src.shape, generator=g) < 0.07
+    row_src[fill] = -1                                                           # rotation fill
+    row_img = torch.arange(b).repeat_interleave(n)
+    ridx, order, seg_off = L.pixel_segments(row_src.int().cuda(), row_img.int().cuda(), hw, b * hw)
+    ref = torch.where(row_src >= 0, row_img.unsqueeze(0) * hw + row_src, torch.full_like(row_src, -1))
+    assert torch.equal(ridx.cpu().long(), ref)
+    keys = ref.flatten()
+    valid = (keys >= 0).nonzero().flatten()
+    ref_order = valid[torch.argsort(keys[valid], stable=True)]
+    counts = torch.bincount(keys[valid], minlength=b * hw)
+    ref_off = torch.cat([torch.zeros(1, dtype=torch.long), counts.cumsum(0)])
+    assert torch.equal(seg_off.cpu().long(), ref_off)
+    assert torch.equal(order.cpu().long()[:valid.numel()], ref_order)
+
+
+def test_view_wplus_kernel_matches_host_construction(L):
+    """gx_view_wplus (both views, one launch) == engine.view_wplus (reference op order, ref swav_clustering.py:593-640)"""
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    from ganecdotes_b200.stylegan2.model import Generator
+    sd = O.init_generator_state(16, 64, 2, 7)
+    gen = Generator(16, 64, 2)
+    gen.load_state_dict(sd, strict=True)
+    gen = gen.cuda()
+    torch.manual_seed(4)
+    b, nl, pstd = 3, 3, [1.0, 0.5, 0.25]
+    mean = torch.randn(1, 64).cuda()
+    z = torch.randn(b, 64)
+    views = [E.ViewDraws(layer_no=[int(v) for v in torch.randint(0, nl, (b,))], pert_z=torch.randn(b, 2 * nl, 64),
+                         angle=[0.0] * b, flip=[False] * b) for _ in range(2)]
+    w = gen.style(z.cuda())
+    for psi in (0.7, 1.0):
+        ref = torch.cat([E.view_wplus(gen, w, mean, psi, v, pstd) for v in views])
+        rows, lno, sig = [], [], []
+        for v in views:
+            for i, l in enumerate(v.layer_no):
+                rows += [v.pert_z[i, 2 * l], v.pert_z[i, 2 * l + 1]]
+                lno.append(l)
+                sig.append(pstd[l])
+        noise_w = gen.style(torch.stack(rows).cuda())
+        got = L.view_wplus(w, noise_w, torch.tensor(lno, dtype=torch.int32).cuda(), torch.tensor(sig).cuda(),
+                           mean.reshape(-1), psi, gen.n_latent)
+        torch.testing.assert_close(got, ref, rtol=1e-6, atol=1e-6)
+
+
+def test_colsum_scale_accumulate(L):
+    torch.manual_seed(0)
+    parts = torch.randn(37, 101).cuda()
+    out = torch.full((101,), 2.0).cuda()
+    L.colsum(parts, 37, 101, out, scale=0.5, accumulate=True)
+    torch.testing.assert_close(out.cpu(), 2.0 + 0.5 * parts.cpu().double().sum(0).float(), rtol=1e-5, atol=1e-6)
+    L.colsum(parts, 37, 101, out, scale=1.0, accumulate=False)
+    torch.testing.assert_close(out.cpu(), parts.cpu().double().sum(0).float(), rtol=1e-5, atol=1e-6)
+    one = torch.zeros(1).cuda()
+    L.colsum(parts.view(-1, 1), parts.numel(), 1, one, scale=2.0)
+    assert abs(one.item() - 2.0 * parts.double().sum().item()) < 1e-3
+
+
+def test_native_ops_match_the_reference_cuda_kernels(L):
+    """gx_upfirdn2d / gx_fused_bias_act against the reference's OWN CUDA kernels (lib/gan/optim/upfirdn2d_kernel.cu,
+    fused_bias_act_kernel.cu), compiled unmodified for sm_100a into oracle/_ref/ by oracle/build_ref.py: every
+    (up, down, pad) family the reference's kernel table covers, and all six act/grad modes of fused_bias_act."""
+    from oracle import build_ref
+    up, fb = build_ref.load("ref_upfirdn2d"), build_ref.load("ref_fused_bias_act")
+    if up is None or fb is None:
+        pytest.skip("oracle/_ref not built (python oracle/build_ref.py in the build container)")
+    g = torch.Generator().manual_seed(0)
+    k4 = torch.tensor([1., 3., 3., 1.])
+    k4 = (k4[None, :] * k4[:, None]) / 64
+    k3 = torch.randn(3, 3, generator=g)
+    k6 = torch.randn(6, 6, generator=g)
+    cases = [((3, 17, 19, 5), k4, (1, 1), (1, 1), (2, 1, 2, 1)),       # blur
+             ((2, 16, 16, 8), k4 * 4, (2, 2), (1, 1), (2, 1, 2, 1)),   # upsample
+             ((2, 16, 16, 3), k4, (1, 1), (2, 2), (1, 1, 1, 1)),       # downsample
+             ((1, 9, 11, 2), k3, (1, 1), (1, 1), (1, 1, 1, 1)),
+             ((2, 13, 7, 4), k6, (2, 2), (1, 1), (3, 2, 3, 2)),
+             ((1, 8, 8, 1), k3, (2, 1), (1, 2), (2, 0, -1, 3))]        # generic path, a negative pad crops
+    for shape, k, (ux, uy), (dx, dy), (px0, px1, py0, py1) in cases:
+        x = torch.randn(*shape, generator=g).cuda()
+        kc = k.contiguous().cuda()
+        ref = up.upfirdn2d(x, kc, ux, uy, dx, dy, px0, px1, py0, py1)
+        got = L.upfirdn2d_raw(x, kc, ux, uy, dx, dy, px0, px1, py0, py1)
+        assert got.shape == ref.shape
+        torch.testing.assert_close(got, ref, rtol=1e-5, atol=1e-6)
+    x = torch.randn(4, 6, 9, 9, generator=g).cuda()
+    b = torch.randn(6, generator=g).cuda()
+    refer = torch.randn(4, 6, 9, 9, generator=g).cuda()
+    empty = torch.empty(0, device="cuda")
+    for act in (1, 3):
+        for grad in (0, 1, 2):
+            r_in = refer if grad > 0 else empty
+            ref = fb.fused_bias_act(x, b if grad == 0 else empty, r_in, act, grad, 0.2, 1.4142135)
+            got = L.fused_bias_act_raw(x, b if grad == 0 else None, refer if grad > 0 else None, act, grad, 0.2, 1.4142135)
+            torch.testing.assert_close(got, ref, rtol=1e-6, atol=1e-7)
