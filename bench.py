@@ -750,7 +750,7 @@ def cpu_kmeans(steps, warmup):
 def run_kmeans(args):
     import torch.distributed as dist
     from ganecdotes_b200 import _lib as L
-    from ganecdotes_b200.hfc_kmeans import FlatKMeansAssign
+    from ganecdotes_b200.hfc_kmeans.hfc_kmeans_clustering import FlatKMeansAssign
     from ganecdotes_b200.stylegan2.model import Generator
     world, rank, local_rank = dist_env()
     torch.cuda.set_device(local_rank)

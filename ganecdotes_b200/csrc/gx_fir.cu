@@ -54,6 +54,97 @@ __global__ void upfirdn2d_kernel(const float* __restrict__ in, const float* __re
 }
 
 // --------------------------------------------------------------------------
+// Planar fast path (minor == 1: the NCHW tensors the Python-level upfirdn2d / Blur / Upsample / Downsample of
+// the reference feed the op, ref upfirdn2d.py:146-162): filters up to 4x4, up/down in {1, 2} with up*down <= 2.
+// A CTA owns a 32 x 64 output tile of one plane: the input rows it needs are staged once in shared memory with
+// row-contiguous (coalesced) loads, zero-filled outside the image, and every thread produces 8 consecutive rows of
+// one output column from the tile, so the taps of neighbouring rows are common sub-expressions and the inner loop
+// has neither bounds checks nor index divisions.  (The per-element kernel above issues ~16 predicated scalar
+// global loads per output: 0.2 TB/s on the 256^2 blur against 1.7 TB/s for the reference's tiled kernel.)
+// --------------------------------------------------------------------------
+constexpr int UT_OW = 64, UT_OH = 32, UT_K = 4, UT_ROWS = 8;
+
+template <int UP, int DOWN>
+__global__ void __launch_bounds__(256)
+upfirdn2d_planar_kernel(const float* __restrict__ in, const float* __restrict__ kern, float* __restrict__ out,
+                        const UpfirParams p) {
+  constexpr int IN_H = ((UT_OH - 1) * DOWN + UT_K - 1) / UP + 2;
+  constexpr int IN_W = ((UT_OW - 1) * DOWN + UT_K - 1) / UP + 2;
+  constexpr int TAPS = (UT_K + UP - 1) / UP;            // taps per axis that land on real samples
+  __shared__ float tile[IN_H][IN_W + 1];
+  __shared__ float fk[UT_K + UP][UT_K + UP];            // flipped taps, zero beyond kh x kw
+  const int tid = threadIdx.x;
+  for (int i = tid; i < (UT_K + UP) * (UT_K + UP); i += 256) {
+    const int ky = i / (UT_K + UP), kx = i % (UT_K + UP);
+    fk[ky][kx] = (ky < p.kh && kx < p.kw) ? kern[(p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx)] : 0.f;
+  }
+  const int ox0 = blockIdx.x * UT_OW, oy0 = blockIdx.y * UT_OH;
+  const int uy0 = oy0 * DOWN - p.pad_y0, ux0 = ox0 * DOWN - p.pad_x0;   // zero-inserted coordinates of tap 0
+  const int iy0 = floor_div(uy0, UP), ix0 = floor_div(ux0, UP);
+  const int tx = tid % UT_OW, ty = tid / UT_OW;
+  const int ox = ox0 + tx;
+  const int ux = ux0 + tx * DOWN;
+  const int kx0 = ((-ux) % UP + UP) % UP;
+  const int lx0 = (ux + kx0) / UP - ix0;                // exact division: ux + kx0 is a multiple of UP
+  for (int mj = blockIdx.z; mj < p.major; mj += gridDim.z) {
+    const float* src = in + (long long)mj * p.in_h * p.in_w;
+    __syncthreads();
+    for (int i = tid; i < IN_H * IN_W; i += 256) {
+      const int r = i / IN_W, c = i - r * IN_W;
+      const int iy = iy0 + r, ix = ix0 + c;
+      tile[r][c] = (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) ? __ldg(src + (long long)iy * p.in_w + ix) : 0.f;
+    }
+    __syncthreads();
+    if (ox < p.out_w) {
+      float* dst = out + (long long)mj * p.out_h * p.out_w + ox;
+      if constexpr (UP == 1 && DOWN == 1) {
+        // sliding window: each of the 8 + 3 tile rows of this column is read once (4 LDS) and feeds the up to four
+        // output rows it overlaps - 5.5 instead of 16 shared-memory loads per output
+        float kr[UT_K][UT_K], acc[UT_ROWS];
+#pragma unroll
+        for (int a = 0; a < UT_K; ++a)
+#pragma unroll
+          for (int b = 0; b < UT_K; ++b) kr[a][b] = fk[a][b];
+#pragma unroll
+        for (int j = 0; j < UT_ROWS; ++j) acc[j] = 0.f;
+        const int ly = ty * UT_ROWS + (uy0 - iy0);            // uy0 - iy0 == 0 for UP == 1
+#pragma unroll
+        for (int r = 0; r < UT_ROWS + UT_K - 1; ++r) {
+          const float v0 = tile[ly + r][lx0], v1 = tile[ly + r][lx0 + 1], v2 = tile[ly + r][lx0 + 2],
+                      v3 = tile[ly + r][lx0 + 3];
+#pragma unroll
+          for (int j = 0; j < UT_ROWS; ++j) {
+            const int ky = r - j;
+            if (ky >= 0 && ky < UT_K)
+              acc[j] = fmaf(v0, kr[ky][0], fmaf(v1, kr[ky][1], fmaf(v2, kr[ky][2], fmaf(v3, kr[ky][3], acc[j]))));
+          }
+        }
+#pragma unroll
+        for (int j = 0; j < UT_ROWS; ++j) {
+          const int oy = oy0 + ty * UT_ROWS + j;
+          if (oy < p.out_h) dst[(long long)oy * p.out_w] = acc[j];
+        }
+      } else {
+#pragma unroll
+      for (int j = 0; j < UT_ROWS; ++j) {
+        const int oyl = ty * UT_ROWS + j;
+        const int uy = uy0 + oyl * DOWN;
+        const int ky0 = ((-uy) % UP + UP) % UP;
+        const int ly0 = (uy + ky0) / UP - iy0;
+        float acc = 0.f;
+#pragma unroll
+        for (int a = 0; a < TAPS; ++a)
+#pragma unroll
+          for (int b = 0; b < TAPS; ++b)
+            acc = fmaf(tile[ly0 + a][lx0 + b], fk[ky0 + a * UP][kx0 + b * UP], acc);
+        if (oy0 + oyl < p.out_h) dst[(long long)(oy0 + oyl) * p.out_w] = acc;
+      }
+      }
+    }
+  }
+}
+
+// --------------------------------------------------------------------------
 // fused_bias_act (ref: fused_bias_act_kernel.cu:18-85)
 // --------------------------------------------------------------------------
 __device__ __forceinline__ float bias_act_one(float x, float b, float ref, int mode, float alpha, float scale) {
@@ -343,10 +434,20 @@ extern "C" int gx_upfirdn2d(const float* input, const float* kernel, float* out,
   GX_CHECK_ARG(p.out_h > 0 && p.out_w > 0);
   GX_CHECK_ARG(kh * kw * 4 <= 48 * 1024);
   const long long total = (long long)major * p.out_h * p.out_w * minor;
+  cudaStream_t st = (cudaStream_t)stream;
+  if (minor == 1 && kh <= UT_K && kw <= UT_K && up_x == up_y && down_x == down_y && up_x <= 2 && down_x <= 2 &&
+      up_x * down_x <= 2 && p.out_w >= 32 && p.out_h >= 8) {
+    dim3 grid(gx_cdiv(p.out_w, UT_OW), gx_cdiv(p.out_h, UT_OH), major < 32768 ? major : 32768);
+    if (up_x == 2) upfirdn2d_planar_kernel<2, 1><<<grid, 256, 0, st>>>(input, kernel, out, p);
+    else if (down_x == 2) upfirdn2d_planar_kernel<1, 2><<<grid, 256, 0, st>>>(input, kernel, out, p);
+    else upfirdn2d_planar_kernel<1, 1><<<grid, 256, 0, st>>>(input, kernel, out, p);
+    GX_LAUNCH_CHECK();
+    return GX_OK;
+  }
   int grid = (int)((total + 255) / 256);
   const int cap = gx_sm_count() * 16;
   if (grid > cap) grid = cap;
-  upfirdn2d_kernel<<<grid, 256, kh * kw * sizeof(float), (cudaStream_t)stream>>>(input, kernel, out, p, total);
+  upfirdn2d_kernel<<<grid, 256, kh * kw * sizeof(float), st>>>(input, kernel, out, p, total);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }

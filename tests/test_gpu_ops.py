@@ -894,7 +894,16 @@ def test_native_ops_match_the_reference_cuda_kernels(L):
              ((2, 16, 16, 3), k4, (1, 1), (2, 2), (1, 1, 1, 1)),       # downsample
              ((1, 9, 11, 2), k3, (1, 1), (1, 1), (1, 1, 1, 1)),
              ((2, 13, 7, 4), k6, (2, 2), (1, 1), (3, 2, 3, 2)),
-             ((1, 8, 8, 1), k3, (2, 1), (1, 2), (2, 0, -1, 3))]        # generic path, a negative pad crops
+             ((1, 8, 8, 1), k3, (2, 1), (1, 2), (2, 0, -1, 3)),        # generic path, a negative pad crops
+             # planar (minor == 1) tiled kernel: tiles with ragged edges, odd pads, 3x3 and 2x2 filters
+             ((5, 67, 70, 1), k4, (1, 1), (1, 1), (2, 1, 2, 1)),
+             ((3, 257, 257, 1), k4, (1, 1), (1, 1), (1, 1, 1, 1)),
+             ((3, 40, 45, 1), k4 * 4, (2, 2), (1, 1), (2, 1, 2, 1)),
+             ((2, 33, 64, 1), k3, (2, 2), (1, 1), (1, 2, 0, 3)),
+             ((4, 70, 66, 1), k4, (1, 1), (2, 2), (1, 1, 1, 1)),
+             ((2, 90, 131, 1), k3, (1, 1), (2, 2), (2, 0, 1, 1)),
+             ((2, 64, 64, 1), torch.randn(2, 2, generator=g), (1, 1), (1, 1), (0, 1, 1, 0)),
+             ((2, 48, 80, 1), k4, (1, 1), (1, 1), (3, -2, -1, 4))]
     for shape, k, (ux, uy), (dx, dy), (px0, px1, py0, py1) in cases:
         x = torch.randn(*shape, generator=g).cuda()
         kc = k.contiguous().cuda()
@@ -912,3 +921,20 @@ def test_native_ops_match_the_reference_cuda_kernels(L):
             ref = fb.fused_bias_act(x, b if grad == 0 else empty, r_in, act, grad, 0.2, 1.4142135)
             got = L.fused_bias_act_raw(x, b if grad == 0 else None, refer if grad > 0 else None, act, grad, 0.2, 1.4142135)
             torch.testing.assert_close(got, ref, rtol=1e-6, atol=1e-7)
+
+
+@pytest.mark.parametrize("up,down,pad,shape,taps", [
+    (1, 1, (2, 1), (2, 3, 67, 70), [1, 3, 3, 1]), (2, 1, (2, 1), (1, 4, 40, 45), [1, 3, 3, 1]),
+    (1, 2, (1, 1), (2, 2, 70, 66), [1, 3, 3, 1]), (1, 1, (1, 1), (1, 2, 257, 257), [1, 2, 1]),
+    (2, 1, (1, 2, 0, 3), (1, 2, 33, 64), [1, 2, 1]), (1, 2, (2, 0, 1, 1), (1, 3, 90, 131), [1, 3, 3, 1])])
+def test_upfirdn2d_planar_path_vs_oracle(L, up, down, pad, shape, taps):
+    """NCHW drop-in calls large enough for the tiled planar kernel (minor == 1), against the oracle's upfirdn2d"""
+    from ganecdotes_b200.stylegan2.op import upfirdn2d
+    g = torch.Generator().manual_seed(sum(shape) + up + 2 * down)
+    x = torch.randn(*shape, generator=g)
+    k = O.make_fir_kernel(taps) * (up ** 2)
+    k = k + 0.01 * torch.randn(k.shape, generator=g)           # non-symmetric: the flip matters
+    ref = O.upfirdn2d(x, k, up=up, down=down, pad=pad)
+    got = upfirdn2d(x.cuda(), k.cuda(), up=up, down=down, pad=pad)
+    assert got.shape == ref.shape
+    torch.testing.assert_close(got.cpu(), ref, rtol=1e-5, atol=1e-6)
