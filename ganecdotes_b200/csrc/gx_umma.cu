@@ -44,6 +44,8 @@ struct UmmaParams {
   int acc_stages;  // TMEM accumulator ring depth (2 when mtiles*block_n <= 256)
   int a_mn, b_mn;
   int f16;         // operand planes are fp16 (single-pass only) instead of bf16
+  int nsub;        // pair gemm: 256-column accumulator sub-tiles per CTA tile (2 = 256 x 512 pair tiles: one A tile
+                   // feeds two N=256 MMAs, a quarter less operand ingest per FLOP; the whole TMEM is one accumulator)
   int pair;        // gemm: CTA pairs (clusters of 2, tcgen05 cta_group::2) on adjacent 128-row tiles of one
                    // n-tile: one M=256 MMA spans both SMs, each CTA loads its A rows and HALF of the B tile
                    // (a third less operand ingest per SM and FLOP than two independent 128-row tiles)
@@ -92,7 +94,7 @@ __device__ __forceinline__ TileInfo decode_tile(const UmmaParams& p, int w, int 
   const int tmn = w - split * tiles_mn;
   const int tile_n = tmn % p.tiles_n;
   const int tile_m = p.pair ? 2 * (tmn / p.tiles_n) + rank : tmn / p.tiles_n;
-  t.n0 = tile_n * p.block_n;
+  t.n0 = tile_n * p.block_n * p.nsub;
   t.m0 = tile_m * BM * p.mtiles;
   t.phase = 0; t.b0 = 0; t.y0 = 0; t.x0 = 0;
   if (p.mode == 0) {
@@ -217,7 +219,8 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   // carve (stage buffers must be 1024-aligned for the 128B swizzle)
   uint8_t* smem = reinterpret_cast<uint8_t*>((reinterpret_cast<uintptr_t>(smem_raw) + 1023) & ~uintptr_t(1023));
-  const int b_plane_bytes = (PAIR ? p.block_n / 2 : p.block_n) * BK * 2;
+  const int b_sub_bytes = (PAIR ? p.block_n / 2 : p.block_n) * BK * 2;
+  const int b_plane_bytes = b_sub_bytes * p.nsub;
   const int nplanes = (p.passes == 3) ? 2 : 1;
   const int a_plane_bytes = A_PLANE_BYTES * p.mtiles;
   const int stage_bytes = nplanes * (a_plane_bytes + b_plane_bytes);
@@ -308,11 +311,14 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
               } else {
                 for (int i = 0; i < 2; ++i) tma_load_2d_pair(da + i * 8192, ma, lead_bar, t.m0 + i * 64, k0);
               }
-              if (!p.b_mn) {
-                tma_load_2d_pair(db, mb, lead_bar, k0, t.n0 + crank * half_rows);
-              } else {
-                for (int i = 0; i < half_rows / 64; ++i)
-                  tma_load_2d_pair(db + i * 8192, mb, lead_bar, t.n0 + crank * half_rows + i * 64, k0);
+              for (int j = 0; j < p.nsub; ++j) {     // this CTA's half of every 256-column sub-tile of B
+                const int nrow = t.n0 + j * p.block_n + crank * half_rows;
+                if (!p.b_mn) {
+                  tma_load_2d_pair(db + j * b_sub_bytes, mb, lead_bar, k0, nrow);
+                } else {
+                  for (int i = 0; i < half_rows / 64; ++i)
+                    tma_load_2d_pair(db + j * b_sub_bytes + i * 8192, mb, lead_bar, nrow + i * 64, k0);
+                }
               }
             }
             if (++stage == p.stages) { stage = 0; phase ^= 1; }
@@ -384,7 +390,11 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
             for (int k4 = 0; k4 < BK / 16; ++k4) {
               const uint64_t bdesc = make_smem_desc(bbase + k4 * b_kstep, b_lbo, 1024u);
               if constexpr (PAIR) {
-                umma_bf16_pair(d_tmem, make_smem_desc(abase + k4 * a_kstep, a_lbo, 1024u), bdesc, idesc, accumulate);
+                const uint64_t adesc = make_smem_desc(abase + k4 * a_kstep, a_lbo, 1024u);
+                umma_bf16_pair(d_tmem, adesc, bdesc, idesc, accumulate);
+                if (p.nsub == 2)
+                  umma_bf16_pair(d_tmem + (uint32_t)p.block_n, adesc,
+                                 make_smem_desc(bbase + b_sub_bytes + k4 * b_kstep, b_lbo, 1024u), idesc, accumulate);
               } else {
                 for (int sub = 0; sub < p.mtiles; ++sub) {
                   const uint64_t adesc = make_smem_desc(abase + sub * A_PLANE_BYTES + k4 * a_kstep, a_lbo, 1024u);
@@ -417,7 +427,7 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
       mbar_wait(&tfull_bar[acc], acc_phase);
       tc_fence_after();
       const uint32_t taddr0 = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * p.mtiles * p.block_n);
-      const int nchunks = p.block_n / 32;
+      const int nchunks = p.block_n * p.nsub / 32;
 
       if (p.mode == 0) {
         // TMEM -> registers (thread = row) -> per-warp 32x33 smem tile -> registers (8 lanes per
@@ -635,9 +645,9 @@ int make_tmap(CUtensorMap* m, const void* base, int rank, const unsigned long lo
   return GX_OK;
 }
 
-int pick_stages(int passes, int block_n, int mtiles, int want) {
+int pick_stages(int passes, int block_n, int mtiles, int want, int nsub = 1) {
   const int nplanes = passes == 3 ? 2 : 1;
-  const int stage_bytes = nplanes * (A_PLANE_BYTES * mtiles + block_n * BK * 2);
+  const int stage_bytes = nplanes * (A_PLANE_BYTES * mtiles + nsub * block_n * BK * 2);
   const int avail = SMEM_LIMIT - 1024 /*align slack*/ - 256 /*barriers*/ - STAGING_BYTES;
   int s = avail / stage_bytes;
   if (s > MAX_STAGES) s = MAX_STAGES;
@@ -656,7 +666,7 @@ int launch(const UmmaParams& p_in, const CUtensorMap* maps, int total_work, cuda
     p.debug = dbg;
   }
   const int nplanes = p.passes == 3 ? 2 : 1;
-  const int stage_bytes = nplanes * (A_PLANE_BYTES * p.mtiles + (p.pair ? p.block_n / 2 : p.block_n) * BK * 2);
+  const int stage_bytes = nplanes * (A_PLANE_BYTES * p.mtiles + p.nsub * (p.pair ? p.block_n / 2 : p.block_n) * BK * 2);
   const int smem_bytes = p.stages * stage_bytes + 256 + STAGING_BYTES + 1024;
   static bool attr_set = false;
   if (!attr_set) {
@@ -719,11 +729,17 @@ extern "C" int gx_gemm(const gx_gemm_desc* d, void* stream) {
   // (MN-major B is loaded in 64-wide boxes: each CTA's half must hold at least one)
   p.pair = (d->cluster_pair && d->m > BM && bn >= (p.b_mn ? 128 : 64)) ? 1 : 0;
   p.mtiles = (p.passes == 1 && bn == 256 && d->m > BM && !d->force_m128 && !p.pair) ? 2 : 1;
-  p.acc_stages = (p.mtiles * bn <= 256) ? 2 : 1;
-  p.stages = pick_stages(p.passes, p.pair ? bn / 2 : bn, p.mtiles, d->stages);
+  // 256 x 512 pair tiles for the single-pass GEMMs with a wide N and a long K loop (dZn = dS Wk, gWk = dS^T Zn):
+  // these are bound by operand ingest through the SM<->L2 port, and the A tile then feeds two N = 256 MMAs.
+  // Not for the score GEMM (short K: the store-heavy epilogue needs the second accumulator stage to overlap).
+  static const int nsub_env = getenv("GX_UMMA_NSUB") ? atoi(getenv("GX_UMMA_NSUB")) : 2;
+  p.nsub = (p.pair && p.passes == 1 && bn == 256 && d->n % 512 == 0 && d->colexp_sum == nullptr && d->k >= 2048 &&
+            nsub_env == 2) ? 2 : 1;
+  p.acc_stages = (p.mtiles * bn * p.nsub <= 256) ? 2 : 1;
+  p.stages = pick_stages(p.passes, p.pair ? bn / 2 : bn, p.mtiles, d->stages, p.nsub);
   GX_CHECK_ARG(p.stages >= 2);
   p.tiles_m = gx_cdiv(d->m, BM * p.mtiles);
-  p.tiles_n = gx_cdiv(d->n, bn);
+  p.tiles_n = gx_cdiv(d->n, bn * p.nsub);
   p.kiters_total = gx_cdiv(d->k, BK);
   int sk = d->split_k < 1 ? 1 : d->split_k;
   if (sk > p.kiters_total) sk = p.kiters_total;
@@ -787,6 +803,7 @@ extern "C" int gx_modconv(const gx_conv_desc* d, void* stream) {
   UmmaParams p;
   memset(&p, 0, sizeof(p));
   p.mode = 1;
+  p.nsub = 1;
   p.passes = d->passes;
   p.B = d->batch; p.H = d->h; p.W = d->w; p.Cin = cin_ld; p.Cout = d->cout;  // the K loop runs over padded channels
   p.upsample = d->upsample ? 1 : 0;

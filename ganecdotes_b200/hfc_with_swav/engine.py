@@ -379,8 +379,9 @@ def scores_backward(head: SwavHead, fw, ds_hi, ds_lo, dz_rows_out=None):
     kit = (n + 63) // 64
     sms = L.load().gx_sinkhorn_max_parts()
     bm = 256 if pb == 1 else 128     # the engine uses 256-row CTA tiles for single-pass GEMMs
-    # CTA pairs: one unit of work = 256 x 256 outputs on two SMs
-    sk1 = pick_split_k(math.ceil(k / 256) * math.ceil(c / 256), kit, sms // 2)
+    # CTA pairs: one unit of work = 256 x 256 outputs on two SMs (256 x 512 for single-pass GEMMs with c % 512 == 0)
+    wide = 512 if (pb == 1 and c % 512 == 0 and n >= 2048) else 256
+    sk1 = pick_split_k(math.ceil(k / 256) * math.ceil(c / wide), kit, sms // 2)
     L.gemm(ds_hi, ds_lo if pb == 3 else None, fw["zn_hi"], fw["zn_lo"] if pb == 3 else None, k, c, n, pb,
            out=head.g_proto, a_mn=True, b_mn=True, split_k=sk1, accumulate=True, tag="gemm_gproto_bwd", pair=True)
     if dz_rows_out is not None:

@@ -177,6 +177,8 @@ def test_gemm_fused_first_sinkhorn_marginal(L):
     (1100, 600, 512, 1, True),       # 9 m-tiles: the second CTA of the last pair has no rows
     (130, 136, 64, 1, False),        # ragged n tail inside the second B half
     (4096, 264, 200, 3, False),
+    (1000, 512, 2560, 1, False),     # 256 x 512 pair tiles (nsub = 2): n % 512 == 0, long K, single pass
+    (1300, 1024, 2048, 1, True),     # two 512-wide n-tiles, 11 m-tiles (ragged last pair), fp16 planes
 ])
 def test_gemm_cta_pair(L, m, n, k, passes, f16):
     """CTA pairs (tcgen05 cta_group::2: one M=256 MMA over two SMs, half of the B tile per SM) give the
