@@ -127,6 +127,7 @@ _SIGNATURES = {
     "gx_larc_sgd": ([_P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _P, _P], _I),
     "gx_argmax_rows": ([_P, _LL, _I, _LL, _P, _P], _I),
     "gx_kmeans_assign": ([_P, _I, _P, _I, _LL, _P, _I, _P, _P, _P], _I),
+    "gx_argmin_affine": ([_P, _LL, _I, _LL, _P, _F, _P, _P], _I),
     "gx_onehot_nearest": ([_P, _I, _I, _I, _I, _I, _I, _P, _P], _I),
 }
 
@@ -989,19 +990,55 @@ def argmax_rows(x):
     return labels
 
 
-def kmeans_assign(x, centers, x2=None, want_dist=False):
+def argmin_affine(s, bias, scale):
+    """labels int32 [n] = first argmin_k (bias[k] + scale * s[n,k])"""
+    lib = load()
+    _f32(s, "s"), _f32(bias, "bias")
+    n, k = s.shape
+    labels = torch.empty((n,), dtype=torch.int32, device=s.device)
+    with timed("kmeans_argmin", 4.0 * n * k):
+        _check(lib.gx_argmin_affine(_ptr(s), n, k, s.stride(0), _ptr(bias), float(scale), _ptr(labels), _stream()),
+               "gx_argmin_affine")
+    _count()
+    return labels
+
+
+def kmeans_assign(x, centers, x2=None, want_dist=False, tensor=None):
     """x [n,c1] (+ x2 [n,c2]) fp32 contiguous, centers [k,c1+c2] -> int32 labels [n]
-    (with want_dist: (labels, squared distance to the assigned centre [n]))"""
+    (with want_dist: (labels, squared distance to the assigned centre [n])).
+
+    Two routes.  Direct (SIMT, sum of (x - c)^2 in fp32): exact distances, used for the k-means fit (want_dist) and
+    for small inputs.  Tensor cores (`tensor`, default for labels-only calls on >= 4096 rows): scores X C^T as a
+    3-pass split-bf16 GEMM (fp32-grade products), then argmin_k(||c_k||^2 - 2 x.c_k) - the GEMM form scikit-learn's
+    predict uses; the features are read once instead of once per centre.  The two routes can differ only where the
+    two nearest centres are closer than ~1e-4 of the squared distance (accumulation rounding of the x.c term)."""
     lib = load()
     _f32(centers, "centers"), _f32(x, "x"), _f32(x2, "x2")
     n, c1 = x.shape
     c2 = 0 if x2 is None else x2.shape[1]
-    if centers.shape[1] != c1 + c2:
+    c = c1 + c2
+    if centers.shape[1] != c:
         raise GxError("kmeans_assign: centers must have c1+c2 columns")
+    if tensor is None:
+        tensor = (not want_dist) and n >= 4096 and c1 % 8 == 0 and c2 % 8 == 0
+    if tensor:
+        if want_dist:
+            raise GxError("kmeans_assign: the tensor-core route returns labels only")
+        k = centers.shape[0]
+        a_hi = torch.empty((n, c), dtype=torch.bfloat16, device=x.device)
+        a_lo = torch.empty_like(a_hi)
+        split_planes(x, out=(a_hi[:, :c1], a_lo[:, :c1]))
+        if x2 is not None:
+            split_planes(x2, out=(a_hi[:, c1:], a_lo[:, c1:]))
+        c_hi, c_lo = split_planes(centers.contiguous())
+        cn = (centers.double() ** 2).sum(1).float().contiguous()        # ||c_k||^2: K numbers, host-side glue
+        s = gemm(a_hi, a_lo, c_hi, c_lo, n, k, c, 3, tag="gemm_kmeans_scores", block_n=64 if k <= 64 else 0)
+        return argmin_affine(s, cn, -2.0)
     labels = torch.empty((n,), dtype=torch.int32, device=x.device)
     dist = torch.empty((n,), dtype=torch.float32, device=x.device) if want_dist else None
-    _check(lib.gx_kmeans_assign(_ptr(x), c1, _ptr(x2), c2, n, _ptr(centers), centers.shape[0], _ptr(labels),
-                                _ptr(dist), _stream()), "gx_kmeans_assign")
+    with timed("kmeans_assign", 4.0 * n * c):
+        _check(lib.gx_kmeans_assign(_ptr(x), c1, _ptr(x2), c2, n, _ptr(centers), centers.shape[0], _ptr(labels),
+                                    _ptr(dist), _stream()), "gx_kmeans_assign")
     _count()
     return (labels, dist) if want_dist else labels
 

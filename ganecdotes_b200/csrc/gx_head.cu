@@ -1461,6 +1461,28 @@ __global__ void kmeans_assign_kernel(const float* __restrict__ x1, int c1, const
   }
 }
 
+// labels[n] = first argmin_k (bias[k] + scale * s[n,k]): nearest centre from the x.c scores of the tensor-core path,
+// ||x - c||^2 = ||x||^2 - 2 x.c + ||c||^2 (the ||x||^2 term does not change the arg-min).  One warp per row.
+__global__ void argmin_affine_kernel(const float* __restrict__ s, long long n, int k, long long lds,
+                                     const float* __restrict__ bias, float scale, int* __restrict__ labels) {
+  const int lane = threadIdx.x & 31;
+  const long long row = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n) return;
+  float best = INFINITY;
+  int bi = 0x7fffffff;
+  for (int kk = lane; kk < k; kk += 32) {
+    const float v = fmaf(scale, s[row * lds + kk], __ldg(bias + kk));
+    if (v < best) { best = v; bi = kk; }           // kk ascends: the first minimum of this lane is kept
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov < best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  if (lane == 0) labels[row] = bi == 0x7fffffff ? 0 : bi;
+}
+
 // one-hot cluster maps resized with nearest neighbour (ref hfc_kmeans_clustering.py:190-206)
 __global__ void onehot_nearest_kernel(const int* __restrict__ labels, int b, int h, int w, int k, int oh, int ow,
                                       float* __restrict__ out) {
@@ -1946,6 +1968,14 @@ extern "C" int gx_kmeans_assign(const float* x1, int c1, const float* x2, int c2
   GX_CHECK_ARG((x2 != nullptr) == (c2 > 0));
   kmeans_assign_kernel<<<gx_cdiv(n, 8), 256, 0, (cudaStream_t)stream>>>(x1, c1, x2, c2, n, centers, k, labels,
                                                                         dist);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_argmin_affine(const float* s, long long n, int k, long long lds, const float* bias, float scale,
+                                int* labels, void* stream) {
+  GX_CHECK_ARG(s && bias && labels && n > 0 && k > 0 && lds >= k);
+  argmin_affine_kernel<<<gx_cdiv(n, 8), 256, 0, (cudaStream_t)stream>>>(s, n, k, lds, bias, scale, labels);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }

@@ -394,6 +394,12 @@ int gx_argmax_rows(const float* x, long long n, int c, long long ldx, long long*
 int gx_kmeans_assign(const float* x1, int c1, const float* x2, int c2, long long n, const float* centers, int k,
                      int* labels, float* dist, void* stream);
 
+/* labels[n] = first argmin_k (bias[k] + scale * s[n,k]).  With s = X C^T from gx_gemm (3-pass split-bf16), bias =
+ * ||c_k||^2 and scale = -2 this is the same nearest-centre assignment on the tensor cores (the GEMM form of the
+ * distance that scikit-learn's predict uses, ref: hfc_kmeans_clustering.py:184). int32 out. */
+int gx_argmin_affine(const float* s, long long n, int k, long long lds, const float* bias, float scale, int* labels,
+                     void* stream);
+
 /* one-hot cluster maps [b,k,out_h,out_w] from labels [b,h,w], nearest-neighbour resize
  * (ref: hfc_kmeans_clustering.py:190-206). */
 int gx_onehot_nearest(const int* labels, int b, int h, int w, int k, int out_h, int out_w, float* out,

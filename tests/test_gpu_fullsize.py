@@ -176,22 +176,28 @@ def test_pidray256_label_map_batch():
     assert torch.equal(l2[0], labels[2])
 
 
+@pytest.mark.parametrize("tensor", [False, True])
 @pytest.mark.parametrize("c,h,k", [(1024, 64, 32), (512, 128, 64), (1024, 8, 4)])
-def test_kmeans_assign_full_shapes(c, h, k):
-    """config 5: per-pixel nearest centre on [b, C, h, w] features"""
+def test_kmeans_assign_full_shapes(c, h, k, tensor):
+    """config 5: per-pixel nearest centre on [b, C, h, w] features, both routes: direct fp32 distances
+    (SIMT) and the tensor-core route (3-pass split-bf16 scores X C^T, then argmin(||c||^2 - 2 x.c))"""
     from ganecdotes_b200 import _lib as L
     torch.manual_seed(c + h)
     b = 2
-    x = torch.randn(b * h * h, c, device="cuda")
-    cen = torch.randn(k, c, device="cuda")
-    lab = L.kmeans_assign(x, cen)
-    d = torch.cdist(x.double(), cen.double())
+    x = torch.randn(b * h * h, c, device="cuda") + 0.5          # non-centred features: x.c is not small against ||x||^2
+    cen = torch.randn(k, c, device="cuda") + 0.5
+    lab = L.kmeans_assign(x[:, :c // 2].contiguous(), cen, x[:, c // 2:].contiguous(), tensor=tensor)
+    d = torch.cdist(x.double(), cen.double()) ** 2
     ref = d.argmin(1)
     mism = lab.long() != ref
-    if mism.any():      # only where fp32 cannot separate the two nearest centres
+    if mism.any():      # only where the two nearest centres are closer than the rounding of the route
         top2 = d.topk(2, dim=1, largest=False).values
         assert ((top2[:, 1] - top2[:, 0])[mism] < 1e-4 * top2[:, 0][mism]).all()
     assert mism.float().mean().item() < 1e-3
+    if not tensor:      # the default route of a large labels-only call is the tensor-core one
+        auto = L.kmeans_assign(x[:, :c // 2].contiguous(), cen, x[:, c // 2:].contiguous())
+        want = L.kmeans_assign(x[:, :c // 2].contiguous(), cen, x[:, c // 2:].contiguous(), tensor=x.shape[0] >= 4096)
+        assert torch.equal(auto, want)
 
 
 def test_score_gemm_precision_modes_at_config_eps():
