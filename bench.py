@@ -108,25 +108,40 @@ def dist_env():
 
 
 def stage_table(log, steps, total_ms, issued=None):
-    """per-kernel totals from the CUDA events recorded around every launch of the timed region"""
+    """per-kernel totals from the CUDA events recorded around every launch of the timed region.  A tensor-core stage
+    is reported against the roofline that bounds it: its algorithmic FLOPs x MMA passes at the sustained bf16 peak,
+    or - when that takes less time than moving its operands and output once at the HBM peak (short-K GEMMs: the
+    per-resolution projections, the k-means scores) - its algorithmic bytes."""
     issued = issued or {}
     stages = {}
-    for name, a, c, work in log:
-        s = stages.setdefault(name, [0.0, 0.0, 0])
+    for ev in log:
+        name, a, c, work = ev[:4]
+        nbytes = ev[4] if len(ev) > 4 else 0.0
+        s = stages.setdefault(name, [0.0, 0.0, 0, 0.0])
         s[0] += a.elapsed_time(c)
         s[1] += work
         s[2] += 1
+        s[3] += nbytes
     pk = peaks()
     rows = []
-    for name, (tms, work, cnt) in sorted(stages.items(), key=lambda kv: -kv[1][0]):
+    for name, (tms, work, cnt, nbytes) in sorted(stages.items(), key=lambda kv: -kv[1][0]):
         is_tensor = name.split("_")[0].split("@")[0] in {"gemm", "modconv", "segmentor"}
+        p = issued.get(name.split("@")[0], 1) if is_tensor else 1
+        if is_tensor and nbytes > 0 and nbytes / (pk["hbm"] * 1e9) > p * work / (pk["tf_sustained"] * 1e12):
+            # HBM-bound contraction
+            achieved = nbytes / (tms * 1e-3) / 1e9 if tms > 0 else 0.0
+            rows.append({"kernel": name, "bound": "hbm", "launches": cnt, "ms_per_step": tms / steps, "share": tms / total_ms,
+                         "achieved": achieved, "peak": pk["hbm"], "unit": "GB/s", "frac": achieved / pk["hbm"],
+                         "note": "tensor-core contraction bound by its operand + output bytes (short K)",
+                         "tflops": work / (tms * 1e-3) / 1e12 if tms > 0 else 0.0})
+            stages[name] = [tms, nbytes, cnt, nbytes]
+            continue
         peak = pk["tf_sustained"] if is_tensor else pk["hbm"]
         achieved = (work / (tms * 1e-3)) / (1e12 if is_tensor else 1e9) if tms > 0 else 0.0
         row = {"kernel": name, "bound": "tensor" if is_tensor else "hbm", "launches": cnt,
                "ms_per_step": tms / steps, "share": tms / total_ms, "achieved": achieved, "peak": peak,
                "unit": "TFLOP/s" if is_tensor else "GB/s", "frac": achieved / peak}
         if is_tensor:
-            p = issued.get(name.split("@")[0], 1)
             row["mma_passes"] = p
             row["frac_issued"] = p * achieved / peak
             if p > 1:   # precision-adjusted ceiling of the algorithmic fraction (DESIGN.md §4.2)
@@ -144,7 +159,7 @@ def roofline_of(rows, stages, pk):
     if os.path.exists(tpath):
         with open(tpath) as f:
             traffic = json.load(f).get(top["kernel"], {}).get("dram_bytes_per_launch")
-    tms, work, cnt = stages[top["kernel"]]
+    tms, work, cnt = stages[top["kernel"]][:3]
     return {"kernel": top["kernel"], "bound": top["bound"], "achieved": top["achieved"], "peak": top["peak"],
             "unit": top["unit"], "frac": top["frac"], "traffic": traffic, "algorithmic_per_launch": work / cnt,
             "launches": cnt, "ms_per_launch": tms / cnt, "peak_source": pk["src"],

@@ -229,8 +229,11 @@ event_log = None
 class timed:
     """with timed("name", work): launch...  - records CUDA events on the launching stream."""
 
-    def __init__(self, name, work=0.0):
-        self.name, self.work = name, work
+    def __init__(self, name, work=0.0, nbytes=0.0):
+        # work: algorithmic FLOPs (tensor-bound stages) or bytes (HBM-bound stages); nbytes: for a tensor stage, the
+        # bytes it must move (operands once + output once) - bench.py reports the stage against whichever roofline
+        # bounds it (a short-K GEMM is bound by its output, not by the tensor pipe)
+        self.name, self.work, self.nbytes = name, work, nbytes
 
     def __enter__(self):
         if event_log is not None:
@@ -242,7 +245,7 @@ class timed:
     def __exit__(self, *a):
         if event_log is not None:
             self.e1.record()
-            event_log.append((self.name, self.e0, self.e1, self.work))
+            event_log.append((self.name, self.e0, self.e1, self.work, self.nbytes))
         return False
 
 
@@ -584,7 +587,7 @@ def gemm(a_hi, a_lo, b_hi, b_lo, m, n, k, passes, out=None, bias=None, a_mn=Fals
     if colexp is not None:      # (zeroed fp32 [n] tensor, scale in the log2 domain)
         d.colexp_sum, d.colexp_scale = _ptr(colexp[0]), float(colexp[1])
     fn = lib.gx_gemm_check if check else lib.gx_gemm
-    with timed(tag, 2.0 * m * n * k):
+    with timed(tag, 2.0 * m * n * k, (2.0 if passes == 1 else 4.0) * (float(m) * k + float(n) * k) + 4.0 * m * n):
         _check(fn(C.byref(d), _stream()), "gx_gemm")
     _count()
     return out

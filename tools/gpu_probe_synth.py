@@ -16,7 +16,7 @@ for _ in range(3): g.synthesize(lat, None, False)
 e1.record(); torch.cuda.synchronize()
 print(f"synthesis B={b}: {e0.elapsed_time(e1)/3:.3f} ms per forward ({90.24*b/(e0.elapsed_time(e1)/3)/1e0:.1f} GFLOP/ms alg)")
 agg = {}
-for name, a, c, work in L.event_log:
+for name, a, c, work, _ in L.event_log:
     t = agg.setdefault(name, [0.0, 0.0, 0]); t[0] += a.elapsed_time(c); t[1] += work; t[2] += 1
 for name, (ms, work, n) in sorted(agg.items(), key=lambda kv: -kv[1][0]):
     unit = "TF" if "modconv" in name else "GB/s"
