@@ -124,6 +124,12 @@ _SIGNATURES = {
     "gx_loss_max_parts": ([], _I),
     "gx_swav_loss": ([_P, _P, _LL, _I, _LL, _F, _F, _P, _P, _F, _P, _P, C.POINTER(_I), _P, _P, _P, _P, _LL, _P, _P,
                       _P], _I),
+    "gx_recip": ([_P, _LL, _F, _I, _P, _P], _I),
+    "gx_bn_stats": ([_P, _LL, _P, _I, _I, _F, _P, _P, _P, _P, _F, _P], _I),
+    "gx_bn_act_apply": ([_P, _LL, _P, _LL, _I, _P, _P, _P, _P, _F, _P, _P, _P, _P], _I),
+    "gx_bn_act_bwd": ([_P, _P, _LL, _P, _I, _I, _P, _P, _P, _P, _F, _P, _P, _P, _P], _I),
+    "gx_simclr_loss": ([_P, _I, _I, _F, _P, _P, _P], _I),
+    "gx_larc_scratch_floats": ([], _I),
     "gx_larc_sgd": ([_P, _P, _P, _LL, _F, _F, _F, _F, _F, _I, _P, _P], _I),
     "gx_argmax_rows": ([_P, _LL, _I, _LL, _P, _P], _I),
     "gx_kmeans_assign": ([_P, _I, _P, _I, _LL, _P, _I, _P, _P, _P], _I),
@@ -976,8 +982,86 @@ def swav_loss(s_s, s_t, inv_eps, inv_temp, la_s, la_t, grad_scale, want_lo=False
     return loss_parts, (ds_s_hi, ds_s_lo), (ds_t_hi, ds_t_lo), db, (fs, ft)
 
 
+def recip_clamp(x, eps):
+    """1 / max(x, eps)"""
+    _f32(x, "x")
+    out = torch.empty_like(x)
+    _check(load().gx_recip(_ptr(x), x.numel(), float(eps), 0, _ptr(out), _stream()), "gx_recip")
+    _count()
+    return out
+
+
+def rsqrt_eps(x, eps):
+    """rsqrt(x + eps)"""
+    _f32(x, "x")
+    out = torch.empty_like(x)
+    _check(load().gx_recip(_ptr(x), x.numel(), float(eps), 1, _ptr(out), _stream()), "gx_recip")
+    _count()
+    return out
+
+
+def bn_stats(hraw, rscale, eps=1e-5, run_mean=None, run_var=None, momentum=0.1):
+    """(mean[c], invstd[c]) of h = hraw * rscale[row] over the rows (training-mode BatchNorm1d); updates the
+    running statistics in place when given"""
+    _f32(hraw, "hraw"), _f32(rscale, "rscale")
+    n, c = hraw.shape
+    mean = torch.empty((c,), dtype=torch.float32, device=hraw.device)
+    invstd = torch.empty_like(mean)
+    _check(load().gx_bn_stats(_ptr(hraw), hraw.stride(0), _ptr(rscale), n, c, float(eps), _ptr(mean), _ptr(invstd),
+                              _ptr(run_mean), _ptr(run_var), float(momentum), _stream()), "gx_bn_stats")
+    _count()
+    return mean, invstd
+
+
+def bn_act_apply(hraw, rscale, mean, invstd, gamma, beta, slope=0.01, want_f32=True, want_planes=True, want_lo=True):
+    """a = lrelu((hraw * rscale - mean) * invstd * gamma + beta) -> (a fp32 or None, hi, lo)"""
+    _f32(hraw, "hraw"), _f32(rscale, "rscale")
+    n, c = hraw.shape
+    dev = hraw.device
+    out = torch.empty((n, c), dtype=torch.float32, device=dev) if want_f32 else None
+    hi = torch.empty((n, c), dtype=torch.bfloat16, device=dev) if want_planes else None
+    lo = torch.empty_like(hi) if (want_planes and want_lo) else None
+    with timed("bn_act_apply", float(n) * c * (4 + (4 if want_f32 else 0) + (4 if lo is not None else 2 if hi is not None else 0))):
+        _check(load().gx_bn_act_apply(_ptr(hraw), hraw.stride(0), _ptr(rscale), n, c, _ptr(mean), _ptr(invstd), _ptr(gamma),
+                                      _ptr(beta), float(slope), _ptr(out), _ptr(hi), _ptr(lo), _stream()), "gx_bn_act_apply")
+    _count()
+    return out, hi, lo
+
+
+def bn_act_bwd(da, hraw, rscale, mean, invstd, gamma, beta, slope=0.01):
+    """(dhs [n,c] = dL/dhraw, dgamma [c], dbeta [c])"""
+    _f32(da, "da"), _f32(hraw, "hraw")
+    n, c = hraw.shape
+    dhs = torch.empty((n, c), dtype=torch.float32, device=hraw.device)
+    dg = torch.empty((c,), dtype=torch.float32, device=hraw.device)
+    db = torch.empty_like(dg)
+    _check(load().gx_bn_act_bwd(_ptr(da), _ptr(hraw), hraw.stride(0), _ptr(rscale), n, c, _ptr(mean), _ptr(invstd),
+                                _ptr(gamma), _ptr(beta), float(slope), _ptr(dhs), _ptr(dg), _ptr(db), _stream()),
+           "gx_bn_act_bwd")
+    _count()
+    return dhs, dg, db
+
+
+def simclr_loss(z, temperature):
+    """(loss [1], dz [n2, c]) of the reference's contrastive loss on the projection output z [n2, c]"""
+    _f32(z, "z")
+    n2, c = z.shape
+    loss = torch.empty((1,), dtype=torch.float32, device=z.device)
+    dz = torch.empty_like(z)
+    _check(load().gx_simclr_loss(_ptr(z), n2, c, 1.0 / float(temperature), _ptr(loss), _ptr(dz), _stream()),
+           "gx_simclr_loss")
+    _count()
+    return loss, dz
+
+
+def larc_scratch(device):
+    return torch.empty(load().gx_larc_scratch_floats(), dtype=torch.float32, device=device)
+
+
 def larc_sgd_(p, g, buf, lr, momentum, trust, weight_decay, eps, first_step, norms):
     lib = load()
+    if norms.numel() < lib.gx_larc_scratch_floats():
+        raise GxError("larc_sgd_: norms scratch must hold gx_larc_scratch_floats() floats (L.larc_scratch)")
     _f32(p, "p"), _f32(g, "g"), _f32(buf, "buf")
     _check(lib.gx_larc_sgd(_ptr(p), _ptr(g), _ptr(buf), p.numel(), float(lr), float(momentum), float(trust),
                            float(weight_decay), float(eps), int(first_step), _ptr(norms), _stream()), "gx_larc_sgd")

@@ -1368,8 +1368,11 @@ swav_loss_pow_kernel(const float* __restrict__ ss, const float* __restrict__ st,
 // ---------------------------------------------------------------------------
 // LARC + SGD(momentum)
 // ---------------------------------------------------------------------------
+// Deterministic two-stage norms: per-block partial sums (no atomics), folded in a fixed order by every block of the
+// update kernel - the LARC trust ratio is then bit-identical from run to run and from rank to rank, which keeps
+// data-parallel replicas in lock-step (float atomics would let them drift apart by an ulp per step).
 __global__ void sq_norms_kernel(const float* __restrict__ p, const float* __restrict__ g, long long n,
-                                float* __restrict__ norms) {
+                                float* __restrict__ parts) {
   float sp = 0.f, sg = 0.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
     sp = fmaf(p[i], p[i], sp);
@@ -1384,15 +1387,24 @@ __global__ void sq_norms_kernel(const float* __restrict__ p, const float* __rest
   if (threadIdx.x == 0) {
     float a = 0.f, b = 0.f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { a += rp[w]; b += rg[w]; }
-    atomicAdd(norms, a);
-    atomicAdd(norms + 1, b);
+    parts[2 * blockIdx.x] = a;
+    parts[2 * blockIdx.x + 1] = b;
   }
 }
 
 __global__ void larc_sgd_kernel(float* __restrict__ p, const float* __restrict__ g, float* __restrict__ buf,
                                 long long n, float lr, float momentum, float trust, float wd, float eps, int first,
-                                const float* __restrict__ norms) {
-  const float pn = sqrtf(norms[0]), gn = sqrtf(norms[1]);
+                                const float* __restrict__ parts, int nparts) {
+  __shared__ float tot[2];
+  if (threadIdx.x < 32) {
+    float a = 0.f, b = 0.f;
+    for (int i = threadIdx.x; i < nparts; i += 32) { a += parts[2 * i]; b += parts[2 * i + 1]; }
+    a = gx_warp_sum(a);
+    b = gx_warp_sum(b);
+    if (threadIdx.x == 0) { tot[0] = a; tot[1] = b; }
+  }
+  __syncthreads();
+  const float pn = sqrtf(tot[0]), gn = sqrtf(tot[1]);
   const bool adapt = (pn != 0.f) && (gn != 0.f);
   const float alr = adapt ? trust * pn / (gn + pn * wd + eps) : 1.f;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
@@ -1939,18 +1951,19 @@ extern "C" int gx_swav_loss(const float* s_s, const float* s_t, long long n, int
   return GX_OK;
 }
 
+extern "C" int gx_larc_scratch_floats(void) { return 2 * 4 * gx_sm_count(); }
+
 extern "C" int gx_larc_sgd(float* p, const float* g, float* buf, long long n, float lr, float momentum, float trust,
                            float weight_decay, float eps, int first_step, float* norms, void* stream) {
   GX_CHECK_ARG(p && g && buf && norms && n > 0);
   cudaStream_t st = (cudaStream_t)stream;
-  GX_CHECK_CUDA(cudaMemsetAsync(norms, 0, 2 * sizeof(float), st));
   int grid = gx_cdiv(n, 256 * 8);
-  const int cap = gx_sm_count() * 4;
+  const int cap = gx_larc_scratch_floats() / 2;
   if (grid > cap) grid = cap;
   if (grid < 1) grid = 1;
   sq_norms_kernel<<<grid, 256, 0, st>>>(p, g, n, norms);
   GX_LAUNCH_CHECK();
-  larc_sgd_kernel<<<grid, 256, 0, st>>>(p, g, buf, n, lr, momentum, trust, weight_decay, eps, first_step, norms);
+  larc_sgd_kernel<<<grid, 256, 0, st>>>(p, g, buf, n, lr, momentum, trust, weight_decay, eps, first_step, norms, grid);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }

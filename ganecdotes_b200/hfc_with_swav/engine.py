@@ -193,7 +193,7 @@ class SwavHead:
         self.m_proj = torch.zeros_like(w_proj)
         self.m_proto = torch.zeros_like(w_proto)
         self.m_bias = torch.zeros_like(b_proto)
-        self.norms = torch.zeros(2, dtype=torch.float32, device=dev)
+        self.norms = L.larc_scratch(dev)
         self.steps = 0
         self.planes_ready = False
 

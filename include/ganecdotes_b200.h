@@ -373,10 +373,38 @@ int gx_swav_loss(const float* s_s, const float* s_t, long long n, int k, long lo
                  long long ldd, float* ds_s_f32, float* ds_t_f32, void* stream);
 
 /* ------------------------------------------------------------------------------------
- * Optimiser: apex LARC(clip=False) around SGD(momentum)
- * (ref: swav_clustering.py:286-292,458-460).  norms: scratch [2] floats (zeroed by the call).
- * first_step != 0: momentum buffer := g.
+ * SimCLR baseline head (ref: baseline/hfc_with_simclr/simclr_clustering.py:133-281, 362-401):
+ * Linear(no bias) -> BatchNorm1d -> LeakyReLU(0.01) -> Linear(no bias) on channel-normalised per-pixel vectors.
+ * The two Linear layers are gx_gemm calls; these are the pieces in between.  hraw [n,c] (row pitch ldh) is the
+ * first GEMM's output on the UN-normalised rows; rscale[n] = 1 / max(|row|, 1e-12) is F.normalize folded in
+ * (h = hraw * rscale; NULL = 1).
  * ---------------------------------------------------------------------------------- */
+/* out[i] = 1 / max(x[i], eps) (mode 0: the 1/|f| of F.normalize from the row norms of gx_gather_rows) or
+ * rsqrt(x[i] + eps) (mode 1: the eval-mode BatchNorm scale from the running variance). */
+int gx_recip(const float* x, long long n, float eps, int mode, float* out, void* stream);
+/* training-mode batch statistics over the n rows: mean[c], invstd[c] = rsqrt(biased var + eps); optionally the
+ * running statistics update run = (1 - momentum) run + momentum (mean, unbiased var)  (nn.BatchNorm1d). */
+int gx_bn_stats(const float* hraw, long long ldh, const float* rscale, int n, int c, float eps, float* mean,
+                float* invstd, float* run_mean, float* run_var, float momentum, void* stream);
+/* a = lrelu_slope((h - mean) * invstd * gamma + beta): fp32 out [n,c] and/or split-bf16 planes (any may be NULL). */
+int gx_bn_act_apply(const float* hraw, long long ldh, const float* rscale, long long n, int c, const float* mean,
+                    const float* invstd, const float* gamma, const float* beta, float slope, float* out, void* hi,
+                    void* lo, void* stream);
+/* backward through lrelu(bn(.)) with batch statistics: dhs[n,c] = dL/dhraw (= dL/dh * rscale), dgamma[c], dbeta[c]. */
+int gx_bn_act_bwd(const float* da, const float* hraw, long long ldh, const float* rscale, int n, int c,
+                  const float* mean, const float* invstd, const float* gamma, const float* beta, float slope,
+                  float* dhs, float* dgamma, float* dbeta, void* stream);
+/* The reference's contrastive loss on the projection output z [n2, c] (n2 = 2 * batch_size <= 64 rows interleaved
+ * s_0, t_0, s_1, ...; ref :235-265 with both of its quirks, see oracle simclr_loss) and its gradient dz [n2, c]. */
+int gx_simclr_loss(const float* z, int n2, int c, float inv_temperature, float* loss, float* dz, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Optimiser: apex LARC(clip=False) around SGD(momentum)
+ * (ref: swav_clustering.py:286-292,458-460).  norms: scratch of gx_larc_scratch_floats() floats (per-block partial
+ * sums of |p|^2, |g|^2, folded in a fixed order: the trust ratio is deterministic, so data-parallel replicas
+ * that apply the same all-reduced gradient stay bit-identical).  first_step != 0: momentum buffer := g.
+ * ---------------------------------------------------------------------------------- */
+int gx_larc_scratch_floats(void);
 int gx_larc_sgd(float* p, const float* g, float* buf, long long n, float lr, float momentum, float trust,
                 float weight_decay, float eps, int first_step, float* norms, void* stream);
 

@@ -600,7 +600,7 @@ def test_larc_sgd_vs_oracle(L):
     ps = [p]
     pd = p.clone().cuda()
     buf = torch.zeros_like(pd)
-    norms = torch.zeros(2, device="cuda")
+    norms = L.larc_scratch("cuda")
     for step in range(3):
         g = torch.randn(1000, 33) * 0.01
         ps, bufs = O.larc_sgd_step(ps, [g], bufs, 0.01, 0.9, 0.01)

@@ -512,3 +512,91 @@ def test_create_hidden_features_from_perturbed_vectors_matches_oracle(gen, tmp_p
         skip = oneshot.create_images_and_features_from_perturbed_latents(
             new.cuda(), gen, {'truncation': 0.7, 'mean_latent': obj.mean_latent}, return_image=False, skip_const=True)
         assert len(skip) == len(feats) - 1 and torch.equal(skip[0], feats[1])
+
+
+# ----------------------------------------------------------------------------------------
+# SimCLR baseline head
+# ----------------------------------------------------------------------------------------
+
+@pytest.mark.parametrize("n2,c", [(12, 32), (40, 512)])
+def test_simclr_head_kernels_vs_oracle_autograd(n2, c):
+    """BatchNorm1d + LeakyReLU forward / backward with the folded row scale, and the contrastive loss + gradient
+    (gx_bn_stats / gx_bn_act_apply / gx_bn_act_bwd / gx_simclr_loss) against autograd of the oracle's formulas"""
+    from ganecdotes_b200 import _lib as L
+    torch.manual_seed(n2 + c)
+    hraw = torch.randn(n2, c) * 3
+    rs = torch.rand(n2) + 0.5
+    gamma, beta = torch.rand(c) + 0.5, 0.1 * torch.randn(c)
+    da = torch.randn(n2, c)
+    hr = hraw.clone().requires_grad_(True)
+    gr, br = gamma.clone().requires_grad_(True), beta.clone().requires_grad_(True)
+    h = hr * rs[:, None]
+    mean, var = h.mean(0), h.var(0, unbiased=False)
+    a_ref = torch.nn.functional.leaky_relu((h - mean) / torch.sqrt(var + 1e-5) * gr + br, 0.01)
+    a_ref.backward(da)
+    run_m, run_v = torch.zeros(c).cuda(), torch.ones(c).cuda()
+    m, isd = L.bn_stats(hraw.cuda(), rs.cuda(), 1e-5, run_m, run_v, 0.1)
+    torch.testing.assert_close(m.cpu(), mean.detach(), rtol=1e-5, atol=1e-6)
+    torch.testing.assert_close(run_v.cpu(), 0.9 + 0.1 * h.detach().var(0, unbiased=True), rtol=1e-5, atol=1e-6)
+    a, a_hi, a_lo = L.bn_act_apply(hraw.cuda(), rs.cuda(), m, isd, gamma.cuda(), beta.cuda(), 0.01)
+    torch.testing.assert_close(a.cpu(), a_ref.detach(), rtol=1e-4, atol=1e-5)
+    torch.testing.assert_close((a_hi.float() + a_lo.float()).cpu(), a_ref.detach(), rtol=1e-4, atol=1e-4)
+    dhs, dg, db = L.bn_act_bwd(da.cuda(), hraw.cuda(), rs.cuda(), m, isd, gamma.cuda(), beta.cuda(), 0.01)
+    torch.testing.assert_close(dhs.cpu(), hr.grad, rtol=2e-3, atol=2e-5)
+    torch.testing.assert_close(dg.cpu(), gr.grad, rtol=1e-3, atol=1e-4)
+    torch.testing.assert_close(db.cpu(), br.grad, rtol=1e-3, atol=1e-4)
+    for temp in (1.0, 0.5):
+        z = torch.randn(n2, c, requires_grad=True)
+        ref = O.simclr_loss(z, temp)
+        ref.backward()
+        loss, dz = L.simclr_loss(z.detach().cuda(), temp)
+        assert abs(loss.item() - ref.item()) < 1e-5 * abs(ref.item()) + 1e-6
+        torch.testing.assert_close(dz.cpu(), z.grad, rtol=2e-3, atol=1e-6)
+
+
+def test_simclr_pretrain_and_codes_match_reference_golden(gen, tmp_path):
+    """SimCLRClustering on the recorded draws of the seeded run of the UNMODIFIED reference (tests/golden/simclr.npz):
+    per-iteration losses, final weights + BatchNorm running statistics, eval-mode codes and label map."""
+    from ganecdotes_b200.hfc_with_simclr import SimCLRClustering, SimCLRHead, simclr_train_step
+    from ganecdotes_b200.hfc_with_simclr.simclr_clustering import SimCLRDraws
+    g = load("simclr")
+    hlen, nclasses, batch, niters, nl = [int(v) for v in g["cfg"]]
+    pstd = [float(v) for v in g["perturb_std"]]
+    mc = types.SimpleNamespace(num_latents_for_mean=64, truncation=0.7, latent_dim=64, image_size=16)
+    cfg = dict(perturb_args=dict(truncation=0.7, n_layers=nl, n_samples=1, layer_no=None, perturb_std=pstd),
+               simclr_args=dict(num_iters=niters, batch_size=batch, patch_size=100, hf_interp='nearest', trust_coeff=0.01,
+                                train_args=dict(lr=0.01, momentum=0.9), temperature=1.0, nclasses=nclasses, hlen=hlen,
+                                epoch_print_freq=1, max_masks=4), train=True, layer_hf_dim=[512, 1024, 1024])
+    obj = SimCLRClustering(gen, mc, out_dir=str(tmp_path), device='cuda', tb=None, **cfg)
+    obj.mean_latent = g["mean_latent"].cuda()
+    proj = torch.nn.Sequential(torch.nn.Linear(hlen, nclasses, bias=False), torch.nn.BatchNorm1d(nclasses),
+                               torch.nn.LeakyReLU(inplace=True), torch.nn.Linear(nclasses, nclasses, bias=False)).cuda()
+    with torch.no_grad():
+        proj[0].weight.copy_(g["init_w1"]); proj[1].weight.copy_(g["init_bn_w"])
+        proj[1].bias.copy_(g["init_bn_b"]); proj[3].weight.copy_(g["init_w2"])
+    head = SimCLRHead(proj, 0.01, 0.9, 0.01)
+    for e in range(niters):
+        draws = SimCLRDraws(z=g[f"s{e}_z"], layer_no=[int(g[f"s{e}_s_layer"]), int(g[f"s{e}_t_layer"])],
+                            pert_z=torch.stack([g[f"s{e}_s_pert_z"], g[f"s{e}_t_pert_z"]]),
+                            angle=[float(g[f"s{e}_s_angle"]), float(g[f"s{e}_t_angle"])],
+                            flip=[bool(g[f"s{e}_s_flip"]), bool(g[f"s{e}_t_flip"])], perm=g[f"s{e}_perm"].long())
+        loss, _ = simclr_train_step(gen, head, obj.mean_latent, draws, hlen, batch, 1.0, 0.7, pstd)
+        assert abs(loss.item() - float(g["losses"][e])) < 2e-3 * abs(float(g["losses"][e])), (e, loss.item())
+    for got, key in zip(head.params, ("final_w1", "final_bn_w", "final_bn_b", "final_w2")):
+        ref = g[key]
+        upd = (ref - g[key.replace("final", "init")]).norm().item()
+        assert (got.cpu() - ref).norm().item() < 5e-2 * upd + 1e-7, key          # the UPDATE agrees within 5 %
+    torch.testing.assert_close(proj[1].running_mean.cpu(), g["final_bn_mean"], rtol=2e-3, atol=1e-5)
+    torch.testing.assert_close(proj[1].running_var.cpu(), g["final_bn_var"], rtol=2e-3, atol=1e-5)
+    obj.projection = proj.eval()
+    preds, labels = obj.predict_simclr_codes(g["pred_w"].cuda())
+    assert tuple(preds.shape) == tuple(g["preds"].shape) and labels.dtype == torch.int64
+    scale = g["preds"].abs().max().item()
+    assert (preds.cpu() - g["preds"]).abs().max().item() < 5e-3 * scale
+    assert (labels.cpu() != g["labels"]).float().mean().item() < 0.02
+    # API: pretrain() from the CPU random stream writes the reference's artefact
+    obj2 = SimCLRClustering(gen, mc, out_dir=str(tmp_path), device='cuda', tb=None, **cfg)
+    obj2.pretrain(None)
+    assert os.path.exists(os.path.join(str(tmp_path), "projection.pt"))
+    p2, l2 = obj2.predict_simclr_codes(g["pred_w"].cuda())
+    assert torch.isfinite(p2).all() and tuple(l2.shape) == (1, 16, 16)
