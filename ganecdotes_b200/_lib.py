@@ -81,6 +81,8 @@ _SIGNATURES = {
     "gx_set_sm_budget": ([_I, _I], _I),
     "gx_upfirdn2d": ([_P, _P, _P] + [_I] * 14 + [_P], _I),
     "gx_fused_bias_act": ([_P, _P, _P, _P, _LL, _I, _I, _I, _I, _F, _F, _P], _I),
+    "gx_upfirdn2d_t": ([_I, _P, _P, _P] + [_I] * 14 + [_P], _I),
+    "gx_fused_bias_act_t": ([_I, _P, _P, _P, _P, _LL, _I, _I, _I, _I, _F, _F, _P], _I),
     "gx_pixel_norm": ([_P, _P, _I, _I, _P], _I),
     "gx_equal_linear": ([_P, _LL, _P, _P, _P, _I, _I, _I, _F, _F, _I, _P], _I),
     "gx_truncate": ([_P, _P, _P, _LL, _I, _F, _P], _I),
@@ -124,6 +126,8 @@ _SIGNATURES = {
     "gx_loss_max_parts": ([], _I),
     "gx_swav_loss": ([_P, _P, _LL, _I, _LL, _F, _F, _P, _P, _F, _P, _P, C.POINTER(_I), _P, _P, _P, _P, _LL, _P, _P,
                       _P], _I),
+    "gx_im2col": ([_P] + [_I] * 14 + [_LL, _P, _P], _I),
+    "gx_col2im": ([_P] + [_I] * 14 + [_LL, _P, _P], _I),
     "gx_recip": ([_P, _LL, _F, _I, _P, _P], _I),
     "gx_bn_stats": ([_P, _LL, _P, _I, _I, _F, _P, _P, _P, _P, _F, _P], _I),
     "gx_bn_act_apply": ([_P, _LL, _P, _LL, _I, _P, _P, _P, _P, _F, _P, _P, _P, _P], _I),
@@ -259,32 +263,49 @@ class timed:
 # op wrappers (raw): callers pass contiguous CUDA tensors of the right dtype
 # ----------------------------------------------------------------------------------------
 
+_DTYPE_CODE = {torch.float32: 0, torch.float16: 1, torch.float64: 2}
+
+
+def _typed(t, name, dtype):
+    if t is None:
+        return None
+    if not t.is_cuda or t.dtype != dtype or not t.is_contiguous():
+        raise GxError(f"{name} must be a contiguous CUDA tensor of dtype {dtype}")
+    return t
+
+
 def upfirdn2d_raw(x4, kernel, up_x, up_y, down_x, down_y, px0, px1, py0, py1):
-    """x4: [major, in_h, in_w, minor] -> [major, out_h, out_w, minor]"""
+    """x4: [major, in_h, in_w, minor] -> [major, out_h, out_w, minor]; float32, float16 or float64 (taps in the
+    input's type, like the reference's dispatch)"""
     lib = load()
-    _f32(x4, "input"), _f32(kernel, "kernel")
+    if x4.dtype not in _DTYPE_CODE:
+        raise GxError("upfirdn2d: float32, float16 or float64 input")
+    _typed(x4, "input", x4.dtype), _typed(kernel, "kernel", x4.dtype)
     major, in_h, in_w, minor = x4.shape
     kh, kw = kernel.shape
     out_h = (in_h * up_y + py0 + py1 - kh + down_y) // down_y
     out_w = (in_w * up_x + px0 + px1 - kw + down_x) // down_x
     if out_h <= 0 or out_w <= 0:
         raise GxError("upfirdn2d: empty output")
-    out = torch.empty((major, out_h, out_w, minor), dtype=torch.float32, device=x4.device)
+    out = torch.empty((major, out_h, out_w, minor), dtype=x4.dtype, device=x4.device)
     if out.numel():
-        _check(lib.gx_upfirdn2d(_ptr(x4), _ptr(kernel), _ptr(out), major, in_h, in_w, minor, kh, kw, up_x, up_y,
-                                down_x, down_y, px0, px1, py0, py1, _stream()), "gx_upfirdn2d")
+        _check(lib.gx_upfirdn2d_t(_DTYPE_CODE[x4.dtype], _ptr(x4), _ptr(kernel), _ptr(out), major, in_h, in_w, minor, kh,
+                                  kw, up_x, up_y, down_x, down_y, px0, px1, py0, py1, _stream()), "gx_upfirdn2d")
         _count()
     return out
 
 
 def fused_bias_act_raw(x, bias, refer, act, grad, alpha, scale):
+    """float32, float16 or float64 (bias / refer in the input's type)"""
     lib = load()
-    _f32(x, "input")
+    if x.dtype not in _DTYPE_CODE:
+        raise GxError("fused_bias_act: float32, float16 or float64 input")
+    _typed(x, "input", x.dtype)
     out = torch.empty_like(x)
     if x.numel() == 0:
         return out
     if bias is not None:
-        _f32(bias, "bias")
+        _typed(bias, "bias", x.dtype)
         step_b = 1
         for d in x.shape[2:]:
             step_b *= d
@@ -294,9 +315,9 @@ def fused_bias_act_raw(x, bias, refer, act, grad, alpha, scale):
     else:
         step_b = size_b = 1
     if refer is not None:
-        _f32(refer, "refer")
-    _check(lib.gx_fused_bias_act(_ptr(x), _ptr(bias), _ptr(refer), _ptr(out), x.numel(), step_b, size_b, act, grad,
-                                 float(alpha), float(scale), _stream()), "gx_fused_bias_act")
+        _typed(refer, "refer", x.dtype)
+    _check(lib.gx_fused_bias_act_t(_DTYPE_CODE[x.dtype], _ptr(x), _ptr(bias), _ptr(refer), _ptr(out), x.numel(), step_b,
+                                   size_b, act, grad, float(alpha), float(scale), _stream()), "gx_fused_bias_act")
     _count()
     return out
 
@@ -468,7 +489,11 @@ def modconv(x_hi, x_lo, w_hi, w_lo, cout, upsample, passes, demod=None, noise=No
     d.block_n, d.stages = block_n, stages
     d.dilation = int(dilation)
     d.cluster_pair = int(pair)
-    with timed(tag + ("_up" if upsample else ""), 2.0 * b * h * w * 9 * (cin_true or cin) * cout):
+    npl = 2 if passes == 3 else 1
+    conv_bytes = (2.0 * npl * b * h * w * cin_ld + 4.0 * b * ho * wo * cout
+                  + (2.0 * (2 if next_lo is not None else 1) * b * ho * wo * next_ld if next_hi is not None else 0.0)
+                  + 2.0 * npl * 9 * cin_ld * cout)          # input planes once + outputs + weights
+    with timed(tag + ("_up" if upsample else ""), 2.0 * b * h * w * 9 * (cin_true or cin) * cout, conv_bytes):
         _check(lib.gx_modconv(C.byref(d), _stream()), "gx_modconv")
     _count()
     return out, next_hi, next_lo
@@ -980,6 +1005,28 @@ def swav_loss(s_s, s_t, inv_eps, inv_temp, la_s, la_t, grad_scale, want_lo=False
         _check(lib.gx_sinkhorn_reduce(_ptr(db_parts), nparts.value, k, _ptr(db), _stream()), "gx_sinkhorn_reduce")
         _count()
     return loss_parts, (ds_s_hi, ds_s_lo), (ds_t_hi, ds_t_lo), db, (fs, ft)
+
+
+def im2col(x, kh, kw, stride, padding, dilation, ho, wo, ld):
+    """x [b,c,h,w] fp32 -> cols [b*ho*wo, ld] fp32 (gx_im2col)"""
+    _f32(x, "x")
+    b, c, h, w = x.shape
+    cols = torch.empty((b * ho * wo, ld), dtype=torch.float32, device=x.device)
+    _check(load().gx_im2col(_ptr(x), b, c, h, w, kh, kw, stride[0], stride[1], padding[0], padding[1], dilation[0],
+                            dilation[1], ho, wo, ld, _ptr(cols), _stream()), "gx_im2col")
+    _count()
+    return cols
+
+
+def col2im(cols, shape, kh, kw, stride, padding, dilation, ho, wo):
+    """cols [b*ho*wo, ld] fp32 -> x [b,c,h,w] fp32: the adjoint of im2col (gx_col2im)"""
+    _f32(cols, "cols")
+    b, c, h, w = shape
+    x = torch.empty((b, c, h, w), dtype=torch.float32, device=cols.device)
+    _check(load().gx_col2im(_ptr(cols), b, c, h, w, kh, kw, stride[0], stride[1], padding[0], padding[1], dilation[0],
+                            dilation[1], ho, wo, cols.stride(0), _ptr(x), _stream()), "gx_col2im")
+    _count()
+    return x
 
 
 def recip_clamp(x, eps):

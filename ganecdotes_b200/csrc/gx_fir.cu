@@ -418,6 +418,129 @@ __global__ void torgb_kernel(const float* __restrict__ x, const float* __restric
   }
 }
 
+// --------------------------------------------------------------------------
+// half / double instantiations of the two native ops (the reference dispatches them with
+// AT_DISPATCH_FLOATING_TYPES_AND_HALF, upfirdn2d_kernel.cu:321, fused_bias_act_kernel.cu:127): same per-element
+// kernels on the storage type T, arithmetic in A (float for half, double for double).
+// --------------------------------------------------------------------------
+template <typename T> struct Acc { using type = float; };
+template <> struct Acc<double> { using type = double; };
+template <typename T> __device__ __forceinline__ typename Acc<T>::type ldv(const T* p) { return (typename Acc<T>::type)(*p); }
+template <> __device__ __forceinline__ float ldv<__half>(const __half* p) { return __half2float(*p); }
+template <typename T, typename A> __device__ __forceinline__ T stv(A v) { return (T)v; }
+template <> __device__ __forceinline__ __half stv<__half, float>(float v) { return __float2half_rn(v); }
+
+template <typename T>
+__global__ void upfirdn2d_typed_kernel(const T* __restrict__ in, const T* __restrict__ kern, T* __restrict__ out,
+                                       const UpfirParams p, long long total) {
+  using A = typename Acc<T>::type;
+  for (long long idx = (long long)blockIdx.x * blockDim.x + threadIdx.x; idx < total;
+       idx += (long long)gridDim.x * blockDim.x) {
+    long long r = idx;
+    const int mi = (int)(r % p.minor); r /= p.minor;
+    const int ox = (int)(r % p.out_w); r /= p.out_w;
+    const int oy = (int)(r % p.out_h); r /= p.out_h;
+    const int mj = (int)r;
+    const int base_y = oy * p.down_y - p.pad_y0;
+    const int base_x = ox * p.down_x - p.pad_x0;
+    const int ky0 = ((-base_y) % p.up_y + p.up_y) % p.up_y;
+    const int kx0 = ((-base_x) % p.up_x + p.up_x) % p.up_x;
+    A acc = (A)0;
+    const T* src = in + (long long)mj * p.in_h * p.in_w * p.minor + mi;
+    for (int ky = ky0; ky < p.kh; ky += p.up_y) {
+      const int iy = floor_div(base_y + ky, p.up_y);
+      if (iy < 0 || iy >= p.in_h) continue;
+      for (int kx = kx0; kx < p.kw; kx += p.up_x) {
+        const int ix = floor_div(base_x + kx, p.up_x);
+        if (ix < 0 || ix >= p.in_w) continue;
+        acc += ldv<T>(src + ((long long)iy * p.in_w + ix) * p.minor) *
+               ldv<T>(kern + (p.kh - 1 - ky) * p.kw + (p.kw - 1 - kx));
+      }
+    }
+    out[idx] = stv<T, A>(acc);
+  }
+}
+
+template <typename T>
+__global__ void fused_bias_act_typed_kernel(const T* __restrict__ x, const T* __restrict__ b, const T* __restrict__ ref,
+                                            T* __restrict__ out, long long n, int step_b, int size_b, int mode,
+                                            float alpha, float scale) {
+  using A = typename Acc<T>::type;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+    A v = ldv<T>(x + i);
+    if (b) v += ldv<T>(b + (i / step_b) % size_b);
+    const A rv = ref ? ldv<T>(ref + i) : (A)0;
+    A y;
+    switch (mode) {
+      default:
+      case 10: case 11: y = v; break;
+      case 12: case 32: y = (A)0; break;
+      case 30: y = (v > (A)0) ? v : v * (A)alpha; break;
+      case 31: y = (rv > (A)0) ? v : v * (A)alpha; break;
+    }
+    out[i] = stv<T, A>(y * (A)scale);
+  }
+}
+
+}  // namespace
+
+// dtype: 0 float32, 1 float16, 2 float64 (all tensors of the call, FIR taps included, in that type)
+extern "C" int gx_upfirdn2d_t(int dtype, const void* input, const void* kernel, void* out, int major, int in_h,
+                              int in_w, int minor, int kh, int kw, int up_x, int up_y, int down_x, int down_y,
+                              int pad_x0, int pad_x1, int pad_y0, int pad_y1, void* stream) {
+  if (dtype == 0)
+    return gx_upfirdn2d((const float*)input, (const float*)kernel, (float*)out, major, in_h, in_w, minor, kh, kw, up_x,
+                        up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1, stream);
+  GX_CHECK_ARG((dtype == 1 || dtype == 2) && input && kernel && out);
+  GX_CHECK_ARG(major > 0 && in_h > 0 && in_w > 0 && minor > 0 && kh > 0 && kw > 0);
+  GX_CHECK_ARG(up_x > 0 && up_y > 0 && down_x > 0 && down_y > 0);
+  UpfirParams p;
+  p.major = major; p.in_h = in_h; p.in_w = in_w; p.minor = minor; p.kh = kh; p.kw = kw;
+  p.up_x = up_x; p.up_y = up_y; p.down_x = down_x; p.down_y = down_y; p.pad_x0 = pad_x0; p.pad_y0 = pad_y0;
+  p.out_h = (in_h * up_y + pad_y0 + pad_y1 - kh + down_y) / down_y;
+  p.out_w = (in_w * up_x + pad_x0 + pad_x1 - kw + down_x) / down_x;
+  GX_CHECK_ARG(p.out_h > 0 && p.out_w > 0);
+  const long long total = (long long)major * p.out_h * p.out_w * minor;
+  int grid = (int)((total + 255) / 256);
+  const int cap = gx_sm_count() * 16;
+  if (grid > cap) grid = cap;
+  if (dtype == 1)
+    upfirdn2d_typed_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>((const __half*)input, (const __half*)kernel,
+                                                                           (__half*)out, p, total);
+  else
+    upfirdn2d_typed_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>((const double*)input, (const double*)kernel,
+                                                                           (double*)out, p, total);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+extern "C" int gx_fused_bias_act_t(int dtype, const void* input, const void* bias, const void* refer, void* out,
+                                   long long n, int step_b, int size_b, int act, int grad, float alpha, float scale,
+                                   void* stream) {
+  if (dtype == 0)
+    return gx_fused_bias_act((const float*)input, (const float*)bias, (const float*)refer, (float*)out, n, step_b, size_b,
+                             act, grad, alpha, scale, stream);
+  GX_CHECK_ARG((dtype == 1 || dtype == 2) && input && out && n >= 0);
+  if (n == 0) return GX_OK;
+  const int mode = act * 10 + grad;
+  GX_CHECK_ARG(mode == 10 || mode == 11 || mode == 12 || mode == 30 || mode == 31 || mode == 32);
+  GX_CHECK_ARG(mode != 31 || refer != nullptr);
+  if (bias) GX_CHECK_ARG(step_b > 0 && size_b > 0);
+  else { step_b = 1; size_b = 1; }
+  int grid = (int)((n + 255) / 256);
+  const int cap = gx_sm_count() * 16;
+  if (grid > cap) grid = cap;
+  if (dtype == 1)
+    fused_bias_act_typed_kernel<__half><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const __half*)input, (const __half*)bias, (const __half*)refer, (__half*)out, n, step_b, size_b, mode, alpha, scale);
+  else
+    fused_bias_act_typed_kernel<double><<<grid, 256, 0, (cudaStream_t)stream>>>(
+        (const double*)input, (const double*)bias, (const double*)refer, (double*)out, n, step_b, size_b, mode, alpha, scale);
+  GX_LAUNCH_CHECK();
+  return GX_OK;
+}
+
+namespace {
 }  // namespace
 
 extern "C" int gx_upfirdn2d(const float* input, const float* kernel, float* out, int major, int in_h, int in_w,

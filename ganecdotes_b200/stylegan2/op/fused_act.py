@@ -24,15 +24,18 @@ def fused_bias_act(input, bias, refer, act, grad, alpha, scale):
         raise RuntimeError("input must be contiguous")
     b = bias if (bias is not None and bias.numel()) else None
     r = refer if (refer is not None and refer.numel()) else None
-    x = input if input.dtype == torch.float32 else input.float()
+    # float32, float16 and float64 run natively (the reference's AT_DISPATCH_FLOATING_TYPES_AND_HALF,
+    # fused_bias_act_kernel.cu:127); anything else (bfloat16) goes through float32
+    native = input.dtype in (torch.float32, torch.float16, torch.float64)
+    x = input if native else input.float()
     if b is not None:
-        b = b.to(torch.float32).contiguous()
+        b = b.to(x.dtype).contiguous()
     if r is not None:
-        r = r.to(torch.float32).contiguous()
+        r = r.to(x.dtype).contiguous()
     if x.dim() < 2 and b is not None:
         raise RuntimeError("fused_bias_act: bias needs an input with a channel dimension")
     out = L.fused_bias_act_raw(x, b, r, int(act), int(grad), float(alpha), float(scale))
-    return out if input.dtype == torch.float32 else out.to(input.dtype)
+    return out if native else out.to(input.dtype)
 
 
 def _bias_grad(g, channel_dim_size):

@@ -35,10 +35,13 @@ def upfirdn2d_native_layout(input, kernel, up_x, up_y, down_x, down_y, pad_x0, p
         raise RuntimeError("input must be contiguous")
     if input.dim() != 4 or kernel.dim() != 2:
         raise RuntimeError("upfirdn2d: expected input [major,h,w,minor] and a 2-D kernel")
-    x = input if input.dtype == torch.float32 else input.float()
-    k = kernel if kernel.dtype == torch.float32 else kernel.float()
+    # float32, float16 and float64 run natively (the reference's AT_DISPATCH_FLOATING_TYPES_AND_HALF,
+    # upfirdn2d_kernel.cu:321), taps in the input's type; anything else (bfloat16) goes through float32
+    native = input.dtype in (torch.float32, torch.float16, torch.float64)
+    x = input if native else input.float()
+    k = kernel if kernel.dtype == x.dtype else kernel.to(x.dtype)
     out = L.upfirdn2d_raw(x, k, up_x, up_y, down_x, down_y, pad_x0, pad_x1, pad_y0, pad_y1)
-    return out if input.dtype == torch.float32 else out.to(input.dtype)
+    return out if native else out.to(input.dtype)
 
 
 class _UpFirDn(torch.autograd.Function):

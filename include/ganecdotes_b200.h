@@ -52,6 +52,16 @@ int gx_upfirdn2d(const float* input, const float* kernel, float* out, int major,
 int gx_fused_bias_act(const float* input, const float* bias, const float* refer, float* out, long long n,
                       int step_b, int size_b, int act, int grad, float alpha, float scale, void* stream);
 
+/* The same two ops on float16 / float64 tensors (dtype: 0 float32, 1 float16, 2 float64; every tensor of the call in
+ * that type, FIR taps and bias included) - the reference instantiates its kernels with
+ * AT_DISPATCH_FLOATING_TYPES_AND_HALF (upfirdn2d_kernel.cu:321, fused_bias_act_kernel.cu:127).  Arithmetic in
+ * float for float16, in double for float64. */
+int gx_upfirdn2d_t(int dtype, const void* input, const void* kernel, void* out, int major, int in_h, int in_w,
+                   int minor, int kh, int kw, int up_x, int up_y, int down_x, int down_y, int pad_x0, int pad_x1,
+                   int pad_y0, int pad_y1, void* stream);
+int gx_fused_bias_act_t(int dtype, const void* input, const void* bias, const void* refer, void* out, long long n,
+                        int step_b, int size_b, int act, int grad, float alpha, float scale, void* stream);
+
 /* ------------------------------------------------------------------------------------
  * StyleGAN2 synthesis (ref: models/stylegan2/model.py)
  * ---------------------------------------------------------------------------------- */
@@ -371,6 +381,17 @@ int gx_swav_loss(const float* s_s, const float* s_t, long long n, int k, long lo
                  float inv_temp, const float* log_a_s, const float* log_a_t, float grad_scale, float* loss_parts,
                  float* db_parts, int* nparts_out, void* ds_s_hi, void* ds_s_lo, void* ds_t_hi, void* ds_t_lo,
                  long long ldd, float* ds_s_f32, float* ds_t_f32, void* stream);
+
+/* ------------------------------------------------------------------------------------
+ * Generic convolution pieces of the conv2d_gradfix drop-in (ref: lib/gan/optim/conv2d_gradfix.py:129-270):
+ * conv2d = im2col + gx_gemm, conv_transpose2d = gx_gemm + col2im; the two maps are an adjoint pair, so gradients
+ * of any order are made of the same three calls.  x [b,c,h,w] fp32 NCHW; cols [b*ho*wo, ld] fp32, column
+ * (ci*kh + ky)*kw + kx, ld >= c*kh*kw (extra columns zero-filled by im2col, ignored by col2im).
+ * ---------------------------------------------------------------------------------- */
+int gx_im2col(const float* x, int b, int c, int h, int w, int kh, int kw, int sy, int sx, int py, int px, int dy,
+              int dx, int ho, int wo, long long ld, float* cols, void* stream);
+int gx_col2im(const float* cols, int b, int c, int h, int w, int kh, int kw, int sy, int sx, int py, int px, int dy,
+              int dx, int ho, int wo, long long ld, float* x, void* stream);
 
 /* ------------------------------------------------------------------------------------
  * SimCLR baseline head (ref: baseline/hfc_with_simclr/simclr_clustering.py:133-281, 362-401):

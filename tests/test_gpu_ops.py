@@ -940,3 +940,95 @@ def test_upfirdn2d_planar_path_vs_oracle(L, up, down, pad, shape, taps):
     got = upfirdn2d(x.cuda(), k.cuda(), up=up, down=down, pad=pad)
     assert got.shape == ref.shape
     torch.testing.assert_close(got.cpu(), ref, rtol=1e-5, atol=1e-6)
+
+
+@pytest.mark.parametrize("cfg", [
+    dict(b=2, cin=6, cout=8, hw=(9, 11), k=3, stride=1, padding=1, dilation=1, groups=1),
+    dict(b=1, cin=8, cout=12, hw=(16, 16), k=3, stride=2, padding=1, dilation=1, groups=2),
+    dict(b=2, cin=4, cout=4, hw=(10, 7), k=(3, 2), stride=(1, 2), padding=(2, 0), dilation=(2, 1), groups=1),
+    dict(b=3, cin=16, cout=16, hw=(8, 8), k=1, stride=1, padding=0, dilation=1, groups=1),
+])
+def test_conv2d_gradfix_matches_torch_to_second_order(L, cfg):
+    """conv2d / conv_transpose2d of the conv2d_gradfix drop-in (ref lib/gan/optim/conv2d_gradfix.py) against
+    torch.nn.functional (what the reference itself calls on torch >= 1.9): values, first-order gradients and a
+    gradient penalty (gradient of a squared gradient norm: second order), plus no_weight_gradients()."""
+    import torch.nn.functional as F
+    from ganecdotes_b200.stylegan2.op import conv2d_gradfix as G
+    old = (torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32)
+    torch.backends.cuda.matmul.allow_tf32 = torch.backends.cudnn.allow_tf32 = False
+    try:
+        g = torch.Generator().manual_seed(cfg["cin"] + cfg["cout"])
+        k = cfg["k"] if isinstance(cfg["k"], tuple) else (cfg["k"], cfg["k"])
+        kw = dict(stride=cfg["stride"], padding=cfg["padding"], dilation=cfg["dilation"], groups=cfg["groups"])
+
+        def mk(*shape):
+            return torch.randn(*shape, generator=g).cuda().requires_grad_(True)
+        for transpose in (False, True):
+            if transpose:
+                x = mk(cfg["b"], cfg["cin"], *cfg["hw"])
+                w = mk(cfg["cin"], cfg["cout"] // cfg["groups"], *k)
+                bias = mk(cfg["cout"])
+                s = cfg["stride"] if isinstance(cfg["stride"], tuple) else (cfg["stride"],) * 2
+                opad = tuple(1 if si > 1 else 0 for si in s)
+                f_ref = lambda x_, w_, b_: F.conv_transpose2d(x_, w_, b_, output_padding=opad, **kw)
+                f_got = lambda x_, w_, b_: G.conv_transpose2d(x_, w_, b_, output_padding=opad, **kw)
+            else:
+                x = mk(cfg["b"], cfg["cin"], *cfg["hw"])
+                w = mk(cfg["cout"], cfg["cin"] // cfg["groups"], *k)
+                bias = mk(cfg["cout"])
+                f_ref = lambda x_, w_, b_: F.conv2d(x_, w_, b_, **kw)
+                f_got = lambda x_, w_, b_: G.conv2d(x_, w_, b_, **kw)
+            y_ref, y_got = f_ref(x, w, bias), f_got(x, w, bias)
+            assert y_got.shape == y_ref.shape
+            scale = y_ref.abs().max().item()
+            assert (y_got - y_ref).abs().max().item() < 1e-4 * scale
+            go = torch.randn(y_ref.shape, generator=g).cuda()
+            r1 = torch.autograd.grad(y_ref, (x, w, bias), go, create_graph=True)
+            g1 = torch.autograd.grad(y_got, (x, w, bias), go, create_graph=True)
+            for a, b_ in zip(g1, r1):
+                assert (a - b_).abs().max().item() < 2e-4 * b_.abs().max().item()
+            # gradient penalty: d/d(w, x) of |dy/dx|^2  (second order through the conv and through its weight gradient)
+            pen_ref = r1[0].pow(2).sum() + r1[1].pow(2).sum()
+            pen_got = g1[0].pow(2).sum() + g1[1].pow(2).sum()
+            r2 = torch.autograd.grad(pen_ref, (x, w))
+            g2 = torch.autograd.grad(pen_got, (x, w))
+            for a, b_ in zip(g2, r2):
+                assert (a - b_).abs().max().item() < 5e-4 * b_.abs().max().item()
+            with G.no_weight_gradients():
+                y = f_got(x, w, bias)
+                gx, = torch.autograd.grad(y, (x,), go, retain_graph=True)
+                assert (gx - r1[0].detach()).abs().max().item() < 2e-4 * r1[0].abs().max().item()
+                assert torch.autograd.grad(y, (w,), go, allow_unused=True)[0] is None
+    finally:
+        torch.backends.cuda.matmul.allow_tf32, torch.backends.cudnn.allow_tf32 = old
+
+
+def test_native_ops_half_and_double(L):
+    """float16 / float64 instantiations of upfirdn2d and fused_bias_act (the reference's
+    AT_DISPATCH_FLOATING_TYPES_AND_HALF) - against the reference's own CUDA kernels when oracle/_ref is built, and
+    against the fp64 oracle formulas in any case"""
+    from ganecdotes_b200.stylegan2.op import upfirdn2d, fused_leaky_relu
+    from oracle import build_ref
+    up, fb = build_ref.load("ref_upfirdn2d"), build_ref.load("ref_fused_bias_act")
+    g = torch.Generator().manual_seed(7)
+    x = torch.randn(2, 3, 20, 22, generator=g, dtype=torch.float64)
+    k = O.make_fir_kernel([1, 3, 3, 1]).double() * 4
+    bias = torch.randn(3, generator=g, dtype=torch.float64)
+    for dt, tol in ((torch.float64, 1e-12), (torch.float16, 4e-3)):
+        for upf, down, pad in ((2, 1, (2, 1)), (1, 2, (1, 1)), (1, 1, (2, 1))):
+            ref = O.upfirdn2d(x, k, up=upf, down=down, pad=pad)
+            got = upfirdn2d(x.cuda().to(dt), k.cuda().to(dt), up=upf, down=down, pad=pad)
+            assert got.dtype == dt
+            assert (got.double().cpu() - ref).abs().max().item() < tol * ref.abs().max().item()
+            if up is not None:
+                xr = x.cuda().to(dt).reshape(-1, 20, 22, 1).contiguous()
+                r2 = up.upfirdn2d(xr, k.cuda().to(dt), upf, upf, down, down, pad[0], pad[1], pad[0], pad[1])
+                assert (got.reshape(r2.shape).double() - r2.double()).abs().max().item() <= 2 * tol * ref.abs().max().item()
+        ref = O.fused_leaky_relu(x, bias)
+        got = fused_leaky_relu(x.cuda().to(dt), bias.cuda().to(dt))
+        assert got.dtype == dt
+        assert (got.double().cpu() - ref).abs().max().item() < tol * ref.abs().max().item()
+        if fb is not None:
+            r2 = fb.fused_bias_act(x.cuda().to(dt), bias.cuda().to(dt), torch.empty(0, device="cuda", dtype=dt), 3, 0, 0.2,
+                                   2 ** 0.5)
+            assert (got.double() - r2.double()).abs().max().item() <= 2 * tol * ref.abs().max().item()
