@@ -1029,7 +1029,9 @@ def test_native_ops_half_and_double(L):
         ref = O.fused_leaky_relu(x, bias)
         got = fused_leaky_relu(x.cuda().to(dt), bias.cuda().to(dt))
         assert got.dtype == dt
-        assert (got.double().cpu() - ref).abs().max().item() < tol * ref.abs().max().item()
+        # alpha and scale cross the ABI as C floats, like the reference's op (fused_bias_act.cpp:18-24): sqrt(2) is
+        # float32-accurate even in the float64 instantiation
+        assert (got.double().cpu() - ref).abs().max().item() < max(tol, 1e-7) * ref.abs().max().item()
         if fb is not None:
             r2 = fb.fused_bias_act(x.cuda().to(dt), bias.cuda().to(dt), torch.empty(0, device="cuda", dtype=dt), 3, 0, 0.2,
                                    2 ** 0.5)
