@@ -1115,10 +1115,12 @@ def larc_sgd_(p, g, buf, lr, momentum, trust, weight_decay, eps, first_step, nor
     _count(2)
 
 
-def argmax_rows(x):
+def argmax_rows(x, out=None):
     lib = load()
     n, c = x.shape
-    labels = torch.empty((n,), dtype=torch.int64, device=x.device)
+    labels = out if out is not None else torch.empty((n,), dtype=torch.int64, device=x.device)
+    if labels.dtype != torch.int64 or labels.numel() != n or not labels.is_contiguous():
+        raise GxError("argmax_rows: out must be a contiguous int64 tensor of n elements")
     _check(lib.gx_argmax_rows(_ptr(x), n, c, x.stride(0), _ptr(labels), _stream()), "gx_argmax_rows")
     _count()
     return labels

@@ -228,7 +228,7 @@ class SimCLRClustering(object):
         w = input_latent.to(dev).float()
         mean = self.mean_latent.reshape(-1).float().contiguous()
         wt = L.truncate(w.contiguous(), mean, self.model_config.truncation) if self.model_config.truncation < 1 else w
-        latent = wt.unsqueeze(1).repeat(1, self.model.n_latent, 1) if wt.dim() == 2 else wt
+        latent = wt.unsqueeze(1).expand(-1, self.model.n_latent, -1) if wt.dim() == 2 else wt
         _, feats = self.model.synthesize(latent, None, need_image=False)
         b, h = latent.shape[0], self.model.size
         hlen, c = self.simclr_args['hlen'], lin1.weight.shape[0]
@@ -255,5 +255,5 @@ class SimCLRClustering(object):
                                            want_f32=False)
             zc = codes[i0 * h * h: i1 * h * h]
             L.gemm(a_hi, a_lo, w2_hi, w2_lo, n, cout, c, 3, out=zc, tag="gemm_simclr", pair=True)
-            labels[i0 * h * h: i1 * h * h] = L.argmax_rows(zc)
+            L.argmax_rows(zc, out=labels[i0 * h * h: i1 * h * h])
         return codes.view(b, h, h, cout).permute(0, 3, 1, 2), labels.view(b, h, h)

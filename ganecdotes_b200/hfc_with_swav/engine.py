@@ -762,7 +762,7 @@ def predict_codes(gen, w_proj, w, mean_latent, truncation, hlen, passes=3, image
     mean = mean_latent.reshape(-1).float().contiguous()
     w = w.to(dev).float().contiguous()
     wt = L.truncate(w, mean, truncation) if truncation < 1 else w
-    latent = wt.unsqueeze(1).repeat(1, gen.n_latent, 1) if wt.dim() == 2 else wt
+    latent = wt.unsqueeze(1).expand(-1, gen.n_latent, -1) if wt.dim() == 2 else wt      # broadcast W+: no copy
     _, feats = gen.synthesize(latent, None, need_image=False)
     b = latent.shape[0]
     h = wd = gen.size
@@ -781,7 +781,7 @@ def predict_codes(gen, w_proj, w, mean_latent, truncation, hlen, passes=3, image
         pl = (z_hi[i0 * h * wd: i1 * h * wd], z_lo[i0 * h * wd: i1 * h * wd]) if want_planes else None
         project_all_pixels(wp_hi, wp_lo, sub, i1 - i0, h, wd, hlen, passes, out=zc, out_planes=pl,
                            bilinear=hf_interp == 'bilinear')
-        labels[i0 * h * wd: i1 * h * wd] = L.argmax_rows(zc)
+        L.argmax_rows(zc, out=labels[i0 * h * wd: i1 * h * wd])
     preds = z.view(b, h, wd, c).permute(0, 3, 1, 2)
     if want_planes:
         return preds, labels.view(b, h, wd), (z_hi, z_lo)

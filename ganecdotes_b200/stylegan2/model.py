@@ -323,7 +323,9 @@ class Generator(nn.Module):
         """latent: W+ [B, n_latent, style_dim].  Returns (image NCHW or None, [NHWC fp32 features]).
 
         ref model.py:622-648 (block loop), :426-432 (StyledConv), :447-454 (ToRGB)."""
-        latent = latent.float().contiguous()
+        latent = latent.float()
+        if latent.stride(-1) != 1:          # rows of W+ are read in place (a broadcast W+ is an expand(), no copy)
+            latent = latent.contiguous()
         b = latent.shape[0]
         dev = latent.device
         if noise is None:
