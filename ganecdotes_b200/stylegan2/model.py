@@ -342,7 +342,11 @@ class Generator(nn.Module):
             preps.append((w_hi, w_lo))
         passes = self.passes
         want_lo = passes == 3
-        const = self.input.input.detach().permute(0, 2, 3, 1).contiguous()
+        ci = self.input.input
+        key = (ci.data_ptr(), ci._version, ci.device)
+        if getattr(self, "_const_key", None) != key:      # NHWC copy of the learned constant, refreshed when it changes
+            self._const_nhwc, self._const_key = ci.detach().permute(0, 2, 3, 1).contiguous(), key
+        const = self._const_nhwc
         x_hi, x_lo = L.modulate_split(const, styles[0], b, want_lo)
         feats = []
         image = None
