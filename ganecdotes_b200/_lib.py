@@ -88,7 +88,7 @@ _SIGNATURES = {
     "gx_truncate": ([_P, _P, _P, _LL, _I, _F, _P], _I),
     "gx_view_wplus": ([_P, _P, _P, _P, _P, _F, _I, _I, _I, _I, _P, _P], _I),
     "gx_pixel_segments_scratch": ([_LL], _I),
-    "gx_pixel_segments": ([_P, _P, _I, _LL, _I, _LL, _P, _P, _P, _P, _P, _P], _I),
+    "gx_pixel_segments": ([_P, _P, _I, _LL, _I, _LL, _I, _I, _P, _P, _P, _P, _P, _P], _I),
     "gx_colsum": ([_P, _I, _I, _F, _I, _P, _P], _I),
     "gx_modconv_prepare": ([_P, _F, _P, _P, _P, _I, _I, _I, _I, _P], _I),
     "gx_modconv_demod": ([_P, _P, _P, _I, _I, _I, _P], _I),
@@ -368,8 +368,9 @@ def view_wplus(w, noise_w, layer_no, sigma, mean, psi, n_latent):
     return out
 
 
-def pixel_segments(row_src, row_img, hw, npix):
-    """(ridx [P, bn], order [P*bn], seg_off [npix+1]) - gx_pixel_segments; int32 device tensors"""
+def pixel_segments(row_src, row_img, hw, npix, patches_per_group=0, img_group_stride=0):
+    """(ridx [P, bn], order [P*bn], seg_off [npix+1]) - gx_pixel_segments; int32 device tensors.  Several views
+    stacked along the patch dim: view v = patch // patches_per_group, its images start at v * img_group_stride."""
     lib = load()
     patches, bn = row_src.shape
     dev = row_src.device
@@ -380,8 +381,9 @@ def pixel_segments(row_src, row_img, hw, npix):
     seg_off = torch.empty((npix + 1,), dtype=torch.int32, device=dev)
     counts = torch.empty((npix,), dtype=torch.int32, device=dev)
     scratch = torch.empty((lib.gx_pixel_segments_scratch(npix),), dtype=torch.int32, device=dev)
-    _check(lib.gx_pixel_segments(_ptr(row_src), _ptr(row_img), patches, bn, int(hw), int(npix), _ptr(ridx),
-                                 _ptr(counts), _ptr(scratch), _ptr(seg_off), _ptr(order), _stream()),
+    _check(lib.gx_pixel_segments(_ptr(row_src), _ptr(row_img), patches, bn, int(hw), int(npix), int(patches_per_group),
+                                 int(img_group_stride), _ptr(ridx), _ptr(counts), _ptr(scratch), _ptr(seg_off),
+                                 _ptr(order), _stream()),
            "gx_pixel_segments")
     _count(6)
     return ridx, order, seg_off

@@ -10,11 +10,13 @@ namespace {
 
 // ridx[p*bn + j] = row_img[j]*hw + row_src[p*bn + j]  (or -1 on rotation fill); counts[pixel] += 1
 __global__ void pixel_keys_kernel(const int* __restrict__ row_src, const int* __restrict__ row_img, long long total,
-                                  long long bn, int hw, int* __restrict__ ridx, int* __restrict__ counts) {
+                                  long long bn, int hw, int patches_per_group, int img_group_stride,
+                                  int* __restrict__ ridx, int* __restrict__ counts) {
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     const int src = row_src[i];
-    const int key = src >= 0 ? row_img[i % bn] * hw + src : -1;
+    const int img = row_img[i % bn] + (int)((i / bn) / patches_per_group) * img_group_stride;
+    const int key = src >= 0 ? img * hw + src : -1;
     ridx[i] = key;
     if (key >= 0) atomicAdd(counts + key, 1);
   }
@@ -178,16 +180,18 @@ colsum_scale_kernel(const float* __restrict__ parts, int nparts, int k, float sc
 }  // namespace
 
 extern "C" int gx_pixel_segments(const int* row_src, const int* row_img, int patches, long long bn, int hw,
-                                 long long npix, int* ridx, int* counts, int* tile_scratch, int* seg_off, int* order,
-                                 void* stream) {
+                                 long long npix, int patches_per_group, int img_group_stride, int* ridx, int* counts,
+                                 int* tile_scratch, int* seg_off, int* order, void* stream) {
   GX_CHECK_ARG(row_src && row_img && ridx && counts && tile_scratch && seg_off && order);
+  if (patches_per_group <= 0) { patches_per_group = patches; img_group_stride = 0; }
   GX_CHECK_ARG(patches > 0 && bn > 0 && hw > 0 && npix > 0 && npix < (1LL << 31) && patches * bn < (1LL << 31));
   cudaStream_t st = (cudaStream_t)stream;
   const long long total = (long long)patches * bn;
   const int ntiles = gx_cdiv(npix, SCAN_TILE);
   const int grid = (int)min((long long)gx_sm_count() * 8, (total + 255) / 256);
   GX_CHECK_CUDA(cudaMemsetAsync(counts, 0, (size_t)npix * sizeof(int), st));
-  pixel_keys_kernel<<<grid, 256, 0, st>>>(row_src, row_img, total, bn, hw, ridx, counts);
+  pixel_keys_kernel<<<grid, 256, 0, st>>>(row_src, row_img, total, bn, hw, patches_per_group, img_group_stride, ridx,
+                                          counts);
   scan_tile_sums_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(counts, npix, tile_scratch);
   scan_tile_offsets_kernel<<<1, SCAN_THREADS, 0, st>>>(tile_scratch, ntiles, seg_off + npix);
   scan_apply_kernel<<<ntiles, SCAN_THREADS, 0, st>>>(counts, npix, tile_scratch, seg_off);

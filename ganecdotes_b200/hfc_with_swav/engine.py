@@ -541,6 +541,7 @@ class StepInputs:
     zcat: Optional[torch.Tensor] = None      # [B + 2B + 2B, D]: latents, view-s draws, view-t draws (one upload)
     layer_no: Optional[torch.Tensor] = None  # int32 [2B]: perturbed layer per (view, latent)
     sigma: Optional[torch.Tensor] = None     # fp32 [2B]: perturb_std of that layer
+    rows_both: Optional[torch.Tensor] = None  # int32 [2P, B*N]: row_src of view s then view t (one upload)
 
 
 def use_dedup(cfg: StepConfig, out_h, out_w) -> bool:
@@ -587,11 +588,17 @@ def prepare_step_inputs(gen, draws: StepDraws, cfg: StepConfig, device, stream=N
     layer_no = _upload(torch.tensor(lno, dtype=torch.int32), device)
     sigma = _upload(torch.tensor(sig, dtype=torch.float32), device)
     nbytes += zcat.numel() * 4 + 8 * len(lno)
+    host_rows = []
     for vi, (name, view) in enumerate((("s", draws.view_s), ("t", draws.view_t))):
         views[name] = (list(view.layer_no), zcat[b + 2 * b * vi: b + 2 * b * (vi + 1)])
-        rs, ri = build_row_indices(out_h, out_w, view, draws.perms, cfg.patch_size, device)
-        rows[name] = (rs, ri)
-        nbytes += rs.numel() * 4 + ri.numel() * 4
+        host_rows.append(build_row_indices(out_h, out_w, view, draws.perms, cfg.patch_size, "cpu"))
+    # one upload for both views: [2P, B*N] source pixels (view s patches first), one image-of-sample vector
+    npatch = host_rows[0][0].shape[0]
+    rs_both = _upload(torch.cat([host_rows[0][0], host_rows[1][0]]), device)
+    ri = _upload(host_rows[0][1], device)
+    nbytes += rs_both.numel() * 4 + ri.numel() * 4
+    for vi, name in enumerate(("s", "t")):
+        rows[name] = (rs_both[vi * npatch:(vi + 1) * npatch], ri)
     dedup = {} if use_dedup(cfg, out_h, out_w) else None
     index_maps = None
     if cfg.source_pdf == 'image':
@@ -603,7 +610,7 @@ def prepare_step_inputs(gen, draws: StepDraws, cfg: StepConfig, device, stream=N
             index_maps[name] = _upload(m, device)
             nbytes += m.numel() * 4
     return StepInputs(z=zcat[:b], views=views, rows=rows, h2d_bytes=nbytes, index_maps=index_maps, dedup=dedup,
-                      zcat=zcat, layer_no=layer_no, sigma=sigma)
+                      zcat=zcat, layer_no=layer_no, sigma=sigma, rows_both=rs_both)
 
 
 def build_pixel_segments(inp: StepInputs, batch, hw):
@@ -611,22 +618,20 @@ def build_pixel_segments(inp: StepInputs, batch, hw):
     and the CSR list of the samples of every pixel (`gx_pixel_segments`: counting sort, deterministic order)."""
     if inp.dedup is None or inp.dedup:
         return
-    for name in ("s", "t"):
-        rs, ri = inp.rows[name]
-        inp.dedup[name] = L.pixel_segments(rs, ri, hw, batch * hw)
+    # both views in one call: the views' images are b apart in the 2b-image batch the synthesis runs on
+    npatch = inp.rows_both.shape[0] // 2
+    ridx, order, seg_off = L.pixel_segments(inp.rows_both, inp.rows["s"][1], hw, 2 * batch * hw, npatch, batch)
+    inp.dedup.update(ridx=ridx, order=order, seg_off=seg_off, npatch=npatch)
 
 
 def _tensors_of(inp: StepInputs):
     out = [inp.zcat, inp.layer_no, inp.sigma]
-    for rs, ri in inp.rows.values():
-        out += [rs, ri]
+    out.append(inp.rows["s"][1])
     for d in (inp.index_maps, ):
         if d:
             out += list(d.values())
-    if inp.dedup:
-        for tup in inp.dedup.values():
-            out += list(tup)
-    return [t for t in out if t.is_cuda]
+    out.append(inp.rows_both)
+    return [t for t in out if t is not None and t.is_cuda]
 
 
 @torch.no_grad()
@@ -670,7 +675,6 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
     out_h = out_w = gen.size
     build_pixel_segments(inp, b, out_h * out_w)
     dedup = inp.dedup is not None
-    allpix = {}
     if cfg.hlen % 8:
         raise ValueError("hlen must be a multiple of 8 (16-byte TMA row pitch of the bf16 operand planes)")
     n_patch_rows = b * (cfg.patch_size if cfg.patch_size is not None else out_h * out_w)
@@ -680,14 +684,14 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
                          cfg.truncation, gen.n_latent)
     _, f_both = gen.synthesize(wplus, None, need_image=cfg.need_image)
     for vi, name in enumerate(("s", "t")):
-        f = [t[vi * b:(vi + 1) * b] for t in f_both]
-        feats[name] = f
-        if dedup:
-            z_all, levels = project_all_pixels(head.wp_hi, head.wp_lo, f, b, out_h, out_w, cfg.hlen, head.passes_fwd,
-                                               want_hi_only_planes=head.passes_bwd != 3,
-                                               bilinear=cfg.hf_interp == 'bilinear')
-            dz_rows = torch.empty((cfg.num_patches * n_patch_rows, head.c), dtype=torch.float32, device=dev)
-            allpix[name] = dict(levels=levels, z=z_all, dz_rows=dz_rows)
+        feats[name] = [t[vi * b:(vi + 1) * b] for t in f_both]
+    if dedup:
+        # every pixel of BOTH views projected in one set of per-resolution GEMMs (2b images): half the launches of
+        # the small levels; rows [0, b*hw) of Z belong to view s, the rest to view t
+        z_all, levels = project_all_pixels(head.wp_hi, head.wp_lo, f_both, 2 * b, out_h, out_w, cfg.hlen,
+                                           head.passes_fwd, want_hi_only_planes=head.passes_bwd != 3,
+                                           bilinear=cfg.hf_interp == 'bilinear')
+        dz_rows = torch.empty((2 * cfg.num_patches * n_patch_rows, head.c), dtype=torch.float32, device=dev)
 
     n_local = b * (cfg.patch_size if cfg.patch_size is not None else out_h * out_w)
     n_total = n_local * world
@@ -700,7 +704,8 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
         fw = {}
         for name in ("s", "t"):
             if dedup:
-                fw[name] = scores_forward_dedup(head, allpix[name]["z"], inp.dedup[name][0][p], cfg.eps)
+                vi = 0 if name == "s" else 1
+                fw[name] = scores_forward_dedup(head, z_all, inp.dedup["ridx"][vi * cfg.num_patches + p], cfg.eps)
             else:
                 row_src, row_img = inp.rows[name]
                 fw[name] = scores_forward(head, feats[name], out_h, out_w, cfg.hlen, row_img, row_src[p], n_local,
@@ -717,8 +722,9 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
                                           la_s, la_t, grad_scale, want_lo=lo, loss_parts=loss_parts[p],
                                           db_accum=head.g_bias)
         fw["s"].pop("s"), fw["t"].pop("s")
-        for name, ds in (("s", ds_s), ("t", ds_t)):
-            out = allpix[name]["dz_rows"][p * n_local:(p + 1) * n_local] if dedup else None
+        for vi, (name, ds) in enumerate((("s", ds_s), ("t", ds_t))):
+            r0 = (vi * cfg.num_patches + p) * n_local
+            out = dz_rows[r0:r0 + n_local] if dedup else None
             scores_backward(head, fw[name], ds[0], ds[1], out)
     # loss = sum of the per-CTA partial sums of every patch / (N_global * P), into the tail of the flat gradient
     L.colsum(loss_parts, cfg.num_patches * maxp, 1, head.loss_slot, scale=grad_scale)
@@ -727,10 +733,8 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
         # prototype gradients + loss travel while the projection-weight gradient is still being folded
         pending = torch.distributed.all_reduce(head.g_flat, group=group.pg, async_op=True)
     if dedup:
-        for name in ("s", "t"):
-            ap = allpix[name]
-            project_backward_dedup(head, ap["dz_rows"], inp.dedup[name][1], inp.dedup[name][2], ap["levels"], b,
-                                   out_h, out_w, bilinear=cfg.hf_interp == 'bilinear')
+        project_backward_dedup(head, dz_rows, inp.dedup["order"], inp.dedup["seg_off"], levels, 2 * b, out_h, out_w,
+                               bilinear=cfg.hf_interp == 'bilinear')
     if group is not None:
         torch.distributed.all_reduce(head.g_proj, group=group.pg)
         pending.wait()

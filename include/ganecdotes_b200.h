@@ -300,10 +300,12 @@ int gx_view_wplus(const float* w, const float* noise_w, const int* layer_no, con
  * row_img [bn] = image of the sample.  Outputs: ridx [patches, bn] = row of Z (image*hw + pixel, or -1),
  * and the CSR list of the samples of every pixel: seg_off [npix + 1], order [patches*bn] (first seg_off[npix]
  * entries valid; ascending sample index inside a segment - deterministic).  counts [npix] and tile_scratch
- * [gx_pixel_segments_scratch(npix)] are int scratch. */
+ * [gx_pixel_segments_scratch(npix)] are int scratch.  Several views in one call: patch p belongs to view
+ * p / patches_per_group, whose images start at (p / patches_per_group) * img_group_stride (0, 0: one view). */
 int gx_pixel_segments_scratch(long long npix);
 int gx_pixel_segments(const int* row_src, const int* row_img, int patches, long long bn, int hw, long long npix,
-                      int* ridx, int* counts, int* tile_scratch, int* seg_off, int* order, void* stream);
+                      int patches_per_group, int img_group_stride, int* ridx, int* counts, int* tile_scratch,
+                      int* seg_off, int* order, void* stream);
 
 /* out[k] = (accumulate ? out[k] : 0) + scale * sum_p parts[p,k]  (deterministic order): loss and bias-gradient
  * reductions of the per-CTA partials of gx_swav_loss. */
