@@ -186,7 +186,8 @@ class SwAVClustering(object):
 
     @staticmethod
     def broadcast_draws(draws: E.StepDraws, group):
-        """rank 0's draws of the global batch replace every other rank's (one small object broadcast per step)"""
+        """rank 0's draws of the global batch replace every other rank's (an object broadcast: for launchers that
+        cannot re-seed; `pretrain` synchronises the generators' seed once instead)"""
         import torch.distributed as dist
         box = [draws if group.rank == 0 else None]
         dist.broadcast_object_list(box, src=0, group=group.pg)
@@ -306,6 +307,12 @@ class SwAVClustering(object):
             for t in (self.projection[0].weight.data, self.prototype.weight.data, self.prototype.bias.data,
                       self.mean_latent):
                 dist.broadcast(t, src=0, group=group.pg)
+            # every rank draws the whole global batch from its own CPU generators and keeps its shard: the generators
+            # are re-seeded from one number drawn on rank 0, so the streams agree whatever the launcher seeded
+            seed = torch.randint(0, 2 ** 31 - 1, (1,), dtype=torch.int64).to(self.device)
+            dist.broadcast(seed, src=0, group=group.pg)
+            torch.manual_seed(int(seed.item()))
+            np.random.seed(int(seed.item()) % (2 ** 32))
         self._head = E.SwavHead(self.projection[0].weight.data, self.prototype.weight.data,
                                 self.prototype.bias.data, ta['lr'], ta.get('momentum', 0.0),
                                 self.swav_args['trust_coeff'], self.passes_fwd, self.passes_bwd, self.proto_f16,
@@ -323,9 +330,6 @@ class SwAVClustering(object):
         def stage_next():
             draws = self.draw_step(b_global)
             if group is not None:
-                # every rank draws the whole global batch from its own CPU generators; rank 0's draws are the ones
-                # that count (identical seeding is not assumed), each rank then keeps its shard
-                draws = self.broadcast_draws(draws, group)
                 draws = self.shard_draws(draws, group.rank, world)
             return E.prepare_step_inputs(self.model, draws, cfg, self.device, stream=side)
 
