@@ -105,7 +105,34 @@ def main():
         if rank == 0:
             print(f"DIST_CHECK world={world} K={k} losses={losses} ref={ref_losses} "
                   f"{'OK' if flag.item() == 1.0 else 'MISMATCH'}", flush=True)
+    # the public class under torchrun: SwAVClustering.pretrain shards `batch_latents` over the ranks; deliberately
+    # DIFFERENT seeds per rank (the class broadcasts weights / mean latent and re-seeds the draw generators)
+    import types
+    torch.manual_seed(100 + rank)
+    np.random.seed(100 + rank)
+    mc = types.SimpleNamespace(num_latents_for_mean=64, truncation=0.7, latent_dim=64, image_size=16)
+    cfg = dict(perturb_args=dict(truncation=0.7, n_layers=3, n_samples=1, layer_no=None, perturb_std=[1.0, 0.5, 1.0]),
+               swav_args=dict(num_epochs=3, num_samples=1, num_patches=2, sampling_method='random', patch_size=100,
+                              hf_interp='nearest', warmup_epochs=3, start_warmup=0.01, use_scheduler=True, base_lr=0.01,
+                              final_lr=0.0001, trust_coeff=0.01, freeze_prototype_niters=313,
+                              train_args=dict(lr=0.01, momentum=0.9), projn_nw='linear', temperature=0.02, nprototypes=48,
+                              nclasses=64, hlen=2560, add_local_loss=False, plot_test_images=False, epoch_print_freq=1,
+                              max_masks=4, batch_latents=2 * world),
+               sinkhorn_args=dict(source_pdf='uniform', niters=10, eps=0.02), train=True, layer_hf_dim=[512, 1024, 1024])
+    losses = []
+    tb = types.SimpleNamespace(add_scalar=lambda name, val, step: losses.append(float(val)))
+    obj = SwAVClustering(gen, mc, out_dir=None, device=str(dev), tb=tb, **cfg)
+    obj.pretrain(None, num_test_samples=1)
+    torch.cuda.synchronize()
+    sig = torch.stack([obj.projection[0].weight.double().sum(), obj.prototype.weight.double().sum(),
+                       torch.tensor(losses[-1], dtype=torch.float64, device=dev)])
+    gathered = [torch.zeros_like(sig) for _ in range(world)]
+    dist.all_gather(gathered, sig)
+    ok_cls = all(torch.equal(gathered[0], t) for t in gathered) and all(np.isfinite(losses)) and len(losses) == 3
+    all_ok = all_ok and ok_cls
     if rank == 0:
+        print(f"DIST_CHECK world={world} SwAVClustering.pretrain (batch_latents={2 * world}, ranks seeded differently) "
+              f"losses={losses} replicas_identical={ok_cls} {'OK' if ok_cls else 'MISMATCH'}", flush=True)
         print("DIST_CHECK", "OK" if all_ok else "MISMATCH", flush=True)
     dist.destroy_process_group()
     sys.exit(0 if all_ok else 1)
