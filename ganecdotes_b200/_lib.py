@@ -831,25 +831,44 @@ class LLExchange:
         self.rank, self.world, self.k, self.channels = rank, world, k, channels
         self.block = world * k                                    # words per block
         nbytes = channels * 2 * self.block * 8
-        own = C.c_void_p()
-        _check(lib.gx_peer_alloc(nbytes, C.byref(own)), "gx_peer_alloc")
-        self.own = own.value
-        handle = (C.c_char * 64)()
-        _check(lib.gx_peer_export(self.own, handle), "gx_peer_export")
+        self.own, self.ptrs = None, []
+        # every step below that can fail locally is followed by a collective that tells the peers, so that no rank is
+        # left waiting in a collective the failed rank never enters
+        handle, local_err = None, None
+        try:
+            own = C.c_void_p()
+            _check(lib.gx_peer_alloc(nbytes, C.byref(own)), "gx_peer_alloc")
+            self.own = own.value
+            h = (C.c_char * 64)()
+            _check(lib.gx_peer_export(self.own, h), "gx_peer_export")
+            handle = bytes(h)
+        except Exception as e:          # noqa: BLE001
+            local_err = e
         handles = [None] * world
-        dist.all_gather_object(handles, bytes(handle), group=pg)
-        self.ptrs = []
+        dist.all_gather_object(handles, handle, group=pg)
+        if any(h is None for h in handles):
+            self.close()
+            raise GxError(f"LLExchange: peer buffer allocation / export failed on a rank ({local_err!r})")
+        open_err = None
         for r in range(world):
             if r == rank:
                 self.ptrs.append(self.own)
                 continue
             p = C.c_void_p()
             buf = (C.c_char * 64).from_buffer_copy(handles[r])
-            _check(lib.gx_peer_open(buf, C.byref(p)), "gx_peer_open")
-            self.ptrs.append(p.value)
+            rc = lib.gx_peer_open(buf, C.byref(p))
+            if rc != 0:
+                open_err = GxError(f"gx_peer_open failed for rank {r} (rc {rc}, cuda error {lib.gx_last_cuda_error()})")
+                self.ptrs.append(None)
+            else:
+                self.ptrs.append(p.value)
+        flags = [None] * world
+        dist.all_gather_object(flags, open_err is None, group=pg)     # also: every buffer is zeroed and mapped from here on
+        if not all(flags):
+            self.close()
+            raise open_err or GxError("LLExchange: a peer could not map the exchange buffers")
         self.err = torch.zeros(1, dtype=torch.int32, device=device)
         self.seq = [0] * channels
-        dist.barrier(group=pg)         # every buffer is zeroed and mapped before the first store
 
     @classmethod
     def simulated(cls, world, k, device, channels=2):
@@ -903,8 +922,6 @@ class LLExchange:
             for p in self._sim_owned:
                 lib.gx_peer_free(p)
             self._sim_owned, self.ptrs = None, []
-            return
-        if self.own is None:
             return
         for r, p in enumerate(self.ptrs):
             if r != self.rank and p:

@@ -7,7 +7,7 @@
 #ifdef __CUDACC__
 namespace gxll {
 
-constexpr long long kTimeoutCycles = 20000000000LL;   // ~10 s at 1.9 GHz: a peer that never arrives is an error
+constexpr long long kTimeoutCycles = 60000000000LL;   // ~30 s at 1.9 GHz: a peer that never arrives is an error
 
 __device__ __forceinline__ void st_word(void* p, float v, unsigned seq) {
   asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(p), "r"(__float_as_uint(v)), "r"(seq) : "memory");

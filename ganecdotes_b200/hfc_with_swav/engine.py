@@ -485,13 +485,35 @@ class DistGroup:
     rank: int
     world: int
     ll: Optional[object] = None          # L.LLExchange: NVLink exchange of the Sinkhorn marginals (CUDA ranks)
+    ll_failed: bool = False              # set when the exchange could not be created (NCCL is used instead)
 
     def ensure_ll(self, k, device):
-        """create the low-latency exchange for K prototypes (collective: every rank must call it)"""
-        if self.ll is None or self.ll.k != k:
-            if self.ll is not None:
-                self.ll.close()
-            self.ll = L.LLExchange(self.pg, self.rank, self.world, k, device)
+        """create the low-latency exchange for K prototypes (collective: every rank must call it).  If any rank cannot
+        set it up (CUDA IPC unavailable between the processes, e.g. separate containers), ALL ranks fall back to the
+        NCCL all-reduce of the marginals - decided together, so the ranks never disagree on the transport."""
+        if self.ll is not None and self.ll.k == k:
+            return self.ll
+        if self.ll is not None:
+            self.ll.close()
+            self.ll = None
+        import warnings
+        ll, err = None, None
+        try:
+            ll = L.LLExchange(self.pg, self.rank, self.world, k, device)
+        except Exception as e:          # noqa: BLE001 - any failure means "no peer memory here"
+            err = e
+        ok = torch.tensor([1 if ll is not None else 0], dtype=torch.int32, device=device)
+        torch.distributed.all_reduce(ok, op=torch.distributed.ReduceOp.MIN, group=self.pg)
+        if int(ok.item()) == 1:
+            self.ll = ll
+        else:
+            if ll is not None:
+                ll.close()
+            if self.rank == 0:
+                warnings.warn(f"ganecdotes_b200: NVLink exchange unavailable ({err!r}); the Sinkhorn marginals use the "
+                              f"NCCL all-reduce")
+            self.ll = None
+            self.ll_failed = True
         return self.ll
 
 
@@ -698,7 +720,8 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
     grad_scale = 1.0 / (n_total * cfg.num_patches)
     maxp = L.load().gx_loss_max_parts()
     loss_parts = torch.zeros((cfg.num_patches, maxp), dtype=torch.float32, device=dev)
-    if group is not None and group.ll is None and os.environ.get("GX_SINKHORN_EXCHANGE", "ll") != "nccl":
+    if group is not None and group.ll is None and not group.ll_failed and \
+            os.environ.get("GX_SINKHORN_EXCHANGE", "ll") != "nccl":
         group.ensure_ll(head.k, dev)           # NVLink exchange of the marginals (GX_SINKHORN_EXCHANGE=nccl: A/B)
     for p in range(cfg.num_patches):
         fw = {}

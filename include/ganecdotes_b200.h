@@ -335,7 +335,7 @@ typedef struct gx_ll_desc {
   int world, rank;
   long long block_words;     /* offset of the block, in 8-byte words, from the buffer base */
   unsigned int seq;          /* tag of this exchange (non-zero, increases by one per exchange of a channel) */
-  int* err;                  /* device int: set to 1 if a consumer gave up waiting (~10 s); may be NULL */
+  int* err;                  /* device int: set to 1 if a consumer gave up waiting (~30 s); may be NULL */
 } gx_ll_desc;
 
 /* exchange buffers: cudaMalloc'ed + zeroed / exported as a 64-byte CUDA IPC handle / mapped from a peer's handle */

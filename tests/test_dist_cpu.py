@@ -64,7 +64,13 @@ def worker(rank, world, port, ret):
         g = torch.full((3,), float(rank + 1))
         dist.all_reduce(g, group=group.pg)
         ok3 = bool((g == sum(range(1, world + 1))).all())
-        ret[rank] = (ok1, ok2, ok3)
+        # transport fallback: without a CUDA device the NVLink exchange cannot be created on any rank; the ranks
+        # agree (one all-reduce) to use the all-reduce transport instead of failing or disagreeing
+        import warnings
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ok4 = group.ensure_ll(k, "cpu") is None and group.ll_failed and group.ll is None
+        ret[rank] = (ok1, ok2, ok3 and ok4)
     finally:
         dist.destroy_process_group()
 
