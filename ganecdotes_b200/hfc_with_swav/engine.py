@@ -657,26 +657,6 @@ def _tensors_of(inp: StepInputs):
 
 
 @torch.no_grad()
-def view_wplus_device(gen, w, mean_latent, truncation, layer_no, pert_rows, perturb_std, noise_w=None):
-    """`view_wplus` on device-resident draws (pert_rows [2B, D]); `noise_w`: style(pert_rows) if the caller
-    already ran the mapping network on them."""
-    b, d = w.shape
-    mean = mean_latent.reshape(-1).float().contiguous()
-    wt = L.truncate(w.float().contiguous(), mean, truncation) if truncation < 1 else w
-    wplus = wt.unsqueeze(1).repeat(1, gen.n_latent, 1).contiguous()
-    if noise_w is None:
-        noise_w = gen.style(pert_rows.float().contiguous())
-    for i in range(b):
-        l = layer_no[i]
-        sg = float(perturb_std[l])
-        for j, r in enumerate((2 * l, 2 * l + 1)):
-            wplus[i, r] = (1 - sg) * wplus[i, r] + sg * noise_w[2 * i + j]
-    if truncation < 1:
-        wplus = L.truncate(wplus, mean, truncation)
-    return wplus
-
-
-@torch.no_grad()
 def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cfg: StepConfig,
                            group: Optional[DistGroup] = None, ws: Optional[L.SinkhornWorkspace] = None):
     """One optimiser step on this rank's latents from device-resident inputs.  Returns the
