@@ -79,6 +79,20 @@ def test_ffhq256_full_step_properties(ffhq):
     assert abs(losses[True] - losses[False]) < 2e-3 * abs(losses[False]), losses
 
 
+def test_generic_config_k8000_step(ffhq):
+    """the generic hfc_with_swav_config.py (afhq-256 and every model without its own file): K = 8000 prototypes -
+    the 512-thread Sinkhorn instantiation and the widest loss kernel, at the shipped eps / T"""
+    E, gen, mean_latent = ffhq
+    cfg = E.StepConfig(hlen=5376, patch_size=20000, num_patches=2, niters=10, eps=0.005, temperature=0.01,
+                       truncation=0.7, perturb_std=[1.0] * 6)
+    head = _head(E, 5376, 512, 8000)
+    loss = E.swav_train_step(gen, head, mean_latent, _draws(E, 1, 512, 6, 65536, 2, 3), cfg)
+    assert math.isfinite(loss.item()) and 0 < loss.item() < 10 * math.log(8000)
+    gb = head.g_bias
+    assert abs(gb.sum().item()) < 1e-3 * gb.abs().sum().item() + 1e-12
+    assert torch.isfinite(head.g_proj).all() and torch.isfinite(head.g_proto).all()
+
+
 @pytest.mark.parametrize("eps", [0.05, 0.005])
 def test_ffhq256_sinkhorn_marginals_full_size(ffhq, eps):
     """Q = softmax_k(S/eps + log a) of a 40000 x 5000 score matrix: unit rows, uniform prototype marginals

@@ -530,7 +530,7 @@ def test_l2norm_fwd_bwd(L):
                                rtol=1e-6, atol=1e-6)
 
 
-@pytest.mark.parametrize("n,k", [(40, 24), (333, 48), (1000, 5000), (64, 4000)])
+@pytest.mark.parametrize("n,k", [(40, 24), (333, 48), (1000, 5000), (64, 4000), (301, 8000), (77, 6144)])
 def test_sinkhorn_vs_oracle(L, n, k):
     from ganecdotes_b200.hfc_with_swav import engine as E
     torch.manual_seed(n + k)
@@ -755,7 +755,7 @@ def test_bilinear_upsample_sum_and_its_adjoint(L):
 # round 2: exchange over peer memory, index bookkeeping, fused W+ construction
 # ----------------------------------------------------------------------------------------
 
-@pytest.mark.parametrize("world,n,k", [(2, 600, 48), (3, 999, 5000), (4, 64, 4000)])
+@pytest.mark.parametrize("world,n,k", [(2, 600, 48), (3, 999, 5000), (4, 64, 4000), (2, 300, 8000)])
 def test_sinkhorn_ll_exchange_simulated_ranks(L, world, n, k):
     """Distributed Sinkhorn through the tagged-word exchange (gx_sinkhorn_reduce_send + the receiving prologue
     of gx_sinkhorn_pass / gx_sinkhorn_log_a) with `world` endpoints simulated in one process: the rows of S are
