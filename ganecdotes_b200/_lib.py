@@ -104,7 +104,7 @@ _SIGNATURES = {
     "gx_l2norm_split": ([_P, _P, _P, _P, _P, _P, _LL, _I, _P], _I),
     "gx_round_f16": ([_P, _LL, _P, _LL, _LL, _P], _I),
     "gx_l2norm_bwd_split": ([_P, _P, _P, _P, _P, _P, _P, _LL, _I, _P], _I),
-    "gx_segment_sum_rows": ([_P, _P, _P, _P, _P, _P, _LL, _I, _P], _I),
+    "gx_segment_sum_rows": ([_P, _I, _P, _P, _P, _P, _P, _LL, _I, _P], _I),
     "gx_upsample_sum": ([_I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P], _I),
     "gx_pool1d_bilinear": ([_P, _LL, _I, _I, _LL, _P, _P], _I),
     "gx_pool_sum": ([_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P], _I),
@@ -674,12 +674,18 @@ def l2norm_split(z, want_lo=True, row_idx=None, want_f16=False):
     return hi, lo, inv
 
 
-def l2norm_bwd_split(dzn, zn_hi, zn_lo, inv_norm, want_lo=True, want_planes=True, out_f32=None):
-    """dz planes and / or fp32 rows written into `out_f32` [n,c]"""
+def l2norm_bwd_split(dzn, zn_hi, zn_lo, inv_norm, want_lo=True, want_planes=True, out_f32=None, out_hi=None):
+    """dz planes and / or fp32 rows written into `out_f32` [n,c]; `out_hi`: a caller-provided bf16 [n,c] (slice) for
+    the hi plane"""
     lib = load()
     _f32(dzn, "dzn")
     n, c = dzn.shape
-    hi = torch.empty((n, c), dtype=torch.bfloat16, device=dzn.device) if want_planes else None
+    if out_hi is not None:
+        if out_hi.dtype != torch.bfloat16 or tuple(out_hi.shape) != (n, c) or not out_hi.is_contiguous():
+            raise GxError("l2norm_bwd_split: out_hi must be a contiguous bf16 [n, c] tensor")
+        hi, want_planes = out_hi, True
+    else:
+        hi = torch.empty((n, c), dtype=torch.bfloat16, device=dzn.device) if want_planes else None
     lo = torch.empty_like(hi) if (want_lo and want_planes) else None
     if out_f32 is not None:
         _f32(out_f32, "out_f32")
@@ -693,14 +699,19 @@ def l2norm_bwd_split(dzn, zn_hi, zn_lo, inv_norm, want_lo=True, want_planes=True
 def segment_sum_rows(rows, order, seg_off, nseg, want_lo=False, want_planes=True, want_f32=False):
     """per-segment sums of `rows[order[...]]` as bf16 planes [nseg, c] and / or fp32"""
     lib = load()
-    _f32(rows, "rows")
+    bf16_rows = rows.dtype == torch.bfloat16
+    if not bf16_rows:
+        _f32(rows, "rows")
+    elif not rows.is_contiguous():
+        raise GxError("segment_sum_rows: rows must be contiguous")
     c = rows.shape[1]
     hi = torch.empty((nseg, c), dtype=torch.bfloat16, device=rows.device) if want_planes else None
     lo = torch.empty_like(hi) if (want_lo and want_planes) else None
     f = torch.empty((nseg, c), dtype=torch.float32, device=rows.device) if want_f32 else None
-    with timed("segment_sum_rows", float(rows.shape[0]) * c * 4 + float(nseg) * c * (4 if want_lo or want_f32 else 2)):
-        _check(lib.gx_segment_sum_rows(_ptr(rows), _ptr(order), _ptr(seg_off), _ptr(hi), _ptr(lo), _ptr(f), nseg, c,
-                                       _stream()), "gx_segment_sum_rows")
+    with timed("segment_sum_rows", float(rows.shape[0]) * c * (2 if bf16_rows else 4) +
+               float(nseg) * c * (4 if want_lo or want_f32 else 2)):
+        _check(lib.gx_segment_sum_rows(_ptr(rows), int(bf16_rows), _ptr(order), _ptr(seg_off), _ptr(hi), _ptr(lo), _ptr(f),
+                                       nseg, c, _stream()), "gx_segment_sum_rows")
     _count()
     return hi, lo, f
 

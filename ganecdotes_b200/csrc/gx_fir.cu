@@ -64,14 +64,23 @@ __global__ void upfirdn2d_kernel(const float* __restrict__ in, const float* __re
 // --------------------------------------------------------------------------
 constexpr int UT_OW = 64, UT_OH = 32, UT_K = 4, UT_ROWS = 8;
 
-template <int UP, int DOWN>
+__device__ __forceinline__ void cp_async_f32(float* smem_dst, const float* gsrc, bool valid) {
+  // 4-byte asynchronous copy; src-size 0 zero-fills the destination (the zero border of the tile)
+  const uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+  const int sz = valid ? 4 : 0;
+  asm volatile("cp.async.ca.shared.global [%0], [%1], 4, %2;" ::"r"(d), "l"(gsrc), "r"(sz) : "memory");
+}
+
+// NBUF = 2: the CTA walks over several planes and the tile of the next plane is in flight (cp.async) while the
+// current one is filtered; NBUF = 1 where two tiles do not fit the static shared-memory budget (DOWN = 2).
+template <int UP, int DOWN, int NBUF>
 __global__ void __launch_bounds__(256)
 upfirdn2d_planar_kernel(const float* __restrict__ in, const float* __restrict__ kern, float* __restrict__ out,
                         const UpfirParams p) {
   constexpr int IN_H = ((UT_OH - 1) * DOWN + UT_K - 1) / UP + 2;
   constexpr int IN_W = ((UT_OW - 1) * DOWN + UT_K - 1) / UP + 2;
   constexpr int TAPS = (UT_K + UP - 1) / UP;            // taps per axis that land on real samples
-  __shared__ float tile[IN_H][IN_W + 1];
+  __shared__ float tile[NBUF][IN_H][IN_W + 1];
   __shared__ float fk[UT_K + UP][UT_K + UP];            // flipped taps, zero beyond kh x kw
   const int tid = threadIdx.x;
   for (int i = tid; i < (UT_K + UP) * (UT_K + UP); i += 256) {
@@ -86,13 +95,25 @@ upfirdn2d_planar_kernel(const float* __restrict__ in, const float* __restrict__ 
   const int ux = ux0 + tx * DOWN;
   const int kx0 = ((-ux) % UP + UP) % UP;
   const int lx0 = (ux + kx0) / UP - ix0;                // exact division: ux + kx0 is a multiple of UP
-  for (int mj = blockIdx.z; mj < p.major; mj += gridDim.z) {
+  auto fetch = [&](int mj, int buf) {
     const float* src = in + (long long)mj * p.in_h * p.in_w;
-    __syncthreads();
     for (int i = tid; i < IN_H * IN_W; i += 256) {
       const int r = i / IN_W, c = i - r * IN_W;
       const int iy = iy0 + r, ix = ix0 + c;
-      tile[r][c] = (iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w) ? __ldg(src + (long long)iy * p.in_w + ix) : 0.f;
+      const bool ok = iy >= 0 && iy < p.in_h && ix >= 0 && ix < p.in_w;
+      cp_async_f32(&tile[buf][r][c], ok ? src + (long long)iy * p.in_w + ix : src, ok);
+    }
+    asm volatile("cp.async.commit_group;" ::: "memory");
+  };
+  int it = 0;
+  if (blockIdx.z < (unsigned)p.major) fetch(blockIdx.z, 0);
+  for (int mj = blockIdx.z; mj < p.major; mj += gridDim.z, ++it) {
+    const int buf = NBUF == 2 ? (it & 1) : 0;
+    if (NBUF == 2 && mj + (int)gridDim.z < p.major) {
+      fetch(mj + gridDim.z, buf ^ 1);
+      asm volatile("cp.async.wait_group 1;" ::: "memory");
+    } else {
+      asm volatile("cp.async.wait_group 0;" ::: "memory");
     }
     __syncthreads();
     if (ox < p.out_w) {
@@ -110,8 +131,8 @@ upfirdn2d_planar_kernel(const float* __restrict__ in, const float* __restrict__ 
         const int ly = ty * UT_ROWS + (uy0 - iy0);            // uy0 - iy0 == 0 for UP == 1
 #pragma unroll
         for (int r = 0; r < UT_ROWS + UT_K - 1; ++r) {
-          const float v0 = tile[ly + r][lx0], v1 = tile[ly + r][lx0 + 1], v2 = tile[ly + r][lx0 + 2],
-                      v3 = tile[ly + r][lx0 + 3];
+          const float v0 = tile[buf][ly + r][lx0], v1 = tile[buf][ly + r][lx0 + 1], v2 = tile[buf][ly + r][lx0 + 2],
+                      v3 = tile[buf][ly + r][lx0 + 3];
 #pragma unroll
           for (int j = 0; j < UT_ROWS; ++j) {
             const int ky = r - j;
@@ -126,21 +147,23 @@ upfirdn2d_planar_kernel(const float* __restrict__ in, const float* __restrict__ 
         }
       } else {
 #pragma unroll
-      for (int j = 0; j < UT_ROWS; ++j) {
-        const int oyl = ty * UT_ROWS + j;
-        const int uy = uy0 + oyl * DOWN;
-        const int ky0 = ((-uy) % UP + UP) % UP;
-        const int ly0 = (uy + ky0) / UP - iy0;
-        float acc = 0.f;
+        for (int j = 0; j < UT_ROWS; ++j) {
+          const int oyl = ty * UT_ROWS + j;
+          const int uy = uy0 + oyl * DOWN;
+          const int ky0 = ((-uy) % UP + UP) % UP;
+          const int ly0 = (uy + ky0) / UP - iy0;
+          float acc = 0.f;
 #pragma unroll
-        for (int a = 0; a < TAPS; ++a)
+          for (int a = 0; a < TAPS; ++a)
 #pragma unroll
-          for (int b = 0; b < TAPS; ++b)
-            acc = fmaf(tile[ly0 + a][lx0 + b], fk[ky0 + a * UP][kx0 + b * UP], acc);
-        if (oy0 + oyl < p.out_h) dst[(long long)(oy0 + oyl) * p.out_w] = acc;
-      }
+            for (int b = 0; b < TAPS; ++b)
+              acc = fmaf(tile[buf][ly0 + a][lx0 + b], fk[ky0 + a * UP][kx0 + b * UP], acc);
+          if (oy0 + oyl < p.out_h) dst[(long long)(oy0 + oyl) * p.out_w] = acc;
+        }
       }
     }
+    __syncthreads();                       // the tile may be overwritten by the next fetch
+    if (NBUF == 1 && mj + (int)gridDim.z < p.major) fetch(mj + gridDim.z, 0);
   }
 }
 
@@ -560,10 +583,17 @@ extern "C" int gx_upfirdn2d(const float* input, const float* kernel, float* out,
   cudaStream_t st = (cudaStream_t)stream;
   if (minor == 1 && kh <= UT_K && kw <= UT_K && up_x == up_y && down_x == down_y && up_x <= 2 && down_x <= 2 &&
       up_x * down_x <= 2 && p.out_w >= 32 && p.out_h >= 8) {
-    dim3 grid(gx_cdiv(p.out_w, UT_OW), gx_cdiv(p.out_h, UT_OH), major < 32768 ? major : 32768);
-    if (up_x == 2) upfirdn2d_planar_kernel<2, 1><<<grid, 256, 0, st>>>(input, kernel, out, p);
-    else if (down_x == 2) upfirdn2d_planar_kernel<1, 2><<<grid, 256, 0, st>>>(input, kernel, out, p);
-    else upfirdn2d_planar_kernel<1, 1><<<grid, 256, 0, st>>>(input, kernel, out, p);
+    // enough CTAs for ~3 waves of 4 CTAs per SM; each CTA then walks over major / grid.z planes with the next
+    // plane's tile in flight
+    const int tiles = gx_cdiv(p.out_w, UT_OW) * gx_cdiv(p.out_h, UT_OH);
+    int gz = gx_cdiv((long long)gx_sm_count() * 12, tiles);
+    if (gz > major) gz = major;
+    if (gz > 32768) gz = 32768;
+    if (gz < 1) gz = 1;
+    dim3 grid(gx_cdiv(p.out_w, UT_OW), gx_cdiv(p.out_h, UT_OH), gz);
+    if (up_x == 2) upfirdn2d_planar_kernel<2, 1, 2><<<grid, 256, 0, st>>>(input, kernel, out, p);
+    else if (down_x == 2) upfirdn2d_planar_kernel<1, 2, 1><<<grid, 256, 0, st>>>(input, kernel, out, p);
+    else upfirdn2d_planar_kernel<1, 1, 2><<<grid, 256, 0, st>>>(input, kernel, out, p);
     GX_LAUNCH_CHECK();
     return GX_OK;
   }

@@ -191,10 +191,14 @@ __global__ void l2norm_bwd_split_kernel(const float* __restrict__ dzn, const __n
 // out[seg,:] = sum over r in [seg_off[seg], seg_off[seg+1]) of rows[order[r], :]  (deterministic
 // gather-reduce; used to fold the per-patch dZ rows of pixels sampled several times into one
 // row per pixel), written as bf16 planes.  Warp per segment.
-__global__ void segment_sum_rows_kernel(const float* __restrict__ rows, const int* __restrict__ order,
+// (BF16_ROWS: the rows are single bf16 planes - the bf16-backward mode stores dZ rows at half the bytes)
+template <bool BF16_ROWS>
+__global__ void segment_sum_rows_kernel(const void* __restrict__ rows_v, const int* __restrict__ order,
                                         const int* __restrict__ seg_off, __nv_bfloat16* __restrict__ hi,
                                         __nv_bfloat16* __restrict__ lo, float* __restrict__ out_f32, long long nseg,
                                         int c) {
+  const float* rows = reinterpret_cast<const float*>(rows_v);
+  const __nv_bfloat16* rows_h = reinterpret_cast<const __nv_bfloat16*>(rows_v);
   const int lane = threadIdx.x & 31;
   const long long seg = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (seg >= nseg) return;
@@ -210,11 +214,14 @@ __global__ void segment_sum_rows_kernel(const float* __restrict__ rows, const in
     for (int j = 0; j < 4; ++j) acc[j] = make_float4(0.f, 0.f, 0.f, 0.f);
     for (int r = r0; r < r1; ++r) {
       const float4* src = reinterpret_cast<const float4*>(rows + (long long)order[r] * c) + i0;
+      const uint2* src_h = reinterpret_cast<const uint2*>(rows_h + (long long)order[r] * c) + i0;
 #pragma unroll
       for (int j = 0; j < 4; ++j) {
         const int i = lane + 32 * j;
         if (i0 + i < cq) {
-          const float4 v = gx_ldg_stream(src + i);
+          float4 v;
+          if constexpr (BF16_ROWS) v = planes_to_float4(__ldg(src_h + i), nullptr);
+          else v = gx_ldg_stream(src + i);
           acc[j].x += v.x; acc[j].y += v.y; acc[j].z += v.z; acc[j].w += v.w;
         }
       }
@@ -1552,11 +1559,16 @@ extern "C" int gx_l2norm_bwd_split(const float* dzn, const void* zn_hi, const vo
   return GX_OK;
 }
 
-extern "C" int gx_segment_sum_rows(const float* rows, const int* order, const int* seg_off, void* hi, void* lo,
-                                   float* out_f32, long long nseg, int c, void* stream) {
+extern "C" int gx_segment_sum_rows(const void* rows, int rows_bf16, const int* order, const int* seg_off, void* hi,
+                                   void* lo, float* out_f32, long long nseg, int c, void* stream) {
   GX_CHECK_ARG(rows && order && seg_off && (hi || out_f32) && nseg > 0 && c % 4 == 0);
   GX_CHECK_ARG(lo == nullptr || hi != nullptr);
-  segment_sum_rows_kernel<<<gx_cdiv(nseg, 8), 256, 0, (cudaStream_t)stream>>>(
+  if (rows_bf16)
+    segment_sum_rows_kernel<true><<<gx_cdiv(nseg, 8), 256, 0, (cudaStream_t)stream>>>(
+        rows, order, seg_off, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), out_f32, nseg,
+        c);
+  else
+    segment_sum_rows_kernel<false><<<gx_cdiv(nseg, 8), 256, 0, (cudaStream_t)stream>>>(
       rows, order, seg_off, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), out_f32, nseg,
       c);
   GX_LAUNCH_CHECK();

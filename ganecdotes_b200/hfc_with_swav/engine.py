@@ -385,7 +385,10 @@ def scores_backward(head: SwavHead, fw, ds_hi, ds_lo, dz_rows_out=None):
     L.gemm(ds_hi, ds_lo if pb == 3 else None, fw["zn_hi"], fw["zn_lo"] if pb == 3 else None, k, c, n, pb,
            out=head.g_proto, a_mn=True, b_mn=True, split_k=sk1, accumulate=True, tag="gemm_gproto_bwd", pair=True)
     if dz_rows_out is not None:
-        L.l2norm_bwd_split(dzn, fw["zn_hi"], fw["zn_lo"], fw["inv"], want_planes=False, out_f32=dz_rows_out)
+        if dz_rows_out.dtype == torch.bfloat16:      # bf16 backward: the rows are kept as one bf16 plane
+            L.l2norm_bwd_split(dzn, fw["zn_hi"], fw["zn_lo"], fw["inv"], want_lo=False, out_hi=dz_rows_out)
+        else:
+            L.l2norm_bwd_split(dzn, fw["zn_hi"], fw["zn_lo"], fw["inv"], want_planes=False, out_f32=dz_rows_out)
         return
     dz_hi, dz_lo = L.l2norm_bwd_split(dzn, fw["zn_hi"], fw["zn_lo"], fw["inv"], want_lo=pb == 3)
     sk2 = pick_split_k(math.ceil(c / bm) * math.ceil(d / 256), kit, sms)
@@ -693,7 +696,10 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
         z_all, levels = project_all_pixels(head.wp_hi, head.wp_lo, f_both, 2 * b, out_h, out_w, cfg.hlen,
                                            head.passes_fwd, want_hi_only_planes=head.passes_bwd != 3,
                                            bilinear=cfg.hf_interp == 'bilinear')
-        dz_rows = torch.empty((2 * cfg.num_patches * n_patch_rows, head.c), dtype=torch.float32, device=dev)
+        # dZ rows of every sample, folded per pixel after the last patch: fp32, or - with bf16 backward operands
+        # (passes_bwd == 1, the default) - one bf16 plane: half the bytes written here and gathered by the segment sum
+        dz_rows = torch.empty((2 * cfg.num_patches * n_patch_rows, head.c), device=dev,
+                              dtype=torch.bfloat16 if head.passes_bwd == 1 else torch.float32)
 
     n_local = b * (cfg.patch_size if cfg.patch_size is not None else out_h * out_w)
     n_total = n_local * world

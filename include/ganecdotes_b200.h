@@ -244,8 +244,9 @@ int gx_l2norm_bwd_split(const float* dzn, const void* zn_hi, const void* zn_lo, 
 
 /* out[seg,:] = sum_{r in [seg_off[seg], seg_off[seg+1])} rows[order[r],:] as bf16 planes: folds the
  * dZ rows of pixels that were sampled by several patches into one row per pixel (deterministic,
- * no atomics), so the projection-weight gradient GEMM runs over pixels, not samples. */
-int gx_segment_sum_rows(const float* rows, const int* order, const int* seg_off, void* hi, void* lo,
+ * no atomics), so the projection-weight gradient GEMM runs over pixels, not samples.  rows: fp32 [*, c], or
+ * - rows_bf16 != 0 - one bf16 plane (the bf16-backward mode keeps the dZ rows at half the bytes). */
+int gx_segment_sum_rows(const void* rows, int rows_bf16, const int* order, const int* seg_off, void* hi, void* lo,
                         float* out_f32, long long nseg, int c, void* stream);
 
 /* Z[b,y,x,:] = sum_l P_l[b, y*h_l/out_h, x*w_l/out_w, :] (fp32 NHWC, c channels).  By linearity the
