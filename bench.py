@@ -235,6 +235,15 @@ def swav_workload_name(cfg, b):
             f"T={cfg['temperature']}, Sinkhorn {cfg['niters']} it, fwd+bwd+LARC/SGD")
 
 
+def swav_config(cfg, b, world, exchange=None):
+    """the `config` block of a SwAV-step line - the same for this repo's arm and for the reference arm"""
+    return {"workload": swav_workload_name(cfg, b), "latents_per_gpu": b, "global_latents": b * world,
+            "vectors_per_step": world * b * 2 * cfg["npatch"] * cfg["patch"],
+            "l2": f"inputs_larger_than_l2 ({4e-9 * b * cfg['patch'] * cfg['nprototypes']:.1f} GB score matrices)",
+            "generator": f"StyleGAN2-{cfg['size']} random init seed 42", "sinkhorn": "joint-batch (distributed)",
+            "exchange": exchange}
+
+
 CPU_SWAV_SAMPLE = ("per step: ONE latent x 2 views x all 5 patches x 20000 px (200000 vectors) through the full step "
                    "of the reference as restated by the oracle, on the host CPU; the GPU arm runs the same step on "
                    "{b} latents per GPU")
@@ -256,7 +265,7 @@ def run_reference(args):
         line = {"impl": "reference", "metric": METRIC[wl], "value": value, "unit": "vectors/s", "n_gpus": args.gpus,
                 "steps": args.steps, "warmup": warm, "ms_per_step": sec * 1e3, "higher_is_better": True,
                 "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-                "config": {"workload": swav_workload_name(cfg, b), "sample": sample},
+                "config": dict(swav_config(cfg, b, max(1, args.gpus)), sample=sample),
                 "cpu_baseline": {"value": value, "unit": "vectors/s", "cores": cores, "kind": "port", "sample": sample},
                 "e2e": {"value": value, "unit": "vectors/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
                 "gpu_launches": 0}
@@ -590,12 +599,7 @@ def run_swav(args, cfg):
             "dtype": f"bf16x{args.passes_fwd}-split fwd" + (" (score GEMM fp16x1 on unit-norm operands)" if args.proto_f16 else "") +
                      f" / bf16x{args.passes_bwd} bwd operands, fp32 accumulate + fp32 everywhere else",
             "data": "synthetic",
-            "config": {"workload": swav_workload_name(cfg, b), "latents_per_gpu": b, "global_latents": b * world,
-                       "vectors_per_step": vec_per_step,
-                       "l2": f"inputs_larger_than_l2 ({4e-9 * b * cfg['patch'] * cfg['nprototypes']:.1f} GB score matrices)",
-                       "generator": f"StyleGAN2-{cfg['size']} random init seed 42",
-                       "sinkhorn": "joint-batch (distributed)",
-                       "exchange": None if world == 1 else ("ll-nvlink" if group.ll is not None else "nccl")},
+            "config": swav_config(cfg, b, world, None if world == 1 else ("ll-nvlink" if group.ll is not None else "nccl")),
             "roofline": roofline, "roofline_stages": stage_rows, "cpu_baseline": cpu_base,
             "e2e": {"value": e2e_value, "unit": "vectors/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": 4,
                     "steps": e2e_steps, "ms_per_step": dt * 1e3 / e2e_steps,
