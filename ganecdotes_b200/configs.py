@@ -81,7 +81,38 @@ def swav_config(model, method='hfc_with_swav'):
     )
 
 
+def simclr_config(model='ffhq-256'):
+    """hfc_prep_args of configs/segmentors/hfc_with_simclr_config.py (:1-48) - keyword arguments of SimCLRClustering"""
+    layers = list(_FFHQ_LAYERS)
+    return dict(
+        perturb_args=dict(truncation=0.7, n_layers=6, n_samples=1, layer_no=None, perturb_std=[1.0] * 6),
+        simclr_args=dict(num_iters=100, batch_size=20, patch_size=20000, hf_interp='nearest', trust_coeff=0.01,
+                         train_args=dict(lr=0.01, momentum=0.9), temperature=1.0, nclasses=512, hlen=sum(layers),
+                         epoch_print_freq=5, max_masks=4),
+        layer_hf_dim=layers,
+    )
+
+
+KMEANS_CLUSTERS = [4, 8, 16, 32, 64]        # hfc_kmeans_config.py:6
+
+
+def kmeans_config(model='ffhq-256'):
+    """hfc_prep_args of configs/segmentors/hfc_kmeans_config.py (:12-40) - keyword arguments of HFCPreprocessor"""
+    return dict(
+        perturb_args=dict(truncation=0.7, n_layers=5, n_samples=4, perturb_std=[1.0] * 5),
+        hfc_algo='hfc_kmeans',
+        hfc_args=dict(kmeans_args=dict(verbose=0),
+                      base_args=dict(out_dir=None, n_layers=5, clusters_per_layer=list(KMEANS_CLUSTERS), out_size=256,
+                                     presaved=False)),
+        hier_encode=False, hle_samples=100,
+    )
+
+
 def seg_args(model, method='hfc_with_swav'):
+    if method == 'hfc_with_simclr':
+        return dict(size='XS', in_ch=512)                       # hfc_with_simclr_config.py:55-56
+    if method == 'hfc_kmeans':
+        return dict(size='S', in_ch=sum(KMEANS_CLUSTERS))        # hfc_kmeans_config.py:68-69
     return dict(size=_METHOD[method_for(model, method)]['seg'], in_ch=512)
 
 

@@ -105,6 +105,29 @@ class FlatKMeansAssign(object):
             centers.append(c)
         return cls(centers, out_size, features[0].device)
 
+    @classmethod
+    def fit_grouped(cls, grouped, clusters_per_layer, out_size=256, seed=0, **kmeans_args):
+        """`fit` on already grouped per-layer features: grouped[n] = [B, C_n, h, w] (the two maps of block n
+        concatenated, what `create_images_and_features_from_perturbed_latents(..., skip_const=True)` returns)"""
+        centers = []
+        for n, k in enumerate(clusters_per_layer):
+            f = grouped[n].permute(0, 2, 3, 1).contiguous().float()
+            c, _, _, _ = kmeans_fit(f.reshape(-1, f.shape[3]), k, seed=seed + n, **kmeans_args)
+            centers.append(c)
+        return cls(centers, out_size, grouped[0].device)
+
+    def predict_grouped(self, grouped):
+        """ref BaseHFCModel.predict (:93-110) on grouped per-layer features [B, C_n, h, w]:
+        (one-hot maps [B, sum K, out, out], [labels [B, 1, h_n, w_n]])"""
+        outs, labs = [], []
+        for n in range(self.n_layers):
+            f = grouped[n]
+            f = (f.permute(0, 2, 3, 1) if f.stride(1) == 1 else f.permute(0, 2, 3, 1).contiguous()).contiguous().float()
+            lab, maps = self._layerwise_predict([f], n)
+            outs.append(maps)
+            labs.append(lab)
+        return torch.cat(outs, 1), labs
+
     def _layerwise_predict(self, feats_nhwc: List[torch.Tensor], n: int):
         """ref :169-208.  feats_nhwc: the map(s) of layer n as fp32 NHWC tensors.
         Returns (labels int32 [b,1,h,w], label_maps float [b,K,out,out])."""

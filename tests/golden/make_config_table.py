@@ -53,6 +53,14 @@ def main():
     for name, f in sorted(segs.items()):
         if name.startswith("hfc_with_swav"):
             table["segmentors"][name] = seg_config(os.path.join(REF, "configs", "segmentors", f))
+    table["baselines"] = {}
+    for name in ("hfc_with_simclr", "hfc_kmeans"):          # plain Python too
+        ns = {}
+        path = os.path.join(REF, "configs", "segmentors", segs[name])
+        exec(compile(open(path).read(), path, "exec"), ns)
+        a = dict(ns["hfc_prep_args"])
+        a.pop("train", None)
+        table["baselines"][name] = dict(hfc_prep_args=a, seg_args=ns["seg_args"], n_hfc_layers=ns["n_hfc_layers"])
     out = os.path.join(os.path.dirname(os.path.abspath(__file__)), "reference_configs.json")
     json.dump(table, open(out, "w"), indent=1, sort_keys=True)
     print(out, len(table["models"]), "models", len(table["segmentors"]), "segmentor configs")

@@ -600,3 +600,63 @@ def test_simclr_pretrain_and_codes_match_reference_golden(gen, tmp_path):
     assert os.path.exists(os.path.join(str(tmp_path), "projection.pt"))
     p2, l2 = obj2.predict_simclr_codes(g["pred_w"].cuda())
     assert torch.isfinite(p2).all() and tuple(l2.shape) == (1, 16, 16)
+
+
+def test_kmeans_preprocessor_train_and_predict(gen, tmp_path):
+    """HFCPreprocessor (ref baseline/hfc_kmeans/segmentor.py:11-226): fit on the latent-perturbed samples of one
+    latent, one-hot cluster maps in {-1, +1}; the labels are the nearest fitted centre of the oracle's assignment on
+    the same hidden features; artefact round trip."""
+    from ganecdotes_b200.hfc_kmeans import HFCPreprocessor, preprocessor
+    from ganecdotes_b200 import oneshot
+    assert preprocessor is HFCPreprocessor
+    mc = types.SimpleNamespace(num_latents_for_mean=64, truncation=0.7, latent_dim=64, image_size=16)
+    cfg = dict(perturb_args=dict(truncation=0.7, n_layers=2, n_samples=4, perturb_std=[1.0, 1.0]), hfc_algo='hfc_kmeans',
+               hfc_args=dict(kmeans_args=dict(verbose=0),
+                             base_args=dict(out_dir=None, n_layers=2, clusters_per_layer=[4, 8], out_size=16,
+                                            presaved=False)),
+               hier_encode=False, hle_samples=10)
+    torch.manual_seed(21)
+    pre = HFCPreprocessor(model=gen, model_config=mc, out_dir=str(tmp_path), logger=None, train=True, **cfg)
+    w = gen.style(torch.randn(1, 64).cuda())
+    hidden, new_latents = pre.train_hfc_model(w, return_aug=True)
+    assert [tuple(h.shape) for h in hidden] == [(4, 1024, 8, 8), (4, 1024, 16, 16)] and len(new_latents) == 4
+    assert [tuple(c.shape) for c in pre.hfc_model.centers] == [(4, 1024), (8, 1024)]
+    torch.manual_seed(22)
+    preds, labels = pre.predict_hfc_vectors(w)
+    assert tuple(preds.shape) == (1, 12, 16, 16) and set(preds.unique().tolist()) <= {-1.0, 1.0}
+    assert (preds > 0).sum(1).eq(2).all()                         # one active cluster per layer and pixel
+    # the same hidden features through the oracle's assignment with the fitted centres
+    torch.manual_seed(22)
+    mean_latent = gen.mean_latent(64)
+    _, wl = gen([w], return_latents=True, truncation_latent=mean_latent, truncation=0.7, input_is_latent=True)
+    _, hf = oneshot.create_images_and_features_from_perturbed_latents(wl, gen, {'truncation': 0.7, 'mean_latent': mean_latent},
+                                                                      skip_const=True)
+    for n in range(2):
+        ref = O.kmeans_assign(hf[n].permute(0, 2, 3, 1).reshape(-1, 1024).cpu(), pre.hfc_model.centers[n].cpu())
+        assert torch.equal(labels[n].flatten().cpu(), ref)
+    # artefact: a second preprocessor in eval mode loads the centres and gives the same maps
+    pre2 = HFCPreprocessor(model=gen, model_config=mc, out_dir=str(tmp_path), logger=None, train=False, **cfg)
+    torch.manual_seed(22)
+    preds2, _ = pre2.predict_hfc_vectors(w)
+    assert torch.equal(preds, preds2)
+    with pytest.raises(NotImplementedError):
+        HFCPreprocessor(model=gen, model_config=mc, out_dir=str(tmp_path), **dict(cfg, hier_encode=True))
+
+
+def test_cli_entry_points_for_the_baselines(tmp_path):
+    """pretrain.py / evaluate.py with --method hfc_with_simclr and hfc_kmeans (the reference's CLI accepts the three
+    methods, pretrain.py:45-57): artefacts written, label maps produced"""
+    import sys
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import evaluate
+    import pretrain
+    out = str(tmp_path / "simclr")
+    pretrain.main(["--model", "ffhq-256", "--method", "hfc_with_simclr", "--out_dir", out, "--num_epochs", "2"])
+    assert os.path.exists(os.path.join(out, "projection.pt"))
+    res = evaluate.main(["--model", "ffhq-256", "--method", "hfc_with_simclr", "--out_dir", out, "--num_test_samples", "1"])
+    assert tuple(res["code_labels"].shape) == (1, 256, 256)
+    out = str(tmp_path / "kmeans")
+    pretrain.main(["--model", "ffhq-256", "--method", "hfc_kmeans", "--out_dir", out])
+    assert os.path.exists(os.path.join(out, "kmeans_centers.pt"))
+    res = evaluate.main(["--model", "ffhq-256", "--method", "hfc_kmeans", "--out_dir", out, "--num_test_samples", "2"])
+    assert [tuple(l.shape) for l in res["layer_labels"]] == [(2, 1, 8 * 2 ** n, 8 * 2 ** n) for n in range(5)]

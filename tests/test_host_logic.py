@@ -125,6 +125,11 @@ def test_config_tables_against_the_reference_config_files():
         assert c["sinkhorn_args"] == ref["sinkhorn_args"], method
         assert c["layer_hf_dim"] == ref["layer_hf_dim"]
         assert configs.seg_args(model) == ref["seg_args"], method
+    # the two baselines' configs (hfc_with_simclr_config.py, hfc_kmeans_config.py)
+    sc, ref = configs.simclr_config(), table["baselines"]["hfc_with_simclr"]
+    assert sc == ref["hfc_prep_args"] and configs.seg_args("ffhq-256", "hfc_with_simclr") == ref["seg_args"]
+    kc, ref = configs.kmeans_config(), table["baselines"]["hfc_kmeans"]
+    assert kc == ref["hfc_prep_args"] and configs.seg_args("ffhq-256", "hfc_kmeans") == ref["seg_args"]
     for tool in ("pliers", "hammer", "powerbank", "wrench", "handcuffs"):
         assert configs.model_config(f"pidray-{tool}-256").truncation == 0.95
         assert configs.method_for(f"pidray-{tool}-256") == "hfc_with_swav_pidray"
