@@ -762,7 +762,7 @@ def swav_train_step(gen, head: SwavHead, mean_latent, draws: StepDraws, cfg: Ste
 
 
 @torch.no_grad()
-def predict_codes(gen, w_proj, w, mean_latent, truncation, hlen, passes=3, images_per_chunk=4, want_planes=False,
+def predict_codes(gen, w_proj, w, mean_latent, truncation, hlen, passes=3, images_per_chunk=16, want_planes=False,
                   hf_interp='nearest'):
     """predict_swav_codes (ref :659-693): generator forward with the fixed noise buffers,
     per-pixel vectors, projection only, arg-max over the code channels.
