@@ -675,8 +675,26 @@ def run_labelmap(args):
     def step(w):
         return E.predict_codes(gen, wp, w, mean_latent, trunc, hlen)[1]
 
+    # ---- eager pass: CUDA events around every launch -> the per-stage table
     for i in range(args.warmup):
         step(ws_dev[i])
+    sync()
+    L.event_log = []
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for i in range(args.steps):
+        step(ws_dev[args.warmup + i])
+    a1.record()
+    sync()
+    eager_ms = a0.elapsed_time(a1)
+    log = L.event_log
+    L.event_log = None
+    rows, stages, pk = stage_table(log, args.steps, eager_ms, {"gemm_projection_fwd": 3, "modconv": 3, "modconv_up": 3})
+    # ---- timed region: the same batch as one CUDA-graph replay per step (engine.PredictGraph; bit-identical results)
+    graph = None if args.no_graph else E.PredictGraph(gen, wp, mean_latent, trunc, hlen, b)
+    run = (lambda w: graph(w)[1]) if graph is not None else step
+    for i in range(args.warmup):
+        run(ws_dev[i])
     sync()
     sampler = ClockSampler(local_rank)
     if rank == 0:
@@ -684,32 +702,29 @@ def run_labelmap(args):
         time.sleep(0.3)
     sampler.mark_begin()
     L.launch_count = 0
-    L.event_log = []
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for i in range(args.steps):
-        labels = step(ws_dev[args.warmup + i])
+        labels = run(ws_dev[args.warmup + i])
     e1.record()
     sync()
     sampler.mark_end()
     clocks = sampler.summary() if rank == 0 else None
     ms = e0.elapsed_time(e1)
-    launches, log = L.launch_count, L.event_log
-    L.event_log = None
+    launches = L.launch_count
     if world > 1:
         t = torch.tensor([ms], device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
     px = world * b * 65536
     value = px * args.steps / (ms * 1e-3)
-    rows, stages, pk = stage_table(log, args.steps, ms, {"gemm_projection_fwd": 3, "modconv": 3, "modconv_up": 3})
     # e2e: pinned host z in, int64 label maps back on the host, every step
     sync()
     t0 = time.perf_counter()
     for i in range(args.steps):
         with torch.no_grad():
             w = gen.style(zs[args.warmup + i].to(dev, non_blocking=True))
-        host = step(w).cpu()
+        host = run(w).cpu()
     sync()
     dt = time.perf_counter() - t0
     if world > 1:
@@ -728,7 +743,9 @@ def run_labelmap(args):
             "data": "synthetic",
             "config": {"workload": labelmap_workload_name(b), "images_per_gpu": b,
                        "l2": "inputs_larger_than_l2 (codes 512 x 65536 x 4 B = 134 MB per image)",
-                       "parallelism": "replicas (no collective)"},
+                       "parallelism": "replicas (no collective)",
+                       "launch": "one CUDA-graph replay per step (engine.PredictGraph)" if graph is not None else "stream launches"},
+            "eager_ms_per_step": eager_ms / args.steps,
             "roofline": roofline_of(rows, stages, pk), "roofline_stages": rows, "cpu_baseline": cpu_base,
             "e2e": {"value": px * args.steps / dt, "unit": "pixels/s", "h2d_bytes_per_step": b * 512 * 4,
                     "d2h_bytes_per_step": b * 65536 * 8, "ms_per_step": dt * 1e3 / args.steps},
@@ -885,6 +902,7 @@ def main():
                     help="pixel x prototype score GEMM on single fp16 planes of the unit-norm operands (|dS| 1.3e-5 "
                          "rms, codes within 3e-3 rms) instead of the default 3-plane bf16 split (2e-7 / 5e-5)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="label-map workload: stream launches instead of a CUDA graph")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

@@ -799,3 +799,48 @@ def predict_codes(gen, w_proj, w, mean_latent, truncation, hlen, passes=3, image
     if want_planes:
         return preds, labels.view(b, h, wd), (z_hi, z_lo)
     return preds, labels.view(b, h, wd)
+
+
+class PredictGraph:
+    """`predict_codes` for a fixed batch size, captured once as a CUDA graph and replayed: the label-map path of a
+    batch is ~150 launches of which many (the 4x4 ... 32x32 synthesis layers, the small per-resolution projections)
+    are shorter than the gap between two stream launches; a graph replay issues them back to back.
+
+        g = PredictGraph(gen, w_proj, mean_latent, truncation, hlen, batch=16)
+        preds, labels = g(w)            # views of the graph's static outputs: valid until the next call
+
+    The generator weights and `w_proj` are baked into the captured launches by ADDRESS (their values may change in
+    place; re-create the object if the tensors are replaced).  Results are bit-identical to `predict_codes`."""
+
+    def __init__(self, gen, w_proj, mean_latent, truncation, hlen, batch, passes=3, want_planes=False,
+                 hf_interp='nearest'):
+        dev = w_proj.device
+        self.args = (gen, w_proj, mean_latent, truncation, hlen, passes, want_planes, hf_interp)
+        self.w_static = torch.zeros((batch, gen.style_dim), dtype=torch.float32, device=dev)
+        self.batch = batch
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(side):                     # warm-up outside the capture: lazy caches, function attributes
+            for _ in range(2):
+                self._run()
+        torch.cuda.current_stream().wait_stream(side)
+        torch.cuda.synchronize()
+        self.graph = torch.cuda.CUDAGraph()
+        launches = L.launch_count
+        with torch.cuda.graph(self.graph):
+            self.out = self._run()
+        self.launches_per_replay = L.launch_count - launches
+
+    def _run(self):
+        gen, w_proj, mean_latent, truncation, hlen, passes, want_planes, hf_interp = self.args
+        return predict_codes(gen, w_proj, self.w_static, mean_latent, truncation, hlen, passes, self.batch,
+                             want_planes, hf_interp)
+
+    @torch.no_grad()
+    def __call__(self, w):
+        if tuple(w.shape) != tuple(self.w_static.shape):
+            raise ValueError(f"PredictGraph was captured for w of shape {tuple(self.w_static.shape)}")
+        self.w_static.copy_(w, non_blocking=True)
+        self.graph.replay()
+        L._count(self.launches_per_replay)
+        return self.out

@@ -660,3 +660,21 @@ def test_cli_entry_points_for_the_baselines(tmp_path):
     assert os.path.exists(os.path.join(out, "kmeans_centers.pt"))
     res = evaluate.main(["--model", "ffhq-256", "--method", "hfc_kmeans", "--out_dir", out, "--num_test_samples", "2"])
     assert [tuple(l.shape) for l in res["layer_labels"]] == [(2, 1, 8 * 2 ** n, 8 * 2 ** n) for n in range(5)]
+
+
+def test_predict_graph_replay_is_bit_identical_to_predict_codes(gen):
+    """engine.PredictGraph: the label-map path of a fixed batch captured as a CUDA graph; replays on new latents give
+    the bits of the stream-launched predict_codes"""
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    torch.manual_seed(9)
+    hlen = 2560
+    wp = (torch.randn(64, hlen) / hlen ** 0.5).cuda()
+    mean_latent = gen.style(torch.randn(64, 64).cuda()).mean(0, keepdim=True)
+    g = E.PredictGraph(gen, wp, mean_latent, 0.7, hlen, batch=3)
+    for seed in (1, 2, 3):
+        w = gen.style(torch.randn(3, 64, generator=torch.Generator().manual_seed(seed)).cuda())
+        ref_p, ref_l = E.predict_codes(gen, wp, w, mean_latent, 0.7, hlen)
+        got_p, got_l = g(w)
+        assert torch.equal(got_l, ref_l) and torch.equal(got_p, ref_p)
+    with pytest.raises(ValueError):
+        g(torch.zeros(2, 64, device="cuda"))
