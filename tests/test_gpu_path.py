@@ -678,3 +678,32 @@ def test_predict_graph_replay_is_bit_identical_to_predict_codes(gen):
         assert torch.equal(got_l, ref_l) and torch.equal(got_p, ref_p)
     with pytest.raises(ValueError):
         g(torch.zeros(2, 64, device="cuda"))
+
+
+def test_train_graph_replay_matches_eager_steps(gen):
+    """engine.TrainGraph: the optimiser step captured as a CUDA graph - two replays on new inputs give the losses and
+    weights of two stream-launched steps from the same state (split-K accumulation order is the only difference)"""
+    from ganecdotes_b200.hfc_with_swav import engine as E
+    torch.manual_seed(2)
+    hlen, c, k = 2560, 64, 48
+    wp = torch.randn(c, hlen) / hlen ** 0.5
+    wk = torch.randn(k, c)
+    bk = 0.05 * torch.randn(k)
+    mean_latent = gen.style(torch.randn(64, 64).cuda()).mean(0, keepdim=True)
+    cfg = E.StepConfig(hlen=hlen, patch_size=96, num_patches=2, niters=10, eps=0.02, temperature=0.02, truncation=0.7,
+                       perturb_std=[1.0] * 3)
+    draws = [make_draws(2, 64, 3, 256, 2, 30 + i) for i in range(3)]
+    heads = [E.SwavHead(wp.clone().cuda(), wk.clone().cuda(), bk.clone().cuda(), 0.01, 0.9, 0.01, 3, 3) for _ in range(2)]
+    inps = [[E.prepare_step_inputs(gen, d, cfg, "cuda") for d in draws] for _ in range(2)]
+    ref = [E.swav_train_step_device(gen, heads[0], mean_latent, inps[0][i], cfg).item() for i in range(3)]
+    first = E.swav_train_step_device(gen, heads[1], mean_latent, inps[1][0], cfg).item()       # eager warm-up step
+    g = E.TrainGraph(gen, heads[1], mean_latent, inps[1][1], cfg)
+    got = [first] + [g(inps[1][i]).item() for i in (1, 2)]
+    for a, b_ in zip(got, ref):
+        assert abs(a - b_) < 1e-5 * abs(b_), (got, ref)
+    for a, b_ in zip((heads[1].w_proj, heads[1].w_proto, heads[1].b_proto), (heads[0].w_proj, heads[0].w_proto, heads[0].b_proto)):
+        torch.testing.assert_close(a, b_, rtol=1e-5, atol=1e-7)
+    assert heads[1].steps == 3
+    with pytest.raises(RuntimeError):
+        E.TrainGraph(gen, E.SwavHead(wp.clone().cuda(), wk.clone().cuda(), bk.clone().cuda(), 0.01, 0.9, 0.01), mean_latent,
+                     inps[1][0], cfg)
