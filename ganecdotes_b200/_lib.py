@@ -1169,6 +1169,23 @@ def argmin_affine(s, bias, scale):
     return labels
 
 
+_CENTER_PLANES = {}
+
+
+def _center_planes(centers):
+    """split-bf16 planes and squared norms of a centre matrix, cached per (storage, version): the centres of a fitted
+    model are re-used for every image"""
+    key = (centers.data_ptr(), centers._version, tuple(centers.shape), str(centers.device))
+    hit = _CENTER_PLANES.get(key)
+    if hit is None:
+        if len(_CENTER_PLANES) > 64:
+            _CENTER_PLANES.clear()
+        c_hi, c_lo = split_planes(centers.contiguous())
+        cn = (centers.double() ** 2).sum(1).float().contiguous()        # ||c_k||^2: K numbers, once per model
+        hit = _CENTER_PLANES[key] = (c_hi, c_lo, cn)
+    return hit
+
+
 def kmeans_assign(x, centers, x2=None, want_dist=False, tensor=None):
     """x [n,c1] (+ x2 [n,c2]) fp32 contiguous, centers [k,c1+c2] -> int32 labels [n]
     (with want_dist: (labels, squared distance to the assigned centre [n])).
@@ -1196,8 +1213,7 @@ def kmeans_assign(x, centers, x2=None, want_dist=False, tensor=None):
         split_planes(x, out=(a_hi[:, :c1], a_lo[:, :c1]))
         if x2 is not None:
             split_planes(x2, out=(a_hi[:, c1:], a_lo[:, c1:]))
-        c_hi, c_lo = split_planes(centers.contiguous())
-        cn = (centers.double() ** 2).sum(1).float().contiguous()        # ||c_k||^2: K numbers, host-side glue
+        c_hi, c_lo, cn = _center_planes(centers)
         s = gemm(a_hi, a_lo, c_hi, c_lo, n, k, c, 3, tag="gemm_kmeans_scores", block_n=64 if k <= 64 else 0)
         return argmin_affine(s, cn, -2.0)
     labels = torch.empty((n,), dtype=torch.int32, device=x.device)
