@@ -138,7 +138,7 @@ _SIGNATURES = {
     "gx_argmax_rows": ([_P, _LL, _I, _LL, _P, _P], _I),
     "gx_kmeans_assign": ([_P, _I, _P, _I, _LL, _P, _I, _P, _P, _P], _I),
     "gx_argmin_affine": ([_P, _LL, _I, _LL, _P, _F, _P, _P], _I),
-    "gx_onehot_nearest": ([_P, _I, _I, _I, _I, _I, _I, _P, _P], _I),
+    "gx_onehot_nearest": ([_P, _I, _I, _I, _I, _I, _I, _P, _LL, _P], _I),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())
@@ -1225,11 +1225,17 @@ def kmeans_assign(x, centers, x2=None, want_dist=False, tensor=None):
     return (labels, dist) if want_dist else labels
 
 
-def onehot_nearest(labels_bhw, k, out_h, out_w):
+def onehot_nearest(labels_bhw, k, out_h, out_w, out=None):
+    """one-hot maps [b, k, out_h, out_w] of int32 labels [b, h, w], nearest resize; `out`: a channel slice
+    [b, k, out_h, out_w] of a wider contiguous [b, K_total, out_h, out_w] tensor to write into"""
     lib = load()
     b, h, w = labels_bhw.shape
-    out = torch.empty((b, k, out_h, out_w), dtype=torch.float32, device=labels_bhw.device)
-    _check(lib.gx_onehot_nearest(_ptr(labels_bhw), b, h, w, k, out_h, out_w, _ptr(out), _stream()),
-           "gx_onehot_nearest")
+    if out is None:
+        out = torch.empty((b, k, out_h, out_w), dtype=torch.float32, device=labels_bhw.device)
+    elif (out.dtype != torch.float32 or tuple(out.shape) != (b, k, out_h, out_w) or out.stride(3) != 1 or
+          out.stride(2) != out_w or out.stride(1) != out_h * out_w):
+        raise GxError("onehot_nearest: out must be a channel slice of a contiguous [b, K, out_h, out_w] float tensor")
+    _check(lib.gx_onehot_nearest(_ptr(labels_bhw), b, h, w, k, out_h, out_w, _ptr(out), out.stride(0) if b > 1 else 0,
+                                 _stream()), "gx_onehot_nearest")
     _count()
     return out

@@ -1504,17 +1504,32 @@ __global__ void argmin_affine_kernel(const float* __restrict__ s, long long n, i
 
 // one-hot cluster maps resized with nearest neighbour (ref hfc_kmeans_clustering.py:190-206)
 __global__ void onehot_nearest_kernel(const int* __restrict__ labels, int b, int h, int w, int k, int oh, int ow,
-                                      float* __restrict__ out) {
-  const long long total = (long long)b * k * oh * ow;
+                                      long long out_bstride, int vw, float* __restrict__ out) {
+  // vw = 4: four consecutive output columns per thread (one 128-bit store; the host checks ow % 4 and alignment);
+  // out[bb] starts at bb * out_bstride so that a layer writes its K channels straight into the concatenated
+  // [B, sum K, oh, ow] maps
+  const int owv = ow / vw;
+  const long long total = (long long)b * k * oh * owv;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < total;
        i += (long long)gridDim.x * blockDim.x) {
     long long r = i;
-    const int ox = (int)(r % ow); r /= ow;
+    const int oxv = (int)(r % owv); r /= owv;
     const int oy = (int)(r % oh); r /= oh;
     const int kk = (int)(r % k);
     const int bb = (int)(r / k);
-    const int sy = (int)(((long long)oy * h) / oh), sx = (int)(((long long)ox * w) / ow);
-    out[i] = labels[((long long)bb * h + sy) * w + sx] == kk ? 1.f : 0.f;
+    const int sy = (int)(((long long)oy * h) / oh);
+    const int* lrow = labels + ((long long)bb * h + sy) * w;
+    float* dst = out + (long long)bb * out_bstride + ((long long)kk * oh + oy) * ow + (long long)oxv * vw;
+    if (vw == 4) {
+      float4 v;
+      v.x = lrow[(int)(((long long)(oxv * 4 + 0) * w) / ow)] == kk ? 1.f : 0.f;
+      v.y = lrow[(int)(((long long)(oxv * 4 + 1) * w) / ow)] == kk ? 1.f : 0.f;
+      v.z = lrow[(int)(((long long)(oxv * 4 + 2) * w) / ow)] == kk ? 1.f : 0.f;
+      v.w = lrow[(int)(((long long)(oxv * 4 + 3) * w) / ow)] == kk ? 1.f : 0.f;
+      *reinterpret_cast<float4*>(dst) = v;
+    } else {
+      dst[0] = lrow[(int)(((long long)oxv * w) / ow)] == kk ? 1.f : 0.f;
+    }
   }
 }
 
@@ -2006,13 +2021,17 @@ extern "C" int gx_argmin_affine(const float* s, long long n, int k, long long ld
 }
 
 extern "C" int gx_onehot_nearest(const int* labels, int b, int h, int w, int k, int out_h, int out_w, float* out,
-                                 void* stream) {
+                                 long long out_batch_stride, void* stream) {
   GX_CHECK_ARG(labels && out && b > 0 && h > 0 && w > 0 && k > 0 && out_h > 0 && out_w > 0);
-  const long long total = (long long)b * k * out_h * out_w;
+  if (out_batch_stride <= 0) out_batch_stride = (long long)k * out_h * out_w;
+  GX_CHECK_ARG(out_batch_stride >= (long long)k * out_h * out_w);
+  const bool vec = (out_w % 4 == 0) && (out_batch_stride % 4 == 0) && ((reinterpret_cast<uintptr_t>(out) & 15) == 0);
+  const long long total = (long long)b * k * out_h * (vec ? out_w / 4 : out_w);
   int grid = gx_cdiv(total, 256);
   const int cap = gx_sm_count() * 16;
   if (grid > cap) grid = cap;
-  onehot_nearest_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(labels, b, h, w, k, out_h, out_w, out);
+  onehot_nearest_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(labels, b, h, w, k, out_h, out_w, out_batch_stride,
+                                                                vec ? 4 : 1, out);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }

@@ -119,24 +119,27 @@ class FlatKMeansAssign(object):
     def predict_grouped(self, grouped):
         """ref BaseHFCModel.predict (:93-110) on grouped per-layer features [B, C_n, h, w]:
         (one-hot maps [B, sum K, out, out], [labels [B, 1, h_n, w_n]])"""
-        outs, labs = [], []
+        labs = []
+        b = grouped[0].shape[0]
+        maps = torch.empty((b, sum(self.clusters_per_layer), self.out_size, self.out_size), dtype=torch.float32,
+                           device=self.device)
+        off = 0
         for n in range(self.n_layers):
-            f = grouped[n]
-            f = (f.permute(0, 2, 3, 1) if f.stride(1) == 1 else f.permute(0, 2, 3, 1).contiguous()).contiguous().float()
-            lab, maps = self._layerwise_predict([f], n)
-            outs.append(maps)
+            f = grouped[n].permute(0, 2, 3, 1).contiguous().float()
+            lab, _ = self._layerwise_predict([f], n, out=maps[:, off:off + self.clusters_per_layer[n]])
+            off += self.clusters_per_layer[n]
             labs.append(lab)
-        return torch.cat(outs, 1), labs
+        return maps, labs
 
-    def _layerwise_predict(self, feats_nhwc: List[torch.Tensor], n: int):
+    def _layerwise_predict(self, feats_nhwc: List[torch.Tensor], n: int, out=None):
         """ref :169-208.  feats_nhwc: the map(s) of layer n as fp32 NHWC tensors.
-        Returns (labels int32 [b,1,h,w], label_maps float [b,K,out,out])."""
+        Returns (labels int32 [b,1,h,w], label_maps float [b,K,out,out]); `out`: where to write the maps."""
         f1 = feats_nhwc[0]
         b, h, w, c1 = f1.shape
         x1 = f1.reshape(-1, c1)
         x2 = feats_nhwc[1].reshape(-1, feats_nhwc[1].shape[3]) if len(feats_nhwc) > 1 else None
         lab = L.kmeans_assign(x1, self.centers[n], x2).view(b, h, w)
-        maps = L.onehot_nearest(lab, self.clusters_per_layer[n], self.out_size, self.out_size)
+        maps = L.onehot_nearest(lab, self.clusters_per_layer[n], self.out_size, self.out_size, out=out)
         return lab.view(b, 1, h, w), maps
 
     def predict(self, features: List[torch.Tensor], channels_last_views=True):
@@ -149,10 +152,14 @@ class FlatKMeansAssign(object):
                 nhwc.append(f.permute(0, 2, 3, 1))
             else:
                 nhwc.append(f.permute(0, 2, 3, 1).contiguous() if channels_last_views else f)
-        outs, labs = [], []
-        for n in range(self.n_layers):
+        labs = []
+        b = nhwc[1].shape[0]
+        maps = torch.empty((b, sum(self.clusters_per_layer), self.out_size, self.out_size), dtype=torch.float32,
+                           device=self.device)
+        off = 0
+        for n in range(self.n_layers):          # every layer writes its K channels straight into the concatenation
             pair = [nhwc[2 * n + 1].contiguous().float(), nhwc[2 * n + 2].contiguous().float()]
-            lab, maps = self._layerwise_predict(pair, n)
-            outs.append(maps)
+            lab, _ = self._layerwise_predict(pair, n, out=maps[:, off:off + self.clusters_per_layer[n]])
+            off += self.clusters_per_layer[n]
             labs.append(lab)
-        return torch.cat(outs, 1), labs
+        return maps, labs

@@ -453,9 +453,10 @@ int gx_argmin_affine(const float* s, long long n, int k, long long lds, const fl
                      void* stream);
 
 /* one-hot cluster maps [b,k,out_h,out_w] from labels [b,h,w], nearest-neighbour resize
- * (ref: hfc_kmeans_clustering.py:190-206). */
+ * (ref: hfc_kmeans_clustering.py:190-206).  out_batch_stride (floats; 0 = k*out_h*out_w): a layer can write its K
+ * channels straight into the concatenated [B, sum K, out_h, out_w] maps (16-byte aligned when out_w % 4 == 0). */
 int gx_onehot_nearest(const int* labels, int b, int h, int w, int k, int out_h, int out_w, float* out,
-                      void* stream);
+                      long long out_batch_stride, void* stream);
 
 #ifdef __cplusplus
 }
