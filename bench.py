@@ -852,17 +852,29 @@ def run_kmeans(args):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = t.item()
     px = world * b * px_img
-    # e2e: features from pinned host memory (the reference's clusterer.predict takes host arrays), labels back
-    host_feats = [feats[i].cpu().pin_memory() for i in range(1, 2 * len(KM_CLUSTERS) + 1)]
+    # e2e: the reference-facing call is predict_hfc_vectors(input_latent) (ref baseline/hfc_kmeans/segmentor.py:168-226):
+    # W+ latents from pinned host memory -> generator -> per-layer assignment -> one-hot maps; label maps back to the host
+    host_lat = lat.cpu().pin_memory()
     sync()
     t0 = time.perf_counter()
     e2e_steps = max(1, min(args.steps, 5))
     for _ in range(e2e_steps):
-        dfe = [feats_nchw[0]] + [h.to(dev, non_blocking=True).permute(0, 3, 1, 2) for h in host_feats] + feats_nchw[11:]
-        _, labs = km.predict(dfe)
+        _, f_e = gen.synthesize(host_lat.to(dev, non_blocking=True), None, need_image=False)
+        _, labs = km.predict([f.permute(0, 3, 1, 2) for f in f_e])
         host = [l.cpu() for l in labs]
     sync()
     dt = time.perf_counter() - t0
+    # the same with the FEATURES coming from pinned host memory (clusterer.predict on host arrays, ref
+    # hfc_kmeans_clustering.py:169-208): bound by the 0.9 GB host-to-device copy per step
+    host_feats = [feats[i].cpu().pin_memory() for i in range(1, 2 * len(KM_CLUSTERS) + 1)]
+    sync()
+    t1 = time.perf_counter()
+    for _ in range(e2e_steps):
+        dfe = [feats_nchw[0]] + [h.to(dev, non_blocking=True).permute(0, 3, 1, 2) for h in host_feats] + feats_nchw[11:]
+        _, labs2 = km.predict(dfe)
+        host = [l.cpu() for l in labs2]
+    sync()
+    dt_feat = time.perf_counter() - t1
     cpu_base = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         v, sec, cores, sample = cpu_kmeans(3, 1)
@@ -877,9 +889,12 @@ def run_kmeans(args):
                        else f"flush: none; {alg_bytes / 1e6:.0f} MB of features per step (< L2: raise --images-per-gpu)",
                        "parallelism": "replicas (no collective)"},
             "roofline": roofline_of(rows, stages, pk), "roofline_stages": rows, "cpu_baseline": cpu_base,
-            "e2e": {"value": px * e2e_steps / dt, "unit": "pixels/s",
-                    "h2d_bytes_per_step": sum(h.numel() * 4 for h in host_feats),
-                    "d2h_bytes_per_step": b * px_img * 4, "ms_per_step": dt * 1e3 / e2e_steps},
+            "e2e": {"value": px * e2e_steps / dt, "unit": "pixels/s", "h2d_bytes_per_step": host_lat.numel() * 4,
+                    "d2h_bytes_per_step": b * px_img * 4, "ms_per_step": dt * 1e3 / e2e_steps,
+                    "path": "host W+ latents -> generator -> assignment + maps -> host label maps (predict_hfc_vectors)"},
+            "e2e_features_from_host": {"value": px * e2e_steps / dt_feat, "unit": "pixels/s",
+                                       "h2d_bytes_per_step": sum(h.numel() * 4 for h in host_feats),
+                                       "d2h_bytes_per_step": b * px_img * 4, "ms_per_step": dt_feat * 1e3 / e2e_steps},
             "gpu_launches": launches, "clocks": clocks, "label_checksum": int(sum(int(l.sum()) for l in labs))}), flush=True)
     if world > 1:
         dist.destroy_process_group()

@@ -105,7 +105,7 @@ _SIGNATURES = {
     "gx_round_f16": ([_P, _LL, _P, _LL, _LL, _P], _I),
     "gx_l2norm_bwd_split": ([_P, _P, _P, _P, _P, _P, _P, _LL, _I, _P], _I),
     "gx_segment_sum_rows": ([_P, _I, _P, _P, _P, _P, _P, _LL, _I, _P], _I),
-    "gx_upsample_sum": ([_I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _I, _P], _I),
+    "gx_upsample_sum": ([_I, _P, _P, _P, _I, _I, _I, _I, _P, _P, _P, _P, _I, _P], _I),
     "gx_pool1d_bilinear": ([_P, _LL, _I, _I, _LL, _P, _P], _I),
     "gx_pool_sum": ([_P, _I, _I, _I, _I, _I, _I, _P, _P, _P, _P], _I),
     "gx_tap_sum": ([_P, _I, _I, _I, _I, _I, _P, _I, _P, _P, _P, _I, _P], _I),
@@ -138,7 +138,10 @@ _SIGNATURES = {
     "gx_argmax_rows": ([_P, _LL, _I, _LL, _P, _P], _I),
     "gx_kmeans_assign": ([_P, _I, _P, _I, _LL, _P, _I, _P, _P, _P], _I),
     "gx_argmin_affine": ([_P, _LL, _I, _LL, _P, _F, _P, _P], _I),
-    "gx_onehot_nearest": ([_P, _I, _I, _I, _I, _I, _I, _P, _LL, _P], _I),
+    "gx_kmeans_frag_bytes": ([_I, _I], _LL),
+    "gx_kmeans_center_frags": ([_P, _I, _I, _P, _P], _I),
+    "gx_kmeans_assign_mma": ([_P, _I, _P, _I, _LL, _P, _P, _I, _P, _P], _I),
+    "gx_onehot_nearest": ([_P, _I, _I, _I, _I, _I, _I, _P, _LL, _F, _F, _P], _I),
 }
 
 EXPORTED_SYMBOLS = tuple(_SIGNATURES.keys())
@@ -148,7 +151,7 @@ def lib_path() -> str:
     return _build.LIB_PATH
 
 
-GX_ABI_VERSION = 200        # include/ganecdotes_b200.h
+GX_ABI_VERSION = 201        # include/ganecdotes_b200.h
 
 
 def load(require_device: bool = True):
@@ -716,8 +719,9 @@ def segment_sum_rows(rows, order, seg_off, nseg, want_lo=False, want_planes=True
     return hi, lo, f
 
 
-def upsample_sum(parts, batch, out_h, out_w, out=None, planes=None, bilinear=False):
-    """parts: list of fp32 [batch, h_l, w_l, c] tensors -> fp32 [batch*out_h*out_w, c]"""
+def upsample_sum(parts, batch, out_h, out_w, out=None, planes=None, bilinear=False, labels=None):
+    """parts: list of fp32 [batch, h_l, w_l, c] tensors -> fp32 [batch*out_h*out_w, c]; labels (int64
+    [batch*out_h*out_w], optional): filled with the first arg-max over c of every pixel by the same kernel"""
     lib = load()
     n = len(parts)
     c = parts[0].shape[3]
@@ -729,11 +733,14 @@ def upsample_sum(parts, batch, out_h, out_w, out=None, planes=None, bilinear=Fal
     if out is None:
         out = torch.empty((batch * out_h * out_w, c), dtype=torch.float32, device=parts[0].device)
     assert out.is_contiguous() and out.numel() == batch * out_h * out_w * c
+    if labels is not None and (labels.dtype != torch.int64 or labels.numel() != batch * out_h * out_w or
+                               not labels.is_contiguous()):
+        raise GxError("upsample_sum: labels must be a contiguous int64 tensor of batch*out_h*out_w elements")
     nbytes = 4.0 * c * (sum(p.shape[0] * p.shape[1] * p.shape[2] for p in parts) + batch * out_h * out_w)
     with timed("upsample_sum", nbytes):
         hi, lo = planes if planes is not None else (None, None)
         _check(lib.gx_upsample_sum(n, ptrs, hs, ws, batch, out_h, out_w, c, _ptr(out), _ptr(hi), _ptr(lo),
-                                   int(bool(bilinear)), _stream()), "gx_upsample_sum")
+                                   _ptr(labels), int(bool(bilinear)), _stream()), "gx_upsample_sum")
     _count()
     return out
 
@@ -1175,14 +1182,28 @@ _CENTER_PLANES = {}
 def _center_planes(centers):
     """split-bf16 planes and squared norms of a centre matrix, cached per (storage, version): the centres of a fitted
     model are re-used for every image"""
-    key = (centers.data_ptr(), centers._version, tuple(centers.shape), str(centers.device))
+    key = (centers.data_ptr(), centers._version, tuple(centers.shape), tuple(centers.stride()), str(centers.device))
     hit = _CENTER_PLANES.get(key)
+    if hit is not None and hit[-1] is not centers and hit[-1].untyped_storage().data_ptr() != \
+            centers.untyped_storage().data_ptr():
+        hit = None
     if hit is None:
         if len(_CENTER_PLANES) > 64:
             _CENTER_PLANES.clear()
         c_hi, c_lo = split_planes(centers.contiguous())
         cn = (centers.double() ** 2).sum(1).float().contiguous()        # ||c_k||^2: K numbers, once per model
-        hit = _CENTER_PLANES[key] = (c_hi, c_lo, cn)
+        frags = cn_pad = None
+        k, c = centers.shape
+        nbytes = load().gx_kmeans_frag_bytes(k, c)
+        if nbytes > 0:      # fragments of the fused kernel (k <= 64): centres in the order its lanes read them
+            frags = torch.empty((nbytes // 16, 4), dtype=torch.int32, device=centers.device)
+            _check(load().gx_kmeans_center_frags(_ptr(centers.contiguous()), k, c, _ptr(frags), _stream()),
+                   "gx_kmeans_center_frags")
+            _count()
+            cn_pad = torch.full((64,), float("inf"), dtype=torch.float32, device=centers.device)
+            cn_pad[:k] = cn
+        # the entry keeps `centers` alive: its address cannot be handed to another tensor while the entry exists
+        hit = _CENTER_PLANES[key] = (c_hi, c_lo, cn, frags, cn_pad, centers)
     return hit
 
 
@@ -1191,9 +1212,12 @@ def kmeans_assign(x, centers, x2=None, want_dist=False, tensor=None):
     (with want_dist: (labels, squared distance to the assigned centre [n])).
 
     Two routes.  Direct (SIMT, sum of (x - c)^2 in fp32): exact distances, used for the k-means fit (want_dist) and
-    for small inputs.  Tensor cores (`tensor`, default for labels-only calls on >= 4096 rows): scores X C^T as a
-    3-pass split-bf16 GEMM (fp32-grade products), then argmin_k(||c_k||^2 - 2 x.c_k) - the GEMM form scikit-learn's
-    predict uses; the features are read once instead of once per centre.  The two routes can differ only where the
+    for small inputs.  Tensor cores (`tensor`, default for labels-only calls on >= 4096 rows): scores X C^T from
+    split-bf16 operands (fp32-grade products), then argmin_k(||c_k||^2 - 2 x.c_k) - the GEMM form scikit-learn's
+    predict uses; the features are read once instead of once per centre.  For k <= 64 the whole route is ONE fused
+    kernel (`gx_kmeans_assign_mma`: rows split in registers, mma.sync against centre fragments in shared memory;
+    channels % 16 == 0); larger k (or tensor="gemm") goes through split_planes -> gx_gemm (3 passes) ->
+    gx_argmin_affine.  The two routes can differ only where the
     two nearest centres are closer than ~1e-4 of the squared distance (accumulation rounding of the x.c term)."""
     lib = load()
     _f32(centers, "centers"), _f32(x, "x"), _f32(x2, "x2")
@@ -1208,12 +1232,21 @@ def kmeans_assign(x, centers, x2=None, want_dist=False, tensor=None):
         if want_dist:
             raise GxError("kmeans_assign: the tensor-core route returns labels only")
         k = centers.shape[0]
+        if tensor != "gemm" and c1 % 16 == 0 and c2 % 16 == 0:
+            frags, cn_pad = _center_planes(centers)[3:5]
+            if frags is not None:       # fused route: rows read once, no planes / scores in HBM
+                labels = torch.empty((n,), dtype=torch.int32, device=x.device)
+                with timed("kmeans_assign_fused", 4.0 * n * c):
+                    _check(lib.gx_kmeans_assign_mma(_ptr(x), c1, _ptr(x2), c2, n, _ptr(frags), _ptr(cn_pad), k,
+                                                    _ptr(labels), _stream()), "gx_kmeans_assign_mma")
+                _count()
+                return labels
         a_hi = torch.empty((n, c), dtype=torch.bfloat16, device=x.device)
         a_lo = torch.empty_like(a_hi)
         split_planes(x, out=(a_hi[:, :c1], a_lo[:, :c1]))
         if x2 is not None:
             split_planes(x2, out=(a_hi[:, c1:], a_lo[:, c1:]))
-        c_hi, c_lo, cn = _center_planes(centers)
+        c_hi, c_lo, cn = _center_planes(centers)[:3]
         s = gemm(a_hi, a_lo, c_hi, c_lo, n, k, c, 3, tag="gemm_kmeans_scores", block_n=64 if k <= 64 else 0)
         return argmin_affine(s, cn, -2.0)
     labels = torch.empty((n,), dtype=torch.int32, device=x.device)
@@ -1225,7 +1258,7 @@ def kmeans_assign(x, centers, x2=None, want_dist=False, tensor=None):
     return (labels, dist) if want_dist else labels
 
 
-def onehot_nearest(labels_bhw, k, out_h, out_w, out=None):
+def onehot_nearest(labels_bhw, k, out_h, out_w, out=None, on=1.0, off=0.0):
     """one-hot maps [b, k, out_h, out_w] of int32 labels [b, h, w], nearest resize; `out`: a channel slice
     [b, k, out_h, out_w] of a wider contiguous [b, K_total, out_h, out_w] tensor to write into"""
     lib = load()
@@ -1235,7 +1268,8 @@ def onehot_nearest(labels_bhw, k, out_h, out_w, out=None):
     elif (out.dtype != torch.float32 or tuple(out.shape) != (b, k, out_h, out_w) or out.stride(3) != 1 or
           out.stride(2) != out_w or out.stride(1) != out_h * out_w):
         raise GxError("onehot_nearest: out must be a channel slice of a contiguous [b, K, out_h, out_w] float tensor")
-    _check(lib.gx_onehot_nearest(_ptr(labels_bhw), b, h, w, k, out_h, out_w, _ptr(out), out.stride(0) if b > 1 else 0,
-                                 _stream()), "gx_onehot_nearest")
+    with timed("onehot_nearest", 4.0 * b * k * out_h * out_w):
+        _check(lib.gx_onehot_nearest(_ptr(labels_bhw), b, h, w, k, out_h, out_w, _ptr(out),
+                                     out.stride(0) if b > 1 else 0, float(on), float(off), _stream()), "gx_onehot_nearest")
     _count()
     return out

@@ -265,11 +265,31 @@ __device__ __forceinline__ void bilinear_src(int dst, int n_in, int n_out, int& 
   i1 = i0 + (i0 < n_in - 1 ? 1 : 0);
   lam = src - (float)i0;
 }
+// first arg-max over the channels of one pixel from per-lane candidates (value, channel): larger value wins, the
+// smaller channel on ties (ref: out_preds.max(1)[1], swav_clustering.py:691)
+__device__ __forceinline__ void upsum_argmax_take(float& best, int& bi, const float4 a, int ch0) {
+  if (a.x > best) { best = a.x; bi = ch0; }
+  if (a.y > best) { best = a.y; bi = ch0 + 1; }
+  if (a.z > best) { best = a.z; bi = ch0 + 2; }
+  if (a.w > best) { best = a.w; bi = ch0 + 3; }
+}
+__device__ __forceinline__ int upsum_argmax_warp(float best, int bi) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+    const int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+    if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+  }
+  return bi == 0x7fffffff ? 0 : bi;
+}
+
 __global__ void upsample_sum_kernel(const UpsumDesc d, float* __restrict__ out, __nv_bfloat16* __restrict__ hi,
-                                    __nv_bfloat16* __restrict__ lo) {
+                                    __nv_bfloat16* __restrict__ lo, long long* __restrict__ labels) {
   const int lane = threadIdx.x & 31;
   const long long pix = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (pix >= d.npix) return;
+  float am_best = -INFINITY;
+  int am_i = 0x7fffffff;
   const int per = d.out_h * d.out_w;
   const int b = (int)(pix / per);
   const int r = (int)(pix - (long long)b * per);
@@ -321,6 +341,7 @@ __global__ void upsample_sum_kernel(const UpsumDesc d, float* __restrict__ out, 
       const int i = lane + 32 * j;
       if (c0 + i < cq) {
         if (out) gx_stg_stream(reinterpret_cast<float4*>(out + pix * d.c) + c0 + i, acc[j]);
+        if (labels) upsum_argmax_take(am_best, am_i, acc[j], 4 * (c0 + i));
         if (hi) {      // operand planes of a consumer conv / GEMM, emitted in the same pass
           uint2 h, l;
           gx_split4(acc[j], h, l);
@@ -329,6 +350,10 @@ __global__ void upsample_sum_kernel(const UpsumDesc d, float* __restrict__ out, 
         }
       }
     }
+  }
+  if (labels) {
+    const int a = upsum_argmax_warp(am_best, am_i);
+    if (lane == 0) labels[pix] = a;
   }
 }
 
@@ -343,7 +368,7 @@ constexpr int UPQ_FINE = 2;
 template <int UPQ_S, int UPQ_F>
 __global__ void __launch_bounds__(256, 2)
 upsample_sum_quad_kernel(const UpsumDesc d, int n_shared, float* __restrict__ out, __nv_bfloat16* __restrict__ hi,
-                         __nv_bfloat16* __restrict__ lo) {
+                         __nv_bfloat16* __restrict__ lo, long long* __restrict__ labels) {
   const int lane = threadIdx.x & 31;
   const int qh = d.out_h >> 1, qw = d.out_w >> 1;
   const long long quad = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
@@ -379,6 +404,8 @@ upsample_sum_quad_kernel(const UpsumDesc d, int n_shared, float* __restrict__ ou
     }
   }
   const long long pix0 = ((long long)b * d.out_h + y) * d.out_w + x;
+  float am_best[4] = {-INFINITY, -INFINITY, -INFINITY, -INFINITY};
+  int am_i[4] = {0x7fffffff, 0x7fffffff, 0x7fffffff, 0x7fffffff};
   for (int i = lane; i < cq; i += 32) {
     float4 v[UPQ_S], f[UPQ_F][4];
 #pragma unroll
@@ -401,12 +428,20 @@ upsample_sum_quad_kernel(const UpsumDesc d, int n_shared, float* __restrict__ ou
         if (m < n_fine) { acc.x += f[m][p].x; acc.y += f[m][p].y; acc.z += f[m][p].z; acc.w += f[m][p].w; }
       const long long pix = pix0 + (p >> 1) * d.out_w + (p & 1);
       if (out) gx_stg_stream(reinterpret_cast<float4*>(out + pix * d.c) + i, acc);
+      if (labels) upsum_argmax_take(am_best[p], am_i[p], acc, 4 * i);
       if (hi) {
         uint2 h2, l2;
         gx_split4(acc, h2, l2);
         reinterpret_cast<uint2*>(hi + pix * d.c)[i] = h2;
         if (lo) reinterpret_cast<uint2*>(lo + pix * d.c)[i] = l2;
       }
+    }
+  }
+  if (labels) {      // the label map of predict_swav_codes from the sums in registers: Z is not read again
+#pragma unroll
+    for (int p = 0; p < 4; ++p) {
+      const int a = upsum_argmax_warp(am_best[p], am_i[p]);
+      if (lane == 0) labels[pix0 + (p >> 1) * d.out_w + (p & 1)] = a;
     }
   }
 }
@@ -1504,7 +1539,7 @@ __global__ void argmin_affine_kernel(const float* __restrict__ s, long long n, i
 
 // one-hot cluster maps resized with nearest neighbour (ref hfc_kmeans_clustering.py:190-206)
 __global__ void onehot_nearest_kernel(const int* __restrict__ labels, int b, int h, int w, int k, int oh, int ow,
-                                      long long out_bstride, int vw, float* __restrict__ out) {
+                                      long long out_bstride, int vw, float on, float off, float* __restrict__ out) {
   // vw = 4: four consecutive output columns per thread (one 128-bit store; the host checks ow % 4 and alignment);
   // out[bb] starts at bb * out_bstride so that a layer writes its K channels straight into the concatenated
   // [B, sum K, oh, ow] maps
@@ -1522,13 +1557,13 @@ __global__ void onehot_nearest_kernel(const int* __restrict__ labels, int b, int
     float* dst = out + (long long)bb * out_bstride + ((long long)kk * oh + oy) * ow + (long long)oxv * vw;
     if (vw == 4) {
       float4 v;
-      v.x = lrow[(int)(((long long)(oxv * 4 + 0) * w) / ow)] == kk ? 1.f : 0.f;
-      v.y = lrow[(int)(((long long)(oxv * 4 + 1) * w) / ow)] == kk ? 1.f : 0.f;
-      v.z = lrow[(int)(((long long)(oxv * 4 + 2) * w) / ow)] == kk ? 1.f : 0.f;
-      v.w = lrow[(int)(((long long)(oxv * 4 + 3) * w) / ow)] == kk ? 1.f : 0.f;
+      v.x = lrow[(int)(((long long)(oxv * 4 + 0) * w) / ow)] == kk ? on : off;
+      v.y = lrow[(int)(((long long)(oxv * 4 + 1) * w) / ow)] == kk ? on : off;
+      v.z = lrow[(int)(((long long)(oxv * 4 + 2) * w) / ow)] == kk ? on : off;
+      v.w = lrow[(int)(((long long)(oxv * 4 + 3) * w) / ow)] == kk ? on : off;
       *reinterpret_cast<float4*>(dst) = v;
     } else {
-      dst[0] = lrow[(int)(((long long)oxv * w) / ow)] == kk ? 1.f : 0.f;
+      dst[0] = lrow[(int)(((long long)oxv * w) / ow)] == kk ? on : off;
     }
   }
 }
@@ -1602,8 +1637,10 @@ extern "C" int gx_pool1d_bilinear(const float* in, long long outer, int n_in, in
 }
 
 extern "C" int gx_upsample_sum(int nlevels, const float* const* p, const int* h, const int* w, int batch, int out_h,
-                               int out_w, int c, float* out, void* hi, void* lo, int bilinear, void* stream) {
-  GX_CHECK_ARG(nlevels > 0 && nlevels <= GX_MAX_LEVELS && p && h && w && (out || hi) && batch > 0 && c % 4 == 0);
+                               int out_w, int c, float* out, void* hi, void* lo, long long* labels, int bilinear,
+                               void* stream) {
+  GX_CHECK_ARG(nlevels > 0 && nlevels <= GX_MAX_LEVELS && p && h && w && (out || hi || labels) && batch > 0 &&
+               c % 4 == 0);
   GX_CHECK_ARG(lo == nullptr || hi != nullptr);
   UpsumDesc d;
   d.nlevels = nlevels;
@@ -1631,13 +1668,13 @@ extern "C" int gx_upsample_sum(int nlevels, const float* const* p, const int* h,
   if (quad_ok) {
     if (n_shared <= 6 && nlevels - n_shared <= 1)
       upsample_sum_quad_kernel<6, 1><<<gx_cdiv(d.npix / 4, 8), 256, 0, (cudaStream_t)stream>>>(
-          d, n_shared, out, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo));
+          d, n_shared, out, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), labels);
     else
       upsample_sum_quad_kernel<UPQ_SHARED, UPQ_FINE><<<gx_cdiv(d.npix / 4, 8), 256, 0, (cudaStream_t)stream>>>(
-          d, n_shared, out, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo));
+          d, n_shared, out, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), labels);
   } else {
     upsample_sum_kernel<<<gx_cdiv(d.npix, 8), 256, 0, (cudaStream_t)stream>>>(
-        d, out, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo));
+        d, out, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), labels);
   }
   GX_LAUNCH_CHECK();
   return GX_OK;
@@ -2021,7 +2058,7 @@ extern "C" int gx_argmin_affine(const float* s, long long n, int k, long long ld
 }
 
 extern "C" int gx_onehot_nearest(const int* labels, int b, int h, int w, int k, int out_h, int out_w, float* out,
-                                 long long out_batch_stride, void* stream) {
+                                 long long out_batch_stride, float on_value, float off_value, void* stream) {
   GX_CHECK_ARG(labels && out && b > 0 && h > 0 && w > 0 && k > 0 && out_h > 0 && out_w > 0);
   if (out_batch_stride <= 0) out_batch_stride = (long long)k * out_h * out_w;
   GX_CHECK_ARG(out_batch_stride >= (long long)k * out_h * out_w);
@@ -2031,7 +2068,7 @@ extern "C" int gx_onehot_nearest(const int* labels, int b, int h, int w, int k, 
   const int cap = gx_sm_count() * 16;
   if (grid > cap) grid = cap;
   onehot_nearest_kernel<<<grid, 256, 0, (cudaStream_t)stream>>>(labels, b, h, w, k, out_h, out_w, out_batch_stride,
-                                                                vec ? 4 : 1, out);
+                                                                vec ? 4 : 1, on_value, off_value, out);
   GX_LAUNCH_CHECK();
   return GX_OK;
 }

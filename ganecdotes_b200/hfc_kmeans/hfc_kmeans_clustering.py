@@ -116,9 +116,10 @@ class FlatKMeansAssign(object):
             centers.append(c)
         return cls(centers, out_size, grouped[0].device)
 
-    def predict_grouped(self, grouped):
+    def predict_grouped(self, grouped, pm1=False):
         """ref BaseHFCModel.predict (:93-110) on grouped per-layer features [B, C_n, h, w]:
-        (one-hot maps [B, sum K, out, out], [labels [B, 1, h_n, w_n]])"""
+        (one-hot maps [B, sum K, out, out], [labels [B, 1, h_n, w_n]]); pm1: maps in {-1, +1} (the `* 2 - 1` of
+        predict_hfc_vectors, ref segmentor.py:222-226, written by the same kernel)"""
         labs = []
         b = grouped[0].shape[0]
         maps = torch.empty((b, sum(self.clusters_per_layer), self.out_size, self.out_size), dtype=torch.float32,
@@ -126,12 +127,12 @@ class FlatKMeansAssign(object):
         off = 0
         for n in range(self.n_layers):
             f = grouped[n].permute(0, 2, 3, 1).contiguous().float()
-            lab, _ = self._layerwise_predict([f], n, out=maps[:, off:off + self.clusters_per_layer[n]])
+            lab, _ = self._layerwise_predict([f], n, out=maps[:, off:off + self.clusters_per_layer[n]], pm1=pm1)
             off += self.clusters_per_layer[n]
             labs.append(lab)
         return maps, labs
 
-    def _layerwise_predict(self, feats_nhwc: List[torch.Tensor], n: int, out=None):
+    def _layerwise_predict(self, feats_nhwc: List[torch.Tensor], n: int, out=None, pm1=False):
         """ref :169-208.  feats_nhwc: the map(s) of layer n as fp32 NHWC tensors.
         Returns (labels int32 [b,1,h,w], label_maps float [b,K,out,out]); `out`: where to write the maps."""
         f1 = feats_nhwc[0]
@@ -139,7 +140,8 @@ class FlatKMeansAssign(object):
         x1 = f1.reshape(-1, c1)
         x2 = feats_nhwc[1].reshape(-1, feats_nhwc[1].shape[3]) if len(feats_nhwc) > 1 else None
         lab = L.kmeans_assign(x1, self.centers[n], x2).view(b, h, w)
-        maps = L.onehot_nearest(lab, self.clusters_per_layer[n], self.out_size, self.out_size, out=out)
+        maps = L.onehot_nearest(lab, self.clusters_per_layer[n], self.out_size, self.out_size, out=out,
+                                off=-1.0 if pm1 else 0.0)
         return lab.view(b, 1, h, w), maps
 
     def predict(self, features: List[torch.Tensor], channels_last_views=True):

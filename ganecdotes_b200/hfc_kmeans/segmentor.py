@@ -125,5 +125,4 @@ class HFCPreprocessor(object):
         _, hfeat = oneshot.create_images_and_features_from_perturbed_latents(
             w, self.model, {'truncation': 0.7, 'mean_latent': mean_latent}, return_feat=True, return_image=True,
             skip_const=True)                                       # the literal 0.7 is the reference's (:198)
-        preds, labels = self.hfc_model.predict_grouped(hfeat[:self.perturb_config['n_layers']])
-        return preds * 2 - 1, labels
+        return self.hfc_model.predict_grouped(hfeat[:self.perturb_config['n_layers']], pm1=True)

@@ -415,7 +415,7 @@ def resolution_groups(feats, hlen):
 
 
 def project_all_pixels(wp_hi, wp_lo, feats, batch, out_h, out_w, hlen, passes, want_hi_only_planes=False, out=None,
-                       out_planes=None, bilinear=False):
+                       out_planes=None, bilinear=False, labels=None):
     """Z[pixel] = Wp . (nearest-upsampled, concatenated feature vector of the pixel) for EVERY
     pixel of `batch` images.  Upsampling and projection are both linear, so
     Z = sum_r upsample(F_r Wp[:, cols_r]^T): each resolution is projected at its native size
@@ -441,10 +441,11 @@ def project_all_pixels(wp_hi, wp_lo, feats, batch, out_h, out_w, hlen, passes, w
         levels.append(dict(a_hi=a_hi, a_lo=None if want_hi_only_planes else a_lo, h=g["h"], w=g["w"], off=g["off"],
                            keep=g["keep"]))
     if len(parts) == 1 and parts[0].shape[1] == out_h and parts[0].shape[2] == out_w and out is None \
-            and out_planes is None:
+            and out_planes is None and labels is None:
         return parts[0].view(-1, c), levels
-    # nearest or bilinear (hf_interp): both are linear, so the per-resolution identity holds for either
-    z = L.upsample_sum(parts, batch, out_h, out_w, out=out, planes=out_planes, bilinear=bilinear)
+    # nearest or bilinear (hf_interp): both are linear, so the per-resolution identity holds for either; `labels`:
+    # the arg-max label map of predict_swav_codes, taken by the same kernel from the sums in registers
+    z = L.upsample_sum(parts, batch, out_h, out_w, out=out, planes=out_planes, bilinear=bilinear, labels=labels)
     return z, levels
 
 
@@ -793,8 +794,7 @@ def predict_codes(gen, w_proj, w, mean_latent, truncation, hlen, passes=3, image
         zc = z[i0 * h * wd: i1 * h * wd]
         pl = (z_hi[i0 * h * wd: i1 * h * wd], z_lo[i0 * h * wd: i1 * h * wd]) if want_planes else None
         project_all_pixels(wp_hi, wp_lo, sub, i1 - i0, h, wd, hlen, passes, out=zc, out_planes=pl,
-                           bilinear=hf_interp == 'bilinear')
-        L.argmax_rows(zc, out=labels[i0 * h * wd: i1 * h * wd])
+                           bilinear=hf_interp == 'bilinear', labels=labels[i0 * h * wd: i1 * h * wd])
     preds = z.view(b, h, wd, c).permute(0, 3, 1, 2)
     if want_planes:
         return preds, labels.view(b, h, wd), (z_hi, z_lo)

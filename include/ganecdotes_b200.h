@@ -23,7 +23,7 @@ extern "C" {
 #define GX_ERR_CUDA (-2)        /* CUDA runtime/driver error: gx_last_cuda_error */
 #define GX_ERR_UNSUPPORTED (-3) /* device is not sm_100                           */
 
-#define GX_ABI_VERSION 200
+#define GX_ABI_VERSION 201
 int gx_version(void);              /* == GX_ABI_VERSION of the header the library was built from */
 int gx_abi_sizeof(int which);      /* sizeof of gx_conv_desc (0), gx_gemm_desc (1), gx_gather_desc (2), gx_ll_desc (3); -1 otherwise */
 int gx_last_cuda_error(void);             /* cudaError_t of the last GX_ERR_CUDA  */
@@ -253,10 +253,12 @@ int gx_segment_sum_rows(const void* rows, int rows_bf16, const int* order, const
  * projection of the nearest-upsampled + concatenated per-pixel vector (ref swav_clustering.py:108-130,
  * :171) is the sum of per-level projections computed at each level's native resolution.
  * hi / lo (optional, out may then be NULL): the same values as bf16 split planes [batch*out_h*out_w, c].
+ * labels (optional, int64 [batch*out_h*out_w]): first arg-max over the c channels of every pixel, taken from the
+ * sums in registers - the label map of predict_swav_codes (ref :691) without a second pass over Z.
  * bilinear != 0: the levels are upsampled like F.interpolate(mode='bilinear', align_corners=False) instead of
  * nearest (swav_args['hf_interp'], ref :112-126) - still linear, so the per-level projection identity holds. */
 int gx_upsample_sum(int nlevels, const float* const* p, const int* h, const int* w, int batch, int out_h,
-                    int out_w, int c, float* out, void* hi, void* lo, int bilinear, void* stream);
+                    int out_w, int c, float* out, void* hi, void* lo, long long* labels, int bilinear, void* stream);
 
 /* Adjoint of 1-D bilinear upsampling (align_corners = False) along the middle axis:
  * in [outer, n_in, inner] -> out [outer, n_out, inner], n_out <= n_in, inner % 4 == 0.  Applied along x and
@@ -452,11 +454,27 @@ int gx_kmeans_assign(const float* x1, int c1, const float* x2, int c2, long long
 int gx_argmin_affine(const float* s, long long n, int k, long long lds, const float* bias, float scale, int* labels,
                      void* stream);
 
+/* The same assignment for few centres (k <= 64) and long fp32 rows (c1, c2 multiples of 16), fused: the feature rows
+ * are read once (4 B per element, no operand planes, no score matrix in HBM), split into bf16 hi / lo in registers and
+ * contracted against centre fragments resident in shared memory on the tensor cores (three bf16 MMAs per product:
+ * fp32-grade), arg-min of ||c_k||^2 - 2 x.c_k in the epilogue.
+ *   gx_kmeans_frag_bytes:   size of the centre-fragment buffer of a [k, c] centre matrix; 0 = shape not supported
+ *                           (k > 64, c % 16, or fragments larger than shared memory) - use gx_gemm + gx_argmin_affine.
+ *   gx_kmeans_center_frags: builds the fragments from fp32 centres [k, c] (once per fitted model).
+ *   gx_kmeans_assign_mma:   cn_pad = ||c_k||^2 padded with +inf to 64 entries; int32 labels out.
+ * (ref: clusterer.predict, baseline/hfc_kmeans/hfc_kmeans_clustering.py:184) */
+long long gx_kmeans_frag_bytes(int k, int c);
+int gx_kmeans_center_frags(const float* centers, int k, int c, void* frags, void* stream);
+int gx_kmeans_assign_mma(const float* x1, int c1, const float* x2, int c2, long long n, const void* frags,
+                         const float* cn_pad, int k, int* labels, void* stream);
+
 /* one-hot cluster maps [b,k,out_h,out_w] from labels [b,h,w], nearest-neighbour resize
  * (ref: hfc_kmeans_clustering.py:190-206).  out_batch_stride (floats; 0 = k*out_h*out_w): a layer can write its K
- * channels straight into the concatenated [B, sum K, out_h, out_w] maps (16-byte aligned when out_w % 4 == 0). */
+ * channels straight into the concatenated [B, sum K, out_h, out_w] maps (16-byte aligned when out_w % 4 == 0).
+ * on_value / off_value: (1, 0) = the maps of clusterer.predict; (1, -1) = the `hier_preds * 2 - 1` encoding that
+ * predict_hfc_vectors returns (ref: baseline/hfc_kmeans/segmentor.py:222-226) without a second pass. */
 int gx_onehot_nearest(const int* labels, int b, int h, int w, int k, int out_h, int out_w, float* out,
-                      long long out_batch_stride, void* stream);
+                      long long out_batch_stride, float on_value, float off_value, void* stream);
 
 #ifdef __cplusplus
 }

@@ -190,11 +190,13 @@ def test_pidray256_label_map_batch():
     assert torch.equal(l2[0], labels[2])
 
 
-@pytest.mark.parametrize("tensor", [False, True])
+@pytest.mark.parametrize("tensor", [False, True, "gemm"])
 @pytest.mark.parametrize("c,h,k", [(1024, 64, 32), (512, 128, 64), (1024, 8, 4)])
 def test_kmeans_assign_full_shapes(c, h, k, tensor):
-    """config 5: per-pixel nearest centre on [b, C, h, w] features, both routes: direct fp32 distances
-    (SIMT) and the tensor-core route (3-pass split-bf16 scores X C^T, then argmin(||c||^2 - 2 x.c))"""
+    """config 5: per-pixel nearest centre on [b, C, h, w] features, all routes: direct fp32 distances
+    (SIMT), the fused tensor-core kernel (True: rows split in registers, mma.sync against centre fragments in shared
+    memory, arg-min of ||c||^2 - 2 x.c in the epilogue) and the GEMM route ("gemm": 3-pass split-bf16 scores X C^T
+    through gx_gemm, then gx_argmin_affine)"""
     from ganecdotes_b200 import _lib as L
     torch.manual_seed(c + h)
     b = 2

@@ -485,9 +485,13 @@ def test_upsample_sum_quad_kernel_is_bit_identical_to_per_pixel_kernel(L, monkey
         monkeypatch.setenv("GX_UPSUM_QUAD", quad)
         hi = torch.empty(b * oh * ow, c, dtype=torch.bfloat16, device="cuda")
         lo = torch.empty_like(hi)
-        res[quad] = (L.upsample_sum(parts, b, oh, ow, planes=(hi, lo)), hi, lo)
+        lab = torch.empty(b * oh * ow, dtype=torch.int64, device="cuda")
+        res[quad] = (L.upsample_sum(parts, b, oh, ow, planes=(hi, lo), labels=lab), hi, lo, lab)
     for x, y in zip(res["0"], res["1"]):
         assert torch.equal(x, y)
+    # the fused label map is the first arg-max of the sums (what a separate arg-max pass over Z gives)
+    assert torch.equal(res["1"][3], L.argmax_rows(res["1"][0]))
+    assert torch.equal(res["1"][3], res["1"][0].max(1)[1])
     ref = torch.zeros(b, oh, ow, c, device="cuda")
     for p in parts:
         ref += torch.nn.functional.interpolate(p.permute(0, 3, 1, 2), size=(oh, ow), mode="nearest").permute(0, 2, 3, 1)
@@ -626,6 +630,36 @@ def test_argmax_and_kmeans(L):
     # exact ties -> first centre
     c2 = torch.stack([c[0], c[1], c[1]])
     assert set(L.kmeans_assign(c2.cuda(), c2.cuda()).cpu().tolist()) <= {0, 1}
+
+
+@pytest.mark.parametrize("n,c1,c2,k", [(5000, 64, 32, 5), (4099, 48, 0, 20), (6001, 256, 256, 50), (4096, 16, 16, 64),
+                                       (4100, 512, 512, 3), (40000, 512, 512, 32), (777, 64, 0, 17), (100, 128, 64, 64)])
+def test_kmeans_fused_kernel_vs_oracle(L, n, c1, c2, k):
+    """gx_kmeans_assign_mma (k <= 64, channels % 16 == 0): ragged row counts, k that is not a multiple of 8, one or two
+    feature maps, more row tiles than resident warps; labels against the oracle's fp32 assignment (they may differ only at near-ties) and against the
+    GEMM route; exact ties go to the first centre"""
+    torch.manual_seed(n + k)
+    x = torch.randn(n, c1 + c2) + 0.3
+    cen = torch.randn(k, c1 + c2) + 0.3
+    x[7] = cen[k - 1]                     # a row that IS a centre
+    xg = x.cuda()
+    a = xg[:, :c1].contiguous()
+    b2 = xg[:, c1:].contiguous() if c2 else None
+    lab = L.kmeans_assign(a, cen.cuda(), b2, tensor=True)
+    assert lab.dtype == torch.int32 and lab.shape == (n,)
+    assert lab[7].item() == k - 1
+    d = torch.cdist(x.double(), cen.double()) ** 2
+    ref = O.kmeans_assign(x, cen)
+    for got in (lab, L.kmeans_assign(a, cen.cuda(), b2, tensor="gemm")):
+        mism = got.cpu().long() != ref.long()
+        if mism.any():
+            top2 = d.topk(2, dim=1, largest=False).values
+            assert ((top2[:, 1] - top2[:, 0])[mism] < 1e-4 * top2[:, 0][mism]).all()
+        assert mism.float().mean().item() < 2e-3
+    # duplicated centres: the first of the two wins
+    cen2 = torch.cat([cen[:1], cen[:1], cen[1:]])[:k].contiguous().cuda()
+    lab2 = L.kmeans_assign(a, cen2, b2, tensor=True)
+    assert not (lab2 == 1).any() or k == 1
 
 
 def test_kmeans_layer_maps_vs_oracle(L):
