@@ -298,13 +298,19 @@ def upfirdn2d_raw(x4, kernel, up_x, up_y, down_x, down_y, px0, px1, py0, py1):
     return out
 
 
-def fused_bias_act_raw(x, bias, refer, act, grad, alpha, scale):
-    """float32, float16 or float64 (bias / refer in the input's type)"""
+def fused_bias_act_raw(x, bias, refer, act, grad, alpha, scale, out=None):
+    """float32, float16 or float64 (bias / refer in the input's type); `out`: a contiguous tensor of the input's
+    type and size to write into (default: a new one)"""
     lib = load()
     if x.dtype not in _DTYPE_CODE:
         raise GxError("fused_bias_act: float32, float16 or float64 input")
     _typed(x, "input", x.dtype)
-    out = torch.empty_like(x)
+    if out is None:
+        out = torch.empty_like(x)
+    else:
+        _typed(out, "out", x.dtype)
+        if out.numel() != x.numel():
+            raise GxError("fused_bias_act: out must have the input's size")
     if x.numel() == 0:
         return out
     if bias is not None:

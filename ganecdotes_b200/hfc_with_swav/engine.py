@@ -168,8 +168,12 @@ class SwavHead:
     parameters of the nn.Modules the caller saves (ref :504-505)."""
 
     def __init__(self, w_proj, w_proto, b_proto, lr, momentum, trust, passes_fwd=3, passes_bwd=1, proto_f16=False,
-                 weight_decay=0.0):
+                 weight_decay=0.0, proj_slope=None):
         self.w_proj, self.w_proto, self.b_proto = w_proj, w_proto, b_proto
+        # projn_nw == '1-layer' (ref :250-256): LeakyReLU(proj_slope) after the projection.  Point-wise, so the
+        # project-every-pixel-once identity holds with the activation applied to Z; no shipped config uses it, and
+        # it runs as two extra element-wise passes (`gx_fused_bias_act` forward / grad mode 1) rather than fused
+        self.proj_slope = None if proj_slope is None else float(proj_slope)
         self.lr, self.momentum, self.trust, self.weight_decay = lr, momentum, trust, float(weight_decay)
         self.passes_fwd, self.passes_bwd = passes_fwd, passes_bwd
         # score GEMM operands.  Default: the 3-plane bf16 split, |dS| = 2e-7 rms -> codes Q within 5e-5 rms of
@@ -269,6 +273,17 @@ def _normalise(head: SwavHead, z, row_idx=None):
     return zn_hi, zn_lo, inv, zn_hi
 
 
+def proj_activation(z, slope, out=None):
+    """LeakyReLU(slope) of the '1-layer' projection network (ref :250-256), element-wise on Z"""
+    return L.fused_bias_act_raw(z, None, None, 3, 0, slope, 1.0, out=out)
+
+
+def proj_activation_bwd(dz, z_act, slope):
+    """dZ * (z > 0 ? 1 : slope); z_act is the activation's OUTPUT (same sign as its input, like the reference's
+    in-place LeakyReLU)"""
+    return L.fused_bias_act_raw(dz, None, z_act, 3, 1, slope, 1.0)
+
+
 def scores_forward(head: SwavHead, feats, out_h, out_w, hlen, row_img, row_src, nrows, eps=None):
     """gather -> projection -> normalise -> prototype scores.  Returns a dict of the
     tensors the backward needs."""
@@ -277,9 +292,12 @@ def scores_forward(head: SwavHead, feats, out_h, out_w, hlen, row_img, row_src, 
     lo = head.passes_fwd == 3
     a_hi, a_lo, _ = L.gather_rows(feats, out_h, out_w, hlen, row_img, row_src, nrows, want_lo=lo)
     z = L.gemm(a_hi, a_lo, head.wp_hi, head.wp_lo, nrows, head.c, hlen, head.passes_fwd, tag="gemm_projection_fwd")
+    if head.proj_slope is not None:
+        z = proj_activation(z, head.proj_slope)
     zn_hi, zn_lo, inv, za = _normalise(head, z)
     s, u0 = _proto_scores(head, za, zn_lo, nrows, eps)
-    return dict(a_hi=a_hi, a_lo=a_lo, zn_hi=zn_hi, zn_lo=zn_lo, inv=inv, s=s, n=nrows, u0=u0)
+    return dict(a_hi=a_hi, a_lo=a_lo, zn_hi=zn_hi, zn_lo=zn_lo, inv=inv, s=s, n=nrows, u0=u0,
+                z_act=z if head.proj_slope is not None else None)
 
 
 def sinkhorn_log_a(s, niters, eps, ws, n_total, group=None, r=None, c=None, pass_fn=None, log_a_fn=None,
@@ -390,7 +408,12 @@ def scores_backward(head: SwavHead, fw, ds_hi, ds_lo, dz_rows_out=None):
         else:
             L.l2norm_bwd_split(dzn, fw["zn_hi"], fw["zn_lo"], fw["inv"], want_planes=False, out_f32=dz_rows_out)
         return
-    dz_hi, dz_lo = L.l2norm_bwd_split(dzn, fw["zn_hi"], fw["zn_lo"], fw["inv"], want_lo=pb == 3)
+    if head.proj_slope is not None:
+        dz = torch.empty((n, c), dtype=torch.float32, device=dzn.device)
+        L.l2norm_bwd_split(dzn, fw["zn_hi"], fw["zn_lo"], fw["inv"], want_planes=False, out_f32=dz)
+        dz_hi, dz_lo = L.split_planes(proj_activation_bwd(dz, fw["z_act"], head.proj_slope), want_lo=pb == 3)
+    else:
+        dz_hi, dz_lo = L.l2norm_bwd_split(dzn, fw["zn_hi"], fw["zn_lo"], fw["inv"], want_lo=pb == 3)
     sk2 = pick_split_k(math.ceil(c / bm) * math.ceil(d / 256), kit, sms)
     L.gemm(dz_hi, dz_lo, fw["a_hi"], fw["a_lo"] if pb == 3 else None, c, d, n, pb, out=head.g_proj, a_mn=True,
            b_mn=True, split_k=sk2, accumulate=True, tag="gemm_gproj_bwd")
@@ -415,7 +438,7 @@ def resolution_groups(feats, hlen):
 
 
 def project_all_pixels(wp_hi, wp_lo, feats, batch, out_h, out_w, hlen, passes, want_hi_only_planes=False, out=None,
-                       out_planes=None, bilinear=False, labels=None):
+                       out_planes=None, bilinear=False, labels=None, act_slope=None):
     """Z[pixel] = Wp . (nearest-upsampled, concatenated feature vector of the pixel) for EVERY
     pixel of `batch` images.  Upsampling and projection are both linear, so
     Z = sum_r upsample(F_r Wp[:, cols_r]^T): each resolution is projected at its native size
@@ -442,23 +465,40 @@ def project_all_pixels(wp_hi, wp_lo, feats, batch, out_h, out_w, hlen, passes, w
                            keep=g["keep"]))
     if len(parts) == 1 and parts[0].shape[1] == out_h and parts[0].shape[2] == out_w and out is None \
             and out_planes is None and labels is None:
-        return parts[0].view(-1, c), levels
+        z = parts[0].view(-1, c)
+        return (proj_activation(z, act_slope) if act_slope is not None else z), levels
     # nearest or bilinear (hf_interp): both are linear, so the per-resolution identity holds for either; `labels`:
     # the arg-max label map of predict_swav_codes, taken by the same kernel from the sums in registers
+    if act_slope is not None:
+        # '1-layer' projection network: the sums, then LeakyReLU; planes and labels come from the activated codes
+        z = proj_activation(L.upsample_sum(parts, batch, out_h, out_w, bilinear=bilinear), act_slope, out=out)
+        if out_planes is not None:
+            L.split_planes(z, out=out_planes)
+        if labels is not None:
+            L.argmax_rows(z, out=labels)
+        return z, levels
     z = L.upsample_sum(parts, batch, out_h, out_w, out=out, planes=out_planes, bilinear=bilinear, labels=labels)
     return z, levels
 
 
-def project_backward_dedup(head: SwavHead, dz_rows, order, seg_off, levels, batch, out_h, out_w, bilinear=False):
+def project_backward_dedup(head: SwavHead, dz_rows, order, seg_off, levels, batch, out_h, out_w, bilinear=False,
+                           z_act=None):
     """gWp[:, cols_r] += pool_r(dZ_pix)^T F_r per resolution, with dZ_pix[pixel] = sum of the dZ rows
-    of all samples of that pixel and pool_r = block sums (the adjoint of nearest upsampling)."""
+    of all samples of that pixel and pool_r = block sums (the adjoint of nearest upsampling).
+    z_act: the activated codes of every pixel ('1-layer' projection network) - the folded dZ of a pixel is
+    multiplied by the LeakyReLU derivative there (the mask depends on the pixel only, so it commutes with the fold)."""
     pb = head.passes_bwd
     c = head.c
     npix = batch * out_h * out_w
     need_f32 = any(lv["h"] != out_h or lv["w"] != out_w for lv in levels)
     need_planes = any(lv["h"] == out_h and lv["w"] == out_w for lv in levels)
-    hi, lo, f32 = L.segment_sum_rows(dz_rows, order, seg_off, npix, want_lo=pb == 3, want_planes=need_planes,
-                                     want_f32=need_f32)
+    if z_act is not None:
+        _, _, f32 = L.segment_sum_rows(dz_rows, order, seg_off, npix, want_planes=False, want_f32=True)
+        f32 = proj_activation_bwd(f32, z_act, head.proj_slope)
+        hi, lo = L.split_planes(f32, want_lo=pb == 3) if need_planes else (None, None)
+    else:
+        hi, lo, f32 = L.segment_sum_rows(dz_rows, order, seg_off, npix, want_lo=pb == 3, want_planes=need_planes,
+                                         want_f32=need_f32)
     cur = dict(h=out_h, w=out_w, f32=f32.view(batch, out_h, out_w, c) if f32 is not None else None, hi=hi, lo=lo)
     bm = 256 if pb == 1 else 128
     sms = L.load().gx_sinkhorn_max_parts()
@@ -696,7 +736,7 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
         # the small levels; rows [0, b*hw) of Z belong to view s, the rest to view t
         z_all, levels = project_all_pixels(head.wp_hi, head.wp_lo, f_both, 2 * b, out_h, out_w, cfg.hlen,
                                            head.passes_fwd, want_hi_only_planes=head.passes_bwd != 3,
-                                           bilinear=cfg.hf_interp == 'bilinear')
+                                           bilinear=cfg.hf_interp == 'bilinear', act_slope=head.proj_slope)
         # dZ rows of every sample, folded per pixel after the last patch: fp32, or - with bf16 backward operands
         # (passes_bwd == 1, the default) - one bf16 plane: half the bytes written here and gathered by the segment sum
         dz_rows = torch.empty((2 * cfg.num_patches * n_patch_rows, head.c), device=dev,
@@ -744,7 +784,8 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
         pending = torch.distributed.all_reduce(head.g_flat, group=group.pg, async_op=True)
     if dedup:
         project_backward_dedup(head, dz_rows, inp.dedup["order"], inp.dedup["seg_off"], levels, 2 * b, out_h, out_w,
-                               bilinear=cfg.hf_interp == 'bilinear')
+                               bilinear=cfg.hf_interp == 'bilinear',
+                               z_act=z_all if head.proj_slope is not None else None)
     if group is not None:
         torch.distributed.all_reduce(head.g_proj, group=group.pg)
         pending.wait()
@@ -764,7 +805,7 @@ def swav_train_step(gen, head: SwavHead, mean_latent, draws: StepDraws, cfg: Ste
 
 @torch.no_grad()
 def predict_codes(gen, w_proj, w, mean_latent, truncation, hlen, passes=3, images_per_chunk=16, want_planes=False,
-                  hf_interp='nearest'):
+                  hf_interp='nearest', proj_slope=None):
     """predict_swav_codes (ref :659-693): generator forward with the fixed noise buffers,
     per-pixel vectors, projection only, arg-max over the code channels.
     Returns (codes [B,C,H,W] fp32 in channels_last memory, labels int64 [B,H,W]); with want_planes also the
@@ -794,7 +835,8 @@ def predict_codes(gen, w_proj, w, mean_latent, truncation, hlen, passes=3, image
         zc = z[i0 * h * wd: i1 * h * wd]
         pl = (z_hi[i0 * h * wd: i1 * h * wd], z_lo[i0 * h * wd: i1 * h * wd]) if want_planes else None
         project_all_pixels(wp_hi, wp_lo, sub, i1 - i0, h, wd, hlen, passes, out=zc, out_planes=pl,
-                           bilinear=hf_interp == 'bilinear', labels=labels[i0 * h * wd: i1 * h * wd])
+                           bilinear=hf_interp == 'bilinear', labels=labels[i0 * h * wd: i1 * h * wd],
+                           act_slope=proj_slope)
     preds = z.view(b, h, wd, c).permute(0, 3, 1, 2)
     if want_planes:
         return preds, labels.view(b, h, wd), (z_hi, z_lo)

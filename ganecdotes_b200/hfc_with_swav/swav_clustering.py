@@ -225,6 +225,17 @@ class SwAVClustering(object):
     def _head_for_inference(self):
         return self.projection[0].weight.data
 
+    def _proj_slope(self):
+        """LeakyReLU slope of a '1-layer' projection network (ref :250-256), None for 'linear'; read from the module so
+        that a `projection.pt` written by either implementation decides."""
+        mods = list(self.projection)
+        if len(mods) == 1:
+            return None
+        if len(mods) == 2 and isinstance(mods[1], nn.LeakyReLU):
+            return float(mods[1].negative_slope)
+        raise NotImplementedError("projection network: 'linear' or '1-layer' ('2-layer' puts BatchNorm1d over the "
+                                  "sampled pixels of a patch between two Linear layers; no shipped config uses it)")
+
     def get_swav_codes_from_hidden_features(self, hfeat, new_shape=None, picks=None, train=False):
         """ref :133-182.  hfeat [1, D, H, W]; picks: a permutation ('random') or the crop offset ('patch')."""
         if self.swav_args['sampling_method'] not in ('random', 'patch'):
@@ -245,6 +256,8 @@ class SwAVClustering(object):
         a_hi, a_lo, _ = L.gather_rows([x], h, w, d, row_img, row_src, n)
         wp_hi, wp_lo = L.split_planes(w_proj)
         z = L.gemm(a_hi, a_lo, wp_hi, wp_lo, n, w_proj.shape[0], d, 3)
+        if self._proj_slope() is not None:
+            z = E.proj_activation(z, self._proj_slope())
         if train:
             zn_hi, zn_lo, _ = L.l2norm_split(z)
             wk_hi, wk_lo = L.split_planes(self.prototype.weight.data)
@@ -269,8 +282,9 @@ class SwAVClustering(object):
         """ref :205-505."""
         num_epochs = self.swav_args['num_epochs']
         num_samples = self.swav_args['num_samples']
-        if self.swav_args['projn_nw'] != 'linear':
-            raise NotImplementedError("projn_nw: only 'linear' (every shipped config)")
+        if self.swav_args['projn_nw'] not in ('linear', '1-layer'):
+            raise NotImplementedError("projn_nw: 'linear' (every shipped config) or '1-layer'; '2-layer' puts "
+                                      "BatchNorm1d over the sampled pixels of a patch between two Linear layers")
         if self.swav_args.get('add_local_loss', False):
             raise NotImplementedError("add_local_loss is broken in the reference (SURVEY §8 quirk 9) and off "
                                       "in every shipped config")
@@ -290,7 +304,10 @@ class SwAVClustering(object):
         for _ in range(num_test_samples):
             self._burn_noise_draws(1)
         # same construction order / default init as the reference (CPU RNG), then to device
-        self.projection = nn.Sequential(nn.Linear(self.swav_args['hlen'], self.nclasses, bias=False)).to(self.device)
+        layers = [nn.Linear(self.swav_args['hlen'], self.nclasses, bias=False)]
+        if self.swav_args['projn_nw'] == '1-layer':               # ref :250-256
+            layers.append(nn.LeakyReLU(inplace=True))
+        self.projection = nn.Sequential(*layers).to(self.device)
         self.prototype = nn.Linear(self.nclasses, self.nprototypes).to(self.device)
         for p in list(self.projection.parameters()) + list(self.prototype.parameters()):
             p.requires_grad_(False)
@@ -316,7 +333,7 @@ class SwAVClustering(object):
         self._head = E.SwavHead(self.projection[0].weight.data, self.prototype.weight.data,
                                 self.prototype.bias.data, ta['lr'], ta.get('momentum', 0.0),
                                 self.swav_args['trust_coeff'], self.passes_fwd, self.passes_bwd, self.proto_f16,
-                                weight_decay=ta.get('weight_decay', 0.0))
+                                weight_decay=ta.get('weight_decay', 0.0), proj_slope=self._proj_slope())
         self._sk_ws = L.SinkhornWorkspace(self.nprototypes, self.device)
         lr_schedule = self.lr_schedule(num_epochs, num_samples) if self.swav_args.get('use_scheduler', False) else None
         b_global = int(self.swav_args.get('batch_latents', 1))
@@ -398,4 +415,4 @@ class SwAVClustering(object):
         """ref :659-693 (the reference ignores `input_is_latent`: always a W latent)."""
         return E.predict_codes(self.model, self.projection[0].weight.data, input_latent, self.mean_latent,
                                self.model_config.truncation, self.swav_args['hlen'], self.passes_fwd,
-                               hf_interp=self._hf_interp())
+                               hf_interp=self._hf_interp(), proj_slope=self._proj_slope())

@@ -422,9 +422,12 @@ def sample_patch_rows(hfeat: torch.Tensor, pick: int, patch_size: int) -> torch.
     return crop[0].flatten(1).t()
 
 
-def swav_scores(rows, w_proj, w_proto, b_proto):
-    """projection -> L2 normalise -> prototype (with bias)  (swav_clustering.py:171-175)."""
+def swav_scores(rows, w_proj, w_proto, b_proto, proj_slope=None):
+    """projection -> L2 normalise -> prototype (with bias)  (swav_clustering.py:171-175).
+    proj_slope: projn_nw == '1-layer' (:250-256) = Linear without bias + LeakyReLU(proj_slope = 0.01)."""
     z = rows @ w_proj.t()
+    if proj_slope is not None:
+        z = F.leaky_relu(z, proj_slope)
     zn = F.normalize(z, p=2, dim=1)
     return zn @ w_proto.t() + b_proto
 
@@ -485,7 +488,7 @@ def larc_sgd_step(params: List[torch.Tensor], grads: List[torch.Tensor],
 
 def swav_step(rows_s: List[torch.Tensor], rows_t: List[torch.Tensor], w_proj, w_proto, b_proto,
               niters: int, eps: float, temperature: float, bufs=None, lr=0.01, momentum=0.9,
-              trust=0.01, marginals=None):
+              trust=0.01, marginals=None, proj_slope=None):
     """One optimiser step of the pretrain loop (swav_clustering.py:377-460) given
     the sampled per-pixel rows of every patch: rows_s[p], rows_t[p] are [N_p, D]
     (for a batch of latents: the row-concatenation over latents = SwAV's joint /
@@ -499,8 +502,8 @@ def swav_step(rows_s: List[torch.Tensor], rows_t: List[torch.Tensor], w_proj, w_
     loss = 0.0
     dbg = []
     for rs, rt in zip(rows_s, rows_t):
-        s_s = swav_scores(rs, wp, wk, bk)
-        s_t = swav_scores(rt, wp, wk, bk)
+        s_s = swav_scores(rs, wp, wk, bk, proj_slope)
+        s_t = swav_scores(rt, wp, wk, bk, proj_slope)
         (r_s, c_s), (r_t, c_t) = marginals if marginals is not None else ((None, None), (None, None))
         with torch.no_grad():
             q_s = sinkhorn_knopp(s_s, niters, eps, r_s, c_s)
@@ -593,7 +596,7 @@ def simclr_predict_codes(sd, w, mean_latent, truncation, params, bn_running, hle
 # Inference  
 # --------------------------------------------------------------------------------------
 
-def predict_codes(sd, w, mean_latent, truncation, w_proj, hlen, mode="nearest"):
+def predict_codes(sd, w, mean_latent, truncation, w_proj, hlen, mode="nearest", proj_slope=None):
     """predict_swav_codes (swav_clustering.py:659-693): codes [B,C,H,W] fp32 and
     int64 label map [B,H,W] = first arg-max over channels."""
     wt = mean_latent + truncation * (w - mean_latent) if truncation < 1 else w
@@ -603,6 +606,8 @@ def predict_codes(sd, w, mean_latent, truncation, w_proj, hlen, mode="nearest"):
     b, d, h, ww = hf.shape
     rows = hf.permute(0, 2, 3, 1).reshape(-1, d)
     z = rows @ w_proj.t()
+    if proj_slope is not None:      # projn_nw == '1-layer' (:250-256)
+        z = F.leaky_relu(z, proj_slope)
     preds = z.view(b, h, ww, -1).permute(0, 3, 1, 2)
     return preds, preds.max(1)[1]
 

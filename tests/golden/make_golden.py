@@ -138,9 +138,10 @@ class Recorder:
         return inner
 
 
-def golden_swav(name="swav", sampling_method='random', patch=100):
+def golden_swav(name="swav", sampling_method='random', patch=100, projn_nw='linear'):
     """sampling_method='patch' (ref swav_clustering.py:150-158, 383-385): `patch` is the side of a square crop at
-    (pick, pick), pick = np.random.choice(h - patch) per patch; saved as swav_patch.npz (training part only)."""
+    (pick, pick), pick = np.random.choice(h - patch) per patch; saved as swav_patch.npz (training part only).
+    projn_nw='1-layer' (ref :250-256: Linear without bias + LeakyReLU(0.01, inplace)): saved as swav_1layer.npz."""
     gen, sd = build_reference_generator()
     swav = ref.swav
     hlen = 512 + 1024 + 1024
@@ -152,7 +153,7 @@ def golden_swav(name="swav", sampling_method='random', patch=100):
                        patch_size=patch, hf_interp='nearest', warmup_epochs=nepochs, start_warmup=0.01,
                        use_scheduler=False, base_lr=0.01, final_lr=0.0001, trust_coeff=0.01,
                        freeze_prototype_niters=313, train_args=dict(lr=0.01, momentum=0.9),
-                       projn_nw='linear', temperature=0.02, nprototypes=nproto, nclasses=nclasses,
+                       projn_nw=projn_nw, temperature=0.02, nprototypes=nproto, nclasses=nclasses,
                        hlen=hlen, add_local_loss=False, plot_test_images=False, epoch_print_freq=1,
                        max_masks=4),
         sinkhorn_args=dict(source_pdf='uniform', niters=10, eps=0.02),
@@ -262,6 +263,10 @@ def golden_swav(name="swav", sampling_method='random', patch=100):
         for k in ("preds", "labels", "pred_w", "sk_scores_s", "sk_scores_t", "sk_q_s", "sk_q_t", "sk_loss",
                   "init_w_proj", "mean_latent_z"):
             out.pop(k)
+    if projn_nw != 'linear':           # the initial weights / mean latent equal swav.npz's (same seed, same constructor)
+        for k in ("sk_scores_s", "sk_scores_t", "sk_q_s", "sk_q_t", "sk_loss", "init_w_proj", "mean_latent_z"):
+            out.pop(k)
+        out["preds"] = preds[:, ::8]
     save(name, **out)
     print(name, "losses", losses)
 
@@ -621,10 +626,14 @@ if __name__ == "__main__":
     if len(sys.argv) > 1 and sys.argv[1] == "swav_patch":
         golden_swav("swav_patch", 'patch', 10)
         sys.exit(0)
+    if len(sys.argv) > 1 and sys.argv[1] == "swav_1layer":
+        golden_swav("swav_1layer", 'random', 100, '1-layer')
+        sys.exit(0)
     golden_ops()
     golden_generator()
     golden_swav()
     golden_swav("swav_patch", 'patch', 10)
+    golden_swav("swav_1layer", 'random', 100, '1-layer')
     golden_simclr()
     golden_labelmap_full()
     golden_labelmap_full(512, "labelmap_car512", 1)

@@ -185,6 +185,57 @@ def test_pretrain_with_patch_sampling_matches_reference_golden(gen, tmp_path):
         assert (f - rf).norm().item() < 3e-2 * upd, ((f - rf).norm().item(), upd)
 
 
+def test_pretrain_with_one_layer_projection_matches_reference_golden(gen, tmp_path):
+    """projn_nw='1-layer' (Linear without bias + LeakyReLU(0.01, inplace), ref swav_clustering.py:250-256): seeded
+    SwAVClustering.pretrain and predict_swav_codes vs the seeded CPU run of the unmodified reference
+    (tests/golden/swav_1layer.npz); the saved projection.pt is the reference's Sequential(Linear, LeakyReLU)."""
+    from ganecdotes_b200.hfc_with_swav import SwAVClustering
+    g = load("swav_1layer")
+    base = load("swav")
+    cfg, mc = golden_cfg(g)
+    cfg["swav_args"]["projn_nw"] = '1-layer'
+    losses = []
+    tb = types.SimpleNamespace(add_scalar=lambda name, val, step: losses.append(float(val)))
+    torch.manual_seed(11)
+    np.random.seed(11)
+    obj = SwAVClustering(gen, mc, out_dir=str(tmp_path), device='cuda', tb=tb, **cfg)
+    recorded = []
+    orig = obj.draw_step
+    obj.draw_step = lambda b: recorded.append(orig(b)) or recorded[-1]
+    obj.pretrain(None, num_test_samples=0)
+    for e, d in enumerate(recorded):        # identical random stream
+        assert torch.equal(d.z, g[f"s{e}_z"])
+        assert torch.equal(d.perms[1][0], g[f"s{e}_perm1"])
+    ref_losses = g["losses"].tolist()
+    assert len(losses) == len(ref_losses)
+    for a, b in zip(losses, ref_losses):
+        assert abs(a - b) < 2e-3 * abs(b), (losses, ref_losses)
+    fin = [obj.projection[0].weight.data.cpu(), obj.prototype.weight.data.cpu(), obj.prototype.bias.data.cpu()]
+    ref_fin = [g["final_w_proj"], g["final_w_proto"], g["final_b_proto"]]
+    ref_init = [base["init_w_proj"], torch.nn.functional.normalize(g["init_w_proto"], dim=1), g["init_b_proto"]]
+    for f, rf, ri in zip(fin, ref_fin, ref_init):
+        upd = (rf - ri).norm().item()
+        assert (f - rf).norm().item() < 3e-2 * upd, ((f - rf).norm().item(), upd)
+    proj = torch.load(os.path.join(str(tmp_path), "projection.pt"), weights_only=False)
+    assert isinstance(proj, torch.nn.Sequential) and isinstance(proj[1], torch.nn.LeakyReLU)
+    # inference through a re-loaded object (the slope comes from the pickled module)
+    cfg["train"] = False
+    obj2 = SwAVClustering(gen, mc, out_dir=str(tmp_path), device='cuda', tb=None, **cfg)
+    obj2.mean_latent = obj.mean_latent          # the constructor drew a new one
+    with torch.no_grad():
+        obj2.projection[0].weight.data.copy_(g["final_w_proj"])
+    preds, labels = obj2.predict_swav_codes(g["pred_w"].cuda())
+    ref_p = g["preds"]
+    assert (preds[:, ::8].cpu() - ref_p).abs().max().item() < 5e-4 * ref_p.abs().max().item()
+    mism = labels.cpu() != g["labels"]
+    if mism.any():   # only where the reference's own top-2 margin is inside the error band
+        full_ref, _ = O.predict_codes(O.init_generator_state(16, 64, 2, 7), g["pred_w"], g["mean_latent"], 0.7,
+                                      g["final_w_proj"], 2560, proj_slope=0.01)
+        top2 = full_ref.topk(2, dim=1).values
+        assert (top2[:, 0] - top2[:, 1])[mism].max().item() < 1e-3 * full_ref.abs().max().item()
+    assert mism.float().mean().item() < 0.02
+
+
 def make_draws(b, d, n_layers, hw, npatch, seed):
     from ganecdotes_b200.hfc_with_swav import engine as E
     g = torch.Generator().manual_seed(seed)
@@ -200,7 +251,7 @@ def make_draws(b, d, n_layers, hw, npatch, seed):
 
 
 def oracle_step(sd, mean_latent, draws, wp, wk, bk, hlen, patch, npatch, pstd, niters, eps, temp, bufs=None,
-                mode="nearest"):
+                mode="nearest", proj_slope=None):
     b = draws.z.shape[0]
     w = O.style_mlp(sd, draws.z)
     rows = {"s": [[] for _ in range(npatch)], "t": [[] for _ in range(npatch)]}
@@ -213,17 +264,22 @@ def oracle_step(sd, mean_latent, draws, wp, wk, bk, hlen, patch, npatch, pstd, n
                 rows[name][p].append(O.sample_rows(hf, draws.perms[p][i], patch))
     rs = [torch.cat(r) for r in rows["s"]]
     rt = [torch.cat(r) for r in rows["t"]]
-    return O.swav_step(rs, rt, wp, wk, bk, niters, eps, temp, bufs)
+    return O.swav_step(rs, rt, wp, wk, bk, niters, eps, temp, bufs, proj_slope=proj_slope)
 
 
-@pytest.mark.parametrize("dedup,proto_f16,interp", [(False, True, "nearest"), (True, True, "nearest"),
-                                                      (True, False, "nearest"), (True, False, "bilinear")])
-def test_batched_joint_step_matches_oracle(gen, dedup, proto_f16, interp):
+@pytest.mark.parametrize("dedup,proto_f16,interp,slope", [(False, True, "nearest", None), (True, True, "nearest", None),
+                                                            (True, False, "nearest", None),
+                                                            (True, False, "bilinear", None),
+                                                            (True, False, "nearest", 0.01),
+                                                            (False, False, "nearest", 0.01),
+                                                            (True, False, "bilinear", 0.01)])
+def test_batched_joint_step_matches_oracle(gen, dedup, proto_f16, interp, slope):
     """B = 3 latents per step: joint-batch Sinkhorn over the row-concatenation.
     dedup=True: every pixel is projected once and the patches gather rows of Z (the path the
     full-size ffhq step takes, where 5 x 20000 samples > 65536 pixels).
     proto_f16: pixel x prototype scores from single fp16 planes of the unit-norm operands (default,
-    |dS| ~ 1e-5) or from the 3-plane bf16 split; both meet the same tolerances."""
+    |dS| ~ 1e-5) or from the 3-plane bf16 split; both meet the same tolerances.
+    slope: projn_nw == '1-layer' (LeakyReLU after the projection, ref :250-256) on both projection routes."""
     from ganecdotes_b200.hfc_with_swav import engine as E
     from ganecdotes_b200 import _lib as L
     sd = O.init_generator_state(16, 64, 2, 7)
@@ -235,7 +291,7 @@ def test_batched_joint_step_matches_oracle(gen, dedup, proto_f16, interp):
     mean_latent = O.style_mlp(sd, torch.randn(64, 64)).mean(0, keepdim=True)
     pstd = [1.0, 0.5, 1.0]
     head = E.SwavHead(wp.clone().cuda(), wk.clone().cuda(), bk.clone().cuda(), 0.01, 0.9, 0.01, 3, 1,
-                      proto_f16=proto_f16)
+                      proto_f16=proto_f16, proj_slope=slope)
     cfg = E.StepConfig(hlen=hlen, patch_size=patch, num_patches=npatch, niters=10, eps=0.02, temperature=0.02,
                        truncation=0.7, perturb_std=pstd, dedup=dedup, hf_interp=interp)
     bufs = None
@@ -243,7 +299,7 @@ def test_batched_joint_step_matches_oracle(gen, dedup, proto_f16, interp):
     for step in range(2):
         draws = make_draws(3, 64, 3, 256, npatch, 100 + step)
         ref = oracle_step(sd, mean_latent, draws, rwp, rwk, rbk, hlen, patch, npatch, pstd, 10, 0.02, 0.02, bufs,
-                          mode=interp)
+                          mode=interp, proj_slope=slope)
         loss = E.swav_train_step(gen, head, mean_latent.cuda(), draws, cfg)
         assert abs(loss.item() - ref["loss"].item()) < 2e-3 * abs(ref["loss"].item()), (loss.item(), ref["loss"])
         # gradients (bf16 backward GEMMs): relative Frobenius error
