@@ -47,15 +47,23 @@ __device__ __forceinline__ uint32_t gx_pack_bf16x2(__nv_bfloat16 a, __nv_bfloat1
   return (uint32_t)__bfloat16_as_ushort(a) | ((uint32_t)__bfloat16_as_ushort(b) << 16);
 }
 
+// two floats -> one packed bf16x2 word (a in the low half), round to nearest even: ONE F2FP.BF16.F32.PACK_AB instead of
+// two single conversions and a PRMT
+__device__ __forceinline__ uint32_t gx_cvt_bf16x2(float a, float b) {
+  uint32_t d;
+  asm("cvt.rn.bf16x2.f32 %0, %1, %2;" : "=r"(d) : "f"(b), "f"(a));
+  return d;
+}
+// split two floats into the packed hi word and the packed lo word (same values as gx_split_bf16 per element)
+__device__ __forceinline__ void gx_split2(float a, float b, uint32_t& hi, uint32_t& lo) {
+  hi = gx_cvt_bf16x2(a, b);
+  lo = gx_cvt_bf16x2(a - __uint_as_float(hi << 16), b - __uint_as_float(hi & 0xffff0000u));
+}
+
 // split 4 floats into packed hi (2 words) and lo (2 words)
 __device__ __forceinline__ void gx_split4(const float4 v, uint2& hi, uint2& lo) {
-  __nv_bfloat16 h0, h1, h2, h3, l0, l1, l2, l3;
-  gx_split_bf16(v.x, h0, l0);
-  gx_split_bf16(v.y, h1, l1);
-  gx_split_bf16(v.z, h2, l2);
-  gx_split_bf16(v.w, h3, l3);
-  hi = make_uint2(gx_pack_bf16x2(h0, h1), gx_pack_bf16x2(h2, h3));
-  lo = make_uint2(gx_pack_bf16x2(l0, l1), gx_pack_bf16x2(l2, l3));
+  gx_split2(v.x, v.y, hi.x, lo.x);
+  gx_split2(v.z, v.w, hi.y, lo.y);
 }
 
 __device__ __forceinline__ float gx_warp_sum(float v) {

@@ -219,6 +219,7 @@ __global__ void fused_bias_act_kernel(const float* __restrict__ x, const float* 
 // each input vector is fetched once per output column.
 // --------------------------------------------------------------------------
 constexpr int BLUR_STRIP = 16;
+constexpr int BLUR_PF = 3;      // L2 prefetch distance of the separable blur kernel, in rows
 
 template <int KH, int KW>
 __global__ void __launch_bounds__(256)
@@ -321,6 +322,7 @@ blur_sep_kernel(const float* __restrict__ in, const float* __restrict__ fir_x, c
                 const float* __restrict__ bias, int act, float* __restrict__ out, const float* __restrict__ next_style,
                 __nv_bfloat16* __restrict__ next_hi, __nv_bfloat16* __restrict__ next_lo, int next_ld, int hi, int wi,
                 int ho, int wo, int c, int cqb) {
+  static_assert(BLUR_STRIP % KT == 0, "the row loop is unrolled by the tap count (static window rotation)");
   const int cq = c >> 2;
   const int cq_groups = cq / cqb;
   const int g = blockIdx.z % cq_groups, b = blockIdx.z / cq_groups;
@@ -330,80 +332,125 @@ blur_sep_kernel(const float* __restrict__ in, const float* __restrict__ fir_x, c
   if (ox >= wo) return;
   const int oy0 = blockIdx.y * BLUR_STRIP;
   const int oy1 = min(ho, oy0 + BLUR_STRIP);
-  float2 gx2[KT], gy2[KT];     // flipped taps (correlation with the flipped filter, ref upfirdn2d_native)
+  // flipped taps (correlation with the flipped filter, ref upfirdn2d_native).  A column outside the input gets a
+  // zero tap and a clamped address, so the row loads need no per-column predicate; addresses are four pointers
+  // advanced by one input row per output row (the previous version recomputed 64-bit addresses: ~80 of its ~210
+  // instructions per row, which bound the kernel by instruction issue at half of the HBM rate).
+  float2 gx2[KT], gy2[KT];
+  const float4* cp[KT];
+  const long long in_row = (long long)wi * cq;
+  const float4* src = reinterpret_cast<const float4*>(in) + (long long)b * hi * in_row + q;
+  int iy = oy0 - pad0;                          // input row of the next load
 #pragma unroll
   for (int i = 0; i < KT; ++i) {
-    const float a = __ldg(fir_x + KT - 1 - i), bq = __ldg(fir_y + KT - 1 - i);
+    const int ix = ox + i - pad0;
+    const bool ok = ix >= 0 && ix < wi;
+    const float a = ok ? __ldg(fir_x + KT - 1 - i) : 0.f, bq = __ldg(fir_y + KT - 1 - i);
     gx2[i] = make_float2(a, a);
     gy2[i] = make_float2(bq, bq);
+    cp[i] = src + (long long)iy * in_row + (long long)min(max(ix, 0), wi - 1) * cq;
   }
-  const float4* src = reinterpret_cast<const float4*>(in) + (long long)b * hi * wi * cq + q;
-  bool col_ok[KT];
+  float4 raw[KT];
+  bool raw_ok = false;                          // block-uniform: the row in `raw` lies inside the input
+  auto load_raw = [&]() {                       // row iy, then advance
+    raw_ok = iy >= 0 && iy < hi;
+    if (raw_ok) {
 #pragma unroll
-  for (int kx = 0; kx < KT; ++kx) col_ok[kx] = (ox + kx - pad0 >= 0) && (ox + kx - pad0 < wi);
-  auto load_raw = [&](int iy, float4 (&v)[KT]) {
-    const bool row_ok = iy >= 0 && iy < hi;
+      for (int kx = 0; kx < KT; ++kx) raw[kx] = __ldg(cp[kx]);
+    }
+    // the loop holds one row of loads in flight per thread (one DRAM latency per output row): pull the row
+    // BLUR_PF rows ahead into L2 meanwhile, no registers needed
+    if (iy + BLUR_PF < hi) asm volatile("prefetch.global.L2 [%0];" ::"l"(cp[KT / 2] + BLUR_PF * in_row));
 #pragma unroll
-    for (int kx = 0; kx < KT; ++kx)
-      v[kx] = (row_ok && col_ok[kx]) ? __ldg(src + ((long long)iy * wi + (ox + kx - pad0)) * cq)
-                                     : make_float4(0.f, 0.f, 0.f, 0.f);
+    for (int kx = 0; kx < KT; ++kx) cp[kx] += in_row;
+    ++iy;
   };
-  auto hfilter = [&](const float4 (&v)[KT]) {
+  auto hfilter = [&]() {
     float2 a = make_float2(0.f, 0.f), bq = make_float2(0.f, 0.f);
+    if (raw_ok) {
 #pragma unroll
-    for (int kx = 0; kx < KT; ++kx) {
-      a = fma2(make_float2(v[kx].x, v[kx].y), gx2[kx], a);
-      bq = fma2(make_float2(v[kx].z, v[kx].w), gx2[kx], bq);
+      for (int kx = 0; kx < KT; ++kx) {
+        a = fma2(make_float2(raw[kx].x, raw[kx].y), gx2[kx], a);
+        bq = fma2(make_float2(raw[kx].z, raw[kx].w), gx2[kx], bq);
+      }
     }
     return make_float4(a.x, a.y, bq.x, bq.y);
   };
-  float4 hw[KT], raw[KT];
-  hw[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+  float4 hw[KT];                                // hw[(r + ky) % KT]: filtered input row of tap ky of output row r
 #pragma unroll
   for (int ky = 0; ky < KT - 1; ++ky) {
-    load_raw(oy0 + ky - pad0, raw);
-    hw[ky + 1] = hfilter(raw);
+    load_raw();
+    hw[ky] = hfilter();
   }
-  load_raw(oy0 + KT - 1 - pad0, raw);
+  load_raw();
   const float nstr = noise ? __ldg(noise_strength) : 0.f;
-  float4 bs = make_float4(0.f, 0.f, 0.f, 0.f);
-  if (bias) bs = __ldg(reinterpret_cast<const float4*>(bias) + q);
-  float4 st = make_float4(1.f, 1.f, 1.f, 1.f);
-  if (next_style) st = __ldg(reinterpret_cast<const float4*>(next_style) + (long long)b * cq + q);
-  for (int oy = oy0; oy < oy1; ++oy) {
+  const float2 ns2 = make_float2(nstr, nstr);
+  float2 b01 = make_float2(0.f, 0.f), b23 = make_float2(0.f, 0.f);
+  if (bias) {
+    const float4 bs = __ldg(reinterpret_cast<const float4*>(bias) + q);
+    b01 = make_float2(bs.x, bs.y);
+    b23 = make_float2(bs.z, bs.w);
+  }
+  float2 s01 = make_float2(1.f, 1.f), s23 = make_float2(1.f, 1.f);
+  if (next_style) {
+    const float4 st = __ldg(reinterpret_cast<const float4*>(next_style) + (long long)b * cq + q);
+    s01 = make_float2(st.x, st.y);
+    s23 = make_float2(st.z, st.w);
+  }
+  const long long opix = ((long long)b * ho + oy0) * wo + ox;
+  float4* op = reinterpret_cast<float4*>(out) + opix * cq + q;
+  const long long out_row = (long long)wo * cq;
+  const int nq = next_ld >> 2;
+  const bool has_noise = noise != nullptr, has_hi = next_hi != nullptr, has_lo = next_lo != nullptr;   // uniform
+  uint2* hp = reinterpret_cast<uint2*>(next_hi) + opix * nq + q;
+  uint2* lp = reinterpret_cast<uint2*>(next_lo) + opix * nq + q;
+  const long long pl_row = (long long)wo * nq;
+  const float* np = noise + (long long)b * noise_bstride + (long long)oy0 * wo + ox;
+  float nz_next = has_noise ? __ldg(np) : 0.f;
+  const float2 k02 = make_float2(0.2f, 0.2f), ks2 = make_float2(1.41421356237309515f, 1.41421356237309515f);
+  for (int oyb = oy0; oyb < oy1; oyb += KT) {
 #pragma unroll
-    for (int ky = 0; ky < KT - 1; ++ky) hw[ky] = hw[ky + 1];
-    hw[KT - 1] = hfilter(raw);
-    float nz = 0.f;
-    if (noise) nz = __ldg(noise + (long long)b * noise_bstride + (long long)oy * wo + ox);
-    if (oy + 1 < oy1) load_raw(oy + KT - pad0, raw);      // next row: in flight during this row's epilogue
-    float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
+    for (int r = 0; r < KT; ++r) {
+      if (oyb + r >= oy1) break;
+      hw[(r + KT - 1) % KT] = hfilter();
+      const float nz = nz_next;
+      if (oyb + r + 1 < oy1) {                  // next row (and its noise value): in flight during this row's epilogue
+        load_raw();
+        if (has_noise) {
+          np += wo;
+          nz_next = __ldg(np);
+        }
+      }
+      float2 a01 = make_float2(0.f, 0.f), a23 = make_float2(0.f, 0.f);
 #pragma unroll
-    for (int ky = 0; ky < KT; ++ky) {
-      a01 = fma2(make_float2(hw[ky].x, hw[ky].y), gy2[ky], a01);
-      a23 = fma2(make_float2(hw[ky].z, hw[ky].w), gy2[ky], a23);
-    }
-    float4 acc = make_float4(a01.x, a01.y, a23.x, a23.y);
-    if (noise) {
-      nz *= nstr;
-      acc.x += nz; acc.y += nz; acc.z += nz; acc.w += nz;
-    }
-    acc.x += bs.x; acc.y += bs.y; acc.z += bs.z; acc.w += bs.w;
-    if (act) {
-      const float s2 = 1.41421356237309515f;
-      acc.x = (acc.x > 0.f ? acc.x : acc.x * 0.2f) * s2;
-      acc.y = (acc.y > 0.f ? acc.y : acc.y * 0.2f) * s2;
-      acc.z = (acc.z > 0.f ? acc.z : acc.z * 0.2f) * s2;
-      acc.w = (acc.w > 0.f ? acc.w : acc.w * 0.2f) * s2;
-    }
-    const long long o = (((long long)b * ho + oy) * wo + ox) * cq + q;
-    gx_stg_stream(reinterpret_cast<float4*>(out) + o, acc);
-    if (next_hi) {
-      uint2 h, l;
-      gx_split4(make_float4(acc.x * st.x, acc.y * st.y, acc.z * st.z, acc.w * st.w), h, l);
-      const long long on = (((long long)b * ho + oy) * wo + ox) * (next_ld >> 2) + q;
-      reinterpret_cast<uint2*>(next_hi)[on] = h;
-      if (next_lo) reinterpret_cast<uint2*>(next_lo)[on] = l;
+      for (int ky = 0; ky < KT; ++ky) {
+        const float4 h = hw[(r + ky) % KT];
+        a01 = fma2(make_float2(h.x, h.y), gy2[ky], a01);
+        a23 = fma2(make_float2(h.z, h.w), gy2[ky], a23);
+      }
+      // reference order: + strength * noise (NoiseInjection), + bias, lrelu(0.2), * sqrt 2 (FusedLeakyReLU)
+      const float2 nz2 = make_float2(nz, nz);
+      a01 = add2(fma2(nz2, ns2, a01), b01);
+      a23 = add2(fma2(nz2, ns2, a23), b23);
+      if (act) {
+        const float2 t01 = mul2(a01, k02), t23 = mul2(a23, k02);     // slope < 1: lrelu(x) = max(x, 0.2 x)
+        a01 = mul2(make_float2(fmaxf(a01.x, t01.x), fmaxf(a01.y, t01.y)), ks2);
+        a23 = mul2(make_float2(fmaxf(a23.x, t23.x), fmaxf(a23.y, t23.y)), ks2);
+      }
+      gx_stg_stream(op, make_float4(a01.x, a01.y, a23.x, a23.y));
+      op += out_row;
+      if (has_hi) {
+        const float2 m01 = mul2(a01, s01), m23 = mul2(a23, s23);
+        uint2 h, l;
+        gx_split2(m01.x, m01.y, h.x, l.x);
+        gx_split2(m23.x, m23.y, h.y, l.y);
+        *hp = h;
+        hp += pl_row;
+        if (has_lo) {
+          *lp = l;
+          lp += pl_row;
+        }
+      }
     }
   }
 }
