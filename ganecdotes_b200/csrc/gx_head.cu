@@ -365,7 +365,9 @@ __global__ void upsample_sum_kernel(const UpsumDesc d, float* __restrict__ out, 
 // HBM: 7 loads + 1 store of 2 KB per pixel).  All loads of a 128-channel sweep are in flight together.
 constexpr int UPQ_SHARED = 8;
 constexpr int UPQ_FINE = 2;
-template <int UPQ_S, int UPQ_F>
+// LABELS: the arg-max bookkeeping is compiled in only for the label-map path (as a run-time test it cost the
+// training step's instantiation 20 %: 0.97 -> 1.19 ms per 16 images)
+template <int UPQ_S, int UPQ_F, bool LABELS>
 __global__ void __launch_bounds__(256, 2)
 upsample_sum_quad_kernel(const UpsumDesc d, int n_shared, float* __restrict__ out, __nv_bfloat16* __restrict__ hi,
                          __nv_bfloat16* __restrict__ lo, long long* __restrict__ labels) {
@@ -428,7 +430,7 @@ upsample_sum_quad_kernel(const UpsumDesc d, int n_shared, float* __restrict__ ou
         if (m < n_fine) { acc.x += f[m][p].x; acc.y += f[m][p].y; acc.z += f[m][p].z; acc.w += f[m][p].w; }
       const long long pix = pix0 + (p >> 1) * d.out_w + (p & 1);
       if (out) gx_stg_stream(reinterpret_cast<float4*>(out + pix * d.c) + i, acc);
-      if (labels) upsum_argmax_take(am_best[p], am_i[p], acc, 4 * i);
+      if constexpr (LABELS) upsum_argmax_take(am_best[p], am_i[p], acc, 4 * i);
       if (hi) {
         uint2 h2, l2;
         gx_split4(acc, h2, l2);
@@ -437,7 +439,7 @@ upsample_sum_quad_kernel(const UpsumDesc d, int n_shared, float* __restrict__ ou
       }
     }
   }
-  if (labels) {      // the label map of predict_swav_codes from the sums in registers: Z is not read again
+  if constexpr (LABELS) {      // the label map of predict_swav_codes from the sums in registers: Z is not read again
 #pragma unroll
     for (int p = 0; p < 4; ++p) {
       const int a = upsum_argmax_warp(am_best[p], am_i[p]);
@@ -1666,12 +1668,19 @@ extern "C" int gx_upsample_sum(int nlevels, const float* const* p, const int* h,
   const char* quad_env = getenv("GX_UPSUM_QUAD");   // GX_UPSUM_QUAD=0: per-pixel kernel (A/B timing)
   if (quad_env && atoi(quad_env) == 0) quad_ok = false;
   if (quad_ok) {
-    if (n_shared <= 6 && nlevels - n_shared <= 1)
-      upsample_sum_quad_kernel<6, 1><<<gx_cdiv(d.npix / 4, 8), 256, 0, (cudaStream_t)stream>>>(
-          d, n_shared, out, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), labels);
+    const dim3 qgrid(gx_cdiv(d.npix / 4, 8));
+    __nv_bfloat16* bhi = reinterpret_cast<__nv_bfloat16*>(hi);
+    __nv_bfloat16* blo = reinterpret_cast<__nv_bfloat16*>(lo);
+    cudaStream_t cs = (cudaStream_t)stream;
+    const bool small = n_shared <= 6 && nlevels - n_shared <= 1;
+    if (small && labels)
+      upsample_sum_quad_kernel<6, 1, true><<<qgrid, 256, 0, cs>>>(d, n_shared, out, bhi, blo, labels);
+    else if (small)
+      upsample_sum_quad_kernel<6, 1, false><<<qgrid, 256, 0, cs>>>(d, n_shared, out, bhi, blo, nullptr);
+    else if (labels)
+      upsample_sum_quad_kernel<UPQ_SHARED, UPQ_FINE, true><<<qgrid, 256, 0, cs>>>(d, n_shared, out, bhi, blo, labels);
     else
-      upsample_sum_quad_kernel<UPQ_SHARED, UPQ_FINE><<<gx_cdiv(d.npix / 4, 8), 256, 0, (cudaStream_t)stream>>>(
-          d, n_shared, out, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), labels);
+      upsample_sum_quad_kernel<UPQ_SHARED, UPQ_FINE, false><<<qgrid, 256, 0, cs>>>(d, n_shared, out, bhi, blo, nullptr);
   } else {
     upsample_sum_kernel<<<gx_cdiv(d.npix, 8), 256, 0, (cudaStream_t)stream>>>(
         d, out, reinterpret_cast<__nv_bfloat16*>(hi), reinterpret_cast<__nv_bfloat16*>(lo), labels);
