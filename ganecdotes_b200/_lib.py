@@ -94,6 +94,8 @@ _SIGNATURES = {
     "gx_modconv_demod": ([_P, _P, _P, _I, _I, _I, _P], _I),
     "gx_modulate_split": ([_P, _LL, _P, _P, _P, _I, _LL, _I, _I, _P], _I),
     "gx_modconv": ([C.POINTER(gx_conv_desc), _P], _I),
+    "gx_modconv_small": ([_P, _P, _P, _P, _P, _LL, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _I, _P], _I),
+    "gx_modconv_small_supported": ([_I, _I], _I),
     "gx_blur_noise_bias_act": ([_P, _P, _I, _I, _I, _I, _P, _LL, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
     "gx_blur_sep_noise_bias_act": ([_P, _P, _P, _I, _I, _I, _P, _LL, _P, _P, _I, _P, _P, _P, _P, _I, _I, _I, _I, _I, _P], _I),
     "gx_torgb": ([_P, _P, _F, _P, _P, _P, _P, _I, _I, _I, _P], _I),
@@ -151,7 +153,7 @@ def lib_path() -> str:
     return _build.LIB_PATH
 
 
-GX_ABI_VERSION = 201        # include/ganecdotes_b200.h
+GX_ABI_VERSION = 202        # include/ganecdotes_b200.h
 
 
 def load(require_device: bool = True):
@@ -506,6 +508,47 @@ def modconv(x_hi, x_lo, w_hi, w_lo, cout, upsample, passes, demod=None, noise=No
                   + 2.0 * npl * 9 * cin_ld * cout)          # input planes once + outputs + weights
     with timed(tag + ("_up" if upsample else ""), 2.0 * b * h * w * 9 * (cin_true or cin) * cout, conv_bytes):
         _check(lib.gx_modconv(C.byref(d), _stream()), "gx_modconv")
+    _count()
+    return out, next_hi, next_lo
+
+
+def modconv_small_supported(cin, cout):
+    return bool(load().gx_modconv_small_supported(int(cin), int(cout)))
+
+
+def modconv_small_weights(weight, scale):
+    """[cout, cin, 3, 3] conv weight -> fp32 [9, cin, cout] with the equalised-lr scale folded in (operand of
+    `modconv_small`; prepared once per weight version, like the bf16 planes of the tcgen05 path)"""
+    return (weight.detach().float() * float(scale)).permute(2, 3, 1, 0).reshape(9, weight.shape[1],
+                                                                                weight.shape[0]).contiguous()
+
+
+def modconv_small(x_nhwc, style, w9, demod=None, noise=None, noise_strength=None, bias=None, act=0, next_style=None,
+                  want_next_lo=True, tag="modconv_small"):
+    """Direct fp32 modulated 3x3 conv for few-channel layers.  x_nhwc fp32 [B,H,W,cin] (unmodulated), style [B,cin],
+    w9 = modconv_small_weights(...).  Returns (out fp32 NHWC [B,H,W,cout], next_hi, next_lo [B,H,W,pad64(cout)])."""
+    lib = load()
+    _f32(x_nhwc, "x"), _f32(style, "style"), _f32(w9, "w9")
+    b, h, w, cin = x_nhwc.shape
+    cout = w9.shape[2]
+    if w9.shape[0] != 9 or w9.shape[1] != cin or style.shape != (b, cin):
+        raise GxError("modconv_small: w9 must be [9, cin, cout] and style [B, cin]")
+    dev = x_nhwc.device
+    out = torch.empty((b, h, w, cout), dtype=torch.float32, device=dev)
+    next_hi = next_lo = None
+    next_ld = pad64(cout)
+    if next_style is not None:
+        next_hi, next_lo = _planes((b, h, w, next_ld), dev, next_ld != cout, want_next_lo)
+    nbs = 0
+    if noise is not None:
+        nbs = 0 if noise.shape[0] == 1 else h * w
+    nbytes = 4.0 * b * h * w * (cin + cout) + (2.0 * (2 if next_lo is not None else 1) * b * h * w * next_ld
+                                                if next_hi is not None else 0.0)
+    with timed(tag, 2.0 * b * h * w * 9 * cin * cout, nbytes):
+        _check(lib.gx_modconv_small(_ptr(x_nhwc), _ptr(style), _ptr(w9), _ptr(demod), _ptr(noise), nbs,
+                                    _ptr(noise_strength), _ptr(bias), int(act), _ptr(out), _ptr(next_style),
+                                    _ptr(next_hi), _ptr(next_lo), next_ld, b, h, w, cin, cout, _stream()),
+               "gx_modconv_small")
     _count()
     return out, next_hi, next_lo
 

@@ -6,7 +6,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB_PATH = os.path.join(CSRC, "libganecdotes_b200.so")
-SOURCES = ["gx_api.cu", "gx_umma.cu", "gx_fir.cu", "gx_synthesis.cu", "gx_head.cu", "gx_exchange.cu", "gx_index.cu", "gx_simclr.cu", "gx_conv_generic.cu", "gx_kmeans.cu"]
+SOURCES = ["gx_api.cu", "gx_umma.cu", "gx_fir.cu", "gx_synthesis.cu", "gx_head.cu", "gx_exchange.cu", "gx_index.cu", "gx_simclr.cu", "gx_conv_generic.cu", "gx_kmeans.cu", "gx_conv_small.cu"]
 HEADERS = ["gx_common.cuh", "gx_ptx.cuh", "gx_ll.cuh", os.path.join("..", "..", "include", "ganecdotes_b200.h")]
 
 NVCC_FLAGS = [

@@ -16,6 +16,7 @@ Forward only: the clustering path runs the generator under no_grad
 (ref hfc_with_swav/swav_clustering.py:593,619,671).
 """
 import math
+import os
 import random
 
 import torch
@@ -162,6 +163,14 @@ class ModulatedConv2d(nn.Module):
         self.demodulate = demodulate
         self._prep = None
         self._prep_version = None
+
+    def prepared_small(self):
+        """fp32 [9, cin, cout] weights of the direct few-channel conv (`gx_modconv_small`), per weight version"""
+        ver = (self.weight._version, self.weight.data_ptr())
+        if getattr(self, "_prep_small", None) is None or self._prep_small_version != ver:
+            self._prep_small = L.modconv_small_weights(self.weight.detach()[0], self.scale)
+            self._prep_small_version = ver
+        return self._prep_small
 
     def prepared(self):
         """(w_hi, w_lo, wsq) planes of scale*W, cached until the weight changes."""
@@ -342,6 +351,14 @@ class Generator(nn.Module):
             preps.append((w_hi, w_lo))
         passes = self.passes
         want_lo = passes == 3
+        # plain 3x3 layers with few channels (BagGAN 128^2 / 256^2: 32 / 16) run as a direct fp32 conv on the fp32
+        # feature map of the layer before: no 64-channel padding, and that layer emits no operand planes for them
+        # (measured, 16 images: 16 -> 16 at 256^2 0.60 -> 0.13 ms; 32 -> 32 at 128^2 0.16 -> 0.20 ms - one CTA of
+        #  115 KB per SM - so only layers of at most 16 channels take this route)
+        small = [(not ly.conv.upsample) and n > 0 and os.environ.get("GX_CONV_SMALL", "1") != "0"
+                 and max(ly.conv.in_channel, ly.conv.out_channel) <= 16
+                 and L.modconv_small_supported(ly.conv.in_channel, ly.conv.out_channel)
+                 for n, ly in enumerate(layers)]
         ci = self.input.input
         key = (ci.data_ptr(), ci._version, ci.device)
         if getattr(self, "_const_key", None) != key:      # NHWC copy of the learned constant, refreshed when it changes
@@ -358,6 +375,8 @@ class Generator(nn.Module):
                 nz = torch.randn(b, 1, res, res, device=dev)
             nz = nz.float().contiguous()
             nxt = styles[n + 1] if n + 1 < len(layers) else None
+            if n + 1 < len(layers) and small[n + 1]:
+                nxt = None                      # the next layer reads this layer's fp32 map itself
             w_hi, w_lo = preps[n]
             strength = layer.noise.weight.detach()
             bias = layer.activate.bias.detach()
@@ -366,6 +385,11 @@ class Generator(nn.Module):
                                       cin_true=conv.in_channel, tag=self._conv_tag(x_hi))
                 f, x_hi, x_lo = L.blur_noise_bias_act(tmp, conv.blur.kernel, conv.blur.pad[0], conv.blur.pad[1], nz,
                                                       strength, bias, 1, nxt, want_lo, sep=conv.blur.separable())
+            elif small[n]:
+                f, x_hi, x_lo = L.modconv_small(feats[-1], styles[n], conv.prepared_small(), demod=demods[n], noise=nz,
+                                                noise_strength=strength, bias=bias, act=1, next_style=nxt,
+                                                want_next_lo=want_lo, tag=f"modconv@{feats[-1].shape[1]}_small"
+                                                if getattr(self, "tag_layers", False) else "modconv_small")
             else:
                 f, x_hi, x_lo = L.modconv(x_hi, x_lo, w_hi, w_lo, conv.out_channel, False, passes, demod=demods[n],
                                           noise=nz, noise_strength=strength, bias=bias, act=1, next_style=nxt,

@@ -23,7 +23,7 @@ extern "C" {
 #define GX_ERR_CUDA (-2)        /* CUDA runtime/driver error: gx_last_cuda_error */
 #define GX_ERR_UNSUPPORTED (-3) /* device is not sm_100                           */
 
-#define GX_ABI_VERSION 201
+#define GX_ABI_VERSION 202
 int gx_version(void);              /* == GX_ABI_VERSION of the header the library was built from */
 int gx_abi_sizeof(int which);      /* sizeof of gx_conv_desc (0), gx_gemm_desc (1), gx_gather_desc (2), gx_ll_desc (3); -1 otherwise */
 int gx_last_cuda_error(void);             /* cudaError_t of the last GX_ERR_CUDA  */
@@ -130,6 +130,18 @@ typedef struct gx_conv_desc {
  * With demod = noise = NULL and unmodulated planes it is a plain (optionally dilated) 3x3 conv + bias +
  * activation: the layers of the one-shot segmentor head. */
 int gx_modconv(const gx_conv_desc* d, void* stream);
+
+/* The same modulated 3x3 conv (stride 1, padding 1) for layers with FEW channels - the 128^2 / 256^2 layers of the
+ * BagGAN generator have 32 / 16 (ref models/baggan/models.py:383-390) - as a direct fp32 conv: the style-modulated
+ * halo tile of the fp32 NHWC input and the whole weight tensor in shared memory, register accumulators, nothing padded
+ * to 64 channels.  x [B,H,W,cin] fp32 (UNmodulated), style [B,cin], w [9,cin,cout] fp32 with the equalised-lr scale
+ * folded in (tap-major, cross-correlation order), demod [B,cout] or NULL; noise / bias / act / next_* as in gx_modconv.
+ * Supported (cin, cout): see gx_modconv_small_supported; anything else returns GX_ERR_ARG (use gx_modconv). */
+int gx_modconv_small(const float* x, const float* style, const float* w, const float* demod, const float* noise,
+                     long long noise_batch_stride, const float* noise_strength, const float* bias, int act,
+                     float* out, const float* next_style, void* next_hi, void* next_lo, int next_ld, int batch,
+                     int h, int w_, int cin, int cout, void* stream);
+int gx_modconv_small_supported(int cin, int cout);
 
 /* Blur (upfirdn2d up=1, down=1, pad=(p0,p1)) of the transposed-conv output fused with
  * noise + bias + leaky-relu*sqrt2 and with the next conv's modulate+split, NHWC.

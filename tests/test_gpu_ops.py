@@ -340,6 +340,47 @@ def test_modconv_fused_epilogue(L):
             torch.testing.assert_close(nxt_got, ref_next, rtol=3e-4, atol=3e-4)
 
 
+@pytest.mark.parametrize("cin,cout,h,w", [(16, 16, 32, 64), (32, 32, 20, 37), (32, 16, 16, 32), (16, 32, 5, 3),
+                                          (8, 8, 33, 40)])
+def test_modconv_small_vs_oracle(L, cin, cout, h, w):
+    """Direct fp32 few-channel modulated conv (`gx_modconv_small`, the BagGAN 128^2 / 256^2 layers) against
+    ModulatedConv2d + NoiseInjection + FusedLeakyReLU of the oracle (ref model.py:327-382), ragged tiles and image
+    borders included, and against the tcgen05 path on the same layer."""
+    torch.manual_seed(cin + cout + h)
+    b = 3
+    x = torch.randn(b, cin, h, w)
+    s = 1 + 0.2 * torch.randn(b, cin)
+    weight = torch.randn(cout, cin, 3, 3)
+    bias = torch.randn(cout)
+    strength = torch.tensor([0.37])
+    nxt = 1 + 0.3 * torch.randn(b, cout)
+    scale = 1 / (cin * 9) ** 0.5
+    assert L.modconv_small_supported(cin, cout) and not L.modconv_small_supported(64, 64)
+    w9 = L.modconv_small_weights(weight.cuda(), scale)
+    _, _, wsq = L.modconv_prepare(weight.cuda(), scale)
+    demod = L.modconv_demod(wsq, s.cuda())
+    x_nhwc = x.permute(0, 2, 3, 1).contiguous().cuda()
+    for per_sample in (False, True):
+        noise = torch.randn(b if per_sample else 1, 1, h, w)
+        wmod = scale * weight[None] * s[:, None, :, None, None]
+        d = torch.rsqrt(wmod.pow(2).sum([2, 3, 4]) + 1e-8)
+        wmod = wmod * d[:, :, None, None, None]
+        ref = torch.cat([torch.nn.functional.conv2d(x[i:i + 1], wmod[i], padding=1) for i in range(b)])
+        ref = O.fused_leaky_relu(ref + strength * noise, bias)
+        out, nh, nl = L.modconv_small(x_nhwc, s.cuda(), w9, demod=demod, noise=noise.cuda(),
+                                      noise_strength=strength.cuda(), bias=bias.cuda(), act=1, next_style=nxt.cuda())
+        torch.testing.assert_close(out.permute(0, 3, 1, 2).cpu(), ref, rtol=2e-5, atol=2e-5)      # fp32 arithmetic
+        assert nh.shape[-1] == 64 and float(nh[..., cout:].float().abs().max()) == 0.0           # zero padding
+        nxt_got = (nh.float() + nl.float())[..., :cout].permute(0, 3, 1, 2).cpu()
+        torch.testing.assert_close(nxt_got, ref * nxt[:, :, None, None], rtol=3e-5, atol=3e-5)
+    # no demodulation / noise / bias / activation: the bare conv
+    out, nh, nl = L.modconv_small(x_nhwc, s.cuda(), w9)
+    assert nh is None and nl is None
+    wmod = scale * weight[None] * s[:, None, :, None, None]
+    ref = torch.cat([torch.nn.functional.conv2d(x[i:i + 1], wmod[i], padding=1) for i in range(b)])
+    torch.testing.assert_close(out.permute(0, 3, 1, 2).cpu(), ref, rtol=2e-5, atol=2e-5)
+
+
 def test_torgb(L):
     torch.manual_seed(2)
     b, c, h = 2, 64, 8

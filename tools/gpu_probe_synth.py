@@ -5,7 +5,12 @@ from ganecdotes_b200 import _lib as L
 from ganecdotes_b200.stylegan2.model import Generator
 torch.manual_seed(0)
 b = int(sys.argv[1]) if len(sys.argv) > 1 else 16
-g = Generator(256, 512, 8).cuda(); g.tag_layers = True
+if len(sys.argv) > 2 and sys.argv[2] == "pidray":       # BagGAN channel map 512 ... 16 (BASELINE config 4)
+    from ganecdotes_b200.baggan import baggan_channels
+    g = Generator(256, 512, 8, channels=baggan_channels()).cuda()
+else:
+    g = Generator(256, 512, 8).cuda()
+g.tag_layers = True
 lat = torch.randn(b, g.n_latent, 512, device="cuda")
 for _ in range(2): g.synthesize(lat, None, False)
 torch.cuda.synchronize()
