@@ -77,6 +77,8 @@ struct UmmaParams {
   __nv_bfloat16* next_hi;
   __nv_bfloat16* next_lo;
   int next_ld;
+  float* ws;            // split-K conv: per-split partial results [split_k][B*Ho*Wo*Cout]
+  long long ws_stride;
 };
 
 struct TileInfo {
@@ -84,6 +86,7 @@ struct TileInfo {
   int m0, n0, kbeg, kend;
   // conv
   int phase, b0, y0, x0;
+  int split;
 };
 
 __device__ __forceinline__ TileInfo decode_tile(const UmmaParams& p, int w, int rank = 0) {
@@ -97,6 +100,7 @@ __device__ __forceinline__ TileInfo decode_tile(const UmmaParams& p, int w, int 
   t.n0 = tile_n * p.block_n * p.nsub;
   t.m0 = tile_m * BM * p.mtiles;
   t.phase = 0; t.b0 = 0; t.y0 = 0; t.x0 = 0;
+  t.split = split;
   if (p.mode == 0) {
     const int per = (p.kiters_total + p.split_k - 1) / p.split_k;
     t.kbeg = split * per;
@@ -113,8 +117,11 @@ __device__ __forceinline__ TileInfo decode_tile(const UmmaParams& p, int w, int 
     t.b0 = g * p.nb;
     t.y0 = ty * p.th;
     t.x0 = tx * p.tw;
-    t.kbeg = 0;
-    t.kend = p.ntaps[ph] * (p.Cin / BK);
+    // split-K (few pixel tiles): every split owns a non-empty slice of this phase's tap x channel-block loop
+    const int ktot = p.ntaps[ph] * (p.Cin / BK);
+    const int per = (ktot + p.split_k - 1) / p.split_k;
+    t.kbeg = split * per;
+    t.kend = min(ktot, t.kbeg + per);
   }
   return t;
 }
@@ -529,6 +536,15 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
 #pragma unroll
           for (int e = 0; e < 32; ++e) v[e] = __uint_as_float(r[e]);
           const int nq = min(8, (p.Cout - co) >> 2);   // valid float4 groups of this chunk (warp-uniform)
+          if (p.split_k > 1) {
+            // this split's partial sums into its own slice of the workspace (plain stores: every split covers every
+            // pixel); conv_finish_kernel adds the slices in split order and applies the epilogue - deterministic
+            float4* dstp = reinterpret_cast<float4*>(p.ws + (long long)t.split * p.ws_stride + pix * p.Cout + co);
+#pragma unroll
+            for (int e = 0; e < 8; ++e)
+              if (e < nq) dstp[e] = make_float4(v[4 * e], v[4 * e + 1], v[4 * e + 2], v[4 * e + 3]);
+            continue;
+          }
           if (p.demod != nullptr) {
             const float4* dm = reinterpret_cast<const float4*>(p.demod + (long long)b * p.Cout + co);
 #pragma unroll
@@ -599,6 +615,79 @@ gx_umma_kernel(const UmmaParams p, const __grid_constant__ CUtensorMap tm_a_hi,
     tc_fence_after();
     if constexpr (PAIR) tmem_dealloc_pair(tmem_base, TMEM_COLS);
     else tmem_dealloc(tmem_base, TMEM_COLS);
+  }
+}
+
+// Grow-only device workspace of the split-K convs (a few MB: only layers of at most ~64 pixel tiles split).  Allocated
+// outside stream capture only; under capture a too small workspace means "no split" (captured graphs are built after
+// an eager pass of the same shapes, which sizes it).
+float* conv_workspace(size_t bytes, cudaStream_t st) {
+  static float* ws = nullptr;
+  static size_t ws_bytes = 0;
+  if (bytes <= ws_bytes) return ws;
+  cudaStreamCaptureStatus cap = cudaStreamCaptureStatusNone;
+  if (cudaStreamIsCapturing(st, &cap) != cudaSuccess || cap != cudaStreamCaptureStatusNone) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  // a smaller buffer is NOT freed: a kernel in flight or a captured graph may still refer to it (a few MB, and the
+  // sizes grow geometrically).  All split-K convs of a process share the workspace: they must be stream-ordered, as the
+  // engine's are (GX_CONV_SPLITK=0 switches the split off).
+  float* fresh = nullptr;
+  const size_t want = 2 * bytes;
+  if (cudaMalloc(&fresh, want) != cudaSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  ws = fresh;
+  ws_bytes = want;
+  return ws;
+}
+
+// Second stage of a split-K conv: the epilogue of the conv branch above (same order of operations) applied in place to
+// the summed partial results, 4 channels per thread.
+__global__ void conv_finish_kernel(const float* __restrict__ ws, int splits, float* __restrict__ out,
+                                   const float* __restrict__ demod,
+                                   const float* __restrict__ noise, long long noise_bstride,
+                                   const float* __restrict__ noise_strength, const float* __restrict__ bias, int act,
+                                   const float* __restrict__ next_style, __nv_bfloat16* __restrict__ next_hi,
+                                   __nv_bfloat16* __restrict__ next_lo, int next_ld, int hw, int cout, long long n4) {
+  const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n4) return;
+  const int cq = cout >> 2;
+  const long long pix = i / cq;
+  const int co = (int)(i - pix * cq) * 4;
+  const int b = (int)(pix / hw);
+  float4 v = __ldg(reinterpret_cast<const float4*>(ws) + i);
+  for (int sp = 1; sp < splits; ++sp) {             // fixed order: run-to-run identical results
+    const float4 u = __ldg(reinterpret_cast<const float4*>(ws) + (long long)sp * n4 + i);
+    v.x += u.x; v.y += u.y; v.z += u.z; v.w += u.w;
+  }
+  if (demod != nullptr) {
+    const float4 d4 = __ldg(reinterpret_cast<const float4*>(demod + (long long)b * cout + co));
+    v.x *= d4.x; v.y *= d4.y; v.z *= d4.z; v.w *= d4.w;
+  }
+  if (noise != nullptr) {
+    const float nz = __ldg(noise_strength) * __ldg(noise + (long long)b * noise_bstride + (pix - (long long)b * hw));
+    v.x += nz; v.y += nz; v.z += nz; v.w += nz;
+  }
+  if (bias != nullptr) {
+    const float4 b4 = __ldg(reinterpret_cast<const float4*>(bias + co));
+    v.x += b4.x; v.y += b4.y; v.z += b4.z; v.w += b4.w;
+  }
+  if (act == 1) {
+    v.x = lrelu_sqrt2(v.x); v.y = lrelu_sqrt2(v.y); v.z = lrelu_sqrt2(v.z); v.w = lrelu_sqrt2(v.w);
+  } else if (act == 2) {
+    v.x = v.x > 0.f ? v.x : v.x * 0.2f; v.y = v.y > 0.f ? v.y : v.y * 0.2f;
+    v.z = v.z > 0.f ? v.z : v.z * 0.2f; v.w = v.w > 0.f ? v.w : v.w * 0.2f;
+  }
+  reinterpret_cast<float4*>(out)[i] = v;
+  if (next_style != nullptr) {
+    const float4 s0 = __ldg(reinterpret_cast<const float4*>(next_style + (long long)b * cout + co));
+    uint2 h0, l0;
+    gx_split4(make_float4(v.x * s0.x, v.y * s0.y, v.z * s0.z, v.w * s0.w), h0, l0);
+    *reinterpret_cast<uint2*>(next_hi + pix * next_ld + co) = h0;
+    if (next_lo != nullptr) *reinterpret_cast<uint2*>(next_lo + pix * next_ld + co) = l0;
   }
 }
 
@@ -886,14 +975,40 @@ extern "C" int gx_modconv(const gx_conv_desc* d, void* stream) {
   }
   // few pixel tiles (4x4 ... 16x16 layers): narrower channel tiles put more SMs on the layer, which is
   // bound by the serial K loop of a handful of CTAs otherwise
-  if (d->block_n == 0) {
+  p.split_k = 1;
+  {
+    // 4x4 / 8x8 layers: a handful of CTAs each walking the whole tap x channel loop (0.1 ms per layer whatever its
+    // size).  Split that loop over otherwise idle SMs (full-width channel tiles, >= 4 splits): every split stores its
+    // partial sums into its own slice of a workspace and a small second kernel adds the slices in a fixed order,
+    // applies demodulation / noise / bias / activation and emits the next layer's planes.
+    static const bool no_split = getenv("GX_CONV_SPLITK") != nullptr && atoi(getenv("GX_CONV_SPLITK")) == 0;
+    const int units = (p.pair ? p.tiles_m / 2 : p.tiles_m) * gx_cdiv(d->cout, bn);
+    const int cblocks = cin_ld / BK;
+    int sk = (no_split || d->block_n != 0) ? 1 : gx_sm_count() / (units * (p.pair ? 2 : 1));
+    if (sk > 16) sk = 16;
+    auto all_nonempty = [&](int s_) {
+      for (int ph = 0; ph < p.nphases; ++ph) {
+        const int ktot = p.ntaps[ph] * cblocks;
+        if ((s_ - 1) * gx_cdiv(ktot, s_) >= ktot) return false;
+      }
+      return true;
+    };
+    while (sk > 1 && !all_nonempty(sk)) --sk;
+    // (two splits pay for the second kernel on a plain conv - 72 k-blocks per tile - but not on the sub-pixel phases
+    //  of a transposed conv, whose longest phase has 32)
+    if (sk >= (p.upsample ? 4 : 2)) {
+      p.ws_stride = (long long)d->batch * p.Ho * p.Wo * d->cout;
+      p.ws = conv_workspace((size_t)sk * (size_t)p.ws_stride * sizeof(float), (cudaStream_t)stream);
+      if (p.ws != nullptr) p.split_k = sk;      // no workspace (allocation refused, e.g. under stream capture): no split
+    }
+  }
+  if (d->block_n == 0 && p.split_k == 1) {
     while (bn > 64 && p.tiles_m * gx_cdiv(d->cout, bn) * 2 <= gx_sm_count()) bn >>= 1;
     p.block_n = bn;
   }
   p.stages = pick_stages(p.passes, p.pair ? bn / 2 : bn, 1, d->stages);
   GX_CHECK_ARG(p.stages >= 2);
   p.tiles_n = gx_cdiv(d->cout, bn);
-  p.split_k = 1;
   p.demod = d->demod; p.noise = d->noise; p.noise_bstride = d->noise_batch_stride;
   p.noise_strength = d->noise_strength; p.bias = d->bias; p.act = d->act;
   GX_CHECK_ARG(d->noise == nullptr || d->noise_strength != nullptr);
@@ -928,7 +1043,18 @@ extern "C" int gx_modconv(const gx_conv_desc* d, void* stream) {
     maps[1] = maps[0];
     maps[3] = maps[2];
   }
-  const int total = (p.pair ? p.tiles_m / 2 : p.tiles_m) * p.tiles_n;
+  const int total = (p.pair ? p.tiles_m / 2 : p.tiles_m) * p.tiles_n * p.split_k;
+  if (p.split_k > 1) {
+    cudaStream_t st = (cudaStream_t)stream;
+    const int rc = launch(p, maps, total, st);
+    if (rc != GX_OK) return rc;
+    const long long n4 = p.ws_stride / 4;
+    conv_finish_kernel<<<gx_cdiv(n4, 256), 256, 0, st>>>(p.ws, p.split_k, p.out, p.demod, p.noise, p.noise_bstride, p.noise_strength,
+                                                         p.bias, p.act, p.next_style, p.next_hi, p.next_lo, p.next_ld,
+                                                         p.Ho * p.Wo, d->cout, n4);
+    GX_LAUNCH_CHECK();
+    return GX_OK;
+  }
   return launch(p, maps, total, (cudaStream_t)stream);
 }
 
