@@ -52,14 +52,53 @@ def peaks():
 
 
 class ClockSampler:
-    """`nvidia-smi -lms 100` running beside the timed region: SM clocks and throttle reasons."""
+    """SM clocks and throttle reasons sampled beside the timed region: NVML queries from a thread of this process
+    every 20 ms (pynvml), else `nvidia-smi -lms 100` as a child process.  (The child process perturbs short timed
+    regions - its polls stall CUDA calls for milliseconds - so NVML is preferred.)"""
     Q = ("clocks.sm,clocks.max.sm,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
          "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
 
     def __init__(self, index):
         self.index, self.proc, self.t0, self.t1 = index, None, None, None
+        self.thread, self.stop, self.samples = None, False, []
+
+    def _nvml_loop(self, nv, h):
+        bits = [("hw_slowdown", nv.nvmlClocksEventReasonHwSlowdown if hasattr(nv, "nvmlClocksEventReasonHwSlowdown")
+                 else nv.nvmlClocksThrottleReasonHwSlowdown),
+                ("hw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonHwThermalSlowdown",
+                                                getattr(nv, "nvmlClocksThrottleReasonHwThermalSlowdown", 0))),
+                ("sw_thermal_slowdown", getattr(nv, "nvmlClocksEventReasonSwThermalSlowdown",
+                                                getattr(nv, "nvmlClocksThrottleReasonSwThermalSlowdown", 0))),
+                ("sw_power_cap", getattr(nv, "nvmlClocksEventReasonSwPowerCap",
+                                         getattr(nv, "nvmlClocksThrottleReasonSwPowerCap", 0)))]
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or \
+            nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        mx = nv.nvmlDeviceGetMaxClockInfo(h, nv.NVML_CLOCK_SM)
+        while not self.stop:
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+                r = int(get_reasons(h))
+                self.samples.append((time.time(), float(sm), float(mx), [n for n, b in bits if b and (r & b)]))
+            except Exception:
+                pass
+            time.sleep(0.02)
 
     def start(self):
+        try:
+            import threading
+            import pynvml as nv
+            nv.nvmlInit()
+            # NVML enumerates physical devices: map the CUDA ordinal through CUDA_VISIBLE_DEVICES when it is numeric
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            ids = [v for v in vis.split(",") if v.strip().isdigit()]
+            phys = int(ids[self.index]) if len(ids) > self.index else self.index
+            h = nv.nvmlDeviceGetHandleByIndex(phys)
+            nv.nvmlDeviceGetClockInfo(h, nv.NVML_CLOCK_SM)
+            self.thread = threading.Thread(target=self._nvml_loop, args=(nv, h), daemon=True)
+            self.thread.start()
+            return
+        except Exception:
+            self.thread = None
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), f"--query-gpu=timestamp,{self.Q}",
                                           "--format=csv,noheader,nounits", "-lms", "100"], stdout=subprocess.PIPE,
@@ -75,6 +114,13 @@ class ClockSampler:
 
     def summary(self):
         rows = []
+        if self.thread is not None:
+            self.stop = True
+            self.thread.join(timeout=1.0)
+            sel = [s_ for s_ in self.samples if self.t0 is None or self.t0 - 0.05 <= s_[0] <= self.t1 + 0.05]
+            sm = [s_[1] for s_ in sel]
+            return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(s_[2] for s_ in sel) if sel else None,
+                    "reasons": sorted({n for s_ in sel for n in s_[3]}), "samples": len(sel), "source": "nvml"}
         if self.proc is not None:
             time.sleep(0.15)
             self.proc.terminate()
@@ -822,6 +868,29 @@ def run_kmeans(args):
     for _ in range(args.warmup):
         km.predict(feats_nchw)
     sync()
+    # the step (ten launches, ~0.7 ms) as one CUDA-graph replay, like the label-map workload: as stream launches from
+    # Python it is bound by the host (0.8 ... 3 ms per step from run to run on the same code)
+    graph, per_replay = None, 0
+    if not args.no_graph:
+        try:
+            side = torch.cuda.Stream(device=dev)
+            side.wait_stream(torch.cuda.current_stream())
+            with torch.cuda.stream(side):
+                km.predict(feats_nchw)
+            torch.cuda.current_stream().wait_stream(side)
+            torch.cuda.synchronize()
+            graph = torch.cuda.CUDAGraph()
+            c0 = L.launch_count
+            with torch.cuda.graph(graph):
+                g_out = km.predict(feats_nchw)
+            per_replay = L.launch_count - c0
+            for _ in range(2):
+                graph.replay()
+            sync()
+        except Exception as exc:      # capture refused: stream launches
+            print(f"kmeans-assign: CUDA-graph capture failed ({exc}); timing stream launches", file=sys.stderr)
+            graph = None
+            torch.cuda.synchronize()
     sampler = ClockSampler(local_rank)
     if rank == 0:
         sampler.start()
@@ -831,7 +900,12 @@ def run_kmeans(args):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(args.steps):
-        maps, labs = km.predict(feats_nchw)
+        if graph is not None:
+            graph.replay()
+            L._count(per_replay)
+            maps, labs = g_out
+        else:
+            maps, labs = km.predict(feats_nchw)
     e1.record()
     sync()
     sampler.mark_end()
@@ -856,13 +930,29 @@ def run_kmeans(args):
     # e2e: the reference-facing call is predict_hfc_vectors(input_latent) (ref baseline/hfc_kmeans/segmentor.py:168-226):
     # W+ latents from pinned host memory -> generator -> per-layer assignment -> one-hot maps; label maps back to the host
     host_lat = lat.cpu().pin_memory()
+    e2e_steps = max(1, min(args.steps, 10))
+    host_labs = None
+    step_ms = []
+
+    def e2e_step():
+        nonlocal host_labs
+        _, f_e = gen.synthesize(host_lat.to(dev, non_blocking=True), None, need_image=False)
+        _, labs_ = km.predict([f.permute(0, 3, 1, 2) for f in f_e])
+        if host_labs is None:
+            host_labs = [torch.empty(l.shape, dtype=l.dtype).pin_memory() for l in labs_]
+        for h_, l_ in zip(host_labs, labs_):
+            h_.copy_(l_, non_blocking=True)
+        return labs_
+
+    for _ in range(2):                       # warm-up of this path (pinned buffers, allocator)
+        e2e_step()
     sync()
     t0 = time.perf_counter()
-    e2e_steps = max(1, min(args.steps, 5))
     for _ in range(e2e_steps):
-        _, f_e = gen.synthesize(host_lat.to(dev, non_blocking=True), None, need_image=False)
-        _, labs = km.predict([f.permute(0, 3, 1, 2) for f in f_e])
-        host = [l.cpu() for l in labs]
+        ts = time.perf_counter()
+        labs = e2e_step()
+        torch.cuda.synchronize()             # the label maps of this step are on the host
+        step_ms.append((time.perf_counter() - ts) * 1e3)
     sync()
     dt = time.perf_counter() - t0
     # the same with the FEATURES coming from pinned host memory (clusterer.predict on host arrays, ref
@@ -888,11 +978,14 @@ def run_kmeans(args):
             "config": {"workload": kmeans_workload_name(b), "images_per_gpu": b,
                        "l2": f"inputs_larger_than_l2 ({alg_bytes / 1e6:.0f} MB of features per step)" if alg_bytes > 126e6
                        else f"flush: none; {alg_bytes / 1e6:.0f} MB of features per step (< L2: raise --images-per-gpu)",
-                       "parallelism": "replicas (no collective)"},
+                       "parallelism": "replicas (no collective)",
+                       "launch": "one CUDA-graph replay per step" if graph is not None else "stream launches"},
             "roofline": roofline_of(rows, stages, pk), "roofline_stages": rows, "cpu_baseline": cpu_base,
             "e2e": {"value": px * e2e_steps / dt, "unit": "pixels/s", "h2d_bytes_per_step": host_lat.numel() * 4,
                     "d2h_bytes_per_step": b * px_img * 4, "ms_per_step": dt * 1e3 / e2e_steps,
-                    "path": "host W+ latents -> generator -> assignment + maps -> host label maps (predict_hfc_vectors)"},
+                    "ms_per_step_median": float(np.median(step_ms)), "ms_per_step_max": float(max(step_ms)),
+                    "path": "host W+ latents -> generator -> assignment + maps -> host label maps (predict_hfc_vectors);"
+                            " ~300 stream launches issued from Python per step: bound by the host"},
             "e2e_features_from_host": {"value": px * e2e_steps / dt_feat, "unit": "pixels/s",
                                        "h2d_bytes_per_step": sum(h.numel() * 4 for h in host_feats),
                                        "d2h_bytes_per_step": b * px_img * 4, "ms_per_step": dt_feat * 1e3 / e2e_steps},

@@ -1,0 +1,24 @@
+#!/bin/bash
+# usage (GPU box, repo root): bash tools/gpu_final.sh TAG   -- the round's final single-GPU measurements into gpurun_out/
+T=$1
+O=gpurun_out
+mkdir -p $O
+python -m pytest tests -m gpu -q 2>&1 | tail -3 > $O/${T}_gpu_tests.txt; cat $O/${T}_gpu_tests.txt
+python bench.py > $O/${T}_bench_n1.json 2> $O/${T}_bench_n1.err || tail -5 $O/${T}_bench_n1.err
+python bench.py --impl reference --steps 2 --warmup 1 > $O/${T}_bench_reference_arm.json 2> $O/${T}_ref.err || tail -5 $O/${T}_ref.err
+for w in car-512 pidray-256-labelmap kmeans-assign; do
+  python bench.py --workload $w > $O/${T}_bench_$w.json 2> $O/${T}_$w.err || tail -5 $O/${T}_$w.err
+done
+# launch list of the bench command (after it exited 0 without ncu above)
+ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-file $O/${T}_launches_raw.csv \
+  python bench.py --steps 2 --warmup 1 --no-alt --no-eager --no-cpu-baseline > $O/${T}_ncu_bench.log 2>&1
+python tools/summarize_launches.py $O/${T}_launches_raw.csv $O/${T}_launches.csv "$T: python bench.py --steps 2 --warmup 1 --no-alt --no-eager --no-cpu-baseline" || true
+rm -f $O/${T}_launches_raw.csv
+# full captures of the kernels changed in this session
+python tools/ncu_small.py > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"blur_sep|upsample_sum_quad" \
+  -s 2 -c 2 -o $O/${T}_small python tools/ncu_small.py > $O/${T}_ncu_small.log 2>&1
+python tools/gpu_probe_synth.py 16 pidray > $O/${T}_synth_pidray.txt 2>&1 && ncu --set full --clock-control none --import-source on \
+  -k regex:"modconv_small|conv_finish" -s 4 -c 2 -o $O/${T}_convsmall python tools/gpu_probe_synth.py 16 pidray > $O/${T}_ncu_convsmall.log 2>&1
+python tools/gpu_probe_synth.py 16 > $O/${T}_synth_ffhq.txt 2>&1
+for f in $O/${T}_bench_n1.json $O/${T}_bench_car-512.json $O/${T}_bench_pidray-256-labelmap.json $O/${T}_bench_kmeans-assign.json; do python tools/show_bench.py $f x | head -3; done
+ls -la $O | tail -30
