@@ -539,7 +539,7 @@ def run_swav(args, cfg):
     roofline = roofline_of(stage_rows, stages, pk)
 
     # ---------------------------------------------------------------- alternative precisions, device-timed
-    alt = alt_bwd = None
+    alt = alt_bwd = alt_sk = None
     if not args.no_alt:
         alt_steps = max(1, min(args.steps, 5))
         head.proto_f16 = not args.proto_f16          # the other score-GEMM operand mode
@@ -558,6 +558,16 @@ def run_swav(args, cfg):
                        "note": "backward GEMMs on 3-plane split-bf16 operands: gradients within 3e-3 of fp32 "
                                "instead of 2e-2 (default bf16x1)"}
             del h3
+        # the Sinkhorn passes 2.. on the fp32 scores instead of the 16-bit cache (the round-1 path)
+        cache_was = scfg.sinkhorn_cache16
+        scfg.sinkhorn_cache16 = False
+        timed_steps(head, 0, min(2, nsteps))
+        sk_ms, _ = timed_steps(head, args.warmup, alt_steps)
+        scfg.sinkhorn_cache16 = cache_was
+        alt_sk = {"sinkhorn_cache16": False, "steps": alt_steps, "ms_per_step": sk_ms / alt_steps,
+                  "value": vec_per_step * alt_steps / (sk_ms * 1e-3), "unit": "vectors/s",
+                  "note": "every Sinkhorn pass streams the fp32 scores (column scalings to ~1e-5 instead of ~5e-4; "
+                          "the codes are computed from the fp32 scores in both modes)"}
 
     # ---------------------------------------------------------------- end-to-end region
     # Same schedule as SwAVClustering.pretrain: host bookkeeping + pinned H2D of step i+1 go on a side stream while
@@ -643,7 +653,9 @@ def run_swav(args, cfg):
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms / args.steps,
             "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": f"bf16x{args.passes_fwd}-split fwd" + (" (score GEMM fp16x1 on unit-norm operands)" if args.proto_f16 else "") +
-                     f" / bf16x{args.passes_bwd} bwd operands, fp32 accumulate + fp32 everywhere else",
+                     f" / bf16x{args.passes_bwd} bwd operands, fp32 accumulate + fp32 everywhere else" +
+                     ("" if scfg.sinkhorn_cache16 is False or os.environ.get("GX_SINKHORN_CACHE16", "1") == "0" else
+                      " (Sinkhorn iterations 2.. stream an fp16 cache of the row-normalised kernel matrix)"),
             "data": "synthetic",
             "config": swav_config(cfg, b, world, None if world == 1 else ("ll-nvlink" if group.ll is not None else "nccl")),
             "roofline": roofline, "roofline_stages": stage_rows, "cpu_baseline": cpu_base,
@@ -651,7 +663,8 @@ def run_swav(args, cfg):
                     "steps": e2e_steps, "ms_per_step": dt * 1e3 / e2e_steps,
                     "host_ms_per_step": {k: v / e2e_steps for k, v in host_ms.items()}},
             "gpu_launches": launches, "clocks": clocks, "final_loss": final_loss, "alt_score_gemm_mode": alt,
-            "alt_bwd_passes3": alt_bwd, "dist_parity": dist_parity, "eager_gpu": eager,
+            "alt_bwd_passes3": alt_bwd, "alt_sinkhorn_fp32_passes": alt_sk, "dist_parity": dist_parity,
+            "eager_gpu": eager,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

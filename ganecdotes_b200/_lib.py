@@ -120,6 +120,8 @@ _SIGNATURES = {
     "gx_peer_open": ([_P, C.POINTER(_P)], _I),
     "gx_peer_close": ([_P], _I),
     "gx_sinkhorn_pass": ([_P, _LL, _I, _LL, _F, _I, _P, _LLD, _P, _P, _LL, _I, _P, C.POINTER(_I), _P], _I),
+    "gx_sinkhorn_pass_cached": ([_P, _LL, _I, _LL, _F, _P, _LLD, _P, _P, _LL, _I, _P, C.POINTER(_I), _P, _LL, _P, _I,
+                                 _P], _I),
     "gx_sinkhorn_reduce": ([_P, _I, _I, _P, _P], _I),
     "gx_sinkhorn_reduce_send": ([_P, _I, _I, _LLD, _P, _P], _I),
     "gx_ll_recv_sum": ([_LLD, _I, _P, _P], _I),
@@ -153,7 +155,7 @@ def lib_path() -> str:
     return _build.LIB_PATH
 
 
-GX_ABI_VERSION = 202        # include/ganecdotes_b200.h
+GX_ABI_VERSION = 203        # include/ganecdotes_b200.h
 
 
 def load(require_device: bool = True):
@@ -880,6 +882,19 @@ class SinkhornWorkspace:
         self.max_parts = lib.gx_sinkhorn_max_parts()
         self.partials = torch.empty((self.max_parts, k), dtype=torch.float32, device=device)
         self.u = torch.empty((k,), dtype=torch.float32, device=device)
+        self._cache = {}
+
+    def cache16(self, chain, n):
+        """(e16 [n, lde] fp16, la1 [k]) of Sinkhorn chain `chain`: the 16-bit plane of gx_sinkhorn_pass_cached, kept
+        between calls (1.6 GB per chain at n = 160000, k = 5000)"""
+        lde = (self.k + 7) // 8 * 8
+        ent = self._cache.get(chain)
+        if ent is None or ent[0].shape[0] < n:
+            dev = self.partials.device
+            ent = (torch.empty((n, lde), dtype=torch.float16, device=dev),
+                   torch.empty((lde,), dtype=torch.float32, device=dev))
+            self._cache[chain] = ent
+        return ent[0][:n], ent[1]
 
 
 class LLExchange:
@@ -1008,6 +1023,24 @@ def sinkhorn_pass_parts(s, inv_eps, first, u_in, r, c, n_total, ws: SinkhornWork
                                     C.byref(u_ll) if u_ll is not None else None, _ptr(r), _ptr(c), int(n_total),
                                     int(bool(reverse)), _ptr(ws.partials), C.byref(nparts), _stream()),
                "gx_sinkhorn_pass")
+    _count()
+    return nparts.value
+
+
+def sinkhorn_pass_cached_parts(s, inv_eps, u_in, r, c, n_total, ws: SinkhornWorkspace, cache, write_cache, u_ll=None,
+                               reverse=False):
+    """A (non-first) pass through the 16-bit cache `cache` = ws.cache16(chain, n): write_cache=True streams S and fills
+    the cache, write_cache=False streams the cache instead of S (gx_sinkhorn_pass_cached)."""
+    lib = load()
+    n, k = s.shape
+    e16, la1 = cache
+    nparts = C.c_int(0)
+    with timed("sinkhorn_pass", (4.0 * n * k + 2.0 * n * k) if write_cache else 2.0 * n * k):
+        _check(lib.gx_sinkhorn_pass_cached(_ptr(s), n, k, s.stride(0), float(inv_eps), _ptr(u_in),
+                                           C.byref(u_ll) if u_ll is not None else None, _ptr(r), _ptr(c), int(n_total),
+                                           int(bool(reverse)), _ptr(ws.partials), C.byref(nparts), _ptr(e16),
+                                           e16.stride(0), _ptr(la1), int(bool(write_cache)), _stream()),
+               "gx_sinkhorn_pass_cached")
     _count()
     return nparts.value
 

@@ -736,12 +736,15 @@ __device__ __forceinline__ void group_bar(int id, int nthreads) {
   asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
 }
 
-template <int J, int R, int GT>
+// MODE 0: rows of S (fp32) in.  MODE 1: the same pass, which also stores its row-normalised terms
+//   e16[n,k] = half(2^15 * a_k e_nk / sum_k a_k e_nk)   and   la1[k] = log2 a_k
+// - the 16-bit cache of the scaled kernel matrix that sinkhorn_pass16_kernel streams in the later passes.
+template <int J, int R, int GT, int MODE>
 __global__ void __launch_bounds__(SK_THREADS, 1)
 sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long lds, float scale_log2, int first,
                      const float* __restrict__ u_in, const gx_ll_desc u_ll, const float* __restrict__ r,
                      const float* __restrict__ cvec, float c_uniform, float* __restrict__ partials, int stages,
-                     int reverse) {
+                     int reverse, __half* __restrict__ e16, long long lde, float* __restrict__ la1) {
   constexpr int NG = SK_THREADS / GT;   // groups per CTA
   constexpr int NW = GT / 32;           // warps per group
   extern __shared__ __align__(128) uint8_t sk_smem[];
@@ -808,6 +811,8 @@ sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long 
         l4[e] = -INFINITY;
       }
     }
+    if (MODE == 1 && col < k && blockIdx.x == 0 && grp == 0)
+      *reinterpret_cast<float4*>(la1 + col) = make_float4(l4[0], l4[1], l4[2], l4[3]);
     la2[j][0] = make_float2(l4[0], l4[1]);
     la2[j][1] = make_float2(l4[2], l4[3]);
     acc[j][0] = acc[j][1] = make_float2(0.f, 0.f);
@@ -848,10 +853,11 @@ sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long 
     }
     group_bar(1 + grp, GT);   // the group has consumed the stage (and published its partial sums)
     if (gt == 0 && it + stages < n_iters) issue(it + stages);
-    float bn[R];
+    float bn[R], e16n[R];
 #pragma unroll
     for (int rr = 0; rr < R; ++rr) {
       bn[rr] = 1.f;
+      e16n[rr] = 0.f;
       if (!first) {
         float tot = 0.f;
 #pragma unroll
@@ -862,6 +868,7 @@ sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long 
         const long long row = row0 + rr;
         const float cn = cvec ? ((row < n) ? cvec[row] : 0.f) : c_uniform;
         bn[rr] = __fdividef(cn, tot);
+        if (MODE == 1) e16n[rr] = __fdividef(32768.f, tot);
       }
     }
     buf ^= 1;
@@ -873,6 +880,20 @@ sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long 
         for (int j = 0; j < J; ++j) {
           acc[j][0] = fma2(p[rr][j][0], b2, acc[j][0]);
           acc[j][1] = fma2(p[rr][j][1], b2, acc[j][1]);
+        }
+        if (MODE == 1) {
+          const float2 n2 = make_float2(e16n[rr], e16n[rr]);
+          __half* erow = e16 + (row0 + rr) * lde;
+#pragma unroll
+          for (int j = 0; j < J; ++j) {
+            const int col = j * (GT * 4) + gt * 4;
+            if (col < k) {
+              const float2 a = mul2(p[rr][j][0], n2), b = mul2(p[rr][j][1], n2);
+              const __half2 h0 = __floats2half2_rn(a.x, a.y), h1 = __floats2half2_rn(b.x, b.y);
+              *reinterpret_cast<uint2*>(erow + col) =
+                  make_uint2(*reinterpret_cast<const uint32_t*>(&h0), *reinterpret_cast<const uint32_t*>(&h1));
+            }
+          }
         }
       }
     }
@@ -886,6 +907,147 @@ sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long 
       *reinterpret_cast<float4*>(prow + col) =
           make_float4(acc[j][0].x * ex2_fast(-la2[j][0].x), acc[j][0].y * ex2_fast(-la2[j][0].y),
                       acc[j][1].x * ex2_fast(-la2[j][1].x), acc[j][1].y * ex2_fast(-la2[j][1].y));
+  }
+}
+
+// ---------------------------------------------------------------------------
+// A later Sinkhorn pass on the 16-bit cache e16 (written by sinkhorn_pass_kernel<.., 1>) instead of S: half the bytes
+// and no exponentials.  With rho_k = a_k / a1_k (a1 = the column scaling the cache was written with) the row totals
+// are t'_n = sum_k e16_nk rho_k and the marginals u_k = (1 / a1_k) sum_n e16_nk c_n / t'_n; the row factor
+// 2^15 / t_n stored in e16 cancels.  Same decomposition as the fp32 pass (NG groups of GT threads, each thread owning
+// 4 consecutive columns per sweep), but R rows per ring stage loaded by ONE bulk copy (the plane is contiguous) and
+// incremental ring bookkeeping: the pass is bound by instruction issue and latency at 16 warps per SM, not by HBM.
+// ---------------------------------------------------------------------------
+template <int J, int R, int GT>
+__global__ void __launch_bounds__(SK_THREADS, 1)
+sinkhorn_pass16_kernel(const __half* __restrict__ e16, long long n, int k, long long lde,
+                       const float* __restrict__ u_in, const gx_ll_desc u_ll, const float* __restrict__ r,
+                       const float* __restrict__ cvec, float c_uniform, const float* __restrict__ la1,
+                       float* __restrict__ partials, int stages, int reverse) {
+  constexpr int NG = SK_THREADS / GT;   // groups per CTA
+  constexpr int NW = GT / 32;           // warps per group
+  extern __shared__ __align__(128) uint8_t sk_smem[];
+  __shared__ __align__(16) float red[NG][2][NW][R];
+  __shared__ uint64_t full_bar[8];
+  const int tid = threadIdx.x, lane = tid & 31;
+  const int grp = tid / GT, gt = tid % GT, gwarp = gt >> 5;
+  const uint32_t row_bytes = (uint32_t)lde * 2u;
+  const uint32_t stage_bytes = row_bytes * R;
+  if (tid == 0) {
+    for (int i = 0; i < stages; ++i) gxptx::mbar_init(&full_bar[i], 1);
+    gxptx::fence_mbar_init();
+  }
+  __syncthreads();
+  const int groups_total = (int)((n + R - 1) / R);
+  const int n_iters = (groups_total - (int)blockIdx.x + (int)gridDim.x - 1) / (int)gridDim.x;
+  const int last_valid = (int)(n - (long long)(groups_total - 1) * R);   // rows of the last (possibly ragged) group
+  auto group_of = [&](int it) -> int {
+    const int g = (int)blockIdx.x + it * (int)gridDim.x;
+    return reverse ? groups_total - 1 - g : g;
+  };
+  auto issue = [&](int it) {
+    const int st = it % stages;
+    const int g = group_of(it);
+    const uint32_t bytes = row_bytes * (uint32_t)(g == groups_total - 1 ? last_valid : R);
+    gxptx::mbar_arrive_expect_tx(&full_bar[st], bytes);
+    gxptx::bulk_load_1d(sk_smem + (size_t)st * stage_bytes, e16 + (long long)g * R * lde, bytes, &full_bar[st]);
+  };
+  if (tid == 0)
+    for (int it = 0; it < stages && it < n_iters; ++it) issue(it);
+
+  float2 rho[J][2], acc[J][2];
+  uint32_t coff[J];   // byte offset of this thread's 4 halves in a row (clamped slots re-read valid columns, rho = 0)
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int col = j * (GT * 4) + gt * 4;
+    coff[j] = (uint32_t)min(col, k - 4) * 2u;
+    float l4[4] = {0.f, 0.f, 0.f, 0.f};
+    if (col < k) {
+      float u4[4];
+      if (u_ll.world > 0) gxll::recv4(u_ll, k, col, u4);
+      else {
+        const float4 uu = *reinterpret_cast<const float4*>(u_in + col);
+        u4[0] = uu.x; u4[1] = uu.y; u4[2] = uu.z; u4[3] = uu.w;
+      }
+      const float4 l1 = *reinterpret_cast<const float4*>(la1 + col);
+      const float l1v[4] = {l1.x, l1.y, l1.z, l1.w};
+#pragma unroll
+      for (int e = 0; e < 4; ++e) {
+        const float rk = r ? r[col + e] : 1.f / (float)k;
+        l4[e] = ex2_fast(log2f(rk / u4[e]) - l1v[e]);
+      }
+    }
+    rho[j][0] = make_float2(l4[0], l4[1]);
+    rho[j][1] = make_float2(l4[2], l4[3]);
+    acc[j][0] = acc[j][1] = make_float2(0.f, 0.f);
+  }
+  int buf = 0, sg = grp;
+  uint32_t phase = 0;
+  for (int it = grp; it < n_iters; it += NG) {
+    const int g = group_of(it);
+    const int valid = g == groups_total - 1 ? last_valid : R;
+    gxptx::mbar_wait(&full_bar[sg], phase);
+    const uint8_t* srow = sk_smem + (size_t)sg * stage_bytes;
+    float2 p[R][J][2];
+    float t[R];
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+      t[rr] = 0.f;
+      if (rr < valid) {   // warp-uniform
+        float2 ta = make_float2(0.f, 0.f), tb = make_float2(0.f, 0.f);
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          const uint2 w = *reinterpret_cast<const uint2*>(srow + (size_t)rr * row_bytes + coff[j]);
+          p[rr][j][0] = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
+          p[rr][j][1] = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+          ta = fma2(p[rr][j][0], rho[j][0], ta);
+          tb = fma2(p[rr][j][1], rho[j][1], tb);
+        }
+        t[rr] = (ta.x + tb.x) + (ta.y + tb.y);
+      }
+    }
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) t[rr] = gx_warp_sum(t[rr]);
+    if (lane == 0) {
+#pragma unroll
+      for (int rr = 0; rr < R; ++rr) red[grp][buf][gwarp][rr] = t[rr];
+    }
+    group_bar(1 + grp, GT);   // the group has consumed the stage (and published its partial sums)
+    if (gt == 0 && it + stages < n_iters) issue(it + stages);
+    float tot[R];
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) tot[rr] = 0.f;
+#pragma unroll
+    for (int w = 0; w < NW; ++w)
+#pragma unroll
+      for (int rr = 0; rr < R; ++rr) tot[rr] += red[grp][buf][w][rr];
+    buf ^= 1;
+#pragma unroll
+    for (int rr = 0; rr < R; ++rr) {
+      if (rr < valid) {
+        const float cn = cvec ? cvec[(long long)g * R + rr] : c_uniform;
+        const float bn = __fdividef(cn, tot[rr]);
+        const float2 b2 = make_float2(bn, bn);
+#pragma unroll
+        for (int j = 0; j < J; ++j) {
+          acc[j][0] = fma2(p[rr][j][0], b2, acc[j][0]);
+          acc[j][1] = fma2(p[rr][j][1], b2, acc[j][1]);
+        }
+      }
+    }
+    sg += NG;
+    if (sg >= stages) { sg -= stages; phase ^= 1u; }
+  }
+  // acc holds sum_n e16_nk c_n / t'_n = a1_k * (the marginal of the unscaled matrix)
+  float* prow = partials + ((long long)blockIdx.x * NG + grp) * k;
+#pragma unroll
+  for (int j = 0; j < J; ++j) {
+    const int col = j * (GT * 4) + gt * 4;
+    if (col < k) {
+      const float4 l = *reinterpret_cast<const float4*>(la1 + col);
+      *reinterpret_cast<float4*>(prow + col) = make_float4(acc[j][0].x * ex2_fast(-l.x), acc[j][0].y * ex2_fast(-l.y),
+                                                           acc[j][1].x * ex2_fast(-l.z), acc[j][1].y * ex2_fast(-l.w));
+    }
   }
 }
 
@@ -1793,10 +1955,11 @@ extern "C" int gx_loss_max_parts(void) { return 2 * gx_sm_count(); }
     default: return GX_ERR_ARG;                          \
   }
 
-template <int J, int R, int GT>
+template <int J, int R, int GT, int MODE>
 static int launch_sinkhorn_pass(const float* s, long long n, int k, long long lds, float scale_log2, int first,
                                 const float* u_in, const gx_ll_desc& u_ll, const float* r, const float* c, float cu,
-                                float* partials, int grid, int reverse, cudaStream_t st) {
+                                float* partials, int grid, int reverse, __half* e16, long long lde, float* la1,
+                                cudaStream_t st) {
   const int stage_bytes = k * 4 * R;
   // Each of the NG groups must own a fixed subset of the ring (stage index parity == iteration
   // parity): with a stage shared between groups, a group running ahead would observe the
@@ -1808,12 +1971,36 @@ static int launch_sinkhorn_pass(const float* s, long long n, int k, long long ld
   GX_CHECK_ARG(stages >= 2 * NG || (NG == 1 && stages >= 2));
   static bool attr = false;
   if (!attr) {
-    GX_CHECK_CUDA(cudaFuncSetAttribute(sinkhorn_pass_kernel<J, R, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+    GX_CHECK_CUDA(cudaFuncSetAttribute(sinkhorn_pass_kernel<J, R, GT, MODE>,
+                                       cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024));
+    attr = true;
+  }
+  sinkhorn_pass_kernel<J, R, GT, MODE><<<grid, SK_THREADS, stages * stage_bytes, st>>>(
+      s, n, k, lds, scale_log2, first, u_in, u_ll, r, c, cu, partials, stages, reverse, e16, lde, la1);
+  return GX_OK;
+}
+
+template <int J, int R, int GT>
+static int launch_sinkhorn_pass16(const __half* e16, long long n, int k, long long lde, const float* u_in,
+                                  const gx_ll_desc& u_ll, const float* r, const float* c, float cu, const float* la1,
+                                  float* partials, int reverse, int* nparts_out, cudaStream_t st) {
+  constexpr int NG = SK_THREADS / GT;
+  const int stage_bytes = (int)lde * 2 * R;
+  int stages = (200 * 1024) / stage_bytes;
+  if (stages > 8) stages = 8;
+  stages -= stages % NG;
+  GX_CHECK_ARG(stages >= 2 * NG || (NG == 1 && stages >= 2));
+  GX_CHECK_ARG((n + R - 1) / R < (1ll << 30));
+  const int grid = sk_grid(n, R);
+  if (nparts_out) *nparts_out = grid * NG;
+  static bool attr = false;
+  if (!attr) {
+    GX_CHECK_CUDA(cudaFuncSetAttribute(sinkhorn_pass16_kernel<J, R, GT>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                        200 * 1024));
     attr = true;
   }
-  sinkhorn_pass_kernel<J, R, GT><<<grid, SK_THREADS, stages * stage_bytes, st>>>(
-      s, n, k, lds, scale_log2, first, u_in, u_ll, r, c, cu, partials, stages, reverse);
+  sinkhorn_pass16_kernel<J, R, GT><<<grid, SK_THREADS, stages * stage_bytes, st>>>(
+      e16, n, k, lde, u_in, u_ll, r, c, cu, la1, partials, stages, reverse);
   return GX_OK;
 }
 
@@ -1832,24 +2019,19 @@ static gx_ll_desc ll_or_none(const gx_ll_desc* d) {
   return (d && d->world > 0) ? *d : z;
 }
 
-extern "C" int gx_sinkhorn_pass(const float* s, long long n, int k, long long lds, float inv_eps, int first,
-                                const float* u_in, const gx_ll_desc* u_ll_p, const float* r, const float* c,
-                                long long n_total, int reverse, float* partials, int* nparts_out, void* stream) {
-  GX_CHECK_ARG(s && partials && n > 0 && k >= 4 && k % 4 == 0 && lds % 4 == 0 && lds >= k);
-  GX_CHECK_ARG(ll_desc_ok(u_ll_p));
-  const gx_ll_desc u_ll = ll_or_none(u_ll_p);
-  GX_CHECK_ARG(first || u_in || u_ll.world > 0);
-  GX_CHECK_ARG(!u_in || (reinterpret_cast<uintptr_t>(u_in) & 15) == 0);
-  GX_CHECK_ARG((reinterpret_cast<uintptr_t>(s) & 15) == 0);
-  GX_CHECK_ARG(k <= 8192);
+template <int MODE>
+static int sinkhorn_pass_mode(const float* s, long long n, int k, long long lds, float inv_eps, int first,
+                              const float* u_in, const gx_ll_desc& u_ll, const float* r, const float* c,
+                              long long n_total, int reverse, float* partials, int* nparts_out, __half* e16,
+                              long long lde, float* la1, cudaStream_t st) {
   const int grid = sk_grid(n, SK_ROWS);
   const float cu = 1.f / (float)(n_total > 0 ? n_total : n);
   const float sl = inv_eps * LOG2E;
-  cudaStream_t st = (cudaStream_t)stream;
   int rc;
   const int j256 = gx_cdiv(k, 1024);
-#define GX_SK(J_, GT_) \
-  rc = launch_sinkhorn_pass<J_, SK_ROWS, GT_>(s, n, k, lds, sl, first, u_in, u_ll, r, c, cu, partials, grid, reverse != 0, st)
+#define GX_SK(J_, GT_)                                                                                               \
+  rc = launch_sinkhorn_pass<J_, SK_ROWS, GT_, MODE>(s, n, k, lds, sl, first, u_in, u_ll, r, c, cu, partials, grid, \
+                                                    reverse != 0, e16, lde, la1, st)
   if (j256 <= 5) {
     if (nparts_out) *nparts_out = grid * 2;
     switch (j256) {
@@ -1865,9 +2047,72 @@ extern "C" int gx_sinkhorn_pass(const float* s, long long n, int k, long long ld
     else GX_SK(4, 512);
   }
 #undef GX_SK
+  return rc;
+}
+
+static int sinkhorn_pass_any(const float* s, long long n, int k, long long lds, float inv_eps, int first,
+                             const float* u_in, const gx_ll_desc* u_ll_p, const float* r, const float* c,
+                             long long n_total, int reverse, float* partials, int* nparts_out, void* e16,
+                             long long lde, float* la1, int mode, void* stream) {
+  GX_CHECK_ARG(partials && n > 0 && k >= 4 && k % 4 == 0 && k <= 8192);
+  GX_CHECK_ARG(mode >= 0 && mode <= 2);
+  if (mode != 2) {
+    GX_CHECK_ARG(s && lds % 4 == 0 && lds >= k && (reinterpret_cast<uintptr_t>(s) & 15) == 0);
+  }
+  if (mode != 0) {   // the 16-bit plane: 16-byte aligned rows (bulk copies), written by a normalising (non-first) pass
+    GX_CHECK_ARG(e16 && la1 && !first && lde % 8 == 0 && lde >= k);
+    GX_CHECK_ARG((reinterpret_cast<uintptr_t>(e16) & 15) == 0 && (reinterpret_cast<uintptr_t>(la1) & 15) == 0);
+  }
+  GX_CHECK_ARG(ll_desc_ok(u_ll_p));
+  const gx_ll_desc u_ll = ll_or_none(u_ll_p);
+  GX_CHECK_ARG(first || u_in || u_ll.world > 0);
+  GX_CHECK_ARG(!u_in || (reinterpret_cast<uintptr_t>(u_in) & 15) == 0);
+  cudaStream_t st = (cudaStream_t)stream;
+  __half* e = reinterpret_cast<__half*>(e16);
+  int rc;
+  if (mode == 0)
+    rc = sinkhorn_pass_mode<0>(s, n, k, lds, inv_eps, first, u_in, u_ll, r, c, n_total, reverse, partials, nparts_out,
+                               e, lde, la1, st);
+  else if (mode == 1)
+    rc = sinkhorn_pass_mode<1>(s, n, k, lds, inv_eps, first, u_in, u_ll, r, c, n_total, reverse, partials, nparts_out,
+                               e, lde, la1, st);
+  else {
+    const float cu = 1.f / (float)(n_total > 0 ? n_total : n);
+    const int j256 = gx_cdiv(k, 1024);
+    // 2 rows per ring stage (8 stages of 20 KB at K = 5000): 0.259 ms per pass at N = 160000 (6.18 TB/s); 3 / 4 rows per
+    // stage measured 0.262 / 0.307 ms (register spills at 4) - profiles/r2g_sinkhorn_cache16.txt
+#define GX_SK16R(J_, GT_)                                                                                          \
+  rc = launch_sinkhorn_pass16<J_, SK_ROWS, GT_>(e, n, k, lde, u_in, u_ll, r, c, cu, la1, partials, reverse != 0, \
+                                                nparts_out, st)
+    switch (j256 <= 5 ? j256 : (k <= 6144 ? 6 : 7)) {
+      case 1: GX_SK16R(1, 256); break;
+      case 2: GX_SK16R(2, 256); break;
+      case 3: GX_SK16R(3, 256); break;
+      case 4: GX_SK16R(4, 256); break;
+      case 5: GX_SK16R(5, 256); break;
+      case 6: GX_SK16R(3, 512); break;
+      default: GX_SK16R(4, 512); break;
+    }
+#undef GX_SK16R
+  }
   if (rc != GX_OK) return rc;
   GX_LAUNCH_CHECK();
   return GX_OK;
+}
+
+extern "C" int gx_sinkhorn_pass(const float* s, long long n, int k, long long lds, float inv_eps, int first,
+                                const float* u_in, const gx_ll_desc* u_ll_p, const float* r, const float* c,
+                                long long n_total, int reverse, float* partials, int* nparts_out, void* stream) {
+  return sinkhorn_pass_any(s, n, k, lds, inv_eps, first, u_in, u_ll_p, r, c, n_total, reverse, partials, nparts_out,
+                           nullptr, 0, nullptr, 0, stream);
+}
+
+extern "C" int gx_sinkhorn_pass_cached(const float* s, long long n, int k, long long lds, float inv_eps,
+                                       const float* u_in, const gx_ll_desc* u_ll_p, const float* r, const float* c,
+                                       long long n_total, int reverse, float* partials, int* nparts_out, void* e16,
+                                       long long lde, float* la1, int write_cache, void* stream) {
+  return sinkhorn_pass_any(s, n, k, lds, inv_eps, 0, u_in, u_ll_p, r, c, n_total, reverse, partials, nparts_out, e16,
+                           lde, la1, write_cache ? 1 : 2, stream);
 }
 
 extern "C" int gx_sinkhorn_reduce(const float* partials, int nparts, int k, float* u, void* stream) {

@@ -301,7 +301,7 @@ def scores_forward(head: SwavHead, feats, out_h, out_w, hlen, row_img, row_src, 
 
 
 def sinkhorn_log_a(s, niters, eps, ws, n_total, group=None, r=None, c=None, pass_fn=None, log_a_fn=None,
-                   u_first=None):
+                   u_first=None, cache16=False):
     """Sinkhorn-Knopp in scaling-vector form (ref :509-544) for ONE score matrix: niters streaming passes over
     the LOCAL rows of S; only u[K] crosses ranks (as in SwAV's distributed Sinkhorn), and c_n = 1/n_total uses
     the GLOBAL row count.  Returns log a[K]; Q = softmax_k(S/eps + log a).
@@ -310,7 +310,8 @@ def sinkhorn_log_a(s, niters, eps, ws, n_total, group=None, r=None, c=None, pass
     `pass_fn(s, inv_eps, first, u_in, r, c, n_total, ws) -> local column sums u[K]`, `log_a_fn(u, r)`) the
     exchange is a torch.distributed all-reduce; the CUDA path is `sinkhorn_multi`."""
     if pass_fn is None and log_a_fn is None:
-        return sinkhorn_multi([dict(s=s, r=r, c=c, u_first=u_first)], niters, eps, ws, n_total, group)[0]
+        return sinkhorn_multi([dict(s=s, r=r, c=c, u_first=u_first)], niters, eps, ws, n_total, group,
+                              cache16=cache16)[0]
     inv_eps = 1.0 / eps
     u = None
     for it in range(niters):
@@ -323,7 +324,7 @@ def sinkhorn_log_a(s, niters, eps, ws, n_total, group=None, r=None, c=None, pass
     return log_a_fn(u, r)
 
 
-def sinkhorn_multi(problems, niters, eps, ws, n_total, group=None):
+def sinkhorn_multi(problems, niters, eps, ws, n_total, group=None, cache16=False):
     """Sinkhorn-Knopp (ref :509-544) on several independent score matrices (the s and t views of a patch):
     `problems` = [dict(s=S [n,K], r=, c=, u_first=)], returns [log a] per problem.
 
@@ -332,7 +333,12 @@ def sinkhorn_multi(problems, niters, eps, ws, n_total, group=None):
     the K-vector of column marginals goes through the low-latency NVLink exchange (`L.LLExchange`): the reduce
     kernel of chain A pushes its sums into every peer's buffer, chain B's pass runs meanwhile, and the next pass of
     chain A picks the peers' values up in its prologue - no collective call, no exposed latency, and a whole
-    pass of slack against rank-to-rank jitter.  Without an exchange object the fallback is an NCCL all-reduce."""
+    pass of slack against rank-to-rank jitter.  Without an exchange object the fallback is an NCCL all-reduce.
+
+    `cache16`: the first row-normalising pass (iteration 1) also stores its terms as a 16-bit plane and the later
+    passes stream that plane instead of S (`gx_sinkhorn_pass_cached`: half the bytes per pass, no exponentials).
+    Only the column scalings log a come out of these passes - the codes are always evaluated from the fp32 scores -
+    and they move by <~ 3e-4 relative (the training step's default; the API calls keep the fp32 passes)."""
     inv_eps = 1.0 / eps
     ll = group.ll if group is not None else None
     k = problems[0]["s"].shape[1]
@@ -347,8 +353,15 @@ def sinkhorn_multi(problems, niters, eps, ws, n_total, group=None):
             parts, nparts = pb["u_first"], 1       # local u_k = sum_n exp(S_nk/eps) from the score GEMM's epilogue
         else:
             u_ll = ll.last(ch) if (ll is not None and it > 0) else None
-            nparts = L.sinkhorn_pass_parts(pb["s"], inv_eps, it == 0, None if u_ll is not None else us[ch],
-                                           pb.get("r"), pb.get("c"), n_total, ws, u_ll=u_ll, reverse=(it & 1) == 1)
+            if cache16 and it >= 1 and niters > 2:
+                nparts = L.sinkhorn_pass_cached_parts(pb["s"], inv_eps, None if u_ll is not None else us[ch],
+                                                      pb.get("r"), pb.get("c"), n_total, ws,
+                                                      ws.cache16(ch, pb["s"].shape[0]), it == 1, u_ll=u_ll,
+                                                      reverse=(it & 1) == 1)
+            else:
+                nparts = L.sinkhorn_pass_parts(pb["s"], inv_eps, it == 0, None if u_ll is not None else us[ch],
+                                               pb.get("r"), pb.get("c"), n_total, ws, u_ll=u_ll,
+                                               reverse=(it & 1) == 1)
             parts = ws.partials
         if ll is not None:
             L.sinkhorn_reduce_send(parts, nparts, k, ll.next_send(ch))
@@ -591,6 +604,8 @@ class StepConfig:
     source_pdf: str = 'uniform'
     dedup: Optional[bool] = None   # project every pixel once (None: automatic, when P*N > H*W)
     hf_interp: str = 'nearest'     # 'nearest' | 'bilinear' (ref :112-126); bilinear needs the all-pixel path
+    sinkhorn_cache16: Optional[bool] = None   # Sinkhorn passes 2.. stream a 16-bit cache of the scaled kernel matrix
+    #                                           (sinkhorn_multi); None: on, unless GX_SINKHORN_CACHE16=0
 
 
 @dataclass
@@ -750,6 +765,9 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
     if group is not None and group.ll is None and not group.ll_failed and \
             os.environ.get("GX_SINKHORN_EXCHANGE", "ll") != "nccl":
         group.ensure_ll(head.k, dev)           # NVLink exchange of the marginals (GX_SINKHORN_EXCHANGE=nccl: A/B)
+    cache16 = cfg.sinkhorn_cache16
+    if cache16 is None:
+        cache16 = os.environ.get("GX_SINKHORN_CACHE16", "1") != "0"
     for p in range(cfg.num_patches):
         fw = {}
         for name in ("s", "t"):
@@ -766,7 +784,7 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
             rc_t = image_marginals(feats["t"], out_h, out_w, cfg.hlen, inp.index_maps["t"], head.k, n_local)
         la_s, la_t = sinkhorn_multi([dict(s=fw["s"]["s"], r=rc_s[0], c=rc_s[1], u_first=fw["s"]["u0"]),
                                      dict(s=fw["t"]["s"], r=rc_t[0], c=rc_t[1], u_first=fw["t"]["u0"])],
-                                    cfg.niters, cfg.eps, ws, n_total, group)
+                                    cfg.niters, cfg.eps, ws, n_total, group, cache16=cache16)
         lo = head.passes_bwd == 3
         _, ds_s, ds_t, _, _ = L.swav_loss(fw["s"]["s"], fw["t"]["s"], 1.0 / cfg.eps, 1.0 / cfg.temperature,
                                           la_s, la_t, grad_scale, want_lo=lo, loss_parts=loss_parts[p],

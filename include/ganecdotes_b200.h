@@ -23,7 +23,7 @@ extern "C" {
 #define GX_ERR_CUDA (-2)        /* CUDA runtime/driver error: gx_last_cuda_error */
 #define GX_ERR_UNSUPPORTED (-3) /* device is not sm_100                           */
 
-#define GX_ABI_VERSION 202
+#define GX_ABI_VERSION 203
 int gx_version(void);              /* == GX_ABI_VERSION of the header the library was built from */
 int gx_abi_sizeof(int which);      /* sizeof of gx_conv_desc (0), gx_gemm_desc (1), gx_gather_desc (2), gx_ll_desc (3); -1 otherwise */
 int gx_last_cuda_error(void);             /* cudaError_t of the last GX_ERR_CUDA  */
@@ -370,6 +370,17 @@ int gx_sinkhorn_max_parts(void);
 int gx_sinkhorn_pass(const float* s, long long n, int k, long long lds, float inv_eps, int first, const float* u_in,
                      const gx_ll_desc* u_ll, const float* r, const float* c, long long n_total, int reverse,
                      float* partials, int* nparts_out, void* stream);
+/* The same pass through a 16-bit cache of the scaled kernel matrix (never a first pass).  write_cache != 0: streams S
+ * like gx_sinkhorn_pass and also stores e16[n,lde] = half(2^15 a_k e_nk / sum_k a_k e_nk) and la1[k] = log2 a_k.
+ * write_cache == 0: streams e16 instead of S (s may be NULL) - half the bytes and no exponentials: with
+ * rho_k = a_k / a1_k the row totals are t'_n = sum_k e16_nk rho_k and u_k = (1/a1_k) sum_n e16_nk c_n / t'_n (the row
+ * factor stored in e16 cancels).  The marginals differ from the fp32 pass by the rounding of e16 (2^-11 per term,
+ * averaged over a column: <~ 3e-4 in the final codes); the codes themselves are always computed from
+ * the fp32 scores (gx_swav_loss / gx_sinkhorn_q).  lde % 8 == 0 (16-byte rows), e16 and la1 16-byte aligned. */
+int gx_sinkhorn_pass_cached(const float* s, long long n, int k, long long lds, float inv_eps, const float* u_in,
+                            const gx_ll_desc* u_ll, const float* r, const float* c, long long n_total, int reverse,
+                            float* partials, int* nparts_out, void* e16, long long lde, float* la1, int write_cache,
+                            void* stream);
 /* u[k] = sum_p partials[p,k] (deterministic order). */
 int gx_sinkhorn_reduce(const float* partials, int nparts, int k, float* u, void* stream);
 /* The same column sums, pushed as tagged words into slot `rank` of ll's block on every rank (fused reduce +

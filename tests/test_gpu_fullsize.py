@@ -110,7 +110,15 @@ def test_ffhq256_sinkhorn_marginals_full_size(ffhq, eps):
     la = E.sinkhorn_log_a(s, 10, eps, ws, n, u_first=u0)
     la_ref = E.sinkhorn_log_a(s, 10, eps, ws, n)                      # first pass by the streaming kernel
     torch.testing.assert_close(la, la_ref, rtol=0, atol=2e-4 if eps > 0.01 else 2e-3)
+    # the training step's route: iterations 2.. through the 16-bit cache (gx_sinkhorn_pass_cached)
+    la16 = E.sinkhorn_log_a(s, 10, eps, ws, n, u_first=u0, cache16=True)
+    assert not torch.equal(la16, la)
+    torch.testing.assert_close(la16, la, rtol=0, atol=1e-3)
+    q16 = L.sinkhorn_q(s, 1.0 / eps, la16)
     q = L.sinkhorn_q(s, 1.0 / eps, la)
+    big = q > 1e-9
+    assert ((q16 - q).abs()[big] / q[big]).max().item() < 1e-3
+    del q16, big
     torch.testing.assert_close(q.sum(1), torch.ones(n, device="cuda"), rtol=1e-4, atol=0)
     col = q.sum(0)
     # 10 iterations from random scores: marginals within a few percent of N/K, mean exactly N/K
