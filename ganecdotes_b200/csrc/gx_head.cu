@@ -945,22 +945,23 @@ sinkhorn_pass16_kernel(const __half* __restrict__ e16, long long n, int k, long 
     const int g = (int)blockIdx.x + it * (int)gridDim.x;
     return reverse ? groups_total - 1 - g : g;
   };
-  auto issue = [&](int it) {
-    const int st = it % stages;
+  auto issue = [&](int it, int st) {   // st == it % stages
     const int g = group_of(it);
     const uint32_t bytes = row_bytes * (uint32_t)(g == groups_total - 1 ? last_valid : R);
     gxptx::mbar_arrive_expect_tx(&full_bar[st], bytes);
     gxptx::bulk_load_1d(sk_smem + (size_t)st * stage_bytes, e16 + (long long)g * R * lde, bytes, &full_bar[st]);
   };
   if (tid == 0)
-    for (int it = 0; it < stages && it < n_iters; ++it) issue(it);
+    for (int it = 0; it < stages && it < n_iters; ++it) issue(it, it);
 
   float2 rho[J][2], acc[J][2];
-  uint32_t coff[J];   // byte offset of this thread's 4 halves in a row (clamped slots re-read valid columns, rho = 0)
+  // byte offset of this thread's 4 halves in a row: gt * 8 + j * GT * 8; only the last sweep can run past column k
+  // (J = ceil(k / (4 GT))): its slot is clamped to re-read valid columns, with rho = 0
+  const uint32_t coff0 = (uint32_t)gt * 8u;
+  const uint32_t coff_last = (uint32_t)min((J - 1) * (GT * 4) + gt * 4, k - 4) * 2u;
 #pragma unroll
   for (int j = 0; j < J; ++j) {
     const int col = j * (GT * 4) + gt * 4;
-    coff[j] = (uint32_t)min(col, k - 4) * 2u;
     float l4[4] = {0.f, 0.f, 0.f, 0.f};
     if (col < k) {
       float u4[4];
@@ -995,9 +996,10 @@ sinkhorn_pass16_kernel(const __half* __restrict__ e16, long long n, int k, long 
       t[rr] = 0.f;
       if (rr < valid) {   // warp-uniform
         float2 ta = make_float2(0.f, 0.f), tb = make_float2(0.f, 0.f);
+        const uint8_t* sr = srow + (size_t)rr * row_bytes;
 #pragma unroll
         for (int j = 0; j < J; ++j) {
-          const uint2 w = *reinterpret_cast<const uint2*>(srow + (size_t)rr * row_bytes + coff[j]);
+          const uint2 w = *reinterpret_cast<const uint2*>(j < J - 1 ? sr + coff0 + j * (GT * 8) : sr + coff_last);
           p[rr][j][0] = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
           p[rr][j][1] = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
           ta = fma2(p[rr][j][0], rho[j][0], ta);
@@ -1006,14 +1008,23 @@ sinkhorn_pass16_kernel(const __half* __restrict__ e16, long long n, int k, long 
         t[rr] = (ta.x + tb.x) + (ta.y + tb.y);
       }
     }
+    if (R == 2) {
+      // both rows in one butterfly: after the first exchange lanes 0-15 carry row 0 and lanes 16-31 row 1
+      const bool up = (lane & 16) != 0;
+      float v = (up ? t[1] : t[0]) + __shfl_xor_sync(0xffffffffu, up ? t[0] : t[1], 16);
 #pragma unroll
-    for (int rr = 0; rr < R; ++rr) t[rr] = gx_warp_sum(t[rr]);
-    if (lane == 0) {
+      for (int o = 8; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+      if ((lane & 15) == 0) red[grp][buf][gwarp][lane >> 4] = v;
+    } else {
 #pragma unroll
-      for (int rr = 0; rr < R; ++rr) red[grp][buf][gwarp][rr] = t[rr];
+      for (int rr = 0; rr < R; ++rr) t[rr] = gx_warp_sum(t[rr]);
+      if (lane == 0) {
+#pragma unroll
+        for (int rr = 0; rr < R; ++rr) red[grp][buf][gwarp][rr] = t[rr];
+      }
     }
     group_bar(1 + grp, GT);   // the group has consumed the stage (and published its partial sums)
-    if (gt == 0 && it + stages < n_iters) issue(it + stages);
+    if (gt == 0 && it + stages < n_iters) issue(it + stages, sg);
     float tot[R];
 #pragma unroll
     for (int rr = 0; rr < R; ++rr) tot[rr] = 0.f;
@@ -1026,7 +1037,9 @@ sinkhorn_pass16_kernel(const __half* __restrict__ e16, long long n, int k, long 
     for (int rr = 0; rr < R; ++rr) {
       if (rr < valid) {
         const float cn = cvec ? cvec[(long long)g * R + rr] : c_uniform;
-        const float bn = __fdividef(cn, tot[rr]);
+        float rt;   // t' is a sum of positive terms of order 2^15: no range handling needed
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(rt) : "f"(tot[rr]));
+        const float bn = cn * rt;
         const float2 b2 = make_float2(bn, bn);
 #pragma unroll
         for (int j = 0; j < J; ++j) {
