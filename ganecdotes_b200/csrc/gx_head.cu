@@ -767,8 +767,7 @@ sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long 
     const long long g = (long long)blockIdx.x + (long long)it * gridDim.x;
     return (reverse ? groups_total - 1 - g : g) * R;
   };
-  auto issue = [&](int it) {
-    const int st = it % stages;
+  auto issue = [&](int it, int st) {   // st == it % stages
     const long long row0 = first_row(it);
     const int valid = (int)min((long long)R, n - row0);
     gxptx::mbar_arrive_expect_tx(&full_bar[st], row_bytes * valid);
@@ -777,7 +776,7 @@ sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long 
                           row_bytes, &full_bar[st]);
   };
   if (tid == 0)
-    for (int it = 0; it < stages && it < n_iters; ++it) issue(it);
+    for (int it = 0; it < stages && it < n_iters; ++it) issue(it, it);
 
   // per-thread columns; out-of-range columns read a clamped (valid) address and are
   // neutralised by log2(a) = -inf  ->  exp2(-inf) = 0
@@ -818,11 +817,11 @@ sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long 
     acc[j][0] = acc[j][1] = make_float2(0.f, 0.f);
   }
   const float2 sc2 = make_float2(scale_log2, scale_log2);
-  int buf = 0;
+  int buf = 0, st = grp;   // st == it % stages, phase == (it / stages) & 1, kept incrementally (no integer division)
+  uint32_t phase = 0;
   for (int it = grp; it < n_iters; it += NG) {
-    const int st = it % stages;
     const long long row0 = first_row(it);
-    gxptx::mbar_wait(&full_bar[st], (uint32_t)((it / stages) & 1));
+    gxptx::mbar_wait(&full_bar[st], phase);
     const float* srow = reinterpret_cast<const float*>(sk_smem + (size_t)st * stage_bytes);
     float2 p[R][J][2];
     float t[R];
@@ -852,7 +851,7 @@ sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long 
       }
     }
     group_bar(1 + grp, GT);   // the group has consumed the stage (and published its partial sums)
-    if (gt == 0 && it + stages < n_iters) issue(it + stages);
+    if (gt == 0 && it + stages < n_iters) issue(it + stages, st);
     float bn[R], e16n[R];
 #pragma unroll
     for (int rr = 0; rr < R; ++rr) {
@@ -897,6 +896,8 @@ sinkhorn_pass_kernel(const float* __restrict__ s, long long n, int k, long long 
         }
       }
     }
+    st += NG;
+    if (st >= stages) { st -= stages; phase ^= 1u; }
   }
   // acc holds sum_n a_k e_nk b_n; the marginal of the unscaled matrix is acc / a_k
   float* prow = partials + ((long long)blockIdx.x * NG + grp) * k;
@@ -1244,15 +1245,14 @@ swav_loss_kernel(const float* __restrict__ ss, const float* __restrict__ st, lon
   }
   __syncthreads();
   const int n_iters = (int)((n - blockIdx.x + gridDim.x - 1) / gridDim.x);
-  auto issue = [&](int it) {
-    const int sg = it % stages;
+  auto issue = [&](int it, int sg) {   // sg == it % stages
     const long long row = (long long)blockIdx.x + (long long)it * gridDim.x;
     gxptx::mbar_arrive_expect_tx(&full_bar[sg], stage_bytes);
     gxptx::bulk_load_1d(sk_smem + (size_t)sg * stage_bytes, ss + row * lds, row_bytes, &full_bar[sg]);
     gxptx::bulk_load_1d(sk_smem + (size_t)sg * stage_bytes + row_bytes, st + row * lds, row_bytes, &full_bar[sg]);
   };
   if (tid == 0)
-    for (int it = 0; it < stages && it < n_iters; ++it) issue(it);
+    for (int it = 0; it < stages && it < n_iters; ++it) issue(it, it);
 
   // log2-domain constants.  log2(a) of both views lives in shared memory behind the ring
   // (K floats each).  Out-of-range columns read a clamped address and are removed by a -inf
@@ -1274,10 +1274,11 @@ swav_loss_kernel(const float* __restrict__ ss, const float* __restrict__ st, lon
   const float2 ce2 = make_float2(ce, ce), ct2 = make_float2(ct, ct);
   float loss_acc = 0.f;
   const float gs = grad_scale * 0.5f * inv_temp;
-  for (int it = grp; it < n_iters; it += NG) {
+  int sg = grp;   // == it % stages, with phase == (it / stages) & 1, kept incrementally (no integer division)
+  uint32_t phase = 0;
+  for (int it = grp; it < n_iters; it += NG, sg = sg + NG >= stages ? (phase ^= 1u, sg + NG - stages) : sg + NG) {
     const long long row = (long long)blockIdx.x + (long long)it * gridDim.x;
-    const int sg = it % stages;
-    gxptx::mbar_wait(&full_bar[sg], (uint32_t)((it / stages) & 1));
+    gxptx::mbar_wait(&full_bar[sg], phase);
     const float* srow_s = reinterpret_cast<const float*>(sk_smem + (size_t)sg * stage_bytes);
     const float* srow_t = srow_s + k;
     float2 vs[J][2], vt[J][2];     // raw scores, later softmax(p) numerators
@@ -1306,7 +1307,7 @@ swav_loss_kernel(const float* __restrict__ ss, const float* __restrict__ st, lon
       }
     }
     group_reduce<4, true, NW>(mx, red_max[grp], gwarp, lane, 1 + grp, GT);   // stage consumed after this barrier
-    if (gt == 0 && it + stages < n_iters) issue(it + stages);
+    if (gt == 0 && it + stages < n_iters) issue(it + stages, sg);
     // pass 2: sums  Z1_s, Z2_s, D_st = sum e1s*s_t, Z1_t, Z2_t, D_ts = sum e1t*s_s   (packed partials)
     float2 s2[6];
 #pragma unroll
@@ -1427,15 +1428,14 @@ swav_loss_pow_kernel(const float* __restrict__ ss, const float* __restrict__ st,
   }
   __syncthreads();
   const int n_iters = (int)((n - blockIdx.x + gridDim.x - 1) / gridDim.x);
-  auto issue = [&](int it) {
-    const int sg = it % stages;
+  auto issue = [&](int it, int sg) {   // sg == it % stages
     const long long row = (long long)blockIdx.x + (long long)it * gridDim.x;
     gxptx::mbar_arrive_expect_tx(&full_bar[sg], stage_bytes);
     gxptx::bulk_load_1d(sk_smem + (size_t)sg * stage_bytes, ss + row * lds, row_bytes, &full_bar[sg]);
     gxptx::bulk_load_1d(sk_smem + (size_t)sg * stage_bytes + row_bytes, st + row * lds, row_bytes, &full_bar[sg]);
   };
   if (tid == 0)
-    for (int it = 0; it < stages && it < n_iters; ++it) issue(it);
+    for (int it = 0; it < stages && it < n_iters; ++it) issue(it, it);
 
   // a_k / max_k a_k of both views behind the ring (K floats each)
   float* sa_s = reinterpret_cast<float*>(sk_smem + (size_t)stages * stage_bytes);
@@ -1466,10 +1466,11 @@ swav_loss_pow_kernel(const float* __restrict__ ss, const float* __restrict__ st,
   const float2 ct2 = make_float2(ct, ct);
   float loss_acc = 0.f;
   const float gs = grad_scale * 0.5f * inv_temp;
-  for (int it = grp; it < n_iters; it += NG) {
+  int sg = grp;   // == it % stages, with phase == (it / stages) & 1, kept incrementally (no integer division)
+  uint32_t phase = 0;
+  for (int it = grp; it < n_iters; it += NG, sg = sg + NG >= stages ? (phase ^= 1u, sg + NG - stages) : sg + NG) {
     const long long row = (long long)blockIdx.x + (long long)it * gridDim.x;
-    const int sg = it % stages;
-    gxptx::mbar_wait(&full_bar[sg], (uint32_t)((it / stages) & 1));
+    gxptx::mbar_wait(&full_bar[sg], phase);
     const float* srow_s = reinterpret_cast<const float*>(sk_smem + (size_t)sg * stage_bytes);
     const float* srow_t = srow_s + k;
     float2 vs[J][2], vt[J][2];     // raw scores, later softmax(S/T) numerators
@@ -1486,7 +1487,7 @@ swav_loss_pow_kernel(const float* __restrict__ ss, const float* __restrict__ st,
       mx[1] = fmaxf(mx[1], fmaxf(fmaxf(b.x, b.y), fmaxf(b.z, b.w)));
     }
     group_reduce<2, true, NW>(mx, red_max[grp], gwarp, lane, 1 + grp, GT);   // stage consumed after this barrier
-    if (gt == 0 && it + stages < n_iters) issue(it + stages);
+    if (gt == 0 && it + stages < n_iters) issue(it + stages, sg);
     // pass 2: sums  Z1_s, Z2_s, D_st = sum q_s*s_t, Z1_t, Z2_t, D_ts = sum q_t*s_s   (packed partials)
     float2 s2[6];
 #pragma unroll
