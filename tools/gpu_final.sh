@@ -14,11 +14,11 @@ ncu --metrics gpu__time_duration.sum --clock-control none -c 2500 --csv --log-fi
   python bench.py --steps 2 --warmup 1 --no-alt --no-eager --no-cpu-baseline > $O/${T}_ncu_bench.log 2>&1
 python tools/summarize_launches.py $O/${T}_launches_raw.csv $O/${T}_launches.csv "$T: python bench.py --steps 2 --warmup 1 --no-alt --no-eager --no-cpu-baseline" || true
 rm -f $O/${T}_launches_raw.csv
-# full captures of the kernels changed in this session
-python tools/ncu_small.py > /dev/null 2>&1 && ncu --set full --clock-control none --import-source on -k regex:"blur_sep|upsample_sum_quad" \
-  -s 2 -c 2 -o $O/${T}_small python tools/ncu_small.py > $O/${T}_ncu_small.log 2>&1
-python tools/gpu_probe_synth.py 16 pidray > $O/${T}_synth_pidray.txt 2>&1 && ncu --set full --clock-control none --import-source on \
-  -k regex:"modconv_small|conv_finish" -s 4 -c 2 -o $O/${T}_convsmall python tools/gpu_probe_synth.py 16 pidray > $O/${T}_ncu_convsmall.log 2>&1
-python tools/gpu_probe_synth.py 16 > $O/${T}_synth_ffhq.txt 2>&1
+# full captures of the kernels changed in this session: the Sinkhorn pass that writes the 16-bit cache (launch 24 of the
+# probe: the last of its 12 writer launches) and the first pass over the cache (launch 25)
+python tools/gpu_probe_sk16.py 160000 5000 > $O/${T}_sk16_probe.txt 2>&1 && ncu --set full --clock-control none --import-source on \
+  -k regex:sinkhorn_pass -s 24 -c 2 -o $O/${T}_sk16 python tools/gpu_probe_sk16.py 160000 5000 > $O/${T}_ncu_sk16.log 2>&1
+python tools/gpu_probe_sk16.py > $O/${T}_sk16_accuracy.txt 2>&1
+python tools/gpu_probe_loss.py > $O/${T}_loss_probe.txt 2>&1
 for f in $O/${T}_bench_n1.json $O/${T}_bench_car-512.json $O/${T}_bench_pidray-256-labelmap.json $O/${T}_bench_kmeans-assign.json; do python tools/show_bench.py $f x | head -3; done
 ls -la $O | tail -30
