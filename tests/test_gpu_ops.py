@@ -967,6 +967,35 @@ def test_pixel_segments_vs_torch(L, b, hw, patches, n):
     assert torch.equal(order.cpu().long()[:valid.numel()], ref_order)
 
 
+@pytest.mark.parametrize("c", [512, 64, 520, 20])
+@pytest.mark.parametrize("bf16_rows", [False, True])
+def test_segment_sum_rows_is_the_sequential_sum(L, c, bf16_rows):
+    """gx_segment_sum_rows: out[seg] = rows[order[r0]] + rows[order[r0 + 1]] + ... added in that order in fp32 (empty
+    segments give zeros; segments longer than a warp; c = 20 takes the 8-byte-load path of the bf16 rows).  Bit-exact
+    against a sequential fp32 sum; the bf16 planes are the split of that sum."""
+    g = torch.Generator().manual_seed(c + int(bf16_rows))
+    nrows, nseg = 3000, 400
+    rows = torch.randn(nrows, c, generator=g)
+    if bf16_rows:
+        rows = rows.bfloat16()
+    lens = torch.randint(0, 6, (nseg,), generator=g)
+    lens[7], lens[100] = 70, 33                                     # more rows than lanes
+    seg_off = torch.cat([torch.zeros(1, dtype=torch.long), lens.cumsum(0)]).int()
+    order = torch.randint(0, nrows, (int(seg_off[-1]),), generator=g).int()
+    ref = torch.zeros(nseg, c)
+    rf = rows.float()
+    for sgi in range(nseg):
+        acc = torch.zeros(c)
+        for r in range(int(seg_off[sgi]), int(seg_off[sgi + 1])):
+            acc = acc + rf[order[r]]
+        ref[sgi] = acc
+    hi, lo, f = L.segment_sum_rows(rows.cuda(), order.cuda(), seg_off.cuda(), nseg, want_lo=True, want_f32=True)
+    assert torch.equal(f.cpu(), ref)
+    torch.testing.assert_close((hi.float() + lo.float()).cpu(), ref, rtol=2e-5, atol=1e-6)
+    hi1, _, _ = L.segment_sum_rows(rows.cuda(), order.cuda(), seg_off.cuda(), nseg)
+    assert torch.equal(hi1, hi)
+
+
 def test_view_wplus_kernel_matches_host_construction(L):
     """gx_view_wplus (both views, one launch) == engine.view_wplus (reference op order, ref swav_clustering.py:593-640)"""
     from ganecdotes_b200.hfc_with_swav import engine as E
