@@ -994,20 +994,20 @@ sinkhorn_pass16_kernel(const __half* __restrict__ e16, long long n, int k, long 
     float t[R];
 #pragma unroll
     for (int rr = 0; rr < R; ++rr) {
-      t[rr] = 0.f;
-      if (rr < valid) {   // warp-uniform
-        float2 ta = make_float2(0.f, 0.f), tb = make_float2(0.f, 0.f);
-        const uint8_t* sr = srow + (size_t)rr * row_bytes;
+      // unconditional: the rows of a ragged last group beyond `valid` hold whatever the stage held before - their
+      // totals are never used and their terms are skipped below (no branch here, so the rows' loads and conversions
+      // interleave)
+      float2 ta = make_float2(0.f, 0.f), tb = make_float2(0.f, 0.f);
+      const uint8_t* sr = srow + (size_t)rr * row_bytes;
 #pragma unroll
-        for (int j = 0; j < J; ++j) {
-          const uint2 w = *reinterpret_cast<const uint2*>(j < J - 1 ? sr + coff0 + j * (GT * 8) : sr + coff_last);
-          p[rr][j][0] = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
-          p[rr][j][1] = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
-          ta = fma2(p[rr][j][0], rho[j][0], ta);
-          tb = fma2(p[rr][j][1], rho[j][1], tb);
-        }
-        t[rr] = (ta.x + tb.x) + (ta.y + tb.y);
+      for (int j = 0; j < J; ++j) {
+        const uint2 w = *reinterpret_cast<const uint2*>(j < J - 1 ? sr + coff0 + j * (GT * 8) : sr + coff_last);
+        p[rr][j][0] = __half22float2(*reinterpret_cast<const __half2*>(&w.x));
+        p[rr][j][1] = __half22float2(*reinterpret_cast<const __half2*>(&w.y));
+        ta = fma2(p[rr][j][0], rho[j][0], ta);
+        tb = fma2(p[rr][j][1], rho[j][1], tb);
       }
+      t[rr] = (ta.x + tb.x) + (ta.y + tb.y);
     }
     if (R == 2) {
       // both rows in one butterfly: after the first exchange lanes 0-15 carry row 0 and lanes 16-31 row 1
