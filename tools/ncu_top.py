@@ -1,11 +1,12 @@
 """The dominant kernels of the ffhq-256 step exactly as the engine launches them (B = 8 latents: N = 160000 rows,
-C = 512, K = 5000), two rounds of six launches matching `sinkhorn_pass_kernel|swav_loss|gx_umma_kernel`:
+C = 512, K = 5000), two rounds of six launches matching `sinkhorn_pass|swav_loss|gx_umma_kernel`:
   gemm_prototype_fwd   bf16x3 split, CTA pairs, fused bias + first Sinkhorn marginal       S = Zn Wk^T + b
-  sinkhorn_pass        reverse sweep (right after the GEMM wrote S), then a forward sweep   (serpentine passes)
+  sinkhorn_pass        iteration 1: fp32 scores in, 16-bit cache out (reverse sweep, right after the GEMM wrote S);
+                       iteration 2: the pass over the cache (forward sweep)                 (serpentine passes)
   swav_loss_fwd_bwd    power-ratio kernel (T / eps = 2)
   gemm_dzn_bwd         bf16x1, 256 x 512 CTA-pair tiles                                     dZn = dS Wk
   gemm_gproto_bwd      bf16x1, 256 x 512 CTA-pair tiles, MN-major operands, split-K         gWk += dS^T Zn
-Capture the second round:  ncu --set full -k regex:'sinkhorn_pass_kernel|swav_loss|gx_umma_kernel' -s 6 -c 6"""
+Capture the second round:  ncu --set full -k regex:'sinkhorn_pass|swav_loss|gx_umma_kernel' -s 6 -c 6"""
 import os
 import sys
 
@@ -33,9 +34,10 @@ def main():
         zn_hi, zn_lo, inv, za = E._normalise(head, z)
         s, u0 = E._proto_scores(head, za, zn_lo, n, eps)                                   # gx_umma (1)
         u = torch.empty(k, device=dev)
-        np_ = L.sinkhorn_pass_parts(s, 1.0 / eps, False, u0, None, None, n, ws, reverse=True)    # pass (2)
+        cache = ws.cache16(0, n)
+        np_ = L.sinkhorn_pass_cached_parts(s, 1.0 / eps, u0, None, None, n, ws, cache, True, reverse=True)   # pass (2)
         L.sinkhorn_reduce(ws.partials, np_, k, u)
-        np_ = L.sinkhorn_pass_parts(s, 1.0 / eps, False, u, None, None, n, ws, reverse=False)    # pass (3)
+        np_ = L.sinkhorn_pass_cached_parts(s, 1.0 / eps, u, None, None, n, ws, cache, False, reverse=False)  # pass (3)
         L.sinkhorn_reduce(ws.partials, np_, k, u)
         la = L.sinkhorn_log_a(u, None)
         _, ds_s, ds_t, _, _ = L.swav_loss(s, s_t, 1.0 / eps, 1.0 / temp, la, la, 1e-6)      # loss (4)
