@@ -729,7 +729,10 @@ def swav_train_step_device(gen, head: SwavHead, mean_latent, inp: StepInputs, cf
     L.normalize_rows_(head.w_proto)
     head.refresh_planes()
     head.zero_grad()
-    ws = ws or L.SinkhornWorkspace(head.k, dev)
+    if ws is None:      # kept on the head: the workspace owns the 16-bit Sinkhorn cache (2 x N x K x 2 bytes), not
+        ws = getattr(head, "_sk_ws", None)   # something to allocate per step
+        if ws is None or ws.k != head.k or ws.partials.device != dev:
+            ws = head._sk_ws = L.SinkhornWorkspace(head.k, dev)
     # one pass of the mapping network over the latents and both views' perturbation draws
     styled = gen.style(inp.zcat)
     feats = {}
