@@ -376,7 +376,10 @@ int gx_sinkhorn_pass(const float* s, long long n, int k, long long lds, float in
  * rho_k = a_k / a1_k the row totals are t'_n = sum_k e16_nk rho_k and u_k = (1/a1_k) sum_n e16_nk c_n / t'_n (the row
  * factor stored in e16 cancels).  The marginals differ from the fp32 pass by the rounding of e16 (2^-11 per term,
  * averaged over a column: <~ 3e-4 in the final codes); the codes themselves are always computed from
- * the fp32 scores (gx_swav_loss / gx_sinkhorn_q).  lde % 8 == 0 (16-byte rows), e16 and la1 16-byte aligned. */
+ * the fp32 scores (gx_swav_loss / gx_sinkhorn_q).  lde % 8 == 0 (16-byte rows), e16 and la1 16-byte aligned.
+ * Meant for uniform (or mildly non-uniform) prototype marginals r: a column whose target mass is below ~1e-8 of the
+ * typical one falls under the fp16 range of the row-normalised plane - the host layer uses the fp32 pass for
+ * source_pdf == 'image', where an empty histogram bin has a mass of 1e-9 counts. */
 int gx_sinkhorn_pass_cached(const float* s, long long n, int k, long long lds, float inv_eps, const float* u_in,
                             const gx_ll_desc* u_ll, const float* r, const float* c, long long n_total, int reverse,
                             float* partials, int* nparts_out, void* e16, long long lde, float* la1, int write_cache,
