@@ -558,7 +558,7 @@ def run_swav(args, cfg):
                        "note": "backward GEMMs on 3-plane split-bf16 operands: gradients within 3e-3 of fp32 "
                                "instead of 2e-2 (default bf16x1)"}
             del h3
-        # the Sinkhorn passes 2.. on the fp32 scores instead of the 16-bit cache (the round-1 path)
+        # the Sinkhorn passes 3.. on the fp32 scores instead of the 16-bit cache (the round-1 path)
         cache_was = scfg.sinkhorn_cache16
         scfg.sinkhorn_cache16 = False
         timed_steps(head, 0, min(2, nsteps))
@@ -655,7 +655,7 @@ def run_swav(args, cfg):
             "dtype": f"bf16x{args.passes_fwd}-split fwd" + (" (score GEMM fp16x1 on unit-norm operands)" if args.proto_f16 else "") +
                      f" / bf16x{args.passes_bwd} bwd operands, fp32 accumulate + fp32 everywhere else" +
                      ("" if scfg.sinkhorn_cache16 is False or os.environ.get("GX_SINKHORN_CACHE16", "1") == "0" else
-                      " (Sinkhorn iterations 2.. stream an fp16 cache of the row-normalised kernel matrix)"),
+                      " (Sinkhorn iterations 3.. stream an fp16 cache of the row-normalised kernel matrix)"),
             "data": "synthetic",
             "config": swav_config(cfg, b, world, None if world == 1 else ("ll-nvlink" if group.ll is not None else "nccl")),
             "roofline": roofline, "roofline_stages": stage_rows, "cpu_baseline": cpu_base,

@@ -324,6 +324,14 @@ def sinkhorn_log_a(s, niters, eps, ws, n_total, group=None, r=None, c=None, pass
     return log_a_fn(u, r)
 
 
+# The iteration whose pass writes the 16-bit cache.  Not the first row-normalising one (1): the column scalings still move
+# by four to five orders of magnitude after it (rho = a / a1 up to 1e5 at eps = 0.005), which lifts terms that underflowed
+# the row-normalised fp16 plane back into play - with sharp score rows (a trained head: one prototype 30-50 nats above
+# the rest) that costs up to 9e-3 in the codes.  Written one iteration later the plane keeps every case tried within
+# 7e-4 (tests/test_oracle_golden.py::test_sinkhorn_cached16_write_iteration), for one more fp32 pass per call.
+CACHE16_WRITE_IT = 2
+
+
 def sinkhorn_multi(problems, niters, eps, ws, n_total, group=None, cache16=False):
     """Sinkhorn-Knopp (ref :509-544) on several independent score matrices (the s and t views of a patch):
     `problems` = [dict(s=S [n,K], r=, c=, u_first=)], returns [log a] per problem.
@@ -335,8 +343,8 @@ def sinkhorn_multi(problems, niters, eps, ws, n_total, group=None, cache16=False
     chain A picks the peers' values up in its prologue - no collective call, no exposed latency, and a whole
     pass of slack against rank-to-rank jitter.  Without an exchange object the fallback is an NCCL all-reduce.
 
-    `cache16`: the first row-normalising pass (iteration 1) also stores its terms as a 16-bit plane and the later
-    passes stream that plane instead of S (`gx_sinkhorn_pass_cached`: half the bytes per pass, no exponentials).
+    `cache16`: the pass of iteration CACHE16_WRITE_IT (2) also stores its row-normalised terms as a 16-bit plane and
+    the later passes stream that plane instead of S (`gx_sinkhorn_pass_cached`: half the bytes per pass, no exponentials).
     Only the column scalings log a come out of these passes - the codes are always evaluated from the fp32 scores -
     and they move by <~ 5e-4 relative (the training step's default; the API calls keep the fp32 passes).  Problems with
     non-uniform marginals (`r` / `c` given: source_pdf == 'image') always take the fp32 passes."""
@@ -356,11 +364,12 @@ def sinkhorn_multi(problems, niters, eps, ws, n_total, group=None, cache16=False
             u_ll = ll.last(ch) if (ll is not None and it > 0) else None
             # (uniform marginals only: with source_pdf == 'image' an empty histogram bin gives a prototype a target
             #  mass of 1e-9 counts against ~10 - its column of the row-normalised plane is below the fp16 range)
-            if cache16 and it >= 1 and niters > 2 and pb.get("r") is None and pb.get("c") is None:
+            if cache16 and it >= CACHE16_WRITE_IT and niters > CACHE16_WRITE_IT + 1 and pb.get("r") is None and \
+                    pb.get("c") is None:
                 nparts = L.sinkhorn_pass_cached_parts(pb["s"], inv_eps, None if u_ll is not None else us[ch],
                                                       pb.get("r"), pb.get("c"), n_total, ws,
-                                                      ws.cache16(ch, pb["s"].shape[0]), it == 1, u_ll=u_ll,
-                                                      reverse=(it & 1) == 1)
+                                                      ws.cache16(ch, pb["s"].shape[0]), it == CACHE16_WRITE_IT,
+                                                      u_ll=u_ll, reverse=(it & 1) == 1)
             else:
                 nparts = L.sinkhorn_pass_parts(pb["s"], inv_eps, it == 0, None if u_ll is not None else us[ch],
                                                pb.get("r"), pb.get("c"), n_total, ws, u_ll=u_ll,
@@ -607,7 +616,7 @@ class StepConfig:
     source_pdf: str = 'uniform'
     dedup: Optional[bool] = None   # project every pixel once (None: automatic, when P*N > H*W)
     hf_interp: str = 'nearest'     # 'nearest' | 'bilinear' (ref :112-126); bilinear needs the all-pixel path
-    sinkhorn_cache16: Optional[bool] = None   # Sinkhorn passes 2.. stream a 16-bit cache of the scaled kernel matrix
+    sinkhorn_cache16: Optional[bool] = None   # Sinkhorn passes 3.. stream a 16-bit cache of the scaled kernel matrix
     #                                           (sinkhorn_multi); None: on, unless GX_SINKHORN_CACHE16=0
 
 

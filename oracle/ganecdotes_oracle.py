@@ -447,34 +447,35 @@ def sinkhorn_knopp(scores, niters: int, eps: float, r=None, c=None):
     return (q / torch.sum(q, dim=0, keepdim=True)).t()
 
 
-def sinkhorn_log_a_cached16(scores, niters: int, eps: float, r=None, c=None):
-    """What the CUDA path computes when the Sinkhorn iterations 2.. run on the 16-bit cache
+def sinkhorn_log_a_cached16(scores, niters: int, eps: float, r=None, c=None, write_iter: int = 2):
+    """What the CUDA path computes when the later Sinkhorn iterations run on the 16-bit cache
     (`gx_sinkhorn_pass_cached`) - a restatement of THIS repo's scheme on top of the reference's
     iteration (swav_clustering.py:509-544), so that the kernels can be checked against it to rounding while the
     distance to `sinkhorn_knopp` (the reference) is what the cache costs.  Scaling-vector form: with E = exp(S/eps),
-    iteration i computes u_k = sum_n E_nk b_n, a_k = r_k / u_k, b_n = c_n / sum_k a_k E_nk.  Iteration 1 stores
-    e16_nk = half(2^15 a1_k E_nk / t_n), t_n = sum_k a1_k E_nk; later iterations use rho_k = a_k / a1_k,
-    t'_n = sum_k e16_nk rho_k, u_k = (1/a1_k) sum_n e16_nk c_n / t'_n.  Returns log a [K] (float64);
+    iteration i computes u_k = sum_n E_nk b_n, a_k = r_k / u_k, b_n = c_n / sum_k a_k E_nk.  Iteration `write_iter`
+    (engine.CACHE16_WRITE_IT) stores e16_nk = half(2^15 aw_k E_nk / t_n), t_n = sum_k aw_k E_nk; later iterations use
+    rho_k = a_k / aw_k, t'_n = sum_k e16_nk rho_k, u_k = (1/aw_k) sum_n e16_nk c_n / t'_n.  Returns log a [K] (float64);
     the codes are softmax_k(S/eps + log a)."""
     e = torch.exp(scores.double() / eps)
     n, k = e.shape
     r = torch.full((k,), 1.0 / k, dtype=torch.float64) if r is None else r.double()
     c = torch.full((n,), 1.0 / n, dtype=torch.float64) if c is None else c.double()
     u = e.sum(0)                                            # iteration 0 (the score GEMM's epilogue on the GPU)
-    if niters <= 2:
-        for _ in range(1, niters):
-            a = r / u
-            u = (e * (c / (e @ a)).unsqueeze(1)).sum(0)
+    cached = niters > write_iter + 1
+    for _ in range(1, niters if not cached else write_iter):
+        a = r / u
+        u = (e * (c / (e @ a)).unsqueeze(1)).sum(0)
+    if not cached:
         return torch.log(r / u)
-    a1 = r / u
-    p = e * a1.unsqueeze(0)
+    aw = r / u
+    p = e * aw.unsqueeze(0)
     t = p.sum(1)
     e16 = (32768.0 * p / t.unsqueeze(1)).to(torch.float16).double()
-    u = (p * (c / t).unsqueeze(1)).sum(0) / a1              # iteration 1, exact terms
-    for _ in range(2, niters):
-        rho = (r / u) / a1
+    u = (p * (c / t).unsqueeze(1)).sum(0) / aw              # iteration write_iter, exact terms
+    for _ in range(write_iter + 1, niters):
+        rho = (r / u) / aw
         tp = e16 @ rho
-        u = (e16 * (c / tp).unsqueeze(1)).sum(0) / a1
+        u = (e16 * (c / tp).unsqueeze(1)).sum(0) / aw
     return torch.log(r / u)
 
 

@@ -591,8 +591,8 @@ def test_sinkhorn_vs_oracle(L, n, k):
 @pytest.mark.parametrize("n,k,std", [(40, 24, 0.05), (333, 48, 0.05), (1000, 5000, 0.05), (257, 4000, 0.02),
                                      (301, 8000, 0.05), (77, 6144, 0.05), (513, 1500, 0.05), (64, 520, 0.05)])
 def test_sinkhorn_cached_passes_vs_oracle(L, n, k, std):
-    """gx_sinkhorn_pass_cached: iteration 1 stores its row-normalised terms as a 16-bit plane (row pitch rounded up to
-    8 columns: k = 1500 -> 1504), iterations 2.. stream that plane instead of S.  Only log a comes out of the passes;
+    """gx_sinkhorn_pass_cached: iteration 2 (engine.CACHE16_WRITE_IT) stores its row-normalised terms as a 16-bit plane
+    (row pitch rounded up to 8 columns: k = 1500 -> 1504), iterations 3.. stream that plane instead of S.  Only log a comes out of the passes;
     the codes softmax_k(S/eps + log a) are evaluated from the fp32 scores and stay within the tolerance of the fp32
     passes (rtol 2e-3 against the fp64 oracle; the cache itself moves them by < 1e-3)."""
     from ganecdotes_b200.hfc_with_swav import engine as E
@@ -610,7 +610,7 @@ def test_sinkhorn_cached_passes_vs_oracle(L, n, k, std):
     # that term - which shows in the columns that a single row dominates: the median distance is fp32 rounding, 1-2 %
     # of the columns may differ by more than 1e-4; against the fp32 passes the median distance is ~1e-4)
     d = (la16.cpu() - O.sinkhorn_log_a_cached16(s.cpu(), 10, 0.005).float()).abs()
-    assert d.median().item() < 2e-5 and d.max().item() < 2e-3 and (d > 1e-4).float().mean().item() < 0.02, \
+    assert d.median().item() < 2e-5 and d.max().item() < 2e-3 and (d > 1e-4).sum().item() <= max(2, 0.02 * k), \
         (d.median().item(), d.max().item(), (d > 1e-4).sum().item())
     q = L.sinkhorn_q(s, 1 / 0.005, la16)
     torch.testing.assert_close(q.cpu(), ref, rtol=2e-3, atol=1e-9)
@@ -929,10 +929,11 @@ def test_sinkhorn_ll_exchange_simulated_ranks(L, world, n, k, cached):
                 descs = []
                 for r, e in enumerate(ends):                    # every endpoint sends ...
                     u_ll = e.last(ch) if it > 0 else None       # ... after receiving the previous exchange
-                    if cached and it >= 1:      # every (chain, shard) has its own 16-bit plane
+                    if cached and it >= E.CACHE16_WRITE_IT:      # every (chain, shard) has its own 16-bit plane
                         nparts = L.sinkhorn_pass_cached_parts(shards[r], inv_eps, None, None, None, n, ws,
-                                                              ws.cache16((ch, r), shards[r].shape[0]), it == 1,
-                                                              u_ll=u_ll, reverse=(it & 1) == 1)
+                                                              ws.cache16((ch, r), shards[r].shape[0]),
+                                                              it == E.CACHE16_WRITE_IT, u_ll=u_ll,
+                                                              reverse=(it & 1) == 1)
                     else:
                         nparts = L.sinkhorn_pass_parts(shards[r], inv_eps, it == 0, None, None, None, n, ws, u_ll=u_ll,
                                                        reverse=(it & 1) == 1)

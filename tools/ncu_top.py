@@ -1,8 +1,8 @@
 """The dominant kernels of the ffhq-256 step exactly as the engine launches them (B = 8 latents: N = 160000 rows,
 C = 512, K = 5000), two rounds of six launches matching `sinkhorn_pass|swav_loss|gx_umma_kernel`:
   gemm_prototype_fwd   bf16x3 split, CTA pairs, fused bias + first Sinkhorn marginal       S = Zn Wk^T + b
-  sinkhorn_pass        iteration 1: fp32 scores in, 16-bit cache out (reverse sweep, right after the GEMM wrote S);
-                       iteration 2: the pass over the cache (forward sweep)                 (serpentine passes)
+  sinkhorn_pass        the cache-writing iteration: fp32 scores in, 16-bit cache out (reverse sweep);
+                       a later iteration: the pass over the cache (forward sweep)                 (serpentine passes)
   swav_loss_fwd_bwd    power-ratio kernel (T / eps = 2)
   gemm_dzn_bwd         bf16x1, 256 x 512 CTA-pair tiles                                     dZn = dS Wk
   gemm_gproto_bwd      bf16x1, 256 x 512 CTA-pair tiles, MN-major operands, split-K         gWk += dS^T Zn
