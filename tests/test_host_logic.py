@@ -181,3 +181,50 @@ def test_blur_module_caches_and_refreshes_its_separable_factors():
     with torch.no_grad():
         blur.kernel.copy_(torch.eye(4))
     assert blur.separable() is None
+
+
+def test_sinkhorn_pass_schedule_with_the_16_bit_cache(monkeypatch):
+    """engine.sinkhorn_multi, host side only (the kernels are replaced by recorders): with cache16 the pass of iteration
+    CACHE16_WRITE_IT writes the plane, the later ones read it, the earlier ones and every pass of a problem with
+    non-uniform marginals stream the fp32 scores; the sweep direction alternates; iteration 0 is skipped when the
+    score GEMM's epilogue delivered the first marginals; short chains never touch the cache."""
+    calls = []
+
+    class WS:
+        partials = torch.zeros(4, 8)
+
+        def cache16(self, chain, n):
+            return ("e16", chain, n)
+
+    def plain(s, inv_eps, first, u_in, r, c, n_total, ws, u_ll=None, reverse=False):
+        calls.append(("fp32", bool(first), bool(reverse)))
+        return 1
+
+    def cached(s, inv_eps, u_in, r, c, n_total, ws, cache, write_cache, u_ll=None, reverse=False):
+        assert cache[0] == "e16" and cache[2] == s.shape[0]
+        calls.append(("write" if write_cache else "read", False, bool(reverse)))
+        return 1
+
+    monkeypatch.setattr(E.L, "sinkhorn_pass_parts", plain)
+    monkeypatch.setattr(E.L, "sinkhorn_pass_cached_parts", cached)
+    monkeypatch.setattr(E.L, "sinkhorn_reduce", lambda parts, nparts, k, out: out)
+    monkeypatch.setattr(E.L, "sinkhorn_log_a", lambda u, r, **kw: u)
+    s = torch.zeros(6, 8)
+    w = E.CACHE16_WRITE_IT
+    assert w == 2
+    E.sinkhorn_multi([dict(s=s, r=None, c=None, u_first=torch.ones(8))], 10, 0.005, WS(), 6, cache16=True)
+    assert [c[0] for c in calls] == ["fp32"] * (w - 1) + ["write"] + ["read"] * (10 - w - 1)
+    assert [c[2] for c in calls] == [(it & 1) == 1 for it in range(1, 10)]
+    assert not any(c[1] for c in calls)
+    calls.clear()
+    E.sinkhorn_multi([dict(s=s, r=None, c=None, u_first=None)], 10, 0.005, WS(), 6, cache16=True)
+    assert calls[0] == ("fp32", True, False) and [c[0] for c in calls[1:]] == ["fp32"] * (w - 1) + ["write"] + ["read"] * 7
+    calls.clear()
+    E.sinkhorn_multi([dict(s=s, r=torch.ones(8) / 8, c=torch.ones(6) / 6, u_first=None)], 10, 0.005, WS(), 6, cache16=True)
+    assert [c[0] for c in calls] == ["fp32"] * 10
+    calls.clear()
+    E.sinkhorn_multi([dict(s=s, r=None, c=None, u_first=None)], w + 1, 0.005, WS(), 6, cache16=True)
+    assert [c[0] for c in calls] == ["fp32"] * (w + 1)
+    calls.clear()
+    E.sinkhorn_multi([dict(s=s, r=None, c=None, u_first=None)], 10, 0.005, WS(), 6)
+    assert [c[0] for c in calls] == ["fp32"] * 10
