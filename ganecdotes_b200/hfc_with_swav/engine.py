@@ -327,7 +327,7 @@ def sinkhorn_log_a(s, niters, eps, ws, n_total, group=None, r=None, c=None, pass
 # The iteration whose pass writes the 16-bit cache.  Not the first row-normalising one (1): the column scalings still move
 # by four to five orders of magnitude after it (rho = a / a1 up to 1e5 at eps = 0.005), which lifts terms that underflowed
 # the row-normalised fp16 plane back into play - with sharp score rows (a trained head: one prototype 30-50 nats above
-# the rest) that costs up to 9e-3 in the codes.  Written one iteration later the plane keeps every case tried within
+# the rest) that costs up to 1.3e-2 in the codes.  Written one iteration later the plane keeps every case tried within
 # 7e-4 (CPU test `test_sinkhorn_cached16_write_iteration`), for one more fp32 pass per call.
 CACHE16_WRITE_IT = 2
 
